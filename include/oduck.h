@@ -1,0 +1,275 @@
+/*
+ * oduck.h -- C-ABI of the B200-native batched Open Duck Mini V2 joystick hot path.
+ *
+ * Drop-in boundary for the one data-parallel path of apirrone/Open_Duck_Playground
+ * (SURVEY.md section 8b).  The reference has no FFI of its own (it is pure Python
+ * on top of MJX/Brax), so every entry point cites the *Python* interface it
+ * replaces (paths relative to the reference repo, playground/...):
+ *
+ *   oduck_create            OpenDuckMiniV2Env.__init__ + mjx.put_model     open_duck_mini_v2/base.py:44-61
+ *                           Joystick._post_init                            open_duck_mini_v2/joystick.py:121-204
+ *   oduck_randomize         randomize.domain_randomize                     common/randomize.py:26-146
+ *   oduck_reset             Joystick.reset (+ wrapper first_state store)   open_duck_mini_v2/joystick.py:206-321
+ *   oduck_step              Joystick.step wrapped by wrap_for_brax_training open_duck_mini_v2/joystick.py:323-481, common/runner.py:117
+ *   oduck_physics_substeps  mjx_env.step(model, data, ctrl, n_substeps)    open_duck_mini_v2/joystick.py:420
+ *   oduck_forward           mjx_env.init's mjx.forward                     open_duck_mini_v2/joystick.py:258
+ *   oduck_policy_forward    Brax make_ppo_networks policy apply            common/runner.py:94-100, common/export_onnx.py:64-72
+ *   oduck_get_buffer        attribute access on mjx.Data / State / info    open_duck_mini_v2/joystick.py:278-321
+ *   oduck_set_state         state.data.replace(qpos=..., qvel=...)         open_duck_mini_v2/joystick.py:399
+ *
+ * Conventions: every call returns 0 on success or a negative OduckStatus; the
+ * message is available from oduck_last_error() (thread local).  The library
+ * owns all per-env state (device memory, one record per env);
+ * the caller owns action / key / weight / output pointers (device pointers for
+ * the CUDA library, host pointers for the CPU oracle).  `stream` is a
+ * cudaStream_t (ignored by the oracle).  Calls are asynchronous on that stream:
+ * no hidden synchronisation, no allocation after oduck_create.  A handle is not
+ * thread-safe; distinct handles are independent.  No torch types appear here.
+ *
+ * The same header is implemented twice:
+ *   open_duck_playground_b200/csrc/  -> liboduck_cuda.so  (the product, sm_100a)
+ *   oracle/                          -> liboduck_oracle.so (CPU fp64 checker; test infrastructure only)
+ */
+#ifndef ODUCK_H_
+#define ODUCK_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ODUCK_ABI_VERSION 3
+
+#define ODUCK_MAX_BODY 20
+#define ODUCK_MAX_JNT 28
+#define ODUCK_MAX_NQ 36
+#define ODUCK_MAX_NV 32
+#define ODUCK_MAX_NU 16
+#define ODUCK_MAX_SITE 8
+#define ODUCK_MAX_VERT 32      /* convex-hull vertices per foot */
+#define ODUCK_MAX_FACE 64      /* convex-hull faces per foot (triangles) */
+#define ODUCK_NFEET 2
+#define ODUCK_CON_PER_PAIR 4   /* MJX emits 4 manifold points per geom pair */
+#define ODUCK_MAX_CON 12       /* 2 x plane/hfield-foot + 1 x foot-foot */
+#define ODUCK_REF_DIM 40       /* reference-motion frame width */
+#define ODUCK_POLY_DEG 16      /* coefficients per polynomial */
+#define ODUCK_OBS_STATE 101
+#define ODUCK_OBS_PRIV 212
+#define ODUCK_NMETRIC 8
+#define ODUCK_NCMD 7
+
+typedef enum {
+  ODUCK_OK = 0,
+  ODUCK_ERR_ARG = -1,
+  ODUCK_ERR_CUDA = -2,
+  ODUCK_ERR_MODEL = -3,
+  ODUCK_ERR_ALLOC = -4,
+  ODUCK_ERR_UNSUPPORTED = -5
+} OduckStatus;
+
+/* Joint types use MuJoCo's enum values (base.py:99 relies on free == 0, hinge == 3). */
+#define ODUCK_JNT_FREE 0
+#define ODUCK_JNT_HINGE 3
+
+/* Compiled model: the subset of mjModel the path reads.  Filled
+ * by open_duck_playground_b200/mjcf.py; all reals are double, the CUDA library
+ * narrows to float at create time. */
+typedef struct OduckModel {
+  int32_t abi_version;
+  int32_t nbody, njnt, nq, nv, nu, nsite;
+  /* bodies (depth-first ids, world = 0) */
+  int32_t body_parentid[ODUCK_MAX_BODY];
+  int32_t body_jntadr[ODUCK_MAX_BODY];
+  int32_t body_jntnum[ODUCK_MAX_BODY];
+  int32_t body_dofadr[ODUCK_MAX_BODY];
+  int32_t body_dofnum[ODUCK_MAX_BODY];
+  double body_pos[ODUCK_MAX_BODY][3];
+  double body_quat[ODUCK_MAX_BODY][4];
+  double body_ipos[ODUCK_MAX_BODY][3];
+  double body_iquat[ODUCK_MAX_BODY][4];
+  double body_mass[ODUCK_MAX_BODY];
+  double body_inertia[ODUCK_MAX_BODY][3];
+  double body_invweight0[ODUCK_MAX_BODY][2];
+  /* joints */
+  int32_t jnt_type[ODUCK_MAX_JNT];
+  int32_t jnt_qposadr[ODUCK_MAX_JNT];
+  int32_t jnt_dofadr[ODUCK_MAX_JNT];
+  int32_t jnt_bodyid[ODUCK_MAX_JNT];
+  int32_t jnt_limited[ODUCK_MAX_JNT];
+  double jnt_pos[ODUCK_MAX_JNT][3];
+  double jnt_axis[ODUCK_MAX_JNT][3];
+  double jnt_range[ODUCK_MAX_JNT][2];
+  double qpos0[ODUCK_MAX_NQ];
+  /* dofs */
+  int32_t dof_bodyid[ODUCK_MAX_NV];
+  int32_t dof_jntid[ODUCK_MAX_NV];
+  int32_t dof_parentid[ODUCK_MAX_NV];
+  double dof_armature[ODUCK_MAX_NV];
+  double dof_damping[ODUCK_MAX_NV];
+  double dof_frictionloss[ODUCK_MAX_NV];
+  double dof_invweight0[ODUCK_MAX_NV];
+  /* position actuators: force = kp*ctrl - kp*q - kv*qd, clipped */
+  int32_t act_jntid[ODUCK_MAX_NU];
+  double act_kp[ODUCK_MAX_NU];
+  double act_kv[ODUCK_MAX_NU];
+  double act_ctrlrange[ODUCK_MAX_NU][2];
+  double act_forcerange[ODUCK_MAX_NU][2];
+  /* sites */
+  int32_t site_bodyid[ODUCK_MAX_SITE];
+  double site_pos[ODUCK_MAX_SITE][3];
+  double site_quat[ODUCK_MAX_SITE][4];
+  int32_t imu_site;
+  int32_t foot_site[ODUCK_NFEET];
+  /* collision: floor (plane z=0 of the world, or height field) vs two convex feet */
+  int32_t floor_is_hfield;
+  double floor_friction;          /* wins by priority=1 for foot-floor pairs */
+  int32_t foot_body[ODUCK_NFEET];
+  int32_t foot_nvert;
+  double foot_vert[ODUCK_NFEET][ODUCK_MAX_VERT][3]; /* hull vertices, BODY frame */
+  int32_t foot_nface;
+  int32_t foot_face[ODUCK_MAX_FACE][3];             /* hull triangles (shared topology) */
+  double foot_friction;           /* foot-foot pair: max of the two geoms */
+  int32_t enable_foot_foot;       /* 1 = instantiate the convex-convex pair */
+  /* options */
+  double timestep;
+  double gravity[3];
+  double tolerance, ls_tolerance, impratio, meaninertia;
+  int32_t iterations, ls_iterations;
+  double solref[2];
+  double solimp[5];
+  /* keyframe "home" */
+  double key_qpos[ODUCK_MAX_NQ];
+  double key_ctrl[ODUCK_MAX_NU];
+} OduckModel;
+
+/* Environment constants: Joystick.default_config() (joystick.py:49-102) plus the
+ * tables _post_init derives (joystick.py:121-204). */
+typedef struct OduckEnvConfig {
+  int32_t n_substeps;            /* ctrl_dt / sim_dt = 10 */
+  int32_t episode_length;        /* 1000 (EpisodeWrapper) */
+  int32_t use_imitation_reward;  /* joystick.py:45 */
+  int32_t use_motor_speed_limits;/* joystick.py:46 */
+  int32_t push_enable;
+  int32_t action_min_delay, action_max_delay;
+  int32_t imu_min_delay, imu_max_delay;
+  int32_t auto_reset;            /* 1 = BraxAutoResetWrapper semantics fused into oduck_step */
+  double ctrl_dt;
+  double action_scale;
+  double dof_vel_scale;
+  double max_motor_velocity;
+  double noise_level;
+  double noise_gyro, noise_accelerometer, noise_gravity, noise_joint_vel;
+  double qpos_noise_scale[ODUCK_MAX_NU];   /* joystick.py:184-200, quirk #3 of SURVEY 2.1 */
+  double scale_tracking_lin_vel, scale_tracking_ang_vel, scale_torques, scale_action_rate;
+  double scale_stand_still, scale_alive, scale_imitation;
+  double tracking_sigma;
+  double push_interval_range[2];
+  double push_magnitude_range[2];
+  double cmd_range[ODUCK_NCMD][2];         /* lin_vel_x, lin_vel_y, ang_vel_yaw, neck_pitch, head_pitch, head_yaw, head_roll */
+  /* reference motion table (poly_reference_motion.py:74-146): float64 host array
+   * [ndx][ndy][ndth][40][16], highest power first (jp.polyval order) */
+  int32_t ndx, ndy, ndth, nb_steps_in_period;
+  double dxs[8], dys[8], dthetas[16];
+  double dx_range[2], dy_range[2], dtheta_range[2];  /* ranges include 0 (poly_reference_motion.py:59-61,105-110) */
+  const double* poly_coef;
+} OduckEnvConfig;
+
+typedef struct OduckHandle OduckHandle;
+
+/* Policy weights for oduck_policy_forward (Brax MLP, swish, NormalTanh head).
+ * Row-major W_l[in][out] like flax Dense kernels; pointers follow the library's
+ * memory space (device for CUDA). */
+typedef struct OduckPolicyWeights {
+  int32_t obs_dim;               /* 101 */
+  int32_t hidden[3];             /* 512, 256, 128 */
+  int32_t out_dim;               /* 2 * nu = 28 */
+  const float* obs_mean;         /* [obs_dim] running-statistics normaliser */
+  const float* obs_std;          /* [obs_dim] */
+  const float* w[4];
+  const float* b[4];
+} OduckPolicyWeights;
+
+typedef enum {
+  ODUCK_BUF_QPOS = 0,        /* f32 [N, nq]  */
+  ODUCK_BUF_QVEL,            /* f32 [N, nv]  */
+  ODUCK_BUF_QACC_WARM,       /* f32 [N, nv]  */
+  ODUCK_BUF_QACC,            /* f32 [N, nv]  last solver output */
+  ODUCK_BUF_CTRL,            /* f32 [N, nu]  motor targets applied */
+  ODUCK_BUF_OBS_STATE,       /* f32 [N, 101] */
+  ODUCK_BUF_OBS_PRIV,        /* f32 [N, 212] */
+  ODUCK_BUF_REWARD,          /* f32 [N]      */
+  ODUCK_BUF_DONE,            /* f32 [N]      */
+  ODUCK_BUF_TRUNCATION,      /* f32 [N]      */
+  ODUCK_BUF_METRICS,         /* f32 [N, 8]: reward/tracking_lin_vel, reward/tracking_ang_vel, cost/torques, cost/action_rate, cost/stand_still, reward/alive, reward/imitation, swing_peak */
+  ODUCK_BUF_EFC_FORCE,       /* f32 [N, nefc] rows: friction dofs, joint limits, contacts x4 */
+  ODUCK_BUF_CONTACT_DIST,    /* f32 [N, 12]  */
+  ODUCK_BUF_SENSORDATA,      /* f32 [N, 24]: gyro3 local_linvel3 accelerometer3 upvector3 global_angvel3 left_foot_linvel3 right_foot_linvel3 pad3 */
+  ODUCK_BUF_ACTUATOR_FORCE,  /* f32 [N, nu]  */
+  ODUCK_BUF_SITE_XPOS_FEET,  /* f32 [N, 6]   */
+  ODUCK_BUF_INFO_RNG,        /* u32 [N, 2]   */
+  ODUCK_BUF_INFO_COMMAND,    /* f32 [N, 7]   */
+  ODUCK_BUF_INFO_STEP,       /* i32 [N]      */
+  ODUCK_BUF_INFO_STEPS,      /* i32 [N]  EpisodeWrapper counter */
+  ODUCK_BUF_INFO_LAST_ACT,   /* f32 [N, 3, nu] last, last_last, last_last_last */
+  ODUCK_BUF_INFO_MOTOR_TARGETS, /* f32 [N, nu] */
+  ODUCK_BUF_INFO_FEET_AIR_TIME, /* f32 [N, 2] */
+  ODUCK_BUF_INFO_LAST_CONTACT,  /* f32 [N, 2] (0/1) */
+  ODUCK_BUF_INFO_SWING_PEAK,    /* f32 [N, 2] */
+  ODUCK_BUF_INFO_PUSH,          /* f32 [N, 2] */
+  ODUCK_BUF_INFO_PUSH_STEP,     /* i32 [N] */
+  ODUCK_BUF_INFO_PUSH_INTERVAL, /* i32 [N] */
+  ODUCK_BUF_INFO_ACTION_HISTORY,/* f32 [N, action_max_delay*nu] */
+  ODUCK_BUF_INFO_IMU_HISTORY,   /* f32 [N, imu_max_delay*3] */
+  ODUCK_BUF_INFO_IMITATION_I,   /* i32 [N] */
+  ODUCK_BUF_INFO_REF_MOTION,    /* f32 [N, 40] */
+  ODUCK_BUF_INFO_IMITATION_PHASE, /* f32 [N, 2] */
+  ODUCK_BUF_DR_PARAMS,          /* f32 [N, dr_stride] per-env randomised model */
+  ODUCK_BUF_FIRST_QPOS,         /* f32 [N, nq] auto-reset target */
+  ODUCK_BUF_FIRST_QVEL,         /* f32 [N, nv] */
+  ODUCK_BUF_FIRST_OBS_STATE,    /* f32 [N, 101] */
+  ODUCK_BUF_FIRST_OBS_PRIV,     /* f32 [N, 212] */
+  ODUCK_BUF_COUNT
+} OduckBufferId;
+
+#define ODUCK_DTYPE_F32 0
+#define ODUCK_DTYPE_I32 1
+#define ODUCK_DTYPE_U32 2
+#define ODUCK_DTYPE_F64 3   /* the oracle's buffers */
+
+int oduck_abi_version(void);
+int oduck_sizeof_model(void);
+int oduck_sizeof_env_config(void);
+
+/* device = CUDA ordinal (ignored by the oracle). */
+int oduck_create(const OduckModel* model, const OduckEnvConfig* cfg, int num_envs, int device, OduckHandle** out);
+int oduck_destroy(OduckHandle* h);
+int oduck_num_envs(const OduckHandle* h);
+
+/* keys: u32 [N,2] threefry keys (jax.random key data). */
+int oduck_randomize(OduckHandle* h, const uint32_t* keys, void* stream);
+/* mask: optional u8 [N]; only envs with mask != 0 are reset (NULL = all).  Stores first_state/first_obs. */
+int oduck_reset(OduckHandle* h, const uint32_t* keys, const uint8_t* mask, void* stream);
+/* action: f32 [N, nu].  Fuses Joystick.step + EpisodeWrapper + AutoReset (cfg.auto_reset). */
+int oduck_step(OduckHandle* h, const float* action, void* stream);
+/* ctrl: f32 [N, nu] (NULL = keep the stored ctrl); n forward+Euler substeps. */
+int oduck_physics_substeps(OduckHandle* h, const float* ctrl, int n, void* stream);
+/* One mjx.forward on the stored qpos/qvel/ctrl (no integration); refreshes sensordata/efc_force/contact. */
+int oduck_forward(OduckHandle* h, void* stream);
+/* qpos [N,nq], qvel [N,nv], qacc_warm [N,nv]; f32, any may be NULL. */
+int oduck_set_state(OduckHandle* h, const float* qpos, const float* qvel, const float* qacc_warm, void* stream);
+/* obs NULL = the handle's own OBS_STATE buffer.  keys u32 [N,2] (ignored if deterministic).
+ * Outputs f32: action [N,nu] (tanh-squashed), raw_action [N,nu] (pre-tanh), log_prob [N]; any may be NULL. */
+int oduck_policy_forward(OduckHandle* h, const OduckPolicyWeights* w, const float* obs, const uint32_t* keys,
+                         int deterministic, float* action, float* raw_action, float* log_prob, void* stream);
+/* Zero-copy view.  shape[4] (unused dims = 0), strides in ELEMENTS. */
+int oduck_get_buffer(OduckHandle* h, int id, void** ptr, int64_t* shape, int64_t* strides, int* dtype);
+/* Number of kernels this library has launched on the handle since create (bench `gpu_launches`). */
+int64_t oduck_launch_count(const OduckHandle* h);
+
+const char* oduck_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ODUCK_H_ */

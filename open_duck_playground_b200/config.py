@@ -1,0 +1,171 @@
+"""Environment configuration: ``default_config()`` of the reference Joystick task.
+
+Mirrors reference open_duck_mini_v2/joystick.py:49-102 (values) and the tables ``_post_init`` derives
+(joystick.py:121-204).  ``ml_collections`` is not available in this image, so :class:`ConfigDict` is a
+minimal attribute dictionary with the same access pattern (``cfg.noise_config.scales.gyro``) and
+``config_overrides`` support (``{"noise_config.level": 0.0}``).
+"""
+from __future__ import annotations
+
+import copy
+import ctypes as C
+from typing import Any, Dict, Optional
+
+import numpy as np
+
+from . import capi
+from .mjcf import CompiledModel
+from .poly_reference_motion import PolyTable
+
+# module-level switches of the reference (joystick.py:45-46)
+USE_IMITATION_REWARD = True
+USE_MOTOR_SPEED_LIMITS = True
+
+JOINTS_ORDER_NO_HEAD = [  # reference constants.py:65-76
+    "left_hip_yaw", "left_hip_roll", "left_hip_pitch", "left_knee", "left_ankle",
+    "right_hip_yaw", "right_hip_roll", "right_hip_pitch", "right_knee", "right_ankle",
+]
+
+
+class ConfigDict(dict):
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+    def __deepcopy__(self, memo):
+        return ConfigDict({k: copy.deepcopy(v, memo) for k, v in self.items()})
+
+    def update_from_flattened_dict(self, overrides: Dict[str, Any]) -> None:
+        for key, val in overrides.items():
+            node = self
+            parts = key.split(".")
+            for p in parts[:-1]:
+                node = node[p]
+            if parts[-1] not in node:
+                raise KeyError(key)
+            node[parts[-1]] = val
+
+
+def _cd(**kw):
+    return ConfigDict(kw)
+
+
+def default_config() -> ConfigDict:
+    return _cd(
+        ctrl_dt=0.02,
+        sim_dt=0.002,
+        episode_length=1000,
+        action_repeat=1,
+        action_scale=0.25,
+        dof_vel_scale=0.05,
+        history_len=0,
+        soft_joint_pos_limit_factor=0.95,
+        max_motor_velocity=5.24,
+        noise_config=_cd(
+            level=1.0,
+            action_min_delay=0,
+            action_max_delay=3,
+            imu_min_delay=0,
+            imu_max_delay=3,
+            scales=_cd(hip_pos=0.03, knee_pos=0.05, ankle_pos=0.08, joint_vel=2.5, gravity=0.1, linvel=0.1, gyro=0.1,
+                       accelerometer=0.05),
+        ),
+        reward_config=_cd(
+            scales=_cd(tracking_lin_vel=2.5, tracking_ang_vel=6.0, torques=-1.0e-3, action_rate=-0.5, stand_still=-0.2,
+                       alive=20.0, imitation=1.0),
+            tracking_sigma=0.01,
+        ),
+        push_config=_cd(enable=True, interval_range=[5.0, 10.0], magnitude_range=[0.1, 1.0]),
+        lin_vel_x=[-0.15, 0.15],
+        lin_vel_y=[-0.2, 0.2],
+        ang_vel_yaw=[-1.0, 1.0],
+        neck_pitch_range=[-0.34, 1.1],
+        head_pitch_range=[-0.78, 0.78],
+        head_yaw_range=[-1.5, 1.5],
+        head_roll_range=[-0.5, 0.5],
+        head_range_factor=1.0,
+    )
+
+
+def qpos_noise_scale(config: ConfigDict, nu: int) -> np.ndarray:
+    """joystick.py:184-200: indices come from the 10-entry JOINTS_ORDER_NO_HEAD but index a 14-long
+    per-actuator array, so the scales land on actuator slots 0..9."""
+    out = np.zeros(nu)
+    s = config.noise_config.scales
+    for idx, j in enumerate(JOINTS_ORDER_NO_HEAD):
+        if "_hip" in j:
+            out[idx] = s.hip_pos
+        if "_knee" in j:
+            out[idx] = s.knee_pos
+        if "_ankle" in j:
+            out[idx] = s.ankle_pos
+    return out
+
+
+def build_env_config(model: CompiledModel, config: ConfigDict, poly: Optional[PolyTable], auto_reset: bool = True,
+                     use_imitation_reward: bool = USE_IMITATION_REWARD,
+                     use_motor_speed_limits: bool = USE_MOTOR_SPEED_LIMITS):
+    """Pack ``config`` into the C struct.  Returns (struct, keepalive) -- keepalive owns the coefficient array."""
+    c = capi.OduckEnvConfig()
+    n_sub = int(round(config.ctrl_dt / config.sim_dt))
+    c.n_substeps = n_sub
+    c.episode_length = int(config.episode_length)
+    c.use_imitation_reward = int(use_imitation_reward)
+    c.use_motor_speed_limits = int(use_motor_speed_limits)
+    c.push_enable = int(bool(config.push_config.enable))
+    nc = config.noise_config
+    c.action_min_delay, c.action_max_delay = int(nc.action_min_delay), int(nc.action_max_delay)
+    c.imu_min_delay, c.imu_max_delay = int(nc.imu_min_delay), int(nc.imu_max_delay)
+    c.auto_reset = int(auto_reset)
+    c.ctrl_dt = float(config.ctrl_dt)
+    c.action_scale = float(config.action_scale)
+    c.dof_vel_scale = float(config.dof_vel_scale)
+    c.max_motor_velocity = float(config.max_motor_velocity)
+    c.noise_level = float(nc.level)
+    c.noise_gyro, c.noise_accelerometer = float(nc.scales.gyro), float(nc.scales.accelerometer)
+    c.noise_gravity, c.noise_joint_vel = float(nc.scales.gravity), float(nc.scales.joint_vel)
+    qn = qpos_noise_scale(config, model.nu)
+    for i in range(model.nu):
+        c.qpos_noise_scale[i] = qn[i]
+    rs = config.reward_config.scales
+    c.scale_tracking_lin_vel, c.scale_tracking_ang_vel = float(rs.tracking_lin_vel), float(rs.tracking_ang_vel)
+    c.scale_torques, c.scale_action_rate = float(rs.torques), float(rs.action_rate)
+    c.scale_stand_still, c.scale_alive, c.scale_imitation = float(rs.stand_still), float(rs.alive), float(rs.imitation)
+    c.tracking_sigma = float(config.reward_config.tracking_sigma)
+    for i in range(2):
+        c.push_interval_range[i] = float(config.push_config.interval_range[i])
+        c.push_magnitude_range[i] = float(config.push_config.magnitude_range[i])
+    f = float(config.head_range_factor)
+    ranges = [config.lin_vel_x, config.lin_vel_y, config.ang_vel_yaw,
+              [config.neck_pitch_range[0] * f, config.neck_pitch_range[1] * f],
+              [config.head_pitch_range[0] * f, config.head_pitch_range[1] * f],
+              [config.head_yaw_range[0] * f, config.head_yaw_range[1] * f],
+              [config.head_roll_range[0] * f, config.head_roll_range[1] * f]]
+    for i, r in enumerate(ranges):
+        c.cmd_range[i][0], c.cmd_range[i][1] = float(r[0]), float(r[1])
+    keep = None
+    if use_imitation_reward:
+        if poly is None:
+            raise ValueError("USE_IMITATION_REWARD needs the polynomial reference-motion table")
+        if len(poly.dxs) > 8 or len(poly.dys) > 8 or len(poly.dthetas) > 16:
+            raise ValueError("reference-motion grid exceeds the C struct limits")
+        c.ndx, c.ndy, c.ndth = len(poly.dxs), len(poly.dys), len(poly.dthetas)
+        c.nb_steps_in_period = int(poly.nb_steps_in_period)
+        for i, v in enumerate(poly.dxs):
+            c.dxs[i] = v
+        for i, v in enumerate(poly.dys):
+            c.dys[i] = v
+        for i, v in enumerate(poly.dthetas):
+            c.dthetas[i] = v
+        for i in range(2):
+            c.dx_range[i], c.dy_range[i], c.dtheta_range[i] = poly.dx_range[i], poly.dy_range[i], poly.dtheta_range[i]
+        keep = np.ascontiguousarray(poly.coef, dtype=np.float64)
+        c.poly_coef = keep.ctypes.data_as(C.POINTER(C.c_double))
+    else:
+        c.nb_steps_in_period = 1
+    return c, keep

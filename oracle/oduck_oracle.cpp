@@ -1,0 +1,1390 @@
+// oduck_oracle.cpp -- CPU restatement (the ORACLE) of the Open Duck Mini V2 joystick hot path.
+//
+// TEST INFRASTRUCTURE ONLY.  Nothing under open_duck_playground_b200/ may import, link or call
+// this file; it exists so that tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg can
+// check / time the CUDA path against an independent implementation of the same algorithm.
+//
+// PARITY UNPINNED for the physics: the arithmetic of the reference's step lives in mujoco.mjx,
+// which is not vendored in the reference, not installable here (no network), and the reference
+// holds no golden vectors for it.  The physics below restates the published
+// MuJoCo/MJX algorithms (MJX 3.x: forward.py, smooth.py, collision_convex.py plane_convex,
+// constraint.py, solver.py, sensor.py) anchored on the reference's call sites:
+//   mjx_env.step / mjx_env.init      open_duck_mini_v2/joystick.py:258,420
+//   geoms_colliding                  open_duck_mini_v2/joystick.py:313-318,424-429
+//   get_sensor_data                  open_duck_mini_v2/base.py:234-264
+// PINNED parts (checked against the reference's own NumPy twins / data in tests/):
+//   rewards            common/rewards.py:11-125           (twin: common/rewards_numpy.py)
+//   imitation reward   open_duck_mini_v2/custom_rewards.py:4-149 (twin: custom_rewards_numpy.py)
+//   reference motion   common/poly_reference_motion.py:148-168   (twin: poly_reference_motion_numpy.py)
+// The env logic follows open_duck_mini_v2/joystick.py:206-725 line by line, jax.random is restated as
+// Threefry-2x32 with jax_threefry_partitionable=True (JAX >= 0.5 default), and the Brax
+// Episode/AutoReset wrappers (common/runner.py:117) are fused into oduck_step.
+//
+// Build: see oracle/Makefile.  ODUCK_REAL selects the arithmetic type (double = checker,
+// float + OpenMP = the CPU baseline timed by bench.py).
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../include/oduck.h"
+
+#ifndef ODUCK_REAL
+#define ODUCK_REAL double
+#endif
+typedef ODUCK_REAL real;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+
+#include <thread>
+// Minimal parallel-for over envs (the image has no libgomp).  ODUCK_THREADS overrides the thread count.
+static int g_threads_used = 1;
+template <typename F> static void pfor(int n, F f) {
+  int nt = (int)std::thread::hardware_concurrency();
+  if (const char* s = getenv("ODUCK_THREADS")) nt = atoi(s);
+  nt = std::max(1, std::min(nt, n));
+  g_threads_used = nt;
+  if (nt == 1) { for (int i = 0; i < n; i++) f(i); return; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < nt; t++) th.emplace_back([=]() { for (int i = (int)((int64_t)n * t / nt); i < (int)((int64_t)n * (t + 1) / nt); i++) f(i); });
+  for (auto& t : th) t.join();
+}
+
+static const real kMinVal = (real)1e-15;
+static const real kMinImp = (real)0.0001, kMaxImp = (real)0.9999;
+
+#define NB ODUCK_MAX_BODY
+#define NJ ODUCK_MAX_JNT
+#define NQ ODUCK_MAX_NQ
+#define NV ODUCK_MAX_NV
+#define NU ODUCK_MAX_NU
+#define NCON ODUCK_MAX_CON
+#define NEFC (ODUCK_MAX_NU + ODUCK_MAX_JNT + 4 * ODUCK_MAX_CON)
+
+// ------------------------------------------------------------------------------------ small math
+static inline void cross3(const real* a, const real* b, real* o) {
+  real x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+static inline real dot3(const real* a, const real* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+static inline void quat_mul(const real* a, const real* b, real* o) {
+  real w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  real x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  real y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+  real z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+  o[0] = w; o[1] = x; o[2] = y; o[3] = z;
+}
+static inline void quat_norm(real* q) {
+  real n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  if (n < kMinVal) { q[0] = 1; q[1] = q[2] = q[3] = 0; return; }
+  for (int i = 0; i < 4; i++) q[i] /= n;
+}
+static inline void quat2mat(const real* q, real* m) {  // row-major 3x3
+  real w = q[0], x = q[1], y = q[2], z = q[3];
+  m[0] = 1 - 2 * (y * y + z * z); m[1] = 2 * (x * y - w * z); m[2] = 2 * (x * z + w * y);
+  m[3] = 2 * (x * y + w * z); m[4] = 1 - 2 * (x * x + z * z); m[5] = 2 * (y * z - w * x);
+  m[6] = 2 * (x * z - w * y); m[7] = 2 * (y * z + w * x); m[8] = 1 - 2 * (x * x + y * y);
+}
+static inline void mat_vec(const real* m, const real* v, real* o) {
+  real x = m[0] * v[0] + m[1] * v[1] + m[2] * v[2], y = m[3] * v[0] + m[4] * v[1] + m[5] * v[2],
+       z = m[6] * v[0] + m[7] * v[1] + m[8] * v[2];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+static inline void matT_vec(const real* m, const real* v, real* o) {
+  real x = m[0] * v[0] + m[3] * v[1] + m[6] * v[2], y = m[1] * v[0] + m[4] * v[1] + m[7] * v[2],
+       z = m[2] * v[0] + m[5] * v[1] + m[8] * v[2];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+// spatial (MuJoCo convention: [angular(3), linear(3)])
+static inline void cross_motion(const real* v, const real* m, real* o) {  // mju_crossMotion
+  real a[3], b[3], c[3];
+  cross3(v, m, a);
+  cross3(v, m + 3, b);
+  cross3(v + 3, m, c);
+  o[0] = a[0]; o[1] = a[1]; o[2] = a[2];
+  o[3] = b[0] + c[0]; o[4] = b[1] + c[1]; o[5] = b[2] + c[2];
+}
+static inline void cross_force(const real* v, const real* f, real* o) {  // mju_crossForce
+  real a[3], b[3], c[3];
+  cross3(v, f, a);
+  cross3(v + 3, f + 3, b);
+  cross3(v, f + 3, c);
+  o[0] = a[0] + b[0]; o[1] = a[1] + b[1]; o[2] = a[2] + b[2];
+  o[3] = c[0]; o[4] = c[1]; o[5] = c[2];
+}
+// 10-number spatial inertia about a reference point: [Ixx Iyy Izz Ixy Ixz Iyz, m*dx m*dy m*dz, m]
+static inline void inert_mul(const real* I, const real* v, real* o) {  // mju_mulInertVec
+  real r0 = I[0] * v[0] + I[3] * v[1] + I[4] * v[2] - I[8] * v[4] + I[7] * v[5];
+  real r1 = I[3] * v[0] + I[1] * v[1] + I[5] * v[2] + I[8] * v[3] - I[6] * v[5];
+  real r2 = I[4] * v[0] + I[5] * v[1] + I[2] * v[2] - I[7] * v[3] + I[6] * v[4];
+  real r3 = I[8] * v[1] - I[7] * v[2] + I[9] * v[3];
+  real r4 = I[6] * v[2] - I[8] * v[0] + I[9] * v[4];
+  real r5 = I[7] * v[0] - I[6] * v[1] + I[9] * v[5];
+  o[0] = r0; o[1] = r1; o[2] = r2; o[3] = r3; o[4] = r4; o[5] = r5;
+}
+
+// ------------------------------------------------------------------------------------ jax.random
+static inline uint32_t rotl(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+static void threefry2x32(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1, uint32_t* o0, uint32_t* o1) {
+  const int R[8] = {13, 15, 26, 6, 17, 29, 16, 24};
+  uint32_t ks[3] = {k0, k1, k0 ^ k1 ^ 0x1BD11BDAu};
+  x0 += ks[0]; x1 += ks[1];
+  for (int blk = 0; blk < 5; blk++) {
+    const int* r = R + 4 * (blk & 1);
+    for (int i = 0; i < 4; i++) { x0 += x1; x1 = rotl(x1, r[i]); x1 ^= x0; }
+    x0 += ks[(blk + 1) % 3];
+    x1 += ks[(blk + 2) % 3] + (uint32_t)(blk + 1);
+  }
+  *o0 = x0; *o1 = x1;
+}
+struct Key { uint32_t a, b; };
+// jax.random.split(key, n)[i] under threefry_partitionable: both output words of block (0, i)
+static inline Key key_split(Key k, uint32_t i) { Key o; threefry2x32(k.a, k.b, 0u, i, &o.a, &o.b); return o; }
+// jax.random.bits(key, shape)[i], 32 bit: xor of the two output words of block (0, i)
+static inline uint32_t key_bits(Key k, uint32_t i) { uint32_t a, b; threefry2x32(k.a, k.b, 0u, i, &a, &b); return a ^ b; }
+static inline real bits_to_unit(uint32_t bits) {
+  uint32_t u = (bits >> 9) | 0x3F800000u;
+  float f; std::memcpy(&f, &u, 4);
+  return (real)(f - 1.0f);
+}
+// jax.random.uniform(key, shape, minval, maxval)[i]
+static inline real key_uniform(Key k, uint32_t i, real lo, real hi) {
+  real v = bits_to_unit(key_bits(k, i)) * (hi - lo) + lo;
+  return std::max(lo, v);
+}
+// jax.random.randint(key, (1,), lo, hi)[0]
+static inline int key_randint(Key k, int lo, int hi) {
+  Key k1 = key_split(k, 0), k2 = key_split(k, 1);
+  uint32_t hb = key_bits(k1, 0), lb = key_bits(k2, 0);
+  uint32_t span = hi <= lo ? 1u : (uint32_t)(hi - lo);
+  uint32_t mult = 65536u % span;
+  mult = (mult * mult) % span;
+  uint32_t off = ((hb % span) * mult + (lb % span)) % span;
+  return lo + (int)off;
+}
+
+// ------------------------------------------------------------------------------------ state
+struct EnvState {
+  // mjx.Data subset
+  real qpos[NQ], qvel[NV], qacc_warm[NV], qacc[NV], ctrl[NU];
+  // per-env randomised model (common/randomize.py)
+  real dr_geom_friction0;  // written, never read by physics: geom 0 is a visual mesh
+  real body_mass[NB], body_ipos[NB][3], dof_frictionloss[NV], dof_armature[NV], qpos0[NQ], act_kp[NU];
+  // outputs of the last forward()
+  real sensordata[24], efc_force[NEFC], contact_dist[NCON], actuator_force[NU], site_xpos_feet[6], imu_xmat[9];
+  // State
+  real obs_state[ODUCK_OBS_STATE], obs_priv[ODUCK_OBS_PRIV], reward, done, truncation, metrics[ODUCK_NMETRIC];
+  // info (joystick.py:278-302)
+  Key rng;
+  int32_t step, steps, push_step, push_interval_steps, imitation_i;
+  real command[ODUCK_NCMD], last_act[3][NU], motor_targets[NU], feet_air_time[2], last_contact[2], swing_peak[2], push[2];
+  real action_history[8 * NU], imu_history[8 * 3], ref_motion[ODUCK_REF_DIM], imitation_phase[2];
+  // auto-reset target
+  real first_qpos[NQ], first_qvel[NV], first_qacc_warm[NV], first_obs_state[ODUCK_OBS_STATE], first_obs_priv[ODUCK_OBS_PRIV];
+  // forward() outputs that have to survive auto-reset bookkeeping are recomputed, not stored
+};
+
+struct OduckHandle {
+  OduckModel m;
+  OduckEnvConfig cfg;
+  std::vector<double> poly;
+  int n;
+  std::vector<EnvState> env;
+  int nefc_fr, nefc_lim;  // static row counts
+  int fr_dof[NV], lim_jnt[NJ];
+  int64_t launches;
+};
+
+// ------------------------------------------------------------------------------------ physics scratch
+struct Scratch {
+  real xpos[NB][3], xquat[NB][4], xmat[NB][9], xipos[NB][3], ximat[NB][9];
+  real xanchor[NJ][3], xaxis[NJ][3];
+  real site_xpos[ODUCK_MAX_SITE][3], site_xmat[ODUCK_MAX_SITE][9];
+  real com[3];  // subtree_com of the robot's kinematic-tree root
+  real cinert[NB][10], crb[NB][10], cdof[NV][6], cdof_dot[NV][6], cvel[NB][6];
+  real M[NV][NV], L[NV][NV];
+  real qfrc_bias[NV], qfrc_passive[NV], qfrc_actuator[NV], qfrc_smooth[NV], qacc_smooth[NV];
+  // contacts
+  real con_dist[NCON], con_pos[NCON][3], con_frame[NCON][9], con_mu[NCON];
+  int con_b1[NCON], con_b2[NCON];
+  // constraints
+  int nefc;
+  real J[NEFC][NV], D[NEFC], aref[NEFC], floss[NEFC];
+  int rtype[NEFC];  // 0 friction, 1 limit/contact (one-sided)
+};
+
+static bool cholesky(int n, real A[NV][NV], real L[NV][NV]) {
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j <= i; j++) {
+      real s = A[i][j];
+      for (int k = 0; k < j; k++) s -= L[i][k] * L[j][k];
+      if (i == j) {
+        if (!(s > 0)) return false;
+        L[i][i] = std::sqrt(s);
+      } else {
+        L[i][j] = s / L[j][j];
+      }
+    }
+  return true;
+}
+static void chol_solve(int n, real L[NV][NV], const real* b, real* x) {
+  real y[NV];
+  for (int i = 0; i < n; i++) {
+    real s = b[i];
+    for (int k = 0; k < i; k++) s -= L[i][k] * y[k];
+    y[i] = s / L[i][i];
+  }
+  for (int i = n - 1; i >= 0; i--) {
+    real s = y[i];
+    for (int k = i + 1; k < n; k++) s -= L[k][i] * x[k];
+    x[i] = s / L[i][i];
+  }
+}
+
+// mjx/_src/smooth.py kinematics + com_pos
+static void kinematics(const OduckModel& m, const EnvState& e, Scratch& s) {
+  s.xpos[0][0] = s.xpos[0][1] = s.xpos[0][2] = 0;
+  s.xquat[0][0] = 1; s.xquat[0][1] = s.xquat[0][2] = s.xquat[0][3] = 0;
+  quat2mat(s.xquat[0], s.xmat[0]);
+  for (int b = 1; b < m.nbody; b++) {
+    int p = m.body_parentid[b];
+    real pos[3], quat[4], bp[3] = {(real)m.body_pos[b][0], (real)m.body_pos[b][1], (real)m.body_pos[b][2]};
+    real bq[4] = {(real)m.body_quat[b][0], (real)m.body_quat[b][1], (real)m.body_quat[b][2], (real)m.body_quat[b][3]};
+    mat_vec(s.xmat[p], bp, pos);
+    for (int i = 0; i < 3; i++) pos[i] += s.xpos[p][i];
+    quat_mul(s.xquat[p], bq, quat);
+    for (int k = 0; k < m.body_jntnum[b]; k++) {
+      int j = m.body_jntadr[b] + k, qa = m.jnt_qposadr[j];
+      if (m.jnt_type[j] == ODUCK_JNT_FREE) {
+        for (int i = 0; i < 3; i++) pos[i] = e.qpos[qa + i];
+        for (int i = 0; i < 4; i++) quat[i] = e.qpos[qa + 3 + i];
+        quat_norm(quat);
+        for (int i = 0; i < 3; i++) { s.xanchor[j][i] = pos[i]; s.xaxis[j][i] = (i == 2); }
+      } else {
+        real R[9], jp_[3] = {(real)m.jnt_pos[j][0], (real)m.jnt_pos[j][1], (real)m.jnt_pos[j][2]};
+        real ja[3] = {(real)m.jnt_axis[j][0], (real)m.jnt_axis[j][1], (real)m.jnt_axis[j][2]}, t[3];
+        quat2mat(quat, R);
+        mat_vec(R, jp_, t);
+        for (int i = 0; i < 3; i++) s.xanchor[j][i] = pos[i] + t[i];
+        mat_vec(R, ja, s.xaxis[j]);
+        real ang = e.qpos[qa] - e.qpos0[qa];
+        real ql[4] = {std::cos(ang / 2), std::sin(ang / 2) * ja[0], std::sin(ang / 2) * ja[1], std::sin(ang / 2) * ja[2]}, qn[4];
+        quat_mul(quat, ql, qn);
+        for (int i = 0; i < 4; i++) quat[i] = qn[i];
+        quat2mat(quat, R);
+        mat_vec(R, jp_, t);
+        for (int i = 0; i < 3; i++) pos[i] = s.xanchor[j][i] - t[i];
+      }
+    }
+    quat_norm(quat);
+    for (int i = 0; i < 3; i++) s.xpos[b][i] = pos[i];
+    for (int i = 0; i < 4; i++) s.xquat[b][i] = quat[i];
+    quat2mat(quat, s.xmat[b]);
+    mat_vec(s.xmat[b], e.body_ipos[b], s.xipos[b]);
+    for (int i = 0; i < 3; i++) s.xipos[b][i] += s.xpos[b][i];
+    real iq[4] = {(real)m.body_iquat[b][0], (real)m.body_iquat[b][1], (real)m.body_iquat[b][2], (real)m.body_iquat[b][3]}, q2[4];
+    quat_mul(quat, iq, q2);
+    quat2mat(q2, s.ximat[b]);
+  }
+  for (int k = 0; k < m.nsite; k++) {
+    int b = m.site_bodyid[k];
+    real sp[3] = {(real)m.site_pos[k][0], (real)m.site_pos[k][1], (real)m.site_pos[k][2]};
+    real sq[4] = {(real)m.site_quat[k][0], (real)m.site_quat[k][1], (real)m.site_quat[k][2], (real)m.site_quat[k][3]}, q2[4];
+    mat_vec(s.xmat[b], sp, s.site_xpos[k]);
+    for (int i = 0; i < 3; i++) s.site_xpos[k][i] += s.xpos[b][i];
+    quat_mul(s.xquat[b], sq, q2);
+    quat2mat(q2, s.site_xmat[k]);
+  }
+}
+
+static bool body_moves(const OduckModel& m, int b) {
+  while (b > 0) { if (m.body_dofnum[b] > 0) return true; b = m.body_parentid[b]; }
+  return false;
+}
+
+static void com_pos(const OduckModel& m, const EnvState& e, Scratch& s) {
+  // subtree COM of the (single) moving kinematic tree; static bodies (floor) refer to the world origin
+  real mt = 0, c[3] = {0, 0, 0};
+  for (int b = 1; b < m.nbody; b++)
+    if (body_moves(m, b)) {
+      mt += e.body_mass[b];
+      for (int i = 0; i < 3; i++) c[i] += e.body_mass[b] * s.xipos[b][i];
+    }
+  for (int i = 0; i < 3; i++) s.com[i] = c[i] / std::max(mt, kMinVal);
+  for (int b = 0; b < m.nbody; b++) {
+    real* I = s.cinert[b];
+    for (int i = 0; i < 10; i++) I[i] = 0;
+    if (b == 0 || !body_moves(m, b)) continue;
+    // mju_inertCom: rotate the principal inertia into the world, shift to the COM reference point
+    const real* R = s.ximat[b];
+    real din[3] = {(real)m.body_inertia[b][0], (real)m.body_inertia[b][1], (real)m.body_inertia[b][2]};
+    real Iw[9];
+    for (int r = 0; r < 3; r++)
+      for (int cc = 0; cc < 3; cc++) Iw[3 * r + cc] = R[3 * r] * din[0] * R[3 * cc] + R[3 * r + 1] * din[1] * R[3 * cc + 1] + R[3 * r + 2] * din[2] * R[3 * cc + 2];
+    real d[3] = {s.xipos[b][0] - s.com[0], s.xipos[b][1] - s.com[1], s.xipos[b][2] - s.com[2]};
+    real ms = e.body_mass[b];
+    I[0] = Iw[0] + ms * (d[1] * d[1] + d[2] * d[2]);
+    I[1] = Iw[4] + ms * (d[0] * d[0] + d[2] * d[2]);
+    I[2] = Iw[8] + ms * (d[0] * d[0] + d[1] * d[1]);
+    I[3] = Iw[1] - ms * d[0] * d[1];
+    I[4] = Iw[2] - ms * d[0] * d[2];
+    I[5] = Iw[5] - ms * d[1] * d[2];
+    I[6] = ms * d[0]; I[7] = ms * d[1]; I[8] = ms * d[2];
+    I[9] = ms;
+  }
+  for (int j = 0; j < m.njnt; j++) {
+    int da = m.jnt_dofadr[j], b = m.jnt_bodyid[j];
+    if (m.jnt_type[j] == ODUCK_JNT_FREE) {
+      for (int k = 0; k < 3; k++) {
+        for (int i = 0; i < 6; i++) s.cdof[da + k][i] = 0;
+        s.cdof[da + k][3 + k] = 1;
+      }
+      real off[3] = {s.com[0] - s.xpos[b][0], s.com[1] - s.xpos[b][1], s.com[2] - s.xpos[b][2]};
+      for (int k = 0; k < 3; k++) {
+        real ax[3] = {s.xmat[b][k], s.xmat[b][3 + k], s.xmat[b][6 + k]};
+        for (int i = 0; i < 3; i++) s.cdof[da + 3 + k][i] = ax[i];
+        cross3(ax, off, s.cdof[da + 3 + k] + 3);
+      }
+    } else {
+      real off[3] = {s.com[0] - s.xanchor[j][0], s.com[1] - s.xanchor[j][1], s.com[2] - s.xanchor[j][2]};
+      for (int i = 0; i < 3; i++) s.cdof[da][i] = s.xaxis[j][i];
+      cross3(s.xaxis[j], off, s.cdof[da] + 3);
+    }
+  }
+}
+
+// composite rigid body + dense mass matrix (smooth.py crb), dense Cholesky (factor_m, dense branch)
+static void crb(const OduckModel& m, const EnvState& e, Scratch& s) {
+  for (int b = 0; b < m.nbody; b++)
+    for (int i = 0; i < 10; i++) s.crb[b][i] = s.cinert[b][i];
+  for (int b = m.nbody - 1; b > 0; b--) {
+    int p = m.body_parentid[b];
+    if (p > 0)
+      for (int i = 0; i < 10; i++) s.crb[p][i] += s.crb[b][i];
+  }
+  for (int i = 0; i < m.nv; i++)
+    for (int j = 0; j < m.nv; j++) s.M[i][j] = 0;
+  for (int i = 0; i < m.nv; i++) {
+    real buf[6];
+    inert_mul(s.crb[m.dof_bodyid[i]], s.cdof[i], buf);
+    s.M[i][i] = e.dof_armature[i];
+    for (int j = i; j >= 0; j = m.dof_parentid[j]) {
+      real v = 0;
+      for (int k = 0; k < 6; k++) v += s.cdof[j][k] * buf[k];
+      s.M[i][j] += v;
+      if (j != i) s.M[j][i] = s.M[i][j];
+    }
+  }
+}
+
+static void com_vel(const OduckModel& m, const EnvState& e, Scratch& s) {
+  for (int i = 0; i < 6; i++) s.cvel[0][i] = 0;
+  for (int b = 1; b < m.nbody; b++) {
+    real cv[6];
+    for (int i = 0; i < 6; i++) cv[i] = s.cvel[m.body_parentid[b]][i];
+    for (int k = 0; k < m.body_jntnum[b]; k++) {
+      int j = m.body_jntadr[b] + k, da = m.jnt_dofadr[j];
+      if (m.jnt_type[j] == ODUCK_JNT_FREE) {
+        for (int d = 0; d < 3; d++) {
+          for (int i = 0; i < 6; i++) { s.cdof_dot[da + d][i] = 0; cv[i] += s.cdof[da + d][i] * e.qvel[da + d]; }
+        }
+        for (int d = 3; d < 6; d++) cross_motion(cv, s.cdof[da + d], s.cdof_dot[da + d]);
+        for (int d = 3; d < 6; d++)
+          for (int i = 0; i < 6; i++) cv[i] += s.cdof[da + d][i] * e.qvel[da + d];
+      } else {
+        cross_motion(cv, s.cdof[da], s.cdof_dot[da]);
+        for (int i = 0; i < 6; i++) cv[i] += s.cdof[da][i] * e.qvel[da];
+      }
+    }
+    for (int i = 0; i < 6; i++) s.cvel[b][i] = cv[i];
+  }
+}
+
+// recursive Newton-Euler bias force (smooth.py rne); with_acc adds cdof*qacc (rne_postconstraint cacc)
+static void rne(const OduckModel& m, const EnvState& e, Scratch& s, const real* qacc, real cacc[NB][6], real* qfrc_bias) {
+  real cfrc[NB][6];
+  for (int i = 0; i < 3; i++) { cacc[0][i] = 0; cacc[0][3 + i] = -(real)m.gravity[i]; }
+  for (int i = 0; i < 6; i++) cfrc[0][i] = 0;
+  for (int b = 1; b < m.nbody; b++) {
+    for (int i = 0; i < 6; i++) cacc[b][i] = cacc[m.body_parentid[b]][i];
+    for (int d = m.body_dofadr[b]; d >= 0 && d < m.body_dofadr[b] + m.body_dofnum[b]; d++)
+      for (int i = 0; i < 6; i++) cacc[b][i] += s.cdof_dot[d][i] * e.qvel[d] + (qacc ? s.cdof[d][i] * qacc[d] : 0);
+    real t1[6], t2[6], t3[6];
+    inert_mul(s.cinert[b], cacc[b], t1);
+    inert_mul(s.cinert[b], s.cvel[b], t2);
+    cross_force(s.cvel[b], t2, t3);
+    for (int i = 0; i < 6; i++) cfrc[b][i] = t1[i] + t3[i];
+  }
+  if (!qfrc_bias) return;
+  for (int b = m.nbody - 1; b > 0; b--)
+    for (int i = 0; i < 6; i++) cfrc[m.body_parentid[b]][i] += cfrc[b][i];
+  for (int d = 0; d < m.nv; d++) {
+    real v = 0;
+    for (int i = 0; i < 6; i++) v += s.cdof[d][i] * cfrc[m.dof_bodyid[d]][i];
+    qfrc_bias[d] = v;
+  }
+}
+
+// math.make_frame (MJX): orthonormal frame whose first row is the normal
+static void make_frame(const real* n, real* f) {
+  real a[3] = {n[0], n[1], n[2]};
+  real nn = std::sqrt(dot3(a, a));
+  for (int i = 0; i < 3; i++) a[i] /= nn;
+  real y[3] = {0, 1, 0}, z[3] = {0, 0, 1};
+  real* b0 = (-0.5 < a[1] && a[1] < 0.5) ? y : z;
+  real b[3];
+  real d = dot3(a, b0);
+  for (int i = 0; i < 3; i++) b[i] = b0[i] - a[i] * d;
+  real bn = std::sqrt(dot3(b, b));
+  for (int i = 0; i < 3; i++) b[i] /= bn;
+  real c[3];
+  cross3(a, b, c);
+  for (int i = 0; i < 3; i++) { f[i] = a[i]; f[3 + i] = b[i]; f[6 + i] = c[i]; }
+}
+
+// collision_convex.py _manifold_points: four polygon points of roughly maximal area
+static void manifold_points(int nv, const real (*poly)[3], const bool* mask, const real* n, int* idx) {
+  auto dmask = [&](int i) { return mask[i] ? (real)0 : (real)-1e6; };
+  int a = 0;
+  { real best = -std::numeric_limits<real>::infinity(); for (int i = 0; i < nv; i++) if (dmask(i) > best) { best = dmask(i); a = i; } }
+  int b = 0;
+  { real best = -std::numeric_limits<real>::infinity();
+    for (int i = 0; i < nv; i++) { real d[3] = {poly[a][0] - poly[i][0], poly[a][1] - poly[i][1], poly[a][2] - poly[i][2]}; real v = dot3(d, d) + dmask(i); if (v > best) { best = v; b = i; } } }
+  real ab[3], amb[3] = {poly[a][0] - poly[b][0], poly[a][1] - poly[b][1], poly[a][2] - poly[b][2]};
+  cross3(n, amb, ab);
+  int c = 0;
+  { real best = -std::numeric_limits<real>::infinity();
+    for (int i = 0; i < nv; i++) { real ap[3] = {poly[a][0] - poly[i][0], poly[a][1] - poly[i][1], poly[a][2] - poly[i][2]}; real v = std::fabs(dot3(ap, ab)) + dmask(i); if (v > best) { best = v; c = i; } } }
+  real ac[3], bc[3], amc[3] = {poly[a][0] - poly[c][0], poly[a][1] - poly[c][1], poly[a][2] - poly[c][2]};
+  real bmc[3] = {poly[b][0] - poly[c][0], poly[b][1] - poly[c][1], poly[b][2] - poly[c][2]};
+  cross3(n, amc, ac);
+  cross3(n, bmc, bc);
+  int d = 0;
+  { real best = -std::numeric_limits<real>::infinity();
+    // argmax over concatenate([dist_bp, dist_ap]) % nv: first maximum, bp block first
+    for (int i = 0; i < nv; i++) { real bp[3] = {poly[b][0] - poly[i][0], poly[b][1] - poly[i][1], poly[b][2] - poly[i][2]}; real v = std::fabs(dot3(bp, bc)) + dmask(i); if (v > best) { best = v; d = i; } }
+    for (int i = 0; i < nv; i++) { real ap[3] = {poly[a][0] - poly[i][0], poly[a][1] - poly[i][1], poly[a][2] - poly[i][2]}; real v = std::fabs(dot3(ap, ac)) + dmask(i); if (v > best) { best = v; d = i; } } }
+  idx[0] = a; idx[1] = b; idx[2] = c; idx[3] = d;
+}
+
+// collision_convex.py plane_convex for the flat floor (plane z = 0, normal +z) vs foot hull k
+static void plane_convex(const OduckModel& m, const Scratch& s, int k, int slot0, Scratch& out) {
+  int b = m.foot_body[k], nvt = m.foot_nvert;
+  const real* R = s.xmat[b];
+  // plane in the hull (body) frame
+  real ppos[3], mp[3] = {-s.xpos[b][0], -s.xpos[b][1], -s.xpos[b][2]}, wn[3] = {0, 0, 1}, n[3];
+  matT_vec(R, mp, ppos);
+  matT_vec(R, wn, n);
+  real vert[ODUCK_MAX_VERT][3], support[ODUCK_MAX_VERT], smax = -std::numeric_limits<real>::infinity();
+  bool mask[ODUCK_MAX_VERT];
+  for (int i = 0; i < nvt; i++) {
+    for (int c = 0; c < 3; c++) vert[i][c] = (real)m.foot_vert[k][i][c];
+    real d[3] = {ppos[0] - vert[i][0], ppos[1] - vert[i][1], ppos[2] - vert[i][2]};
+    support[i] = dot3(d, n);
+    smax = std::max(smax, support[i]);
+  }
+  real thr = std::max((real)0, smax - (real)1e-3);
+  for (int i = 0; i < nvt; i++) mask[i] = support[i] > thr;
+  int idx[4];
+  manifold_points(nvt, vert, mask, n, idx);
+  real frame[9];
+  make_frame(wn, frame);
+  for (int c = 0; c < 4; c++) {
+    int sl = slot0 + c;
+    // unique = first occurrence of this vertex index in idx
+    bool unique = true;
+    for (int p = 0; p < c; p++) unique &= idx[p] != idx[c];
+    real dist = unique ? -support[idx[c]] : (real)1;
+    real pw[3];
+    mat_vec(R, vert[idx[c]], pw);
+    for (int i = 0; i < 3; i++) out.con_pos[sl][i] = s.xpos[b][i] + pw[i] - (real)0.5 * dist * wn[i];
+    out.con_dist[sl] = dist;
+    for (int i = 0; i < 9; i++) out.con_frame[sl][i] = frame[i];
+    out.con_b1[sl] = 0;  // floor body is static: zero Jacobian, zero invweight
+    out.con_b2[sl] = b;
+    out.con_mu[sl] = (real)m.floor_friction;
+  }
+}
+
+// constraint.py _kbi / _efc_row
+static void kbi(const OduckModel& m, real pos, real* k, real* b, real* imp) {
+  real timeconst = std::max((real)m.solref[0], 2 * (real)m.timestep), dampratio = (real)m.solref[1];
+  real dmin = std::min(std::max((real)m.solimp[0], kMinImp), kMaxImp), dmax = std::min(std::max((real)m.solimp[1], kMinImp), kMaxImp);
+  real width = std::max(kMinVal, (real)m.solimp[2]);
+  real mid = std::min(std::max((real)m.solimp[3], kMinImp), kMaxImp), power = std::max((real)1, (real)m.solimp[4]);
+  *k = 1 / (dmax * dmax * timeconst * timeconst * dampratio * dampratio);
+  *b = 2 / (dmax * timeconst);
+  if (m.solref[0] <= 0) *k = -(real)m.solref[0] / (dmax * dmax);
+  if (m.solref[1] <= 0) *b = -(real)m.solref[1] / dmax;
+  real x = std::fabs(pos) / width;
+  real ia = (1 / std::pow(mid, power - 1)) * std::pow(x, power);
+  real ib = 1 - (1 / std::pow(1 - mid, power - 1)) * std::pow(1 - x, power);
+  real y = x < mid ? ia : ib;
+  real im = dmin + y * (dmax - dmin);
+  im = std::min(std::max(im, dmin), dmax);
+  if (x > 1) im = dmax;
+  *imp = im;
+}
+
+static void make_constraint(const OduckHandle& h, const EnvState& e, Scratch& s) {
+  const OduckModel& m = h.m;
+  int r = 0;
+  auto zero_row = [&](int row) { for (int j = 0; j < m.nv; j++) s.J[row][j] = 0; s.D[row] = 0; s.aref[row] = 0; s.floss[row] = 0; };
+  // dof friction loss (constraint.py _instantiate_friction)
+  for (int i = 0; i < h.nefc_fr; i++, r++) {
+    int d = h.fr_dof[i];
+    zero_row(r);
+    s.rtype[r] = 0;
+    real k, b, imp;
+    kbi(m, 0, &k, &b, &imp);
+    s.J[r][d] = 1;
+    real rr = std::max((real)m.dof_invweight0[d] * (1 - imp) / imp, kMinVal);
+    s.D[r] = 1 / rr;
+    s.aref[r] = -b * e.qvel[d];
+    s.floss[r] = e.dof_frictionloss[d];
+  }
+  // hinge limits (_instantiate_limit_slide_hinge)
+  for (int i = 0; i < h.nefc_lim; i++, r++) {
+    int j = h.lim_jnt[i], d = m.jnt_dofadr[j];
+    zero_row(r);
+    s.rtype[r] = 1;
+    real q = e.qpos[m.jnt_qposadr[j]];
+    real dmin = q - (real)m.jnt_range[j][0], dmax = (real)m.jnt_range[j][1] - q;
+    real pos = std::min(dmin, dmax);
+    if (!(pos < 0)) continue;
+    real sign = dmin < dmax ? (real)1 : (real)-1;
+    real k, b, imp;
+    kbi(m, pos, &k, &b, &imp);
+    s.J[r][d] = sign;
+    real rr = std::max((real)m.dof_invweight0[d] * (1 - imp) / imp, kMinVal);
+    s.D[r] = 1 / rr;
+    s.aref[r] = -b * (sign * e.qvel[d]) - k * imp * pos;
+  }
+  // pyramidal frictional contacts (_instantiate_contact, condim 3)
+  int ncon = ODUCK_CON_PER_PAIR * (2 + (m.enable_foot_foot ? 1 : 0));
+  for (int c = 0; c < ncon; c++) {
+    real dist = s.con_dist[c];
+    bool active = dist < 0;
+    real diff[3][NV];  // (jacp(body2) - jacp(body1)) rotated into the contact frame
+    for (int j = 0; j < m.nv; j++) diff[0][j] = diff[1][j] = diff[2][j] = 0;
+    if (active) {
+      real off[3] = {s.con_pos[c][0] - s.com[0], s.con_pos[c][1] - s.com[1], s.con_pos[c][2] - s.com[2]};
+      for (int side = 0; side < 2; side++) {
+        int b = side ? s.con_b2[c] : s.con_b1[c];
+        real sg = side ? (real)1 : (real)-1;
+        if (b <= 0) continue;
+        for (int d = m.body_dofadr[b] + m.body_dofnum[b] - 1; d >= 0; d = m.dof_parentid[d]) {
+          real jp_[3], t[3];
+          cross3(s.cdof[d], off, t);
+          for (int i = 0; i < 3; i++) jp_[i] = s.cdof[d][3 + i] + t[i];
+          for (int a = 0; a < 3; a++) diff[a][d] += sg * dot3(s.con_frame[c] + 3 * a, jp_);
+        }
+      }
+    }
+    real mu = s.con_mu[c];
+    real t = (real)m.body_invweight0[s.con_b1[c]][0] + (real)m.body_invweight0[s.con_b2[c]][0];
+    real invw = (t + mu * mu * t) * 2 * mu * mu / (real)m.impratio;
+    real k, b, imp;
+    kbi(m, dist, &k, &b, &imp);
+    for (int e4 = 0; e4 < 4; e4++, r++) {
+      zero_row(r);
+      s.rtype[r] = 1;
+      if (!active) continue;
+      int dim = 1 + e4 / 2;
+      real sg = (e4 & 1) ? (real)-1 : (real)1;
+      real vel = 0;
+      for (int j = 0; j < m.nv; j++) { s.J[r][j] = diff[0][j] + sg * mu * diff[dim][j]; vel += s.J[r][j] * e.qvel[j]; }
+      real rr = std::max(invw * (1 - imp) / imp, kMinVal);
+      s.D[r] = 1 / rr;
+      s.aref[r] = -b * vel - k * imp * dist;
+    }
+  }
+  s.nefc = r;
+}
+
+// ------------------------------------------------------------------------------------ solver.py (Newton)
+struct Ctx {
+  real qacc[NV], Ma[NV], Jaref[NEFC], efc_force[NEFC], qfrc_constraint[NV], grad[NV], Mgrad[NV], search[NV];
+  bool active[NEFC];
+  real gauss, cost, prev_cost;
+};
+
+static void update_constraint(const OduckModel& m, const Scratch& s, Ctx& c) {
+  real cost = 0;
+  for (int r = 0; r < s.nefc; r++) {
+    real x = c.Jaref[r];
+    if (s.rtype[r] == 0) {
+      real f = s.floss[r], rf = (1 / (s.D[r] + (s.D[r] == 0 ? kMinVal : 0))) * f;
+      if (x <= -rf) { c.efc_force[r] = f; c.active[r] = false; cost += f * (-(real)0.5 * rf - x); }
+      else if (x >= rf) { c.efc_force[r] = -f; c.active[r] = false; cost += f * (-(real)0.5 * rf + x); }
+      else { c.efc_force[r] = -s.D[r] * x; c.active[r] = true; cost += (real)0.5 * s.D[r] * x * x; }
+    } else {
+      c.active[r] = x < 0;
+      c.efc_force[r] = c.active[r] ? -s.D[r] * x : 0;
+      if (c.active[r]) cost += (real)0.5 * s.D[r] * x * x;
+    }
+  }
+  for (int j = 0; j < m.nv; j++) {
+    real v = 0;
+    for (int r = 0; r < s.nefc; r++) v += s.J[r][j] * c.efc_force[r];
+    c.qfrc_constraint[j] = v;
+  }
+  real g = 0;
+  for (int j = 0; j < m.nv; j++) g += (c.Ma[j] - s.qfrc_smooth[j]) * (c.qacc[j] - s.qacc_smooth[j]);
+  c.gauss = (real)0.5 * g;
+  c.prev_cost = c.cost;
+  c.cost = cost + c.gauss;
+}
+
+static void update_gradient(const OduckModel& m, Scratch& s, Ctx& c) {
+  static thread_local real H[NV][NV], LH[NV][NV];
+  for (int j = 0; j < m.nv; j++) c.grad[j] = c.Ma[j] - s.qfrc_smooth[j] - c.qfrc_constraint[j];
+  for (int i = 0; i < m.nv; i++)
+    for (int j = 0; j < m.nv; j++) H[i][j] = s.M[i][j];
+  for (int r = 0; r < s.nefc; r++) {
+    if (!c.active[r] || s.D[r] == 0) continue;
+    for (int i = 0; i < m.nv; i++) {
+      if (s.J[r][i] == 0) continue;
+      real w = s.J[r][i] * s.D[r];
+      for (int j = 0; j < m.nv; j++) H[i][j] += w * s.J[r][j];
+    }
+  }
+  if (!cholesky(m.nv, H, LH)) {
+    for (int j = 0; j < m.nv; j++) c.Mgrad[j] = std::numeric_limits<real>::quiet_NaN();
+    return;
+  }
+  chol_solve(m.nv, LH, c.grad, c.Mgrad);
+}
+
+static void ctx_create(const OduckModel& m, Scratch& s, const real* qacc, Ctx& c, bool grad) {
+  for (int j = 0; j < m.nv; j++) {
+    c.qacc[j] = qacc[j];
+    real v = 0;
+    for (int k = 0; k < m.nv; k++) v += s.M[j][k] * qacc[k];
+    c.Ma[j] = v;
+    c.search[j] = 0;
+  }
+  for (int r = 0; r < s.nefc; r++) {
+    real v = 0;
+    for (int j = 0; j < m.nv; j++) v += s.J[r][j] * qacc[j];
+    c.Jaref[r] = v - s.aref[r];
+  }
+  c.cost = std::numeric_limits<real>::infinity();
+  c.prev_cost = 0;
+  update_constraint(m, s, c);
+  if (grad) {
+    update_gradient(m, s, c);
+    for (int j = 0; j < m.nv; j++) c.search[j] = -c.Mgrad[j];
+  }
+}
+
+struct LSPoint { real alpha, cost, d0, d1; };
+
+static void linesearch(const OduckModel& m, const Scratch& s, Ctx& c) {
+  real mv[NV], jv[NEFC], snorm = 0;
+  for (int j = 0; j < m.nv; j++) snorm += c.search[j] * c.search[j];
+  snorm = std::sqrt(snorm);
+  real gtol = (real)m.tolerance * (real)m.ls_tolerance * snorm * (real)m.meaninertia * std::max(1, m.nv);
+  for (int j = 0; j < m.nv; j++) {
+    real v = 0;
+    for (int k = 0; k < m.nv; k++) v += s.M[j][k] * c.search[k];
+    mv[j] = v;
+  }
+  for (int r = 0; r < s.nefc; r++) {
+    real v = 0;
+    for (int j = 0; j < m.nv; j++) v += s.J[r][j] * c.search[j];
+    jv[r] = v;
+  }
+  real qg[3] = {c.gauss, 0, 0};
+  for (int j = 0; j < m.nv; j++) { qg[1] += c.search[j] * c.Ma[j] - c.search[j] * s.qfrc_smooth[j]; qg[2] += (real)0.5 * c.search[j] * mv[j]; }
+  auto point = [&](real alpha) {
+    real q0 = qg[0], q1 = qg[1], q2 = qg[2];
+    for (int r = 0; r < s.nefc; r++) {
+      real x = c.Jaref[r] + alpha * jv[r], D = s.D[r];
+      if (s.rtype[r] == 0) {
+        real f = s.floss[r], rf = (1 / (D + (D == 0 ? kMinVal : 0))) * f;
+        if (x <= -rf) { q0 += f * (-(real)0.5 * rf - c.Jaref[r]); q1 += -f * jv[r]; }
+        else if (x >= rf) { q0 += f * (-(real)0.5 * rf + c.Jaref[r]); q1 += f * jv[r]; }
+        else { q0 += (real)0.5 * D * c.Jaref[r] * c.Jaref[r]; q1 += D * jv[r] * c.Jaref[r]; q2 += (real)0.5 * D * jv[r] * jv[r]; }
+      } else if (x < 0) {
+        q0 += (real)0.5 * D * c.Jaref[r] * c.Jaref[r]; q1 += D * jv[r] * c.Jaref[r]; q2 += (real)0.5 * D * jv[r] * jv[r];
+      }
+    }
+    LSPoint p;
+    p.alpha = alpha;
+    p.cost = alpha * alpha * q2 + alpha * q1 + q0;
+    p.d0 = 2 * alpha * q2 + q1;
+    p.d1 = 2 * q2 + (q2 == 0 ? kMinVal : 0);
+    return p;
+  };
+  LSPoint p0 = point(0);
+  LSPoint lo = point(p0.alpha - p0.d0 / p0.d1), hi;
+  if (lo.d0 < p0.d0) { hi = p0; } else { hi = lo; lo = p0; }
+  bool swap = true;
+  int it = 0;
+  while (true) {
+    bool done = it >= m.ls_iterations;
+    done |= !swap;
+    done |= (lo.d0 < 0) && (lo.d0 > -gtol);
+    done |= (hi.d0 > 0) && (hi.d0 < gtol);
+    if (done) break;
+    LSPoint lo_next = point(lo.alpha - lo.d0 / lo.d1);
+    LSPoint hi_next = point(hi.alpha - hi.d0 / hi.d1);
+    LSPoint mid = point((real)0.5 * (lo.alpha + hi.alpha));
+    bool swap_lo_next = (lo.d0 > 0) || (lo.d0 < lo_next.d0);
+    if (swap_lo_next) lo = lo_next;
+    bool swap_lo_mid = (mid.d0 < 0) && (lo.d0 < mid.d0);
+    if (swap_lo_mid) lo = mid;
+    bool swap_hi_next = (hi.d0 < 0) || (hi.d0 > hi_next.d0);
+    if (swap_hi_next) hi = hi_next;
+    bool swap_hi_mid = (mid.d0 > 0) && (hi.d0 > mid.d0);
+    if (swap_hi_mid) hi = mid;
+    swap = swap_lo_next || swap_lo_mid || swap_hi_next || swap_hi_mid;
+    it++;
+  }
+  bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
+  real alpha = lo.cost < hi.cost ? lo.alpha : hi.alpha;
+  if (improved) {
+    for (int j = 0; j < m.nv; j++) { c.qacc[j] += c.search[j] * alpha; c.Ma[j] += mv[j] * alpha; }
+    for (int r = 0; r < s.nefc; r++) c.Jaref[r] += jv[r] * alpha;
+  }
+}
+
+static void solve(const OduckModel& m, EnvState& e, Scratch& s) {
+  static thread_local Ctx warm, smth, c;
+  ctx_create(m, s, e.qacc_warm, warm, false);
+  ctx_create(m, s, s.qacc_smooth, smth, false);
+  const real* start = warm.cost < smth.cost ? e.qacc_warm : s.qacc_smooth;
+  ctx_create(m, s, start, c, true);
+  real scale = 1 / ((real)m.meaninertia * std::max(1, m.nv));
+  for (int it = 0; it < m.iterations; it++) {
+    if (m.iterations > 1) {
+      real gn = 0;
+      for (int j = 0; j < m.nv; j++) gn += c.grad[j] * c.grad[j];
+      if ((c.prev_cost - c.cost) * scale < (real)m.tolerance || std::sqrt(gn) * scale < (real)m.tolerance) break;
+    }
+    linesearch(m, s, c);
+    update_constraint(m, s, c);
+    update_gradient(m, s, c);
+    for (int j = 0; j < m.nv; j++) c.search[j] = -c.Mgrad[j];
+  }
+  for (int j = 0; j < m.nv; j++) { e.qacc[j] = c.qacc[j]; e.qacc_warm[j] = c.qacc[j]; }
+  for (int r = 0; r < NEFC; r++) e.efc_force[r] = r < s.nefc ? c.efc_force[r] : 0;
+}
+
+// ------------------------------------------------------------------------------------ forward / step
+static void sensors(const OduckModel& m, EnvState& e, Scratch& s) {
+  real cacc[NB][6];
+  rne(m, e, s, e.qacc, cacc, nullptr);
+  auto site_vel = [&](int site, real* ang, real* lin) {  // world-frame velocity of the site point
+    int b = m.site_bodyid[site];
+    real diff[3] = {s.site_xpos[site][0] - s.com[0], s.site_xpos[site][1] - s.com[1], s.site_xpos[site][2] - s.com[2]}, t[3];
+    cross3(diff, s.cvel[b], t);
+    for (int i = 0; i < 3; i++) { ang[i] = s.cvel[b][i]; lin[i] = s.cvel[b][3 + i] - t[i]; }
+  };
+  int imu = m.imu_site, ib = m.site_bodyid[imu];
+  const real* R = s.site_xmat[imu];
+  real ang[3], lin[3], angl[3], linl[3];
+  site_vel(imu, ang, lin);
+  matT_vec(R, ang, angl);
+  matT_vec(R, lin, linl);
+  real diff[3] = {s.site_xpos[imu][0] - s.com[0], s.site_xpos[imu][1] - s.com[1], s.site_xpos[imu][2] - s.com[2]}, t[3], acc[3], accl[3], corr[3];
+  cross3(diff, cacc[ib], t);
+  for (int i = 0; i < 3; i++) acc[i] = cacc[ib][3 + i] - t[i];
+  matT_vec(R, acc, accl);
+  cross3(angl, linl, corr);
+  real* sd = e.sensordata;
+  for (int i = 0; i < 3; i++) {
+    sd[0 + i] = angl[i];               // gyro
+    sd[3 + i] = linl[i];               // local_linvel (velocimeter)
+    sd[6 + i] = accl[i] + corr[i];     // accelerometer
+    sd[9 + i] = R[3 * i + 2];          // upvector (framezaxis)
+    sd[12 + i] = ang[i];               // global_angvel
+  }
+  for (int k = 0; k < 2; k++) {
+    real a2[3], l2[3];
+    site_vel(m.foot_site[k], a2, l2);
+    for (int i = 0; i < 3; i++) { sd[15 + 3 * k + i] = l2[i]; e.site_xpos_feet[3 * k + i] = s.site_xpos[m.foot_site[k]][i]; }
+  }
+  for (int i = 21; i < 24; i++) sd[i] = 0;
+  for (int i = 0; i < 9; i++) e.imu_xmat[i] = R[i];
+}
+
+static void forward(const OduckHandle& h, EnvState& e, Scratch& s) {
+  const OduckModel& m = h.m;
+  kinematics(m, e, s);
+  com_pos(m, e, s);
+  crb(m, e, s);
+  bool pd = cholesky(m.nv, s.M, s.L);
+  // collision
+  int ncon = ODUCK_CON_PER_PAIR * (2 + (m.enable_foot_foot ? 1 : 0));
+  for (int c = 0; c < NCON; c++) { s.con_dist[c] = 1; s.con_b1[c] = s.con_b2[c] = 0; s.con_mu[c] = 0; for (int i = 0; i < 3; i++) s.con_pos[c][i] = 0; for (int i = 0; i < 9; i++) s.con_frame[c][i] = (i % 4 == 0); }
+  if (!m.floor_is_hfield) {
+    plane_convex(m, s, 0, 0, s);
+    plane_convex(m, s, 1, 4, s);
+  }
+  if (m.enable_foot_foot)
+    for (int c = 8; c < 12; c++) { s.con_b1[c] = m.foot_body[0]; s.con_b2[c] = m.foot_body[1]; s.con_mu[c] = (real)m.foot_friction; }
+  (void)ncon;
+  make_constraint(h, e, s);
+  com_vel(m, e, s);
+  real cacc[NB][6];
+  rne(m, e, s, nullptr, cacc, s.qfrc_bias);
+  for (int d = 0; d < m.nv; d++) { s.qfrc_passive[d] = -(real)m.dof_damping[d] * e.qvel[d]; s.qfrc_actuator[d] = 0; }
+  for (int u = 0; u < m.nu; u++) {
+    int j = m.act_jntid[u];
+    real c = std::min(std::max(e.ctrl[u], (real)m.act_ctrlrange[u][0]), (real)m.act_ctrlrange[u][1]);
+    real f = e.act_kp[u] * c - e.act_kp[u] * e.qpos[m.jnt_qposadr[j]] - (real)m.act_kv[u] * e.qvel[m.jnt_dofadr[j]];
+    f = std::min(std::max(f, (real)m.act_forcerange[u][0]), (real)m.act_forcerange[u][1]);
+    e.actuator_force[u] = f;
+    s.qfrc_actuator[m.jnt_dofadr[j]] += f;
+  }
+  for (int d = 0; d < m.nv; d++) s.qfrc_smooth[d] = s.qfrc_passive[d] - s.qfrc_bias[d] + s.qfrc_actuator[d];
+  if (pd) chol_solve(m.nv, s.L, s.qfrc_smooth, s.qacc_smooth);
+  else for (int d = 0; d < m.nv; d++) s.qacc_smooth[d] = std::numeric_limits<real>::quiet_NaN();
+  solve(m, e, s);
+  sensors(m, e, s);
+  for (int c = 0; c < NCON; c++) e.contact_dist[c] = s.con_dist[c];
+}
+
+static void euler(const OduckModel& m, EnvState& e) {
+  real dt = (real)m.timestep;
+  for (int d = 0; d < m.nv; d++) e.qvel[d] += dt * e.qacc[d];
+  for (int j = 0; j < m.njnt; j++) {
+    int qa = m.jnt_qposadr[j], da = m.jnt_dofadr[j];
+    if (m.jnt_type[j] == ODUCK_JNT_FREE) {
+      for (int i = 0; i < 3; i++) e.qpos[qa + i] += dt * e.qvel[da + i];
+      real w[3] = {e.qvel[da + 3], e.qvel[da + 4], e.qvel[da + 5]};
+      real nrm = std::sqrt(dot3(w, w));
+      real ax[3] = {0, 0, 0};
+      if (nrm > 0) for (int i = 0; i < 3; i++) ax[i] = w[i] / nrm;
+      real ang = dt * nrm;
+      real qr[4] = {std::cos(ang / 2), std::sin(ang / 2) * ax[0], std::sin(ang / 2) * ax[1], std::sin(ang / 2) * ax[2]}, qn[4];
+      quat_mul(e.qpos + qa + 3, qr, qn);
+      quat_norm(qn);
+      for (int i = 0; i < 4; i++) e.qpos[qa + 3 + i] = qn[i];
+    } else {
+      e.qpos[qa] += dt * e.qvel[da];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ env logic
+static void poly_reference_motion(const OduckHandle& h, real dx, real dy, real dth, int i, real* out) {
+  // poly_reference_motion.py:148-168
+  const OduckEnvConfig& c = h.cfg;
+  auto nearest = [](real v, const double* grid, int n, const double* range) {
+    v = std::min(std::max(v, (real)range[0]), (real)range[1]);
+    int best = 0;
+    real bd = std::numeric_limits<real>::infinity();
+    for (int k = 0; k < n; k++) { real d = std::fabs((real)grid[k] - v); if (d < bd) { bd = d; best = k; } }
+    return best;
+  };
+  int ix = nearest(dx, c.dxs, c.ndx, c.dx_range), iy = nearest(dy, c.dys, c.ndy, c.dy_range), it = nearest(dth, c.dthetas, c.ndth, c.dtheta_range);
+  real t = (real)(i % c.nb_steps_in_period) / (real)c.nb_steps_in_period;
+  t = std::min(std::max(t, (real)0), (real)1);
+  const double* base = h.poly.data() + (((size_t)ix * c.ndy + iy) * c.ndth + it) * ODUCK_REF_DIM * ODUCK_POLY_DEG;
+  for (int d = 0; d < ODUCK_REF_DIM; d++) {
+    real acc = 0;
+    for (int k = 0; k < ODUCK_POLY_DEG; k++) acc = acc * t + (real)base[d * ODUCK_POLY_DEG + k];
+    out[d] = acc;
+  }
+}
+
+static void sample_command(const OduckHandle& h, Key rng, real* cmd) {  // joystick.py:671-725
+  const OduckEnvConfig& c = h.cfg;
+  Key k[8];
+  for (int i = 0; i < 8; i++) k[i] = key_split(rng, i);
+  const int which[7] = {0, 1, 2, 4, 5, 6, 7};
+  for (int i = 0; i < 7; i++) cmd[i] = key_uniform(k[which[i]], 0, (real)c.cmd_range[i][0], (real)c.cmd_range[i][1]);
+  bool zero = key_uniform(k[3], 0, 0, 1) < (real)0.1;
+  if (zero) for (int i = 0; i < 7; i++) cmd[i] = 0;
+}
+
+static real nan_to_num(real x) {
+  if (std::isnan(x)) return 0;
+  if (std::isinf(x)) return x > 0 ? std::numeric_limits<float>::max() : -std::numeric_limits<float>::max();
+  return x;
+}
+
+static void actuated(const OduckModel& m, const real* qpos, const real* qvel, real* q, real* qd) {
+  for (int u = 0; u < m.nu; u++) { int j = m.act_jntid[u]; if (q) q[u] = qpos[m.jnt_qposadr[j]]; if (qd) qd[u] = qvel[m.jnt_dofadr[j]]; }
+}
+
+// joystick.py:487-620.  Advances e.rng exactly as the reference (5 splits).
+static void get_obs(const OduckHandle& h, EnvState& e, const real* contact) {
+  const OduckModel& m = h.m;
+  const OduckEnvConfig& c = h.cfg;
+  const real* sd = e.sensordata;
+  real lvl = (real)c.noise_level;
+  auto split_noise = [&]() { Key nk = key_split(e.rng, 1); e.rng = key_split(e.rng, 0); return nk; };
+  Key nk = split_noise();
+  real noisy_gyro[3], noisy_acc[3], gravity[3], noisy_grav[3];
+  for (int i = 0; i < 3; i++) noisy_gyro[i] = sd[i] + (2 * key_uniform(nk, i, 0, 1) - 1) * lvl * (real)c.noise_gyro;
+  nk = split_noise();  // accelerometer: the +1.3 bias of joystick.py:502 is discarded by the reference (quirk #2)
+  for (int i = 0; i < 3; i++) noisy_acc[i] = sd[6 + i] + (2 * key_uniform(nk, i, 0, 1) - 1) * lvl * (real)c.noise_accelerometer;
+  for (int i = 0; i < 3; i++) gravity[i] = -e.imu_xmat[6 + i];  // site_xmat.T @ [0,0,-1]
+  nk = split_noise();
+  for (int i = 0; i < 3; i++) noisy_grav[i] = gravity[i] + (2 * key_uniform(nk, i, 0, 1) - 1) * lvl * (real)c.noise_gravity;
+  int nh = c.imu_max_delay * 3;
+  for (int i = nh - 1; i >= 3; i--) e.imu_history[i] = e.imu_history[i - 3];  // jp.roll(hist, 3).at[:3].set(...)
+  for (int i = 0; i < 3 && i < nh; i++) e.imu_history[i] = noisy_grav[i];
+  (void)key_randint(nk, c.imu_min_delay, c.imu_max_delay);  // imu delay index: computed, never observed (quirk #4)
+  real q[NU], qd[NU], ja[NU];
+  actuated(m, e.qpos, e.qvel, q, qd);
+  for (int u = 0; u < m.nu; u++) {
+    ja[u] = q[u];
+    // backlash joint = the joint right after the actuated one on the same body (base.py:121-125, joystick.py:535-541)
+    int j = m.act_jntid[u];
+    if (j + 1 < m.njnt && m.jnt_bodyid[j + 1] == m.jnt_bodyid[j] && m.jnt_type[j + 1] == ODUCK_JNT_HINGE) ja[u] += e.qpos[m.jnt_qposadr[j + 1]];
+  }
+  real nja[NU], njv[NU];
+  nk = split_noise();
+  for (int u = 0; u < m.nu; u++) nja[u] = ja[u] + (2 * key_uniform(nk, u, 0, 1) - 1) * lvl * (real)c.qpos_noise_scale[u];
+  nk = split_noise();
+  for (int u = 0; u < m.nu; u++) njv[u] = qd[u] + (2 * key_uniform(nk, u, 0, 1) - 1) * lvl * (real)c.noise_joint_vel;
+  real* o = e.obs_state;
+  int p = 0;
+  for (int i = 0; i < 3; i++) o[p++] = noisy_gyro[i];
+  for (int i = 0; i < 3; i++) o[p++] = noisy_acc[i];
+  for (int i = 0; i < 7; i++) o[p++] = e.command[i];
+  for (int u = 0; u < m.nu; u++) o[p++] = nja[u] - (real)m.key_ctrl[u];
+  for (int u = 0; u < m.nu; u++) o[p++] = njv[u] * (real)c.dof_vel_scale;
+  for (int k = 0; k < 3; k++) for (int u = 0; u < m.nu; u++) o[p++] = e.last_act[k][u];
+  for (int u = 0; u < m.nu; u++) o[p++] = e.motor_targets[u];
+  for (int i = 0; i < 2; i++) o[p++] = contact[i];
+  for (int i = 0; i < 2; i++) o[p++] = e.imitation_phase[i];
+  real* pr = e.obs_priv;
+  int r = 0;
+  for (int i = 0; i < p; i++) pr[r++] = o[i];
+  for (int i = 0; i < 3; i++) pr[r++] = sd[i];
+  for (int i = 0; i < 3; i++) pr[r++] = sd[6 + i];
+  for (int i = 0; i < 3; i++) pr[r++] = gravity[i];
+  for (int i = 0; i < 3; i++) pr[r++] = sd[3 + i];
+  for (int i = 0; i < 3; i++) pr[r++] = sd[12 + i];
+  for (int u = 0; u < m.nu; u++) pr[r++] = ja[u] - (real)m.key_ctrl[u];
+  for (int u = 0; u < m.nu; u++) pr[r++] = qd[u];
+  pr[r++] = e.qpos[2];
+  for (int u = 0; u < m.nu; u++) pr[r++] = e.actuator_force[u];
+  for (int i = 0; i < 2; i++) pr[r++] = contact[i];
+  for (int i = 0; i < 6; i++) pr[r++] = sd[15 + i];  // [left, right] foot linvel (joystick.py:173-181)
+  for (int i = 0; i < 2; i++) pr[r++] = e.feet_air_time[i];
+  for (int i = 0; i < ODUCK_REF_DIM; i++) pr[r++] = e.ref_motion[i];
+  pr[r++] = (real)e.imitation_i;
+  for (int i = 0; i < 2; i++) pr[r++] = e.imitation_phase[i];
+}
+
+static void geoms_colliding(const EnvState& e, real* contact) {
+  for (int k = 0; k < 2; k++) {
+    real dmin = (real)1e4;
+    for (int c = 0; c < 4; c++) dmin = std::min(dmin, e.contact_dist[4 * k + c]);
+    contact[k] = dmin < 0 ? 1 : 0;
+  }
+}
+
+static void env_reset(OduckHandle& h, EnvState& e, Key rng) {  // joystick.py:206-321
+  const OduckModel& m = h.m;
+  const OduckEnvConfig& c = h.cfg;
+  static thread_local Scratch s;
+  for (int i = 0; i < m.nq; i++) e.qpos[i] = (real)m.key_qpos[i];
+  for (int i = 0; i < m.nv; i++) { e.qvel[i] = 0; e.qacc_warm[i] = 0; e.qacc[i] = 0; }
+  Key key;
+  key = key_split(rng, 1); rng = key_split(rng, 0);
+  for (int i = 0; i < 2; i++) e.qpos[i] = (real)m.key_qpos[i] + key_uniform(key, i, (real)-0.05, (real)0.05);
+  key = key_split(rng, 1); rng = key_split(rng, 0);
+  real yaw = key_uniform(key, 0, (real)-3.14, (real)3.14);
+  real qy[4] = {std::cos(yaw / 2), 0, 0, std::sin(yaw / 2)}, q0[4] = {(real)m.key_qpos[3], (real)m.key_qpos[4], (real)m.key_qpos[5], (real)m.key_qpos[6]}, qn[4];
+  quat_mul(q0, qy, qn);
+  for (int i = 0; i < 4; i++) e.qpos[3 + i] = qn[i];
+  key = key_split(rng, 1); rng = key_split(rng, 0);
+  for (int u = 0; u < m.nu; u++) { int qa = m.jnt_qposadr[m.act_jntid[u]]; e.qpos[qa] = e.qpos[qa] * key_uniform(key, u, (real)0.5, (real)1.5); }
+  key = key_split(rng, 1); rng = key_split(rng, 0);
+  for (int i = 0; i < 6; i++) e.qvel[i] = key_uniform(key, i, (real)-0.05, (real)0.05);
+  for (int u = 0; u < m.nu; u++) e.ctrl[u] = e.qpos[m.jnt_qposadr[m.act_jntid[u]]];
+  forward(h, e, s);  // mjx_env.init
+  Key cmd_rng = key_split(rng, 1); rng = key_split(rng, 0);
+  sample_command(h, cmd_rng, e.command);
+  Key push_rng = key_split(rng, 1); rng = key_split(rng, 0);
+  real pi_ = key_uniform(push_rng, 0, (real)c.push_interval_range[0], (real)c.push_interval_range[1]);
+  e.push_interval_steps = (int32_t)std::nearbyint(pi_ / (real)c.ctrl_dt);
+  if (c.use_imitation_reward) poly_reference_motion(h, e.command[0], e.command[1], e.command[2], 0, e.ref_motion);
+  else for (int i = 0; i < ODUCK_REF_DIM; i++) e.ref_motion[i] = 0;
+  e.rng = rng;
+  e.step = 0; e.steps = 0; e.push_step = 0; e.imitation_i = 0;
+  for (int k = 0; k < 3; k++) for (int u = 0; u < NU; u++) e.last_act[k][u] = 0;
+  for (int u = 0; u < m.nu; u++) e.motor_targets[u] = (real)m.key_ctrl[u];
+  for (int i = 0; i < 2; i++) { e.feet_air_time[i] = 0; e.last_contact[i] = 0; e.swing_peak[i] = 0; e.push[i] = 0; e.imitation_phase[i] = 0; }
+  for (int i = 0; i < 8 * NU; i++) e.action_history[i] = 0;
+  for (int i = 0; i < 24; i++) e.imu_history[i] = 0;
+  for (int i = 0; i < ODUCK_NMETRIC; i++) e.metrics[i] = 0;
+  real contact[2];
+  geoms_colliding(e, contact);
+  get_obs(h, e, contact);
+  e.reward = 0; e.done = 0; e.truncation = 0;
+  // BraxAutoResetWrapper.reset: first_state / first_obs
+  for (int i = 0; i < NQ; i++) e.first_qpos[i] = e.qpos[i];
+  for (int i = 0; i < NV; i++) { e.first_qvel[i] = e.qvel[i]; e.first_qacc_warm[i] = e.qacc_warm[i]; }
+  for (int i = 0; i < ODUCK_OBS_STATE; i++) e.first_obs_state[i] = e.obs_state[i];
+  for (int i = 0; i < ODUCK_OBS_PRIV; i++) e.first_obs_priv[i] = e.obs_priv[i];
+}
+
+static void env_step(OduckHandle& h, EnvState& e, const float* action_f) {  // joystick.py:323-481 + wrappers
+  const OduckModel& m = h.m;
+  const OduckEnvConfig& c = h.cfg;
+  static thread_local Scratch s;
+  const real pi = (real)3.14159265358979323846;
+  real action[NU];
+  for (int u = 0; u < m.nu; u++) action[u] = (real)action_f[u];
+  // AutoResetWrapper.step prologue: steps = where(done, 0, steps); done = 0
+  if (e.done != 0) e.steps = 0;
+  real dt = (real)c.ctrl_dt;
+  if (c.use_imitation_reward) {
+    e.imitation_i = (e.imitation_i + 1) % c.nb_steps_in_period;
+    real ph = ((real)e.imitation_i / (real)c.nb_steps_in_period) * 2 * pi;
+    e.imitation_phase[0] = std::cos(ph);
+    e.imitation_phase[1] = std::sin(ph);
+    poly_reference_motion(h, e.command[0], e.command[1], e.command[2], e.imitation_i, e.ref_motion);
+  } else {
+    e.imitation_i = 0;
+  }
+  Key push1 = key_split(e.rng, 1), push2 = key_split(e.rng, 2), delay = key_split(e.rng, 3);
+  e.rng = key_split(e.rng, 0);
+  int nh = c.action_max_delay * m.nu;
+  for (int i = nh - 1; i >= m.nu; i--) e.action_history[i] = e.action_history[i - m.nu];
+  for (int u = 0; u < m.nu && u < nh; u++) e.action_history[u] = action[u];
+  int aidx = key_randint(delay, c.action_min_delay, c.action_max_delay);
+  const real* act_delayed = e.action_history + aidx * m.nu;
+  real theta = key_uniform(push1, 0, 0, 2 * pi);
+  real mag = key_uniform(push2, 0, (real)c.push_magnitude_range[0], (real)c.push_magnitude_range[1]);
+  real push[2] = {std::cos(theta), std::sin(theta)};
+  bool fire = ((e.push_step + 1) % e.push_interval_steps) == 0;  // jp.mod of positive ints
+  for (int i = 0; i < 2; i++) { push[i] *= fire ? 1 : 0; push[i] *= c.push_enable ? 1 : 0; e.qvel[i] += push[i] * mag; }
+  real targets[NU];
+  for (int u = 0; u < m.nu; u++) {
+    targets[u] = (real)m.key_ctrl[u] + act_delayed[u] * (real)c.action_scale;
+    if (c.use_motor_speed_limits) {
+      real lim = (real)c.max_motor_velocity * dt;
+      targets[u] = std::min(std::max(targets[u], e.motor_targets[u] - lim), e.motor_targets[u] + lim);
+    }
+  }
+  for (int u = 0; u < m.nu; u++) e.ctrl[u] = targets[u];
+  for (int k = 0; k < c.n_substeps; k++) { forward(h, e, s); euler(m, e); }
+  for (int u = 0; u < m.nu; u++) e.motor_targets[u] = targets[u];
+  real contact[2], first_contact[2];
+  geoms_colliding(e, contact);
+  for (int i = 0; i < 2; i++) {
+    real filt = (contact[i] != 0 || e.last_contact[i] != 0) ? 1 : 0;
+    first_contact[i] = (e.feet_air_time[i] > 0 ? 1 : 0) * filt;
+    e.feet_air_time[i] += dt;
+    e.swing_peak[i] = std::max(e.swing_peak[i], e.site_xpos_feet[3 * i + 2]);
+  }
+  (void)first_contact;
+  get_obs(h, e, contact);
+  bool nan_state = false;
+  for (int i = 0; i < m.nq; i++) nan_state |= std::isnan(e.qpos[i]);
+  for (int i = 0; i < m.nv; i++) nan_state |= std::isnan(e.qvel[i]);
+  bool done = (e.sensordata[9 + 2] < 0) || nan_state;
+  // rewards (common/rewards.py, custom_rewards.py)
+  const real* sd = e.sensordata;
+  real q[NU], qd[NU];
+  actuated(m, e.qpos, e.qvel, q, qd);
+  real r_lin, r_ang, c_torque = 0, c_rate = 0, c_still, r_alive = 1, r_imit = 0;
+  {
+    real ex = (e.command[0] - sd[3]) * (e.command[0] - sd[3]);
+    real ey = std::max(std::fabs(sd[4] - e.command[1]) - (real)0.1, (real)0);
+    r_lin = nan_to_num(std::exp(-(ex + ey * ey) / (real)c.tracking_sigma));
+    real ea = (e.command[2] - sd[2]) * (e.command[2] - sd[2]);
+    r_ang = nan_to_num(std::exp(-ea / (real)c.tracking_sigma));
+    for (int u = 0; u < m.nu; u++) { c_torque += e.actuator_force[u] * e.actuator_force[u]; real d = action[u] - e.last_act[0][u]; c_rate += d * d; }
+    c_torque = nan_to_num(c_torque);
+    c_rate = nan_to_num(c_rate);
+    real cmd_norm = std::sqrt(e.command[0] * e.command[0] + e.command[1] * e.command[1] + e.command[2] * e.command[2]);
+    real pose = 0, vel = 0;
+    for (int u = 0; u < m.nu; u++) { pose += std::fabs(q[u] - (real)m.key_ctrl[u]); vel += std::fabs(qd[u]); }
+    c_still = nan_to_num(pose + vel) * (cmd_norm < (real)0.01 ? 1 : 0);
+    if (c.use_imitation_reward) {
+      const real* ref = e.ref_motion;
+      real lxy = (e.qvel[0] - ref[34]) * (e.qvel[0] - ref[34]) + (e.qvel[1] - ref[35]) * (e.qvel[1] - ref[35]);
+      real lz = (e.qvel[2] - ref[36]) * (e.qvel[2] - ref[36]);
+      real axy = (e.qvel[3] - ref[37]) * (e.qvel[3] - ref[37]) + (e.qvel[4] - ref[38]) * (e.qvel[4] - ref[38]);
+      real az = (e.qvel[5] - ref[39]) * (e.qvel[5] - ref[39]);
+      real jp_ = 0, jv_ = 0;
+      for (int k = 0; k < 10; k++) {
+        int u = k < 5 ? k : k + 4;       // joints_qpos[:5] ++ joints_qpos[9:]
+        int rr = k < 5 ? k : k + 6;      // ref[:5] ++ ref[11:16]
+        jp_ += (q[u] - ref[rr]) * (q[u] - ref[rr]);
+        jv_ += (qd[u] - ref[16 + rr]) * (qd[u] - ref[16 + rr]);
+      }
+      real crew = 0;
+      for (int i = 0; i < 2; i++) crew += (contact[i] == (ref[32 + i] > (real)0.5 ? (real)1 : (real)0)) ? 1 : 0;
+      real rew = std::exp(-8 * lxy) + std::exp(-8 * lz) + (real)0.5 * std::exp(-2 * axy) + (real)0.5 * std::exp(-2 * az) - 15 * jp_ - (real)1e-3 * jv_ + crew;
+      rew *= cmd_norm > (real)0.01 ? 1 : 0;
+      r_imit = nan_to_num(rew);
+    }
+  }
+  real sc[7] = {r_lin * (real)c.scale_tracking_lin_vel, r_ang * (real)c.scale_tracking_ang_vel, c_torque * (real)c.scale_torques,
+                c_rate * (real)c.scale_action_rate, c_still * (real)c.scale_stand_still, r_alive * (real)c.scale_alive, r_imit * (real)c.scale_imitation};
+  // sum order of the rewards dict (joystick.py:634-667): lin, ang, torques, action_rate, alive, imitation, stand_still
+  real total = sc[0] + sc[1] + sc[2] + sc[3] + sc[5] + sc[6] + sc[4];
+  real reward = std::min(std::max(total * dt, (real)0), (real)10000);
+  for (int i = 0; i < 2; i++) e.push[i] = push[i];
+  e.step += 1;
+  e.push_step += 1;
+  for (int u = 0; u < m.nu; u++) { e.last_act[2][u] = e.last_act[1][u]; e.last_act[1][u] = e.last_act[0][u]; e.last_act[0][u] = action[u]; }
+  Key cmd_rng = key_split(e.rng, 1);
+  e.rng = key_split(e.rng, 0);
+  if (e.step > 500) sample_command(h, cmd_rng, e.command);
+  if (done || e.step > 500) e.step = 0;
+  for (int i = 0; i < 2; i++) {
+    real nc = contact[i] != 0 ? 0 : 1;
+    e.feet_air_time[i] *= nc;
+    e.last_contact[i] = contact[i];
+    e.swing_peak[i] *= nc;
+  }
+  // metrics: reward/<k> = v, cost/<k> = -v for negative scales (joystick.py:470-477)
+  const double scales[7] = {c.scale_tracking_lin_vel, c.scale_tracking_ang_vel, c.scale_torques, c.scale_action_rate, c.scale_stand_still, c.scale_alive, c.scale_imitation};
+  for (int k = 0; k < 7; k++) e.metrics[k] = scales[k] == 0 ? 0 : (scales[k] > 0 ? sc[k] : -sc[k]);
+  e.metrics[7] = (e.swing_peak[0] + e.swing_peak[1]) / 2;
+  e.reward = reward;
+  // EpisodeWrapper.step (action_repeat = 1)
+  e.steps += 1;
+  real d = done ? 1 : 0;
+  bool trunc = e.steps >= c.episode_length;
+  e.truncation = trunc ? 1 - d : 0;
+  e.done = trunc ? 1 : d;
+  // BraxAutoResetWrapper.step: data/obs <- first_state where done (info is NOT reset)
+  if (c.auto_reset && e.done != 0) {
+    for (int i = 0; i < NQ; i++) e.qpos[i] = e.first_qpos[i];
+    for (int i = 0; i < NV; i++) { e.qvel[i] = e.first_qvel[i]; e.qacc_warm[i] = e.first_qacc_warm[i]; }
+    for (int i = 0; i < ODUCK_OBS_STATE; i++) e.obs_state[i] = e.first_obs_state[i];
+    for (int i = 0; i < ODUCK_OBS_PRIV; i++) e.obs_priv[i] = e.first_obs_priv[i];
+  }
+}
+
+static void env_randomize(OduckHandle& h, EnvState& e, Key rng) {  // common/randomize.py:39-106
+  const OduckModel& m = h.m;
+  Key key;
+  key = key_split(rng, 1); rng = key_split(rng, 0);
+  e.dr_geom_friction0 = key_uniform(key, 0, (real)0.5, (real)1.0);
+  key = key_split(rng, 1); rng = key_split(rng, 0);
+  for (int i = 0; i < h.nefc_fr; i++) e.dof_frictionloss[h.fr_dof[i]] = (real)m.dof_frictionloss[h.fr_dof[i]] * key_uniform(key, i, (real)0.9, (real)1.1);
+  key = key_split(rng, 1); rng = key_split(rng, 0);
+  for (int i = 0; i < h.nefc_fr; i++) e.dof_armature[h.fr_dof[i]] = (real)m.dof_armature[h.fr_dof[i]] * key_uniform(key, i, (real)1.0, (real)1.05);
+  key = key_split(rng, 1); rng = key_split(rng, 0);
+  for (int i = 0; i < 3; i++) e.body_ipos[1][i] = (real)m.body_ipos[1][i] + key_uniform(key, i, (real)-0.05, (real)0.05);
+  key = key_split(rng, 1); rng = key_split(rng, 0);
+  for (int b = 0; b < m.nbody; b++) e.body_mass[b] = (real)m.body_mass[b] * key_uniform(key, b, (real)0.9, (real)1.1);
+  key = key_split(rng, 1); rng = key_split(rng, 0);
+  e.body_mass[1] += key_uniform(key, 0, (real)-0.1, (real)0.1);
+  key = key_split(rng, 1); rng = key_split(rng, 0);
+  for (int i = 0; i < h.nefc_fr; i++) { int qa = m.jnt_qposadr[m.dof_jntid[h.fr_dof[i]]]; e.qpos0[qa] = (real)m.qpos0[qa] + key_uniform(key, i, (real)-0.03, (real)0.03); }
+  key = key_split(rng, 1); rng = key_split(rng, 0);
+  for (int u = 0; u < m.nu; u++) e.act_kp[u] = (real)m.act_kp[u] * key_uniform(key, u, (real)0.9, (real)1.1);
+}
+
+static void env_nominal(const OduckHandle& h, EnvState& e) {
+  const OduckModel& m = h.m;
+  std::memset(&e, 0, sizeof(e));
+  e.dr_geom_friction0 = 1;
+  for (int b = 0; b < NB; b++) { e.body_mass[b] = (real)m.body_mass[b]; for (int i = 0; i < 3; i++) e.body_ipos[b][i] = (real)m.body_ipos[b][i]; }
+  for (int d = 0; d < NV; d++) { e.dof_frictionloss[d] = (real)m.dof_frictionloss[d]; e.dof_armature[d] = (real)m.dof_armature[d]; }
+  for (int i = 0; i < NQ; i++) { e.qpos0[i] = (real)m.qpos0[i]; e.qpos[i] = (real)m.key_qpos[i]; e.first_qpos[i] = e.qpos[i]; }
+  for (int u = 0; u < NU; u++) { e.act_kp[u] = (real)m.act_kp[u]; e.ctrl[u] = (real)m.key_ctrl[u]; }
+  e.push_interval_steps = 1 << 30;
+  for (int c = 0; c < NCON; c++) e.contact_dist[c] = 1;
+}
+
+// ------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+int oduck_abi_version(void) { return ODUCK_ABI_VERSION; }
+int oduck_sizeof_model(void) { return (int)sizeof(OduckModel); }
+int oduck_sizeof_env_config(void) { return (int)sizeof(OduckEnvConfig); }
+const char* oduck_last_error(void) { return g_err.c_str(); }
+
+int oduck_create(const OduckModel* model, const OduckEnvConfig* cfg, int num_envs, int device, OduckHandle** out) {
+  (void)device;
+  if (!model || !cfg || !out || num_envs <= 0) return fail(ODUCK_ERR_ARG, "oduck_create: bad argument");
+  if (model->abi_version != ODUCK_ABI_VERSION) return fail(ODUCK_ERR_MODEL, "oduck_create: model ABI version mismatch");
+  if (model->nv > NV || model->nq > NQ || model->nbody > NB || model->nu > NU) return fail(ODUCK_ERR_MODEL, "oduck_create: model too large");
+  if (model->floor_is_hfield) return fail(ODUCK_ERR_UNSUPPORTED, "oduck_create: height-field floor not implemented yet");
+  if (cfg->action_max_delay > 8 || cfg->imu_max_delay > 8) return fail(ODUCK_ERR_ARG, "oduck_create: delay history too long");
+  OduckHandle* h = new OduckHandle();
+  h->m = *model;
+  h->cfg = *cfg;
+  size_t npoly = (size_t)cfg->ndx * cfg->ndy * cfg->ndth * ODUCK_REF_DIM * ODUCK_POLY_DEG;
+  if (cfg->use_imitation_reward) {
+    if (!cfg->poly_coef || npoly == 0) { delete h; return fail(ODUCK_ERR_ARG, "oduck_create: imitation reward needs poly_coef"); }
+    h->poly.assign(cfg->poly_coef, cfg->poly_coef + npoly);
+  }
+  h->cfg.poly_coef = nullptr;
+  h->n = num_envs;
+  h->launches = 0;
+  h->nefc_fr = h->nefc_lim = 0;
+  for (int d = 0; d < model->nv; d++) if (model->dof_frictionloss[d] > 0) h->fr_dof[h->nefc_fr++] = d;
+  for (int j = 0; j < model->njnt; j++) if (model->jnt_limited[j] && model->jnt_type[j] == ODUCK_JNT_HINGE) h->lim_jnt[h->nefc_lim++] = j;
+  h->env.resize(num_envs);
+  for (auto& e : h->env) env_nominal(*h, e);
+  *out = h;
+  return ODUCK_OK;
+}
+int oduck_destroy(OduckHandle* h) { delete h; return ODUCK_OK; }
+int oduck_num_envs(const OduckHandle* h) { return h ? h->n : 0; }
+int64_t oduck_launch_count(const OduckHandle* h) { return h ? h->launches : 0; }
+
+int oduck_randomize(OduckHandle* h, const uint32_t* keys, void*) {
+  if (!h || !keys) return fail(ODUCK_ERR_ARG, "oduck_randomize: bad argument");
+  pfor(h->n, [&](int i) { env_randomize(*h, h->env[i], Key{keys[2 * i], keys[2 * i + 1]}); });
+  return ODUCK_OK;
+}
+int oduck_reset(OduckHandle* h, const uint32_t* keys, const uint8_t* mask, void*) {
+  if (!h || !keys) return fail(ODUCK_ERR_ARG, "oduck_reset: bad argument");
+  pfor(h->n, [&](int i) { if (!mask || mask[i]) env_reset(*h, h->env[i], Key{keys[2 * i], keys[2 * i + 1]}); });
+  return ODUCK_OK;
+}
+int oduck_step(OduckHandle* h, const float* action, void*) {
+  if (!h || !action) return fail(ODUCK_ERR_ARG, "oduck_step: bad argument");
+  pfor(h->n, [&](int i) { env_step(*h, h->env[i], action + (size_t)i * h->m.nu); });
+  return ODUCK_OK;
+}
+int oduck_physics_substeps(OduckHandle* h, const float* ctrl, int n, void*) {
+  if (!h || n < 0) return fail(ODUCK_ERR_ARG, "oduck_physics_substeps: bad argument");
+  pfor(h->n, [&](int i) {
+    static thread_local Scratch s;
+    EnvState& e = h->env[i];
+    if (ctrl) for (int u = 0; u < h->m.nu; u++) e.ctrl[u] = (real)ctrl[(size_t)i * h->m.nu + u];
+    for (int k = 0; k < n; k++) { forward(*h, e, s); euler(h->m, e); }
+  });
+  return ODUCK_OK;
+}
+int oduck_forward(OduckHandle* h, void*) {
+  if (!h) return fail(ODUCK_ERR_ARG, "oduck_forward: bad argument");
+  pfor(h->n, [&](int i) { { static thread_local Scratch s; forward(*h, h->env[i], s); } });
+  return ODUCK_OK;
+}
+int oduck_set_state(OduckHandle* h, const float* qpos, const float* qvel, const float* qacc_warm, void*) {
+  if (!h) return fail(ODUCK_ERR_ARG, "oduck_set_state: bad argument");
+  for (int i = 0; i < h->n; i++) {
+    EnvState& e = h->env[i];
+    if (qpos) for (int k = 0; k < h->m.nq; k++) e.qpos[k] = (real)qpos[(size_t)i * h->m.nq + k];
+    if (qvel) for (int k = 0; k < h->m.nv; k++) e.qvel[k] = (real)qvel[(size_t)i * h->m.nv + k];
+    if (qacc_warm) for (int k = 0; k < h->m.nv; k++) e.qacc_warm[k] = (real)qacc_warm[(size_t)i * h->m.nv + k];
+  }
+  return ODUCK_OK;
+}
+
+// Brax policy MLP: normalise -> 3 x (Dense + swish) -> Dense -> NormalTanhDistribution (common/export_onnx.py:64-72)
+int oduck_policy_forward(OduckHandle* h, const OduckPolicyWeights* w, const float* obs, const uint32_t* keys, int deterministic,
+                         float* action, float* raw_action, float* log_prob, void*) {
+  if (!h || !w) return fail(ODUCK_ERR_ARG, "oduck_policy_forward: bad argument");
+  if (!deterministic && !keys) return fail(ODUCK_ERR_ARG, "oduck_policy_forward: stochastic policy needs keys");
+  int dims[5] = {w->obs_dim, w->hidden[0], w->hidden[1], w->hidden[2], w->out_dim};
+  int na = w->out_dim / 2;
+  pfor(h->n, [&](int i) {
+    std::vector<real> x(dims[0]), y;
+    for (int k = 0; k < dims[0]; k++) {
+      real o = obs ? (real)obs[(size_t)i * dims[0] + k] : h->env[i].obs_state[k];
+      x[k] = (o - (real)w->obs_mean[k]) / (real)w->obs_std[k];
+    }
+    for (int l = 0; l < 4; l++) {
+      y.assign(dims[l + 1], 0);
+      for (int o = 0; o < dims[l + 1]; o++) {
+        real acc = (real)w->b[l][o];
+        for (int k = 0; k < dims[l]; k++) acc += x[k] * (real)w->w[l][(size_t)k * dims[l + 1] + o];
+        y[o] = l < 3 ? acc / (1 + std::exp(-acc)) : acc;
+      }
+      x = y;
+    }
+    real lp = 0;
+    for (int a = 0; a < na; a++) {
+      real loc = x[a], scale = std::log1p(std::exp(x[na + a])) + (real)0.001;  // softplus + min_std
+      real raw = loc;
+      if (!deterministic) {
+        // standard normal from two uniforms of the per-env key (Box-Muller); the reference draws jax.random.normal
+        Key k = Key{keys[2 * i], keys[2 * i + 1]};
+        real u1 = std::max(bits_to_unit(key_bits(k, 2 * a)), (real)1e-7), u2 = bits_to_unit(key_bits(k, 2 * a + 1));
+        real z = std::sqrt(-2 * std::log(u1)) * std::cos(2 * (real)3.14159265358979323846 * u2);
+        raw = loc + scale * z;
+        real lpn = -(real)0.5 * z * z - std::log(scale) - (real)0.5 * std::log(2 * (real)3.14159265358979323846);
+        real ldj = 2 * (std::log((real)2) - raw - std::log1p(std::exp(-2 * raw)));
+        lp += lpn - ldj;
+      }
+      if (action) action[(size_t)i * na + a] = (float)std::tanh(raw);
+      if (raw_action) raw_action[(size_t)i * na + a] = (float)raw;
+    }
+    if (log_prob) log_prob[i] = (float)lp;
+  });
+  return ODUCK_OK;
+}
+
+int oduck_get_buffer(OduckHandle* h, int id, void** ptr, int64_t* shape, int64_t* strides, int* dtype) {
+  if (!h || !ptr || !shape || !strides || !dtype) return fail(ODUCK_ERR_ARG, "oduck_get_buffer: bad argument");
+  EnvState* e0 = h->env.data();
+  const OduckModel& m = h->m;
+  const int64_t es = sizeof(EnvState) / sizeof(real);
+  static_assert(sizeof(EnvState) % sizeof(real) == 0, "EnvState must be a whole number of reals");
+  int64_t d1 = 0, d2 = 0, s1 = 1, s2 = 1;
+  void* p = nullptr;
+  int dt = sizeof(real) == 8 ? ODUCK_DTYPE_F64 : ODUCK_DTYPE_F32;
+  const int64_t es32 = sizeof(EnvState) / 4;
+  bool is32 = false;
+#define FIELD(f, n1) p = (void*)(e0->f); d1 = (n1);
+  switch (id) {
+    case ODUCK_BUF_QPOS: FIELD(qpos, m.nq) break;
+    case ODUCK_BUF_QVEL: FIELD(qvel, m.nv) break;
+    case ODUCK_BUF_QACC_WARM: FIELD(qacc_warm, m.nv) break;
+    case ODUCK_BUF_QACC: FIELD(qacc, m.nv) break;
+    case ODUCK_BUF_CTRL: FIELD(ctrl, m.nu) break;
+    case ODUCK_BUF_OBS_STATE: FIELD(obs_state, ODUCK_OBS_STATE) break;
+    case ODUCK_BUF_OBS_PRIV: FIELD(obs_priv, ODUCK_OBS_PRIV) break;
+    case ODUCK_BUF_REWARD: p = &e0->reward; break;
+    case ODUCK_BUF_DONE: p = &e0->done; break;
+    case ODUCK_BUF_TRUNCATION: p = &e0->truncation; break;
+    case ODUCK_BUF_METRICS: FIELD(metrics, ODUCK_NMETRIC) break;
+    case ODUCK_BUF_EFC_FORCE: FIELD(efc_force, h->nefc_fr + h->nefc_lim + 4 * ODUCK_CON_PER_PAIR * (2 + (m.enable_foot_foot ? 1 : 0))) break;
+    case ODUCK_BUF_CONTACT_DIST: FIELD(contact_dist, NCON) break;
+    case ODUCK_BUF_SENSORDATA: FIELD(sensordata, 24) break;
+    case ODUCK_BUF_ACTUATOR_FORCE: FIELD(actuator_force, m.nu) break;
+    case ODUCK_BUF_SITE_XPOS_FEET: FIELD(site_xpos_feet, 6) break;
+    case ODUCK_BUF_INFO_RNG: p = &e0->rng; d1 = 2; dt = ODUCK_DTYPE_U32; is32 = true; break;
+    case ODUCK_BUF_INFO_COMMAND: FIELD(command, ODUCK_NCMD) break;
+    case ODUCK_BUF_INFO_STEP: p = &e0->step; dt = ODUCK_DTYPE_I32; is32 = true; break;
+    case ODUCK_BUF_INFO_STEPS: p = &e0->steps; dt = ODUCK_DTYPE_I32; is32 = true; break;
+    case ODUCK_BUF_INFO_LAST_ACT: p = (void*)e0->last_act; d1 = 3; d2 = m.nu; s1 = NU; break;
+    case ODUCK_BUF_INFO_MOTOR_TARGETS: FIELD(motor_targets, m.nu) break;
+    case ODUCK_BUF_INFO_FEET_AIR_TIME: FIELD(feet_air_time, 2) break;
+    case ODUCK_BUF_INFO_LAST_CONTACT: FIELD(last_contact, 2) break;
+    case ODUCK_BUF_INFO_SWING_PEAK: FIELD(swing_peak, 2) break;
+    case ODUCK_BUF_INFO_PUSH: FIELD(push, 2) break;
+    case ODUCK_BUF_INFO_PUSH_STEP: p = &e0->push_step; dt = ODUCK_DTYPE_I32; is32 = true; break;
+    case ODUCK_BUF_INFO_PUSH_INTERVAL: p = &e0->push_interval_steps; dt = ODUCK_DTYPE_I32; is32 = true; break;
+    case ODUCK_BUF_INFO_ACTION_HISTORY: FIELD(action_history, h->cfg.action_max_delay * m.nu) break;
+    case ODUCK_BUF_INFO_IMU_HISTORY: FIELD(imu_history, h->cfg.imu_max_delay * 3) break;
+    case ODUCK_BUF_INFO_IMITATION_I: p = &e0->imitation_i; dt = ODUCK_DTYPE_I32; is32 = true; break;
+    case ODUCK_BUF_INFO_REF_MOTION: FIELD(ref_motion, ODUCK_REF_DIM) break;
+    case ODUCK_BUF_INFO_IMITATION_PHASE: FIELD(imitation_phase, 2) break;
+    case ODUCK_BUF_DR_PARAMS: p = &e0->dr_geom_friction0; d1 = (int64_t)(offsetof(EnvState, sensordata) - offsetof(EnvState, dr_geom_friction0)) / (int64_t)sizeof(real); break;
+    case ODUCK_BUF_FIRST_QPOS: FIELD(first_qpos, m.nq) break;
+    case ODUCK_BUF_FIRST_QVEL: FIELD(first_qvel, m.nv) break;
+    case ODUCK_BUF_FIRST_OBS_STATE: FIELD(first_obs_state, ODUCK_OBS_STATE) break;
+    case ODUCK_BUF_FIRST_OBS_PRIV: FIELD(first_obs_priv, ODUCK_OBS_PRIV) break;
+    default: return fail(ODUCK_ERR_ARG, "oduck_get_buffer: unknown buffer id");
+  }
+#undef FIELD
+  *ptr = p;
+  shape[0] = h->n; shape[1] = d1; shape[2] = d2; shape[3] = 0;
+  strides[0] = is32 ? es32 : es; strides[1] = d2 ? s1 : 1; strides[2] = 1; strides[3] = 0;
+  (void)s2;
+  *dtype = dt;
+  return ODUCK_OK;
+}
+
+}  // extern "C"
