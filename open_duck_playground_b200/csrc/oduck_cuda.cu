@@ -1,0 +1,847 @@
+// oduck_cuda.cu -- liboduck_cuda.so: the B200 (sm_100a) implementation of include/oduck.h.
+// One warp per env; all per-timestep work of the reference's Joystick.step (joystick.py:323-481), including the ten
+// mjx.step substeps it calls at joystick.py:420, runs inside ONE kernel launch per env.step.  No CPU fallback.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/oduck.h"
+#include "oduck_env.cuh"
+
+#define WPB 8   // warps (= envs in flight) per CTA
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CUDA_TRY(x)                                                                                   \
+  do {                                                                                                \
+    cudaError_t e_ = (x);                                                                             \
+    if (e_ != cudaSuccess) return fail(ODUCK_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+struct Params {
+  const DevModel* model;
+  const DevEnvCfg* cfg;
+  const float* poly;
+  float *phys, *dr, *out, *info, *obs_state, *obs_priv, *reward, *done, *trunc, *metrics;
+  float *first_phys, *first_obs_state, *first_obs_priv, *dbg;
+  const float* action;     // step: [N, nu];  physics: ctrl [N, nu] or null
+  const uint32_t* keys;
+  const uint8_t* mask;
+  int N, nsub, integrate;
+};
+
+struct OduckHandle {
+  int n, device;
+  OduckModel hm;
+  OduckEnvConfig hcfg;
+  DevModel hdm;
+  DevEnvCfg hdc;
+  DevModel* dmodel;
+  DevEnvCfg* dcfg;
+  float* poly;
+  float *phys, *dr, *out, *info, *obs_state, *obs_priv, *reward, *done, *trunc, *metrics, *first_phys, *first_obs_state, *first_obs_priv, *dbg;
+  int nefc, smem_bytes, grid;
+  int64_t launches;
+};
+
+// ------------------------------------------------------------------------------------------------- device helpers
+__device__ __forceinline__ size_t smem_model_bytes() { return (sizeof(DevModel) + 15) & ~(size_t)15; }
+__device__ __forceinline__ size_t smem_cfg_bytes() { return (sizeof(DevEnvCfg) + 15) & ~(size_t)15; }
+
+__device__ __forceinline__ void block_load_tables(const Params& p, unsigned char* raw, DevModel*& m, DevEnvCfg*& c, WarpSmem*& ws) {
+  m = reinterpret_cast<DevModel*>(raw);
+  c = reinterpret_cast<DevEnvCfg*>(raw + smem_model_bytes());
+  ws = reinterpret_cast<WarpSmem*>(raw + smem_model_bytes() + smem_cfg_bytes());
+  const int* gm = reinterpret_cast<const int*>(p.model);
+  int* sm = reinterpret_cast<int*>(m);
+  for (int i = threadIdx.x; i < (int)(sizeof(DevModel) / 4); i += blockDim.x) sm[i] = gm[i];
+  const int* gc = reinterpret_cast<const int*>(p.cfg);
+  int* sc = reinterpret_cast<int*>(c);
+  for (int i = threadIdx.x; i < (int)(sizeof(DevEnvCfg) / 4); i += blockDim.x) sc[i] = gc[i];
+  __syncthreads();
+}
+
+__device__ __forceinline__ void load_env(const DevModel& m, WarpSmem& s, Lane& L, int lane, const float* __restrict__ ph, const float* __restrict__ dr) {
+  if (lane < m.nq) { s.qpos[lane] = ph[lane]; s.qpos0[lane] = dr[DR_QPOS0 + lane]; }
+  if (lane + 32 < m.nq) { s.qpos[lane + 32] = ph[lane + 32]; s.qpos0[lane + 32] = dr[DR_QPOS0 + lane + 32]; }
+  const bool isd = lane < m.nv;
+  L.qvel = isd ? ph[PHYS_QVEL + lane] : 0.f;
+  L.qaccw = isd ? ph[PHYS_QACCW + lane] : 0.f;
+  L.qacc = 0.f;
+  const int a = m.d_act[lane];
+  L.ctrl = a >= 0 ? ph[PHYS_CTRL + a] : 0.f;
+  L.kp = a >= 0 ? dr[DR_KP + a] : 0.f;
+  L.floss = isd ? dr[DR_FLOSS + lane] : 0.f;
+  L.arm = isd ? dr[DR_ARM + lane] : 0.f;
+  L.mass = lane < m.nbody ? dr[lane] : 0.f;
+  L.ipos = v3(m.b_ipos[0][lane], m.b_ipos[1][lane], m.b_ipos[2][lane]);
+  if (lane == 1) L.ipos = v3(dr[DR_IPOS1], dr[DR_IPOS1 + 1], dr[DR_IPOS1 + 2]);   // TORSO_BODY_ID = 1 (randomize.py:23)
+  __syncwarp();
+}
+__device__ __forceinline__ void store_phys(const DevModel& m, const WarpSmem& s, const Lane& L, int lane, float* __restrict__ ph) {
+  if (lane < m.nq) ph[lane] = s.qpos[lane];
+  if (lane + 32 < m.nq) ph[lane + 32] = s.qpos[lane + 32];
+  if (lane < m.nv) { ph[PHYS_QVEL + lane] = L.qvel; ph[PHYS_QACCW + lane] = L.qaccw; }
+  const int a = m.d_act[lane];
+  if (a >= 0) ph[PHYS_CTRL + a] = L.ctrl;
+}
+__device__ __forceinline__ void store_out(const WarpSmem& s, int lane, float* __restrict__ o) {
+  for (int i = lane; i < OUT_STRIDE; i += 32) o[i] = s.outrec[i];
+}
+
+// ------------------------------------------------------------------------------------------------- kernels
+// A8 / A9 of SURVEY 8a: n x (forward + euler), or one forward without integration (mjx_env.init's forward).
+template <bool DBG>
+__global__ void __launch_bounds__(WPB * 32, 2) k_physics(Params p) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  DevModel* mp; DevEnvCfg* cp; WarpSmem* ws;
+  block_load_tables(p, raw, mp, cp, ws);
+  const DevModel& m = *mp;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WarpSmem& s = ws[warp];
+  for (int env = blockIdx.x * WPB + warp; env < p.N; env += gridDim.x * WPB) {
+    Lane L;
+    float* ph = p.phys + (size_t)env * PHYS_STRIDE;
+    load_env(m, s, L, lane, ph, p.dr + (size_t)env * DR_STRIDE);
+    if (p.action) { const int a = m.d_act[lane]; if (a >= 0) L.ctrl = p.action[(size_t)env * m.nu + a]; }
+    for (int i = lane; i < OUT_STRIDE; i += 32) s.outrec[i] = 0.f;
+    __syncwarp();
+    float* dbg = DBG ? p.dbg + (size_t)env * DBG_STRIDE : nullptr;
+    for (int k = 0; k < p.nsub; ++k) forward_euler<DBG>(m, s, L, lane, k == p.nsub - 1, p.integrate != 0, s.outrec, dbg);
+    __syncwarp();
+    store_phys(m, s, L, lane, ph);
+    store_out(s, lane, p.out + (size_t)env * OUT_STRIDE);
+    __syncwarp();
+  }
+}
+
+__device__ __forceinline__ void load_info(const DevModel& m, const DevEnvCfg& c, const float* __restrict__ inf, EnvRegs& er, int lane) {
+  const int* ii = reinterpret_cast<const int*>(inf);
+  er.rng.a = (uint32_t)ii[INFO_RNG]; er.rng.b = (uint32_t)ii[INFO_RNG + 1];
+  er.step = ii[INFO_STEP]; er.steps = ii[INFO_STEPS]; er.push_step = ii[INFO_PUSH_STEP]; er.push_interval = ii[INFO_PUSH_INT];
+  er.imitation_i = ii[INFO_IMIT_I];
+  er.cmd = lane < 7 ? inf[INFO_CMD + lane] : 0.f;
+  const bool u = lane < m.nu;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) er.last_act[k] = u ? inf[INFO_LAST_ACT + 16 * k + lane] : 0.f;
+  er.targets = u ? inf[INFO_TARGETS + lane] : 0.f;
+#pragma unroll
+  for (int k = 0; k < MAX_DELAY; ++k) er.hist[k] = (u && k < c.act_max_delay) ? inf[INFO_AHIST + k * m.nu + lane] : 0.f;
+  er.air = lane < 2 ? inf[INFO_AIR + lane] : 0.f;
+  er.lastc = lane < 2 ? inf[INFO_LASTC + lane] : 0.f;
+  er.swing = lane < 2 ? inf[INFO_SWING + lane] : 0.f;
+  er.ref_lo = inf[INFO_REF + lane];
+  er.ref_hi = inf[INFO_REF + 32 + (lane & 7)];
+  er.phase = lane < 2 ? inf[INFO_PHASE + lane] : 0.f;
+}
+__device__ __forceinline__ void store_info(const DevModel& m, const DevEnvCfg& c, float* __restrict__ inf, const EnvRegs& er, float push, int lane) {
+  int* ii = reinterpret_cast<int*>(inf);
+  if (lane == 0) {
+    ii[INFO_RNG] = (int)er.rng.a; ii[INFO_RNG + 1] = (int)er.rng.b;
+    ii[INFO_STEP] = er.step; ii[INFO_STEPS] = er.steps; ii[INFO_PUSH_STEP] = er.push_step; ii[INFO_PUSH_INT] = er.push_interval;
+    ii[INFO_IMIT_I] = er.imitation_i;
+  }
+  if (lane < 7) inf[INFO_CMD + lane] = er.cmd;
+  if (lane < m.nu) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) inf[INFO_LAST_ACT + 16 * k + lane] = er.last_act[k];
+    inf[INFO_TARGETS + lane] = er.targets;
+#pragma unroll
+    for (int k = 0; k < MAX_DELAY; ++k) if (k < c.act_max_delay) inf[INFO_AHIST + k * m.nu + lane] = er.hist[k];
+  }
+  if (lane < 2) {
+    inf[INFO_AIR + lane] = er.air; inf[INFO_LASTC + lane] = er.lastc; inf[INFO_SWING + lane] = er.swing;
+    inf[INFO_PUSH + lane] = push; inf[INFO_PHASE + lane] = er.phase;
+  }
+  inf[INFO_REF + lane] = er.ref_lo;
+  if (lane < 8) inf[INFO_REF + 32 + lane] = er.ref_hi;
+}
+__device__ __forceinline__ float feet_contact(const WarpSmem& s, int lane) {   // geoms_colliding, lane k < 2
+  const int k = lane & 1;
+  const float* d = s.outrec + OUT_CDIST + 4 * k;
+  return fminf(fminf(d[0], d[1]), fminf(d[2], d[3])) < 0.f ? 1.f : 0.f;
+}
+
+// A2 (+A9, first_state store): Joystick.reset for the masked envs.
+__global__ void __launch_bounds__(WPB * 32, 2) k_reset(Params p) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  DevModel* mp; DevEnvCfg* cp; WarpSmem* ws;
+  block_load_tables(p, raw, mp, cp, ws);
+  const DevModel& m = *mp;
+  const DevEnvCfg& c = *cp;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WarpSmem& s = ws[warp];
+  for (int env = blockIdx.x * WPB + warp; env < p.N; env += gridDim.x * WPB) {
+    if (p.mask && !p.mask[env]) continue;
+    Lane L;
+    float* ph = p.phys + (size_t)env * PHYS_STRIDE;
+    load_env(m, s, L, lane, ph, p.dr + (size_t)env * DR_STRIDE);
+    // six chained splits (joystick.py:213-263): dxy, yaw, joints, base qvel, command, push interval
+    RKey rng; rng.a = p.keys[2 * env]; rng.b = p.keys[2 * env + 1];
+    RKey ks[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { RKey o = rblock(rng, lane & 1); ks[k] = kshfl(o, 1); rng = kshfl(o, 0); }
+    // one round of draws: lanes 0-1 dxy | 2 yaw | 3 push interval | 4..9 base qvel | 10..10+nu joints
+    RKey kk; uint32_t cnt;
+    if (lane < 2) { kk = ks[0]; cnt = lane; }
+    else if (lane == 2) { kk = ks[1]; cnt = 0; }
+    else if (lane == 3) { kk = ks[5]; cnt = 0; }
+    else if (lane < 10) { kk = ks[3]; cnt = lane - 4; }
+    else { kk = ks[2]; cnt = lane - 10; }
+    RKey b = rblock(kk, cnt);
+    const uint32_t bits = b.a ^ b.b;
+    if (lane < m.nq) s.qpos[lane] = m.key_qpos[lane];
+    if (lane + 32 < m.nq) s.qpos[lane + 32] = m.key_qpos[lane + 32];
+    __syncwarp();
+    if (lane < 2) s.qpos[lane] = m.key_qpos[lane] + bits_uniform(bits, -0.05f, 0.05f);
+    if (lane == 2) {
+      const float yaw = bits_uniform(bits, -3.14f, 3.14f);
+      Q4 q0; q0.w = m.key_qpos[3]; q0.x = m.key_qpos[4]; q0.y = m.key_qpos[5]; q0.z = m.key_qpos[6];
+      Q4 qn = qmul(q0, axis_angle(v3(0.f, 0.f, 1.f), yaw));
+      s.qpos[3] = qn.w; s.qpos[4] = qn.x; s.qpos[5] = qn.y; s.qpos[6] = qn.z;
+    }
+    if (lane >= 10 && lane < 10 + m.nu) { const int qa = m.act_qadr[lane - 10]; s.qpos[qa] = m.key_qpos[qa] * bits_uniform(bits, 0.5f, 1.5f); }
+    const float bq = bits_uniform(bits, -0.05f, 0.05f);
+    L.qvel = 0.f;
+    {
+      const float v = __shfl_sync(FULLMASK, bq, 4 + (lane < 6 ? lane : 0));
+      if (lane < 6) L.qvel = v;
+    }
+    const float push_iv = __shfl_sync(FULLMASK, bits_uniform(bits, c.push_interval[0], c.push_interval[1]), 3);
+    L.qaccw = 0.f;
+    __syncwarp();
+    { const int a = m.d_act[lane]; L.ctrl = a >= 0 ? s.qpos[m.act_qadr[a]] : 0.f; }
+    for (int i = lane; i < OUT_STRIDE; i += 32) s.outrec[i] = 0.f;
+    __syncwarp();
+    forward_euler<false>(m, s, L, lane, true, false, s.outrec, nullptr);   // mjx_env.init
+    __syncwarp();
+    EnvRegs er;
+    er.rng = rng;
+    er.step = 0; er.steps = 0; er.push_step = 0; er.imitation_i = 0;
+    er.push_interval = (int)rintf(push_iv / c.ctrl_dt);
+    er.cmd = sample_command(c, ks[4], lane);
+    if (lane >= 7) er.cmd = 0.f;
+    er.last_act[0] = er.last_act[1] = er.last_act[2] = 0.f;
+    er.targets = lane < m.nu ? m.key_ctrl[lane] : 0.f;
+#pragma unroll
+    for (int k = 0; k < MAX_DELAY; ++k) er.hist[k] = 0.f;
+    er.air = er.lastc = er.swing = 0.f;
+    er.phase = 0.f;
+    er.ref_lo = er.ref_hi = 0.f;
+    if (c.use_imitation) {
+      const float c0 = __shfl_sync(FULLMASK, er.cmd, 0), c1 = __shfl_sync(FULLMASK, er.cmd, 1), c2 = __shfl_sync(FULLMASK, er.cmd, 2);
+      reference_motion(c, p.poly, c0, c1, c2, 0, lane, er.ref_lo, er.ref_hi);
+    }
+    float* inf = p.info + (size_t)env * INFO_STRIDE;
+    if (lane < c.imu_max_delay * 3) inf[INFO_IMUHIST + lane] = 0.f;
+    __syncwarp();
+    const float contact = feet_contact(s, lane);
+    float* ost = p.obs_state + (size_t)env * ODUCK_OBS_STATE;
+    float* opr = p.obs_priv + (size_t)env * ODUCK_OBS_PRIV;
+    write_obs(m, c, s, s.outrec, L, er, contact, lane, ost, opr, inf + INFO_IMUHIST);
+    store_info(m, c, inf, er, 0.f, lane);
+    if (lane == 0) { p.reward[env] = 0.f; p.done[env] = 0.f; p.trunc[env] = 0.f; }
+    if (lane < ODUCK_NMETRIC) p.metrics[(size_t)env * ODUCK_NMETRIC + lane] = 0.f;
+    store_phys(m, s, L, lane, ph);
+    store_out(s, lane, p.out + (size_t)env * OUT_STRIDE);
+    __syncwarp();
+    // BraxAutoResetWrapper.reset: first_state, first_obs
+    float* fp = p.first_phys + (size_t)env * PHYS_STRIDE;
+    for (int i = lane; i < PHYS_STRIDE; i += 32) fp[i] = ph[i];
+    float* fs_ = p.first_obs_state + (size_t)env * ODUCK_OBS_STATE;
+    for (int i = lane; i < ODUCK_OBS_STATE; i += 32) fs_[i] = ost[i];
+    float* fpv = p.first_obs_priv + (size_t)env * ODUCK_OBS_PRIV;
+    for (int i = lane; i < ODUCK_OBS_PRIV; i += 32) fpv[i] = opr[i];
+    __syncwarp();
+  }
+}
+
+// A1 + A16: Joystick.step fused with EpisodeWrapper + AutoResetWrapper.
+__global__ void __launch_bounds__(WPB * 32, 2) k_step(Params p) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  DevModel* mp; DevEnvCfg* cp; WarpSmem* ws;
+  block_load_tables(p, raw, mp, cp, ws);
+  const DevModel& m = *mp;
+  const DevEnvCfg& c = *cp;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WarpSmem& s = ws[warp];
+  const float PI = 3.14159265358979323846f;
+  for (int env = blockIdx.x * WPB + warp; env < p.N; env += gridDim.x * WPB) {
+    Lane L;
+    float* ph = p.phys + (size_t)env * PHYS_STRIDE;
+    load_env(m, s, L, lane, ph, p.dr + (size_t)env * DR_STRIDE);
+    float* inf = p.info + (size_t)env * INFO_STRIDE;
+    EnvRegs er;
+    load_info(m, c, inf, er, lane);
+    const int nu = m.nu;
+    const float act = lane < nu ? p.action[(size_t)env * nu + lane] : 0.f;
+    if (p.done[env] != 0.f) er.steps = 0;                       // AutoResetWrapper.step prologue
+    const float dt = c.ctrl_dt;
+    const float c0 = __shfl_sync(FULLMASK, er.cmd, 0), c1 = __shfl_sync(FULLMASK, er.cmd, 1), c2 = __shfl_sync(FULLMASK, er.cmd, 2);
+    if (c.use_imitation) {
+      er.imitation_i = (er.imitation_i + 1) % c.nb_steps;
+      const float phs = ((float)er.imitation_i / (float)c.nb_steps) * 2.f * PI;
+      er.phase = lane == 0 ? cosf(phs) : (lane == 1 ? sinf(phs) : 0.f);
+      reference_motion(c, p.poly, c0, c1, c2, er.imitation_i, lane, er.ref_lo, er.ref_hi);
+    } else {
+      er.imitation_i = 0;
+    }
+    // rng, push1, push2, delay = split(rng, 4)
+    RKey push1, push2, delay;
+    { RKey o = rblock(er.rng, lane & 3); push1 = kshfl(o, 1); push2 = kshfl(o, 2); delay = kshfl(o, 3); er.rng = kshfl(o, 0); }
+    // action delay (joystick.py:361-376)
+#pragma unroll
+    for (int k = MAX_DELAY - 1; k >= 1; --k) er.hist[k] = er.hist[k - 1];
+    er.hist[0] = act;
+    const int aidx = warp_randint(delay, c.act_min_delay, c.act_max_delay, lane);
+    float act_d = er.hist[0];
+#pragma unroll
+    for (int k = 1; k < MAX_DELAY; ++k) if (aidx == k) act_d = er.hist[k];
+    // push (joystick.py:381-400)
+    float pushv = 0.f;
+    {
+      RKey b = rblock(lane == 0 ? push1 : push2, 0u);
+      const uint32_t bits = b.a ^ b.b;
+      const float theta = bits_uniform(__shfl_sync(FULLMASK, bits, 0), 0.f, 2.f * PI);
+      const float mag = bits_uniform(__shfl_sync(FULLMASK, bits, 1), c.push_magnitude[0], c.push_magnitude[1]);
+      const bool fire = ((er.push_step + 1) % er.push_interval) == 0 && c.push_enable;
+      if (lane < 2) { pushv = fire ? (lane == 0 ? cosf(theta) : sinf(theta)) : 0.f; L.qvel += pushv * mag; }
+    }
+    // motor targets with speed limit (joystick.py:404-417)
+    float tgt = (lane < nu ? m.key_ctrl[lane] : 0.f) + act_d * c.action_scale;
+    if (c.use_speed_limits) { const float lim = c.max_motor_velocity * dt; tgt = fminf(fmaxf(tgt, er.targets - lim), er.targets + lim); }
+    { const int a = m.d_act[lane]; const float t = __shfl_sync(FULLMASK, tgt, a < 0 ? 0 : a); if (a >= 0) L.ctrl = t; }
+    // physics: n_substeps x mjx.step (joystick.py:420)
+    for (int k = 0; k < c.n_substeps; ++k) forward_euler<false>(m, s, L, lane, k == c.n_substeps - 1, true, s.outrec, nullptr);
+    __syncwarp();
+    er.targets = tgt;
+    // contacts / air time / swing peak (joystick.py:424-435)
+    const float contact = feet_contact(s, lane);
+    er.air += dt;
+    if (lane < 2) er.swing = fmaxf(er.swing, s.outrec[OUT_FEET + 3 * lane + 2]);
+    float* ost = p.obs_state + (size_t)env * ODUCK_OBS_STATE;
+    float* opr = p.obs_priv + (size_t)env * ODUCK_OBS_PRIV;
+    write_obs(m, c, s, s.outrec, L, er, contact, lane, ost, opr, inf + INFO_IMUHIST);
+    // termination (joystick.py:483-485)
+    bool bad = (lane < m.nq && isnan(s.qpos[lane])) || (lane + 32 < m.nq && isnan(s.qpos[lane + 32])) || isnan(L.qvel);
+    const bool done = (s.outrec[OUT_SENS + 11] < 0.f) || (__ballot_sync(FULLMASK, bad) != 0u);
+    // rewards (joystick.py:622-669)
+    const float* sd = s.outrec + OUT_SENS;
+    float q = 0.f, afrc = 0.f, dflt = 0.f;
+    if (lane < nu) { q = s.qpos[m.act_qadr[lane]]; afrc = s.outrec[OUT_AFRC + lane]; dflt = m.key_ctrl[lane]; }
+    const float qdv = __shfl_sync(FULLMASK, L.qvel, lane < nu ? m.act_dof[lane] : 0);
+    const float qd = lane < nu ? qdv : 0.f;
+    const float ex = (c0 - sd[3]) * (c0 - sd[3]);
+    const float ey = fmaxf(fabsf(sd[4] - c1) - 0.1f, 0.f);
+    const float r_lin = nan_to_num(expf(-(ex + ey * ey) / c.tracking_sigma));
+    const float r_ang = nan_to_num(expf(-((c2 - sd[2]) * (c2 - sd[2])) / c.tracking_sigma));
+    const float c_torque = nan_to_num(wsum(afrc * afrc));
+    const float dact = act - er.last_act[0];
+    const float c_rate = nan_to_num(wsum(lane < nu ? dact * dact : 0.f));
+    const float cmd_norm = sqrtf(c0 * c0 + c1 * c1 + c2 * c2);
+    const float c_still = nan_to_num(wsum(lane < nu ? fabsf(q - dflt) + fabsf(qd) : 0.f)) * (cmd_norm < 0.01f ? 1.f : 0.f);
+    float r_imit = 0.f;
+    if (c.use_imitation) {
+      // base velocity error vs ref[34:40]; lanes 0..5
+      const float bv = L.qvel;                                        // lane d < 6: floating-base qvel (post-integration)
+      const float rv = __shfl_sync(FULLMASK, er.ref_hi, 2 + (lane < 6 ? lane : 0));
+      const float e = lane < 6 ? (bv - rv) * (bv - rv) : 0.f;
+      const float lxy = __shfl_sync(FULLMASK, e, 0) + __shfl_sync(FULLMASK, e, 1), lz = __shfl_sync(FULLMASK, e, 2);
+      const float axy = __shfl_sync(FULLMASK, e, 3) + __shfl_sync(FULLMASK, e, 4), az = __shfl_sync(FULLMASK, e, 5);
+      // leg joints: actuator lanes 0..4 and 9..13 vs ref[rr], ref[16 + rr]
+      const bool leg = lane < 5 || (lane >= 9 && lane < 14);
+      const int rr = lane < 5 ? lane : lane + 2;
+      const float rp = __shfl_sync(FULLMASK, er.ref_lo, leg ? rr : 0), rvv = __shfl_sync(FULLMASK, er.ref_lo, leg ? 16 + rr : 0);
+      const float jp_ = wsum(leg ? (q - rp) * (q - rp) : 0.f), jv_ = wsum(leg ? (qd - rvv) * (qd - rvv) : 0.f);
+      const float rc = er.ref_hi > 0.5f ? 1.f : 0.f;                  // lane k < 2: ref[32 + k]
+      const float cm = (lane < 2 && contact == rc) ? 1.f : 0.f;
+      const float crew = __shfl_sync(FULLMASK, cm, 0) + __shfl_sync(FULLMASK, cm, 1);
+      float rew = expf(-8.f * lxy) + expf(-8.f * lz) + 0.5f * expf(-2.f * axy) + 0.5f * expf(-2.f * az) - 15.f * jp_ - 1e-3f * jv_ + crew;
+      rew *= cmd_norm > 0.01f ? 1.f : 0.f;
+      r_imit = nan_to_num(rew);
+    }
+    const float sc0 = r_lin * c.sc_lin, sc1 = r_ang * c.sc_ang, sc2 = c_torque * c.sc_torques, sc3 = c_rate * c.sc_rate;
+    const float sc4 = c_still * c.sc_still, sc5 = 1.f * c.sc_alive, sc6 = r_imit * c.sc_imit;
+    const float total = sc0 + sc1 + sc2 + sc3 + sc5 + sc6 + sc4;       // dict order of joystick.py:634-667
+    const float reward = fminf(fmaxf(total * dt, 0.f), 10000.f);
+    // info updates (joystick.py:449-469)
+    er.step += 1;
+    er.push_step += 1;
+    er.last_act[2] = er.last_act[1]; er.last_act[1] = er.last_act[0]; er.last_act[0] = act;
+    RKey cmd_rng;
+    { RKey o = rblock(er.rng, lane & 1); cmd_rng = kshfl(o, 1); er.rng = kshfl(o, 0); }
+    if (er.step > 500) { const float nc = sample_command(c, cmd_rng, lane); er.cmd = lane < 7 ? nc : 0.f; }
+    if (done || er.step > 500) er.step = 0;
+    { const float nc = contact != 0.f ? 0.f : 1.f; er.air *= nc; er.lastc = contact; er.swing *= nc; }
+    // metrics (joystick.py:470-477): scaled term, sign flipped for costs
+    {
+      float mv = 0.f;
+      const float scs[7] = {sc0, sc1, sc2, sc3, sc4, sc5, sc6};
+      const float sg[7] = {c.sc_lin, c.sc_ang, c.sc_torques, c.sc_rate, c.sc_still, c.sc_alive, c.sc_imit};
+#pragma unroll
+      for (int k = 0; k < 7; ++k) if (lane == k) mv = sg[k] == 0.f ? 0.f : (sg[k] > 0.f ? scs[k] : -scs[k]);
+      const float sw = 0.5f * (__shfl_sync(FULLMASK, er.swing, 0) + __shfl_sync(FULLMASK, er.swing, 1));
+      if (lane == 7) mv = sw;
+      if (lane < ODUCK_NMETRIC) p.metrics[(size_t)env * ODUCK_NMETRIC + lane] = mv;
+    }
+    // EpisodeWrapper (action_repeat = 1) + AutoReset
+    er.steps += 1;
+    const bool trunc = er.steps >= c.episode_length;
+    const float d = done ? 1.f : 0.f;
+    const float done_f = trunc ? 1.f : d;
+    if (lane == 0) { p.reward[env] = reward; p.done[env] = done_f; p.trunc[env] = trunc ? 1.f - d : 0.f; }
+    store_info(m, c, inf, er, pushv, lane);
+    store_out(s, lane, p.out + (size_t)env * OUT_STRIDE);
+    if (c.auto_reset && done_f != 0.f) {
+      __syncwarp();
+      const float* fp = p.first_phys + (size_t)env * PHYS_STRIDE;
+      for (int i = lane; i < PHYS_CTRL; i += 32) ph[i] = fp[i];      // qpos, qvel, qacc_warmstart <- first_state
+      const int a = m.d_act[lane];
+      if (a >= 0) ph[PHYS_CTRL + a] = L.ctrl;
+      const float* fs_ = p.first_obs_state + (size_t)env * ODUCK_OBS_STATE;
+      for (int i = lane; i < ODUCK_OBS_STATE; i += 32) ost[i] = fs_[i];
+      const float* fpv = p.first_obs_priv + (size_t)env * ODUCK_OBS_PRIV;
+      for (int i = lane; i < ODUCK_OBS_PRIV; i += 32) opr[i] = fpv[i];
+    } else {
+      store_phys(m, s, L, lane, ph);
+    }
+    __syncwarp();
+  }
+}
+
+// A14: domain_randomize (common/randomize.py:39-106), one warp per env, one round per split.
+__global__ void __launch_bounds__(WPB * 32, 2) k_randomize(Params p) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  DevModel* mp; DevEnvCfg* cp; WarpSmem* ws;
+  block_load_tables(p, raw, mp, cp, ws);
+  const DevModel& m = *mp;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int env = blockIdx.x * WPB + warp; env < p.N; env += gridDim.x * WPB) {
+    float* dr = p.dr + (size_t)env * DR_STRIDE;
+    RKey rng; rng.a = p.keys[2 * env]; rng.b = p.keys[2 * env + 1];
+    float u[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      RKey o = rblock(rng, lane & 1);
+      RKey key = kshfl(o, 1);
+      rng = kshfl(o, 0);
+      RKey b = rblock(key, (uint32_t)lane);
+      u[k] = bits_unit(b.a ^ b.b);
+    }
+    auto uni = [](float x, float lo, float hi) { return fmaxf(lo, x * (hi - lo) + lo); };
+    if (lane == 0) dr[DR_FRIC0] = uni(u[0], 0.5f, 1.0f);
+    // friction-loss dofs in dof order; row index = draw index
+    for (int d = 0; d < m.nv; ++d) {
+      const int r = m.d_frrow[d];
+      if (r < 0 || r != lane) continue;
+      dr[DR_FLOSS + d] = m.d_floss[d] * uni(u[1], 0.9f, 1.1f);
+      dr[DR_ARM + d] = m.d_arm[d] * uni(u[2], 1.0f, 1.05f);
+      dr[DR_QPOS0 + m.d_qadr[d]] = m.qpos0[m.d_qadr[d]] + uni(u[6], -0.03f, 0.03f);
+    }
+    if (lane < 3) dr[DR_IPOS1 + lane] = m.b_ipos[lane][1] + uni(u[3], -0.05f, 0.05f);
+    const float dm1 = uni(__shfl_sync(FULLMASK, u[5], 0), -0.1f, 0.1f);
+    if (lane < m.nbody) dr[lane] = m.b_mass[lane] * uni(u[4], 0.9f, 1.1f) + (lane == 1 ? dm1 : 0.f);
+    if (lane < m.nu) dr[DR_KP + lane] = m.d_kp[m.act_dof[lane]] * uni(u[7], 0.9f, 1.1f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- host side
+static int build_dev_model(const OduckModel& M, DevModel& D, std::string& err) {
+  memset(&D, 0, sizeof(D));
+  if (M.nv > 32 || M.nbody > 32 || M.nq > 36 || M.nu > 16 || M.foot_nvert > 32) { err = "model exceeds the warp-per-env limits (nv, nbody, nvert <= 32)"; return -1; }
+  D.nbody = M.nbody; D.njnt = M.njnt; D.nq = M.nq; D.nv = M.nv; D.nu = M.nu;
+  D.nvert = M.foot_nvert; D.enable_ff = M.enable_foot_foot;
+  D.iterations = M.iterations; D.ls_iterations = M.ls_iterations;
+  D.timestep = (float)M.timestep;
+  for (int i = 0; i < 3; i++) D.gravity[i] = (float)M.gravity[i];
+  D.tolerance = (float)M.tolerance; D.ls_tolerance = (float)M.ls_tolerance; D.meaninertia = (float)M.meaninertia; D.impratio = (float)M.impratio;
+  {
+    double timeconst = std::max(M.solref[0], 2 * M.timestep), damp = M.solref[1];
+    auto clampd = [](double v, double lo, double hi) { return std::min(std::max(v, lo), hi); };
+    double dmin = clampd(M.solimp[0], 1e-4, 0.9999), dmax = clampd(M.solimp[1], 1e-4, 0.9999);
+    double k = 1 / (dmax * dmax * timeconst * timeconst * damp * damp), b = 2 / (dmax * timeconst);
+    if (M.solref[0] <= 0) k = -M.solref[0] / (dmax * dmax);
+    if (M.solref[1] <= 0) b = -M.solref[1] / dmax;
+    D.sol_k = (float)k; D.sol_b = (float)b; D.dmin = (float)dmin; D.dmax = (float)dmax;
+    D.width = (float)std::max(1e-15, M.solimp[2]); D.mid = (float)clampd(M.solimp[3], 1e-4, 0.9999); D.power = (float)std::max(1.0, M.solimp[4]);
+  }
+  D.floor_mu = (float)M.floor_friction; D.foot_mu = (float)M.foot_friction;
+  if (M.iterations != 1) { err = "only option iterations=1 (the reference scenes) is implemented"; return -1; }
+  // bodies
+  auto quat2mat = [](const double* q, double* R) {
+    double w = q[0], x = q[1], y = q[2], z = q[3];
+    R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - w * z); R[2] = 2 * (x * z + w * y);
+    R[3] = 2 * (x * y + w * z); R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - w * x);
+    R[6] = 2 * (x * z - w * y); R[7] = 2 * (y * z + w * x); R[8] = 1 - 2 * (x * x + y * y);
+  };
+  int depth[32] = {0};
+  D.maxdepth = 0;
+  for (int b = 0; b < 32; b++) { D.b_depth[b] = -1; D.b_lastdof[b] = -1; D.b_quat[0][b] = 1.f; }
+  for (int b = 0; b < M.nbody; b++) {
+    int p = M.body_parentid[b];
+    depth[b] = b == 0 ? 0 : depth[p] + 1;
+    D.b_depth[b] = b == 0 ? 0 : depth[b];
+    D.maxdepth = std::max(D.maxdepth, depth[b]);
+    D.b_parent[b] = p;
+    for (int i = 0; i < 3; i++) { D.b_pos[i][b] = (float)M.body_pos[b][i]; D.b_ipos[i][b] = (float)M.body_ipos[b][i]; }
+    for (int i = 0; i < 4; i++) D.b_quat[i][b] = (float)M.body_quat[b][i];
+    D.b_mass[b] = (float)M.body_mass[b];
+    D.b_invw0[b] = (float)M.body_invweight0[b][0];
+    double Ri[9];
+    quat2mat(M.body_iquat[b], Ri);
+    double Ib[9];
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) Ib[3 * r + c] = Ri[3 * r] * M.body_inertia[b][0] * Ri[3 * c] + Ri[3 * r + 1] * M.body_inertia[b][1] * Ri[3 * c + 1] + Ri[3 * r + 2] * M.body_inertia[b][2] * Ri[3 * c + 2];
+    D.b_Ib[0][b] = (float)Ib[0]; D.b_Ib[1][b] = (float)Ib[4]; D.b_Ib[2][b] = (float)Ib[8];
+    D.b_Ib[3][b] = (float)Ib[1]; D.b_Ib[4][b] = (float)Ib[2]; D.b_Ib[5][b] = (float)Ib[5];
+    D.b_dofadr[b] = M.body_dofadr[b];
+    int nj = M.body_jntnum[b], j0 = M.body_jntadr[b];
+    D.b_jtype[b] = 0;
+    if (nj > 0) {
+      if (M.jnt_type[j0] == ODUCK_JNT_FREE) {
+        if (nj != 1) { err = "free joint must be alone on its body"; return -1; }
+        D.b_jtype[b] = 1; D.b_qadr0[b] = M.jnt_qposadr[j0];
+      } else {
+        if (nj > 2) { err = "at most two hinge joints per body"; return -1; }
+        D.b_jtype[b] = 1 + nj;
+        for (int k = 0; k < nj; k++) {
+          int j = j0 + k;
+          if (M.jnt_type[j] != ODUCK_JNT_HINGE) { err = "unsupported joint type"; return -1; }
+          if (M.jnt_pos[j][0] != 0 || M.jnt_pos[j][1] != 0 || M.jnt_pos[j][2] != 0) { err = "hinge joints must sit at the body origin (jnt_pos = 0)"; return -1; }
+          for (int i = 0; i < 3; i++) (k == 0 ? D.b_ax0 : D.b_ax1)[i][b] = (float)M.jnt_axis[j][i];
+          (k == 0 ? D.b_qadr0 : D.b_qadr1)[b] = M.jnt_qposadr[j];
+        }
+      }
+    }
+    // last dof of the nearest ancestor-or-self with dofs
+    int a = b;
+    while (a > 0 && M.body_dofnum[a] == 0) a = M.body_parentid[a];
+    D.b_lastdof[b] = (a > 0) ? M.body_dofadr[a] + M.body_dofnum[a] - 1 : -1;
+  }
+  for (int b = 1; b < M.nbody; b++) {   // subtree masks
+    int a = b;
+    while (a > 0) { D.b_submask[a] |= 1 << b; a = M.body_parentid[a]; }
+  }
+  // dofs
+  int maxchain = 1, nfr = 0, nlim = 0;
+  for (int d = 0; d < 32; d++) { D.d_parent[d] = -1; D.d_vparent[d] = -1; D.d_act[d] = -1; D.d_frrow[d] = -1; D.d_limrow[d] = -1; }
+  for (int d = 0; d < M.nv; d++) {
+    int j = M.dof_jntid[d], b = M.dof_bodyid[d];
+    D.d_body[d] = b;
+    D.d_parent[d] = M.dof_parentid[d];
+    D.d_bsubmask[d] = D.b_submask[b];
+    int chain = 0;
+    for (int a = d; a >= 0; a = M.dof_parentid[a]) { D.d_ancmask[d] |= 1 << a; chain++; }
+    maxchain = std::max(maxchain, chain);
+    D.d_damping[d] = (float)M.dof_damping[d];
+    D.d_invw0[d] = (float)M.dof_invweight0[d];
+    D.d_floss[d] = (float)M.dof_frictionloss[d];
+    D.d_arm[d] = (float)M.dof_armature[d];
+    int k = d - M.jnt_dofadr[j];
+    if (M.jnt_type[j] == ODUCK_JNT_FREE) {
+      D.d_flags[d] = k < 3 ? DF_TRANS : DF_ROT;
+      D.d_qadr[d] = k < 3 ? M.jnt_qposadr[j] + k : M.jnt_qposadr[j] + 3;
+      D.d_vparent[d] = k < 3 ? M.dof_parentid[d] : M.jnt_dofadr[j] + 2;
+    } else {
+      D.d_flags[d] = DF_HINGE;
+      D.d_qadr[d] = M.jnt_qposadr[j];
+      D.d_vparent[d] = M.dof_parentid[d];
+      if (M.jnt_limited[j]) { D.d_flags[d] |= DF_LIMITED; D.d_lo[d] = (float)M.jnt_range[j][0]; D.d_hi[d] = (float)M.jnt_range[j][1]; D.d_limrow[d] = nlim++; }
+    }
+    if (M.dof_frictionloss[d] > 0) {
+      D.d_flags[d] |= DF_FLOSS;
+      D.d_frrow[d] = nfr++;
+      double imp = D.dmin;
+      D.d_Dfric[d] = (float)(1.0 / std::max(M.dof_invweight0[d] * (1 - imp) / imp, 1e-15));
+    } else {
+      D.d_Dfric[d] = 1.f;
+    }
+  }
+  D.nfr = nfr; D.nlim = nlim;
+  D.prefix_rounds = 0;
+  while ((1 << D.prefix_rounds) < maxchain) D.prefix_rounds++;
+  for (int u = 0; u < M.nu; u++) {
+    int j = M.act_jntid[u], d = M.jnt_dofadr[j];
+    D.d_act[d] = u;
+    D.d_kp[d] = (float)M.act_kp[u]; D.d_kv[d] = (float)M.act_kv[u];
+    D.d_clo[d] = (float)M.act_ctrlrange[u][0]; D.d_chi[d] = (float)M.act_ctrlrange[u][1];
+    D.d_flo[d] = (float)M.act_forcerange[u][0]; D.d_fhi[d] = (float)M.act_forcerange[u][1];
+    D.act_dof[u] = d; D.act_qadr[u] = M.jnt_qposadr[j];
+    D.act_bl_qadr[u] = -1;   // base.py:121-125: "<name>_backlash" joint = the next joint on the same body
+    if (j + 1 < M.njnt && M.jnt_bodyid[j + 1] == M.jnt_bodyid[j] && M.jnt_type[j + 1] == ODUCK_JNT_HINGE) D.act_bl_qadr[u] = M.jnt_qposadr[j + 1];
+    D.key_ctrl[u] = (float)M.key_ctrl[u];
+  }
+  for (int i = 0; i < M.nq; i++) { D.key_qpos[i] = (float)M.key_qpos[i]; D.qpos0[i] = (float)M.qpos0[i]; }
+  // sites
+  auto chain_of_body = [&](int b) { int a = b; while (a > 0 && M.body_dofnum[a] == 0) a = M.body_parentid[a]; int mask = 0; if (a > 0) for (int d = M.body_dofadr[a] + M.body_dofnum[a] - 1; d >= 0; d = M.dof_parentid[d]) mask |= 1 << d; return mask; };
+  {
+    int sidx = M.imu_site;
+    D.imu_body = M.site_bodyid[sidx];
+    D.imu_chain = chain_of_body(D.imu_body);
+    double R[9];
+    quat2mat(M.site_quat[sidx], R);
+    for (int i = 0; i < 9; i++) D.imu_rot[i] = (float)R[i];
+    for (int i = 0; i < 3; i++) D.imu_pos[i] = (float)M.site_pos[sidx][i];
+  }
+  for (int k = 0; k < 2; k++) {
+    int sidx = M.foot_site[k];
+    D.foot_site_body[k] = M.site_bodyid[sidx];
+    for (int i = 0; i < 3; i++) D.foot_site_pos[k][i] = (float)M.site_pos[sidx][i];
+    D.foot_body[k] = M.foot_body[k];
+    D.foot_chain[k] = chain_of_body(M.foot_body[k]);
+    for (int v = 0; v < M.foot_nvert; v++)
+      for (int i = 0; i < 3; i++) D.vert[k][i][v] = (float)M.foot_vert[k][v][i];
+  }
+  return 0;
+}
+
+static void build_dev_cfg(const OduckEnvConfig& C, DevEnvCfg& D) {
+  memset(&D, 0, sizeof(D));
+  D.n_substeps = C.n_substeps; D.episode_length = C.episode_length; D.use_imitation = C.use_imitation_reward; D.use_speed_limits = C.use_motor_speed_limits;
+  D.push_enable = C.push_enable; D.act_min_delay = C.action_min_delay; D.act_max_delay = C.action_max_delay; D.imu_min_delay = C.imu_min_delay; D.imu_max_delay = C.imu_max_delay;
+  D.auto_reset = C.auto_reset;
+  D.ctrl_dt = (float)C.ctrl_dt; D.action_scale = (float)C.action_scale; D.dof_vel_scale = (float)C.dof_vel_scale; D.max_motor_velocity = (float)C.max_motor_velocity;
+  D.noise_level = (float)C.noise_level; D.noise_gyro = (float)C.noise_gyro; D.noise_acc = (float)C.noise_accelerometer; D.noise_gravity = (float)C.noise_gravity; D.noise_joint_vel = (float)C.noise_joint_vel;
+  for (int i = 0; i < 16; i++) D.qpos_noise_scale[i] = (float)C.qpos_noise_scale[i];
+  D.sc_lin = (float)C.scale_tracking_lin_vel; D.sc_ang = (float)C.scale_tracking_ang_vel; D.sc_torques = (float)C.scale_torques; D.sc_rate = (float)C.scale_action_rate;
+  D.sc_still = (float)C.scale_stand_still; D.sc_alive = (float)C.scale_alive; D.sc_imit = (float)C.scale_imitation; D.tracking_sigma = (float)C.tracking_sigma;
+  for (int i = 0; i < 2; i++) { D.push_interval[i] = (float)C.push_interval_range[i]; D.push_magnitude[i] = (float)C.push_magnitude_range[i]; }
+  for (int i = 0; i < 7; i++) { D.cmd_range[i][0] = (float)C.cmd_range[i][0]; D.cmd_range[i][1] = (float)C.cmd_range[i][1]; }
+  D.ndx = C.ndx; D.ndy = C.ndy; D.ndth = C.ndth; D.nb_steps = C.nb_steps_in_period > 0 ? C.nb_steps_in_period : 1;
+  for (int i = 0; i < 8; i++) { D.dxs[i] = (float)C.dxs[i]; D.dys[i] = (float)C.dys[i]; }
+  for (int i = 0; i < 16; i++) D.dths[i] = (float)C.dthetas[i];
+  for (int i = 0; i < 2; i++) { D.dx_range[i] = (float)C.dx_range[i]; D.dy_range[i] = (float)C.dy_range[i]; D.dth_range[i] = (float)C.dtheta_range[i]; }
+}
+
+static Params make_params(OduckHandle* h) {
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.model = h->dmodel; p.cfg = h->dcfg; p.poly = h->poly;
+  p.phys = h->phys; p.dr = h->dr; p.out = h->out; p.info = h->info; p.obs_state = h->obs_state; p.obs_priv = h->obs_priv;
+  p.reward = h->reward; p.done = h->done; p.trunc = h->trunc; p.metrics = h->metrics;
+  p.first_phys = h->first_phys; p.first_obs_state = h->first_obs_state; p.first_obs_priv = h->first_obs_priv; p.dbg = h->dbg;
+  p.N = h->n;
+  return p;
+}
+
+template <typename K>
+static int launch(OduckHandle* h, K kernel, const Params& p, void* stream) {
+  CUDA_TRY(cudaSetDevice(h->device));
+  kernel<<<h->grid, WPB * 32, h->smem_bytes, (cudaStream_t)stream>>>(p);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
+  return ODUCK_OK;
+}
+
+extern "C" {
+
+int oduck_abi_version(void) { return ODUCK_ABI_VERSION; }
+int oduck_sizeof_model(void) { return (int)sizeof(OduckModel); }
+int oduck_sizeof_env_config(void) { return (int)sizeof(OduckEnvConfig); }
+const char* oduck_last_error(void) { return g_err.c_str(); }
+int oduck_num_envs(const OduckHandle* h) { return h ? h->n : 0; }
+int64_t oduck_launch_count(const OduckHandle* h) { return h ? h->launches : 0; }
+
+int oduck_destroy(OduckHandle* h) {
+  if (!h) return ODUCK_OK;
+  cudaSetDevice(h->device);
+  void* ptrs[] = {h->dmodel, h->dcfg, h->poly, h->phys, h->dr, h->out, h->info, h->obs_state, h->obs_priv, h->reward, h->done, h->trunc,
+                  h->metrics, h->first_phys, h->first_obs_state, h->first_obs_priv, h->dbg};
+  for (void* q : ptrs) if (q) cudaFree(q);
+  delete h;
+  return ODUCK_OK;
+}
+
+int oduck_create(const OduckModel* model, const OduckEnvConfig* cfg, int num_envs, int device, OduckHandle** out) {
+  if (!model || !cfg || !out || num_envs <= 0) return fail(ODUCK_ERR_ARG, "oduck_create: bad argument");
+  if (model->abi_version != ODUCK_ABI_VERSION) return fail(ODUCK_ERR_MODEL, "oduck_create: model ABI version mismatch");
+  if (model->floor_is_hfield) return fail(ODUCK_ERR_UNSUPPORTED, "oduck_create: height-field floor not implemented yet");
+  if (cfg->action_max_delay > MAX_DELAY || cfg->imu_max_delay * 3 > 16 || cfg->action_max_delay < 1) return fail(ODUCK_ERR_ARG, "oduck_create: delay history out of range");
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(ODUCK_ERR_CUDA, "oduck_create: no such CUDA device");
+  CUDA_TRY(cudaSetDevice(device));
+  OduckHandle* h = new OduckHandle();
+  memset(h, 0, sizeof(*h));
+  h->n = num_envs; h->device = device; h->hm = *model; h->hcfg = *cfg;
+  std::string err;
+  if (build_dev_model(*model, h->hdm, err) != 0) { delete h; return fail(ODUCK_ERR_MODEL, "oduck_create: " + err); }
+  build_dev_cfg(*cfg, h->hdc);
+  h->nefc = h->hdm.nfr + h->hdm.nlim + 4 * NCON_ALL;
+  if (h->nefc > 96) { delete h; return fail(ODUCK_ERR_MODEL, "oduck_create: too many constraint rows"); }
+  const size_t N = (size_t)num_envs;
+#define ALLOC(ptr, count) do { if (cudaMalloc((void**)&(ptr), (count) * sizeof(float)) != cudaSuccess) { oduck_destroy(h); return fail(ODUCK_ERR_ALLOC, "oduck_create: cudaMalloc failed"); } cudaMemset((ptr), 0, (count) * sizeof(float)); } while (0)
+  if (cudaMalloc((void**)&h->dmodel, sizeof(DevModel)) != cudaSuccess || cudaMalloc((void**)&h->dcfg, sizeof(DevEnvCfg)) != cudaSuccess) { oduck_destroy(h); return fail(ODUCK_ERR_ALLOC, "oduck_create: cudaMalloc failed"); }
+  CUDA_TRY(cudaMemcpy(h->dmodel, &h->hdm, sizeof(DevModel), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(h->dcfg, &h->hdc, sizeof(DevEnvCfg), cudaMemcpyHostToDevice));
+  if (cfg->use_imitation_reward) {
+    if (!cfg->poly_coef) { oduck_destroy(h); return fail(ODUCK_ERR_ARG, "oduck_create: imitation reward needs poly_coef"); }
+    size_t np = (size_t)cfg->ndx * cfg->ndy * cfg->ndth * ODUCK_REF_DIM * ODUCK_POLY_DEG;
+    std::vector<float> pf(np);
+    for (size_t i = 0; i < np; i++) pf[i] = (float)cfg->poly_coef[i];   // jax float32 (x64 disabled)
+    ALLOC(h->poly, np);
+    CUDA_TRY(cudaMemcpy(h->poly, pf.data(), np * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  h->hcfg.poly_coef = nullptr;
+  ALLOC(h->phys, N * PHYS_STRIDE); ALLOC(h->dr, N * DR_STRIDE); ALLOC(h->out, N * OUT_STRIDE); ALLOC(h->info, N * INFO_STRIDE);
+  ALLOC(h->obs_state, N * ODUCK_OBS_STATE); ALLOC(h->obs_priv, N * ODUCK_OBS_PRIV);
+  ALLOC(h->reward, N); ALLOC(h->done, N); ALLOC(h->trunc, N); ALLOC(h->metrics, N * ODUCK_NMETRIC);
+  ALLOC(h->first_phys, N * PHYS_STRIDE); ALLOC(h->first_obs_state, N * ODUCK_OBS_STATE); ALLOC(h->first_obs_priv, N * ODUCK_OBS_PRIV);
+#undef ALLOC
+  // nominal state and nominal (un-randomised) per-env model
+  {
+    std::vector<float> ph(PHYS_STRIDE, 0.f), dr(DR_STRIDE, 0.f), inf(INFO_STRIDE, 0.f);
+    for (int i = 0; i < model->nq; i++) { ph[i] = (float)model->key_qpos[i]; dr[DR_QPOS0 + i] = (float)model->qpos0[i]; }
+    for (int u = 0; u < model->nu; u++) { ph[PHYS_CTRL + u] = (float)model->key_ctrl[u]; dr[DR_KP + u] = (float)model->act_kp[u]; }
+    for (int b = 0; b < model->nbody; b++) dr[b] = (float)model->body_mass[b];
+    for (int i = 0; i < 3; i++) dr[DR_IPOS1 + i] = (float)model->body_ipos[1][i];
+    dr[DR_FRIC0] = 1.f;
+    for (int d = 0; d < model->nv; d++) { dr[DR_FLOSS + d] = (float)model->dof_frictionloss[d]; dr[DR_ARM + d] = (float)model->dof_armature[d]; }
+    int big = 1 << 30;
+    memcpy(&inf[INFO_PUSH_INT], &big, 4);
+    std::vector<float> all;
+    auto fill = [&](float* dst, const std::vector<float>& rec) {
+      all.resize(N * rec.size());
+      for (size_t e = 0; e < N; e++) memcpy(&all[e * rec.size()], rec.data(), rec.size() * sizeof(float));
+      return cudaMemcpy(dst, all.data(), all.size() * sizeof(float), cudaMemcpyHostToDevice);
+    };
+    CUDA_TRY(fill(h->phys, ph)); CUDA_TRY(fill(h->first_phys, ph)); CUDA_TRY(fill(h->dr, dr)); CUDA_TRY(fill(h->info, inf));
+  }
+  h->smem_bytes = (int)(((sizeof(DevModel) + 15) & ~15u) + ((sizeof(DevEnvCfg) + 15) & ~15u) + WPB * sizeof(WarpSmem));
+  CUDA_TRY(cudaFuncSetAttribute(k_physics<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+  CUDA_TRY(cudaFuncSetAttribute(k_physics<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+  CUDA_TRY(cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+  CUDA_TRY(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+  CUDA_TRY(cudaFuncSetAttribute(k_randomize, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+  h->grid = (num_envs + WPB - 1) / WPB;
+  CUDA_TRY(cudaDeviceSynchronize());
+  *out = h;
+  return ODUCK_OK;
+}
+
+int oduck_randomize(OduckHandle* h, const uint32_t* keys, void* stream) {
+  if (!h || !keys) return fail(ODUCK_ERR_ARG, "oduck_randomize: bad argument");
+  Params p = make_params(h);
+  p.keys = keys;
+  return launch(h, k_randomize, p, stream);
+}
+int oduck_reset(OduckHandle* h, const uint32_t* keys, const uint8_t* mask, void* stream) {
+  if (!h || !keys) return fail(ODUCK_ERR_ARG, "oduck_reset: bad argument");
+  Params p = make_params(h);
+  p.keys = keys; p.mask = mask;
+  return launch(h, k_reset, p, stream);
+}
+int oduck_step(OduckHandle* h, const float* action, void* stream) {
+  if (!h || !action) return fail(ODUCK_ERR_ARG, "oduck_step: bad argument");
+  Params p = make_params(h);
+  p.action = action;
+  return launch(h, k_step, p, stream);
+}
+int oduck_physics_substeps(OduckHandle* h, const float* ctrl, int n, void* stream) {
+  if (!h || n < 0) return fail(ODUCK_ERR_ARG, "oduck_physics_substeps: bad argument");
+  Params p = make_params(h);
+  p.action = ctrl; p.nsub = n; p.integrate = 1;
+  return launch(h, k_physics<false>, p, stream);
+}
+int oduck_forward(OduckHandle* h, void* stream) {
+  if (!h) return fail(ODUCK_ERR_ARG, "oduck_forward: bad argument");
+  Params p = make_params(h);
+  p.nsub = 1; p.integrate = 0;
+  return launch(h, k_physics<false>, p, stream);
+}
+// Diagnostic (not part of the reference surface): one forward with every intermediate dumped, DBG_STRIDE floats per env
+// copied to host memory `out`.  Used by tests/test_parity_gpu.py to localise a parity failure.
+int oduck_debug_forward(OduckHandle* h, float* out_host) {
+  if (!h || !out_host) return fail(ODUCK_ERR_ARG, "oduck_debug_forward: bad argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (!h->dbg) { CUDA_TRY(cudaMalloc((void**)&h->dbg, (size_t)h->n * DBG_STRIDE * sizeof(float))); }
+  CUDA_TRY(cudaMemset(h->dbg, 0, (size_t)h->n * DBG_STRIDE * sizeof(float)));
+  Params p = make_params(h);
+  p.nsub = 1; p.integrate = 0;
+  int rc = launch(h, k_physics<true>, p, nullptr);
+  if (rc) return rc;
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(out_host, h->dbg, (size_t)h->n * DBG_STRIDE * sizeof(float), cudaMemcpyDeviceToHost));
+  return ODUCK_OK;
+}
+int oduck_debug_stride(void) { return DBG_STRIDE; }
+
+int oduck_set_state(OduckHandle* h, const float* qpos, const float* qvel, const float* qacc_warm, void* stream) {
+  if (!h) return fail(ODUCK_ERR_ARG, "oduck_set_state: bad argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t N = (size_t)h->n, pitch = PHYS_STRIDE * sizeof(float);
+  if (qpos) CUDA_TRY(cudaMemcpy2DAsync(h->phys, pitch, qpos, h->hm.nq * sizeof(float), h->hm.nq * sizeof(float), N, cudaMemcpyDeviceToDevice, st));
+  if (qvel) CUDA_TRY(cudaMemcpy2DAsync(h->phys + PHYS_QVEL, pitch, qvel, h->hm.nv * sizeof(float), h->hm.nv * sizeof(float), N, cudaMemcpyDeviceToDevice, st));
+  if (qacc_warm) CUDA_TRY(cudaMemcpy2DAsync(h->phys + PHYS_QACCW, pitch, qacc_warm, h->hm.nv * sizeof(float), h->hm.nv * sizeof(float), N, cudaMemcpyDeviceToDevice, st));
+  return ODUCK_OK;
+}
+
+int oduck_policy_forward(OduckHandle* h, const OduckPolicyWeights* w, const float* obs, const uint32_t* keys, int deterministic,
+                         float* action, float* raw_action, float* log_prob, void* stream) {
+  (void)h; (void)w; (void)obs; (void)keys; (void)deterministic; (void)action; (void)raw_action; (void)log_prob; (void)stream;
+  return fail(ODUCK_ERR_UNSUPPORTED, "oduck_policy_forward: actor-MLP kernel not built yet");
+}
+
+int oduck_get_buffer(OduckHandle* h, int id, void** ptr, int64_t* shape, int64_t* strides, int* dtype) {
+  if (!h || !ptr || !shape || !strides || !dtype) return fail(ODUCK_ERR_ARG, "oduck_get_buffer: bad argument");
+  const OduckModel& m = h->hm;
+  float* p = nullptr;
+  int64_t d1 = 0, d2 = 0, s0 = 0, s1 = 1;
+  int dt = ODUCK_DTYPE_F32;
+#define REC(base, stride, off, n1) p = (base) + (off); s0 = (stride); d1 = (n1);
+  switch (id) {
+    case ODUCK_BUF_QPOS: REC(h->phys, PHYS_STRIDE, 0, m.nq) break;
+    case ODUCK_BUF_QVEL: REC(h->phys, PHYS_STRIDE, PHYS_QVEL, m.nv) break;
+    case ODUCK_BUF_QACC_WARM: REC(h->phys, PHYS_STRIDE, PHYS_QACCW, m.nv) break;
+    case ODUCK_BUF_CTRL: REC(h->phys, PHYS_STRIDE, PHYS_CTRL, m.nu) break;
+    case ODUCK_BUF_QACC: REC(h->out, OUT_STRIDE, OUT_QACC, m.nv) break;
+    case ODUCK_BUF_SENSORDATA: REC(h->out, OUT_STRIDE, OUT_SENS, 24) break;
+    case ODUCK_BUF_EFC_FORCE: REC(h->out, OUT_STRIDE, OUT_EFC, h->nefc) break;
+    case ODUCK_BUF_CONTACT_DIST: REC(h->out, OUT_STRIDE, OUT_CDIST, 12) break;
+    case ODUCK_BUF_ACTUATOR_FORCE: REC(h->out, OUT_STRIDE, OUT_AFRC, m.nu) break;
+    case ODUCK_BUF_SITE_XPOS_FEET: REC(h->out, OUT_STRIDE, OUT_FEET, 6) break;
+    case ODUCK_BUF_OBS_STATE: REC(h->obs_state, ODUCK_OBS_STATE, 0, ODUCK_OBS_STATE) break;
+    case ODUCK_BUF_OBS_PRIV: REC(h->obs_priv, ODUCK_OBS_PRIV, 0, ODUCK_OBS_PRIV) break;
+    case ODUCK_BUF_REWARD: REC(h->reward, 1, 0, 0) break;
+    case ODUCK_BUF_DONE: REC(h->done, 1, 0, 0) break;
+    case ODUCK_BUF_TRUNCATION: REC(h->trunc, 1, 0, 0) break;
+    case ODUCK_BUF_METRICS: REC(h->metrics, ODUCK_NMETRIC, 0, ODUCK_NMETRIC) break;
+    case ODUCK_BUF_INFO_RNG: REC(h->info, INFO_STRIDE, INFO_RNG, 2) dt = ODUCK_DTYPE_U32; break;
+    case ODUCK_BUF_INFO_COMMAND: REC(h->info, INFO_STRIDE, INFO_CMD, 7) break;
+    case ODUCK_BUF_INFO_STEP: REC(h->info, INFO_STRIDE, INFO_STEP, 0) dt = ODUCK_DTYPE_I32; break;
+    case ODUCK_BUF_INFO_STEPS: REC(h->info, INFO_STRIDE, INFO_STEPS, 0) dt = ODUCK_DTYPE_I32; break;
+    case ODUCK_BUF_INFO_LAST_ACT: REC(h->info, INFO_STRIDE, INFO_LAST_ACT, 3) d2 = m.nu; s1 = 16; break;
+    case ODUCK_BUF_INFO_MOTOR_TARGETS: REC(h->info, INFO_STRIDE, INFO_TARGETS, m.nu) break;
+    case ODUCK_BUF_INFO_FEET_AIR_TIME: REC(h->info, INFO_STRIDE, INFO_AIR, 2) break;
+    case ODUCK_BUF_INFO_LAST_CONTACT: REC(h->info, INFO_STRIDE, INFO_LASTC, 2) break;
+    case ODUCK_BUF_INFO_SWING_PEAK: REC(h->info, INFO_STRIDE, INFO_SWING, 2) break;
+    case ODUCK_BUF_INFO_PUSH: REC(h->info, INFO_STRIDE, INFO_PUSH, 2) break;
+    case ODUCK_BUF_INFO_PUSH_STEP: REC(h->info, INFO_STRIDE, INFO_PUSH_STEP, 0) dt = ODUCK_DTYPE_I32; break;
+    case ODUCK_BUF_INFO_PUSH_INTERVAL: REC(h->info, INFO_STRIDE, INFO_PUSH_INT, 0) dt = ODUCK_DTYPE_I32; break;
+    case ODUCK_BUF_INFO_ACTION_HISTORY: REC(h->info, INFO_STRIDE, INFO_AHIST, h->hcfg.action_max_delay * m.nu) break;
+    case ODUCK_BUF_INFO_IMU_HISTORY: REC(h->info, INFO_STRIDE, INFO_IMUHIST, h->hcfg.imu_max_delay * 3) break;
+    case ODUCK_BUF_INFO_IMITATION_I: REC(h->info, INFO_STRIDE, INFO_IMIT_I, 0) dt = ODUCK_DTYPE_I32; break;
+    case ODUCK_BUF_INFO_REF_MOTION: REC(h->info, INFO_STRIDE, INFO_REF, ODUCK_REF_DIM) break;
+    case ODUCK_BUF_INFO_IMITATION_PHASE: REC(h->info, INFO_STRIDE, INFO_PHASE, 2) break;
+    case ODUCK_BUF_DR_PARAMS: REC(h->dr, DR_STRIDE, 0, DR_STRIDE) break;
+    case ODUCK_BUF_FIRST_QPOS: REC(h->first_phys, PHYS_STRIDE, 0, m.nq) break;
+    case ODUCK_BUF_FIRST_QVEL: REC(h->first_phys, PHYS_STRIDE, PHYS_QVEL, m.nv) break;
+    case ODUCK_BUF_FIRST_OBS_STATE: REC(h->first_obs_state, ODUCK_OBS_STATE, 0, ODUCK_OBS_STATE) break;
+    case ODUCK_BUF_FIRST_OBS_PRIV: REC(h->first_obs_priv, ODUCK_OBS_PRIV, 0, ODUCK_OBS_PRIV) break;
+    default: return fail(ODUCK_ERR_ARG, "oduck_get_buffer: unknown buffer id");
+  }
+#undef REC
+  *ptr = p;
+  shape[0] = h->n; shape[1] = d1; shape[2] = d2; shape[3] = 0;
+  strides[0] = s0; strides[1] = d2 ? s1 : 1; strides[2] = 1; strides[3] = 0;
+  *dtype = dt;
+  return ODUCK_OK;
+}
+
+}  // extern "C"

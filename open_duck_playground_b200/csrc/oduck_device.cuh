@@ -1,0 +1,272 @@
+// oduck_device.cuh -- device-side model tables and per-warp physics for the Open Duck step (sm_100a).
+//
+// Mapping: ONE WARP PER ENV.  Depending on the phase a lane is a dof (nv <= 32),
+// a body (nbody <= 32), a hull vertex (<= 32) or a contact-Jacobian row.  Tree recurrences run as
+// parallel prefix sums over the dof tree with warp shuffles; the joint-space inertia M and the Newton
+// Hessian H live in shared memory as packed lower triangles (bank-conflict free by row and by column,
+// because triangular numbers mod 32 are a permutation) and are factorised leaf-to-root (M = L^T L),
+// which has no fill-in on a kinematic tree.  Restates what mjx.step computes for the reference at
+// open_duck_mini_v2/joystick.py:420 (algorithms: SURVEY.md section 3.3 / 9; oracle/oduck_oracle.cpp).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define FULLMASK 0xffffffffu
+#define NLANE 32
+#define TRI(i) (((i) * ((i) + 1)) >> 1)
+#define JROWS 24          // 8 foot-floor contacts x (normal, tangent1, tangent2)
+#define JSTRIDE 33
+#define NCON_FLOOR 8
+#define NCON_ALL 12
+
+// record strides (floats) of the per-env state in HBM -- one contiguous record per env per group
+#define PHYS_STRIDE 128   // qpos[36] qvel[32] qacc_warm[32] ctrl[16] pad
+#define PHYS_QVEL 36
+#define PHYS_QACCW 68
+#define PHYS_CTRL 100
+#define DR_STRIDE 144     // mass[20] ipos1[3] fric0 frictionloss[32] armature[32] qpos0[36] kp[16]
+#define DR_IPOS1 20
+#define DR_FRIC0 23
+#define DR_FLOSS 24
+#define DR_ARM 56
+#define DR_QPOS0 88
+#define DR_KP 124
+#define OUT_STRIDE 224    // qacc[32] sensordata[24] efc_force[96] contact_dist[12] actuator_force[16] site_xpos_feet[6] pad imu_xmat[9] pad
+#define OUT_QACC 0
+#define OUT_SENS 32
+#define OUT_EFC 56
+#define OUT_CDIST 152
+#define OUT_AFRC 164
+#define OUT_FEET 180
+#define OUT_IMUMAT 188
+#define DBG_STRIDE 5120
+
+// flags of a dof lane
+#define DF_TRANS 1     // free-joint translation
+#define DF_ROT 2       // free-joint rotation (body-local axis)
+#define DF_HINGE 4
+#define DF_LIMITED 8
+#define DF_FLOSS 16
+
+struct DevModel {
+  int nbody, njnt, nq, nv, nu, maxdepth, prefix_rounds, nfr, nlim, nvert, enable_ff;
+  int imu_body, foot_body[2], foot_site_body[2], foot_chain[2];  // foot_chain: dof bitmask of the foot's ancestor chain
+  int imu_chain;
+  int iterations, ls_iterations;
+  float imu_pos[3], imu_rot[9], foot_site_pos[2][3];
+  float timestep, gravity[3], tolerance, ls_tolerance, meaninertia, impratio;
+  float sol_k, sol_b, dmin, dmax, width, mid, power;
+  float floor_mu, foot_mu;
+  // body tables (lane = body)
+  int b_parent[NLANE], b_depth[NLANE], b_jtype[NLANE], b_qadr0[NLANE], b_qadr1[NLANE], b_dofadr[NLANE], b_lastdof[NLANE];
+  int b_submask[NLANE];
+  float b_pos[3][NLANE], b_quat[4][NLANE], b_ipos[3][NLANE], b_Ib[6][NLANE], b_mass[NLANE], b_ax0[3][NLANE], b_ax1[3][NLANE], b_invw0[NLANE];
+  // dof tables (lane = dof)
+  int d_body[NLANE], d_parent[NLANE], d_vparent[NLANE], d_flags[NLANE], d_ancmask[NLANE], d_bsubmask[NLANE], d_qadr[NLANE], d_act[NLANE];
+  int d_frrow[NLANE], d_limrow[NLANE];
+  float d_damping[NLANE], d_invw0[NLANE], d_lo[NLANE], d_hi[NLANE], d_Dfric[NLANE], d_floss[NLANE], d_arm[NLANE];
+  float d_kv[NLANE], d_kp[NLANE], d_clo[NLANE], d_chi[NLANE], d_flo[NLANE], d_fhi[NLANE];
+  float vert[2][3][NLANE];
+  float key_qpos[36], key_ctrl[16], qpos0[36];
+  int act_dof[16], act_qadr[16], act_bl_qadr[16];
+};
+
+// per-warp shared memory
+struct WarpSmem {
+  float A[528];               // M, packed lower
+  float H[528];               // chol(M), then H = M + J^T D J and its factor
+  float J[JROWS][JSTRIDE];    // contact Jacobian rows (frame-rotated point Jacobians)
+  float xpos[3][NLANE];
+  float xmat[9][NLANE];
+  float cdof[6][NLANE];
+  float qpos[36];
+  float qpos0[36];
+  float con[NCON_ALL][8];     // dist, pos xyz, F(n,t1,t2), pad
+  float misc[64];
+  float outrec[OUT_STRIDE];     // staged outputs of the last forward (copied to HBM once per launch)
+};
+
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
+  return v;
+}
+__device__ __forceinline__ float wmaxf(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULLMASK, v, o));
+  return v;
+}
+// argmax with first-index tie break (jp.argmax semantics); every lane gets the winner
+__device__ __forceinline__ int wargmax(float v, int lane) {
+  int idx = lane;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    float ov = __shfl_xor_sync(FULLMASK, v, o);
+    int oi = __shfl_xor_sync(FULLMASK, idx, o);
+    bool take = (ov > v) || (ov == v && oi < idx);
+    v = take ? ov : v;
+    idx = take ? oi : idx;
+  }
+  return idx;
+}
+__device__ __forceinline__ float wargmax_val(float v, int lane, int* out_idx) {
+  int idx = lane;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    float ov = __shfl_xor_sync(FULLMASK, v, o);
+    int oi = __shfl_xor_sync(FULLMASK, idx, o);
+    bool take = (ov > v) || (ov == v && oi < idx);
+    v = take ? ov : v;
+    idx = take ? oi : idx;
+  }
+  *out_idx = idx;
+  return v;
+}
+
+struct V3 { float x, y, z; };
+__device__ __forceinline__ V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ V3 cross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+__device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 operator*(float s, V3 a) { return v3(s * a.x, s * a.y, s * a.z); }
+struct Q4 { float w, x, y, z; };
+__device__ __forceinline__ Q4 qmul(Q4 a, Q4 b) {
+  Q4 r;
+  r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
+  r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
+  r.y = a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x;
+  r.z = a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w;
+  return r;
+}
+__device__ __forceinline__ V3 qrot(Q4 q, V3 v) {
+  V3 u = v3(q.x, q.y, q.z);
+  V3 t = 2.f * cross(u, v);
+  return v + q.w * t + cross(u, t);
+}
+__device__ __forceinline__ Q4 qnormalize(Q4 q) {
+  float n = sqrtf(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
+  if (n < 1e-15f) { q.w = 1.f; q.x = q.y = q.z = 0.f; return q; }
+  float inv = 1.f / n;
+  q.w *= inv; q.x *= inv; q.y *= inv; q.z *= inv;
+  return q;
+}
+__device__ __forceinline__ Q4 axis_angle(V3 ax, float ang) {
+  float s, c;
+  sincosf(0.5f * ang, &s, &c);
+  Q4 q; q.w = c; q.x = s * ax.x; q.y = s * ax.y; q.z = s * ax.z;
+  return q;
+}
+
+struct S6 { float a0, a1, a2, l0, l1, l2; };   // spatial vector [angular, linear]
+__device__ __forceinline__ S6 s6zero() { S6 r; r.a0 = r.a1 = r.a2 = r.l0 = r.l1 = r.l2 = 0.f; return r; }
+__device__ __forceinline__ S6 s6add(S6 a, S6 b) { S6 r; r.a0 = a.a0 + b.a0; r.a1 = a.a1 + b.a1; r.a2 = a.a2 + b.a2; r.l0 = a.l0 + b.l0; r.l1 = a.l1 + b.l1; r.l2 = a.l2 + b.l2; return r; }
+__device__ __forceinline__ S6 s6scale(S6 a, float s) { S6 r; r.a0 = a.a0 * s; r.a1 = a.a1 * s; r.a2 = a.a2 * s; r.l0 = a.l0 * s; r.l1 = a.l1 * s; r.l2 = a.l2 * s; return r; }
+__device__ __forceinline__ float s6dot(S6 a, S6 b) { return a.a0 * b.a0 + a.a1 * b.a1 + a.a2 * b.a2 + a.l0 * b.l0 + a.l1 * b.l1 + a.l2 * b.l2; }
+__device__ __forceinline__ S6 s6shfl(S6 a, int src) {
+  S6 r;
+  r.a0 = __shfl_sync(FULLMASK, a.a0, src); r.a1 = __shfl_sync(FULLMASK, a.a1, src); r.a2 = __shfl_sync(FULLMASK, a.a2, src);
+  r.l0 = __shfl_sync(FULLMASK, a.l0, src); r.l1 = __shfl_sync(FULLMASK, a.l1, src); r.l2 = __shfl_sync(FULLMASK, a.l2, src);
+  return r;
+}
+__device__ __forceinline__ S6 cross_motion(S6 v, S6 m) {   // mju_crossMotion
+  V3 va = v3(v.a0, v.a1, v.a2), vl = v3(v.l0, v.l1, v.l2), ma = v3(m.a0, m.a1, m.a2), ml = v3(m.l0, m.l1, m.l2);
+  V3 a = cross(va, ma), l = cross(va, ml) + cross(vl, ma);
+  S6 r; r.a0 = a.x; r.a1 = a.y; r.a2 = a.z; r.l0 = l.x; r.l1 = l.y; r.l2 = l.z;
+  return r;
+}
+__device__ __forceinline__ S6 cross_force(S6 v, S6 f) {    // mju_crossForce
+  V3 va = v3(v.a0, v.a1, v.a2), vl = v3(v.l0, v.l1, v.l2), fa = v3(f.a0, f.a1, f.a2), fl = v3(f.l0, f.l1, f.l2);
+  V3 a = cross(va, fa) + cross(vl, fl), l = cross(va, fl);
+  S6 r; r.a0 = a.x; r.a1 = a.y; r.a2 = a.z; r.l0 = l.x; r.l1 = l.y; r.l2 = l.z;
+  return r;
+}
+// 10-number spatial inertia about the common reference point (world axes)
+struct I10 { float xx, yy, zz, xy, xz, yz, hx, hy, hz, m; };
+__device__ __forceinline__ S6 inert_mul(const I10& I, S6 v) {  // mju_mulInertVec
+  S6 r;
+  r.a0 = I.xx * v.a0 + I.xy * v.a1 + I.xz * v.a2 - I.hz * v.l1 + I.hy * v.l2;
+  r.a1 = I.xy * v.a0 + I.yy * v.a1 + I.yz * v.a2 + I.hz * v.l0 - I.hx * v.l2;
+  r.a2 = I.xz * v.a0 + I.yz * v.a1 + I.zz * v.a2 - I.hy * v.l0 + I.hx * v.l1;
+  r.l0 = I.hz * v.a1 - I.hy * v.a2 + I.m * v.l0;
+  r.l1 = I.hx * v.a2 - I.hz * v.a0 + I.m * v.l1;
+  r.l2 = I.hy * v.a0 - I.hx * v.a1 + I.m * v.l2;
+  return r;
+}
+
+// ---------------------------------------------------------------------------------- dense kernels on packed triangles
+// In-place leaf-to-root factorisation A = L^T L (L lower, stored where A was).  With tree == true only the
+// ancestors of k are visited (exact for the sparsity of a kinematic tree); otherwise every earlier row.
+__device__ __forceinline__ void chol_rev(float* A, int n, int lane, const int* dparent, bool tree) {
+  for (int k = n - 1; k >= 0; --k) {
+    const int rk = TRI(k);
+    float akk = A[rk + k];
+    float inv = rsqrtf(akk);
+    float lkj = 0.f;
+    if (lane < k) { lkj = A[rk + lane] * inv; A[rk + lane] = lkj; }
+    else if (lane == k) A[rk + k] = akk * inv;
+    __syncwarp();
+    if (tree) {
+      for (int i = dparent[k]; i >= 0; i = dparent[i]) {
+        float lki = A[rk + i];
+        if (lane <= i) A[TRI(i) + lane] -= lki * lkj;
+      }
+    } else {
+      for (int i = k - 1; i >= 0; --i) {
+        float lki = A[rk + i];
+        if (lki != 0.f && lane <= i) A[TRI(i) + lane] -= lki * lkj;
+      }
+    }
+    __syncwarp();
+  }
+}
+// Solve (L^T L) x = b with b, x distributed one element per lane.
+__device__ __forceinline__ float chol_rev_solve(const float* L, int n, int lane, float b) {
+  for (int k = n - 1; k >= 0; --k) {
+    float yk = __shfl_sync(FULLMASK, b, k) / L[TRI(k) + k];
+    if (lane == k) b = yk;
+    else if (lane < k) b -= L[TRI(k) + lane] * yk;
+  }
+  for (int j = 0; j < n; ++j) {
+    float xj = __shfl_sync(FULLMASK, b, j) / L[TRI(j) + j];
+    if (lane == j) b = xj;
+    else if (lane > j && lane < n) b -= L[TRI(lane) + j] * xj;
+  }
+  return b;
+}
+// y = A x for the packed symmetric matrix; one element per lane.
+__device__ __forceinline__ float symv(const float* A, int n, int lane, float x) {
+  float acc = 0.f;
+  const int ri = TRI(lane);
+  for (int j = 0; j < n; ++j) {
+    float xj = __shfl_sync(FULLMASK, x, j);
+    int idx = (j <= lane) ? ri + j : TRI(j) + lane;
+    float a = A[idx];
+    acc = fmaf(a, xj, acc);
+  }
+  return lane < n ? acc : 0.f;
+}
+// products of the contact rows with a dof vector: lane r gets J[r] . x
+__device__ __forceinline__ float jdot(const float (*J)[JSTRIDE], int n, int lane, float x) {
+  float acc = 0.f;
+  const float* row = J[lane < JROWS ? lane : 0];
+  for (int d = 0; d < n; ++d) acc = fmaf(row[d], __shfl_sync(FULLMASK, x, d), acc);
+  return lane < JROWS ? acc : 0.f;
+}
+
+// constraint.py _kbi impedance for a signed distance
+__device__ __forceinline__ float impedance(const DevModel& m, float pos) {
+  float x = fabsf(pos) / m.width;
+  float y;
+  if (m.power == 2.f) {
+    y = x < m.mid ? x * x / m.mid : 1.f - (1.f - x) * (1.f - x) / (1.f - m.mid);
+  } else {
+    float ia = (1.f / powf(m.mid, m.power - 1.f)) * powf(x, m.power);
+    float ib = 1.f - (1.f / powf(1.f - m.mid, m.power - 1.f)) * powf(1.f - x, m.power);
+    y = x < m.mid ? ia : ib;
+  }
+  float imp = m.dmin + y * (m.dmax - m.dmin);
+  imp = fminf(fmaxf(imp, m.dmin), m.dmax);
+  if (x > 1.f) imp = m.dmax;
+  return imp;
+}

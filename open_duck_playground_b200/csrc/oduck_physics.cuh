@@ -1,0 +1,628 @@
+// oduck_physics.cuh -- one mjx.forward (+ optional Euler step) for one env, executed by one warp.
+// Phases follow MJX forward(): fwd_position (kinematics, com_pos, crb, factor_m, collision,
+// make_constraint), fwd_velocity, fwd_actuation, fwd_acceleration, solver.solve (Newton, 1 iteration,
+// parallel line search), sensors, euler.  See oduck_device.cuh for the lane mapping.
+#pragma once
+#include "oduck_device.cuh"
+
+// per-thread state that persists across the substeps of one launch
+struct Lane {
+  float qvel, qaccw, qacc, ctrl, kp, floss, arm;   // dof role (ctrl/kp: the dof's actuator, if any)
+  float mass;                                     // body role
+  V3 ipos;
+};
+
+struct LSPoint { float alpha, cost, d0, d1; };
+
+template <bool DBG>
+__device__ __forceinline__ void forward_euler(const DevModel& m, WarpSmem& s, Lane& L, const int lane, const bool last,
+                                              const bool integrate, float* __restrict__ out, float* __restrict__ dbg) {
+  const int nv = m.nv, nb = m.nbody;
+  // ------------------------------------------------------------------ kinematics (lane = body)
+  const int par = m.b_parent[lane], dep = m.b_depth[lane], jt = m.b_jtype[lane];
+  V3 xp = v3(0.f, 0.f, 0.f);
+  Q4 xq; xq.w = 1.f; xq.x = xq.y = xq.z = 0.f;
+  V3 ax0w = v3(0.f, 0.f, 0.f), ax1w = v3(0.f, 0.f, 0.f);
+  for (int lev = 1; lev <= m.maxdepth; ++lev) {
+    V3 pp = v3(__shfl_sync(FULLMASK, xp.x, par), __shfl_sync(FULLMASK, xp.y, par), __shfl_sync(FULLMASK, xp.z, par));
+    Q4 pq;
+    pq.w = __shfl_sync(FULLMASK, xq.w, par); pq.x = __shfl_sync(FULLMASK, xq.x, par);
+    pq.y = __shfl_sync(FULLMASK, xq.y, par); pq.z = __shfl_sync(FULLMASK, xq.z, par);
+    if (dep == lev) {
+      V3 bp = v3(m.b_pos[0][lane], m.b_pos[1][lane], m.b_pos[2][lane]);
+      Q4 bq; bq.w = m.b_quat[0][lane]; bq.x = m.b_quat[1][lane]; bq.y = m.b_quat[2][lane]; bq.z = m.b_quat[3][lane];
+      xp = pp + qrot(pq, bp);
+      xq = qmul(pq, bq);
+      if (jt == 1) {
+        const int qa = m.b_qadr0[lane];
+        xp = v3(s.qpos[qa], s.qpos[qa + 1], s.qpos[qa + 2]);
+        xq.w = s.qpos[qa + 3]; xq.x = s.qpos[qa + 4]; xq.y = s.qpos[qa + 5]; xq.z = s.qpos[qa + 6];
+      } else if (jt >= 2) {
+        V3 a0 = v3(m.b_ax0[0][lane], m.b_ax0[1][lane], m.b_ax0[2][lane]);
+        ax0w = qrot(xq, a0);
+        const int qa = m.b_qadr0[lane];
+        xq = qmul(xq, axis_angle(a0, s.qpos[qa] - s.qpos0[qa]));
+        if (jt == 3) {
+          V3 a1 = v3(m.b_ax1[0][lane], m.b_ax1[1][lane], m.b_ax1[2][lane]);
+          ax1w = qrot(xq, a1);
+          const int qb = m.b_qadr1[lane];
+          xq = qmul(xq, axis_angle(a1, s.qpos[qb] - s.qpos0[qb]));
+        }
+      }
+      xq = qnormalize(xq);
+    }
+  }
+  float R[9];
+  {
+    const float w = xq.w, x = xq.x, y = xq.y, z = xq.z;
+    R[0] = 1.f - 2.f * (y * y + z * z); R[1] = 2.f * (x * y - w * z); R[2] = 2.f * (x * z + w * y);
+    R[3] = 2.f * (x * y + w * z); R[4] = 1.f - 2.f * (x * x + z * z); R[5] = 2.f * (y * z - w * x);
+    R[6] = 2.f * (x * z - w * y); R[7] = 2.f * (y * z + w * x); R[8] = 1.f - 2.f * (x * x + y * y);
+  }
+  s.xpos[0][lane] = xp.x; s.xpos[1][lane] = xp.y; s.xpos[2][lane] = xp.z;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) s.xmat[k][lane] = R[k];
+  if (lane < nb) {
+    const int da = m.b_dofadr[lane];
+    if (jt == 1) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        s.cdof[0][da + k] = 0.f; s.cdof[1][da + k] = 0.f; s.cdof[2][da + k] = 0.f;
+        s.cdof[3][da + k] = (k == 0); s.cdof[4][da + k] = (k == 1); s.cdof[5][da + k] = (k == 2);
+        s.cdof[0][da + 3 + k] = R[k]; s.cdof[1][da + 3 + k] = R[3 + k]; s.cdof[2][da + 3 + k] = R[6 + k];
+      }
+    } else if (jt >= 2) {
+      s.cdof[0][da] = ax0w.x; s.cdof[1][da] = ax0w.y; s.cdof[2][da] = ax0w.z;
+      if (jt == 3) { s.cdof[0][da + 1] = ax1w.x; s.cdof[1][da + 1] = ax1w.y; s.cdof[2][da + 1] = ax1w.z; }
+    }
+  }
+  __syncwarp();
+
+  // ------------------------------------------------------------------ com_pos (lane = body)
+  V3 xi = v3(xp.x + R[0] * L.ipos.x + R[1] * L.ipos.y + R[2] * L.ipos.z,
+             xp.y + R[3] * L.ipos.x + R[4] * L.ipos.y + R[5] * L.ipos.z,
+             xp.z + R[6] * L.ipos.x + R[7] * L.ipos.y + R[8] * L.ipos.z);
+  const float ms = L.mass;
+  const float mt = wsum(ms);
+  const float imt = 1.f / fmaxf(mt, 1e-15f);
+  const V3 com = v3(wsum(ms * xi.x) * imt, wsum(ms * xi.y) * imt, wsum(ms * xi.z) * imt);
+  I10 cin;
+  {
+    // body-frame inertia about its COM (constant) rotated into the world, shifted to the common reference point
+    const float b0 = m.b_Ib[0][lane], b1 = m.b_Ib[1][lane], b2 = m.b_Ib[2][lane], b3 = m.b_Ib[3][lane], b4 = m.b_Ib[4][lane], b5 = m.b_Ib[5][lane];
+    float T[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      T[3 * r + 0] = R[3 * r] * b0 + R[3 * r + 1] * b3 + R[3 * r + 2] * b4;
+      T[3 * r + 1] = R[3 * r] * b3 + R[3 * r + 1] * b1 + R[3 * r + 2] * b5;
+      T[3 * r + 2] = R[3 * r] * b4 + R[3 * r + 1] * b5 + R[3 * r + 2] * b2;
+    }
+    const V3 d = xi - com;
+    cin.xx = T[0] * R[0] + T[1] * R[1] + T[2] * R[2] + ms * (d.y * d.y + d.z * d.z);
+    cin.yy = T[3] * R[3] + T[4] * R[4] + T[5] * R[5] + ms * (d.x * d.x + d.z * d.z);
+    cin.zz = T[6] * R[6] + T[7] * R[7] + T[8] * R[8] + ms * (d.x * d.x + d.y * d.y);
+    cin.xy = T[0] * R[3] + T[1] * R[4] + T[2] * R[5] - ms * d.x * d.y;
+    cin.xz = T[0] * R[6] + T[1] * R[7] + T[2] * R[8] - ms * d.x * d.z;
+    cin.yz = T[3] * R[6] + T[4] * R[7] + T[5] * R[8] - ms * d.y * d.z;
+    cin.hx = ms * d.x; cin.hy = ms * d.y; cin.hz = ms * d.z; cin.m = ms;
+  }
+
+  // ------------------------------------------------------------------ cdof (lane = dof)
+  const int flags = m.d_flags[lane];
+  const int dbody = m.d_body[lane];
+  S6 cd = s6zero();
+  if (lane < nv) {
+    cd.a0 = s.cdof[0][lane]; cd.a1 = s.cdof[1][lane]; cd.a2 = s.cdof[2][lane];
+    if (flags & DF_TRANS) {
+      cd.l0 = s.cdof[3][lane]; cd.l1 = s.cdof[4][lane]; cd.l2 = s.cdof[5][lane];
+    } else {
+      V3 off = com - v3(s.xpos[0][dbody], s.xpos[1][dbody], s.xpos[2][dbody]);
+      V3 l = cross(v3(cd.a0, cd.a1, cd.a2), off);
+      cd.l0 = l.x; cd.l1 = l.y; cd.l2 = l.z;
+      s.cdof[3][lane] = l.x; s.cdof[4][lane] = l.y; s.cdof[5][lane] = l.z;
+    }
+  }
+  __syncwarp();
+
+  // ------------------------------------------------------------------ crb: subtree sums of cinert (lane = body)
+  I10 crb;
+  crb.xx = crb.yy = crb.zz = crb.xy = crb.xz = crb.yz = crb.hx = crb.hy = crb.hz = crb.m = 0.f;
+  {
+    const int sub = m.b_submask[lane];
+    for (int c = 1; c < nb; ++c) {
+      const bool in = (sub >> c) & 1;
+#define ACC(f) { float v = __shfl_sync(FULLMASK, cin.f, c); if (in) crb.f += v; }
+      ACC(xx) ACC(yy) ACC(zz) ACC(xy) ACC(xz) ACC(yz) ACC(hx) ACC(hy) ACC(hz) ACC(m)
+#undef ACC
+    }
+  }
+  // ------------------------------------------------------------------ M (lane = dof row i), packed lower triangle
+  {
+    I10 cb;
+#define GET(f) cb.f = __shfl_sync(FULLMASK, crb.f, dbody);
+    GET(xx) GET(yy) GET(zz) GET(xy) GET(xz) GET(yz) GET(hx) GET(hy) GET(hz) GET(m)
+#undef GET
+    const S6 buf = inert_mul(cb, cd);
+    const int anc = m.d_ancmask[lane];
+    const int ri = TRI(lane);
+    for (int j = 0; j < nv; ++j) {
+      S6 cj; cj.a0 = s.cdof[0][j]; cj.a1 = s.cdof[1][j]; cj.a2 = s.cdof[2][j]; cj.l0 = s.cdof[3][j]; cj.l1 = s.cdof[4][j]; cj.l2 = s.cdof[5][j];
+      float v = s6dot(cj, buf);
+      if (j <= lane && lane < nv) {
+        float val = ((anc >> j) & 1) ? v : 0.f;
+        if (j == lane) val += L.arm;
+        s.A[ri + j] = val;
+      }
+    }
+  }
+  __syncwarp();
+  for (int idx = lane; idx < TRI(nv); idx += 32) s.H[idx] = s.A[idx];
+  __syncwarp();
+  chol_rev(s.H, nv, lane, m.d_parent, true);
+
+  // ------------------------------------------------------------------ com_vel: prefix sums over the dof tree (lane = dof)
+  const int dpar = m.d_parent[lane];
+  S6 Sv = lane < nv ? s6scale(cd, L.qvel) : s6zero();
+  {
+    int P = dpar;
+    for (int r = 0; r < m.prefix_rounds; ++r) {
+      const int src = P < 0 ? 0 : P;
+      S6 o = s6shfl(Sv, src);
+      int Pn = __shfl_sync(FULLMASK, P, src);
+      if (P >= 0) { Sv = s6add(Sv, o); P = Pn; }
+    }
+  }
+  S6 cdd = s6zero();
+  {
+    const int vp = m.d_vparent[lane];
+    S6 cvb = s6shfl(Sv, vp < 0 ? 0 : vp);
+    if (vp < 0) cvb = s6zero();
+    if (lane < nv && !(flags & DF_TRANS)) cdd = cross_motion(cvb, cd);
+  }
+  const int lastd = m.b_lastdof[lane];
+  S6 cvel = s6shfl(Sv, lastd < 0 ? 0 : lastd);
+  if (lastd < 0) cvel = s6zero();
+  // ------------------------------------------------------------------ rne (bias force)
+  S6 Sa = lane < nv ? s6scale(cdd, L.qvel) : s6zero();
+  {
+    int P = dpar;
+    for (int r = 0; r < m.prefix_rounds; ++r) {
+      const int src = P < 0 ? 0 : P;
+      S6 o = s6shfl(Sa, src);
+      int Pn = __shfl_sync(FULLMASK, P, src);
+      if (P >= 0) { Sa = s6add(Sa, o); P = Pn; }
+    }
+  }
+  float qfrc_bias = 0.f;
+  {
+    S6 cacc = s6shfl(Sa, lastd < 0 ? 0 : lastd);
+    if (lastd < 0) cacc = s6zero();
+    cacc.l0 -= m.gravity[0]; cacc.l1 -= m.gravity[1]; cacc.l2 -= m.gravity[2];
+    S6 cfrc = s6add(inert_mul(cin, cacc), cross_force(cvel, inert_mul(cin, cvel)));
+    const int bsub = m.d_bsubmask[lane];
+    for (int b = 1; b < nb; ++b) {
+      S6 f = s6shfl(cfrc, b);
+      if ((bsub >> b) & 1) qfrc_bias += s6dot(cd, f);
+    }
+  }
+  // ------------------------------------------------------------------ passive + actuation + smooth acceleration (lane = dof)
+  const int qadr = m.d_qadr[lane];
+  const float qd = (flags & DF_HINGE) ? s.qpos[qadr] : 0.f;
+  float aforce = 0.f;
+  if (m.d_act[lane] >= 0) {
+    float c = fminf(fmaxf(L.ctrl, m.d_clo[lane]), m.d_chi[lane]);
+    float f = L.kp * c - L.kp * qd - m.d_kv[lane] * L.qvel;
+    aforce = fminf(fmaxf(f, m.d_flo[lane]), m.d_fhi[lane]);
+  }
+  const float fs = lane < nv ? (-m.d_damping[lane] * L.qvel - qfrc_bias + aforce) : 0.f;   // qfrc_smooth
+  const float as = chol_rev_solve(s.H, nv, lane, fs);                                      // qacc_smooth
+
+  // ------------------------------------------------------------------ collision: plane (z = 0) vs convex foot hulls (lane = vertex)
+  for (int f = 0; f < 2; ++f) {
+    const int fb = m.foot_body[f];
+    float Rf[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Rf[k] = s.xmat[k][fb];
+    const V3 p0 = v3(s.xpos[0][fb], s.xpos[1][fb], s.xpos[2][fb]);
+    const bool valid = lane < m.nvert;
+    const V3 vl = v3(m.vert[f][0][lane], m.vert[f][1][lane], m.vert[f][2][lane]);
+    const V3 pw = v3(p0.x + Rf[0] * vl.x + Rf[1] * vl.y + Rf[2] * vl.z, p0.y + Rf[3] * vl.x + Rf[4] * vl.y + Rf[5] * vl.z,
+                     p0.z + Rf[6] * vl.x + Rf[7] * vl.y + Rf[8] * vl.z);
+    const float support = -pw.z;
+    const float ninf = -__int_as_float(0x7f800000);
+    const float smax = wmaxf(valid ? support : ninf);
+    const float thr = fmaxf(0.f, smax - 1e-3f);
+    const bool mask = valid && support > thr;
+    const float dm = valid ? (mask ? 0.f : -1e6f) : ninf;
+    const V3 nl = v3(Rf[6], Rf[7], Rf[8]);  // plane normal in the hull frame
+    int idx[4];
+    idx[0] = wargmax(dm, lane);
+    const V3 va = v3(__shfl_sync(FULLMASK, vl.x, idx[0]), __shfl_sync(FULLMASK, vl.y, idx[0]), __shfl_sync(FULLMASK, vl.z, idx[0]));
+    const V3 ap = va - vl;
+    idx[1] = wargmax(dot(ap, ap) + dm, lane);
+    const V3 vb = v3(__shfl_sync(FULLMASK, vl.x, idx[1]), __shfl_sync(FULLMASK, vl.y, idx[1]), __shfl_sync(FULLMASK, vl.z, idx[1]));
+    const V3 ab = cross(nl, va - vb);
+    idx[2] = wargmax(fabsf(dot(ap, ab)) + dm, lane);
+    const V3 vc = v3(__shfl_sync(FULLMASK, vl.x, idx[2]), __shfl_sync(FULLMASK, vl.y, idx[2]), __shfl_sync(FULLMASK, vl.z, idx[2]));
+    const V3 ac = cross(nl, va - vc), bc = cross(nl, vb - vc), bp = vb - vl;
+    int i1, i2;
+    const float v1 = wargmax_val(fabsf(dot(bp, bc)) + dm, lane, &i1);
+    const float v2 = wargmax_val(fabsf(dot(ap, ac)) + dm, lane, &i2);
+    idx[3] = (v1 >= v2) ? i1 : i2;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float sup = __shfl_sync(FULLMASK, support, idx[c]);
+      const float px = __shfl_sync(FULLMASK, pw.x, idx[c]), py = __shfl_sync(FULLMASK, pw.y, idx[c]), pz = __shfl_sync(FULLMASK, pw.z, idx[c]);
+      bool uniq = true;
+#pragma unroll
+      for (int p = 0; p < c; ++p) uniq = uniq && (idx[p] != idx[c]);
+      const float dist = uniq ? -sup : 1.f;
+      if (lane == c) {
+        float* cc = s.con[4 * f + c];
+        cc[0] = dist; cc[1] = px; cc[2] = py; cc[3] = pz - 0.5f * dist;
+      }
+    }
+  }
+  if (lane >= NCON_FLOOR && lane < NCON_ALL) { s.con[lane][0] = 1.f; s.con[lane][1] = s.con[lane][2] = s.con[lane][3] = 0.f; }
+  __syncwarp();
+
+  // ------------------------------------------------------------------ contact Jacobian rows (lane = dof): frame = [n=+z, t1=+y, t2=-x]
+  for (int c = 0; c < NCON_FLOOR; ++c) {
+    const float dist = s.con[c][0];
+    float jn = 0.f, jt1 = 0.f, jt2 = 0.f;
+    if (dist < 0.f && ((m.foot_chain[c >> 2] >> lane) & 1)) {
+      V3 off = v3(s.con[c][1], s.con[c][2], s.con[c][3]) - com;
+      V3 jp = v3(cd.l0, cd.l1, cd.l2) + cross(v3(cd.a0, cd.a1, cd.a2), off);
+      jn = jp.z; jt1 = jp.y; jt2 = -jp.x;
+    }
+    s.J[3 * c][lane] = jn; s.J[3 * c + 1][lane] = jt1; s.J[3 * c + 2][lane] = jt2;
+  }
+  __syncwarp();
+
+  // ------------------------------------------------------------------ constraint rows
+  // dof lane: friction-loss row and joint-limit row; contact lane c < 8: four pyramid rows
+  const bool hasf = (flags & DF_FLOSS) != 0;
+  const float Df = m.d_Dfric[lane];
+  const float floss = L.floss;
+  const float rf = hasf ? floss / Df : 0.f;
+  const float areff = -m.sol_b * L.qvel;
+  bool lact = false;
+  float Dl = 0.f, arefl = 0.f, lsign = 0.f;
+  if (flags & DF_LIMITED) {
+    const float dmin_ = qd - m.d_lo[lane], dmax_ = m.d_hi[lane] - qd;
+    const float pos = fminf(dmin_, dmax_);
+    if (pos < 0.f) {
+      lact = true;
+      lsign = dmin_ < dmax_ ? 1.f : -1.f;
+      const float imp = impedance(m, pos);
+      Dl = 1.f / fmaxf(m.d_invw0[lane] * (1.f - imp) / imp, 1e-15f);
+      arefl = -m.sol_b * (lsign * L.qvel) - m.sol_k * imp * pos;
+    }
+  }
+  const int cl = lane < NCON_FLOOR ? lane : 0;
+  const float cdist = s.con[cl][0];
+  const bool cact = lane < NCON_FLOOR && cdist < 0.f;
+  const float mu = m.floor_mu;
+  float Dc = 0.f, arefc[4] = {0.f, 0.f, 0.f, 0.f};
+  {
+    const float pr = jdot(s.J, nv, lane, L.qvel);
+    const float pn = __shfl_sync(FULLMASK, pr, 3 * cl), pt1 = __shfl_sync(FULLMASK, pr, 3 * cl + 1), pt2 = __shfl_sync(FULLMASK, pr, 3 * cl + 2);
+    if (cact) {
+      const float imp = impedance(m, cdist);
+      const float t = m.b_invw0[m.foot_body[cl >> 2]];
+      const float invw = (t + mu * mu * t) * 2.f * mu * mu / m.impratio;
+      Dc = 1.f / fmaxf(invw * (1.f - imp) / imp, 1e-15f);
+      const float kp_ = m.sol_k * imp * cdist;
+      arefc[0] = -m.sol_b * (pn + mu * pt1) - kp_;
+      arefc[1] = -m.sol_b * (pn - mu * pt1) - kp_;
+      arefc[2] = -m.sol_b * (pn + mu * pt2) - kp_;
+      arefc[3] = -m.sol_b * (pn - mu * pt2) - kp_;
+    }
+  }
+  // J x for the four pyramid rows of this lane's contact
+#define CONTACT_PRODUCTS(x, o)                                                                                         \
+  {                                                                                                                    \
+    const float pr_ = jdot(s.J, nv, lane, (x));                                                                        \
+    const float pn_ = __shfl_sync(FULLMASK, pr_, 3 * cl), p1_ = __shfl_sync(FULLMASK, pr_, 3 * cl + 1), p2_ = __shfl_sync(FULLMASK, pr_, 3 * cl + 2); \
+    o[0] = pn_ + mu * p1_; o[1] = pn_ - mu * p1_; o[2] = pn_ + mu * p2_; o[3] = pn_ - mu * p2_;                         \
+  }
+  // lane-local constraint cost for given Jaref values
+#define ROW_COST(Jf_, Jl_, Jc_, acc)                                                                                   \
+  {                                                                                                                    \
+    if (hasf) {                                                                                                        \
+      if ((Jf_) <= -rf) acc += floss * (-0.5f * rf - (Jf_));                                                           \
+      else if ((Jf_) >= rf) acc += floss * (-0.5f * rf + (Jf_));                                                       \
+      else acc += 0.5f * Df * (Jf_) * (Jf_);                                                                           \
+    }                                                                                                                  \
+    if (lact && (Jl_) < 0.f) acc += 0.5f * Dl * (Jl_) * (Jl_);                                                         \
+    if (cact) {                                                                                                        \
+      _Pragma("unroll") for (int r_ = 0; r_ < 4; ++r_) if (Jc_[r_] < 0.f) acc += 0.5f * Dc * Jc_[r_] * Jc_[r_];        \
+    }                                                                                                                  \
+  }
+
+  // ------------------------------------------------------------------ solver.solve: warm start selection
+  float qacc, Ma, Jf, Jl, Jc[4], gauss;
+  {
+    const float qw = lane < nv ? L.qaccw : 0.f;
+    const float Maw = symv(s.A, nv, lane, qw);
+    float Jcw[4], Jcs[4];
+    CONTACT_PRODUCTS(qw, Jcw)
+    CONTACT_PRODUCTS(as, Jcs)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { Jcw[r] -= arefc[r]; Jcs[r] -= arefc[r]; }
+    const float Jfw = qw - areff, Jfs = as - areff;
+    const float Jlw = lsign * qw - arefl, Jls = lsign * as - arefl;
+    float cw = 0.5f * (Maw - fs) * (qw - as), cs = 0.f;
+    const float gw = wsum(cw);
+    ROW_COST(Jfw, Jlw, Jcw, cw)
+    ROW_COST(Jfs, Jls, Jcs, cs)
+    const float costw = wsum(cw), costs = wsum(cs);
+    const bool usew = costw < costs;
+    qacc = usew ? qw : as;
+    Ma = usew ? Maw : fs;
+    Jf = usew ? Jfw : Jfs;
+    Jl = usew ? Jlw : Jls;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) Jc[r] = usew ? Jcw[r] : Jcs[r];
+    gauss = usew ? gw : 0.f;
+    if (DBG && lane == 0) { dbg[2536] = costw; dbg[2537] = costs; }
+  }
+  // ------------------------------------------------------------------ gradient + Hessian + Newton direction
+  float search, grad;
+  {
+    // constraint forces at the start point (update_constraint)
+    float ff = 0.f; bool fquad = false;
+    if (hasf) {
+      if (Jf <= -rf) ff = floss; else if (Jf >= rf) ff = -floss; else { ff = -Df * Jf; fquad = true; }
+    }
+    const bool lon = lact && Jl < 0.f;
+    const float fl = lon ? -Dl * Jl : 0.f;
+    float fc[4]; bool ca[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { ca[r] = cact && Jc[r] < 0.f; fc[r] = ca[r] ? -Dc * Jc[r] : 0.f; }
+    if (lane < NCON_FLOOR) {
+      float* cc = s.con[lane];
+      cc[4] = fc[0] + fc[1] + fc[2] + fc[3];
+      cc[5] = mu * (fc[0] - fc[1]);
+      cc[6] = mu * (fc[2] - fc[3]);
+    }
+    // Hessian weights of this contact in (n, t1, t2) coordinates
+    const float a0 = ca[0], a1 = ca[1], a2 = ca[2], a3 = ca[3];
+    const float Wnn = Dc * (a0 + a1 + a2 + a3), Wn1 = Dc * mu * (a0 - a1), Wn2 = Dc * mu * (a2 - a3);
+    const float W11 = Dc * mu * mu * (a0 + a1), W22 = Dc * mu * mu * (a2 + a3);
+    __syncwarp();
+    float qfc = ff + lsign * fl;
+    for (int c = 0; c < NCON_FLOOR; ++c) {
+      if (s.con[c][0] < 0.f) qfc += s.J[3 * c][lane] * s.con[c][4] + s.J[3 * c + 1][lane] * s.con[c][5] + s.J[3 * c + 2][lane] * s.con[c][6];
+    }
+    grad = lane < nv ? Ma - fs - qfc : 0.f;
+    // H = M + J^T D J
+    for (int idx = lane; idx < TRI(nv); idx += 32) s.H[idx] = s.A[idx];
+    __syncwarp();
+    if (lane < nv) s.H[TRI(lane) + lane] += (fquad ? Df : 0.f) + (lon ? Dl : 0.f);
+    for (int f = 0; f < 2; ++f) {
+      const bool any = (s.con[4 * f][0] < 0.f) || (s.con[4 * f + 1][0] < 0.f) || (s.con[4 * f + 2][0] < 0.f) || (s.con[4 * f + 3][0] < 0.f);
+      if (!any) continue;
+      float Zn[4], Z1[4], Z2[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int cc = 4 * f + c;
+        const float wnn = __shfl_sync(FULLMASK, Wnn, cc), wn1 = __shfl_sync(FULLMASK, Wn1, cc), wn2 = __shfl_sync(FULLMASK, Wn2, cc);
+        const float w11 = __shfl_sync(FULLMASK, W11, cc), w22 = __shfl_sync(FULLMASK, W22, cc);
+        const float jn = s.J[3 * cc][lane], j1 = s.J[3 * cc + 1][lane], j2 = s.J[3 * cc + 2][lane];
+        Zn[c] = wnn * jn + wn1 * j1 + wn2 * j2;
+        Z1[c] = wn1 * jn + w11 * j1;
+        Z2[c] = wn2 * jn + w22 * j2;
+      }
+      const int chain = m.foot_chain[f];
+      const int ri = TRI(lane);
+      for (int j = 0; j < nv; ++j) {
+        if (!((chain >> j) & 1)) continue;
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int cc = 4 * f + c;
+          acc += Zn[c] * s.J[3 * cc][j] + Z1[c] * s.J[3 * cc + 1][j] + Z2[c] * s.J[3 * cc + 2][j];
+        }
+        if (j <= lane && lane < nv) s.H[ri + j] += acc;
+      }
+    }
+    __syncwarp();
+    if (DBG) {
+      for (int j = 0; j <= lane && lane < nv; ++j) { dbg[4096 + lane * 32 + j] = s.H[TRI(lane) + j]; dbg[4096 + j * 32 + lane] = s.H[TRI(lane) + j]; }
+    }
+    chol_rev(s.H, nv, lane, m.d_parent, true);
+    search = -chol_rev_solve(s.H, nv, lane, grad);
+    if (lane >= nv) search = 0.f;
+  }
+  // ------------------------------------------------------------------ line search (solver.py _linesearch)
+  {
+    const float Mv = symv(s.A, nv, lane, search);
+    float jvc[4];
+    CONTACT_PRODUCTS(search, jvc)
+    const float jvf = search, jvl = lsign * search;
+    const float snorm = sqrtf(wsum(search * search));
+    const float gtol = m.tolerance * m.ls_tolerance * snorm * m.meaninertia * (float)max(1, nv);
+    const float qg0 = gauss;
+    const float qg1 = wsum(search * (Ma - fs));
+    const float qg2 = 0.5f * wsum(search * Mv);
+    auto point = [&](float alpha) {
+      float q0 = 0.f, q1 = 0.f, q2 = 0.f;
+      if (hasf) {
+        const float x = Jf + alpha * jvf;
+        if (x <= -rf) { q0 += floss * (-0.5f * rf - Jf); q1 += -floss * jvf; }
+        else if (x >= rf) { q0 += floss * (-0.5f * rf + Jf); q1 += floss * jvf; }
+        else { q0 += 0.5f * Df * Jf * Jf; q1 += Df * jvf * Jf; q2 += 0.5f * Df * jvf * jvf; }
+      }
+      if (lact && (Jl + alpha * jvl) < 0.f) { q0 += 0.5f * Dl * Jl * Jl; q1 += Dl * jvl * Jl; q2 += 0.5f * Dl * jvl * jvl; }
+      if (cact) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          if (Jc[r] + alpha * jvc[r] < 0.f) { q0 += 0.5f * Dc * Jc[r] * Jc[r]; q1 += Dc * jvc[r] * Jc[r]; q2 += 0.5f * Dc * jvc[r] * jvc[r]; }
+      }
+      q0 = wsum(q0) + qg0; q1 = wsum(q1) + qg1; q2 = wsum(q2) + qg2;
+      LSPoint p;
+      p.alpha = alpha;
+      p.cost = alpha * alpha * q2 + alpha * q1 + q0;
+      p.d0 = 2.f * alpha * q2 + q1;
+      p.d1 = 2.f * q2 + (q2 == 0.f ? 1e-15f : 0.f);
+      return p;
+    };
+    const LSPoint p0 = point(0.f);
+    LSPoint lo = point(p0.alpha - p0.d0 / p0.d1), hi;
+    if (lo.d0 < p0.d0) { hi = p0; } else { hi = lo; lo = p0; }
+    bool swap = true;
+    int it = 0;
+    while (true) {
+      bool done = it >= m.ls_iterations;
+      done |= !swap;
+      done |= (lo.d0 < 0.f) && (lo.d0 > -gtol);
+      done |= (hi.d0 > 0.f) && (hi.d0 < gtol);
+      if (done) break;
+      const LSPoint lo_next = point(lo.alpha - lo.d0 / lo.d1);
+      const LSPoint hi_next = point(hi.alpha - hi.d0 / hi.d1);
+      const LSPoint mid = point(0.5f * (lo.alpha + hi.alpha));
+      const bool swap_lo_next = (lo.d0 > 0.f) || (lo.d0 < lo_next.d0);
+      if (swap_lo_next) lo = lo_next;
+      const bool swap_lo_mid = (mid.d0 < 0.f) && (lo.d0 < mid.d0);
+      if (swap_lo_mid) lo = mid;
+      const bool swap_hi_next = (hi.d0 < 0.f) || (hi.d0 > hi_next.d0);
+      if (swap_hi_next) hi = hi_next;
+      const bool swap_hi_mid = (mid.d0 > 0.f) && (hi.d0 > mid.d0);
+      if (swap_hi_mid) hi = mid;
+      swap = swap_lo_next || swap_lo_mid || swap_hi_next || swap_hi_mid;
+      ++it;
+    }
+    const bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
+    const float alpha = improved ? (lo.cost < hi.cost ? lo.alpha : hi.alpha) : 0.f;
+    qacc += alpha * search;
+    Ma += alpha * Mv;
+    Jf += alpha * jvf;
+    Jl += alpha * jvl;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) Jc[r] += alpha * jvc[r];
+    if (DBG && lane == 0) { dbg[2538] = alpha; dbg[2539] = (float)it; }
+  }
+  if (lane >= nv) qacc = 0.f;
+  L.qacc = qacc;
+  L.qaccw = qacc;
+
+  // ------------------------------------------------------------------ outputs of the last forward: forces, sensors
+  if (last) {
+    if (lane < nv) out[OUT_QACC + lane] = qacc;
+    // efc_force rows: friction | limits | contacts x 4   (update_constraint after the line search)
+    if (hasf) {
+      float ff;
+      if (Jf <= -rf) ff = floss; else if (Jf >= rf) ff = -floss; else ff = -Df * Jf;
+      out[OUT_EFC + m.d_frrow[lane]] = ff;
+    }
+    if (flags & DF_LIMITED) out[OUT_EFC + m.nfr + m.d_limrow[lane]] = (lact && Jl < 0.f) ? -Dl * Jl : 0.f;
+    if (lane < NCON_ALL) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) out[OUT_EFC + m.nfr + m.nlim + 4 * lane + r] = (cact && Jc[r] < 0.f) ? -Dc * Jc[r] : 0.f;
+      out[OUT_CDIST + lane] = s.con[lane][0];
+    }
+    if (m.d_act[lane] >= 0) out[OUT_AFRC + m.d_act[lane]] = aforce;
+    // sensors (sensor.py): all site-attached; cacc of the imu body needs the post-constraint qacc
+    {
+      const int ch = m.imu_chain;
+      const bool in = lane < nv && ((ch >> lane) & 1);
+      S6 t = s6add(s6scale(cdd, L.qvel), s6scale(cd, qacc));
+      S6 ca;
+      ca.a0 = wsum(in ? t.a0 : 0.f); ca.a1 = wsum(in ? t.a1 : 0.f); ca.a2 = wsum(in ? t.a2 : 0.f);
+      ca.l0 = wsum(in ? t.l0 : 0.f) - m.gravity[0]; ca.l1 = wsum(in ? t.l1 : 0.f) - m.gravity[1]; ca.l2 = wsum(in ? t.l2 : 0.f) - m.gravity[2];
+      const int ib = m.imu_body;
+      const S6 cv = s6shfl(cvel, ib);
+      float Rb[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) Rb[k] = s.xmat[k][ib];
+      float Rs[9];  // site_xmat = R_body * R_site_local
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) Rs[3 * r + c] = Rb[3 * r] * m.imu_rot[c] + Rb[3 * r + 1] * m.imu_rot[3 + c] + Rb[3 * r + 2] * m.imu_rot[6 + c];
+      const V3 sp = v3(s.xpos[0][ib] + Rb[0] * m.imu_pos[0] + Rb[1] * m.imu_pos[1] + Rb[2] * m.imu_pos[2],
+                       s.xpos[1][ib] + Rb[3] * m.imu_pos[0] + Rb[4] * m.imu_pos[1] + Rb[5] * m.imu_pos[2],
+                       s.xpos[2][ib] + Rb[6] * m.imu_pos[0] + Rb[7] * m.imu_pos[1] + Rb[8] * m.imu_pos[2]);
+      const V3 diff = sp - com;
+      const V3 ang = v3(cv.a0, cv.a1, cv.a2);
+      const V3 lin = v3(cv.l0, cv.l1, cv.l2) - cross(diff, ang);
+      const V3 acc = v3(ca.l0, ca.l1, ca.l2) - cross(diff, v3(ca.a0, ca.a1, ca.a2));
+      auto toLocal = [&](V3 v) { return v3(Rs[0] * v.x + Rs[3] * v.y + Rs[6] * v.z, Rs[1] * v.x + Rs[4] * v.y + Rs[7] * v.z, Rs[2] * v.x + Rs[5] * v.y + Rs[8] * v.z); };
+      const V3 angl = toLocal(ang), linl = toLocal(lin), accl = toLocal(acc);
+      const V3 corr = cross(angl, linl);
+      if (lane == 0) {
+        float* sd = out + OUT_SENS;
+        sd[0] = angl.x; sd[1] = angl.y; sd[2] = angl.z;
+        sd[3] = linl.x; sd[4] = linl.y; sd[5] = linl.z;
+        sd[6] = accl.x + corr.x; sd[7] = accl.y + corr.y; sd[8] = accl.z + corr.z;
+        sd[9] = Rs[2]; sd[10] = Rs[5]; sd[11] = Rs[8];
+        sd[12] = ang.x; sd[13] = ang.y; sd[14] = ang.z;
+        sd[21] = 0.f; sd[22] = 0.f; sd[23] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) out[OUT_IMUMAT + k] = Rs[k];
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int fb = m.foot_site_body[k];
+        const S6 fv = s6shfl(cvel, fb);
+        const V3 fp = v3(s.xpos[0][fb] + s.xmat[0][fb] * m.foot_site_pos[k][0] + s.xmat[1][fb] * m.foot_site_pos[k][1] + s.xmat[2][fb] * m.foot_site_pos[k][2],
+                         s.xpos[1][fb] + s.xmat[3][fb] * m.foot_site_pos[k][0] + s.xmat[4][fb] * m.foot_site_pos[k][1] + s.xmat[5][fb] * m.foot_site_pos[k][2],
+                         s.xpos[2][fb] + s.xmat[6][fb] * m.foot_site_pos[k][0] + s.xmat[7][fb] * m.foot_site_pos[k][1] + s.xmat[8][fb] * m.foot_site_pos[k][2]);
+        const V3 fl = v3(fv.l0, fv.l1, fv.l2) - cross(fp - com, v3(fv.a0, fv.a1, fv.a2));
+        if (lane == 0) {
+          out[OUT_SENS + 15 + 3 * k] = fl.x; out[OUT_SENS + 16 + 3 * k] = fl.y; out[OUT_SENS + 17 + 3 * k] = fl.z;
+          out[OUT_FEET + 3 * k] = fp.x; out[OUT_FEET + 3 * k + 1] = fp.y; out[OUT_FEET + 3 * k + 2] = fp.z;
+        }
+      }
+    }
+  }
+  if (DBG) {
+    // dense M, smooth dynamics, contacts, rows, Newton direction (layout: tests/test_parity_gpu.py DBG_*)
+    for (int j = 0; j <= lane && lane < nv; ++j) { dbg[lane * 32 + j] = s.A[TRI(lane) + j]; dbg[j * 32 + lane] = s.A[TRI(lane) + j]; }
+    if (lane < nv) {
+      dbg[1024 + lane] = qfrc_bias; dbg[1056 + lane] = fs; dbg[1088 + lane] = as;
+      dbg[1184 + lane] = hasf ? Df : 0.f; dbg[1216 + lane] = Dl;
+      dbg[1264 + lane] = hasf ? areff : 0.f; dbg[1296 + lane] = arefl;
+      dbg[1376 + lane] = search; dbg[1408 + lane] = grad; dbg[1736 + lane] = qacc;
+      dbg[1540 + lane * 6 + 0] = cd.a0; dbg[1540 + lane * 6 + 1] = cd.a1; dbg[1540 + lane * 6 + 2] = cd.a2;
+      dbg[1540 + lane * 6 + 3] = cd.l0; dbg[1540 + lane * 6 + 4] = cd.l1; dbg[1540 + lane * 6 + 5] = cd.l2;
+    }
+    if (lane < NCON_ALL) {
+      dbg[1120 + lane] = s.con[lane][0];
+      dbg[1136 + 3 * lane] = s.con[lane][1]; dbg[1137 + 3 * lane] = s.con[lane][2]; dbg[1138 + 3 * lane] = s.con[lane][3];
+      dbg[1248 + lane] = Dc;
+      for (int r = 0; r < 4; ++r) dbg[1328 + 4 * lane + r] = arefc[r];
+    }
+    if (lane < nb) { dbg[1440 + 3 * lane] = xp.x; dbg[1441 + 3 * lane] = xp.y; dbg[1442 + 3 * lane] = xp.z; }
+    if (lane == 0) { dbg[1536] = com.x; dbg[1537] = com.y; dbg[1538] = com.z; }
+    for (int r = 0; r < JROWS; ++r) dbg[1768 + r * 32 + lane] = lane < nv ? s.J[r][lane] : 0.f;
+  }
+  __syncwarp();
+
+  // ------------------------------------------------------------------ euler (eulerdamp disabled)
+  if (integrate) {
+    const float dt = m.timestep;
+    if (lane < nv) L.qvel += dt * qacc;
+    if (flags & DF_HINGE) s.qpos[qadr] = qd + dt * L.qvel;
+    if (flags & DF_TRANS) s.qpos[qadr] += dt * L.qvel;   // qadr of a free-joint translation dof = its coordinate
+    // free-joint quaternion: q <- normalize(q * exp(dt * w_local)); rotation dofs carry qadr = address of qw
+    const int rl = __ffs(__ballot_sync(FULLMASK, (flags & DF_ROT) != 0)) - 1;  // first rotation dof lane
+    if (rl >= 0) {
+      const float wx = __shfl_sync(FULLMASK, L.qvel, rl), wy = __shfl_sync(FULLMASK, L.qvel, rl + 1), wz = __shfl_sync(FULLMASK, L.qvel, rl + 2);
+      const int qa = __shfl_sync(FULLMASK, qadr, rl);
+      __syncwarp();
+      if (lane == 0) {
+        const float nrm = sqrtf(wx * wx + wy * wy + wz * wz);
+        V3 ax = v3(0.f, 0.f, 0.f);
+        if (nrm > 0.f) ax = v3(wx / nrm, wy / nrm, wz / nrm);
+        Q4 q; q.w = s.qpos[qa]; q.x = s.qpos[qa + 1]; q.y = s.qpos[qa + 2]; q.z = s.qpos[qa + 3];
+        Q4 qn = qnormalize(qmul(q, axis_angle(ax, dt * nrm)));
+        s.qpos[qa] = qn.w; s.qpos[qa + 1] = qn.x; s.qpos[qa + 2] = qn.y; s.qpos[qa + 3] = qn.z;
+      }
+    }
+    __syncwarp();
+  }
+#undef CONTACT_PRODUCTS
+#undef ROW_COST
+}

@@ -610,6 +610,9 @@ static void make_constraint(const OduckHandle& h, const EnvState& e, Scratch& s)
   s.nefc = r;
 }
 
+struct DebugCapture { bool on; real search[NV], grad[NV], H[NV][NV], costw, costs, alpha; int ls_it; };
+static thread_local DebugCapture g_dbg = {false};
+
 // ------------------------------------------------------------------------------------ solver.py (Newton)
 struct Ctx {
   real qacc[NV], Ma[NV], Jaref[NEFC], efc_force[NEFC], qfrc_constraint[NV], grad[NV], Mgrad[NV], search[NV];
@@ -657,6 +660,7 @@ static void update_gradient(const OduckModel& m, Scratch& s, Ctx& c) {
       for (int j = 0; j < m.nv; j++) H[i][j] += w * s.J[r][j];
     }
   }
+  if (g_dbg.on) for (int i = 0; i < m.nv; i++) for (int j = 0; j < m.nv; j++) g_dbg.H[i][j] = H[i][j];
   if (!cholesky(m.nv, H, LH)) {
     for (int j = 0; j < m.nv; j++) c.Mgrad[j] = std::numeric_limits<real>::quiet_NaN();
     return;
@@ -752,6 +756,7 @@ static void linesearch(const OduckModel& m, const Scratch& s, Ctx& c) {
   }
   bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
   real alpha = lo.cost < hi.cost ? lo.alpha : hi.alpha;
+  if (g_dbg.on) { g_dbg.alpha = improved ? alpha : 0; g_dbg.ls_it = it; }
   if (improved) {
     for (int j = 0; j < m.nv; j++) { c.qacc[j] += c.search[j] * alpha; c.Ma[j] += mv[j] * alpha; }
     for (int r = 0; r < s.nefc; r++) c.Jaref[r] += jv[r] * alpha;
@@ -764,6 +769,7 @@ static void solve(const OduckModel& m, EnvState& e, Scratch& s) {
   ctx_create(m, s, s.qacc_smooth, smth, false);
   const real* start = warm.cost < smth.cost ? e.qacc_warm : s.qacc_smooth;
   ctx_create(m, s, start, c, true);
+  if (g_dbg.on) { g_dbg.costw = warm.cost; g_dbg.costs = smth.cost; for (int j = 0; j < m.nv; j++) { g_dbg.search[j] = c.search[j]; g_dbg.grad[j] = c.grad[j]; } }
   real scale = 1 / ((real)m.meaninertia * std::max(1, m.nv));
   for (int it = 0; it < m.iterations; it++) {
     if (m.iterations > 1) {
@@ -1322,6 +1328,38 @@ int oduck_policy_forward(OduckHandle* h, const OduckPolicyWeights* w, const floa
     }
     if (log_prob) log_prob[i] = (float)lp;
   });
+  return ODUCK_OK;
+}
+
+// Diagnostic twin of liboduck_cuda's oduck_debug_forward: same layout (DBG_STRIDE reals per env), values in double.
+int oduck_debug_stride(void) { return 5120; }
+int oduck_debug_forward(OduckHandle* h, double* out) {
+  if (!h || !out) return fail(ODUCK_ERR_ARG, "oduck_debug_forward: bad argument");
+  const OduckModel& m = h->m;
+  for (int i = 0; i < h->n; i++) {
+    static thread_local Scratch s;
+    EnvState e = h->env[i];   // copy: diagnostic forward does not advance the warm start
+    double* d = out + (size_t)i * 5120;
+    for (int k = 0; k < 5120; k++) d[k] = 0;
+    g_dbg.on = true;
+    forward(*h, e, s);
+    g_dbg.on = false;
+    h->env[i] = e;
+    for (int a = 0; a < m.nv; a++) for (int b = 0; b < m.nv; b++) { d[a * 32 + b] = s.M[a][b]; d[4096 + a * 32 + b] = g_dbg.H[a][b]; }
+    for (int a = 0; a < m.nv; a++) {
+      d[1024 + a] = s.qfrc_bias[a]; d[1056 + a] = s.qfrc_smooth[a]; d[1088 + a] = s.qacc_smooth[a];
+      d[1376 + a] = g_dbg.search[a]; d[1408 + a] = g_dbg.grad[a]; d[1736 + a] = e.qacc[a];
+      for (int k = 0; k < 6; k++) d[1540 + a * 6 + k] = s.cdof[a][k];
+    }
+    for (int c = 0; c < NCON; c++) { d[1120 + c] = s.con_dist[c]; for (int k = 0; k < 3; k++) d[1136 + 3 * c + k] = s.con_pos[c][k]; }
+    int r = 0;
+    for (int k = 0; k < h->nefc_fr; k++, r++) { d[1184 + h->fr_dof[k]] = s.D[r]; d[1264 + h->fr_dof[k]] = s.aref[r]; }
+    for (int k = 0; k < h->nefc_lim; k++, r++) { int dd = m.jnt_dofadr[h->lim_jnt[k]]; d[1216 + dd] = s.D[r]; d[1296 + dd] = s.aref[r]; }
+    for (int c = 0; c < NCON && r + 3 < s.nefc + 4; c++) { d[1248 + c] = s.D[r]; for (int k = 0; k < 4; k++, r++) d[1328 + 4 * c + k] = r < s.nefc ? s.aref[r] : 0; }
+    for (int b = 0; b < m.nbody; b++) for (int k = 0; k < 3; k++) d[1440 + 3 * b + k] = s.xpos[b][k];
+    for (int k = 0; k < 3; k++) d[1536 + k] = s.com[k];
+    d[2536] = g_dbg.costw; d[2537] = g_dbg.costs; d[2538] = g_dbg.alpha; d[2539] = g_dbg.ls_it;
+  }
   return ODUCK_OK;
 }
 
