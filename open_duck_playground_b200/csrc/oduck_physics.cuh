@@ -482,15 +482,15 @@ __device__ __forceinline__ void forward_euler(const DevModel& m, WarpSmem& s, La
       const LSPoint lo_next = point(lo.alpha - lo.d0 / lo.d1);
       const LSPoint hi_next = point(hi.alpha - hi.d0 / hi.d1);
       const LSPoint mid = point(0.5f * (lo.alpha + hi.alpha));
-      const bool swap_lo_next = (lo.d0 > 0.f) || (lo.d0 < lo_next.d0);
-      if (swap_lo_next) lo = lo_next;
-      const bool swap_lo_mid = (mid.d0 < 0.f) && (lo.d0 < mid.d0);
-      if (swap_lo_mid) lo = mid;
-      const bool swap_hi_next = (hi.d0 < 0.f) || (hi.d0 > hi_next.d0);
-      if (swap_hi_next) hi = hi_next;
-      const bool swap_hi_mid = (mid.d0 > 0.f) && (hi.d0 > mid.d0);
-      if (swap_hi_mid) hi = mid;
-      swap = swap_lo_next || swap_lo_mid || swap_hi_next || swap_hi_mid;
+      // solver.py _in_bracket: a candidate replaces a bracket end when it lies between that end and the root, same side
+      auto in_bracket = [](float x, float y) { return ((x < y) && (y < 0.f)) || ((x > y) && (y > 0.f)); };
+      const bool s1 = in_bracket(lo.d0, lo_next.d0); if (s1) lo = lo_next;
+      const bool s2 = in_bracket(lo.d0, mid.d0);     if (s2) lo = mid;
+      const bool s3 = in_bracket(lo.d0, hi_next.d0); if (s3) lo = hi_next;
+      const bool s4 = in_bracket(hi.d0, hi_next.d0); if (s4) hi = hi_next;
+      const bool s5 = in_bracket(hi.d0, mid.d0);     if (s5) hi = mid;
+      const bool s6 = in_bracket(hi.d0, lo_next.d0); if (s6) hi = lo_next;
+      swap = s1 || s2 || s3 || s4 || s5 || s6;
       ++it;
     }
     const bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);

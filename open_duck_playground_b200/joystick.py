@@ -216,7 +216,8 @@ class Joystick:
     # ------------------------------------------------------------------ env API
     def randomize(self, rng) -> None:
         """domain_randomize (common/randomize.py:26): per-env friction/frictionloss/armature/COM/mass/qpos0/kp."""
-        self.handle.randomize(self._keys(rng), self._stream())
+        keys = self._keys(rng)   # creates the handle on first use
+        self.handle.randomize(keys, self._stream())
 
     def reset(self, rng, mask: Optional[torch.Tensor] = None) -> State:
         keys = self._keys(rng)

@@ -450,19 +450,20 @@ static void make_frame(const real* n, real* f) {
   for (int i = 0; i < 3; i++) { f[i] = a[i]; f[3 + i] = b[i]; f[6 + i] = c[i]; }
 }
 
-// collision_convex.py _manifold_points: four polygon points of roughly maximal area
+// collision_convex.py _manifold_points: four polygon points of roughly maximal area.  The scores are rounded to float32
+// before the argmax because MJX runs in float32, where `x + (-1e6)` ties for every masked-out vertex.
 static void manifold_points(int nv, const real (*poly)[3], const bool* mask, const real* n, int* idx) {
   auto dmask = [&](int i) { return mask[i] ? (real)0 : (real)-1e6; };
   int a = 0;
   { real best = -std::numeric_limits<real>::infinity(); for (int i = 0; i < nv; i++) if (dmask(i) > best) { best = dmask(i); a = i; } }
   int b = 0;
   { real best = -std::numeric_limits<real>::infinity();
-    for (int i = 0; i < nv; i++) { real d[3] = {poly[a][0] - poly[i][0], poly[a][1] - poly[i][1], poly[a][2] - poly[i][2]}; real v = dot3(d, d) + dmask(i); if (v > best) { best = v; b = i; } } }
+    for (int i = 0; i < nv; i++) { real d[3] = {poly[a][0] - poly[i][0], poly[a][1] - poly[i][1], poly[a][2] - poly[i][2]}; real v = (real)((float)dot3(d, d) + (float)dmask(i)); if (v > best) { best = v; b = i; } } }
   real ab[3], amb[3] = {poly[a][0] - poly[b][0], poly[a][1] - poly[b][1], poly[a][2] - poly[b][2]};
   cross3(n, amb, ab);
   int c = 0;
   { real best = -std::numeric_limits<real>::infinity();
-    for (int i = 0; i < nv; i++) { real ap[3] = {poly[a][0] - poly[i][0], poly[a][1] - poly[i][1], poly[a][2] - poly[i][2]}; real v = std::fabs(dot3(ap, ab)) + dmask(i); if (v > best) { best = v; c = i; } } }
+    for (int i = 0; i < nv; i++) { real ap[3] = {poly[a][0] - poly[i][0], poly[a][1] - poly[i][1], poly[a][2] - poly[i][2]}; real v = (real)((float)std::fabs(dot3(ap, ab)) + (float)dmask(i)); if (v > best) { best = v; c = i; } } }
   real ac[3], bc[3], amc[3] = {poly[a][0] - poly[c][0], poly[a][1] - poly[c][1], poly[a][2] - poly[c][2]};
   real bmc[3] = {poly[b][0] - poly[c][0], poly[b][1] - poly[c][1], poly[b][2] - poly[c][2]};
   cross3(n, amc, ac);
@@ -470,8 +471,8 @@ static void manifold_points(int nv, const real (*poly)[3], const bool* mask, con
   int d = 0;
   { real best = -std::numeric_limits<real>::infinity();
     // argmax over concatenate([dist_bp, dist_ap]) % nv: first maximum, bp block first
-    for (int i = 0; i < nv; i++) { real bp[3] = {poly[b][0] - poly[i][0], poly[b][1] - poly[i][1], poly[b][2] - poly[i][2]}; real v = std::fabs(dot3(bp, bc)) + dmask(i); if (v > best) { best = v; d = i; } }
-    for (int i = 0; i < nv; i++) { real ap[3] = {poly[a][0] - poly[i][0], poly[a][1] - poly[i][1], poly[a][2] - poly[i][2]}; real v = std::fabs(dot3(ap, ac)) + dmask(i); if (v > best) { best = v; d = i; } } }
+    for (int i = 0; i < nv; i++) { real bp[3] = {poly[b][0] - poly[i][0], poly[b][1] - poly[i][1], poly[b][2] - poly[i][2]}; real v = (real)((float)std::fabs(dot3(bp, bc)) + (float)dmask(i)); if (v > best) { best = v; d = i; } }
+    for (int i = 0; i < nv; i++) { real ap[3] = {poly[a][0] - poly[i][0], poly[a][1] - poly[i][1], poly[a][2] - poly[i][2]}; real v = (real)((float)std::fabs(dot3(ap, ac)) + (float)dmask(i)); if (v > best) { best = v; d = i; } } }
   idx[0] = a; idx[1] = b; idx[2] = c; idx[3] = d;
 }
 
@@ -743,15 +744,15 @@ static void linesearch(const OduckModel& m, const Scratch& s, Ctx& c) {
     LSPoint lo_next = point(lo.alpha - lo.d0 / lo.d1);
     LSPoint hi_next = point(hi.alpha - hi.d0 / hi.d1);
     LSPoint mid = point((real)0.5 * (lo.alpha + hi.alpha));
-    bool swap_lo_next = (lo.d0 > 0) || (lo.d0 < lo_next.d0);
-    if (swap_lo_next) lo = lo_next;
-    bool swap_lo_mid = (mid.d0 < 0) && (lo.d0 < mid.d0);
-    if (swap_lo_mid) lo = mid;
-    bool swap_hi_next = (hi.d0 < 0) || (hi.d0 > hi_next.d0);
-    if (swap_hi_next) hi = hi_next;
-    bool swap_hi_mid = (mid.d0 > 0) && (hi.d0 > mid.d0);
-    if (swap_hi_mid) hi = mid;
-    swap = swap_lo_next || swap_lo_mid || swap_hi_next || swap_hi_mid;
+    // solver.py: a candidate y replaces bracket end x when it lies between x and the root on the same side
+    auto in_bracket = [](real x, real y) { return ((x < y) && (y < 0)) || ((x > y) && (y > 0)); };
+    bool s1 = in_bracket(lo.d0, lo_next.d0); if (s1) lo = lo_next;
+    bool s2 = in_bracket(lo.d0, mid.d0);     if (s2) lo = mid;
+    bool s3 = in_bracket(lo.d0, hi_next.d0); if (s3) lo = hi_next;
+    bool s4 = in_bracket(hi.d0, hi_next.d0); if (s4) hi = hi_next;
+    bool s5 = in_bracket(hi.d0, mid.d0);     if (s5) hi = mid;
+    bool s6 = in_bracket(hi.d0, lo_next.d0); if (s6) hi = lo_next;
+    swap = s1 || s2 || s3 || s4 || s5 || s6;
     it++;
   }
   bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
@@ -915,6 +916,9 @@ static void sample_command(const OduckHandle& h, Key rng, real* cmd) {  // joyst
   if (zero) for (int i = 0; i < 7; i++) cmd[i] = 0;
 }
 
+
+
+
 static real nan_to_num(real x) {
   if (std::isnan(x)) return 0;
   if (std::isinf(x)) return x > 0 ? std::numeric_limits<float>::max() : -std::numeric_limits<float>::max();
@@ -923,6 +927,50 @@ static real nan_to_num(real x) {
 
 static void actuated(const OduckModel& m, const real* qpos, const real* qvel, real* q, real* qd) {
   for (int u = 0; u < m.nu; u++) { int j = m.act_jntid[u]; if (q) q[u] = qpos[m.jnt_qposadr[j]]; if (qd) qd[u] = qvel[m.jnt_dofadr[j]]; }
+}
+
+// The seven reward terms of Joystick._get_reward (joystick.py:622-669), unscaled:
+//   [tracking_lin_vel, tracking_ang_vel, torques, action_rate, stand_still, alive, imitation]
+// rewards.py:11-31,68-79,93-125 and custom_rewards.py:4-149.  Checked against the reference's NumPy twins
+// (tests/golden/rewards.npz, made by tools/make_golden.py).
+static void compute_rewards(const OduckHandle& h, const real* command, const real* local_linvel, const real* gyro, const real* actuator_force,
+                            const real* action, const real* last_act, const real* base_qvel, const real* q, const real* qd, const real* contact,
+                            const real* ref, real* out) {
+  const OduckModel& m = h.m;
+  const OduckEnvConfig& c = h.cfg;
+  real ex = (command[0] - local_linvel[0]) * (command[0] - local_linvel[0]);
+  real ey = std::max(std::fabs(local_linvel[1] - command[1]) - (real)0.1, (real)0);
+  out[0] = nan_to_num(std::exp(-(ex + ey * ey) / (real)c.tracking_sigma));
+  real ea = (command[2] - gyro[2]) * (command[2] - gyro[2]);
+  out[1] = nan_to_num(std::exp(-ea / (real)c.tracking_sigma));
+  real c_torque = 0, c_rate = 0;
+  for (int u = 0; u < m.nu; u++) { c_torque += actuator_force[u] * actuator_force[u]; real d = action[u] - last_act[u]; c_rate += d * d; }
+  out[2] = nan_to_num(c_torque);
+  out[3] = nan_to_num(c_rate);
+  real cmd_norm = std::sqrt(command[0] * command[0] + command[1] * command[1] + command[2] * command[2]);
+  real pose = 0, vel = 0;
+  for (int u = 0; u < m.nu; u++) { pose += std::fabs(q[u] - (real)m.key_ctrl[u]); vel += std::fabs(qd[u]); }
+  out[4] = nan_to_num(pose + vel) * (cmd_norm < (real)0.01 ? 1 : 0);
+  out[5] = 1;
+  out[6] = 0;
+  if (c.use_imitation_reward) {
+    real lxy = (base_qvel[0] - ref[34]) * (base_qvel[0] - ref[34]) + (base_qvel[1] - ref[35]) * (base_qvel[1] - ref[35]);
+    real lz = (base_qvel[2] - ref[36]) * (base_qvel[2] - ref[36]);
+    real axy = (base_qvel[3] - ref[37]) * (base_qvel[3] - ref[37]) + (base_qvel[4] - ref[38]) * (base_qvel[4] - ref[38]);
+    real az = (base_qvel[5] - ref[39]) * (base_qvel[5] - ref[39]);
+    real jp_ = 0, jv_ = 0;
+    for (int k = 0; k < 10; k++) {
+      int u = k < 5 ? k : k + 4;       // joints_qpos[:5] ++ joints_qpos[9:]
+      int rr = k < 5 ? k : k + 6;      // ref[:5] ++ ref[11:16]
+      jp_ += (q[u] - ref[rr]) * (q[u] - ref[rr]);
+      jv_ += (qd[u] - ref[16 + rr]) * (qd[u] - ref[16 + rr]);
+    }
+    real crew = 0;
+    for (int i = 0; i < 2; i++) crew += (contact[i] == (ref[32 + i] > (real)0.5 ? (real)1 : (real)0)) ? 1 : 0;
+    real rew = std::exp(-8 * lxy) + std::exp(-8 * lz) + (real)0.5 * std::exp(-2 * axy) + (real)0.5 * std::exp(-2 * az) - 15 * jp_ - (real)1e-3 * jv_ + crew;
+    rew *= cmd_norm > (real)0.01 ? 1 : 0;
+    out[6] = nan_to_num(rew);
+  }
 }
 
 // joystick.py:487-620.  Advances e.rng exactly as the reference (5 splits).
@@ -1099,43 +1147,11 @@ static void env_step(OduckHandle& h, EnvState& e, const float* action_f) {  // j
   for (int i = 0; i < m.nv; i++) nan_state |= std::isnan(e.qvel[i]);
   bool done = (e.sensordata[9 + 2] < 0) || nan_state;
   // rewards (common/rewards.py, custom_rewards.py)
-  const real* sd = e.sensordata;
   real q[NU], qd[NU];
   actuated(m, e.qpos, e.qvel, q, qd);
-  real r_lin, r_ang, c_torque = 0, c_rate = 0, c_still, r_alive = 1, r_imit = 0;
-  {
-    real ex = (e.command[0] - sd[3]) * (e.command[0] - sd[3]);
-    real ey = std::max(std::fabs(sd[4] - e.command[1]) - (real)0.1, (real)0);
-    r_lin = nan_to_num(std::exp(-(ex + ey * ey) / (real)c.tracking_sigma));
-    real ea = (e.command[2] - sd[2]) * (e.command[2] - sd[2]);
-    r_ang = nan_to_num(std::exp(-ea / (real)c.tracking_sigma));
-    for (int u = 0; u < m.nu; u++) { c_torque += e.actuator_force[u] * e.actuator_force[u]; real d = action[u] - e.last_act[0][u]; c_rate += d * d; }
-    c_torque = nan_to_num(c_torque);
-    c_rate = nan_to_num(c_rate);
-    real cmd_norm = std::sqrt(e.command[0] * e.command[0] + e.command[1] * e.command[1] + e.command[2] * e.command[2]);
-    real pose = 0, vel = 0;
-    for (int u = 0; u < m.nu; u++) { pose += std::fabs(q[u] - (real)m.key_ctrl[u]); vel += std::fabs(qd[u]); }
-    c_still = nan_to_num(pose + vel) * (cmd_norm < (real)0.01 ? 1 : 0);
-    if (c.use_imitation_reward) {
-      const real* ref = e.ref_motion;
-      real lxy = (e.qvel[0] - ref[34]) * (e.qvel[0] - ref[34]) + (e.qvel[1] - ref[35]) * (e.qvel[1] - ref[35]);
-      real lz = (e.qvel[2] - ref[36]) * (e.qvel[2] - ref[36]);
-      real axy = (e.qvel[3] - ref[37]) * (e.qvel[3] - ref[37]) + (e.qvel[4] - ref[38]) * (e.qvel[4] - ref[38]);
-      real az = (e.qvel[5] - ref[39]) * (e.qvel[5] - ref[39]);
-      real jp_ = 0, jv_ = 0;
-      for (int k = 0; k < 10; k++) {
-        int u = k < 5 ? k : k + 4;       // joints_qpos[:5] ++ joints_qpos[9:]
-        int rr = k < 5 ? k : k + 6;      // ref[:5] ++ ref[11:16]
-        jp_ += (q[u] - ref[rr]) * (q[u] - ref[rr]);
-        jv_ += (qd[u] - ref[16 + rr]) * (qd[u] - ref[16 + rr]);
-      }
-      real crew = 0;
-      for (int i = 0; i < 2; i++) crew += (contact[i] == (ref[32 + i] > (real)0.5 ? (real)1 : (real)0)) ? 1 : 0;
-      real rew = std::exp(-8 * lxy) + std::exp(-8 * lz) + (real)0.5 * std::exp(-2 * axy) + (real)0.5 * std::exp(-2 * az) - 15 * jp_ - (real)1e-3 * jv_ + crew;
-      rew *= cmd_norm > (real)0.01 ? 1 : 0;
-      r_imit = nan_to_num(rew);
-    }
-  }
+  real terms[7];
+  compute_rewards(h, e.command, e.sensordata + 3, e.sensordata, e.actuator_force, action, e.last_act[0], e.qvel, q, qd, contact, e.ref_motion, terms);
+  const real r_lin = terms[0], r_ang = terms[1], c_torque = terms[2], c_rate = terms[3], c_still = terms[4], r_alive = terms[5], r_imit = terms[6];
   real sc[7] = {r_lin * (real)c.scale_tracking_lin_vel, r_ang * (real)c.scale_tracking_ang_vel, c_torque * (real)c.scale_torques,
                 c_rate * (real)c.scale_action_rate, c_still * (real)c.scale_stand_still, r_alive * (real)c.scale_alive, r_imit * (real)c.scale_imitation};
   // sum order of the rewards dict (joystick.py:634-667): lin, ang, torques, action_rate, alive, imitation, stand_still
@@ -1328,6 +1344,27 @@ int oduck_policy_forward(OduckHandle* h, const OduckPolicyWeights* w, const floa
     }
     if (log_prob) log_prob[i] = (float)lp;
   });
+  return ODUCK_OK;
+}
+
+// Test-only exports (oracle only): direct access to the pieces pinned by tests/golden/*.npz.
+int oduck_test_reference_motion(OduckHandle* h, double dx, double dy, double dth, int i, double* out40) {
+  if (!h || !out40) return fail(ODUCK_ERR_ARG, "oduck_test_reference_motion: bad argument");
+  real o[ODUCK_REF_DIM];
+  poly_reference_motion(*h, (real)dx, (real)dy, (real)dth, i, o);
+  for (int k = 0; k < ODUCK_REF_DIM; k++) out40[k] = o[k];
+  return ODUCK_OK;
+}
+// in: command[7] local_linvel[3] gyro[3] actuator_force[nu] action[nu] last_act[nu] base_qvel[6] q[nu] qd[nu] contact[2] ref[40]
+int oduck_test_rewards(OduckHandle* h, const double* in, double* out7) {
+  if (!h || !in || !out7) return fail(ODUCK_ERR_ARG, "oduck_test_rewards: bad argument");
+  const int nu = h->m.nu;
+  std::vector<real> v(in, in + 7 + 3 + 3 + 3 * nu + 6 + 2 * nu + 2 + ODUCK_REF_DIM);
+  const real* p = v.data();
+  const real *cmd = p, *lv = p + 7, *gy = p + 10, *af = p + 13, *ac = af + nu, *la = ac + nu, *bq = la + nu, *q = bq + 6, *qd = q + nu, *ct = qd + nu, *rf = ct + 2;
+  real o[7];
+  compute_rewards(*h, cmd, lv, gy, af, ac, la, bq, q, qd, ct, rf, o);
+  for (int k = 0; k < 7; k++) out7[k] = o[k];
   return ODUCK_OK;
 }
 

@@ -1,0 +1,163 @@
+"""Physics invariants of the CPU oracle.  The reference's step arithmetic (mujoco.mjx) is not available, so the oracle is
+checked against first principles and against an independent numpy formulation of M(q) (mjcf.mass_matrix)."""
+import copy
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import make_handle
+from open_duck_playground_b200 import mjcf
+
+G = 9.81
+
+
+def _dump(lib, h):
+    stride = lib.lib.oduck_debug_stride()
+    out = np.zeros((h.n, stride))
+    lib.lib.oduck_debug_forward.argtypes = [C.c_void_p, C.c_void_p]
+    lib.check(lib.lib.oduck_debug_forward(h.h, out.ctypes.data))
+    return out
+
+
+def _free_model(model, dt=None):
+    m = copy.deepcopy(model)
+    A = m.arrays
+    A["dof_damping"][:] = 0; A["dof_frictionloss"][:] = 0; A["act_kp"][:] = 0; A["jnt_limited"][:] = 0
+    if dt is not None:
+        A["timestep"] = np.array(dt)
+    return m
+
+
+def _random_state(model, n, seed, z=2.0):
+    rng = np.random.default_rng(seed)
+    qpos = np.tile(model.key_qpos[: model.nq], (n, 1)).astype(np.float32)
+    qpos[:, 2] = z
+    quat = rng.normal(size=(n, 4)); qpos[:, 3:7] = quat / np.linalg.norm(quat, axis=1, keepdims=True)
+    qpos[:, 7:] += rng.uniform(-0.3, 0.3, (n, model.nq - 7)).astype(np.float32)
+    qvel = rng.uniform(-2, 2, (n, model.nv)).astype(np.float32)
+    return qpos, qvel
+
+
+def test_mass_matrix_matches_jacobian_formula(oracle, model_backlash, poly_table):
+    n = 4
+    h = make_handle(oracle, model_backlash, poly_table, n)
+    qpos, qvel = _random_state(model_backlash, n, 0)
+    h.set_state(qpos.ctypes.data, qvel.ctypes.data, 0)
+    d = _dump(oracle, h)
+    nv = model_backlash.nv
+    for i in range(n):
+        M = d[i, :1024].reshape(32, 32)[:nv, :nv]
+        Mref = mjcf.mass_matrix(model_backlash, qpos[i].astype(np.float64))
+        assert np.abs(M - Mref).max() < 1e-9
+        assert np.allclose(M, M.T)
+
+
+def test_energy_drift_is_first_order_in_dt(oracle, model_backlash, poly_table):
+    """No damping / friction / actuation / contact: E = KE + PE must be conserved up to the integrator's O(dt) error."""
+    drift = []
+    for dt in (0.002, 0.001, 0.0005):
+        m = _free_model(model_backlash, dt)
+        h = make_handle(oracle, m, poly_table, 2)
+        qpos, qvel = _random_state(m, 2, 1)
+        qpos[:, 3:7] = [1, 0, 0, 0]
+        h.set_state(qpos.ctypes.data, qvel.ctypes.data, 0)
+
+        def energy():
+            q, v = h.buffer_numpy("QPOS"), h.buffer_numpy("QVEL")
+            out = []
+            for i in range(2):
+                M = mjcf.mass_matrix(m, q[i, : m.nq].copy())
+                xipos = mjcf.body_jacobians(m, q[i, : m.nq].copy())[2]
+                out.append(0.5 * v[i, : m.nv] @ M @ v[i, : m.nv] + G * np.sum(m.body_mass[: m.nbody] * xipos[:, 2]))
+            return np.array(out)
+        e0 = energy()
+        h.physics_substeps(0, int(round(0.1 / dt)))
+        drift.append(np.abs(energy() - e0).max())
+    assert drift[0] < 0.05                                           # of ~45 J
+    assert 1.7 < drift[0] / drift[1] < 2.3 and 1.7 < drift[1] / drift[2] < 2.3
+
+
+def test_free_fall_and_momentum(oracle, model_backlash, poly_table):
+    m = _free_model(model_backlash)
+    h = make_handle(oracle, m, poly_table, 3)
+    qpos, qvel = _random_state(m, 3, 2)
+    h.set_state(qpos.ctypes.data, qvel.ctypes.data, 0)
+
+    def com_vel():
+        q, v = h.buffer_numpy("QPOS"), h.buffer_numpy("QVEL")
+        out = []
+        for i in range(3):
+            jacp = mjcf.body_jacobians(m, q[i, : m.nq].copy())[3]
+            mass = m.body_mass[: m.nbody]
+            out.append(sum(mass[b] * jacp[b] @ v[i, : m.nv] for b in range(m.nbody)) / mass.sum())
+        return np.array(out)
+    v0 = com_vel()
+    h.physics_substeps(0, 50)
+    dv = com_vel() - v0
+    assert np.abs(dv[:, :2]).max() < 1e-3 and np.abs(dv[:, 2] + G * 0.1).max() < 2e-3     # only gravity acts on the COM
+
+
+def test_standing_equilibrium_and_sensors(oracle, model_backlash, poly_table):
+    h = make_handle(oracle, model_backlash, poly_table, 1)
+    h.physics_substeps(0, 1500)                         # settle from the keyframe under the home ctrl (3 s)
+    nfr, nlim = 14, 24
+    f = h.buffer_numpy("EFC_FORCE")[0]
+    dist = h.buffer_numpy("CONTACT_DIST")[0]
+    assert (dist[:8] < 0).sum() >= 6 and np.all(dist[8:] == 1)
+    # pyramid edge forces sum to the normal force: sum(f_edges) * 1 (each edge has unit normal component)
+    normal = f[nfr + nlim: nfr + nlim + 32].sum()
+    weight = model_backlash.body_mass[: model_backlash.nbody].sum() * G
+    assert abs(normal - weight) / weight < 0.02
+    sd = h.buffer_numpy("SENSORDATA")[0]
+    assert np.abs(sd[0:3]).max() < 5e-3 and np.abs(sd[3:6]).max() < 5e-3          # gyro, local linvel ~ 0 at rest
+    assert abs(np.linalg.norm(sd[6:9]) - G) < 0.05 and sd[11] > 0.99              # accelerometer reads +g, upvector z ~ 1
+    q = h.buffer_numpy("QPOS")[0]
+    assert 0.12 < q[2] < 0.2 and abs(np.linalg.norm(q[3:7]) - 1) < 1e-12
+
+
+def test_joint_limit_pushes_back(oracle, model_backlash, poly_table):
+    m = copy.deepcopy(model_backlash)
+    m.arrays["act_kp"][:] = 0
+    h = make_handle(oracle, m, poly_table, 1)
+    qpos = m.key_qpos[: m.nq].astype(np.float32)[None].copy()
+    qpos[0, 2] = 1.0
+    hi = m.jnt_range[1, 1]
+    qpos[0, 7] = hi + 0.05                                   # left_hip_yaw past its upper limit
+    qvel = np.zeros((1, m.nv), np.float32)
+    h.set_state(qpos.ctypes.data, qvel.ctypes.data, 0)
+    h.forward()
+    f = h.buffer_numpy("EFC_FORCE")[0]
+    assert f[14] > 0                                          # first limit row active, force positive (one-sided)
+    assert h.buffer_numpy("QACC")[0, 6] < 0                   # accelerates back inside the range
+    h.physics_substeps(0, 200)
+    assert h.buffer_numpy("QPOS")[0, 7] < hi + 0.01
+
+
+def test_frictionloss_holds_a_slow_joint(oracle, model_backlash, poly_table):
+    """Dry friction (0.068 N m) cancels small torques exactly: a head joint with a tiny velocity stops instead of coasting."""
+    m = copy.deepcopy(model_backlash)
+    A = m.arrays
+    A["act_kp"][:] = 0; A["dof_damping"][:] = 0; A["gravity"][:] = 0
+    h = make_handle(oracle, m, poly_table, 1)
+    qpos = m.key_qpos[: m.nq].astype(np.float32)[None].copy(); qpos[0, 2] = 1.0
+    qvel = np.zeros((1, m.nv), np.float32)
+    d = int(m.jnt_dofadr[m.joint_id("head_yaw")])
+    qvel[0, d] = 0.01
+    h.set_state(qpos.ctypes.data, qvel.ctypes.data, 0)
+    h.physics_substeps(0, 100)
+    assert abs(h.buffer_numpy("QVEL")[0, d]) < 1e-5
+
+
+def test_nan_state_terminates(oracle, model_backlash, poly_table):
+    h = make_handle(oracle, model_backlash, poly_table, 2)
+    keys = np.array([[0, 1], [0, 2]], np.uint32)
+    h.reset(keys.ctypes.data)
+    qpos = h.buffer_numpy("QPOS")[:, :31].astype(np.float32).copy()
+    qpos[1, 9] = np.nan
+    h.set_state(qpos.ctypes.data, 0, 0)
+    act = np.zeros((2, 14), np.float32)
+    h.step(act.ctypes.data)
+    assert h.buffer_numpy("DONE").tolist() == [0.0, 1.0]
+    assert not np.isnan(h.buffer_numpy("QPOS")[1]).any()      # auto-reset restored the first state
+    assert abs(h.buffer_numpy("REWARD")[1] - 20.0 * 0.02) < 1e-12   # every term is nan_to_num-ed: only "alive" survives

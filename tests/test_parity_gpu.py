@@ -1,0 +1,171 @@
+"""CUDA path vs the CPU oracle through the C-ABI (run on the B200 box: pytest -m gpu).
+
+Tolerances (fp32 kernel vs fp64 oracle on identical inputs): qacc rel 1e-4, qpos abs 1e-4 and qvel abs 1e-3
+after one control step (10 substeps), efc_force rel 1e-3 (abs 1e-3 N), rewards abs 1e-4, obs abs 2e-3, reference motion
+abs 1e-4 vs the fp64 Horner of the oracle (fp32 Horner on |coef| ~ 2e5 polynomials), integer / key / index state bit-exact.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from open_duck_playground_b200 import rng as jr
+from open_duck_playground_b200.joystick import Joystick
+
+pytestmark = pytest.mark.gpu
+
+TASKS = ["flat_terrain_backlash", "flat_terrain"]
+
+
+def _pair(oracle, task, n, **kw):
+    gpu = Joystick(task, device="cuda:0", **kw)
+    ref = Joystick(task, library=oracle, **kw)
+    for e in (gpu, ref):
+        e.randomize(jr.split(jr.PRNGKey(11), n))
+    keys = jr.split(jr.PRNGKey(0), n)
+    return gpu, ref, gpu.reset(keys), ref.reset(keys)
+
+
+def _np(t):
+    return t.detach().cpu().numpy().astype(np.float64)
+
+
+def _close(a, b, atol, rtol=0.0, what=""):
+    a, b = _np(a), _np(b)
+    err = np.abs(a - b) - rtol * np.abs(b)
+    assert err.max() <= atol, f"{what}: max err {np.abs(a - b).max():.3e} (atol {atol}, rtol {rtol})"
+
+
+def _sync_from_ref(gpu, ref):
+    f = lambda name: torch.from_numpy(ref.buffer(name).numpy().astype(np.float32))
+    gpu.set_state(f("QPOS"), f("QVEL"), f("QACC_WARM"))
+
+
+@pytest.mark.parametrize("task", TASKS)
+def test_randomize_and_reset_parity(oracle, task):
+    n = 256
+    gpu, ref, sg, sr = _pair(oracle, task, n)
+    torch.cuda.synchronize()
+    m = gpu.mj_model
+    assert np.array_equal(gpu.buffer("INFO_RNG").cpu().numpy(), ref.buffer("INFO_RNG").numpy())          # key stream bit-exact
+    assert np.array_equal(gpu.buffer("INFO_PUSH_INTERVAL").cpu().numpy(), ref.buffer("INFO_PUSH_INTERVAL").numpy())
+    _close(gpu.buffer("DR_PARAMS")[:, : m.nbody], ref.buffer("DR_PARAMS")[:, 1:1 + m.nbody], 1e-6, what="dr mass")
+    _close(sg.data.qpos, sr.data.qpos, 1e-6, what="qpos")
+    _close(sg.data.qvel, sr.data.qvel, 1e-7, what="qvel")
+    _close(sg.data.qacc_warmstart, sr.data.qacc_warmstart, 2e-2, 1e-4, what="qacc")
+    _close(sg.info["command"], sr.info["command"], 1e-6, what="command")
+    _close(sg.info["current_reference_motion"], sr.info["current_reference_motion"], 1e-4, what="reference motion")
+    _close(sg.data.efc_force, sr.data.efc_force, 1e-3, 1e-3, what="efc_force")
+    _close(sg.obs["state"], sr.obs["state"], 2e-3, 1e-4, what="obs state")
+    _close(sg.obs["privileged_state"], sr.obs["privileged_state"], 2e-3, 1e-4, what="obs privileged")
+    # contact distances of ACTIVE contacts agree; the active sets agree
+    dg, dr = _np(sg.data.contact_dist), _np(sr.data.contact_dist)
+    assert np.array_equal(dg < 0, dr < 0)
+    assert np.abs(dg - dr)[dr < 0].max() < 1e-6
+
+
+@pytest.mark.parametrize("task", TASKS)
+def test_physics_substeps_parity(oracle, task):
+    n = 256
+    gpu, ref, sg, sr = _pair(oracle, task, n)
+    m = gpu.mj_model
+    rs = np.random.default_rng(1)
+    for _ in range(3):
+        ctrl = (m.key_ctrl[: m.nu] + 0.25 * rs.uniform(-1, 1, (n, m.nu))).astype(np.float32)
+        _sync_from_ref(gpu, ref)
+        dg = gpu.physics_substeps(torch.from_numpy(ctrl).cuda(), 10)
+        dr = ref.physics_substeps(torch.from_numpy(ctrl), 10)
+        torch.cuda.synchronize()
+        _close(dg.qpos, dr.qpos, 1e-4, what="qpos after 10 substeps")
+        _close(dg.qvel, dr.qvel, 1e-3, what="qvel after 10 substeps")
+        _close(dg.qacc, dr.qacc, 2e-2, 1e-4, what="qacc")
+        _close(dg.efc_force, dr.efc_force, 1e-3, 1e-3, what="efc_force")
+        _close(dg.sensordata, dr.sensordata, 2e-3, 1e-4, what="sensordata")
+        _close(dg.actuator_force, dr.actuator_force, 1e-4, what="actuator_force")
+
+
+def test_single_substep_intermediates(oracle):
+    """mass matrix, bias forces, smooth acceleration, constraint rows and the Newton direction, phase by phase."""
+    n = 64
+    gpu, ref, sg, sr = _pair(oracle, "flat_terrain_backlash", n)
+    outs = []
+    for env, dt in ((gpu, np.float32), (ref, np.float64)):
+        L = env.handle.L.lib
+        buf = np.zeros((n, L.oduck_debug_stride()), dt)
+        L.oduck_debug_forward.argtypes = [C.c_void_p, C.c_void_p]
+        env.handle.L.check(L.oduck_debug_forward(env.handle.h, buf.ctypes.data))
+        outs.append(buf.astype(np.float64))
+    g, r = outs
+    sect = {"M": (0, 1024, 2e-6, 1e-5), "qfrc_bias": (1024, 32, 2e-5, 1e-5), "qacc_smooth": (1088, 32, 1e-3, 1e-4), "D_lim": (1216, 32, 1e-5, 1e-4),
+            "D_con": (1248, 12, 1e-3, 1e-3), "aref_lim": (1296, 32, 1e-2, 1e-4), "aref_con": (1328, 48, 1e-2, 1e-4), "xpos": (1440, 96, 1e-6, 0),
+            "com": (1536, 3, 1e-6, 0), "cdof": (1540, 192, 2e-6, 0), "qacc": (1736, 32, 3e-2, 1e-4)}
+    for name, (o, ln, atol, rtol) in sect.items():
+        err = np.abs(g[:, o:o + ln] - r[:, o:o + ln]) - rtol * np.abs(r[:, o:o + ln])
+        assert err.max() <= atol, f"{name}: {np.abs(g[:, o:o + ln] - r[:, o:o + ln]).max():.3e}"
+
+
+@pytest.mark.parametrize("task", TASKS)
+def test_env_step_parity(oracle, task):
+    n = 256
+    gpu, ref, sg, sr = _pair(oracle, task, n)
+    rs = np.random.default_rng(2)
+    for t in range(8):
+        act = rs.uniform(-1, 1, (n, gpu.action_size)).astype(np.float32)
+        _sync_from_ref(gpu, ref)                    # compare one control step from shared states (chaotic divergence otherwise)
+        sg, sr = gpu.step(sg, torch.from_numpy(act).cuda()), ref.step(sr, torch.from_numpy(act))
+        torch.cuda.synchronize()
+        for name in ("INFO_RNG", "INFO_STEP", "INFO_STEPS", "INFO_PUSH_STEP", "INFO_IMITATION_I"):
+            assert np.array_equal(gpu.buffer(name).cpu().numpy(), ref.buffer(name).numpy()), name
+        _close(sg.data.qpos, sr.data.qpos, 1e-4, what="qpos")
+        _close(sg.data.qvel, sr.data.qvel, 1e-3, what="qvel")
+        _close(sg.reward, sr.reward, 1e-4, what="reward")
+        assert np.array_equal(_np(sg.done), _np(sr.done))
+        _close(gpu.buffer("METRICS"), ref.buffer("METRICS"), 1e-3, 1e-4, what="metrics")
+        _close(sg.obs["state"], sr.obs["state"], 2e-3, 1e-4, what="obs state")
+        _close(sg.obs["privileged_state"], sr.obs["privileged_state"], 2e-3, 1e-4, what="obs privileged")
+        for k in ("command", "motor_targets", "action_history", "feet_air_time", "last_contact", "swing_peak", "push", "imitation_phase", "imu_history"):
+            _close(sg.info[k], sr.info[k], 1e-5, what=k)
+        _close(sg.info["current_reference_motion"], sr.info["current_reference_motion"], 1e-4, what="reference motion")
+
+
+def test_rollout_statistics_match(oracle):
+    """Long rollouts diverge chaotically; their statistics must not (same seeds, 150 control steps, fixed action noise)."""
+    n = 512
+    gpu, ref, sg, sr = _pair(oracle, "flat_terrain_backlash", n)
+    rs = np.random.default_rng(3)
+    rg = rr = 0.0
+    dg = dr = 0.0
+    for t in range(150):
+        act = (0.3 * rs.standard_normal((n, 14))).astype(np.float32)
+        sg, sr = gpu.step(sg, torch.from_numpy(act).cuda()), ref.step(sr, torch.from_numpy(act))
+        rg += float(sg.reward.mean()); rr += float(sr.reward.mean())
+        dg += float(sg.done.sum()); dr += float(sr.done.sum())
+    assert abs(rg - rr) / abs(rr) < 0.03, (rg, rr)
+    assert abs(dg - dr) <= max(10.0, 0.15 * dr), (dg, dr)
+
+
+def test_autoreset_truncation_and_full_size_invariants(oracle):
+    """BASELINE-size batch (8192 envs): size-independent properties -- unit quaternions, finite state, clip range of the reward,
+    truncation exactly at episode_length with data/obs restored to the stored first state."""
+    n = 8192
+    gpu = Joystick("flat_terrain_backlash", device="cuda:0", config_overrides={"episode_length": 4})
+    gpu.randomize(jr.split(jr.PRNGKey(1), n))
+    st = gpu.reset(jr.split(jr.PRNGKey(0), n))
+    first_q, first_o = st.data.qpos.clone(), st.obs["state"].clone()
+    rs = torch.Generator(device="cuda").manual_seed(0)
+    for k in range(4):
+        act = torch.rand(n, 14, device="cuda", generator=rs) * 2 - 1
+        st = gpu.step(st, act)
+        q = st.data.qpos
+        assert torch.isfinite(q).all() and torch.isfinite(st.obs["privileged_state"]).all()
+        assert (q[:, 3:7].norm(dim=1) - 1).abs().max() < 1e-5
+        assert (st.reward >= 0).all() and (st.reward <= 1e4).all()
+    assert (st.done == 1).all() and torch.equal(st.data.qpos, first_q) and torch.equal(st.obs["state"], first_o)
+    assert int(gpu.handle.launch_count()) == 2 + 4          # randomize + reset + 4 fused steps: one launch per env.step
+
+
+def test_library_is_the_cuda_one():
+    from open_duck_playground_b200 import capi
+    lib = capi.load_cuda_library()
+    assert lib.is_device and lib.path.endswith("csrc/liboduck_cuda.so")
