@@ -636,10 +636,10 @@ static void update_constraint(const OduckModel& m, const Scratch& s, Ctx& c) {
       if (c.active[r]) cost += (real)0.5 * s.D[r] * x * x;
     }
   }
-  for (int j = 0; j < m.nv; j++) {
-    real v = 0;
-    for (int r = 0; r < s.nefc; r++) v += s.J[r][j] * c.efc_force[r];
-    c.qfrc_constraint[j] = v;
+  for (int j = 0; j < m.nv; j++) c.qfrc_constraint[j] = 0;
+  for (int r = 0; r < s.nefc; r++) {
+    if (c.efc_force[r] == 0) continue;
+    for (int j = 0; j < m.nv; j++) c.qfrc_constraint[j] += s.J[r][j] * c.efc_force[r];
   }
   real g = 0;
   for (int j = 0; j < m.nv; j++) g += (c.Ma[j] - s.qfrc_smooth[j]) * (c.qacc[j] - s.qacc_smooth[j]);
@@ -678,6 +678,7 @@ static void ctx_create(const OduckModel& m, Scratch& s, const real* qacc, Ctx& c
     c.search[j] = 0;
   }
   for (int r = 0; r < s.nefc; r++) {
+    if (s.D[r] == 0) { c.Jaref[r] = 0; continue; }   // empty (inactive) row: J = 0, aref = 0
     real v = 0;
     for (int j = 0; j < m.nv; j++) v += s.J[r][j] * qacc[j];
     c.Jaref[r] = v - s.aref[r];
@@ -705,7 +706,7 @@ static void linesearch(const OduckModel& m, const Scratch& s, Ctx& c) {
   }
   for (int r = 0; r < s.nefc; r++) {
     real v = 0;
-    for (int j = 0; j < m.nv; j++) v += s.J[r][j] * c.search[j];
+    if (s.D[r] != 0) for (int j = 0; j < m.nv; j++) v += s.J[r][j] * c.search[j];
     jv[r] = v;
   }
   real qg[3] = {c.gauss, 0, 0};
