@@ -79,6 +79,7 @@ __device__ __forceinline__ void load_env(const DevModel& m, WarpSmem& s, Lane& L
   L.floss = isd ? dr[DR_FLOSS + lane] : 0.f;
   L.arm = isd ? dr[DR_ARM + lane] : 0.f;
   L.mass = lane < m.nbody ? dr[lane] : 0.f;
+  for (int i = lane; i < 528; i += 32) s.A[i] = 0.f;   // structural zeros of M (only ancestor pairs are rewritten each substep)
   L.ipos = v3(m.b_ipos[0][lane], m.b_ipos[1][lane], m.b_ipos[2][lane]);
   if (lane == 1) L.ipos = v3(dr[DR_IPOS1], dr[DR_IPOS1 + 1], dr[DR_IPOS1 + 2]);   // TORSO_BODY_ID = 1 (randomize.py:23)
   __syncwarp();
@@ -563,6 +564,24 @@ static int build_dev_model(const OduckModel& M, DevModel& D, std::string& err) {
     }
   }
   D.nfr = nfr; D.nlim = nlim;
+  for (int d = 0; d < M.nv; d++) {
+    int cnt = 0, tmp[32];
+    for (int a = M.dof_parentid[d]; a >= 0; a = M.dof_parentid[a]) tmp[cnt++] = a;
+    D.d_depth[d] = cnt;
+    D.max_dof_depth = std::max(D.max_dof_depth, cnt);
+    for (int t = 0; t < cnt; t++) D.anc[d][t] = (unsigned char)tmp[cnt - 1 - t];   // root first
+  }
+  for (int a = 0, p = 0; a < 32 && p < 512; a++)
+    for (int b = 0; b <= a && p < 512; b++, p++) D.pair_ab[p] = (unsigned short)((a << 8) | b);
+  D.n_mpairs = 0;
+  for (int i = 0; i < M.nv; i++)
+    for (int j = i; j >= 0; j = M.dof_parentid[j]) D.mpair[D.n_mpairs++] = (unsigned short)((i << 8) | j);
+  D.body_rounds = 0;
+  while ((1 << D.body_rounds) < D.maxdepth) D.body_rounds++;
+  for (int b = 0; b < M.nbody; b++) {
+    int j0 = M.body_jntadr[b];
+    D.b_sameaxis[b] = (M.body_jntnum[b] == 2 && M.jnt_axis[j0][0] == M.jnt_axis[j0 + 1][0] && M.jnt_axis[j0][1] == M.jnt_axis[j0 + 1][1] && M.jnt_axis[j0][2] == M.jnt_axis[j0 + 1][2]);
+  }
   D.prefix_rounds = 0;
   while ((1 << D.prefix_rounds) < maxchain) D.prefix_rounds++;
   for (int u = 0; u < M.nu; u++) {

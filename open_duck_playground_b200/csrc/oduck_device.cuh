@@ -69,6 +69,14 @@ struct DevModel {
   float vert[2][3][NLANE];
   float key_qpos[36], key_ctrl[16], qpos0[36];
   int act_dof[16], act_qadr[16], act_bl_qadr[16];
+  // factorisation tables: anc[k] = dof ancestors of k, root first (anc[k][l] is the ancestor at depth l); d_depth[k] = their count
+  unsigned char anc[NLANE][NLANE];
+  int d_depth[NLANE];
+  int max_dof_depth;
+  unsigned short pair_ab[512];   // p -> (a << 8 | b), b <= a, p = a (a + 1) / 2 + b
+  unsigned short mpair[512];     // structural non-zeros of M: (i << 8 | j), j an ancestor of i or i itself
+  int n_mpairs, body_rounds;
+  int b_sameaxis[NLANE];
 };
 
 // per-warp shared memory
@@ -83,6 +91,7 @@ struct WarpSmem {
   float qpos0[36];
   float con[NCON_ALL][8];     // dist, pos xyz, F(n,t1,t2), pad
   float misc[64];
+  float rhs[NLANE];            // right-hand side swept leaf-to-root inside chol_rev
   float outrec[OUT_STRIDE];     // staged outputs of the last forward (copied to HBM once per launch)
 };
 
@@ -195,44 +204,62 @@ __device__ __forceinline__ S6 inert_mul(const I10& I, S6 v) {  // mju_mulInertVe
 }
 
 // ---------------------------------------------------------------------------------- dense kernels on packed triangles
-// In-place leaf-to-root factorisation A = L^T L (L lower, stored where A was).  With tree == true only the
-// ancestors of k are visited (exact for the sparsity of a kinematic tree); otherwise every earlier row.
-__device__ __forceinline__ void chol_rev(float* A, int n, int lane, const int* dparent, bool tree) {
+// In-place leaf-to-root factorisation A = L^T L (L lower, stored where A was), fused with the leaf-to-root sweep
+// rhs <- L^-T rhs.  For pivot k only rows/columns in S(k) are touched, S(k) = dof ancestors of k (tree == true: exact for
+// the sparsity of a kinematic tree, no fill-in) or all j < k (dense fallback).  The |S|(|S|+1)/2 rank-1 updates of one
+// pivot are independent, so they are spread over the warp 32 at a time (pair table), instead of one ancestor row per step.
+__device__ __forceinline__ void chol_rev(const DevModel& m, float* A, float* rhs, int n, int lane, bool tree) {
   for (int k = n - 1; k >= 0; --k) {
     const int rk = TRI(k);
-    float akk = A[rk + k];
-    float inv = rsqrtf(akk);
-    float lkj = 0.f;
-    if (lane < k) { lkj = A[rk + lane] * inv; A[rk + lane] = lkj; }
-    else if (lane == k) A[rk + k] = akk * inv;
-    __syncwarp();
-    if (tree) {
-      for (int i = dparent[k]; i >= 0; i = dparent[i]) {
-        float lki = A[rk + i];
-        if (lane <= i) A[TRI(i) + lane] -= lki * lkj;
-      }
-    } else {
-      for (int i = k - 1; i >= 0; --i) {
-        float lki = A[rk + i];
-        if (lki != 0.f && lane <= i) A[TRI(i) + lane] -= lki * lkj;
-      }
+    const int d = tree ? m.d_depth[k] : k;
+    const unsigned char* ak = m.anc[k];
+    __syncwarp();                                  // rank-1 updates of the previous pivot are visible
+    const float akk = A[rk + k];
+    const float inv = rsqrtf(akk);
+    const float yk = rhs[k] * inv;
+    __syncwarp();                                  // everyone holds akk / rhs[k] before they are overwritten
+    if (lane < d) {
+      const int i = tree ? ak[lane] : lane;
+      const float l = A[rk + i] * inv;
+      A[rk + i] = l;
+      rhs[i] -= l * yk;
+    } else if (lane == d) {
+      A[rk + k] = akk * inv;
+      rhs[k] = yk;
     }
     __syncwarp();
+    const int npairs = (d * (d + 1)) >> 1;
+    for (int p = lane; p < npairs; p += 32) {
+      const unsigned ab = m.pair_ab[p];
+      const int a = ab >> 8, b = ab & 255;
+      const int ia = tree ? ak[a] : a, ib = tree ? ak[b] : b;
+      A[TRI(ia) + ib] -= A[rk + ia] * A[rk + ib];
+    }
   }
+  __syncwarp();
 }
-// Solve (L^T L) x = b with b, x distributed one element per lane.
-__device__ __forceinline__ float chol_rev_solve(const float* L, int n, int lane, float b) {
-  for (int k = n - 1; k >= 0; --k) {
-    float yk = __shfl_sync(FULLMASK, b, k) / L[TRI(k) + k];
-    if (lane == k) b = yk;
-    else if (lane < k) b -= L[TRI(k) + lane] * yk;
+// Root-to-leaf sweep x <- L^-1 y with y one element per lane (y = rhs after chol_rev).  tree: all dofs of one depth level
+// are finished together (their ancestors are done), so the dependency chain is max_dof_depth long instead of n.
+__device__ __forceinline__ float chol_rev_back(const DevModel& m, const float* L, int n, int lane, float y, bool tree) {
+  if (tree) {
+    const int dep = lane < n ? m.d_depth[lane] : -1;
+    const float invd = lane < n ? 1.f / L[TRI(lane) + lane] : 0.f;
+    const unsigned char* al = m.anc[lane];
+    const int ri = TRI(lane);
+    for (int lev = 0; lev <= m.max_dof_depth; ++lev) {
+      if (dep == lev) y *= invd;
+      const int j = dep > lev ? al[lev] : lane;
+      const float xj = __shfl_sync(FULLMASK, y, j);
+      if (dep > lev) y -= L[ri + j] * xj;
+    }
+    return y;
   }
   for (int j = 0; j < n; ++j) {
-    float xj = __shfl_sync(FULLMASK, b, j) / L[TRI(j) + j];
-    if (lane == j) b = xj;
-    else if (lane > j && lane < n) b -= L[TRI(lane) + j] * xj;
+    float xj = __shfl_sync(FULLMASK, y, j) / L[TRI(j) + j];
+    if (lane == j) y = xj;
+    else if (lane > j && lane < n) y -= L[TRI(lane) + j] * xj;
   }
-  return b;
+  return y;
 }
 // y = A x for the packed symmetric matrix; one element per lane.
 __device__ __forceinline__ float symv(const float* A, int n, int lane, float x) {

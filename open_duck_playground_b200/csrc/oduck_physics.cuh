@@ -19,39 +19,50 @@ __device__ __forceinline__ void forward_euler(const DevModel& m, WarpSmem& s, La
                                               const bool integrate, float* __restrict__ out, float* __restrict__ dbg) {
   const int nv = m.nv, nb = m.nbody;
   // ------------------------------------------------------------------ kinematics (lane = body)
-  const int par = m.b_parent[lane], dep = m.b_depth[lane], jt = m.b_jtype[lane];
-  V3 xp = v3(0.f, 0.f, 0.f);
-  Q4 xq; xq.w = 1.f; xq.x = xq.y = xq.z = 0.f;
-  V3 ax0w = v3(0.f, 0.f, 0.f), ax1w = v3(0.f, 0.f, 0.f);
-  for (int lev = 1; lev <= m.maxdepth; ++lev) {
-    V3 pp = v3(__shfl_sync(FULLMASK, xp.x, par), __shfl_sync(FULLMASK, xp.y, par), __shfl_sync(FULLMASK, xp.z, par));
-    Q4 pq;
-    pq.w = __shfl_sync(FULLMASK, xq.w, par); pq.x = __shfl_sync(FULLMASK, xq.x, par);
-    pq.y = __shfl_sync(FULLMASK, xq.y, par); pq.z = __shfl_sync(FULLMASK, xq.z, par);
-    if (dep == lev) {
-      V3 bp = v3(m.b_pos[0][lane], m.b_pos[1][lane], m.b_pos[2][lane]);
-      Q4 bq; bq.w = m.b_quat[0][lane]; bq.x = m.b_quat[1][lane]; bq.y = m.b_quat[2][lane]; bq.z = m.b_quat[3][lane];
-      xp = pp + qrot(pq, bp);
-      xq = qmul(pq, bq);
-      if (jt == 1) {
-        const int qa = m.b_qadr0[lane];
-        xp = v3(s.qpos[qa], s.qpos[qa + 1], s.qpos[qa + 2]);
-        xq.w = s.qpos[qa + 3]; xq.x = s.qpos[qa + 4]; xq.y = s.qpos[qa + 5]; xq.z = s.qpos[qa + 6];
-      } else if (jt >= 2) {
-        V3 a0 = v3(m.b_ax0[0][lane], m.b_ax0[1][lane], m.b_ax0[2][lane]);
-        ax0w = qrot(xq, a0);
-        const int qa = m.b_qadr0[lane];
-        xq = qmul(xq, axis_angle(a0, s.qpos[qa] - s.qpos0[qa]));
-        if (jt == 3) {
-          V3 a1 = v3(m.b_ax1[0][lane], m.b_ax1[1][lane], m.b_ax1[2][lane]);
-          ax1w = qrot(xq, a1);
-          const int qb = m.b_qadr1[lane];
-          xq = qmul(xq, axis_angle(a1, s.qpos[qb] - s.qpos0[qb]));
-        }
+  // local transform of every body at once (joint rotations do not depend on the parents), then log2(depth) rounds of
+  // pointer jumping compose them into world poses: X_world[b] = X_world[parent] o T_b is an associative prefix product.
+  const int jt = m.b_jtype[lane];
+  V3 xp = v3(m.b_pos[0][lane], m.b_pos[1][lane], m.b_pos[2][lane]);
+  Q4 xq; xq.w = m.b_quat[0][lane]; xq.x = m.b_quat[1][lane]; xq.y = m.b_quat[2][lane]; xq.z = m.b_quat[3][lane];
+  V3 a0f = v3(m.b_ax0[0][lane], m.b_ax0[1][lane], m.b_ax0[2][lane]);   // joint-0 axis in the final body frame
+  const V3 a1 = v3(m.b_ax1[0][lane], m.b_ax1[1][lane], m.b_ax1[2][lane]);
+  int up = m.b_parent[lane] > 0 ? m.b_parent[lane] : -1;               // nearest ancestor not yet folded in (-1: world)
+  if (jt == 1) {
+    const int qa = m.b_qadr0[lane];
+    xp = v3(s.qpos[qa], s.qpos[qa + 1], s.qpos[qa + 2]);
+    xq.w = s.qpos[qa + 3]; xq.x = s.qpos[qa + 4]; xq.y = s.qpos[qa + 5]; xq.z = s.qpos[qa + 6];
+    xq = qnormalize(xq);
+    up = -1;
+  } else if (jt >= 2) {
+    const int qa = m.b_qadr0[lane];
+    float ang0 = s.qpos[qa] - s.qpos0[qa];
+    if (jt == 3) {
+      const int qb = m.b_qadr1[lane];
+      const float ang1 = s.qpos[qb] - s.qpos0[qb];
+      if (m.b_sameaxis[lane]) {
+        ang0 += ang1;                                                    // two hinges about one axis: angles add
+        xq = qmul(xq, axis_angle(a0f, ang0));
+      } else {
+        const Q4 q1 = axis_angle(a1, ang1);
+        xq = qmul(qmul(xq, axis_angle(a0f, ang0)), q1);
+        Q4 q1c = q1; q1c.x = -q1.x; q1c.y = -q1.y; q1c.z = -q1.z;
+        a0f = qrot(q1c, a0f);
       }
-      xq = qnormalize(xq);
+    } else {
+      xq = qmul(xq, axis_angle(a0f, ang0));
     }
   }
+  for (int r = 0; r < m.body_rounds; ++r) {
+    const int src = up < 0 ? 0 : up;
+    const V3 pp = v3(__shfl_sync(FULLMASK, xp.x, src), __shfl_sync(FULLMASK, xp.y, src), __shfl_sync(FULLMASK, xp.z, src));
+    Q4 pq;
+    pq.w = __shfl_sync(FULLMASK, xq.w, src); pq.x = __shfl_sync(FULLMASK, xq.x, src);
+    pq.y = __shfl_sync(FULLMASK, xq.y, src); pq.z = __shfl_sync(FULLMASK, xq.z, src);
+    const int pup = __shfl_sync(FULLMASK, up, src);
+    if (up >= 0) { xp = pp + qrot(pq, xp); xq = qmul(pq, xq); up = pup; }
+  }
+  xq = qnormalize(xq);
+  const V3 ax0w = qrot(xq, a0f), ax1w = qrot(xq, a1);
   float R[9];
   {
     const float w = xq.w, x = xq.x, y = xq.y, z = xq.z;
@@ -136,30 +147,27 @@ __device__ __forceinline__ void forward_euler(const DevModel& m, WarpSmem& s, La
 #undef ACC
     }
   }
-  // ------------------------------------------------------------------ M (lane = dof row i), packed lower triangle
+  // ------------------------------------------------------------------ M: one (dof, ancestor-or-self) pair per lane and wave
   {
     I10 cb;
 #define GET(f) cb.f = __shfl_sync(FULLMASK, crb.f, dbody);
     GET(xx) GET(yy) GET(zz) GET(xy) GET(xz) GET(yz) GET(hx) GET(hy) GET(hz) GET(m)
 #undef GET
-    const S6 buf = inert_mul(cb, cd);
-    const int anc = m.d_ancmask[lane];
-    const int ri = TRI(lane);
-    for (int j = 0; j < nv; ++j) {
-      S6 cj; cj.a0 = s.cdof[0][j]; cj.a1 = s.cdof[1][j]; cj.a2 = s.cdof[2][j]; cj.l0 = s.cdof[3][j]; cj.l1 = s.cdof[4][j]; cj.l2 = s.cdof[5][j];
-      float v = s6dot(cj, buf);
-      if (j <= lane && lane < nv) {
-        float val = ((anc >> j) & 1) ? v : 0.f;
-        if (j == lane) val += L.arm;
-        s.A[ri + j] = val;
-      }
+    const S6 buf = inert_mul(cb, cd);                                   // crb[body_i] * cdof_i, staged for the pair pass
+    float (*bf)[NLANE] = reinterpret_cast<float (*)[NLANE]>(&s.J[0][0]); // J is not live yet
+    bf[0][lane] = buf.a0; bf[1][lane] = buf.a1; bf[2][lane] = buf.a2; bf[3][lane] = buf.l0; bf[4][lane] = buf.l1; bf[5][lane] = buf.l2;
+    bf[6][lane] = L.arm;
+    __syncwarp();
+    for (int pp = lane; pp < m.n_mpairs; pp += 32) {
+      const unsigned ij = m.mpair[pp];
+      const int i = ij >> 8, j = ij & 255;
+      float v = s.cdof[0][j] * bf[0][i] + s.cdof[1][j] * bf[1][i] + s.cdof[2][j] * bf[2][i] + s.cdof[3][j] * bf[3][i] + s.cdof[4][j] * bf[4][i] +
+                s.cdof[5][j] * bf[5][i];
+      if (i == j) v += bf[6][i];
+      s.A[TRI(i) + j] = v;
     }
   }
   __syncwarp();
-  for (int idx = lane; idx < TRI(nv); idx += 32) s.H[idx] = s.A[idx];
-  __syncwarp();
-  chol_rev(s.H, nv, lane, m.d_parent, true);
-
   // ------------------------------------------------------------------ com_vel: prefix sums over the dof tree (lane = dof)
   const int dpar = m.d_parent[lane];
   S6 Sv = lane < nv ? s6scale(cd, L.qvel) : s6zero();
@@ -215,7 +223,11 @@ __device__ __forceinline__ void forward_euler(const DevModel& m, WarpSmem& s, La
     aforce = fminf(fmaxf(f, m.d_flo[lane]), m.d_fhi[lane]);
   }
   const float fs = lane < nv ? (-m.d_damping[lane] * L.qvel - qfrc_bias + aforce) : 0.f;   // qfrc_smooth
-  const float as = chol_rev_solve(s.H, nv, lane, fs);                                      // qacc_smooth
+  for (int idx = lane; idx < TRI(nv); idx += 32) s.H[idx] = s.A[idx];
+  s.rhs[lane] = fs;
+  __syncwarp();
+  chol_rev(m, s.H, s.rhs, nv, lane, true);                                                  // factor_m + L^-T qfrc_smooth
+  const float as = chol_rev_back(m, s.H, nv, lane, s.rhs[lane], true);                      // qacc_smooth
 
   // ------------------------------------------------------------------ collision: plane (z = 0) vs convex foot hulls (lane = vertex)
   for (int f = 0; f < 2; ++f) {
@@ -431,8 +443,10 @@ __device__ __forceinline__ void forward_euler(const DevModel& m, WarpSmem& s, La
     if (DBG) {
       for (int j = 0; j <= lane && lane < nv; ++j) { dbg[4096 + lane * 32 + j] = s.H[TRI(lane) + j]; dbg[4096 + j * 32 + lane] = s.H[TRI(lane) + j]; }
     }
-    chol_rev(s.H, nv, lane, m.d_parent, true);
-    search = -chol_rev_solve(s.H, nv, lane, grad);
+    s.rhs[lane] = grad;
+    __syncwarp();
+    chol_rev(m, s.H, s.rhs, nv, lane, true);
+    search = -chol_rev_back(m, s.H, nv, lane, s.rhs[lane], true);
     if (lane >= nv) search = 0.f;
   }
   // ------------------------------------------------------------------ line search (solver.py _linesearch)
@@ -482,15 +496,15 @@ __device__ __forceinline__ void forward_euler(const DevModel& m, WarpSmem& s, La
       const LSPoint lo_next = point(lo.alpha - lo.d0 / lo.d1);
       const LSPoint hi_next = point(hi.alpha - hi.d0 / hi.d1);
       const LSPoint mid = point(0.5f * (lo.alpha + hi.alpha));
-      // solver.py _in_bracket: a candidate replaces a bracket end when it lies between that end and the root, same side
-      auto in_bracket = [](float x, float y) { return ((x < y) && (y < 0.f)) || ((x > y) && (y > 0.f)); };
-      const bool s1 = in_bracket(lo.d0, lo_next.d0); if (s1) lo = lo_next;
-      const bool s2 = in_bracket(lo.d0, mid.d0);     if (s2) lo = mid;
-      const bool s3 = in_bracket(lo.d0, hi_next.d0); if (s3) lo = hi_next;
-      const bool s4 = in_bracket(hi.d0, hi_next.d0); if (s4) hi = hi_next;
-      const bool s5 = in_bracket(hi.d0, mid.d0);     if (s5) hi = mid;
-      const bool s6 = in_bracket(hi.d0, lo_next.d0); if (s6) hi = lo_next;
-      swap = s1 || s2 || s3 || s4 || s5 || s6;
+      // Bracket update (oracle/oduck_oracle.cpp linesearch has the rationale): a candidate becomes the new lo if its slope is
+      // negative and (lo sits on the wrong side of the root or the candidate is closer to it); symmetrically for hi.
+      swap = false;
+#define TRY_LO(c) if ((c).d0 < 0.f && (lo.d0 > 0.f || (c).d0 > lo.d0)) { lo = (c); swap = true; }
+#define TRY_HI(c) if ((c).d0 >= 0.f && (hi.d0 < 0.f || (c).d0 < hi.d0)) { hi = (c); swap = true; }
+      TRY_LO(lo_next) TRY_LO(mid) TRY_LO(hi_next)
+      TRY_HI(hi_next) TRY_HI(mid) TRY_HI(lo_next)
+#undef TRY_LO
+#undef TRY_HI
       ++it;
     }
     const bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);

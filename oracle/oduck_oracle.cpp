@@ -736,7 +736,10 @@ static void linesearch(const OduckModel& m, const Scratch& s, Ctx& c) {
   if (lo.d0 < p0.d0) { hi = p0; } else { hi = lo; lo = p0; }
   bool swap = true;
   int it = 0;
+  const bool trace = getenv("ODUCK_LS_TRACE") != nullptr;
+  if (trace) printf("LS p0: a=%g cost=%.9g d0=%g d1=%g | gtol=%g\n", (double)p0.alpha, (double)p0.cost, (double)p0.d0, (double)p0.d1, (double)gtol);
   while (true) {
+    if (trace) printf("  it%d lo(a=%.6g c=%.9g d0=%g) hi(a=%.6g c=%.9g d0=%g) swap=%d\n", it, (double)lo.alpha, (double)lo.cost, (double)lo.d0, (double)hi.alpha, (double)hi.cost, (double)hi.d0, (int)swap);
     bool done = it >= m.ls_iterations;
     done |= !swap;
     done |= (lo.d0 < 0) && (lo.d0 > -gtol);
@@ -745,15 +748,20 @@ static void linesearch(const OduckModel& m, const Scratch& s, Ctx& c) {
     LSPoint lo_next = point(lo.alpha - lo.d0 / lo.d1);
     LSPoint hi_next = point(hi.alpha - hi.d0 / hi.d1);
     LSPoint mid = point((real)0.5 * (lo.alpha + hi.alpha));
-    // solver.py: a candidate y replaces bracket end x when it lies between x and the root on the same side
-    auto in_bracket = [](real x, real y) { return ((x < y) && (y < 0)) || ((x > y) && (y > 0)); };
-    bool s1 = in_bracket(lo.d0, lo_next.d0); if (s1) lo = lo_next;
-    bool s2 = in_bracket(lo.d0, mid.d0);     if (s2) lo = mid;
-    bool s3 = in_bracket(lo.d0, hi_next.d0); if (s3) lo = hi_next;
-    bool s4 = in_bracket(hi.d0, hi_next.d0); if (s4) hi = hi_next;
-    bool s5 = in_bracket(hi.d0, mid.d0);     if (s5) hi = mid;
-    bool s6 = in_bracket(hi.d0, lo_next.d0); if (s6) hi = lo_next;
-    swap = s1 || s2 || s3 || s4 || s5 || s6;
+    // Bracket update.  solver.py swaps an end "if 1) it is not correctly at a bracket boundary (e.g. lo.deriv_0 > 0), OR
+    // 2) moving to next or mid narrows the bracket".  Restated so that the outcome does not depend on the rounding sign of a
+    // candidate that lands exactly on the root: each candidate c (Newton step from lo, midpoint, Newton step from hi) becomes
+    // the new lo if its slope is negative and (lo is on the wrong side or c is closer to the root), symmetrically for hi.
+    swap = false;
+    const LSPoint cand_lo[3] = {lo_next, mid, hi_next}, cand_hi[3] = {hi_next, mid, lo_next};
+    for (int k = 0; k < 3; k++) {
+      const LSPoint& c = cand_lo[k];
+      if (c.d0 < 0 && (lo.d0 > 0 || c.d0 > lo.d0)) { lo = c; swap = true; }
+    }
+    for (int k = 0; k < 3; k++) {
+      const LSPoint& c = cand_hi[k];
+      if (c.d0 >= 0 && (hi.d0 < 0 || c.d0 < hi.d0)) { hi = c; swap = true; }
+    }
     it++;
   }
   bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
