@@ -4,8 +4,9 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--envs-per-gpu E] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one env.step over the whole batch = one ``oduck_step`` launch: action delay / push / motor-target logic,
-10 x (forward dynamics + contact solve + Euler), obs (101 + 212), 7 reward terms, episode + auto-reset bookkeeping.
+One "step" = one rollout step over the whole batch = ``oduck_policy_forward`` (actor MLP + NormalTanh sampling) followed by one
+``oduck_step`` launch: action delay / push / motor-target logic, 10 x (forward dynamics + contact solve + Euler), obs (101 + 212),
+7 reward terms, episode + auto-reset bookkeeping.
 Workload at N = 1: BASELINE.json configs[1] -- ``flat_terrain_backlash`` (the task the metric names), 4096 envs per GPU,
 domain randomisation on, no PPO update.  Envs are independent, so ranks take disjoint env shards (weak scaling: per-GPU
 work fixed) and there is no data-path collective in this config.
@@ -115,6 +116,40 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def run_ppo(args, rank, world, dev):
+    """BASELINE configs[2]: full PPO (8192 envs x unroll 20 per training step), timed end to end with the rollout / gather / update split."""
+    import torch
+    import torch.distributed as dist
+    from open_duck_playground_b200 import ppo
+    from open_duck_playground_b200.joystick import Joystick
+    n_total = 8192 if args.envs_per_gpu == 4096 else args.envs_per_gpu * world
+    cfg = ppo.PPOConfig(num_envs=n_total)
+    tr = ppo.PPOTrainer(Joystick(TASK, device=dev), cfg, rank=rank, world=world)
+    for _ in range(max(1, min(args.warmup, 3))):
+        tr.training_step()
+    steps = max(1, args.steps // 20)
+    split = {"rollout_ms": 0.0, "gather_ms": 0.0, "update_ms": 0.0}
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tr.training_step()
+        for k in split:
+            split[k] += tr.timing[k]
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dt = time.perf_counter() - t0
+    if rank == 0:
+        print(json.dumps({"metric": "env-steps/sec (full PPO: rollout + gather + update)", "value": steps * cfg.num_envs * cfg.unroll_length / dt, "unit": "env-steps/s",
+                          "n_gpus": world, "steps": steps, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "strong", "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": f"{TASK} full PPO, {cfg.num_envs} envs x unroll {cfg.unroll_length}, 4 epochs x 32 minibatches (BASELINE configs[2])"},
+                          "split_ms_per_training_step": {k: v / steps for k, v in split.items()}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -123,6 +158,7 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=4096)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="rollout", choices=["rollout", "ppo"], help="ppo = BASELINE configs[2]: full PPO training steps (rollout / gather / update split)")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
@@ -141,6 +177,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n = args.envs_per_gpu
+    if args.mode == "ppo":
+        return run_ppo(args, rank, world, dev)
     # env sets rotated so that the working set exceeds L2 (timing rule: inputs larger than L2)
     n_sets = max(3, int(np.ceil(1.3 * L2_BYTES / (n * STATE_BYTES_PER_ENV))))
     # per-rank keys: split(seed, world*n) then sliced, so results do not depend on the GPU count
@@ -152,12 +190,17 @@ def main():
         e.randomize(all_dr[sl])
         states.append(e.reset(jr.split(jr.PRNGKey(100 + s), world * n)[sl]))
         envs.append(e)
-    gen = torch.Generator(device=dev).manual_seed(1 + rank)
-    n_act = 8
-    acts = [torch.rand(n, 14, device=dev, generator=gen) * 2 - 1 for _ in range(n_act)]       # resident in HBM
-    host_acts = [a.cpu().pin_memory() for a in acts]
+    # rollout step = actor-MLP forward (A15, random-init weights of the reference architecture 101-512-256-128-28) + env.step
+    from open_duck_playground_b200 import ppo
+    torch.manual_seed(0)
+    policy = ppo.MLP([101, 512, 256, 128, 28]).to(dev)
+    weights = ppo.PolicyWeights(policy, 101, dev)
+    n_keys = 8
+    keys = [torch.from_numpy(jr.split(jr.PRNGKey(1000 + k), world * n)[rank * n:(rank + 1) * n].view(np.int32).copy()).to(dev) for k in range(n_keys)]   # resident in HBM
+    host_keys = [k.cpu().pin_memory() for k in keys]
     host_obs = torch.empty(n, 101).pin_memory()
-    host_rd = torch.empty(2, n).pin_memory()
+    host_out = torch.empty(n, 14 + 3).pin_memory()
+    dev_out = torch.empty(n, 14 + 3, device=dev)
 
     def barrier():
         if world > 1:
@@ -165,16 +208,19 @@ def main():
         torch.cuda.synchronize()
 
     def step_resident(k):
-        envs[k % n_sets].step(None, acts[k % n_act])
+        e = envs[k % n_sets]
+        act, raw, logp = ppo.policy_forward(e, weights, keys[k % n_keys], deterministic=False)
+        e.step(None, act)
 
     def step_e2e(k):
         e = envs[k % n_sets]
-        a = host_acts[k % n_act].to(dev, non_blocking=True)
-        st = e.step(None, a)
-        host_obs.copy_(st.obs["state"], non_blocking=True)
-        host_rd[0].copy_(st.reward, non_blocking=True)
-        host_rd[1].copy_(st.done, non_blocking=True)
-        torch.cuda.current_stream().synchronize()            # the host consumes the result every step
+        kd = host_keys[k % n_keys].to(dev, non_blocking=True)           # H2D: this step's sampling keys
+        act, raw, logp = ppo.policy_forward(e, weights, kd, deterministic=False)
+        st = e.step(None, act)
+        dev_out[:, :14] = raw; dev_out[:, 14] = logp; dev_out[:, 15] = st.reward; dev_out[:, 16] = st.done
+        host_obs.copy_(st.obs["state"], non_blocking=True)              # D2H: what a host-side learner stores per transition
+        host_out.copy_(dev_out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()                       # the host consumes the result every step
 
     def timed(fn, steps):
         barrier()
@@ -218,15 +264,15 @@ def main():
             "metric": "env-steps/sec (batched physics+rollout)", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"{TASK} joystick env.step (10 substeps + obs/reward/auto-reset), {n} envs per GPU, domain randomisation on, no PPO update (BASELINE configs[1])",
+            "config": {"workload": f"{TASK} joystick rollout step = actor-MLP forward + env.step (10 substeps + obs/reward/auto-reset), {n} envs per GPU, domain randomisation on, no PPO update (BASELINE configs[1])",
                        "task": TASK, "envs_per_gpu": n, "global_envs": world * n, "substeps_per_step": 10, "parallelism": f"env-shard x{world}",
                        "l2": f"{n_sets} env sets rotated, {n_sets * n * STATE_BYTES_PER_ENV / 1e6:.0f} MB working set > L2"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
                          "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6.65 TB/s",
                          "note": "the path is fp32-latency/compute bound (~300-400 FLOP/B), so the HBM fraction is small by construction; see fp32_frac",
                          "fp32_frac": FLOP_PER_ENV_STEP * value / world / fp32_peak, "algorithmic_bytes_per_env_step": BYTES_PER_ENV_STEP,
-                         "kernel": "k_step", "kernel_ms": ms_step},
-            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": n * 14 * 4, "d2h_bytes_per_step": n * (101 + 2) * 4, "steps": e2e_steps},
+                         "kernel": "k_step", "kernel_ms": ms_step, "kernel_ms_note": "rollout step = k_policy + k_step; k_step is the dominant kernel (share in profiles/)"},
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": n * 2 * 4, "d2h_bytes_per_step": n * (101 + 17) * 4, "steps": e2e_steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "physics_substeps_per_s": value * 10,

@@ -16,38 +16,15 @@
 #define WPB 8   // warps (= envs in flight) per CTA
 
 static thread_local std::string g_err;
-static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int oduck_fail(int code, const std::string& msg) { g_err = msg; return code; }   // shared with oduck_policy.cu
+static int fail(int code, const std::string& msg) { return oduck_fail(code, msg); }
 #define CUDA_TRY(x)                                                                                   \
   do {                                                                                                \
     cudaError_t e_ = (x);                                                                             \
     if (e_ != cudaSuccess) return fail(ODUCK_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); \
   } while (0)
 
-struct Params {
-  const DevModel* model;
-  const DevEnvCfg* cfg;
-  const float* poly;
-  float *phys, *dr, *out, *info, *obs_state, *obs_priv, *reward, *done, *trunc, *metrics;
-  float *first_phys, *first_obs_state, *first_obs_priv, *dbg;
-  const float* action;     // step: [N, nu];  physics: ctrl [N, nu] or null
-  const uint32_t* keys;
-  const uint8_t* mask;
-  int N, nsub, integrate;
-};
-
-struct OduckHandle {
-  int n, device;
-  OduckModel hm;
-  OduckEnvConfig hcfg;
-  DevModel hdm;
-  DevEnvCfg hdc;
-  DevModel* dmodel;
-  DevEnvCfg* dcfg;
-  float* poly;
-  float *phys, *dr, *out, *info, *obs_state, *obs_priv, *reward, *done, *trunc, *metrics, *first_phys, *first_obs_state, *first_obs_priv, *dbg;
-  int nefc, smem_bytes, grid;
-  int64_t launches;
-};
+#include "oduck_handle.cuh"
 
 // ------------------------------------------------------------------------------------------------- device helpers
 __device__ __forceinline__ size_t smem_model_bytes() { return (sizeof(DevModel) + 15) & ~(size_t)15; }
@@ -799,12 +776,6 @@ int oduck_set_state(OduckHandle* h, const float* qpos, const float* qvel, const 
   if (qvel) CUDA_TRY(cudaMemcpy2DAsync(h->phys + PHYS_QVEL, pitch, qvel, h->hm.nv * sizeof(float), h->hm.nv * sizeof(float), N, cudaMemcpyDeviceToDevice, st));
   if (qacc_warm) CUDA_TRY(cudaMemcpy2DAsync(h->phys + PHYS_QACCW, pitch, qacc_warm, h->hm.nv * sizeof(float), h->hm.nv * sizeof(float), N, cudaMemcpyDeviceToDevice, st));
   return ODUCK_OK;
-}
-
-int oduck_policy_forward(OduckHandle* h, const OduckPolicyWeights* w, const float* obs, const uint32_t* keys, int deterministic,
-                         float* action, float* raw_action, float* log_prob, void* stream) {
-  (void)h; (void)w; (void)obs; (void)keys; (void)deterministic; (void)action; (void)raw_action; (void)log_prob; (void)stream;
-  return fail(ODUCK_ERR_UNSUPPORTED, "oduck_policy_forward: actor-MLP kernel not built yet");
 }
 
 int oduck_get_buffer(OduckHandle* h, int id, void** ptr, int64_t* shape, int64_t* strides, int* dtype) {

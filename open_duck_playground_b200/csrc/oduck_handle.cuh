@@ -1,0 +1,33 @@
+// oduck_handle.cuh -- host-side handle shared by the translation units of liboduck_cuda.so
+#pragma once
+#include <stdint.h>
+
+#include "../../include/oduck.h"
+#include "oduck_env.cuh"
+
+struct Params {
+  const DevModel* model;
+  const DevEnvCfg* cfg;
+  const float* poly;
+  float *phys, *dr, *out, *info, *obs_state, *obs_priv, *reward, *done, *trunc, *metrics;
+  float *first_phys, *first_obs_state, *first_obs_priv, *dbg;
+  const float* action;     // step: [N, nu];  physics: ctrl [N, nu] or null
+  const uint32_t* keys;
+  const uint8_t* mask;
+  int N, nsub, integrate;
+};
+
+struct OduckHandle {
+  int n, device;
+  OduckModel hm;
+  OduckEnvConfig hcfg;
+  DevModel hdm;
+  DevEnvCfg hdc;
+  DevModel* dmodel;
+  DevEnvCfg* dcfg;
+  float* poly;
+  float *phys, *dr, *out, *info, *obs_state, *obs_priv, *reward, *done, *trunc, *metrics, *first_phys, *first_obs_state, *first_obs_priv, *dbg;
+  int nefc, smem_bytes, grid;
+  int64_t launches;
+};
+

@@ -1,0 +1,303 @@
+"""PPO rollout + update around the fused env step (reference: Brax ``ppo.train`` as driven by common/runner.py:86-118).
+
+The hot path -- policy forward (``oduck_policy_forward``) and ``env.step`` -- runs in the CUDA library; the update (GAE,
+clipped surrogate, Adam, observation normaliser) is host-orchestrated PyTorch like the reference's is host-orchestrated
+JAX.  Hyper-parameters default to ``locomotion_params.brax_ppo_config("BerkeleyHumanoidJoystickFlatTerrain")`` -- the table
+the reference looks up at common/runner.py:87-89 (values: SURVEY.md 3.1).
+
+Multi-GPU: ranks own disjoint env shards; one ``all_gather`` of the rollout per training step over NCCL,
+then a replicated (bit-identical) update.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import Callable, Dict, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import capi, rng as jr
+
+
+@dataclass
+class PPOConfig:
+    num_timesteps: int = 150_000_000
+    num_envs: int = 8192
+    unroll_length: int = 20
+    batch_size: int = 256
+    num_minibatches: int = 32
+    num_updates_per_batch: int = 4
+    discounting: float = 0.97
+    gae_lambda: float = 0.95
+    learning_rate: float = 3e-4
+    entropy_cost: float = 0.005
+    clipping_epsilon: float = 0.2
+    max_grad_norm: float = 1.0
+    reward_scaling: float = 1.0
+    normalize_observations: bool = True
+    episode_length: int = 1000
+    num_evals: int = 15
+    policy_hidden_layer_sizes: Tuple[int, ...] = (512, 256, 128)
+    value_hidden_layer_sizes: Tuple[int, ...] = (512, 256, 128)
+    policy_obs_key: str = "state"
+    value_obs_key: str = "privileged_state"
+    seed: int = 0
+
+
+class MLP(torch.nn.Module):
+    """flax ``MLP``: Dense layers with swish, lecun_uniform kernels, zero biases, no final activation."""
+
+    def __init__(self, sizes):
+        super().__init__()
+        self.layers = torch.nn.ModuleList(torch.nn.Linear(a, b) for a, b in zip(sizes[:-1], sizes[1:]))
+        for lin in self.layers:
+            bound = math.sqrt(3.0 / lin.in_features)
+            torch.nn.init.uniform_(lin.weight, -bound, bound)
+            torch.nn.init.zeros_(lin.bias)
+
+    def forward(self, x):
+        for i, lin in enumerate(self.layers):
+            x = lin(x)
+            if i + 1 < len(self.layers):
+                x = torch.nn.functional.silu(x)
+        return x
+
+
+class RunningStats:
+    """brax.training.acme.running_statistics: Welford mean/std per feature (std clipped to [1e-6, 1e6])."""
+
+    def __init__(self, dim, device):
+        self.count = torch.zeros((), device=device, dtype=torch.float64)
+        self.mean = torch.zeros(dim, device=device, dtype=torch.float64)
+        self.m2 = torch.zeros(dim, device=device, dtype=torch.float64)
+        self.std = torch.ones(dim, device=device)
+
+    def update(self, batch: torch.Tensor) -> None:
+        b = batch.reshape(-1, batch.shape[-1]).double()
+        n = b.shape[0]
+        new_count = self.count + n
+        delta = b.mean(0) - self.mean
+        self.m2 += ((b - b.mean(0)) ** 2).sum(0) + delta ** 2 * self.count * n / new_count
+        self.mean += delta * n / new_count
+        self.count = new_count
+        self.std = torch.sqrt(self.m2 / self.count).clamp(1e-6, 1e6).float()
+
+    @property
+    def mean32(self):
+        return self.mean.float()
+
+
+class PolicyWeights:
+    """Packs a policy MLP + normaliser into ``OduckPolicyWeights`` (row-major [in][out] kernels like flax)."""
+
+    def __init__(self, policy: MLP, obs_dim: int, device):
+        self.policy, self.device = policy, device
+        self.struct = capi.OduckPolicyWeights()
+        self.struct.obs_dim = obs_dim
+        hs = [l.out_features for l in policy.layers]
+        for i in range(3):
+            self.struct.hidden[i] = hs[i]
+        self.struct.out_dim = hs[3]
+        self.refresh(torch.zeros(obs_dim, device=device), torch.ones(obs_dim, device=device))
+
+    @torch.no_grad()
+    def refresh(self, mean: torch.Tensor, std: torch.Tensor) -> None:
+        self.mean, self.std = mean.float().contiguous(), std.float().contiguous()
+        self.w = [l.weight.detach().t().contiguous() for l in self.policy.layers]     # [in][out]
+        self.b = [l.bias.detach().contiguous() for l in self.policy.layers]
+        self.struct.obs_mean, self.struct.obs_std = self.mean.data_ptr(), self.std.data_ptr()
+        for i in range(4):
+            self.struct.w[i], self.struct.b[i] = self.w[i].data_ptr(), self.b[i].data_ptr()
+
+
+def policy_forward(env, weights: PolicyWeights, keys: Optional[torch.Tensor], deterministic: bool, obs: Optional[torch.Tensor] = None):
+    """A15 through the C-ABI.  Returns (action, raw_action, log_prob) tensors on the env's device."""
+    n, na = env.handle.n, env.action_size
+    dev = env.device
+    act = torch.empty(n, na, device=dev)
+    raw = torch.empty(n, na, device=dev)
+    logp = torch.empty(n, device=dev)
+    kp = 0 if keys is None else env._ptr(keys, torch.int32, (n, 2))
+    op = 0 if obs is None else env._ptr(obs, torch.float32, (n, weights.struct.obs_dim))
+    env.handle.policy_forward(weights.struct, op, kp, deterministic, act.data_ptr(), raw.data_ptr(), logp.data_ptr(), env._stream())
+    return act, raw, logp
+
+
+def torch_policy_logprob(policy: MLP, obs_n: torch.Tensor, raw: torch.Tensor):
+    """log-prob / entropy of ``raw`` (pre-tanh) under NormalTanh(policy(obs)) -- the differentiable twin of the kernel's head."""
+    out = policy(obs_n)
+    loc, sp = out.chunk(2, dim=-1)
+    scale = torch.nn.functional.softplus(sp) + 0.001
+    z = (raw - loc) / scale
+    logn = -0.5 * z * z - torch.log(scale) - 0.5 * math.log(2 * math.pi)
+    ldj = 2.0 * (math.log(2.0) - raw - torch.nn.functional.softplus(-2.0 * raw))
+    logp = (logn - ldj).sum(-1)
+    # Brax entropy: normal entropy + E[log det jacobian] estimated at a fresh sample
+    sample = loc + scale * torch.randn_like(loc)
+    ent = (0.5 + 0.5 * math.log(2 * math.pi) + torch.log(scale) + 2.0 * (math.log(2.0) - sample - torch.nn.functional.softplus(-2.0 * sample))).sum(-1)
+    return logp, ent
+
+
+def compute_gae(truncation, termination, rewards, values, bootstrap_value, lambda_, discount):
+    """brax ppo losses.compute_gae; inputs [T, N]."""
+    mask = 1.0 - truncation
+    values_tp1 = torch.cat([values[1:], bootstrap_value[None]], 0)
+    deltas = (rewards + discount * (1 - termination) * values_tp1 - values) * mask
+    acc = torch.zeros_like(bootstrap_value)
+    vs_minus = []
+    for t in reversed(range(rewards.shape[0])):
+        acc = deltas[t] + discount * (1 - termination[t]) * mask[t] * lambda_ * acc
+        vs_minus.append(acc)
+    vs_minus = torch.stack(vs_minus[::-1], 0)
+    vs = vs_minus + values
+    vs_tp1 = torch.cat([vs[1:], bootstrap_value[None]], 0)
+    adv = (rewards + discount * (1 - termination) * vs_tp1 - values) * mask
+    return vs.detach(), adv.detach()
+
+
+def shard_keys(seed: int, world: int, rank: int, n_per_rank: int) -> np.ndarray:
+    """Per-env keys independent of the GPU count: split(seed, world * n) sliced per rank."""
+    return jr.split(jr.PRNGKey(seed), world * n_per_rank)[rank * n_per_rank:(rank + 1) * n_per_rank]
+
+
+def all_gather_rollout(batch: Dict[str, torch.Tensor], world: int) -> Dict[str, torch.Tensor]:
+    """The one exchange of a training step: every rank contributes its env shard ([T, n, ...] -> [T, world * n, ...])."""
+    if world == 1:
+        return batch
+    out = {}
+    for k, v in batch.items():
+        v = v.contiguous()
+        parts = [torch.empty_like(v) for _ in range(world)]
+        dist.all_gather(parts, v)
+        out[k] = torch.cat(parts, dim=1)
+    return out
+
+
+class PPOTrainer:
+    def __init__(self, env, cfg: PPOConfig, rank: int = 0, world: int = 1, progress_fn: Optional[Callable] = None,
+                 policy_params_fn: Optional[Callable] = None):
+        self.env, self.cfg, self.rank, self.world = env, cfg, rank, world
+        self.progress_fn, self.policy_params_fn = progress_fn, policy_params_fn
+        self.n_local = cfg.num_envs // world
+        dev = env.device
+        torch.manual_seed(cfg.seed)                                     # identical initial weights on every rank
+        na = env.action_size
+        self.policy = MLP([env.observation_size[cfg.policy_obs_key][0], *cfg.policy_hidden_layer_sizes, 2 * na]).to(dev)
+        self.value = MLP([env.observation_size[cfg.value_obs_key][0], *cfg.value_hidden_layer_sizes, 1]).to(dev)
+        self.opt = torch.optim.Adam(list(self.policy.parameters()) + list(self.value.parameters()), lr=cfg.learning_rate)
+        self.stats = {k: RunningStats(env.observation_size[k][0], dev) for k in (cfg.policy_obs_key, cfg.value_obs_key)}
+        self.weights = PolicyWeights(self.policy, env.observation_size[cfg.policy_obs_key][0], dev)
+        self.key = jr.PRNGKey(cfg.seed + 17)
+        self.env_steps = 0
+        env.randomize(shard_keys(cfg.seed + 1, world, rank, self.n_local))
+        self.state = env.reset(shard_keys(cfg.seed, world, rank, self.n_local))
+        self.timing = {"rollout_ms": 0.0, "gather_ms": 0.0, "update_ms": 0.0}
+
+    # ------------------------------------------------------------------ A17: unroll
+    def rollout(self) -> Dict[str, torch.Tensor]:
+        cfg, env = self.cfg, self.env
+        T, n = cfg.unroll_length, self.n_local
+        dev = env.device
+        pk, vk = cfg.policy_obs_key, cfg.value_obs_key
+        buf = {"obs_p": torch.empty(T + 1, n, env.observation_size[pk][0], device=dev), "obs_v": torch.empty(T + 1, n, env.observation_size[vk][0], device=dev),
+               "raw": torch.empty(T, n, env.action_size, device=dev), "logp": torch.empty(T, n, device=dev), "reward": torch.empty(T, n, device=dev),
+               "done": torch.empty(T, n, device=dev), "trunc": torch.empty(T, n, device=dev)}
+        st = self.state
+        mean, std = (self.stats[pk].mean32, self.stats[pk].std) if cfg.normalize_observations else (torch.zeros_like(self.stats[pk].std), torch.ones_like(self.stats[pk].std))
+        self.weights.refresh(mean, std)
+        self.key, sub = jr.split(self.key, 2)
+        step_keys = jr.split(sub, T)
+        for t in range(T):
+            buf["obs_p"][t].copy_(st.obs[pk]); buf["obs_v"][t].copy_(st.obs[vk])
+            keys = jr.split(step_keys[t], self.world * n)[self.rank * n:(self.rank + 1) * n]
+            act, raw, logp = policy_forward(env, self.weights, torch.from_numpy(keys.view(np.int32)), deterministic=False)
+            st = env.step(st, act)
+            buf["raw"][t].copy_(raw); buf["logp"][t].copy_(logp)
+            buf["reward"][t].copy_(st.reward); buf["done"][t].copy_(st.done); buf["trunc"][t].copy_(st.info["truncation"])
+        buf["obs_p"][T].copy_(st.obs[pk]); buf["obs_v"][T].copy_(st.obs[vk])
+        self.state = st
+        return buf
+
+    # ------------------------------------------------------------------ update (replicated on every rank)
+    def update(self, batch: Dict[str, torch.Tensor]) -> Dict[str, float]:
+        cfg = self.cfg
+        pk, vk = cfg.policy_obs_key, cfg.value_obs_key
+        if cfg.normalize_observations:
+            self.stats[pk].update(batch["obs_p"][:-1]); self.stats[vk].update(batch["obs_v"][:-1])
+        norm = (lambda x, k: (x - self.stats[k].mean32) / self.stats[k].std) if cfg.normalize_observations else (lambda x, k: x)
+        T, N = batch["reward"].shape
+        gen = torch.Generator(device="cpu").manual_seed(cfg.seed + self.env_steps)       # same permutation on every rank
+        metrics = {}
+        mb = N // cfg.num_minibatches
+        for _ in range(cfg.num_updates_per_batch):
+            perm = torch.randperm(N, generator=gen).to(batch["reward"].device)
+            for i in range(cfg.num_minibatches):
+                idx = perm[i * mb:(i + 1) * mb]
+                obs_p, obs_v = norm(batch["obs_p"][:, idx], pk), norm(batch["obs_v"][:, idx], vk)
+                values = self.value(obs_v).squeeze(-1)
+                baseline, bootstrap = values[:-1], values[-1]
+                trunc, done = batch["trunc"][:, idx], batch["done"][:, idx]
+                termination = done * (1 - trunc)
+                rewards = batch["reward"][:, idx] * cfg.reward_scaling
+                vs, adv = compute_gae(trunc, termination, rewards, baseline.detach(), bootstrap.detach(), cfg.gae_lambda, cfg.discounting)
+                adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+                logp, ent = torch_policy_logprob(self.policy, obs_p[:-1], batch["raw"][:, idx])
+                rho = torch.exp(logp - batch["logp"][:, idx])
+                policy_loss = -torch.min(rho * adv, rho.clamp(1 - cfg.clipping_epsilon, 1 + cfg.clipping_epsilon) * adv).mean()
+                v_loss = ((vs - baseline) ** 2).mean() * 0.5 * 0.5
+                ent_loss = -cfg.entropy_cost * ent.mean()
+                loss = policy_loss + v_loss + ent_loss
+                self.opt.zero_grad(set_to_none=True)
+                loss.backward()
+                torch.nn.utils.clip_grad_norm_(list(self.policy.parameters()) + list(self.value.parameters()), cfg.max_grad_norm)
+                self.opt.step()
+        metrics.update(loss=float(loss), policy_loss=float(policy_loss), v_loss=float(v_loss), entropy=float(ent.mean()))
+        return metrics
+
+    def training_step(self) -> Dict[str, float]:
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if self.env.device.type == "cuda" else None
+        if ev: ev[0].record()
+        local = self.rollout()
+        if ev: ev[1].record()
+        batch = all_gather_rollout(local, self.world)
+        if ev: ev[2].record()
+        m = self.update(batch)
+        if ev:
+            ev[3].record(); torch.cuda.synchronize()
+            self.timing = {"rollout_ms": ev[0].elapsed_time(ev[1]), "gather_ms": ev[1].elapsed_time(ev[2]), "update_ms": ev[2].elapsed_time(ev[3])}
+        self.env_steps += self.cfg.num_envs * self.cfg.unroll_length
+        m["reward_per_step"] = float(batch["reward"].mean())
+        m["episode_done_rate"] = float(batch["done"].mean())
+        return m
+
+    def train(self):
+        cfg = self.cfg
+        n_steps = max(1, cfg.num_timesteps // (cfg.num_envs * cfg.unroll_length))
+        eval_every = max(1, n_steps // max(1, cfg.num_evals))
+        for it in range(n_steps):
+            m = self.training_step()
+            if self.rank == 0 and (it % eval_every == 0 or it == n_steps - 1):
+                metrics = {"eval/episode_reward": m["reward_per_step"] * cfg.episode_length, "eval/episode_reward_std": 0.0, **{f"training/{k}": v for k, v in m.items()},
+                           **{f"time/{k}": v for k, v in self.timing.items()}}
+                if self.progress_fn:
+                    self.progress_fn(self.env_steps, metrics)
+                if self.policy_params_fn:
+                    self.policy_params_fn(self.env_steps, None, self.params())
+        return self.params()
+
+    def params(self):
+        pk = self.cfg.policy_obs_key
+        return {"normalizer": {k: {"mean": s.mean32.cpu(), "std": s.std.cpu(), "count": float(s.count)} for k, s in self.stats.items()},
+                "policy": {k: v.cpu() for k, v in self.policy.state_dict().items()}, "value": {k: v.cpu() for k, v in self.value.state_dict().items()},
+                "optimizer": self.opt.state_dict(), "env_steps": self.env_steps, "policy_obs_key": pk}
+
+    def load(self, params) -> None:
+        self.policy.load_state_dict(params["policy"]); self.value.load_state_dict(params["value"]); self.opt.load_state_dict(params["optimizer"])
+        for k, s in self.stats.items():
+            d = params["normalizer"][k]
+            s.mean = d["mean"].double().to(self.env.device); s.std = d["std"].to(self.env.device); s.count = torch.tensor(d["count"], dtype=torch.float64, device=self.env.device)
+            s.m2 = (s.std.double() ** 2) * s.count
+        self.env_steps = int(params["env_steps"])

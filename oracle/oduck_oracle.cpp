@@ -1339,10 +1339,23 @@ int oduck_policy_forward(OduckHandle* h, const OduckPolicyWeights* w, const floa
       real loc = x[a], scale = std::log1p(std::exp(x[na + a])) + (real)0.001;  // softplus + min_std
       real raw = loc;
       if (!deterministic) {
-        // standard normal from two uniforms of the per-env key (Box-Muller); the reference draws jax.random.normal
+        // jax.random.normal: sqrt(2) * erf_inv(uniform(-1 + ulp, 1)); erf_inv = the f32 polynomial XLA uses (M. Giles)
         Key k = Key{keys[2 * i], keys[2 * i + 1]};
-        real u1 = std::max(bits_to_unit(key_bits(k, 2 * a)), (real)1e-7), u2 = bits_to_unit(key_bits(k, 2 * a + 1));
-        real z = std::sqrt(-2 * std::log(u1)) * std::cos(2 * (real)3.14159265358979323846 * u2);
+        const real lo = (real)-0.99999994f;
+        real u = std::max(lo, bits_to_unit(key_bits(k, a)) * (1 - lo) + lo);
+        real w2 = -std::log((1 - u) * (1 + u)), pp;
+        if (w2 < 5) {
+          w2 -= (real)2.5;
+          pp = (real)2.81022636e-08; pp = (real)3.43273939e-07 + pp * w2; pp = (real)-3.5233877e-06 + pp * w2; pp = (real)-4.39150654e-06 + pp * w2;
+          pp = (real)0.00021858087 + pp * w2; pp = (real)-0.00125372503 + pp * w2; pp = (real)-0.00417768164 + pp * w2; pp = (real)0.246640727 + pp * w2;
+          pp = (real)1.50140941 + pp * w2;
+        } else {
+          w2 = std::sqrt(w2) - 3;
+          pp = (real)-0.000200214257; pp = (real)0.000100950558 + pp * w2; pp = (real)0.00134934322 + pp * w2; pp = (real)-0.00367342844 + pp * w2;
+          pp = (real)0.00573950773 + pp * w2; pp = (real)-0.0076224613 + pp * w2; pp = (real)0.00943887047 + pp * w2; pp = (real)1.00167406 + pp * w2;
+          pp = (real)2.83297682 + pp * w2;
+        }
+        real z = (real)1.41421356237 * pp * u;
         raw = loc + scale * z;
         real lpn = -(real)0.5 * z * z - std::log(scale) - (real)0.5 * std::log(2 * (real)3.14159265358979323846);
         real ldj = 2 * (std::log((real)2) - raw - std::log1p(std::exp(-2 * raw)));

@@ -228,6 +228,44 @@ def test_autoreset_truncation_and_full_size_invariants(oracle):
     assert int(gpu.handle.launch_count()) == 2 + 4          # randomize + reset + 4 fused steps: one launch per env.step
 
 
+def test_policy_forward_parity(oracle):
+    """A15: CUDA actor-MLP kernel vs the oracle's fp64 MLP and vs the torch module the PPO update differentiates."""
+    from open_duck_playground_b200 import ppo
+    n = 300                                              # not a multiple of the 16-env tile
+    gpu, ref, sg, sr = _pair(oracle, "flat_terrain_backlash", n)
+    torch.manual_seed(0)
+    pol = ppo.MLP([101, 512, 256, 128, 28])
+    mean, std = torch.randn(101) * 0.1, torch.rand(101) + 0.5
+    wr = ppo.PolicyWeights(pol, 101, ref.device); wr.refresh(mean, std)
+    polg = ppo.MLP([101, 512, 256, 128, 28]).cuda(); polg.load_state_dict(pol.state_dict())
+    wg = ppo.PolicyWeights(polg, 101, gpu.device); wg.refresh(mean.cuda(), std.cuda())
+    obs = sr.obs["state"].float()
+    keys = torch.from_numpy(jr.split(jr.PRNGKey(9), n).view(np.int32))
+    c = Checks()
+    ag, rg, lg = ppo.policy_forward(gpu, wg, None, True, obs=obs.cuda())
+    ar, rr, lr = ppo.policy_forward(ref, wr, None, True, obs=obs)
+    c.close(ag, ar, 2e-4, what="deterministic action")
+    ag, rg, lg = ppo.policy_forward(gpu, wg, keys, False, obs=obs.cuda())
+    ar, rr, lr = ppo.policy_forward(ref, wr, keys, False, obs=obs)
+    c.close(rg, rr, 1e-3, 1e-3, what="raw action")
+    c.close(ag, ar, 1e-3, what="action")
+    c.close(lg[:, None], lr[:, None], 5e-3, 1e-3, what="log-prob")
+    lp_t, _ = ppo.torch_policy_logprob(polg, (obs.cuda() - mean.cuda()) / std.cuda(), rg)
+    c.close(lg[:, None], lp_t.detach()[:, None], 5e-3, 1e-3, what="log-prob vs torch twin")
+    c.done()
+
+
+def test_ppo_training_step_on_gpu():
+    from open_duck_playground_b200 import ppo
+    env = Joystick("flat_terrain_backlash", device="cuda:0")
+    cfg = ppo.PPOConfig(num_envs=512, unroll_length=5, num_minibatches=4, num_updates_per_batch=2)
+    tr = ppo.PPOTrainer(env, cfg)
+    m1 = tr.training_step()
+    m2 = tr.training_step()
+    assert np.isfinite(m1["loss"]) and np.isfinite(m2["loss"]) and tr.env_steps == 2 * 512 * 5
+    assert tr.timing["rollout_ms"] > 0 and tr.timing["update_ms"] > 0
+
+
 def test_library_is_the_cuda_one():
     from open_duck_playground_b200 import capi
     lib = capi.load_cuda_library()
