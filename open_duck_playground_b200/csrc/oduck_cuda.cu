@@ -647,7 +647,7 @@ int oduck_destroy(OduckHandle* h) {
   if (!h) return ODUCK_OK;
   cudaSetDevice(h->device);
   void* ptrs[] = {h->dmodel, h->dcfg, h->poly, h->phys, h->dr, h->out, h->info, h->obs_state, h->obs_priv, h->reward, h->done, h->trunc,
-                  h->metrics, h->first_phys, h->first_obs_state, h->first_obs_priv, h->dbg};
+                  h->metrics, h->first_phys, h->first_obs_state, h->first_obs_priv, h->dbg, h->policy_scratch};
   for (void* q : ptrs) if (q) cudaFree(q);
   delete h;
   return ODUCK_OK;

@@ -29,5 +29,8 @@ struct OduckHandle {
   float *phys, *dr, *out, *info, *obs_state, *obs_priv, *reward, *done, *trunc, *metrics, *first_phys, *first_obs_state, *first_obs_priv, *dbg;
   int nefc, smem_bytes, grid;
   int64_t launches;
+  float* policy_scratch;          // hidden activations of the actor MLP (tensor-core path)
+  size_t policy_scratch_floats;
+  const float* policy_packed_for;  // w[0] pointer the packed weight copy was made from
 };
 
