@@ -550,6 +550,20 @@ static int build_dev_model(const OduckModel& M, DevModel& D, std::string& err) {
   }
   for (int a = 0, p = 0; a < 32 && p < 512; a++)
     for (int b = 0; b <= a && p < 512; b++, p++) D.pair_ab[p] = (unsigned short)((a << 8) | b);
+  {
+    int cnt = 0;
+    for (int k = 0; k < M.nv; k++) {
+      D.chol_ofs[k] = cnt;
+      const int dd = D.d_depth[k], rk = k * (k + 1) / 2;
+      for (int a = 0; a < dd; a++)
+        for (int b = 0; b <= a; b++) {
+          const int ia = D.anc[k][a], ib = D.anc[k][b];
+          if (cnt >= 1536) { err = "factorisation table overflow"; return -1; }
+          D.chol_tab[cnt++] = (unsigned)(ia * (ia + 1) / 2 + ib) | ((unsigned)(rk + ia) << 10) | ((unsigned)(rk + ib) << 20);
+        }
+    }
+    for (int k = M.nv; k <= 32; k++) D.chol_ofs[k] = cnt;
+  }
   D.n_mpairs = 0;
   for (int i = 0; i < M.nv; i++)
     for (int j = i; j >= 0; j = M.dof_parentid[j]) D.mpair[D.n_mpairs++] = (unsigned short)((i << 8) | j);

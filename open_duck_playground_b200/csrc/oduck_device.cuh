@@ -74,6 +74,8 @@ struct DevModel {
   int d_depth[NLANE];
   int max_dof_depth;
   unsigned short pair_ab[512];   // p -> (a << 8 | b), b <= a, p = a (a + 1) / 2 + b
+  unsigned int chol_tab[1536];    // per pivot k, per ancestor pair: target | src_a << 10 | src_b << 20 (offsets into the packed triangle)
+  int chol_ofs[NLANE + 1];
   unsigned short mpair[512];     // structural non-zeros of M: (i << 8 | j), j an ancestor of i or i itself
   int n_mpairs, body_rounds;
   int b_sameaxis[NLANE];
@@ -208,7 +210,7 @@ __device__ __forceinline__ S6 inert_mul(const I10& I, S6 v) {  // mju_mulInertVe
 // rhs <- L^-T rhs.  For pivot k only rows/columns in S(k) are touched, S(k) = dof ancestors of k (tree == true: exact for
 // the sparsity of a kinematic tree, no fill-in) or all j < k (dense fallback).  The |S|(|S|+1)/2 rank-1 updates of one
 // pivot are independent, so they are spread over the warp 32 at a time (pair table), instead of one ancestor row per step.
-__device__ __forceinline__ void chol_rev(const DevModel& m, float* A, float* rhs, int n, int lane, bool tree) {
+static __device__ __noinline__ void chol_rev(const DevModel& m, float* A, float* rhs, int n, int lane, bool tree) {
   for (int k = n - 1; k >= 0; --k) {
     const int rk = TRI(k);
     const int d = tree ? m.d_depth[k] : k;
@@ -228,19 +230,26 @@ __device__ __forceinline__ void chol_rev(const DevModel& m, float* A, float* rhs
       rhs[k] = yk;
     }
     __syncwarp();
-    const int npairs = (d * (d + 1)) >> 1;
-    for (int p = lane; p < npairs; p += 32) {
-      const unsigned ab = m.pair_ab[p];
-      const int a = ab >> 8, b = ab & 255;
-      const int ia = tree ? ak[a] : a, ib = tree ? ak[b] : b;
-      A[TRI(ia) + ib] -= A[rk + ia] * A[rk + ib];
+    if (tree) {
+      const int e0 = m.chol_ofs[k], e1 = m.chol_ofs[k + 1];
+      for (int p = e0 + lane; p < e1; p += 32) {
+        const unsigned e = m.chol_tab[p];
+        A[e & 1023u] -= A[(e >> 10) & 1023u] * A[e >> 20];
+      }
+    } else {
+      const int npairs = (d * (d + 1)) >> 1;
+      for (int p = lane; p < npairs; p += 32) {
+        const unsigned ab = m.pair_ab[p];
+        const int a = ab >> 8, b = ab & 255;
+        A[TRI(a) + b] -= A[rk + a] * A[rk + b];
+      }
     }
   }
   __syncwarp();
 }
 // Root-to-leaf sweep x <- L^-1 y with y one element per lane (y = rhs after chol_rev).  tree: all dofs of one depth level
 // are finished together (their ancestors are done), so the dependency chain is max_dof_depth long instead of n.
-__device__ __forceinline__ float chol_rev_back(const DevModel& m, const float* L, int n, int lane, float y, bool tree) {
+static __device__ __noinline__ float chol_rev_back(const DevModel& m, const float* L, int n, int lane, float y, bool tree) {
   if (tree) {
     const int dep = lane < n ? m.d_depth[lane] : -1;
     const float invd = lane < n ? 1.f / L[TRI(lane) + lane] : 0.f;
@@ -262,7 +271,7 @@ __device__ __forceinline__ float chol_rev_back(const DevModel& m, const float* L
   return y;
 }
 // y = A x for the packed symmetric matrix; one element per lane.
-__device__ __forceinline__ float symv(const float* A, int n, int lane, float x) {
+static __device__ __noinline__ float symv(const float* A, int n, int lane, float x) {
   float acc = 0.f;
   const int ri = TRI(lane);
   for (int j = 0; j < n; ++j) {
@@ -274,7 +283,7 @@ __device__ __forceinline__ float symv(const float* A, int n, int lane, float x) 
   return lane < n ? acc : 0.f;
 }
 // products of the contact rows with a dof vector: lane r gets J[r] . x
-__device__ __forceinline__ float jdot(const float (*J)[JSTRIDE], int n, int lane, float x) {
+static __device__ __noinline__ float jdot(const float (*J)[JSTRIDE], int n, int lane, float x) {
   float acc = 0.f;
   const float* row = J[lane < JROWS ? lane : 0];
   for (int d = 0; d < n; ++d) acc = fmaf(row[d], __shfl_sync(FULLMASK, x, d), acc);

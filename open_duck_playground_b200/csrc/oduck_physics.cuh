@@ -482,8 +482,14 @@ __device__ __forceinline__ void forward_euler(const DevModel& m, WarpSmem& s, La
       p.d1 = 2.f * q2 + (q2 == 0.f ? 1e-15f : 0.f);
       return p;
     };
-    const LSPoint p0 = point(0.f);
-    LSPoint lo = point(p0.alpha - p0.d0 / p0.d1), hi;
+    LSPoint p0, lo, hi;
+    {
+      LSPoint ini[2];
+      float a_ = 0.f;
+#pragma unroll 1
+      for (int q = 0; q < 2; ++q) { ini[q] = point(a_); a_ = ini[0].alpha - ini[0].d0 / ini[0].d1; }
+      p0 = ini[0]; lo = ini[1];
+    }
     if (lo.d0 < p0.d0) { hi = p0; } else { hi = lo; lo = p0; }
     bool swap = true;
     int it = 0;
@@ -493,9 +499,11 @@ __device__ __forceinline__ void forward_euler(const DevModel& m, WarpSmem& s, La
       done |= (lo.d0 < 0.f) && (lo.d0 > -gtol);
       done |= (hi.d0 > 0.f) && (hi.d0 < gtol);
       if (done) break;
-      const LSPoint lo_next = point(lo.alpha - lo.d0 / lo.d1);
-      const LSPoint hi_next = point(hi.alpha - hi.d0 / hi.d1);
-      const LSPoint mid = point(0.5f * (lo.alpha + hi.alpha));
+      LSPoint cand[3];
+      const float al[3] = {lo.alpha - lo.d0 / lo.d1, 0.5f * (lo.alpha + hi.alpha), hi.alpha - hi.d0 / hi.d1};
+#pragma unroll 1
+      for (int q = 0; q < 3; ++q) cand[q] = point(al[q]);
+      const LSPoint lo_next = cand[0], mid = cand[1], hi_next = cand[2];
       // Bracket update (oracle/oduck_oracle.cpp linesearch has the rationale): a candidate becomes the new lo if its slope is
       // negative and (lo sits on the wrong side of the root or the candidate is closer to it); symmetrically for hi.
       swap = false;
