@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define ODUCK_ABI_VERSION 3
+#define ODUCK_ABI_VERSION 4
 
 #define ODUCK_MAX_BODY 20
 #define ODUCK_MAX_JNT 28
@@ -49,6 +49,9 @@ extern "C" {
 #define ODUCK_MAX_SITE 8
 #define ODUCK_MAX_VERT 32      /* convex-hull vertices per foot */
 #define ODUCK_MAX_FACE 64      /* convex-hull faces per foot (triangles) */
+#define ODUCK_MAX_PLANE 32     /* merged (coplanar) polygon faces per foot */
+#define ODUCK_MAX_PVERT 8      /* vertices per polygon face */
+#define ODUCK_MAX_EDGE 48      /* hull edges between two different polygon faces */
 #define ODUCK_NFEET 2
 #define ODUCK_CON_PER_PAIR 4   /* MJX emits 4 manifold points per geom pair */
 #define ODUCK_MAX_CON 12       /* 2 x plane/hfield-foot + 1 x foot-foot */
@@ -129,6 +132,16 @@ typedef struct OduckModel {
   double foot_vert[ODUCK_NFEET][ODUCK_MAX_VERT][3]; /* hull vertices, BODY frame */
   int32_t foot_nface;
   int32_t foot_face[ODUCK_MAX_FACE][3];             /* hull triangles (shared topology) */
+  /* polygon faces and edges of the hull (topology shared by both feet; normals per foot, BODY frame) for convex-convex */
+  int32_t foot_nplane;
+  int32_t foot_plane_nvert[ODUCK_MAX_PLANE];
+  int32_t foot_plane_vert[ODUCK_MAX_PLANE][ODUCK_MAX_PVERT];   /* counter-clockwise seen from outside */
+  double foot_plane_normal[ODUCK_NFEET][ODUCK_MAX_PLANE][3];
+  int32_t foot_nedge;
+  int32_t foot_edge_vert[ODUCK_MAX_EDGE][2];
+  int32_t foot_edge_plane[ODUCK_MAX_EDGE][2];
+  double foot_center[ODUCK_NFEET][3];                          /* bounding sphere (BODY frame) */
+  double foot_radius;
   double foot_friction;           /* foot-foot pair: max of the two geoms */
   int32_t enable_foot_foot;       /* 1 = instantiate the convex-convex pair */
   /* options */

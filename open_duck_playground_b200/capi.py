@@ -14,7 +14,7 @@ import numpy as np
 
 from .mjcf import CompiledModel
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_BODY, MAX_JNT, MAX_NQ, MAX_NV, MAX_NU, MAX_SITE, MAX_VERT, MAX_FACE, NFEET, NCMD = 20, 28, 36, 32, 16, 8, 32, 64, 2, 7
 OBS_STATE, OBS_PRIV, NMETRIC, REF_DIM, POLY_DEG, MAX_CON = 101, 212, 8, 40, 16, 12
 
@@ -42,6 +42,8 @@ class OduckModel(C.Structure):
         ("imu_site", i32), ("foot_site", i32 * NFEET),
         ("floor_is_hfield", i32), ("floor_friction", d), ("foot_body", i32 * NFEET), ("foot_nvert", i32),
         ("foot_vert", d * 3 * MAX_VERT * NFEET), ("foot_nface", i32), ("foot_face", i32 * 3 * MAX_FACE),
+        ("foot_nplane", i32), ("foot_plane_nvert", i32 * 32), ("foot_plane_vert", i32 * 8 * 32), ("foot_plane_normal", d * 3 * 32 * NFEET),
+        ("foot_nedge", i32), ("foot_edge_vert", i32 * 2 * 48), ("foot_edge_plane", i32 * 2 * 48), ("foot_center", d * 3 * NFEET), ("foot_radius", d),
         ("foot_friction", d), ("enable_foot_foot", i32),
         ("timestep", d), ("gravity", d * 3), ("tolerance", d), ("ls_tolerance", d), ("impratio", d), ("meaninertia", d),
         ("iterations", i32), ("ls_iterations", i32), ("solref", d * 2), ("solimp", d * 5),

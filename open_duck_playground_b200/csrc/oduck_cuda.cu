@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(WPB * 32, 2) k_physics(Params p) {
     for (int i = lane; i < OUT_STRIDE; i += 32) s.outrec[i] = 0.f;
     __syncwarp();
     float* dbg = DBG ? p.dbg + (size_t)env * DBG_STRIDE : nullptr;
-    for (int k = 0; k < p.nsub; ++k) forward_euler<DBG>(m, s, L, lane, k == p.nsub - 1, p.integrate != 0, s.outrec, dbg);
+    for (int k = 0; k < p.nsub; ++k) forward_euler<DBG>(m, s, L, lane, k == p.nsub - 1, p.integrate != 0, s.outrec, dbg, p.ffmodel, p.ffscratch + (size_t)env * (FFJ_SIZE + FFV_SIZE));
     __syncwarp();
     store_phys(m, s, L, lane, ph);
     store_out(s, lane, p.out + (size_t)env * OUT_STRIDE);
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(WPB * 32, 2) k_reset(Params p) {
     { const int a = m.d_act[lane]; L.ctrl = a >= 0 ? s.qpos[m.act_qadr[a]] : 0.f; }
     for (int i = lane; i < OUT_STRIDE; i += 32) s.outrec[i] = 0.f;
     __syncwarp();
-    forward_euler<false>(m, s, L, lane, true, false, s.outrec, nullptr);   // mjx_env.init
+    forward_euler<false>(m, s, L, lane, true, false, s.outrec, nullptr, p.ffmodel, p.ffscratch + (size_t)env * (FFJ_SIZE + FFV_SIZE));   // mjx_env.init
     __syncwarp();
     EnvRegs er;
     er.rng = rng;
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(WPB * 32, 2) k_step(Params p) {
     if (c.use_speed_limits) { const float lim = c.max_motor_velocity * dt; tgt = fminf(fmaxf(tgt, er.targets - lim), er.targets + lim); }
     { const int a = m.d_act[lane]; const float t = __shfl_sync(FULLMASK, tgt, a < 0 ? 0 : a); if (a >= 0) L.ctrl = t; }
     // physics: n_substeps x mjx.step (joystick.py:420)
-    for (int k = 0; k < c.n_substeps; ++k) forward_euler<false>(m, s, L, lane, k == c.n_substeps - 1, true, s.outrec, nullptr);
+    for (int k = 0; k < c.n_substeps; ++k) forward_euler<false>(m, s, L, lane, k == c.n_substeps - 1, true, s.outrec, nullptr, p.ffmodel, p.ffscratch + (size_t)env * (FFJ_SIZE + FFV_SIZE));
     __syncwarp();
     er.targets = tgt;
     // contacts / air time / swing peak (joystick.py:424-435)
@@ -635,6 +635,7 @@ static Params make_params(OduckHandle* h) {
   p.phys = h->phys; p.dr = h->dr; p.out = h->out; p.info = h->info; p.obs_state = h->obs_state; p.obs_priv = h->obs_priv;
   p.reward = h->reward; p.done = h->done; p.trunc = h->trunc; p.metrics = h->metrics;
   p.first_phys = h->first_phys; p.first_obs_state = h->first_obs_state; p.first_obs_priv = h->first_obs_priv; p.dbg = h->dbg;
+  p.ffmodel = h->dff; p.ffscratch = h->ffscratch;
   p.N = h->n;
   return p;
 }
@@ -661,7 +662,7 @@ int oduck_destroy(OduckHandle* h) {
   if (!h) return ODUCK_OK;
   cudaSetDevice(h->device);
   void* ptrs[] = {h->dmodel, h->dcfg, h->poly, h->phys, h->dr, h->out, h->info, h->obs_state, h->obs_priv, h->reward, h->done, h->trunc,
-                  h->metrics, h->first_phys, h->first_obs_state, h->first_obs_priv, h->dbg, h->policy_scratch};
+                  h->metrics, h->first_phys, h->first_obs_state, h->first_obs_priv, h->dbg, h->policy_scratch, h->dff, h->ffscratch};
   for (void* q : ptrs) if (q) cudaFree(q);
   delete h;
   return ODUCK_OK;
@@ -698,6 +699,17 @@ int oduck_create(const OduckModel* model, const OduckEnvConfig* cfg, int num_env
     CUDA_TRY(cudaMemcpy(h->poly, pf.data(), np * sizeof(float), cudaMemcpyHostToDevice));
   }
   h->hcfg.poly_coef = nullptr;
+  {
+    DevFF f;
+    memset(&f, 0, sizeof(f));
+    f.nplane = model->foot_nplane; f.nedge = model->foot_nedge; f.nvert = model->foot_nvert; f.radius = (float)model->foot_radius;
+    for (int q = 0; q < 32; q++) { f.plane_nvert[q] = model->foot_plane_nvert[q]; for (int k = 0; k < 8; k++) f.plane_vert[q][k] = model->foot_plane_vert[q][k]; }
+    for (int e2 = 0; e2 < 48; e2++) for (int k = 0; k < 2; k++) { f.edge_vert[e2][k] = model->foot_edge_vert[e2][k]; f.edge_plane[e2][k] = model->foot_edge_plane[e2][k]; }
+    for (int k = 0; k < 2; k++) { for (int i = 0; i < 3; i++) { f.center[k][i] = (float)model->foot_center[k][i]; for (int q = 0; q < 32; q++) f.plane_normal[k][i][q] = (float)model->foot_plane_normal[k][q][i]; } }
+    if (cudaMalloc((void**)&h->dff, sizeof(DevFF)) != cudaSuccess) { oduck_destroy(h); return fail(ODUCK_ERR_ALLOC, "oduck_create: cudaMalloc failed"); }
+    CUDA_TRY(cudaMemcpy(h->dff, &f, sizeof(DevFF), cudaMemcpyHostToDevice));
+  }
+  ALLOC(h->ffscratch, N * (FFJ_SIZE + FFV_SIZE));
   ALLOC(h->phys, N * PHYS_STRIDE); ALLOC(h->dr, N * DR_STRIDE); ALLOC(h->out, N * OUT_STRIDE); ALLOC(h->info, N * INFO_STRIDE);
   ALLOC(h->obs_state, N * ODUCK_OBS_STATE); ALLOC(h->obs_priv, N * ODUCK_OBS_PRIV);
   ALLOC(h->reward, N); ALLOC(h->done, N); ALLOC(h->trunc, N); ALLOC(h->metrics, N * ODUCK_NMETRIC);

@@ -14,6 +14,8 @@ struct Params {
   const float* action;     // step: [N, nu];  physics: ctrl [N, nu] or null
   const uint32_t* keys;
   const uint8_t* mask;
+  const DevFF* ffmodel;
+  float* ffscratch;
   int N, nsub, integrate;
 };
 
@@ -29,6 +31,8 @@ struct OduckHandle {
   float *phys, *dr, *out, *info, *obs_state, *obs_priv, *reward, *done, *trunc, *metrics, *first_phys, *first_obs_state, *first_obs_priv, *dbg;
   int nefc, smem_bytes, grid;
   int64_t launches;
+  DevFF* dff;
+  float* ffscratch;               // per env: 12 x 32 foot-foot Jacobian rows + SAT operands (rare path)
   float* policy_scratch;          // hidden activations of the actor MLP (tensor-core path)
   size_t policy_scratch_floats;
   const float* policy_packed_for;  // w[0] pointer the packed weight copy was made from

@@ -4,6 +4,7 @@
 // parallel line search), sensors, euler.  See oduck_device.cuh for the lane mapping.
 #pragma once
 #include "oduck_device.cuh"
+#include "oduck_ffcollide.cuh"
 
 // per-thread state that persists across the substeps of one launch
 struct Lane {
@@ -14,9 +15,12 @@ struct Lane {
 
 struct LSPoint { float alpha, cost, d0, d1; };
 
-template <bool DBG>
-__device__ __forceinline__ void forward_euler(const DevModel& m, WarpSmem& s, Lane& L, const int lane, const bool last,
-                                              const bool integrate, float* __restrict__ out, float* __restrict__ dbg) {
+// FF = false: no foot-foot code is compiled in; if the feet's bounding spheres overlap the function returns true BEFORE
+// touching any persistent state and the caller re-runs the substep with FF = true (rare).
+template <bool DBG, bool FF>
+__device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& s, Lane& L, const int lane, const bool last,
+                                              const bool integrate, float* __restrict__ out, float* __restrict__ dbg,
+                                              const DevFF* __restrict__ ffm, float* __restrict__ ffs) {
   const int nv = m.nv, nb = m.nbody;
   // ------------------------------------------------------------------ kinematics (lane = body)
   // local transform of every body at once (joint rotations do not depend on the parents), then log2(depth) rounds of
@@ -277,6 +281,13 @@ __device__ __forceinline__ void forward_euler(const DevModel& m, WarpSmem& s, La
   }
   if (lane >= NCON_FLOOR && lane < NCON_ALL) { s.con[lane][0] = 1.f; s.con[lane][1] = s.con[lane][2] = s.con[lane][3] = 0.f; }
   __syncwarp();
+  // foot-foot convex-convex pair (rare: warp-uniform early exit on the bounding spheres); its 12 Jacobian rows live in HBM scratch
+  float* ffJ = ffs;
+  bool ffact = false;
+  if (m.enable_ff) {
+    if (FF) ffact = ff_collide(m, ffm, s, lane, com, cd, ffJ, ffs + FFJ_SIZE);
+    else if (ff_maybe_close(m, ffm, s, lane)) return true;
+  }
 
   // ------------------------------------------------------------------ contact Jacobian rows (lane = dof): frame = [n=+z, t1=+y, t2=-x]
   for (int c = 0; c < NCON_FLOOR; ++c) {
@@ -311,17 +322,23 @@ __device__ __forceinline__ void forward_euler(const DevModel& m, WarpSmem& s, La
       arefl = -m.sol_b * (lsign * L.qvel) - m.sol_k * imp * pos;
     }
   }
-  const int cl = lane < NCON_FLOOR ? lane : 0;
+  const int cl = lane < NCON_ALL ? lane : 0;          // contact lane: 0..7 foot-floor, 8..11 foot-foot
+  const int cs = cl < NCON_FLOOR ? cl : 0, cf = cl >= NCON_FLOOR ? cl - NCON_FLOOR : 0;
   const float cdist = s.con[cl][0];
-  const bool cact = lane < NCON_FLOOR && cdist < 0.f;
-  const float mu = m.floor_mu;
+  const bool cact = lane < NCON_ALL && cdist < 0.f;
+  const float mu = cl < NCON_FLOOR ? m.floor_mu : m.foot_mu;
   float Dc = 0.f, arefc[4] = {0.f, 0.f, 0.f, 0.f};
   {
     const float pr = jdot(s.J, nv, lane, L.qvel);
-    const float pn = __shfl_sync(FULLMASK, pr, 3 * cl), pt1 = __shfl_sync(FULLMASK, pr, 3 * cl + 1), pt2 = __shfl_sync(FULLMASK, pr, 3 * cl + 2);
+    float pn = __shfl_sync(FULLMASK, pr, 3 * cs), pt1 = __shfl_sync(FULLMASK, pr, 3 * cs + 1), pt2 = __shfl_sync(FULLMASK, pr, 3 * cs + 2);
+    if (FF && ffact) {
+      const float pf = ffdot(ffJ, nv, lane, L.qvel);
+      const float fn = __shfl_sync(FULLMASK, pf, 3 * cf), f1 = __shfl_sync(FULLMASK, pf, 3 * cf + 1), f2 = __shfl_sync(FULLMASK, pf, 3 * cf + 2);
+      if (cl >= NCON_FLOOR) { pn = fn; pt1 = f1; pt2 = f2; }
+    }
     if (cact) {
       const float imp = impedance(m, cdist);
-      const float t = m.b_invw0[m.foot_body[cl >> 2]];
+      const float t = cl < NCON_FLOOR ? m.b_invw0[m.foot_body[cl >> 2]] : m.b_invw0[m.foot_body[0]] + m.b_invw0[m.foot_body[1]];
       const float invw = (t + mu * mu * t) * 2.f * mu * mu / m.impratio;
       Dc = 1.f / fmaxf(invw * (1.f - imp) / imp, 1e-15f);
       const float kp_ = m.sol_k * imp * cdist;
@@ -335,7 +352,12 @@ __device__ __forceinline__ void forward_euler(const DevModel& m, WarpSmem& s, La
 #define CONTACT_PRODUCTS(x, o)                                                                                         \
   {                                                                                                                    \
     const float pr_ = jdot(s.J, nv, lane, (x));                                                                        \
-    const float pn_ = __shfl_sync(FULLMASK, pr_, 3 * cl), p1_ = __shfl_sync(FULLMASK, pr_, 3 * cl + 1), p2_ = __shfl_sync(FULLMASK, pr_, 3 * cl + 2); \
+    float pn_ = __shfl_sync(FULLMASK, pr_, 3 * cs), p1_ = __shfl_sync(FULLMASK, pr_, 3 * cs + 1), p2_ = __shfl_sync(FULLMASK, pr_, 3 * cs + 2); \
+    if (FF && ffact) {                                                                                                 \
+      const float pf_ = ffdot(ffJ, nv, lane, (x));                                                                     \
+      const float fn_ = __shfl_sync(FULLMASK, pf_, 3 * cf), f1_ = __shfl_sync(FULLMASK, pf_, 3 * cf + 1), f2_ = __shfl_sync(FULLMASK, pf_, 3 * cf + 2); \
+      if (cl >= NCON_FLOOR) { pn_ = fn_; p1_ = f1_; p2_ = f2_; }                                                       \
+    }                                                                                                                  \
     o[0] = pn_ + mu * p1_; o[1] = pn_ - mu * p1_; o[2] = pn_ + mu * p2_; o[3] = pn_ - mu * p2_;                         \
   }
   // lane-local constraint cost for given Jaref values
@@ -392,7 +414,7 @@ __device__ __forceinline__ void forward_euler(const DevModel& m, WarpSmem& s, La
     float fc[4]; bool ca[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) { ca[r] = cact && Jc[r] < 0.f; fc[r] = ca[r] ? -Dc * Jc[r] : 0.f; }
-    if (lane < NCON_FLOOR) {
+    if (lane < NCON_ALL) {
       float* cc = s.con[lane];
       cc[4] = fc[0] + fc[1] + fc[2] + fc[3];
       cc[5] = mu * (fc[0] - fc[1]);
@@ -406,6 +428,11 @@ __device__ __forceinline__ void forward_euler(const DevModel& m, WarpSmem& s, La
     float qfc = ff + lsign * fl;
     for (int c = 0; c < NCON_FLOOR; ++c) {
       if (s.con[c][0] < 0.f) qfc += s.J[3 * c][lane] * s.con[c][4] + s.J[3 * c + 1][lane] * s.con[c][5] + s.J[3 * c + 2][lane] * s.con[c][6];
+    }
+    if (FF && ffact) {
+      for (int c = 0; c < 4; ++c)
+        if (s.con[NCON_FLOOR + c][0] < 0.f)
+          qfc += ffJ[(3 * c) * 32 + lane] * s.con[NCON_FLOOR + c][4] + ffJ[(3 * c + 1) * 32 + lane] * s.con[NCON_FLOOR + c][5] + ffJ[(3 * c + 2) * 32 + lane] * s.con[NCON_FLOOR + c][6];
     }
     grad = lane < nv ? Ma - fs - qfc : 0.f;
     // H = M + J^T D J
@@ -439,14 +466,34 @@ __device__ __forceinline__ void forward_euler(const DevModel& m, WarpSmem& s, La
         if (j <= lane && lane < nv) s.H[ri + j] += acc;
       }
     }
+    if (FF && ffact) {
+      // foot-foot rows couple the two legs: dense update (every i >= j), dense factorisation below
+      float Zn[4], Z1[4], Z2[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int cc = NCON_FLOOR + c;
+        const float wnn = __shfl_sync(FULLMASK, Wnn, cc), wn1 = __shfl_sync(FULLMASK, Wn1, cc), wn2 = __shfl_sync(FULLMASK, Wn2, cc);
+        const float w11 = __shfl_sync(FULLMASK, W11, cc), w22 = __shfl_sync(FULLMASK, W22, cc);
+        const float jn = ffJ[(3 * c) * 32 + lane], j1 = ffJ[(3 * c + 1) * 32 + lane], j2 = ffJ[(3 * c + 2) * 32 + lane];
+        Zn[c] = wnn * jn + wn1 * j1 + wn2 * j2;
+        Z1[c] = wn1 * jn + w11 * j1;
+        Z2[c] = wn2 * jn + w22 * j2;
+      }
+      for (int j = 0; j < nv; ++j) {
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc += Zn[c] * ffJ[(3 * c) * 32 + j] + Z1[c] * ffJ[(3 * c + 1) * 32 + j] + Z2[c] * ffJ[(3 * c + 2) * 32 + j];
+        if (j <= lane && lane < nv) s.H[TRI(lane) + j] += acc;
+      }
+    }
     __syncwarp();
     if (DBG) {
       for (int j = 0; j <= lane && lane < nv; ++j) { dbg[4096 + lane * 32 + j] = s.H[TRI(lane) + j]; dbg[4096 + j * 32 + lane] = s.H[TRI(lane) + j]; }
     }
     s.rhs[lane] = grad;
     __syncwarp();
-    chol_rev(m, s.H, s.rhs, nv, lane, true);
-    search = -chol_rev_back(m, s.H, nv, lane, s.rhs[lane], true);
+    chol_rev(m, s.H, s.rhs, nv, lane, !(FF && ffact));
+    search = -chol_rev_back(m, s.H, nv, lane, s.rhs[lane], !(FF && ffact));
     if (lane >= nv) search = 0.f;
   }
   // ------------------------------------------------------------------ line search (solver.py _linesearch)
@@ -614,6 +661,7 @@ __device__ __forceinline__ void forward_euler(const DevModel& m, WarpSmem& s, La
       dbg[1120 + lane] = s.con[lane][0];
       dbg[1136 + 3 * lane] = s.con[lane][1]; dbg[1137 + 3 * lane] = s.con[lane][2]; dbg[1138 + 3 * lane] = s.con[lane][3];
       dbg[1248 + lane] = Dc;
+      dbg[2560 + 3 * lane] = lane < NCON_FLOOR ? 0.f : ((FF && ffact) ? s.misc[0] : 1.f); dbg[2561 + 3 * lane] = lane < NCON_FLOOR ? 0.f : ((FF && ffact) ? s.misc[1] : 0.f); dbg[2562 + 3 * lane] = lane < NCON_FLOOR ? 1.f : ((FF && ffact) ? s.misc[2] : 0.f);
       for (int r = 0; r < 4; ++r) dbg[1328 + 4 * lane + r] = arefc[r];
     }
     if (lane < nb) { dbg[1440 + 3 * lane] = xp.x; dbg[1441 + 3 * lane] = xp.y; dbg[1442 + 3 * lane] = xp.z; }
@@ -647,4 +695,12 @@ __device__ __forceinline__ void forward_euler(const DevModel& m, WarpSmem& s, La
   }
 #undef CONTACT_PRODUCTS
 #undef ROW_COST
+  return false;
+}
+
+template <bool DBG>
+__device__ __forceinline__ void forward_euler(const DevModel& m, WarpSmem& s, Lane& L, const int lane, const bool last, const bool integrate,
+                                              float* __restrict__ out, float* __restrict__ dbg, const DevFF* __restrict__ ffm, float* __restrict__ ffs) {
+  if (forward_euler_impl<DBG, false>(m, s, L, lane, last, integrate, out, dbg, ffm, ffs))
+    forward_euler_impl<DBG, true>(m, s, L, lane, last, integrate, out, dbg, ffm, ffs);
 }

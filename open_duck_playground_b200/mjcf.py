@@ -227,6 +227,36 @@ def _convex_hull(tris: np.ndarray):
     return verts, np.array(faces, dtype=np.int32)
 
 
+def _hull_features(verts: np.ndarray, faces: np.ndarray):
+    """Polygon faces (coplanar hull triangles merged, vertices counter-clockwise seen from outside) and the edges between
+    two different polygon faces, with the ids of both -- the face / edge features convex-convex SAT works on."""
+    n = np.cross(verts[faces[:, 1]] - verts[faces[:, 0]], verts[faces[:, 2]] - verts[faces[:, 0]])
+    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    planes = []
+    for i, nn in enumerate(n):
+        for u in planes:
+            if np.dot(u["n"], nn) > 0.99999 and abs(np.dot(u["n"], verts[faces[i, 0]]) - u["d"]) < 1e-6:
+                u["tri"].append(i)
+                break
+        else:
+            planes.append(dict(n=nn, d=float(np.dot(nn, verts[faces[i, 0]])), tri=[i]))
+    tri_plane = {t: k for k, u in enumerate(planes) for t in u["tri"]}
+    for u in planes:
+        vs = sorted(set(faces[u["tri"]].ravel().tolist()))
+        c = verts[vs].mean(axis=0)
+        e1 = verts[vs[0]] - c
+        e1 /= np.linalg.norm(e1)
+        e2 = np.cross(u["n"], e1)
+        ang = [np.arctan2(np.dot(verts[v] - c, e2), np.dot(verts[v] - c, e1)) for v in vs]
+        u["loop"] = [v for _, v in sorted(zip(ang, vs))]
+    edge_planes: Dict[tuple, set] = {}
+    for t, f in enumerate(faces):
+        for a, b in ((f[0], f[1]), (f[1], f[2]), (f[2], f[0])):
+            edge_planes.setdefault((int(min(a, b)), int(max(a, b))), set()).add(tri_plane[t])
+    edges = [(e, sorted(ps)) for e, ps in sorted(edge_planes.items()) if len(ps) == 2]
+    return planes, edges
+
+
 # --------------------------------------------------------------------------- compile
 def compile_mjcf(xml_path: str, timestep: float = 0.002) -> CompiledModel:
     """Compile a scene XML.  ``timestep`` mirrors ``mj_model.opt.timestep = sim_dt`` (base.py:56)."""
@@ -464,6 +494,28 @@ def compile_mjcf(xml_path: str, timestep: float = 0.002) -> CompiledModel:
         A["foot_nvert"] = np.array(len(verts), np.int32)
         A["foot_nface"] = np.array(len(faces), np.int32)
         A["foot_face"][: len(faces)] = faces
+        planes, edges = _hull_features(verts, faces)
+        if len(planes) > 32 or len(edges) > 48 or max(len(u["loop"]) for u in planes) > 8:
+            raise ValueError("foot hull has too many polygon faces / edges")
+        if k == 0:
+            A["foot_nplane"] = np.array(len(planes), np.int32)
+            A["foot_plane_nvert"] = np.zeros(32, np.int32)
+            A["foot_plane_vert"] = np.zeros((32, 8), np.int32)
+            A["foot_plane_normal"] = np.zeros((2, 32, 3))
+            A["foot_nedge"] = np.array(len(edges), np.int32)
+            A["foot_edge_vert"] = np.zeros((48, 2), np.int32)
+            A["foot_edge_plane"] = np.zeros((48, 2), np.int32)
+            A["foot_center"] = np.zeros((2, 3))
+            for q, u in enumerate(planes):
+                A["foot_plane_nvert"][q] = len(u["loop"])
+                A["foot_plane_vert"][q, : len(u["loop"])] = u["loop"]
+            for q, (e, ps) in enumerate(edges):
+                A["foot_edge_vert"][q], A["foot_edge_plane"][q] = e, ps
+        for q, u in enumerate(planes):
+            A["foot_plane_normal"][k, q] = R @ u["n"]
+        body_v = A["foot_vert"][k, : len(verts)]
+        A["foot_center"][k] = body_v.mean(axis=0)
+        A["foot_radius"] = np.array(max(float(A["foot_radius"]) if "foot_radius" in A else 0.0, float(np.linalg.norm(body_v - body_v.mean(axis=0), axis=1).max())))
     # contact parameter mixing: higher priority wins, else max friction (MuJoCo mj_contactParam)
     f0 = feet[0]
     A["floor_friction"] = np.array(floor["friction"][0] if floor["priority"] > f0["priority"] else

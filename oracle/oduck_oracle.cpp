@@ -515,6 +515,132 @@ static void plane_convex(const OduckModel& m, const Scratch& s, int k, int slot0
   }
 }
 
+
+// Convex-convex narrow phase for the two feet (the mesh-mesh pair MJX instantiates: both collision meshes have
+// contype = conaffinity = 1).  PARITY UNPINNED like the rest of the physics: MJX's convex_convex source is
+// not available, so this is a restatement of the documented scheme -- separating-axis test over the face normals of
+// both hulls and the cross products of edge pairs, then a clipped-polygon manifold of at most 4 points:
+//   * face axes: signed distance of the other hull's deepest vertex to every polygon face,
+//   * edge axes: only edge pairs that span a face of the Minkowski difference (Gauss-map arc test), distance between the
+//     two edge lines along their common normal,
+//   * face contact: the incident face (most anti-parallel) is Sutherland-Hodgman clipped against the side planes of the
+//     reference face; dist = signed distance to the reference plane, pos = midway; >4 points -> _manifold_points,
+//   * edge contact (chosen only if it separates 0.1 mm better than the best face): closest points of the two edges.
+// Normal points from geom1 (left foot) to geom2 (right foot).
+static void convex_convex(const OduckModel& m, const Scratch& s, Scratch& out) {
+  const int bA = m.foot_body[0], bB = m.foot_body[1], nvt = m.foot_nvert, np_ = m.foot_nplane, ne = m.foot_nedge;
+  for (int c = 8; c < 12; c++) { out.con_dist[c] = 1; out.con_b1[c] = bA; out.con_b2[c] = bB; out.con_mu[c] = (real)m.foot_friction; }
+  real VA[ODUCK_MAX_VERT][3], VB[ODUCK_MAX_VERT][3], nrmA[ODUCK_MAX_PLANE][3], nrmB[ODUCK_MAX_PLANE][3], cA[3], cB[3];
+  auto xform = [&](int b, const double* v, real* o) { real t[3] = {(real)v[0], (real)v[1], (real)v[2]}; mat_vec(s.xmat[b], t, o); for (int i = 0; i < 3; i++) o[i] += s.xpos[b][i]; };
+  xform(bA, m.foot_center[0], cA);
+  xform(bB, m.foot_center[1], cB);
+  real dc[3] = {cB[0] - cA[0], cB[1] - cA[1], cB[2] - cA[2]};
+  if (std::sqrt(dot3(dc, dc)) > 2 * (real)m.foot_radius) return;                      // bounding spheres apart: no contact
+  for (int i = 0; i < nvt; i++) { xform(bA, m.foot_vert[0][i], VA[i]); xform(bB, m.foot_vert[1][i], VB[i]); }
+  for (int q = 0; q < np_; q++) {
+    real a[3] = {(real)m.foot_plane_normal[0][q][0], (real)m.foot_plane_normal[0][q][1], (real)m.foot_plane_normal[0][q][2]};
+    real b[3] = {(real)m.foot_plane_normal[1][q][0], (real)m.foot_plane_normal[1][q][1], (real)m.foot_plane_normal[1][q][2]};
+    mat_vec(s.xmat[bA], a, nrmA[q]);
+    mat_vec(s.xmat[bB], b, nrmB[q]);
+  }
+  const real ninf = -std::numeric_limits<real>::infinity();
+  real face_sep = ninf; int face_hull = 0, face_idx = 0;
+  for (int h = 0; h < 2; h++)
+    for (int q = 0; q < np_; q++) {
+      const real* n = h ? nrmB[q] : nrmA[q];
+      const real (*Vr)[3] = h ? VB : VA; const real (*Vo)[3] = h ? VA : VB;
+      real off = dot3(n, Vr[m.foot_plane_vert[q][0]]), mn = std::numeric_limits<real>::infinity();
+      for (int j = 0; j < nvt; j++) mn = std::min(mn, dot3(n, Vo[j]));
+      if (mn - off > face_sep) { face_sep = mn - off; face_hull = h; face_idx = q; }
+    }
+  if (face_sep > 0) return;
+  real edge_sep = ninf, edge_n[3] = {0, 0, 1}; int eA_best = -1, eB_best = -1;
+  for (int ea = 0; ea < ne; ea++) {
+    const real *a = nrmA[m.foot_edge_plane[ea][0]], *b = nrmA[m.foot_edge_plane[ea][1]];
+    const real *pa0 = VA[m.foot_edge_vert[ea][0]], *pa1 = VA[m.foot_edge_vert[ea][1]];
+    real dA[3] = {pa1[0] - pa0[0], pa1[1] - pa0[1], pa1[2] - pa0[2]}, bxa[3];
+    cross3(b, a, bxa);
+    for (int eb = 0; eb < ne; eb++) {
+      real c[3], d[3], dxc[3];
+      for (int i = 0; i < 3; i++) { c[i] = -nrmB[m.foot_edge_plane[eb][0]][i]; d[i] = -nrmB[m.foot_edge_plane[eb][1]][i]; }
+      cross3(d, c, dxc);
+      real cba = dot3(c, bxa), dba = dot3(d, bxa), adc = dot3(a, dxc), bdc = dot3(b, dxc);
+      if (!(cba * dba < 0 && adc * bdc < 0 && cba * bdc > 0)) continue;            // the two arcs do not cross on the Gauss map
+      const real *pb0 = VB[m.foot_edge_vert[eb][0]], *pb1 = VB[m.foot_edge_vert[eb][1]];
+      real dB[3] = {pb1[0] - pb0[0], pb1[1] - pb0[1], pb1[2] - pb0[2]}, n[3];
+      cross3(dA, dB, n);
+      real len2 = dot3(n, n);
+      if (len2 < (real)1e-10 * dot3(dA, dA) * dot3(dB, dB)) continue;                  // parallel edges
+      real inv = 1 / std::sqrt(len2);
+      for (int i = 0; i < 3; i++) n[i] *= inv;
+      real rel[3] = {pa0[0] - cA[0], pa0[1] - cA[1], pa0[2] - cA[2]};
+      if (dot3(n, rel) < 0) for (int i = 0; i < 3; i++) n[i] = -n[i];                 // away from hull A
+      real w[3] = {pb0[0] - pa0[0], pb0[1] - pa0[1], pb0[2] - pa0[2]};
+      real sep = dot3(n, w);
+      if (sep > edge_sep) { edge_sep = sep; eA_best = ea; eB_best = eb; for (int i = 0; i < 3; i++) edge_n[i] = n[i]; }
+    }
+  }
+  if (edge_sep > 0) return;
+  if (eA_best >= 0 && edge_sep > face_sep + (real)1e-4) {
+    // closest points of the two supporting edges
+    const real *p1 = VA[m.foot_edge_vert[eA_best][0]], *q1 = VA[m.foot_edge_vert[eA_best][1]], *p2 = VB[m.foot_edge_vert[eB_best][0]], *q2 = VB[m.foot_edge_vert[eB_best][1]];
+    real d1[3], d2[3], r[3];
+    for (int i = 0; i < 3; i++) { d1[i] = q1[i] - p1[i]; d2[i] = q2[i] - p2[i]; r[i] = p1[i] - p2[i]; }
+    real a = dot3(d1, d1), e = dot3(d2, d2), f = dot3(d2, r), c = dot3(d1, r), b = dot3(d1, d2), den = a * e - b * b;
+    real sA = den > (real)1e-18 ? std::min(std::max((b * f - c * e) / den, (real)0), (real)1) : 0;
+    real tB = std::min(std::max((b * sA + f) / e, (real)0), (real)1);
+    sA = std::min(std::max((b * tB - c) / a, (real)0), (real)1);
+    out.con_dist[8] = edge_sep;
+    for (int i = 0; i < 3; i++) out.con_pos[8][i] = (real)0.5 * (p1[i] + sA * d1[i] + p2[i] + tB * d2[i]);
+    make_frame(edge_n, out.con_frame[8]);
+    for (int c2 = 9; c2 < 12; c2++) for (int i = 0; i < 9; i++) out.con_frame[c2][i] = out.con_frame[8][i];
+    return;
+  }
+  // face contact: reference face on hull `face_hull`, incident face = most anti-parallel face of the other hull
+  const real (*Vr)[3] = face_hull ? VB : VA; const real (*Vi)[3] = face_hull ? VA : VB;
+  const real (*Ni)[3] = face_hull ? nrmA : nrmB;
+  const real* nref = face_hull ? nrmB[face_idx] : nrmA[face_idx];
+  int inc = 0; real best = std::numeric_limits<real>::infinity();
+  for (int q = 0; q < np_; q++) { real v = dot3(Ni[q], nref); if (v < best) { best = v; inc = q; } }
+  real poly[2][2 * ODUCK_MAX_PVERT + 2][3];
+  int cur = 0, cnt = m.foot_plane_nvert[inc];
+  for (int k = 0; k < cnt; k++) for (int i = 0; i < 3; i++) poly[0][k][i] = Vi[m.foot_plane_vert[inc][k]][i];
+  const int nr = m.foot_plane_nvert[face_idx];
+  for (int k = 0; k < nr && cnt > 0; k++) {
+    const real *r0 = Vr[m.foot_plane_vert[face_idx][k]], *r1 = Vr[m.foot_plane_vert[face_idx][(k + 1) % nr]];
+    real e[3] = {r1[0] - r0[0], r1[1] - r0[1], r1[2] - r0[2]}, sd[3];
+    cross3(e, nref, sd);                                                              // outward side-plane normal (loop is CCW from outside)
+    int no = 0;
+    for (int v = 0; v < cnt; v++) {
+      const real *x0 = poly[cur][v], *x1 = poly[cur][(v + 1) % cnt];
+      real w0[3] = {x0[0] - r0[0], x0[1] - r0[1], x0[2] - r0[2]}, w1[3] = {x1[0] - r0[0], x1[1] - r0[1], x1[2] - r0[2]};
+      real d0 = dot3(sd, w0), d1 = dot3(sd, w1);
+      if (d0 <= 0) { for (int i = 0; i < 3; i++) poly[1 - cur][no][i] = x0[i]; no++; }
+      if ((d0 <= 0) != (d1 <= 0)) { real t = d0 / (d0 - d1); for (int i = 0; i < 3; i++) poly[1 - cur][no][i] = x0[i] + t * (x1[i] - x0[i]); no++; }
+    }
+    cur = 1 - cur; cnt = no;
+  }
+  if (cnt == 0) return;
+  real dist[2 * ODUCK_MAX_PVERT + 2];
+  bool mask[2 * ODUCK_MAX_PVERT + 2];
+  const real* r0 = Vr[m.foot_plane_vert[face_idx][0]];
+  for (int v = 0; v < cnt; v++) { real w[3] = {poly[cur][v][0] - r0[0], poly[cur][v][1] - r0[1], poly[cur][v][2] - r0[2]}; dist[v] = dot3(nref, w); mask[v] = dist[v] < 0; }
+  int idx[4] = {0, 1, 2, 3};
+  if (cnt > 4) manifold_points(cnt, poly[cur], mask, nref, idx);
+  real n12[3] = {face_hull ? -nref[0] : nref[0], face_hull ? -nref[1] : nref[1], face_hull ? -nref[2] : nref[2]};   // geom1 -> geom2
+  real frame[9];
+  make_frame(n12, frame);
+  for (int c = 0; c < 4; c++) {
+    int sl = 8 + c, v = idx[c];
+    bool ok = v < cnt;
+    for (int p2 = 0; p2 < c && ok; p2++) ok = idx[p2] != v;                           // duplicates (cnt > 4 selection) are inactive
+    for (int i = 0; i < 9; i++) out.con_frame[sl][i] = frame[i];
+    if (!ok) continue;
+    out.con_dist[sl] = dist[v];
+    for (int i = 0; i < 3; i++) out.con_pos[sl][i] = poly[cur][v][i] - (real)0.5 * dist[v] * nref[i];
+  }
+}
+
 // constraint.py _kbi / _efc_row
 static void kbi(const OduckModel& m, real pos, real* k, real* b, real* imp) {
   real timeconst = std::max((real)m.solref[0], 2 * (real)m.timestep), dampratio = (real)m.solref[1];
@@ -847,8 +973,7 @@ static void forward(const OduckHandle& h, EnvState& e, Scratch& s) {
     plane_convex(m, s, 0, 0, s);
     plane_convex(m, s, 1, 4, s);
   }
-  if (m.enable_foot_foot)
-    for (int c = 8; c < 12; c++) { s.con_b1[c] = m.foot_body[0]; s.con_b2[c] = m.foot_body[1]; s.con_mu[c] = (real)m.foot_friction; }
+  if (m.enable_foot_foot) convex_convex(m, s, s);
   (void)ncon;
   make_constraint(h, e, s);
   com_vel(m, e, s);
@@ -1410,7 +1535,7 @@ int oduck_debug_forward(OduckHandle* h, double* out) {
       d[1376 + a] = g_dbg.search[a]; d[1408 + a] = g_dbg.grad[a]; d[1736 + a] = e.qacc[a];
       for (int k = 0; k < 6; k++) d[1540 + a * 6 + k] = s.cdof[a][k];
     }
-    for (int c = 0; c < NCON; c++) { d[1120 + c] = s.con_dist[c]; for (int k = 0; k < 3; k++) d[1136 + 3 * c + k] = s.con_pos[c][k]; }
+    for (int c = 0; c < NCON; c++) { d[1120 + c] = s.con_dist[c]; for (int k = 0; k < 3; k++) { d[1136 + 3 * c + k] = s.con_pos[c][k]; d[2560 + 3 * c + k] = s.con_frame[c][k]; } }
     int r = 0;
     for (int k = 0; k < h->nefc_fr; k++, r++) { d[1184 + h->fr_dof[k]] = s.D[r]; d[1264 + h->fr_dof[k]] = s.aref[r]; }
     for (int k = 0; k < h->nefc_lim; k++, r++) { int dd = m.jnt_dofadr[h->lim_jnt[k]]; d[1216 + dd] = s.D[r]; d[1296 + dd] = s.aref[r]; }

@@ -161,3 +161,54 @@ def test_nan_state_terminates(oracle, model_backlash, poly_table):
     assert h.buffer_numpy("DONE").tolist() == [0.0, 1.0]
     assert not np.isnan(h.buffer_numpy("QPOS")[1]).any()      # auto-reset restored the first state
     assert abs(h.buffer_numpy("REWARD")[1] - 20.0 * 0.02) < 1e-12   # every term is nan_to_num-ed: only "alive" survives
+
+
+def _ff_poses(model, n, seed):
+    """Random in-range joint poses with both hip rolls driven inward, so that a fair share of them has foot-foot contact."""
+    rng = np.random.default_rng(seed)
+    q = np.tile(model.key_qpos[: model.nq], (n, 1)).astype(np.float32)
+    q[:, 2] = 0.6
+    for j in range(1, model.njnt):
+        lo, hi = model.jnt_range[j]
+        q[:, model.jnt_qposadr[j]] = rng.uniform(lo, hi, n)
+    q[:, model.jnt_qposadr[model.joint_id("left_hip_roll")]] = rng.uniform(0.3, 0.436, n)
+    q[:, model.jnt_qposadr[model.joint_id("right_hip_roll")]] = -rng.uniform(0.3, 0.436, n)
+    for name in ("left_hip_pitch", "right_hip_pitch", "left_knee", "right_knee", "left_ankle", "right_ankle"):
+        q[:, model.jnt_qposadr[model.joint_id(name)]] = model.key_qpos[model.jnt_qposadr[model.joint_id(name)]] + rng.normal(0, 0.1, n)
+    return q
+
+
+def test_foot_foot_contacts_are_sane_and_repulsive(oracle, model_backlash, poly_table):
+    m = copy.deepcopy(model_backlash)
+    m.arrays["act_kp"][:] = 0; m.arrays["gravity"][:] = 0
+    n = 256
+    h = make_handle(oracle, m, poly_table, n)
+    q = _ff_poses(m, n, 0)
+    v = np.zeros((n, m.nv), np.float32)
+    h.set_state(q.ctypes.data, v.ctypes.data, v.ctypes.data)
+    d = _dump(oracle, h)
+    dist, pos, nrm = d[:, 1128:1132], d[:, 1136 + 24:1136 + 36].reshape(n, 4, 3), d[:, 2560 + 24:2560 + 27]
+    hit = (dist < 0).any(axis=1)
+    assert 10 < hit.sum() < n                                     # the rare path is exercised, and not always
+    for i in np.nonzero(hit)[0]:
+        xpos, xmat, _, _ = mjcf.world_kinematics(m, q[i].astype(np.float64))
+        cl = xpos[7] + xmat[7] @ m.foot_center[0]; cr = xpos[16] + xmat[16] @ m.foot_center[1]
+        assert abs(np.linalg.norm(nrm[i]) - 1) < 1e-9
+        assert np.dot(nrm[i], cr - cl) > 0                        # normal points from the left foot (geom1) to the right foot (geom2)
+        for c in range(4):
+            if dist[i, c] < 0:
+                assert np.linalg.norm(pos[i, c] - cl) < float(m.foot_radius) + 0.02 and np.linalg.norm(pos[i, c] - cr) < float(m.foot_radius) + 0.02
+                assert dist[i, c] > -0.05
+    # contact forces are repulsive: after 20 ms of free motion the deepest penetration has shrunk in (almost) every env
+    h.physics_substeps(0, 10)
+    d2 = _dump(oracle, h)
+    before, after = dist[hit].min(axis=1), np.minimum(d2[hit, 1128:1132].min(axis=1), 0)
+    assert (after > before).mean() > 0.9
+    assert np.all(np.isfinite(h.buffer_numpy("QPOS")))
+
+
+def test_no_foot_foot_contact_in_nominal_poses(oracle, model_backlash, poly_table):
+    h = make_handle(oracle, model_backlash, poly_table, 64)
+    keys = np.stack([np.zeros(64, np.uint32), np.arange(64, dtype=np.uint32)], 1)
+    h.reset(keys.ctypes.data)
+    assert np.all(h.buffer_numpy("CONTACT_DIST")[:, 8:12] == 1)

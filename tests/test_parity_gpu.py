@@ -228,6 +228,40 @@ def test_autoreset_truncation_and_full_size_invariants(oracle):
     assert int(gpu.handle.launch_count()) == 2 + 4          # randomize + reset + 4 fused steps: one launch per env.step
 
 
+def test_foot_foot_rare_path_parity(oracle):
+    """A8.5 convex-convex: poses with the hip rolls driven inward so that many envs take the foot-foot path (dense Hessian)."""
+    from test_oracle_physics import _ff_poses
+    n = 512
+    gpu, ref, sg, sr = _pair(oracle, "flat_terrain_backlash", n)
+    q = torch.from_numpy(_ff_poses(gpu.mj_model, n, 3))
+    v = torch.zeros(n, 30)
+    gpu.set_state(q, v, v); ref.set_state(q, v, v)
+    outs = []
+    for env, dt in ((gpu, np.float32), (ref, np.float64)):
+        L = env.handle.L.lib
+        buf = np.zeros((n, L.oduck_debug_stride()), dt)
+        L.oduck_debug_forward.argtypes = [C.c_void_p, C.c_void_p]
+        env.handle.L.check(L.oduck_debug_forward(env.handle.h, buf.ctypes.data))
+        outs.append(buf.astype(np.float64))
+    g, r = outs
+    hit = (r[:, 1128:1132] < 0).any(axis=1)
+    assert hit.sum() > 20
+    c = Checks()
+    c.mostly_equal(g[:, 1128:1132] < 0, r[:, 1128:1132] < 0, "active foot-foot contact set")
+    both = (g[:, 1128:1132] < 0) & (r[:, 1128:1132] < 0)
+    c.close(torch.from_numpy(np.where(both, g[:, 1128:1132], 0)), torch.from_numpy(np.where(both, r[:, 1128:1132], 0)), 2e-6, what="foot-foot dist")
+    gp, rp = g[:, 1136 + 24:1136 + 36].reshape(n, 4, 3), r[:, 1136 + 24:1136 + 36].reshape(n, 4, 3)
+    c.close(torch.from_numpy(np.where(both[..., None], gp, 0)), torch.from_numpy(np.where(both[..., None], rp, 0)), 2e-6, what="foot-foot pos")
+    c.close(torch.from_numpy(np.where(hit[:, None], g[:, 2560 + 24:2560 + 27], 0)), torch.from_numpy(np.where(hit[:, None], r[:, 2560 + 24:2560 + 27], 0)), 1e-4, what="foot-foot normal")
+    c.rows(torch.from_numpy(g[:, 1736:1766]), torch.from_numpy(r[:, 1736:1766]), 1e-3, 2e-3, what="qacc with foot-foot contacts")
+    # and a control step from this state
+    act = torch.zeros(n, 14)
+    sg, sr = gpu.step(sg, act.cuda()), ref.step(sr, act)
+    c.close(sg.data.qpos, sr.data.qpos, 2e-4, what="qpos after a control step")
+    c.rows(sg.data.qvel, sr.data.qvel, 5e-3, 2e-3, what="qvel after a control step")
+    c.done()
+
+
 def test_policy_forward_parity(oracle):
     """A15: CUDA actor-MLP kernel vs the oracle's fp64 MLP and vs the torch module the PPO update differentiates."""
     from open_duck_playground_b200 import ppo
