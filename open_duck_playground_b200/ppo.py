@@ -45,6 +45,10 @@ class PPOConfig:
     policy_obs_key: str = "state"
     value_obs_key: str = "privileged_state"
     seed: int = 0
+    update_mode: str = "auto"       # "replicated": all_gather rollouts, identical update on every rank;
+                                    # "sharded": every rank updates on its own env shard, gradients all-reduced per minibatch (Brax's pmean);
+                                    # "auto": sharded on CUDA with world > 1, else replicated
+    cuda_graph: bool = True         # capture one minibatch update (fwd + bwd + clip + Adam) in a CUDA graph on GPU
 
 
 class MLP(torch.nn.Module):
@@ -75,15 +79,20 @@ class RunningStats:
         self.m2 = torch.zeros(dim, device=device, dtype=torch.float64)
         self.std = torch.ones(dim, device=device)
 
-    def update(self, batch: torch.Tensor) -> None:
+    def update(self, batch: torch.Tensor, reduce: bool = False) -> None:
         b = batch.reshape(-1, batch.shape[-1]).double()
-        n = b.shape[0]
+        mom = torch.cat([torch.full((1,), float(b.shape[0]), device=b.device, dtype=torch.float64), b.sum(0), (b * b).sum(0)])
+        if reduce:                                           # sharded update: merge the ranks' moments (one small all-reduce)
+            dist.all_reduce(mom)
+        n, bsum, bsq = mom[0], mom[1:1 + b.shape[1]], mom[1 + b.shape[1]:]
+        bmean = bsum / n
+        bm2 = bsq - n * bmean * bmean
         new_count = self.count + n
-        delta = b.mean(0) - self.mean
-        self.m2 += ((b - b.mean(0)) ** 2).sum(0) + delta ** 2 * self.count * n / new_count
+        delta = bmean - self.mean
+        self.m2 += bm2 + delta ** 2 * self.count * n / new_count
         self.mean += delta * n / new_count
         self.count = new_count
-        self.std = torch.sqrt(self.m2 / self.count).clamp(1e-6, 1e6).float()
+        self.std.copy_(torch.sqrt(self.m2 / self.count).clamp(1e-6, 1e6).float())
 
     @property
     def mean32(self):
@@ -187,8 +196,9 @@ class PPOTrainer:
         na = env.action_size
         self.policy = MLP([env.observation_size[cfg.policy_obs_key][0], *cfg.policy_hidden_layer_sizes, 2 * na]).to(dev)
         self.value = MLP([env.observation_size[cfg.value_obs_key][0], *cfg.value_hidden_layer_sizes, 1]).to(dev)
-        self.opt = torch.optim.Adam(list(self.policy.parameters()) + list(self.value.parameters()), lr=cfg.learning_rate)
+        self.opt = torch.optim.Adam(list(self.policy.parameters()) + list(self.value.parameters()), lr=cfg.learning_rate, capturable=dev.type == "cuda")
         self.stats = {k: RunningStats(env.observation_size[k][0], dev) for k in (cfg.policy_obs_key, cfg.value_obs_key)}
+        self._mean32 = {k: torch.zeros(env.observation_size[k][0], device=dev) for k in self.stats}
         self.weights = PolicyWeights(self.policy, env.observation_size[cfg.policy_obs_key][0], dev)
         self.key = jr.PRNGKey(cfg.seed + 17)
         self.env_steps = 0
@@ -221,55 +231,133 @@ class PPOTrainer:
         self.state = st
         return buf
 
-    # ------------------------------------------------------------------ update (replicated on every rank)
-    def update(self, batch: Dict[str, torch.Tensor]) -> Dict[str, float]:
+    # ------------------------------------------------------------------ update
+    def _minibatch_loss(self, mb: Dict[str, torch.Tensor]):
         cfg = self.cfg
         pk, vk = cfg.policy_obs_key, cfg.value_obs_key
         if cfg.normalize_observations:
-            self.stats[pk].update(batch["obs_p"][:-1]); self.stats[vk].update(batch["obs_v"][:-1])
-        norm = (lambda x, k: (x - self.stats[k].mean32) / self.stats[k].std) if cfg.normalize_observations else (lambda x, k: x)
+            obs_p = (mb["obs_p"] - self._mean32[pk]) / self.stats[pk].std
+            obs_v = (mb["obs_v"] - self._mean32[vk]) / self.stats[vk].std
+        else:
+            obs_p, obs_v = mb["obs_p"], mb["obs_v"]
+        values = self.value(obs_v).squeeze(-1)
+        baseline, bootstrap = values[:-1], values[-1]
+        trunc, done = mb["trunc"], mb["done"]
+        termination = done * (1 - trunc)
+        rewards = mb["reward"] * cfg.reward_scaling
+        vs, adv = compute_gae(trunc, termination, rewards, baseline.detach(), bootstrap.detach(), cfg.gae_lambda, cfg.discounting)
+        adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+        logp, ent = torch_policy_logprob(self.policy, obs_p[:-1], mb["raw"])
+        rho = torch.exp(logp - mb["logp"])
+        policy_loss = -torch.min(rho * adv, rho.clamp(1 - cfg.clipping_epsilon, 1 + cfg.clipping_epsilon) * adv).mean()
+        v_loss = ((vs - baseline) ** 2).mean() * 0.5 * 0.5
+        ent_mean = ent.mean()
+        return policy_loss + v_loss - cfg.entropy_cost * ent_mean, policy_loss, v_loss, ent_mean
+
+    def _params(self):
+        return list(self.policy.parameters()) + list(self.value.parameters())
+
+    def _apply_grads(self):
+        torch.nn.utils.clip_grad_norm_(self._params(), self.cfg.max_grad_norm, foreach=True)
+        self.opt.step()
+
+    def _build_graphs(self, mb_shapes: Dict[str, torch.Size], sharded: bool) -> None:
+        """Capture (forward + backward) and (clip + Adam) of one minibatch; the sharded mode all-reduces the flat gradient in between."""
+        dev = self.env.device
+        self._static = {k: torch.zeros(shp, device=dev) for k, shp in mb_shapes.items()}
+        self._out = torch.zeros(4, device=dev)
+        snap = [p.detach().clone() for p in self._params()]
+        opt_state = self.opt.state_dict()
+        for prm in self._params():
+            prm.grad = torch.zeros_like(prm)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):                                   # warm-up outside capture (allocator, cuBLAS handles, Adam state)
+                for prm in self._params():
+                    prm.grad.zero_()
+                loss, *_ = self._minibatch_loss(self._static)
+                loss.backward()
+                self._apply_grads()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self._g_fb, self._g_step = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._g_fb):
+            for prm in self._params():
+                prm.grad.zero_()
+            loss, pl, vl, en = self._minibatch_loss(self._static)
+            loss.backward()
+            self._out.copy_(torch.stack([loss.detach(), pl.detach(), vl.detach(), en.detach()]))
+        with torch.cuda.graph(self._g_step):
+            self._apply_grads()
+        with torch.no_grad():                                    # undo the warm-up / capture-time updates
+            for prm, sv in zip(self._params(), snap):
+                prm.copy_(sv)
+        self.opt.load_state_dict(opt_state)
+        self._graph_sharded = sharded
+
+    def update(self, batch: Dict[str, torch.Tensor], sharded: bool = False) -> Dict[str, float]:
+        """4 epochs x num_minibatches clipped-PPO updates on ``batch`` ([T(+1), N, ...]).  sharded: ``batch`` is this rank's env shard and
+        gradients are averaged over ranks (Brax's pmean); otherwise ``batch`` is the gathered global batch and every rank does the same update."""
+        cfg = self.cfg
+        pk, vk = cfg.policy_obs_key, cfg.value_obs_key
+        if cfg.normalize_observations:
+            self.stats[pk].update(batch["obs_p"][:-1], reduce=sharded); self.stats[vk].update(batch["obs_v"][:-1], reduce=sharded)
+        for k in (pk, vk):
+            self._mean32[k].copy_(self.stats[k].mean32)
         T, N = batch["reward"].shape
-        gen = torch.Generator(device="cpu").manual_seed(cfg.seed + self.env_steps)       # same permutation on every rank
-        metrics = {}
+        gen = torch.Generator(device="cpu").manual_seed(cfg.seed + self.env_steps + (self.rank if sharded else 0))
         mb = N // cfg.num_minibatches
+        use_graph = cfg.cuda_graph and self.env.device.type == "cuda"
+        keys = ("obs_p", "obs_v", "raw", "logp", "reward", "done", "trunc")
+        if use_graph and getattr(self, "_g_fb", None) is None:
+            self._build_graphs({k: batch[k][:, :mb].shape for k in keys}, sharded)
+        params = self._params()
         for _ in range(cfg.num_updates_per_batch):
             perm = torch.randperm(N, generator=gen).to(batch["reward"].device)
             for i in range(cfg.num_minibatches):
                 idx = perm[i * mb:(i + 1) * mb]
-                obs_p, obs_v = norm(batch["obs_p"][:, idx], pk), norm(batch["obs_v"][:, idx], vk)
-                values = self.value(obs_v).squeeze(-1)
-                baseline, bootstrap = values[:-1], values[-1]
-                trunc, done = batch["trunc"][:, idx], batch["done"][:, idx]
-                termination = done * (1 - trunc)
-                rewards = batch["reward"][:, idx] * cfg.reward_scaling
-                vs, adv = compute_gae(trunc, termination, rewards, baseline.detach(), bootstrap.detach(), cfg.gae_lambda, cfg.discounting)
-                adv = (adv - adv.mean()) / (adv.std() + 1e-8)
-                logp, ent = torch_policy_logprob(self.policy, obs_p[:-1], batch["raw"][:, idx])
-                rho = torch.exp(logp - batch["logp"][:, idx])
-                policy_loss = -torch.min(rho * adv, rho.clamp(1 - cfg.clipping_epsilon, 1 + cfg.clipping_epsilon) * adv).mean()
-                v_loss = ((vs - baseline) ** 2).mean() * 0.5 * 0.5
-                ent_loss = -cfg.entropy_cost * ent.mean()
-                loss = policy_loss + v_loss + ent_loss
-                self.opt.zero_grad(set_to_none=True)
-                loss.backward()
-                torch.nn.utils.clip_grad_norm_(list(self.policy.parameters()) + list(self.value.parameters()), cfg.max_grad_norm)
-                self.opt.step()
-        metrics.update(loss=float(loss), policy_loss=float(policy_loss), v_loss=float(v_loss), entropy=float(ent.mean()))
-        return metrics
+                if use_graph:
+                    for k in keys:
+                        torch.index_select(batch[k], 1, idx, out=self._static[k])
+                    self._g_fb.replay()
+                    if sharded:
+                        flat = torch.cat([p.grad.flatten() for p in params])
+                        dist.all_reduce(flat)
+                        flat /= self.world
+                        off = 0
+                        for p in params:
+                            p.grad.copy_(flat[off:off + p.numel()].view_as(p)); off += p.numel()
+                    self._g_step.replay()
+                else:
+                    loss, pl, vl, en = self._minibatch_loss({k: batch[k][:, idx] for k in keys})
+                    self.opt.zero_grad(set_to_none=True)
+                    loss.backward()
+                    if sharded:
+                        for p in params:
+                            dist.all_reduce(p.grad); p.grad /= self.world
+                    self._apply_grads()
+        if use_graph:
+            o = self._out.tolist()
+            return dict(loss=o[0], policy_loss=o[1], v_loss=o[2], entropy=o[3])
+        return dict(loss=float(loss.detach()), policy_loss=float(pl.detach()), v_loss=float(vl.detach()), entropy=float(en.detach()))
 
     def training_step(self) -> Dict[str, float]:
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if self.env.device.type == "cuda" else None
         if ev: ev[0].record()
         local = self.rollout()
         if ev: ev[1].record()
-        batch = all_gather_rollout(local, self.world)
+        mode = self.cfg.update_mode
+        if mode == "auto":
+            mode = "sharded" if (self.world > 1 and self.env.device.type == "cuda") else "replicated"
+        sharded = mode == "sharded" and self.world > 1
+        batch = local if sharded else all_gather_rollout(local, self.world)
         if ev: ev[2].record()
-        m = self.update(batch)
+        m = self.update(batch, sharded=sharded)
         if ev:
             ev[3].record(); torch.cuda.synchronize()
             self.timing = {"rollout_ms": ev[0].elapsed_time(ev[1]), "gather_ms": ev[1].elapsed_time(ev[2]), "update_ms": ev[2].elapsed_time(ev[3])}
         self.env_steps += self.cfg.num_envs * self.cfg.unroll_length
-        m["reward_per_step"] = float(batch["reward"].mean())
+        m["reward_per_step"] = float(batch["reward"].mean())        # (this rank's shard in sharded mode)
         m["episode_done_rate"] = float(batch["done"].mean())
         return m
 
@@ -298,6 +386,6 @@ class PPOTrainer:
         self.policy.load_state_dict(params["policy"]); self.value.load_state_dict(params["value"]); self.opt.load_state_dict(params["optimizer"])
         for k, s in self.stats.items():
             d = params["normalizer"][k]
-            s.mean = d["mean"].double().to(self.env.device); s.std = d["std"].to(self.env.device); s.count = torch.tensor(d["count"], dtype=torch.float64, device=self.env.device)
+            s.mean = d["mean"].double().to(self.env.device); s.std.copy_(d["std"].to(self.env.device)); s.count = torch.tensor(d["count"], dtype=torch.float64, device=self.env.device)
             s.m2 = (s.std.double() ** 2) * s.count
         self.env_steps = int(params["env_steps"])
