@@ -564,6 +564,37 @@ static int build_dev_model(const OduckModel& M, DevModel& D, std::string& err) {
     }
     for (int k = M.nv; k <= 32; k++) D.chol_ofs[k] = cnt;
   }
+  {
+    // chain plan: root chain 0..nb-1 (each the parent of the next), every other dof in a pure chain attached to dof nb-1
+    int nb = 0;
+    while (nb < M.nv && M.dof_parentid[nb] == nb - 1 && (nb == 0 || true)) { nb++; if (nb < M.nv && M.dof_parentid[nb] != nb - 1) break; }
+    // nb = length of the initial run with parent(d) = d-1; the first branch shares that run, so cut it at the free joint's 6 dofs
+    D.plan_ok = 0;
+    const int NB6 = 6;
+    if (M.nv > NB6) {
+      bool ok = true;
+      for (int d2 = 1; d2 < NB6; d2++) ok = ok && M.dof_parentid[d2] == d2 - 1;
+      int starts[8], lens[8], nbr = 0;
+      for (int d2 = NB6; d2 < M.nv && ok; ) {
+        if (M.dof_parentid[d2] != NB6 - 1 || nbr >= 8) { ok = false; break; }
+        int len = 1;
+        while (d2 + len < M.nv && M.dof_parentid[d2 + len] == d2 + len - 1) len++;
+        starts[nbr] = d2; lens[nbr] = len; nbr++;
+        d2 += len;
+      }
+      if (ok && nbr == 3) {
+        // two equal branches (legs) + one single (head)
+        int a = -1, b = -1, c2 = -1;
+        if (lens[0] == lens[2]) { a = 0; b = 2; c2 = 1; } else if (lens[0] == lens[1]) { a = 0; b = 1; c2 = 2; } else if (lens[1] == lens[2]) { a = 1; b = 2; c2 = 0; }
+        if (a >= 0 && lens[c2] == 4 && (lens[a] == 10 || lens[a] == 5)) {
+          D.plan_ok = lens[a] == 10 ? 1 : 2;
+          D.plan_nbase = NB6; D.plan_pair_len = lens[a]; D.plan_pair_start[0] = starts[a]; D.plan_pair_start[1] = starts[b];
+          D.plan_single_len = lens[c2]; D.plan_single_start = starts[c2];
+        }
+      }
+    }
+    (void)nb;
+  }
   D.n_mpairs = 0;
   for (int i = 0; i < M.nv; i++)
     for (int j = i; j >= 0; j = M.dof_parentid[j]) D.mpair[D.n_mpairs++] = (unsigned short)((i << 8) | j);

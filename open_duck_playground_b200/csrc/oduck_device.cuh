@@ -74,6 +74,8 @@ struct DevModel {
   int d_depth[NLANE];
   int max_dof_depth;
   unsigned short pair_ab[512];   // p -> (a << 8 | b), b <= a, p = a (a + 1) / 2 + b
+  // chain plan of the factorisation: root chain of plan_nbase dofs + pure chains attached to its last dof
+  int plan_ok, plan_nbase, plan_pair_len, plan_pair_start[2], plan_single_len, plan_single_start;
   unsigned int chol_tab[1536];    // per pivot k, per ancestor pair: target | src_a << 10 | src_b << 20 (offsets into the packed triangle)
   int chol_ofs[NLANE + 1];
   unsigned short mpair[512];     // structural non-zeros of M: (i << 8 | j), j an ancestor of i or i itself
@@ -247,6 +249,96 @@ static __device__ __noinline__ void chol_rev(const DevModel& m, float* A, float*
   }
   __syncwarp();
 }
+
+// ---------------------------------------------------------------------------------- register-blocked chain factorisation
+// The dof tree of the duck is a root chain (the 6 free-joint dofs) with pure chains (left leg, head, right leg) attached to
+// its last dof.  Restricted to {root chain + one branch} the matrix is a dense lower triangle, so a branch is eliminated
+// leaf-to-root entirely in registers: lane = column (half-warp local), a[i] = entry (row i, own column); the rank-1 update of
+// pivot k is k shuffles + k FMAs.  The two equal-length legs run simultaneously in the two half-warps.  Each branch leaves
+// its Schur-complement contribution to the root block (accumulated from zero) in a[0..5]; the root block is finished last.
+// Same arithmetic as chol_rev(tree = true) up to summation order; rhs is swept leaf-to-root alongside.
+#define CH_NB 6
+template <int NLOC>
+__device__ __forceinline__ void branch_elim(float* H, float* rhs, const int lane, const int gstart, const bool store, float (&a)[NLOC], float& r) {
+  const int j = lane & 15, hb = lane & 16;
+  const int gj = j < CH_NB ? j : gstart + j - CH_NB;
+  const bool col = j < NLOC;
+#pragma unroll
+  for (int i = 0; i < NLOC; ++i) {
+    const int gi = i < CH_NB ? i : gstart + i - CH_NB;
+    a[i] = (i >= CH_NB && j <= i && col) ? H[TRI(gi) + gj] : 0.f;
+  }
+  r = (j >= CH_NB && col) ? rhs[gj] : 0.f;
+#pragma unroll
+  for (int k = NLOC - 1; k >= CH_NB; --k) {
+    const float akk = __shfl_sync(FULLMASK, a[k], hb | k);
+    const float inv = rsqrtf(akk);
+    const float lk = j < k ? a[k] * inv : 0.f;                 // L[k][j]
+    a[k] = j == k ? akk * inv : lk;
+    const float yk = __shfl_sync(FULLMASK, r, hb | k) * inv;
+    r = j == k ? yk : r - lk * yk;
+#pragma unroll
+    for (int i = 0; i < k; ++i) a[i] = fmaf(-__shfl_sync(FULLMASK, lk, hb | i), lk, a[i]);   // A[i][j] -= L[k][i] L[k][j]
+  }
+  if (store && col) {
+#pragma unroll
+    for (int i = CH_NB; i < NLOC; ++i)
+      if (j <= i) H[TRI(gstart + i - CH_NB) + gj] = a[i];
+    if (j >= CH_NB) rhs[gj] = r;
+  }
+}
+
+template <int NPAIR, int NSINGLE>   // branch lengths
+static __device__ __noinline__ void chol_rev_chain(const DevModel& m, float* H, float* rhs, const int lane) {
+  const int j = lane & 15;
+  float db[CH_NB], dr;
+  {
+    float a[CH_NB + NPAIR], r;
+    branch_elim<CH_NB + NPAIR>(H, rhs, lane, m.plan_pair_start[lane >> 4], true, a, r);
+#pragma unroll
+    for (int i = 0; i < CH_NB; ++i) db[i] = a[i] + __shfl_xor_sync(FULLMASK, a[i], 16);
+    dr = r + __shfl_xor_sync(FULLMASK, r, 16);
+  }
+  if (NSINGLE > 0) {
+    float a[CH_NB + (NSINGLE > 0 ? NSINGLE : 1)], r;
+    branch_elim<CH_NB + (NSINGLE > 0 ? NSINGLE : 1)>(H, rhs, lane, m.plan_single_start, lane < 16, a, r);   // both halves compute, half 0 stores
+#pragma unroll
+    for (int i = 0; i < CH_NB; ++i) db[i] += a[i];
+    dr += r;
+  }
+  __syncwarp();
+  // root block (pivots 5 .. 0): true entries + the branches' Schur complements
+  float b[CH_NB], rb = 0.f;
+#pragma unroll
+  for (int i = 0; i < CH_NB; ++i) b[i] = (j <= i && j < CH_NB) ? H[TRI(i) + j] + db[i] : 0.f;
+  if (j < CH_NB) rb = rhs[j] + dr;
+  const int hb = lane & 16;
+#pragma unroll
+  for (int k = CH_NB - 1; k >= 0; --k) {
+    const float akk = __shfl_sync(FULLMASK, b[k], hb | k);
+    const float inv = rsqrtf(akk);
+    const float lk = j < k ? b[k] * inv : 0.f;
+    b[k] = j == k ? akk * inv : lk;
+    const float yk = __shfl_sync(FULLMASK, rb, hb | k) * inv;
+    rb = j == k ? yk : rb - lk * yk;
+#pragma unroll
+    for (int i = 0; i < k; ++i) b[i] = fmaf(-__shfl_sync(FULLMASK, lk, hb | i), lk, b[i]);
+  }
+  if (lane < CH_NB) {
+#pragma unroll
+    for (int i = 0; i < CH_NB; ++i)
+      if (j <= i) H[TRI(i) + j] = b[i];
+    rhs[j] = rb;
+  }
+  __syncwarp();
+}
+// factorise + sweep: register-blocked chains when the model matches a compiled plan, else the generic pair-table version
+__device__ __forceinline__ void chol_rev_tree(const DevModel& m, float* H, float* rhs, int n, int lane) {
+  if (m.plan_ok == 1) chol_rev_chain<10, 4>(m, H, rhs, lane);
+  else if (m.plan_ok == 2) chol_rev_chain<5, 4>(m, H, rhs, lane);
+  else chol_rev(m, H, rhs, n, lane, true);
+}
+
 // Root-to-leaf sweep x <- L^-1 y with y one element per lane (y = rhs after chol_rev).  tree: all dofs of one depth level
 // are finished together (their ancestors are done), so the dependency chain is max_dof_depth long instead of n.
 static __device__ __noinline__ float chol_rev_back(const DevModel& m, const float* L, int n, int lane, float y, bool tree) {

@@ -230,7 +230,7 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
   for (int idx = lane; idx < TRI(nv); idx += 32) s.H[idx] = s.A[idx];
   s.rhs[lane] = fs;
   __syncwarp();
-  chol_rev(m, s.H, s.rhs, nv, lane, true);                                                  // factor_m + L^-T qfrc_smooth
+  chol_rev_tree(m, s.H, s.rhs, nv, lane);                                                   // factor_m + L^-T qfrc_smooth
   const float as = chol_rev_back(m, s.H, nv, lane, s.rhs[lane], true);                      // qacc_smooth
 
   // ------------------------------------------------------------------ collision: plane (z = 0) vs convex foot hulls (lane = vertex)
@@ -492,7 +492,8 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
     }
     s.rhs[lane] = grad;
     __syncwarp();
-    chol_rev(m, s.H, s.rhs, nv, lane, !(FF && ffact));
+    if (FF && ffact) chol_rev(m, s.H, s.rhs, nv, lane, false);
+    else chol_rev_tree(m, s.H, s.rhs, nv, lane);
     search = -chol_rev_back(m, s.H, nv, lane, s.rhs[lane], !(FF && ffact));
     if (lane >= nv) search = 0.f;
   }
