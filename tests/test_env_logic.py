@@ -134,3 +134,23 @@ def test_config_struct_mirrors_default_config(model_backlash, poly_table):
     assert list(c.qpos_noise_scale)[:14] == [0.03, 0.03, 0.03, 0.05, 0.08, 0.03, 0.03, 0.03, 0.05, 0.08, 0, 0, 0, 0]   # quirk #3
     assert c.scale_alive == 20.0 and c.scale_torques == -1e-3 and c.tracking_sigma == 0.01
     assert [list(r) for r in c.cmd_range][3] == [-0.34, 1.1]
+
+
+def test_single_env_headless_loop_config1(oracle):
+    """BASELINE configs[0]: flat_terrain, 1 env, CPU step loop (the mujoco_infer.py plumbing case): zero command,
+    fixed-seed random MLP policy, 500 control steps headless, no NaN, and the robot keeps a sane height under ctrl = home."""
+    from open_duck_playground_b200 import ppo
+    env = Joystick("flat_terrain", library=oracle, config_overrides={"noise_config.level": 0.0, "push_config.enable": False})
+    st = env.reset(jr.split(jr.PRNGKey(0), 1))
+    assert env.mj_model.nq == 21
+    for _ in range(50):                                      # ctrl = home for the first 50 steps
+        st = env.step(st, torch.zeros(1, 14))
+        assert 0.05 < float(st.data.qpos[0, 2]) < 0.25
+    torch.manual_seed(0)
+    pol = ppo.MLP([101, 512, 256, 128, 28])
+    w = ppo.PolicyWeights(pol, 101, env.device)
+    for _ in range(450):
+        act, _, _ = ppo.policy_forward(env, w, None, deterministic=True)
+        st = env.step(st, 0.2 * act)
+    assert torch.isfinite(st.obs["privileged_state"]).all() and torch.isfinite(st.data.qpos).all()
+    assert abs(float(st.data.qpos[0, 3:7].norm()) - 1) < 1e-9

@@ -304,3 +304,14 @@ def test_library_is_the_cuda_one():
     from open_duck_playground_b200 import capi
     lib = capi.load_cuda_library()
     assert lib.is_device and lib.path.endswith("csrc/liboduck_cuda.so")
+
+
+def test_single_env_and_odd_batch_sizes():
+    """N = 1 and N not a multiple of the 8-env CTA: the grid tail must not read or write out of bounds."""
+    for n in (1, 7, 33):
+        env = Joystick("flat_terrain", device="cuda:0")
+        st = env.reset(jr.split(jr.PRNGKey(n), n))
+        for _ in range(20):
+            st = env.step(st, torch.zeros(n, 14, device="cuda"))
+        assert torch.isfinite(st.obs["privileged_state"]).all() and st.obs["state"].shape == (n, 101)
+        assert ((st.data.qpos[:, 2] > 0.05) & (st.data.qpos[:, 2] < 0.25)).all()
