@@ -214,6 +214,10 @@ _cuda_lib: Optional[Library] = None
 
 
 def cuda_library_path() -> str:
+    """In-tree product library; ODUCK_CUDA_LIB points at another build of the same sources (kernel tuning, tools/variants.py)."""
+    override = os.environ.get("ODUCK_CUDA_LIB")
+    if override:
+        return override
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "liboduck_cuda.so")
 
 

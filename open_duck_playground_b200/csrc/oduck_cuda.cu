@@ -13,7 +13,18 @@
 #include "../../include/oduck.h"
 #include "oduck_env.cuh"
 
+#ifndef WPB
 #define WPB 8   // warps (= envs in flight) per CTA
+#endif
+#define CTAS_PER_SM (WPB <= 8 ? 2 : 1)
+// Thread ids behind an opaque move: ptxas otherwise rematerialises lane / warp / the warp's smem base (S2R + shifts + IMAD)
+// dozens of times per substep instead of keeping them in registers.
+__device__ __forceinline__ int opaque(int x) {
+#ifdef ODUCK_OPAQUE_IDS
+  asm volatile("mov.b32 %0, %0;" : "+r"(x));
+#endif
+  return x;
+}
 
 static thread_local std::string g_err;
 int oduck_fail(int code, const std::string& msg) { g_err = msg; return code; }   // shared with oduck_policy.cu
@@ -75,7 +86,7 @@ __device__ __forceinline__ void store_out(const WarpSmem& s, int lane, float* __
 // ------------------------------------------------------------------------------------------------- kernels
 // A8 / A9 of SURVEY 8a: n x (forward + euler), or one forward without integration (mjx_env.init's forward).
 template <bool DBG>
-__global__ void __launch_bounds__(WPB * 32, 2) k_physics(Params p) {
+__global__ void __launch_bounds__(WPB * 32, CTAS_PER_SM) k_physics(Params p) {
   extern __shared__ __align__(16) unsigned char raw[];
   DevModel* mp; DevEnvCfg* cp; WarpSmem* ws;
   block_load_tables(p, raw, mp, cp, ws);
@@ -146,7 +157,7 @@ __device__ __forceinline__ float feet_contact(const WarpSmem& s, int lane) {   /
 }
 
 // A2 (+A9, first_state store): Joystick.reset for the masked envs.
-__global__ void __launch_bounds__(WPB * 32, 2) k_reset(Params p) {
+__global__ void __launch_bounds__(WPB * 32, CTAS_PER_SM) k_reset(Params p) {
   extern __shared__ __align__(16) unsigned char raw[];
   DevModel* mp; DevEnvCfg* cp; WarpSmem* ws;
   block_load_tables(p, raw, mp, cp, ws);
@@ -240,16 +251,18 @@ __global__ void __launch_bounds__(WPB * 32, 2) k_reset(Params p) {
 }
 
 // A1 + A16: Joystick.step fused with EpisodeWrapper + AutoResetWrapper.
-__global__ void __launch_bounds__(WPB * 32, 2) k_step(Params p) {
+__global__ void __launch_bounds__(WPB * 32, CTAS_PER_SM) k_step(Params p) {
   extern __shared__ __align__(16) unsigned char raw[];
   DevModel* mp; DevEnvCfg* cp; WarpSmem* ws;
   block_load_tables(p, raw, mp, cp, ws);
   const DevModel& m = *mp;
   const DevEnvCfg& c = *cp;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = opaque(threadIdx.x >> 5), lane = opaque(threadIdx.x & 31);
   WarpSmem& s = ws[warp];
   const float PI = 3.14159265358979323846f;
-  for (int env = blockIdx.x * WPB + warp; env < p.N; env += gridDim.x * WPB) {
+  for (int env0 = blockIdx.x * WPB; env0 < p.N; env0 += gridDim.x * WPB) {
+    const int env = env0 + warp;
+    if (env >= p.N) { substep_idle_barriers(c.n_substeps); continue; }   // the CTA's other warps synchronise inside the substeps
     Lane L;
     float* ph = p.phys + (size_t)env * PHYS_STRIDE;
     load_env(m, s, L, lane, ph, p.dr + (size_t)env * DR_STRIDE);
@@ -295,7 +308,8 @@ __global__ void __launch_bounds__(WPB * 32, 2) k_step(Params p) {
     if (c.use_speed_limits) { const float lim = c.max_motor_velocity * dt; tgt = fminf(fmaxf(tgt, er.targets - lim), er.targets + lim); }
     { const int a = m.d_act[lane]; const float t = __shfl_sync(FULLMASK, tgt, a < 0 ? 0 : a); if (a >= 0) L.ctrl = t; }
     // physics: n_substeps x mjx.step (joystick.py:420)
-    for (int k = 0; k < c.n_substeps; ++k) forward_euler<false>(m, s, L, lane, k == c.n_substeps - 1, true, s.outrec, nullptr, p.ffmodel, p.ffscratch + (size_t)env * (FFJ_SIZE + FFV_SIZE));
+    for (int k = 0; k < c.n_substeps; ++k)
+      forward_euler<false, true>(m, s, L, lane, k == c.n_substeps - 1, true, s.outrec, nullptr, p.ffmodel, p.ffscratch + (size_t)env * (FFJ_SIZE + FFV_SIZE));
     __syncwarp();
     er.targets = tgt;
     // contacts / air time / swing peak (joystick.py:424-435)
@@ -393,7 +407,7 @@ __global__ void __launch_bounds__(WPB * 32, 2) k_step(Params p) {
 }
 
 // A14: domain_randomize (common/randomize.py:39-106), one warp per env, one round per split.
-__global__ void __launch_bounds__(WPB * 32, 2) k_randomize(Params p) {
+__global__ void __launch_bounds__(WPB * 32, CTAS_PER_SM) k_randomize(Params p) {
   extern __shared__ __align__(16) unsigned char raw[];
   DevModel* mp; DevEnvCfg* cp; WarpSmem* ws;
   block_load_tables(p, raw, mp, cp, ws);

@@ -14,8 +14,7 @@
 #define FULLMASK 0xffffffffu
 #define NLANE 32
 #define TRI(i) (((i) * ((i) + 1)) >> 1)
-#define JROWS 24          // 8 foot-floor contacts x (normal, tangent1, tangent2)
-#define JSTRIDE 33
+#define CON_STRIDE 16     // floats per contact record in shared memory
 #define NCON_FLOOR 8
 #define NCON_ALL 12
 
@@ -87,13 +86,15 @@ struct DevModel {
 struct WarpSmem {
   float A[528];               // M, packed lower
   float H[528];               // chol(M), then H = M + J^T D J and its factor
-  float J[JROWS][JSTRIDE];    // contact Jacobian rows (frame-rotated point Jacobians)
+  float bf[8][NLANE];         // staging: crb[body_i] * cdof_i and armature for the M pair pass
   float xpos[3][NLANE];
   float xmat[9][NLANE];
   float cdof[6][NLANE];
   float qpos[36];
   float qpos0[36];
-  float con[NCON_ALL][8];     // dist, pos xyz, F(n,t1,t2), pad
+  // contact records, read back as float4 broadcasts: [0] dist, [1..3] pos | [4..6] force (n, t1, t2) | [8..12] Hessian
+  // weights (nn, n1, n2, 11, 22) of the contact in its own frame
+  float con[NCON_ALL][CON_STRIDE];
   float misc[64];
   float rhs[NLANE];            // right-hand side swept leaf-to-root inside chol_rev
   float outrec[OUT_STRIDE];     // staged outputs of the last forward (copied to HBM once per launch)
@@ -104,6 +105,38 @@ __device__ __forceinline__ float wsum(float v) {
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
   return v;
 }
+// Sums of K lane-local values over the warp with a folding butterfly: at every level a lane keeps the values whose index
+// bit matches its lane bit and sends the others, so K values cost about K + 3 shuffles instead of 5 K.  Every lane ends up
+// with the total of value number (lane & (P - 1)), P = K rounded up to a power of two; read value k with wfold_get(t, k).
+template <int N, int BIT>
+struct WFold {
+  static __device__ __forceinline__ float run(float* v, const int lane) {
+    if constexpr (BIT >= 32) {
+      return v[0];
+    } else if constexpr (N == 1) {
+      v[0] += __shfl_xor_sync(FULLMASK, v[0], BIT);
+      return WFold<1, BIT * 2>::run(v, lane);
+    } else {
+      const bool up = (lane & BIT) != 0;
+#pragma unroll
+      for (int k = 0; k < N / 2; ++k) {
+        const float keep = up ? v[2 * k + 1] : v[2 * k];
+        const float send = up ? v[2 * k] : v[2 * k + 1];
+        v[k] = keep + __shfl_xor_sync(FULLMASK, send, BIT);
+      }
+      if constexpr (N & 1) {   // unpaired value: its partner is an implicit zero
+        const float x = v[N - 1];
+        v[N / 2] = (up ? 0.f : x) + __shfl_xor_sync(FULLMASK, up ? x : 0.f, BIT);
+      }
+      return WFold<(N + 1) / 2, BIT * 2>::run(v, lane);
+    }
+  }
+};
+template <int K>
+__device__ __forceinline__ float wfold(float (&v)[K], const int lane) { return WFold<K, 1>::run(v, lane); }
+__device__ __forceinline__ float wfold_get(const float t, const int k) { return __shfl_sync(FULLMASK, t, k); }
+__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
 __device__ __forceinline__ float wmaxf(float v) {
 #pragma unroll
   for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULLMASK, v, o));
@@ -374,14 +407,6 @@ static __device__ __noinline__ float symv(const float* A, int n, int lane, float
   }
   return lane < n ? acc : 0.f;
 }
-// products of the contact rows with a dof vector: lane r gets J[r] . x
-static __device__ __noinline__ float jdot(const float (*J)[JSTRIDE], int n, int lane, float x) {
-  float acc = 0.f;
-  const float* row = J[lane < JROWS ? lane : 0];
-  for (int d = 0; d < n; ++d) acc = fmaf(row[d], __shfl_sync(FULLMASK, x, d), acc);
-  return lane < JROWS ? acc : 0.f;
-}
-
 // constraint.py _kbi impedance for a signed distance
 __device__ __forceinline__ float impedance(const DevModel& m, float pos) {
   float x = fabsf(pos) / m.width;

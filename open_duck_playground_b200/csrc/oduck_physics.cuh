@@ -13,15 +13,29 @@ struct Lane {
   V3 ipos;
 };
 
-struct LSPoint { float alpha, cost, d0, d1; };
+struct LSPoint { float alpha, d0, d1; };
 
 // FF = false: no foot-foot code is compiled in; if the feet's bounding spheres overlap the function returns true BEFORE
 // touching any persistent state and the caller re-runs the substep with FF = true (rare).
-template <bool DBG, bool FF>
+// BAR = true (k_step): CTA barriers at the phase boundaries selected by ODUCK_BARRIERS keep the CTA's warps on the same
+// stretch of this ~200 KB instruction stream, so that they share instruction-cache lines instead of each streaming the code
+// from L2 (measured: -15 % kernel time with one barrier per substep).  Every warp of the CTA must execute the same number of
+// barriers: points before the foot-foot early exit exist only in the FF = false instantiation (the FF = true re-run skips
+// them), points after it exist in both; warps without an env call substep_idle_barriers().
+#ifndef ODUCK_BARRIERS
+#define ODUCK_BARRIERS 0x01
+#endif
+#define PHASE_SYNC(bit, pre_exit) { if (BAR && ((ODUCK_BARRIERS >> (bit)) & 1) && (!(pre_exit) || !FF)) __syncthreads(); }
+__device__ __forceinline__ void substep_idle_barriers(int substeps) {
+  for (int k = 0; k < substeps * __popc(ODUCK_BARRIERS & 0x3f); ++k) __syncthreads();
+}
+
+template <bool DBG, bool FF, bool BAR>
 __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& s, Lane& L, const int lane, const bool last,
                                               const bool integrate, float* __restrict__ out, float* __restrict__ dbg,
                                               const DevFF* __restrict__ ffm, float* __restrict__ ffs) {
   const int nv = m.nv, nb = m.nbody;
+  PHASE_SYNC(0, true)
   // ------------------------------------------------------------------ kinematics (lane = body)
   // local transform of every body at once (joint rotations do not depend on the parents), then log2(depth) rounds of
   // pointer jumping compose them into world poses: X_world[b] = X_world[parent] o T_b is an associative prefix product.
@@ -158,7 +172,7 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
     GET(xx) GET(yy) GET(zz) GET(xy) GET(xz) GET(yz) GET(hx) GET(hy) GET(hz) GET(m)
 #undef GET
     const S6 buf = inert_mul(cb, cd);                                   // crb[body_i] * cdof_i, staged for the pair pass
-    float (*bf)[NLANE] = reinterpret_cast<float (*)[NLANE]>(&s.J[0][0]); // J is not live yet
+    float (*bf)[NLANE] = s.bf;
     bf[0][lane] = buf.a0; bf[1][lane] = buf.a1; bf[2][lane] = buf.a2; bf[3][lane] = buf.l0; bf[4][lane] = buf.l1; bf[5][lane] = buf.l2;
     bf[6][lane] = L.arm;
     __syncwarp();
@@ -172,6 +186,7 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
     }
   }
   __syncwarp();
+  PHASE_SYNC(1, true)
   // ------------------------------------------------------------------ com_vel: prefix sums over the dof tree (lane = dof)
   const int dpar = m.d_parent[lane];
   S6 Sv = lane < nv ? s6scale(cd, L.qvel) : s6zero();
@@ -233,6 +248,7 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
   chol_rev_tree(m, s.H, s.rhs, nv, lane);                                                   // factor_m + L^-T qfrc_smooth
   const float as = chol_rev_back(m, s.H, nv, lane, s.rhs[lane], true);                      // qacc_smooth
 
+  PHASE_SYNC(2, true)
   // ------------------------------------------------------------------ collision: plane (z = 0) vs convex foot hulls (lane = vertex)
   for (int f = 0; f < 2; ++f) {
     const int fb = m.foot_body[f];
@@ -289,19 +305,12 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
     else if (ff_maybe_close(m, ffm, s, lane)) return true;
   }
 
-  // ------------------------------------------------------------------ contact Jacobian rows (lane = dof): frame = [n=+z, t1=+y, t2=-x]
-  for (int c = 0; c < NCON_FLOOR; ++c) {
-    const float dist = s.con[c][0];
-    float jn = 0.f, jt1 = 0.f, jt2 = 0.f;
-    if (dist < 0.f && ((m.foot_chain[c >> 2] >> lane) & 1)) {
-      V3 off = v3(s.con[c][1], s.con[c][2], s.con[c][3]) - com;
-      V3 jp = v3(cd.l0, cd.l1, cd.l2) + cross(v3(cd.a0, cd.a1, cd.a2), off);
-      jn = jp.z; jt1 = jp.y; jt2 = -jp.x;
-    }
-    s.J[3 * c][lane] = jn; s.J[3 * c + 1][lane] = jt1; s.J[3 * c + 2][lane] = jt2;
-  }
-  __syncwarp();
-
+  // ------------------------------------------------------------------ foot-floor contact Jacobians, implicit
+  // A floor contact c of foot f has the point Jacobian jp_i(c) = lin_i + ang_i x (pos_c - com) for the dofs i of the foot's
+  // chain (cdof_i = [ang_i; lin_i]), rows (n, t1, t2) = (+z, +y, -x) . jp.  The rows are never stored: J x is the foot's
+  // spatial velocity sum_i cdof_i x_i (one folded warp reduction for both feet) evaluated at the contact point, and J^T f /
+  // J^T D J are accumulated per dof lane from the contact records (see the gradient + Hessian phase).
+  const bool inF0 = (m.foot_chain[0] >> lane) & 1, inF1 = (m.foot_chain[1] >> lane) & 1;
   // ------------------------------------------------------------------ constraint rows
   // dof lane: friction-loss row and joint-limit row; contact lane c < 8: four pyramid rows
   const bool hasf = (flags & DF_FLOSS) != 0;
@@ -327,10 +336,22 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
   const float cdist = s.con[cl][0];
   const bool cact = lane < NCON_ALL && cdist < 0.f;
   const float mu = cl < NCON_FLOOR ? m.floor_mu : m.foot_mu;
+  const V3 coff = v3(s.con[cs][1], s.con[cs][2], s.con[cs][3]) - com;     // contact lane: its point relative to the com
+  // rows (n, t1, t2) of this lane's floor contact applied to the foot's spatial vector [a; l]
+#define POINT_ROWS(a_, l_, pn_, p1_, p2_)                                                                               \
+  {                                                                                                                    \
+    const V3 jp_ = (l_) + cross((a_), coff);                                                                           \
+    pn_ = jp_.z; p1_ = jp_.y; p2_ = -jp_.x;                                                                            \
+  }
   float Dc = 0.f, arefc[4] = {0.f, 0.f, 0.f, 0.f};
   {
-    const float pr = jdot(s.J, nv, lane, L.qvel);
-    float pn = __shfl_sync(FULLMASK, pr, 3 * cs), pt1 = __shfl_sync(FULLMASK, pr, 3 * cs + 1), pt2 = __shfl_sync(FULLMASK, pr, 3 * cs + 2);
+    // J qvel = velocity of the contact point: the foot body's cvel (com_vel prefix sums) at the point
+    float pn, pt1, pt2;
+    {
+      const int fb = m.foot_body[cs >> 2];
+      const S6 fv = s6shfl(cvel, fb);
+      POINT_ROWS(v3(fv.a0, fv.a1, fv.a2), v3(fv.l0, fv.l1, fv.l2), pn, pt1, pt2)
+    }
     if (FF && ffact) {
       const float pf = ffdot(ffJ, nv, lane, L.qvel);
       const float fn = __shfl_sync(FULLMASK, pf, 3 * cf), f1 = __shfl_sync(FULLMASK, pf, 3 * cf + 1), f2 = __shfl_sync(FULLMASK, pf, 3 * cf + 2);
@@ -351,8 +372,18 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
   // J x for the four pyramid rows of this lane's contact
 #define CONTACT_PRODUCTS(x, o)                                                                                         \
   {                                                                                                                    \
-    const float pr_ = jdot(s.J, nv, lane, (x));                                                                        \
-    float pn_ = __shfl_sync(FULLMASK, pr_, 3 * cs), p1_ = __shfl_sync(FULLMASK, pr_, 3 * cs + 1), p2_ = __shfl_sync(FULLMASK, pr_, 3 * cs + 2); \
+    float sv_[12];                                                                                                     \
+    {                                                                                                                  \
+      const float x0_ = inF0 ? (x) : 0.f, x1_ = inF1 ? (x) : 0.f;                                                      \
+      sv_[0] = cd.a0 * x0_; sv_[1] = cd.a1 * x0_; sv_[2] = cd.a2 * x0_; sv_[3] = cd.l0 * x0_; sv_[4] = cd.l1 * x0_; sv_[5] = cd.l2 * x0_; \
+      sv_[6] = cd.a0 * x1_; sv_[7] = cd.a1 * x1_; sv_[8] = cd.a2 * x1_; sv_[9] = cd.l0 * x1_; sv_[10] = cd.l1 * x1_; sv_[11] = cd.l2 * x1_; \
+    }                                                                                                                  \
+    const float st_ = wfold<12>(sv_, lane);                                                                            \
+    const int fo_ = 6 * (cs >> 2);                                                                                     \
+    const V3 fa_ = v3(wfold_get(st_, fo_), wfold_get(st_, fo_ + 1), wfold_get(st_, fo_ + 2));                           \
+    const V3 fl_ = v3(wfold_get(st_, fo_ + 3), wfold_get(st_, fo_ + 4), wfold_get(st_, fo_ + 5));                       \
+    float pn_, p1_, p2_;                                                                                               \
+    POINT_ROWS(fa_, fl_, pn_, p1_, p2_)                                                                                \
     if (FF && ffact) {                                                                                                 \
       const float pf_ = ffdot(ffJ, nv, lane, (x));                                                                     \
       const float fn_ = __shfl_sync(FULLMASK, pf_, 3 * cf), f1_ = __shfl_sync(FULLMASK, pf_, 3 * cf + 1), f2_ = __shfl_sync(FULLMASK, pf_, 3 * cf + 2); \
@@ -401,6 +432,7 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
     gauss = usew ? gw : 0.f;
     if (DBG && lane == 0) { dbg[2536] = costw; dbg[2537] = costs; }
   }
+  PHASE_SYNC(3, false)
   // ------------------------------------------------------------------ gradient + Hessian + Newton direction
   float search, grad;
   {
@@ -414,20 +446,45 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
     float fc[4]; bool ca[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) { ca[r] = cact && Jc[r] < 0.f; fc[r] = ca[r] ? -Dc * Jc[r] : 0.f; }
-    if (lane < NCON_ALL) {
-      float* cc = s.con[lane];
-      cc[4] = fc[0] + fc[1] + fc[2] + fc[3];
-      cc[5] = mu * (fc[0] - fc[1]);
-      cc[6] = mu * (fc[2] - fc[3]);
+    {
+      // contact record: force and Hessian weights of this lane's contact in its (n, t1, t2) frame
+      const float a0 = ca[0], a1 = ca[1], a2 = ca[2], a3 = ca[3];
+      if (lane < NCON_ALL) {
+        float* cc = s.con[lane];
+        cc[4] = fc[0] + fc[1] + fc[2] + fc[3];
+        cc[5] = mu * (fc[0] - fc[1]);
+        cc[6] = mu * (fc[2] - fc[3]);
+        cc[8] = Dc * (a0 + a1 + a2 + a3);
+        cc[9] = Dc * mu * (a0 - a1);
+        cc[10] = Dc * mu * (a2 - a3);
+        cc[11] = Dc * mu * mu * (a0 + a1);
+        cc[12] = Dc * mu * mu * (a2 + a3);
+      }
     }
-    // Hessian weights of this contact in (n, t1, t2) coordinates
-    const float a0 = ca[0], a1 = ca[1], a2 = ca[2], a3 = ca[3];
-    const float Wnn = Dc * (a0 + a1 + a2 + a3), Wn1 = Dc * mu * (a0 - a1), Wn2 = Dc * mu * (a2 - a3);
-    const float W11 = Dc * mu * mu * (a0 + a1), W22 = Dc * mu * mu * (a2 + a3);
     __syncwarp();
+    // J^T f and z_i = sum_c T_c^T W_c jp_i(c) (a wrench per dof lane): H_ij += z_i . cdof_j for j ancestor-or-self of i
     float qfc = ff + lsign * fl;
-    for (int c = 0; c < NCON_FLOOR; ++c) {
-      if (s.con[c][0] < 0.f) qfc += s.J[3 * c][lane] * s.con[c][4] + s.J[3 * c + 1][lane] * s.con[c][5] + s.J[3 * c + 2][lane] * s.con[c][6];
+    S6 z = s6zero();
+    bool anyc = false;
+    {
+      const V3 ang = v3(cd.a0, cd.a1, cd.a2), lin = v3(cd.l0, cd.l1, cd.l2);
+#pragma unroll 1
+      for (int c = 0; c < NCON_FLOOR; ++c) {
+        const float4 r0 = lds4(&s.con[c][0]);
+        if (!(r0.x < 0.f)) continue;                                        // warp-uniform
+        anyc = true;
+        const float4 r1 = lds4(&s.con[c][4]), r2 = lds4(&s.con[c][8]);
+        const float w22 = s.con[c][12];
+        const V3 off = v3(r0.y, r0.z, r0.w) - com;
+        V3 jp = lin + cross(ang, off);
+        if (!(c < 4 ? inF0 : inF1)) jp = v3(0.f, 0.f, 0.f);
+        const float jn = jp.z, j1 = jp.y, j2 = -jp.x;
+        qfc += jn * r1.x + j1 * r1.y + j2 * r1.z;
+        const float un = r2.x * jn + r2.y * j1 + r2.z * j2, u1 = r2.y * jn + r2.w * j1, u2 = r2.z * jn + w22 * j2;
+        const V3 U = v3(-u2, u1, un);                                       // back to world axes
+        const V3 oxU = cross(off, U);
+        z.a0 += oxU.x; z.a1 += oxU.y; z.a2 += oxU.z; z.l0 += U.x; z.l1 += U.y; z.l2 += U.z;
+      }
     }
     if (FF && ffact) {
       for (int c = 0; c < 4; ++c)
@@ -439,31 +496,16 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
     for (int idx = lane; idx < TRI(nv); idx += 32) s.H[idx] = s.A[idx];
     __syncwarp();
     if (lane < nv) s.H[TRI(lane) + lane] += (fquad ? Df : 0.f) + (lon ? Dl : 0.f);
-    for (int f = 0; f < 2; ++f) {
-      const bool any = (s.con[4 * f][0] < 0.f) || (s.con[4 * f + 1][0] < 0.f) || (s.con[4 * f + 2][0] < 0.f) || (s.con[4 * f + 3][0] < 0.f);
-      if (!any) continue;
-      float Zn[4], Z1[4], Z2[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int cc = 4 * f + c;
-        const float wnn = __shfl_sync(FULLMASK, Wnn, cc), wn1 = __shfl_sync(FULLMASK, Wn1, cc), wn2 = __shfl_sync(FULLMASK, Wn2, cc);
-        const float w11 = __shfl_sync(FULLMASK, W11, cc), w22 = __shfl_sync(FULLMASK, W22, cc);
-        const float jn = s.J[3 * cc][lane], j1 = s.J[3 * cc + 1][lane], j2 = s.J[3 * cc + 2][lane];
-        Zn[c] = wnn * jn + wn1 * j1 + wn2 * j2;
-        Z1[c] = wn1 * jn + w11 * j1;
-        Z2[c] = wn2 * jn + w22 * j2;
-      }
-      const int chain = m.foot_chain[f];
-      const int ri = TRI(lane);
-      for (int j = 0; j < nv; ++j) {
-        if (!((chain >> j) & 1)) continue;
-        float acc = 0.f;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int cc = 4 * f + c;
-          acc += Zn[c] * s.J[3 * cc][j] + Z1[c] * s.J[3 * cc + 1][j] + Z2[c] * s.J[3 * cc + 2][j];
+    if (anyc) {
+      const int dep = lane < nv ? m.d_depth[lane] : -1;
+      const unsigned char* al = m.anc[lane];
+      float* Hi = s.H + TRI(lane);
+#pragma unroll 1
+      for (int lev = 0; lev <= m.max_dof_depth; ++lev) {
+        if (lev <= dep) {
+          const int j = lev < dep ? al[lev] : lane;
+          Hi[j] += z.a0 * s.cdof[0][j] + z.a1 * s.cdof[1][j] + z.a2 * s.cdof[2][j] + z.l0 * s.cdof[3][j] + z.l1 * s.cdof[4][j] + z.l2 * s.cdof[5][j];
         }
-        if (j <= lane && lane < nv) s.H[ri + j] += acc;
       }
     }
     if (FF && ffact) {
@@ -471,9 +513,8 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
       float Zn[4], Z1[4], Z2[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const int cc = NCON_FLOOR + c;
-        const float wnn = __shfl_sync(FULLMASK, Wnn, cc), wn1 = __shfl_sync(FULLMASK, Wn1, cc), wn2 = __shfl_sync(FULLMASK, Wn2, cc);
-        const float w11 = __shfl_sync(FULLMASK, W11, cc), w22 = __shfl_sync(FULLMASK, W22, cc);
+        const float* cc = s.con[NCON_FLOOR + c];
+        const float wnn = cc[8], wn1 = cc[9], wn2 = cc[10], w11 = cc[11], w22 = cc[12];
         const float jn = ffJ[(3 * c) * 32 + lane], j1 = ffJ[(3 * c + 1) * 32 + lane], j2 = ffJ[(3 * c + 2) * 32 + lane];
         Zn[c] = wnn * jn + wn1 * j1 + wn2 * j2;
         Z1[c] = wn1 * jn + w11 * j1;
@@ -497,45 +538,76 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
     search = -chol_rev_back(m, s.H, nv, lane, s.rhs[lane], !(FF && ffact));
     if (lane >= nv) search = 0.f;
   }
+  PHASE_SYNC(4, false)
   // ------------------------------------------------------------------ line search (solver.py _linesearch)
+  // Along qacc + alpha search the cost is piecewise quadratic; a trial point needs its slope d0 and curvature d1 (sums over
+  // the rows that are active AT alpha).  The three trial points of an iteration are evaluated lane-locally and their six
+  // sums folded in one butterfly (wfold); costs are only needed to choose between the final bracket ends and the start.
   {
     const float Mv = symv(s.A, nv, lane, search);
     float jvc[4];
     CONTACT_PRODUCTS(search, jvc)
     const float jvf = search, jvl = lsign * search;
-    const float snorm = sqrtf(wsum(search * search));
+    float snorm, qg1, qg2;
+    {
+      float g[3] = {search * search, search * (Ma - fs), search * Mv};
+      const float t = wfold<3>(g, lane);
+      snorm = sqrtf(wfold_get(t, 0)); qg1 = wfold_get(t, 1); qg2 = 0.5f * wfold_get(t, 2);
+    }
     const float gtol = m.tolerance * m.ls_tolerance * snorm * m.meaninertia * (float)max(1, nv);
     const float qg0 = gauss;
-    const float qg1 = wsum(search * (Ma - fs));
-    const float qg2 = 0.5f * wsum(search * Mv);
-    auto point = [&](float alpha) {
+    // per-row polynomial pieces (zero for rows this lane does not have)
+    const float Dfe = hasf ? Df : 0.f;
+    const float fq1 = Dfe * jvf * Jf, fq2 = Dfe * jvf * jvf, flin = hasf ? floss * jvf : 0.f;
+    const float lq1 = Dl * jvl * Jl, lq2 = Dl * jvl * jvl;
+    float cq1[4], cq2[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { cq1[r] = Dc * jvc[r] * Jc[r]; cq2[r] = Dc * jvc[r] * jvc[r]; }
+    // lane-local slope and curvature at alpha
+    auto slope = [&](const float alpha, float& d0, float& d1) {
+      const float x = Jf + alpha * jvf;
+      const bool quad = hasf && x > -rf && x < rf;
+      d0 = quad ? fmaf(alpha, fq2, fq1) : (x >= rf ? flin : -flin);
+      d1 = quad ? fq2 : 0.f;
+      if (Jl + alpha * jvl < 0.f) { d0 += fmaf(alpha, lq2, lq1); d1 += lq2; }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (Jc[r] + alpha * jvc[r] < 0.f) { d0 += fmaf(alpha, cq2[r], cq1[r]); d1 += cq2[r]; }
+    };
+    // lane-local cost at alpha
+    auto cost = [&](const float alpha) {
       float q0 = 0.f, q1 = 0.f, q2 = 0.f;
       if (hasf) {
         const float x = Jf + alpha * jvf;
-        if (x <= -rf) { q0 += floss * (-0.5f * rf - Jf); q1 += -floss * jvf; }
-        else if (x >= rf) { q0 += floss * (-0.5f * rf + Jf); q1 += floss * jvf; }
-        else { q0 += 0.5f * Df * Jf * Jf; q1 += Df * jvf * Jf; q2 += 0.5f * Df * jvf * jvf; }
+        if (x <= -rf) { q0 = floss * (-0.5f * rf - Jf); q1 = -flin; }
+        else if (x >= rf) { q0 = floss * (-0.5f * rf + Jf); q1 = flin; }
+        else { q0 = 0.5f * Df * Jf * Jf; q1 = fq1; q2 = 0.5f * fq2; }
       }
-      if (lact && (Jl + alpha * jvl) < 0.f) { q0 += 0.5f * Dl * Jl * Jl; q1 += Dl * jvl * Jl; q2 += 0.5f * Dl * jvl * jvl; }
-      if (cact) {
+      if (Jl + alpha * jvl < 0.f) { q0 += 0.5f * Dl * Jl * Jl; q1 += lq1; q2 += 0.5f * lq2; }
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
-          if (Jc[r] + alpha * jvc[r] < 0.f) { q0 += 0.5f * Dc * Jc[r] * Jc[r]; q1 += Dc * jvc[r] * Jc[r]; q2 += 0.5f * Dc * jvc[r] * jvc[r]; }
-      }
-      q0 = wsum(q0) + qg0; q1 = wsum(q1) + qg1; q2 = wsum(q2) + qg2;
-      LSPoint p;
-      p.alpha = alpha;
-      p.cost = alpha * alpha * q2 + alpha * q1 + q0;
-      p.d0 = 2.f * alpha * q2 + q1;
-      p.d1 = 2.f * q2 + (q2 == 0.f ? 1e-15f : 0.f);
-      return p;
+      for (int r = 0; r < 4; ++r)
+        if (Jc[r] + alpha * jvc[r] < 0.f) { q0 += 0.5f * Dc * Jc[r] * Jc[r]; q1 += cq1[r]; q2 += 0.5f * cq2[r]; }
+      return fmaf(alpha, fmaf(alpha, q2, q1), q0);
     };
+#define LS_FINISH(pt, sd0, sd1)                                                                                        \
+  {                                                                                                                    \
+    (pt).d0 = (sd0) + qg1 + 2.f * (pt).alpha * qg2;                                                                    \
+    const float c_ = (sd1) + 2.f * qg2;                                                                                \
+    (pt).d1 = c_ + (c_ == 0.f ? 1e-15f : 0.f);                                                                         \
+  }
     LSPoint p0, lo, hi;
     {
       LSPoint ini[2];
       float a_ = 0.f;
 #pragma unroll 1
-      for (int q = 0; q < 2; ++q) { ini[q] = point(a_); a_ = ini[0].alpha - ini[0].d0 / ini[0].d1; }
+      for (int q = 0; q < 2; ++q) {
+        float v[2];
+        slope(a_, v[0], v[1]);
+        const float t = wfold<2>(v, lane);
+        ini[q].alpha = a_;
+        LS_FINISH(ini[q], wfold_get(t, 0), wfold_get(t, 1))
+        a_ = ini[0].alpha - ini[0].d0 / ini[0].d1;
+      }
       p0 = ini[0]; lo = ini[1];
     }
     if (lo.d0 < p0.d0) { hi = p0; } else { hi = lo; lo = p0; }
@@ -547,11 +619,18 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
       done |= (lo.d0 < 0.f) && (lo.d0 > -gtol);
       done |= (hi.d0 > 0.f) && (hi.d0 < gtol);
       if (done) break;
-      LSPoint cand[3];
-      const float al[3] = {lo.alpha - lo.d0 / lo.d1, 0.5f * (lo.alpha + hi.alpha), hi.alpha - hi.d0 / hi.d1};
-#pragma unroll 1
-      for (int q = 0; q < 3; ++q) cand[q] = point(al[q]);
-      const LSPoint lo_next = cand[0], mid = cand[1], hi_next = cand[2];
+      LSPoint lo_next, mid, hi_next;
+      lo_next.alpha = lo.alpha - lo.d0 / lo.d1; mid.alpha = 0.5f * (lo.alpha + hi.alpha); hi_next.alpha = hi.alpha - hi.d0 / hi.d1;
+      {
+        float v[6];
+        slope(lo_next.alpha, v[0], v[1]);
+        slope(mid.alpha, v[2], v[3]);
+        slope(hi_next.alpha, v[4], v[5]);
+        const float t = wfold<6>(v, lane);
+        LS_FINISH(lo_next, wfold_get(t, 0), wfold_get(t, 1))
+        LS_FINISH(mid, wfold_get(t, 2), wfold_get(t, 3))
+        LS_FINISH(hi_next, wfold_get(t, 4), wfold_get(t, 5))
+      }
       // Bracket update (oracle/oduck_oracle.cpp linesearch has the rationale): a candidate becomes the new lo if its slope is
       // negative and (lo sits on the wrong side of the root or the candidate is closer to it); symmetrically for hi.
       swap = false;
@@ -563,8 +642,17 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
 #undef TRY_HI
       ++it;
     }
-    const bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
-    const float alpha = improved ? (lo.cost < hi.cost ? lo.alpha : hi.alpha) : 0.f;
+#undef LS_FINISH
+    float alpha;
+    {
+      float v[3] = {cost(lo.alpha), cost(hi.alpha), cost(0.f)};
+      const float t = wfold<3>(v, lane);
+      const float clo = wfold_get(t, 0) + fmaf(lo.alpha, fmaf(lo.alpha, qg2, qg1), qg0);
+      const float chi = wfold_get(t, 1) + fmaf(hi.alpha, fmaf(hi.alpha, qg2, qg1), qg0);
+      const float c00 = wfold_get(t, 2) + qg0;
+      const bool improved = (clo < c00) || (chi < c00);
+      alpha = improved ? (clo < chi ? lo.alpha : hi.alpha) : 0.f;
+    }
     qacc += alpha * search;
     Ma += alpha * Mv;
     Jf += alpha * jvf;
@@ -577,6 +665,7 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
   L.qacc = qacc;
   L.qaccw = qacc;
 
+  PHASE_SYNC(5, false)
   // ------------------------------------------------------------------ outputs of the last forward: forces, sensors
   if (last) {
     if (lane < nv) out[OUT_QACC + lane] = qacc;
@@ -667,7 +756,11 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
     }
     if (lane < nb) { dbg[1440 + 3 * lane] = xp.x; dbg[1441 + 3 * lane] = xp.y; dbg[1442 + 3 * lane] = xp.z; }
     if (lane == 0) { dbg[1536] = com.x; dbg[1537] = com.y; dbg[1538] = com.z; }
-    for (int r = 0; r < JROWS; ++r) dbg[1768 + r * 32 + lane] = lane < nv ? s.J[r][lane] : 0.f;
+    for (int c = 0; c < NCON_FLOOR; ++c) {
+      V3 jp = v3(0.f, 0.f, 0.f);
+      if (s.con[c][0] < 0.f && (c < 4 ? inF0 : inF1)) jp = v3(cd.l0, cd.l1, cd.l2) + cross(v3(cd.a0, cd.a1, cd.a2), v3(s.con[c][1], s.con[c][2], s.con[c][3]) - com);
+      dbg[1768 + (3 * c) * 32 + lane] = jp.z; dbg[1768 + (3 * c + 1) * 32 + lane] = jp.y; dbg[1768 + (3 * c + 2) * 32 + lane] = -jp.x;
+    }
   }
   __syncwarp();
 
@@ -699,9 +792,9 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
   return false;
 }
 
-template <bool DBG>
+template <bool DBG, bool BAR = false>
 __device__ __forceinline__ void forward_euler(const DevModel& m, WarpSmem& s, Lane& L, const int lane, const bool last, const bool integrate,
                                               float* __restrict__ out, float* __restrict__ dbg, const DevFF* __restrict__ ffm, float* __restrict__ ffs) {
-  if (forward_euler_impl<DBG, false>(m, s, L, lane, last, integrate, out, dbg, ffm, ffs))
-    forward_euler_impl<DBG, true>(m, s, L, lane, last, integrate, out, dbg, ffm, ffs);
+  if (forward_euler_impl<DBG, false, BAR>(m, s, L, lane, last, integrate, out, dbg, ffm, ffs))
+    forward_euler_impl<DBG, true, BAR>(m, s, L, lane, last, integrate, out, dbg, ffm, ffs);
 }
