@@ -48,32 +48,61 @@ def _peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML in-process every 10 ms (an
+    nvidia-smi subprocess takes longer than the timed region of a short run), nvidia-smi as the fallback.  Only samples whose
+    host timestamp falls inside a window marked with ``window()`` count."""
 
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index):
+    def __init__(self, index, uuid=None):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.uuid, self.samples, self.stop_flag, self.windows, self.source = index, uuid, [], False, [], None
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid) if uuid else pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml, self.source = pynvml, "nvml"
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        bits = [n.nvmlClocksThrottleReasonHwSlowdown, n.nvmlClocksThrottleReasonHwThermalSlowdown, n.nvmlClocksThrottleReasonSwThermalSlowdown, n.nvmlClocksThrottleReasonSwPowerCap]
+        return (time.perf_counter(), sm, self.sm_max, [bool(r & b) for b in bits])
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=10).stdout.strip()
+        f = [x.strip() for x in out.split(",")]
+        return (time.perf_counter(), float(f[0]), float(f[1]), [x.lower().startswith("active") for x in f[2:6]])
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                self.samples.append(self._sample_nvml() if self.nvml else self._sample_smi())
+                self.source = self.source or "nvidia-smi"
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.01 if self.nvml else 0.1)
+
+    def window(self, t0, t1):
+        self.windows.append((t0, t1))
 
     def summary(self):
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(len(s) > 2 + k and s[2 + k].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons, "samples": len(self.samples)}
+        inside = [s for s in self.samples if any(a <= s[0] <= b for a, b in self.windows)] if self.windows else self.samples
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock sample inside the timed region"], "samples": 0, "source": self.source}
+        sm = sorted(s[1] for s in inside)
+        reasons = [n for k, n in enumerate(self.NAMES) if any(s[3][k] for s in inside)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": inside[0][2], "reasons": reasons, "samples": len(inside), "source": self.source}
 
 
 def cpu_port_rate(n_envs, steps, f32=True):
@@ -198,9 +227,15 @@ def main():
     n_keys = 8
     keys = [torch.from_numpy(jr.split(jr.PRNGKey(1000 + k), world * n)[rank * n:(rank + 1) * n].view(np.int32).copy()).to(dev) for k in range(n_keys)]   # resident in HBM
     host_keys = [k.cpu().pin_memory() for k in keys]
-    host_obs = torch.empty(n, 101).pin_memory()
-    host_out = torch.empty(n, 14 + 3).pin_memory()
-    dev_out = torch.empty(n, 14 + 3, device=dev)
+    # e2e staging: per step the host receives obs["state"] (what a host-side learner stores per transition) and
+    # [raw action 14 | log-prob | reward | done]; two device staging slots + two pinned host slots so that the D2H of step k
+    # (copy stream) overlaps the compute of step k+1 -- the host still consumes every step's result inside the timed region.
+    stage = [torch.empty(n, 101 + 17, device=dev) for _ in range(2)]
+    host_out = [torch.empty(n, 101 + 17).pin_memory() for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    ev_ready = [torch.cuda.Event() for _ in range(2)]
+    ev_done = [torch.cuda.Event() for _ in range(2)]
+    host_sink = torch.zeros(())
 
     def barrier():
         if world > 1:
@@ -218,32 +253,53 @@ def main():
         b.record()
         kstep_events.append((a, b))
 
+    def consume(slot):
+        nonlocal host_sink
+        ev_done[slot].synchronize()
+        host_sink = host_sink + host_out[slot][0, 101 + 15]              # the host reads the delivered result (a reward)
+
     def step_e2e(k):
         e = envs[k % n_sets]
-        kd = host_keys[k % n_keys].to(dev, non_blocking=True)           # H2D: this step's sampling keys
+        slot = k & 1
+        main = torch.cuda.current_stream(dev)
+        kd = host_keys[k % n_keys].to(dev, non_blocking=True)           # H2D: this step's sampling keys (pinned)
         act, raw, logp = ppo.policy_forward(e, weights, kd, deterministic=False)
         st = e.step(None, act)
-        dev_out[:, :14] = raw; dev_out[:, 14] = logp; dev_out[:, 15] = st.reward; dev_out[:, 16] = st.done
-        host_obs.copy_(st.obs["state"], non_blocking=True)              # D2H: what a host-side learner stores per transition
-        host_out.copy_(dev_out, non_blocking=True)
-        torch.cuda.current_stream().synchronize()                       # the host consumes the result every step
+        sg = stage[slot]                                                # its previous D2H (step k-2) was consumed at step k-1
+        sg[:, :101] = st.obs["state"]; sg[:, 101:115] = raw; sg[:, 115] = logp; sg[:, 116] = st.reward; sg[:, 117] = st.done
+        ev_ready[slot].record(main)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_ready[slot])
+            host_out[slot].copy_(sg, non_blocking=True)                 # D2H on the copy stream
+            ev_done[slot].record(copy_stream)
+        if k > 0:
+            consume(slot ^ 1)                                           # host waits for (and reads) step k-1 while step k runs
 
-    def timed(fn, steps):
+    def timed(fn, steps, after=None):
         barrier()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0 = time.perf_counter()
         t0.record()
         for k in range(steps):
             fn(k)
+        if after:
+            after(steps)
         t1.record()
         barrier()
+        sampler.window(h0, time.perf_counter())
         ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    uuid = None
+    try:
+        uuid = "GPU-" + str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:
+        pass
+    sampler = ClockSampler(local, uuid)
     for k in range(max(3, args.warmup)):
         step_resident(k)
-    sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     l0 = sum(e.handle.launch_count() for e in envs)
@@ -251,10 +307,11 @@ def main():
     ms_total = timed(step_resident, args.steps)
     ms_kstep = sum(a.elapsed_time(b) for a, b in kstep_events) / len(kstep_events)   # average k_step launch duration, on its stream
     launches = sum(e.handle.launch_count() for e in envs) - l0
-    for k in range(3):
+    for k in range(4):
         step_e2e(k)
+    torch.cuda.synchronize()
     e2e_steps = max(10, args.steps // 2)
-    ms_e2e = timed(step_e2e, e2e_steps)
+    ms_e2e = timed(step_e2e, e2e_steps, after=lambda steps: consume((steps - 1) & 1))   # the last step's result is consumed too
     sampler.stop_flag = True
     ms_step = ms_total / args.steps
     value = world * n * args.steps / (ms_total * 1e-3)
@@ -281,7 +338,8 @@ def main():
                          "fp32_frac": FLOP_PER_ENV_STEP * value / world / fp32_peak, "algorithmic_bytes_per_env_step": BYTES_PER_ENV_STEP,
                          "kernel": "k_step", "kernel_ms": ms_kstep, "kernel_share_of_step": ms_kstep / ms_step,
                          "kernel_ms_note": "average k_step launch duration from CUDA events around every launch of the timed region; rollout step = policy kernels + k_step"},
-            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": n * 2 * 4, "d2h_bytes_per_step": n * (101 + 17) * 4, "steps": e2e_steps},
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": n * 2 * 4, "d2h_bytes_per_step": n * (101 + 17) * 4, "steps": e2e_steps,
+                    "note": "host keys H2D + policy + env.step + D2H of obs/raw/logp/reward/done every step; the D2H of step k runs on a copy stream under step k+1 and the host reads step k-1's result before it issues step k+1"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "physics_substeps_per_s": value * 10,

@@ -275,6 +275,9 @@ int oduck_set_state(OduckHandle* h, const float* qpos, const float* qvel, const 
  * Outputs f32: action [N,nu] (tanh-squashed), raw_action [N,nu] (pre-tanh), log_prob [N]; any may be NULL. */
 int oduck_policy_forward(OduckHandle* h, const OduckPolicyWeights* w, const float* obs, const uint32_t* keys,
                          int deterministic, float* action, float* raw_action, float* log_prob, void* stream);
+/* The library caches a tensor-core repack of the weights keyed by w->w[0]; call this after the weights behind the same
+ * pointers changed in place (the device learner of oduck_ppo.h updates them every SGD step). */
+int oduck_policy_invalidate(OduckHandle* h);
 /* Zero-copy view.  shape[4] (unused dims = 0), strides in ELEMENTS. */
 int oduck_get_buffer(OduckHandle* h, int id, void** ptr, int64_t* shape, int64_t* strides, int* dtype);
 /* Number of kernels this library has launched on the handle since create (bench `gpu_launches`). */

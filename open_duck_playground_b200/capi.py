@@ -76,6 +76,32 @@ class OduckPolicyWeights(C.Structure):
     ]
 
 
+class OduckPpoConfig(C.Structure):
+    """include/oduck_ppo.h"""
+    _fields_ = [
+        ("batch_envs", i32), ("unroll", i32), ("num_actions", i32), ("policy_dims", i32 * 5), ("value_dims", i32 * 5),
+        ("normalize_advantage", i32),
+        ("discounting", C.c_float), ("gae_lambda", C.c_float), ("clipping_epsilon", C.c_float), ("entropy_cost", C.c_float),
+        ("reward_scaling", C.c_float), ("learning_rate", C.c_float), ("max_grad_norm", C.c_float),
+        ("adam_b1", C.c_float), ("adam_b2", C.c_float), ("adam_eps", C.c_float),
+    ]
+
+
+class OduckRollout(C.Structure):
+    _fields_ = [
+        ("num_envs", i32), ("unroll", i32),
+        ("obs_policy", C.c_void_p), ("obs_value", C.c_void_p), ("raw_action", C.c_void_p), ("log_prob", C.c_void_p),
+        ("reward", C.c_void_p), ("done", C.c_void_p), ("truncation", C.c_void_p),
+    ]
+
+
+class OduckNormalizer(C.Structure):
+    _fields_ = [("policy_mean", C.c_void_p), ("policy_std", C.c_void_p), ("value_mean", C.c_void_p), ("value_std", C.c_void_p)]
+
+
+PPO_STAGE_FORWARD, PPO_STAGE_LOSS, PPO_STAGE_BACKWARD, PPO_STAGE_ADAM, PPO_ALL, PPO_DEBUG_SIMT = 1, 2, 4, 8, 15, 256
+PPO_BUF = {name: k for k, name in enumerate(["PARAMS", "GRADS", "ADAM_M", "ADAM_V", "LOGITS", "VALUES", "LOSSES", "ADV", "VS", "STEP"])}
+
 BUF = {name: k for k, name in enumerate([
     "QPOS", "QVEL", "QACC_WARM", "QACC", "CTRL", "OBS_STATE", "OBS_PRIV", "REWARD", "DONE", "TRUNCATION", "METRICS",
     "EFC_FORCE", "CONTACT_DIST", "SENSORDATA", "ACTUATOR_FORCE", "SITE_XPOS_FEET", "INFO_RNG", "INFO_COMMAND",
@@ -134,6 +160,19 @@ class Library:
         L.oduck_get_buffer.argtypes = [vp, C.c_int, p(vp), p(C.c_int64), p(C.c_int64), p(C.c_int)]
         L.oduck_launch_count.argtypes = [vp]
         L.oduck_launch_count.restype = C.c_int64
+        L.oduck_policy_invalidate.argtypes = [vp]
+        self.has_ppo = hasattr(L, "oduck_ppo_create")            # the device learner (include/oduck_ppo.h) exists in the CUDA library only
+        if self.has_ppo:
+            L.oduck_ppo_create.argtypes = [p(OduckPpoConfig), C.c_int, p(vp)]
+            L.oduck_ppo_destroy.argtypes = [vp]
+            L.oduck_ppo_num_params.argtypes = [vp]
+            L.oduck_ppo_num_params.restype = C.c_int64
+            L.oduck_ppo_launch_count.argtypes = [vp]
+            L.oduck_ppo_launch_count.restype = C.c_int64
+            L.oduck_ppo_param_info.argtypes = [vp, C.c_int, C.c_int, C.c_int, p(C.c_int64), p(C.c_int64), p(C.c_int64)]
+            L.oduck_ppo_set_params.argtypes = [vp, vp, C.c_int, vp]
+            L.oduck_ppo_get_buffer.argtypes = [vp, C.c_int, p(vp), p(C.c_int64), p(C.c_int)]
+            L.oduck_ppo_minibatch.argtypes = [vp, p(OduckRollout), p(OduckNormalizer), vp, vp, vp, C.c_int, vp]
         if L.oduck_abi_version() != ABI_VERSION:
             raise OduckError(f"{path}: ABI version {L.oduck_abi_version()} != {ABI_VERSION}")
         if L.oduck_sizeof_model() != C.sizeof(OduckModel) or L.oduck_sizeof_env_config() != C.sizeof(OduckEnvConfig):
@@ -192,6 +231,9 @@ class Handle:
     def launch_count(self) -> int:
         return int(self.L.lib.oduck_launch_count(self.h))
 
+    def policy_invalidate(self) -> None:
+        self.L.check(self.L.lib.oduck_policy_invalidate(self.h))
+
     def buffer_info(self, name: str) -> Tuple[int, Tuple[int, ...], Tuple[int, ...], type]:
         ptr, shape, strides, dt = C.c_void_p(), (C.c_int64 * 4)(), (C.c_int64 * 4)(), C.c_int()
         self.L.check(self.L.lib.oduck_get_buffer(self.h, BUF[name], C.byref(ptr), shape, strides, C.byref(dt)))
@@ -208,6 +250,49 @@ class Handle:
         raw = (C.c_char * (n_items * item)).from_address(ptr)
         base = np.frombuffer(raw, dtype=dt)
         return np.lib.stride_tricks.as_strided(base, shape=shape, strides=tuple(st * item for st in strides))
+
+
+class PpoHandle:
+    """Owns one ``OduckPpo*`` (include/oduck_ppo.h): the on-device PPO learner step."""
+
+    def __init__(self, lib: Library, cfg: OduckPpoConfig, device: int = 0):
+        if not lib.has_ppo:
+            raise OduckError(f"{lib.path} does not export the oduck_ppo_* learner (CUDA library only)")
+        self.L, self.cfg = lib, cfg
+        h = C.c_void_p()
+        lib.check(lib.lib.oduck_ppo_create(C.byref(cfg), device, C.byref(h)))
+        self.h = h
+        self.num_params = int(lib.lib.oduck_ppo_num_params(h))
+
+    def close(self):
+        if self.h:
+            self.L.lib.oduck_ppo_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def param_info(self, net: int, layer: int, which: int) -> Tuple[int, int, int]:
+        off, r, c = C.c_int64(), C.c_int64(), C.c_int64()
+        self.L.check(self.L.lib.oduck_ppo_param_info(self.h, net, layer, which, C.byref(off), C.byref(r), C.byref(c)))
+        return off.value, r.value, c.value
+
+    def set_params(self, flat: int, reset_opt: bool, stream: int = 0):
+        self.L.check(self.L.lib.oduck_ppo_set_params(self.h, flat, int(reset_opt), stream))
+
+    def buffer_info(self, name: str) -> Tuple[int, int, type]:
+        ptr, cnt, dt = C.c_void_p(), C.c_int64(), C.c_int()
+        self.L.check(self.L.lib.oduck_ppo_get_buffer(self.h, PPO_BUF[name], C.byref(ptr), C.byref(cnt), C.byref(dt)))
+        return ptr.value, cnt.value, DTYPE_NP[dt.value]
+
+    def minibatch(self, rollout: OduckRollout, norm: OduckNormalizer, env_idx: int, noise: int, key: int, stages: int, stream: int = 0):
+        self.L.check(self.L.lib.oduck_ppo_minibatch(self.h, C.byref(rollout), C.byref(norm), env_idx, noise or None, key or None, stages, stream))
+
+    def launch_count(self) -> int:
+        return int(self.L.lib.oduck_ppo_launch_count(self.h))
 
 
 _cuda_lib: Optional[Library] = None

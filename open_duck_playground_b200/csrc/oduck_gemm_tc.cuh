@@ -1,0 +1,266 @@
+// oduck_gemm_tc.cuh -- D[M x N] = A[M x K] . B[N x K]^T on the tcgen05 tensor cores (sm_100a), fp32-faithful (3xTF32),
+// with the epilogues the PPO learner needs (oduck_ppo.cu).  Generalises the actor-MLP layer kernel of oduck_policy.cu:
+//
+//   * both operands live in HBM/L2 already in the canonical K-major, no-swizzle UMMA form, split in hi/lo tf32 halves:
+//       R(X) for a matrix X[rows][cols] = blocks [row-tile][k-chunk], a block = [hi | lo], each half ROWS x 32 floats with
+//       element (r, k) at (r/8)*256 + (k/4)*32 + (r%8)*4 + (k%4)                 (8 x 16-byte core matrices, LBO 128 B, SBO 1 KB)
+//     A blocks have 128 rows (32 KB), B blocks NT rows (NT = 128 or 32); a pipeline stage is two 1-D TMA bulk copies;
+//   * one elected thread runs the producer + tcgen05.mma issue loop over an NSTAGE-deep mbarrier ring (NSTAGE - 1 copies in
+//     flight under the MMAs), the fp32 accumulator lives in TMEM, gridDim.z splits K (dW GEMMs reduce over the batch);
+//   * epilogues read TMEM with tcgen05.ld (one output row per thread, 32 columns at a time) and write what the NEXT GEMMs
+//     consume, already in operand form: R(Y) (row-major use) and R(Y^T) (the dW GEMM contracts over the batch), so no
+//     separate transpose / pack pass exists between layers.
+// A CUDA-core twin (k_gemm_simt) runs the same operands through the same epilogues; it exists to bisect a tcgen05
+// problem in the parity tests (ODUCK_PPO_DEBUG_SIMT) and is never on the product path.
+#pragma once
+#include "oduck_policy_tc.cuh"
+
+#define GBLK_A (2 * TC_M * TC_KC)                                   // floats per A block (hi + lo) = 8192
+__host__ __device__ constexpr int gblk_b(int nt) { return 2 * nt * TC_KC; }
+__device__ __forceinline__ int gblk_off(int r, int kk) { return (r >> 3) * 256 + (kk >> 2) * 32 + (r & 7) * 4 + (kk & 3); }
+__device__ __forceinline__ void gsplit_tf32(float v, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  lo = v - hi;
+}
+
+enum { EPI_FWD = 0, EPI_OUT = 1, EPI_DX = 2, EPI_DW = 3 };
+
+struct GemmParams {
+  const float* A;        // [mtiles][nchunks][GBLK_A]
+  const float* B;        // [ntiles][nchunks][gblk_b(NT)]
+  int nchunks, cps;      // k-chunks of the operands; chunks per split (gridDim.z = ceil(nchunks / cps), no split is empty)
+  const float* bias;     // FWD / OUT: [nvalid]
+  float* Z; int ldz;     // FWD: pre-activations written; DX: pre-activations read ([rows][ldz])
+  float* Yr; int yr_nch; // R(Y):   block (mt, n / 32)
+  float* Yt; int yt_nch; // R(Y^T): block (n / 128, row / 32), yt_nch = padded rows / 32
+  float* out; int ldo;   // OUT: plain [rows][ldo]; DW: partial sums [split][rows][ldo]
+  long long out_split;   // DW: floats between splits
+  float* dbpart; int ldb;// DX: per-warp column sums [rows / 32][ldb]  (bias gradients)
+  int nvalid;            // valid output columns (bias reads are guarded)
+};
+
+__device__ __forceinline__ void gbulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void gmbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+// Column sums over the 32 lanes of a warp of 32 lane-local values: folding butterfly, 31 shuffles; lane l returns column l.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], const int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float keep = up ? v[i + off] : v[i];
+      const float send = up ? v[i] : v[i + off];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+// 32 consecutive output columns [n0, n0 + 32) of output row `row` (tile row rt of tile mt), split z.
+template <int EPI>
+__device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const int mt, const int rt, const int n0, const int z, const int lane, float (&v)[32]) {
+  const int row = mt * TC_M + rt;
+  if (EPI == EPI_OUT) {
+    float* o = p.out + (size_t)row * p.ldo + n0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float4 w;
+      float* pw = reinterpret_cast<float*>(&w);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const int n = n0 + 4 * q + e; pw[e] = n < p.nvalid ? v[4 * q + e] + __ldg(p.bias + n) : 0.f; }
+      *reinterpret_cast<float4*>(o + 4 * q) = w;
+    }
+    return;
+  }
+  if (EPI == EPI_DW) {
+    float* o = p.out + (size_t)z * p.out_split + (size_t)row * p.ldo + n0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(o + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    return;
+  }
+  // FWD: y = swish(acc + bias), pre-activation kept for the backward pass.  DX: y = acc * swish'(z).
+  float* zrow = p.Z + (size_t)row * p.ldz + n0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    if (EPI == EPI_FWD) {
+      float4 w;
+      float* pw = reinterpret_cast<float*>(&w);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int n = n0 + 4 * q + e;
+        const float zz = v[4 * q + e] + (n < p.nvalid ? __ldg(p.bias + n) : 0.f);
+        pw[e] = zz;
+        v[4 * q + e] = zz / (1.f + __expf(-zz));
+      }
+      *reinterpret_cast<float4*>(zrow + 4 * q) = w;
+    } else {
+      const float4 w = *reinterpret_cast<const float4*>(zrow + 4 * q);
+      const float* pw = reinterpret_cast<const float*>(&w);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float zz = pw[e], s = 1.f / (1.f + __expf(-zz));
+        v[4 * q + e] *= s * (1.f + zz * (1.f - s));
+      }
+    }
+  }
+  {
+    float* blk = p.Yr + ((size_t)mt * p.yr_nch + (n0 >> 5)) * GBLK_A;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float4 h4, l4;
+      float* ph = reinterpret_cast<float*>(&h4);
+      float* pl = reinterpret_cast<float*>(&l4);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) gsplit_tf32(v[4 * q + e], ph[e], pl[e]);
+      *reinterpret_cast<float4*>(blk + gblk_off(rt, 4 * q)) = h4;
+      *reinterpret_cast<float4*>(blk + TC_M * TC_KC + gblk_off(rt, 4 * q)) = l4;
+    }
+  }
+  {
+    // transposed operand: element (n, row) of Y^T; the warp's 32 rows are exactly one k-chunk of it
+    float* blk = p.Yt + ((size_t)(n0 >> 7) * p.yt_nch + (row >> 5)) * GBLK_A;
+    const int kk = row & 31, nb = n0 & 127;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      float hi, lo;
+      gsplit_tf32(v[e], hi, lo);
+      const int off = gblk_off(nb + e, kk);
+      blk[off] = hi;
+      blk[TC_M * TC_KC + off] = lo;
+    }
+  }
+  if (EPI == EPI_DX) {
+    const float cs = warp_colsum32(v, lane);
+    p.dbpart[(size_t)(row >> 5) * p.ldb + n0 + lane] = cs;
+  }
+}
+
+template <int NT, int NSTAGE, int EPI>
+__global__ void __launch_bounds__(TC_THREADS) k_gemm_tc(GemmParams p) {
+  extern __shared__ __align__(128) unsigned char raw_smem[];
+  __shared__ __align__(8) uint64_t full[NSTAGE], empty[NSTAGE], done;
+  __shared__ uint32_t tmem_base_s;
+  constexpr int BLKB = gblk_b(NT);
+  constexpr int STAGE = GBLK_A + BLKB;                            // floats per stage
+  float* const smem = reinterpret_cast<float*>(raw_smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = blockIdx.x, nt = blockIdx.y, z = blockIdx.z;
+  constexpr uint32_t kCols = NT < 32 ? 32 : NT;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "r"(kCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(&done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+  const int c0 = z * p.cps;
+  const int n = min(p.nchunks - c0, p.cps);                        // >= 1 by construction of the grid
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = umma_idesc_tf32(NT);
+    const float* xa = p.A + ((size_t)mt * p.nchunks + c0) * GBLK_A;
+    const float* wb = p.B + ((size_t)nt * p.nchunks + c0) * BLKB;
+    auto issue = [&](int i) {
+      const int s = i % NSTAGE;
+      float* st = smem + (size_t)s * STAGE;
+      gmbar_expect_tx(&full[s], (uint32_t)(STAGE * sizeof(float)));
+      gbulk_g2s(st, xa + (size_t)i * GBLK_A, GBLK_A * sizeof(float), &full[s]);
+      gbulk_g2s(st + GBLK_A, wb + (size_t)i * BLKB, BLKB * sizeof(float), &full[s]);
+    };
+    for (int i = 0; i < NSTAGE - 1 && i < n; ++i) issue(i);
+    for (int i = 0; i < n; ++i) {
+      const int nx = i + NSTAGE - 1;                               // keep NSTAGE - 1 copies in flight
+      if (nx < n) {
+        if (nx >= NSTAGE) mbar_wait(&empty[nx % NSTAGE], (uint32_t)(((nx / NSTAGE) - 1) & 1));   // MMAs of chunk nx - NSTAGE retired
+        issue(nx);
+      }
+      const int s = i % NSTAGE;
+      mbar_wait(&full[s], (uint32_t)((i / NSTAGE) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      const uint32_t a_hi = smem_u32(smem + (size_t)s * STAGE), a_lo = a_hi + TC_M * TC_KC * 4, b_hi = a_hi + GBLK_A * 4, b_lo = b_hi + NT * TC_KC * 4;
+#pragma unroll
+      for (int kk = 0; kk < TC_KC / 8; ++kk) {
+        const uint32_t o = kk * 256;
+        umma_tf32(tmem_base, umma_smem_desc(a_hi + o, 128, 1024), umma_smem_desc(b_hi + o, 128, 1024), idesc, (i > 0 || kk > 0) ? 1u : 0u);
+        umma_tf32(tmem_base, umma_smem_desc(a_lo + o, 128, 1024), umma_smem_desc(b_hi + o, 128, 1024), idesc, 1u);
+        umma_tf32(tmem_base, umma_smem_desc(a_hi + o, 128, 1024), umma_smem_desc(b_lo + o, 128, 1024), idesc, 1u);
+      }
+      umma_commit(&empty[s]);
+    }
+    umma_commit(&done);
+  }
+  if (warp == 0) __syncwarp();
+  mbar_wait(&done, 0u);
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const int rt = 32 * warp + lane;                                 // output row of the tile = TMEM lane
+  const uint32_t tlane = (uint32_t)(32 * warp) << 16;
+#pragma unroll 1
+  for (int j = 0; j < (NT < 32 ? 1 : NT / 32); ++j) {
+    float v[32];
+    tmem_ld32(tmem_base + tlane + (uint32_t)(j * 32), v);
+    gemm_epilogue<EPI>(p, mt, rt, nt * NT + j * 32, z, lane, v);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(kCols) : "memory");
+}
+
+// CUDA-core twin: same grid, operands and epilogues; fp32 FMAs on hi + lo.  Debug / bisect only.
+template <int NT, int EPI>
+__global__ void __launch_bounds__(TC_THREADS) k_gemm_simt(GemmParams p) {
+  constexpr int BLKB = gblk_b(NT);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = blockIdx.x, nt = blockIdx.y, z = blockIdx.z;
+  const int c0 = z * p.cps;
+  const int n = min(p.nchunks - c0, p.cps);
+  const int rt = 32 * warp + lane;
+  for (int j = 0; j < (NT < 32 ? 1 : NT / 32); ++j) {
+    float v[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) v[e] = 0.f;
+    for (int i = 0; i < n; ++i) {
+      const float* a = p.A + ((size_t)mt * p.nchunks + c0 + i) * GBLK_A;
+      const float* b = p.B + ((size_t)nt * p.nchunks + c0 + i) * BLKB;
+      for (int kk = 0; kk < TC_KC; ++kk) {
+        const float av = a[gblk_off(rt, kk)] + a[TC_M * TC_KC + gblk_off(rt, kk)];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int off = gblk_off(j * 32 + e, kk);
+          v[e] = fmaf(av, b[off] + b[NT * TC_KC + off], v[e]);
+        }
+      }
+    }
+    gemm_epilogue<EPI>(p, mt, rt, nt * NT + j * 32, z, lane, v);
+  }
+}
+
+template <int NT, int NSTAGE, int EPI>
+static cudaError_t launch_gemm(const GemmParams& p, int mtiles, int ntiles, bool simt, cudaStream_t st) {
+  const int splits = (p.nchunks + p.cps - 1) / p.cps;
+  dim3 grid(mtiles, ntiles, splits);
+  if (simt) {
+    k_gemm_simt<NT, EPI><<<grid, TC_THREADS, 0, st>>>(p);
+    return cudaGetLastError();
+  }
+  const int smem = NSTAGE * (GBLK_A + gblk_b(NT)) * (int)sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<NT, NSTAGE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  k_gemm_tc<NT, NSTAGE, EPI><<<grid, TC_THREADS, smem, st>>>(p);
+  return cudaGetLastError();
+}

@@ -219,6 +219,12 @@ static cudaError_t launch_dense(const DenseParams& p, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+extern "C" int oduck_policy_invalidate(OduckHandle* h) {
+  if (!h) return oduck_fail(ODUCK_ERR_ARG, "oduck_policy_invalidate: bad argument");
+  h->policy_packed_for = nullptr;
+  return ODUCK_OK;
+}
+
 extern "C" int oduck_policy_forward(OduckHandle* h, const OduckPolicyWeights* w, const float* obs, const uint32_t* keys, int deterministic,
                                     float* action, float* raw_action, float* log_prob, void* stream) {
   if (!h || !w) return oduck_fail(ODUCK_ERR_ARG, "oduck_policy_forward: bad argument");

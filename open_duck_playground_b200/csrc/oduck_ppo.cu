@@ -1,0 +1,681 @@
+// oduck_ppo.cu -- the PPO learner step on the device (include/oduck_ppo.h).
+// Restates what Brax's `ppo.train` does per minibatch for the reference's runner (playground/common/runner.py:86-118):
+// compute_ppo_loss (losses.py: value/policy forward, compute_gae, clipped surrogate, sampled NormalTanh entropy),
+// its gradient, optax.clip_by_global_norm + optax.adam.  Checker: the PyTorch fp32 twin (ppo.py) in tests/test_ppo_device.py.
+//
+// Launch sequence of one minibatch (B trajectories x T steps; Mp = T B policy rows, Mv = (T + 1) B value rows):
+//   k_ppo_pack x2        gather rows by env index, normalise, write R(X0) and R(X0^T) (hi/lo tf32 operand blocks)
+//   k_gemm_tc  x8        forward: 3 x (Dense + swish) + head, per net; epilogues emit the next operands in both orientations
+//   k_ppo_gae            per-trajectory GAE scan, advantage statistics (one CTA, deterministic)
+//   k_ppo_loss           per-row NormalTanh log-prob / ratio / clip / entropy / value error -> head gradients as operands
+//   k_gemm_tc  x14       backward: dW_l = X_l^T dZ_l (split-K over the batch) and dZ_{l-1} = (dZ_l W_l^T) * swish'(Z_{l-1})
+//   k_ppo_grad_reduce    sum split-K / per-warp partials into the flat gradient, partial sums of squares
+//   k_ppo_adam           global-norm clip, Adam, master weights + both packed operand forms of every kernel matrix
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/oduck.h"
+#include "../../include/oduck_ppo.h"
+#include "oduck_env.cuh"
+#include "oduck_gemm_tc.cuh"
+
+extern int oduck_fail(int code, const std::string& msg);
+#define PPO_TRY(x)                                                                                             \
+  do {                                                                                                         \
+    cudaError_t e_ = (x);                                                                                      \
+    if (e_ != cudaSuccess) return oduck_fail(ODUCK_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+#define PPO_NL 4            // dense layers per net
+#define PPO_MAXT 64
+#define PPO_HEADW 32        // padded head width (one NT = 32 tile)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
+
+// one tensor of the flat parameter vector
+struct Seg {
+  long long off;            // offset in the flat vector
+  int net, layer, bias, K, N;   // kernel: K x N row-major ([in][out]); bias: N
+  int nt;                   // forward B-operand tile height (128 hidden, 32 head)
+  long long wf, wb;         // offsets of the packed operands inside the pack buffer (wb < 0: not needed)
+  long long dwpart, dbpart; // offsets inside the partial-gradient buffer
+  int ldo, nsplit, ldb, nwarprows;
+  long long split_stride;
+};
+#define PPO_NSEG (2 * PPO_NL * 2)
+struct SegTable { Seg s[PPO_NSEG]; int n; long long total; };
+
+struct NetBuf {
+  int dims[PPO_NL + 1];
+  int M, Mpad, mtiles;                  // rows of this net's batch
+  float* Xr[PPO_NL];                    // R(X_l)   A operand of the forward GEMM of layer l
+  float* Xt[PPO_NL];                    // R(X_l^T) A operand of the dW GEMM of layer l
+  float* Z[PPO_NL - 1];                 // pre-activations [Mpad][d_{l+1}]
+  float* out;                           // head output [Mpad][32]
+  float* dZr[PPO_NL];                   // R(dZ_l)   A operand of the dX GEMM
+  float* dZt[PPO_NL];                   // R(dZ_l^T) B operand of the dW GEMM
+};
+
+struct OduckPpo {
+  OduckPpoConfig cfg;
+  int device;
+  int B, T, na;
+  SegTable seg;
+  SegTable* dseg;
+  NetBuf net[2];
+  float *params, *grads, *adam_m, *adam_v, *packed, *partial;
+  long long P, packed_floats, partial_floats;
+  float *adv, *vs;
+  double* losses;           // [8]
+  double* stats;            // [4] adv mean, std
+  float* sumsq_part;        // [grid of grad_reduce]
+  int* step;                // [2]: adam step count, finished-block ticket
+  int reduce_blocks;
+  int64_t launches;
+  std::vector<void*> allocs;
+};
+
+// ------------------------------------------------------------------------------------------------- kernels
+// Gather the minibatch rows (row = t * B + b <- env idx[b] at time t), normalise, emit R(X) and R(X^T).
+__global__ void k_ppo_pack(const float* __restrict__ obs, int N, int K, const int* __restrict__ idx, int B, int M, int Mpad, int kch,
+                           const float* __restrict__ mean, const float* __restrict__ stdv, float* __restrict__ Xr, float* __restrict__ Xt) {
+  const int K32 = kch * TC_KC, ytn = Mpad / TC_KC;
+  const long long total = (long long)Mpad * K32;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int row = (int)(i / K32), k = (int)(i % K32);
+    float v = 0.f;
+    if (row < M && k < K) {
+      const int t = row / B, b = row - t * B;
+      v = (obs[((size_t)t * N + idx[b]) * K + k] - mean[k]) / stdv[k];
+    }
+    float hi, lo;
+    gsplit_tf32(v, hi, lo);
+    float* blk = Xr + ((size_t)(row >> 7) * kch + (k >> 5)) * GBLK_A;
+    int off = gblk_off(row & 127, k & 31);
+    blk[off] = hi; blk[TC_M * TC_KC + off] = lo;
+    blk = Xt + ((size_t)(k >> 7) * ytn + (row >> 5)) * GBLK_A;
+    off = gblk_off(k & 127, row & 31);
+    blk[off] = hi; blk[TC_M * TC_KC + off] = lo;
+  }
+}
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < nw; ++w) t += sh[w];
+  return t;
+}
+
+// brax losses.compute_gae over one trajectory per thread; one CTA so that the advantage statistics are deterministic.
+__global__ void __launch_bounds__(1024) k_ppo_gae(const float* __restrict__ values /*[Mv_pad][32]*/, OduckRollout ro, const int* __restrict__ idx, int B, int T,
+                                                  float discount, float lambda, float reward_scaling, int normalize, float* __restrict__ adv,
+                                                  float* __restrict__ vs, double* __restrict__ stats, double* __restrict__ losses) {
+  __shared__ double sh[32];
+  if (threadIdx.x < 8) losses[threadIdx.x] = 0.0;
+  double s1 = 0.0, s2 = 0.0;
+  const int N = ro.num_envs;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const int env = idx[b];
+    float acc = 0.f;
+    const float boot = values[(size_t)(T * B + b) * PPO_HEADW];
+    float v_next = boot, vs_next = boot;
+    for (int t = T - 1; t >= 0; --t) {
+      const size_t g = (size_t)t * N + env;
+      const float trunc = ro.truncation[g], done = ro.done[g], rew = ro.reward[g] * reward_scaling;
+      const float term = done * (1.f - trunc), mask = 1.f - trunc;
+      const float v = values[(size_t)(t * B + b) * PPO_HEADW];
+      const float delta = (rew + discount * (1.f - term) * v_next - v) * mask;
+      acc = delta + discount * (1.f - term) * mask * lambda * acc;
+      const float vst = acc + v;
+      const float a = (rew + discount * (1.f - term) * vs_next - v) * mask;
+      vs[t * B + b] = vst;
+      adv[t * B + b] = a;
+      s1 += a; s2 += (double)a * a;
+      v_next = v; vs_next = vst;
+    }
+  }
+  const double S1 = block_sum(s1, sh), S2 = block_sum(s2, sh);
+  const double n = (double)B * T;
+  const double mean = S1 / n, var = fmax(S2 / n - mean * mean, 0.0);
+  const float mf = (float)mean, sf = (float)sqrt(var);
+  if (threadIdx.x == 0) { stats[0] = mean; stats[1] = sqrt(var); }
+  if (normalize) {
+    for (int b = threadIdx.x; b < B; b += blockDim.x)
+      for (int t = 0; t < T; ++t) adv[t * B + b] = (adv[t * B + b] - mf) / (sf + 1e-8f);
+  }
+}
+
+__device__ __forceinline__ float ppo_erfinv(float x) {   // XLA's f32 erf_inv polynomial (as in oduck_policy.cu)
+  float w = -__logf((1.0f - x) * (1.0f + x)), p;
+  if (w < 5.0f) {
+    w -= 2.5f;
+    p = 2.81022636e-08f; p = 3.43273939e-07f + p * w; p = -3.5233877e-06f + p * w; p = -4.39150654e-06f + p * w; p = 0.00021858087f + p * w;
+    p = -0.00125372503f + p * w; p = -0.00417768164f + p * w; p = 0.246640727f + p * w; p = 1.50140941f + p * w;
+  } else {
+    w = sqrtf(w) - 3.0f;
+    p = -0.000200214257f; p = 0.000100950558f + p * w; p = 0.00134934322f + p * w; p = -0.00367342844f + p * w; p = 0.00573950773f + p * w;
+    p = -0.0076224613f + p * w; p = 0.00943887047f + p * w; p = 1.00167406f + p * w; p = 2.83297682f + p * w;
+  }
+  return p * x;
+}
+__device__ __forceinline__ float softplusf(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+
+struct LossParams {
+  const float* logits;      // [Mp_pad][32]
+  const float* values;      // [Mv_pad][32]
+  const float* adv; const float* vs;
+  OduckRollout ro;
+  const int* idx;
+  const float* noise;       // [Mp][na] or null
+  const uint32_t* key;      // device u32[2] (used when noise == null)
+  int B, T, na, Mp, Mp_pad, Mv, Mv_pad;
+  float clip_eps, entropy_cost;
+  float *dZr_p, *dZt_p, *db_p;   // policy head gradient: R(dZ) [Mp_pad/128][1], Rb32(dZ^T) [1][Mp_pad/32], column sums [Mp_pad/32][32]
+  float *dZr_v, *dZt_v, *db_v;
+  double* losses;
+};
+
+// One thread per row: policy rows r < Mp (value baseline rows are the same indices), bootstrap rows Mp <= r < Mv get zero gradient.
+__global__ void __launch_bounds__(128) k_ppo_loss(LossParams p) {
+  __shared__ double sh[32];
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  double l_pol = 0.0, l_val = 0.0, l_ent = 0.0, l_clip = 0.0, l_adv = 0.0;
+  const float invM = 1.f / (float)p.Mp;
+  // ---------------- policy head
+  if (r < p.Mp_pad) {                                   // warp-uniform: Mp_pad is a multiple of 128
+    float g[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) g[e] = 0.f;
+    if (r < p.Mp) {
+      const int t = r / p.B, b = r - t * p.B;
+      const size_t gi = (size_t)t * p.ro.num_envs + p.idx[b];
+      const float* lg = p.logits + (size_t)r * PPO_HEADW;
+      const float A = p.adv[r];
+      RKey rowkey; rowkey.a = 0; rowkey.b = 0;
+      if (!p.noise) { RKey k0; k0.a = p.key[0]; k0.b = p.key[1]; rowkey = rblock(k0, (uint32_t)r); }
+      float logp = 0.f, ent = 0.f;
+      float dlp_loc[16], dlp_sc[16], dent_loc[16], dent_sc[16], sig[16];
+#pragma unroll
+      for (int a = 0; a < 16; ++a) {
+        dlp_loc[a] = dlp_sc[a] = dent_loc[a] = dent_sc[a] = sig[a] = 0.f;
+        if (a < p.na) {
+          const float loc = lg[a], sp = lg[p.na + a];
+          const float scale = softplusf(sp) + 0.001f;
+          const float raw = p.ro.raw_action[gi * p.na + a];
+          const float zz = (raw - loc) / scale;
+          logp += -0.5f * zz * zz - logf(scale) - 0.91893853320467f - 2.f * (0.69314718056f - raw - softplusf(-2.f * raw));
+          float eps;
+          if (p.noise) eps = p.noise[(size_t)r * p.na + a];
+          else {
+            RKey bk = rblock(rowkey, (uint32_t)a);
+            const float lo = -0.99999994f;
+            eps = 1.41421356237f * ppo_erfinv(fmaxf(lo, bits_unit(bk.a ^ bk.b) * (1.0f - lo) + lo));
+          }
+          const float x = loc + scale * eps;
+          ent += 0.5f + 0.91893853320467f + logf(scale) + 2.f * (0.69314718056f - x - softplusf(-2.f * x));
+          const float th = tanhf(x);
+          dlp_loc[a] = zz / scale; dlp_sc[a] = (zz * zz - 1.f) / scale;
+          dent_loc[a] = -2.f * th; dent_sc[a] = 1.f / scale - 2.f * th * eps;
+          sig[a] = 1.f / (1.f + expf(-sp));
+        }
+      }
+      const float rho = expf(logp - p.ro.log_prob[gi]);
+      const float lo = 1.f - p.clip_eps, hi = 1.f + p.clip_eps;
+      const float s1 = rho * A, s2 = fminf(fmaxf(rho, lo), hi) * A;
+      const bool inr = rho >= lo && rho <= hi;
+      float w = s1 < s2 ? 1.f : (s1 > s2 ? (inr ? 1.f : 0.f) : 0.5f + (inr ? 0.5f : 0.f));   // d min(s1, s2) / d s1-path, ties split like jnp/torch minimum
+      const float glp = -A * rho * w * invM;              // d loss / d logp
+      const float ge = -p.entropy_cost * invM;            // d loss / d entropy_row
+#pragma unroll
+      for (int a = 0; a < 16; ++a) {
+        if (a < p.na) {
+          g[a] = glp * dlp_loc[a] + ge * dent_loc[a];
+          g[p.na + a] = (glp * dlp_sc[a] + ge * dent_sc[a]) * sig[a];
+        }
+      }
+      l_pol = -(double)fminf(s1, s2); l_ent = ent; l_clip = inr ? 0.0 : 1.0; l_adv = fabsf(A);
+    }
+    float* blk = p.dZr_p + (size_t)(r >> 7) * GBLK_A;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float4 h4, l4;
+      float* ph = reinterpret_cast<float*>(&h4);
+      float* pl = reinterpret_cast<float*>(&l4);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) gsplit_tf32(g[4 * q + e], ph[e], pl[e]);
+      *reinterpret_cast<float4*>(blk + gblk_off(r & 127, 4 * q)) = h4;
+      *reinterpret_cast<float4*>(blk + TC_M * TC_KC + gblk_off(r & 127, 4 * q)) = l4;
+    }
+    float* bt = p.dZt_p + (size_t)(r >> 5) * gblk_b(PPO_HEADW);
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      float hi, lo;
+      gsplit_tf32(g[e], hi, lo);
+      const int off = gblk_off(e, r & 31);
+      bt[off] = hi; bt[PPO_HEADW * TC_KC + off] = lo;
+    }
+    const float cs = warp_colsum32(g, lane);
+    p.db_p[(size_t)(r >> 5) * PPO_HEADW + lane] = cs;
+  }
+  // ---------------- value head: v_loss = 0.5 * 0.5 * mean((vs - v)^2)
+  if (r < p.Mv_pad) {
+    float dv = 0.f;
+    if (r < p.Mp) {
+      const float err = p.vs[r] - p.values[(size_t)r * PPO_HEADW];
+      dv = -0.5f * err * invM;
+      l_val = 0.25 * (double)err * err;
+    }
+    float hi, lo;
+    gsplit_tf32(dv, hi, lo);
+    float* blk = p.dZr_v + (size_t)(r >> 7) * GBLK_A;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 h4 = make_float4(q == 0 ? hi : 0.f, 0.f, 0.f, 0.f), l4 = make_float4(q == 0 ? lo : 0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(blk + gblk_off(r & 127, 4 * q)) = h4;
+      *reinterpret_cast<float4*>(blk + TC_M * TC_KC + gblk_off(r & 127, 4 * q)) = l4;
+    }
+    float* bt = p.dZt_v + (size_t)(r >> 5) * gblk_b(PPO_HEADW);
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      const int off = gblk_off(e, r & 31);
+      bt[off] = e == 0 ? hi : 0.f; bt[PPO_HEADW * TC_KC + off] = e == 0 ? lo : 0.f;
+    }
+    float s = dv;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    p.db_v[(size_t)(r >> 5) * PPO_HEADW + lane] = lane == 0 ? s : 0.f;
+  }
+  const double inv = 1.0 / (double)p.Mp;
+  const double a0 = block_sum(l_pol, sh), a1 = block_sum(l_val, sh), a2 = block_sum(l_ent, sh), a3 = block_sum(l_clip, sh), a4 = block_sum(l_adv, sh);
+  if (threadIdx.x == 0) {
+    atomicAdd(p.losses + 1, a0 * inv); atomicAdd(p.losses + 2, a1 * inv); atomicAdd(p.losses + 3, a2 * inv);
+    atomicAdd(p.losses + 0, (a0 + a1 - (double)p.entropy_cost * a2) * inv);
+    atomicAdd(p.losses + 4, a4 * inv); atomicAdd(p.losses + 5, a3 * inv);
+  }
+}
+
+__device__ __forceinline__ const Seg& find_seg(const SegTable& tb, long long i) {
+  int k = 0;
+#pragma unroll 1
+  for (int s = 1; s < tb.n; ++s) if (i >= tb.s[s].off) k = s;
+  return tb.s[k];
+}
+
+// flat gradient <- split-K partials (kernels) / per-warp column sums (biases); per-block sum of squares for the global norm
+__global__ void __launch_bounds__(256) k_ppo_grad_reduce(const SegTable* __restrict__ tbp, const float* __restrict__ partial, float* __restrict__ grads, float* __restrict__ sumsq_part) {
+  __shared__ double sh[32];
+  __shared__ SegTable tb;
+  for (int i = threadIdx.x; i < (int)(sizeof(SegTable) / 4); i += blockDim.x) reinterpret_cast<int*>(&tb)[i] = reinterpret_cast<const int*>(tbp)[i];
+  __syncthreads();
+  double ss = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tb.total; i += (long long)gridDim.x * blockDim.x) {
+    const Seg& s = find_seg(tb, i);
+    const long long j = i - s.off;
+    float g = 0.f;
+    if (!s.bias) {
+      const int k = (int)(j / s.N), n = (int)(j % s.N);
+      const float* q = partial + s.dwpart + (size_t)k * s.ldo + n;
+      for (int z = 0; z < s.nsplit; ++z) g += q[(size_t)z * s.split_stride];
+    } else {
+      const float* q = partial + s.dbpart + j;
+      for (int w = 0; w < s.nwarprows; ++w) g += q[(size_t)w * s.ldb];
+    }
+    grads[i] = g;
+    ss += (double)g * g;
+  }
+  const double t = block_sum(ss, sh);
+  if (threadIdx.x == 0) sumsq_part[blockIdx.x] = (float)t;
+}
+
+__global__ void __launch_bounds__(256) k_ppo_gradnorm(const float* __restrict__ grads, long long total, float* __restrict__ sumsq_part) {
+  __shared__ double sh[32];
+  double ss = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) ss += (double)grads[i] * grads[i];
+  const double t = block_sum(ss, sh);
+  if (threadIdx.x == 0) sumsq_part[blockIdx.x] = (float)t;
+}
+
+// optax.chain(clip_by_global_norm(max_norm), adam(lr)); update = 0: only (re)write the packed operand forms from `params`.
+__global__ void __launch_bounds__(256) k_ppo_adam(const SegTable* __restrict__ tbp, float* __restrict__ params, const float* __restrict__ grads, float* __restrict__ m1,
+                                                  float* __restrict__ m2, float* __restrict__ packed, const float* __restrict__ sumsq_part, int nparts, int* __restrict__ step,
+                                                  float lr, float b1, float b2, float eps, float max_norm, int update) {
+  __shared__ SegTable tb;
+  __shared__ float s_scale, s_c1, s_c2;
+  for (int i = threadIdx.x; i < (int)(sizeof(SegTable) / 4); i += blockDim.x) reinterpret_cast<int*>(&tb)[i] = reinterpret_cast<const int*>(tbp)[i];
+  if (threadIdx.x == 0 && update) {
+    double ss = 0.0;
+    for (int k = 0; k < nparts; ++k) ss += (double)sumsq_part[k];
+    const float gn = (float)sqrt(ss);
+    s_scale = (max_norm > 0.f && gn >= max_norm) ? max_norm / gn : 1.f;
+    const int t = step[0] + 1;
+    s_c1 = 1.f / (1.f - powf(b1, (float)t));
+    s_c2 = 1.f / (1.f - powf(b2, (float)t));
+  }
+  __syncthreads();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tb.total; i += (long long)gridDim.x * blockDim.x) {
+    float w = params[i];
+    if (update) {
+      const float g = grads[i] * s_scale;
+      const float mm = b1 * m1[i] + (1.f - b1) * g, vv = b2 * m2[i] + (1.f - b2) * g * g;
+      m1[i] = mm; m2[i] = vv;
+      w -= lr * (mm * s_c1) / (sqrtf(vv * s_c2) + eps);
+      params[i] = w;
+    }
+    const Seg& s = find_seg(tb, i);
+    if (s.bias) continue;
+    const long long j = i - s.off;
+    const int k = (int)(j / s.N), n = (int)(j % s.N);
+    float hi, lo;
+    gsplit_tf32(w, hi, lo);
+    {
+      // forward B operand: R_nt(W^T), rows = out feature n, contraction over the in feature k
+      const int kch = (s.K + TC_KC - 1) / TC_KC;
+      float* blk = packed + s.wf + ((size_t)(n / s.nt) * kch + (k >> 5)) * gblk_b(s.nt);
+      const int off = gblk_off(n % s.nt, k & 31);
+      blk[off] = hi; blk[s.nt * TC_KC + off] = lo;
+    }
+    if (s.wb >= 0) {
+      // dX B operand: R(W), rows = in feature k, contraction over the out feature n
+      const int nch = (s.N + TC_KC - 1) / TC_KC;
+      float* blk = packed + s.wb + ((size_t)(k >> 7) * nch + (n >> 5)) * GBLK_A;
+      const int off = gblk_off(k & 127, n & 31);
+      blk[off] = hi; blk[TC_M * TC_KC + off] = lo;
+    }
+  }
+  if (update) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int ticket = atomicAdd(step + 1, 1);
+      if (ticket == (int)gridDim.x - 1) { step[0] += 1; step[1] = 0; }     // every block has read step[0] by now
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- host side
+template <typename T>
+static int dev_alloc(OduckPpo* h, T*& ptr, size_t count) {
+  if (cudaMalloc((void**)&ptr, count * sizeof(T)) != cudaSuccess) return -1;
+  cudaMemset(ptr, 0, count * sizeof(T));
+  h->allocs.push_back((void*)ptr);
+  return 0;
+}
+
+extern "C" {
+
+int oduck_ppo_destroy(OduckPpo* h) {
+  if (!h) return ODUCK_OK;
+  cudaSetDevice(h->device);
+  for (void* q : h->allocs) cudaFree(q);
+  delete h;
+  return ODUCK_OK;
+}
+
+int oduck_ppo_create(const OduckPpoConfig* cfg, int device, OduckPpo** out) {
+  if (!cfg || !out) return oduck_fail(ODUCK_ERR_ARG, "oduck_ppo_create: bad argument");
+  const int B = cfg->batch_envs, T = cfg->unroll, na = cfg->num_actions;
+  if (B <= 0 || T <= 0 || T > PPO_MAXT || na <= 0 || na > 16) return oduck_fail(ODUCK_ERR_ARG, "oduck_ppo_create: batch_envs / unroll / num_actions out of range");
+  if (cfg->policy_dims[4] != 2 * na || cfg->value_dims[4] != 1) return oduck_fail(ODUCK_ERR_ARG, "oduck_ppo_create: heads must be 2 * num_actions (policy) and 1 (value)");
+  for (int net = 0; net < 2; ++net) {
+    const int32_t* d = net ? cfg->value_dims : cfg->policy_dims;
+    if (d[0] <= 0) return oduck_fail(ODUCK_ERR_ARG, "oduck_ppo_create: bad observation size");
+    for (int l = 1; l <= 3; ++l)
+      if (d[l] <= 0 || d[l] % 128) return oduck_fail(ODUCK_ERR_UNSUPPORTED, "oduck_ppo_create: hidden sizes must be multiples of 128 (reference: 512, 256, 128)");
+  }
+  int ndev = 0;
+  PPO_TRY(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return oduck_fail(ODUCK_ERR_CUDA, "oduck_ppo_create: no such CUDA device");
+  PPO_TRY(cudaSetDevice(device));
+  OduckPpo* h = new OduckPpo();
+  h->cfg = *cfg; h->device = device; h->B = B; h->T = T; h->na = na; h->launches = 0;
+  // ---- parameter segments, packed-operand and partial-gradient layouts
+  SegTable& tb = h->seg;
+  memset(&tb, 0, sizeof(tb));
+  long long off = 0, poff = 0, goff = 0;
+  for (int net = 0; net < 2; ++net) {
+    NetBuf& nb = h->net[net];
+    const int32_t* d = net ? cfg->value_dims : cfg->policy_dims;
+    for (int l = 0; l <= PPO_NL; ++l) nb.dims[l] = d[l];
+    nb.M = (net ? T + 1 : T) * B;
+    nb.Mpad = round_up(nb.M, 128);
+    nb.mtiles = nb.Mpad / 128;
+    for (int l = 0; l < PPO_NL; ++l) {
+      const int K = d[l], N = d[l + 1];
+      const int nt = l == PPO_NL - 1 ? PPO_HEADW : 128;
+      const int Npad = round_up(N, nt), kch = ceil_div(K, TC_KC);
+      Seg w;
+      memset(&w, 0, sizeof(w));
+      w.off = off; w.net = net; w.layer = l; w.bias = 0; w.K = K; w.N = N; w.nt = nt;
+      w.wf = poff; poff += (long long)(Npad / nt) * kch * gblk_b(nt);
+      w.wb = -1;
+      if (l > 0) { w.wb = poff; poff += (long long)ceil_div(K, 128) * ceil_div(N, TC_KC) * GBLK_A; }
+      // dW partials: [nsplit][round_up(K, 128)][Npad]; about 16 splits over the batch chunks
+      const int bch = nb.Mpad / TC_KC, cps = ceil_div(bch, 16);
+      w.nsplit = ceil_div(bch, cps); w.ldo = Npad; w.split_stride = (long long)round_up(K, 128) * Npad;
+      w.dwpart = goff; goff += w.split_stride * w.nsplit;
+      off += (long long)K * N;
+      Seg b = w;
+      b.off = off; b.bias = 1; b.K = 1; b.wf = b.wb = -1;
+      b.ldb = round_up(N, 32); b.nwarprows = nb.Mpad / 32;
+      b.dbpart = goff; goff += (long long)b.ldb * b.nwarprows;
+      off += N;
+      tb.s[tb.n++] = w; tb.s[tb.n++] = b;
+    }
+  }
+  tb.total = off;
+  h->P = off; h->packed_floats = poff; h->partial_floats = goff;
+  bool ok = true;
+  ok = ok && dev_alloc(h, h->dseg, 1) == 0;
+  ok = ok && dev_alloc(h, h->params, (size_t)h->P) == 0 && dev_alloc(h, h->grads, (size_t)h->P) == 0 && dev_alloc(h, h->adam_m, (size_t)h->P) == 0 && dev_alloc(h, h->adam_v, (size_t)h->P) == 0;
+  ok = ok && dev_alloc(h, h->packed, (size_t)poff) == 0 && dev_alloc(h, h->partial, (size_t)goff) == 0;
+  ok = ok && dev_alloc(h, h->adv, (size_t)T * B) == 0 && dev_alloc(h, h->vs, (size_t)T * B) == 0;
+  ok = ok && dev_alloc(h, h->losses, 8) == 0 && dev_alloc(h, h->stats, 4) == 0 && dev_alloc(h, h->step, 2) == 0;
+  h->reduce_blocks = 296;
+  ok = ok && dev_alloc(h, h->sumsq_part, (size_t)h->reduce_blocks) == 0;
+  for (int net = 0; net < 2 && ok; ++net) {
+    NetBuf& nb = h->net[net];
+    const size_t bch = nb.Mpad / TC_KC;
+    for (int l = 0; l < PPO_NL && ok; ++l) {
+      const int K = nb.dims[l];
+      ok = ok && dev_alloc(h, nb.Xr[l], (size_t)nb.mtiles * ceil_div(K, TC_KC) * GBLK_A) == 0;
+      ok = ok && dev_alloc(h, nb.Xt[l], (size_t)ceil_div(K, 128) * bch * GBLK_A) == 0;
+      const int N = nb.dims[l + 1];
+      if (l < PPO_NL - 1) {
+        ok = ok && dev_alloc(h, nb.Z[l], (size_t)nb.Mpad * N) == 0;
+        ok = ok && dev_alloc(h, nb.dZr[l], (size_t)nb.mtiles * (N / TC_KC) * GBLK_A) == 0;
+        ok = ok && dev_alloc(h, nb.dZt[l], (size_t)(N / 128) * bch * GBLK_A) == 0;
+      } else {
+        ok = ok && dev_alloc(h, nb.dZr[l], (size_t)nb.mtiles * GBLK_A) == 0;
+        ok = ok && dev_alloc(h, nb.dZt[l], bch * gblk_b(PPO_HEADW)) == 0;
+      }
+    }
+    ok = ok && dev_alloc(h, nb.out, (size_t)nb.Mpad * PPO_HEADW) == 0;
+  }
+  if (!ok) { oduck_ppo_destroy(h); return oduck_fail(ODUCK_ERR_ALLOC, "oduck_ppo_create: cudaMalloc failed"); }
+  PPO_TRY(cudaMemcpy(h->dseg, &h->seg, sizeof(SegTable), cudaMemcpyHostToDevice));
+  PPO_TRY(cudaDeviceSynchronize());
+  *out = h;
+  return ODUCK_OK;
+}
+
+int64_t oduck_ppo_num_params(const OduckPpo* h) { return h ? h->P : 0; }
+int64_t oduck_ppo_launch_count(const OduckPpo* h) { return h ? h->launches : 0; }
+
+int oduck_ppo_param_info(const OduckPpo* h, int net, int layer, int which, int64_t* offset, int64_t* rows, int64_t* cols) {
+  if (!h || net < 0 || net > 1 || layer < 0 || layer >= PPO_NL || which < 0 || which > 1 || !offset || !rows || !cols) return oduck_fail(ODUCK_ERR_ARG, "oduck_ppo_param_info: bad argument");
+  const Seg& s = h->seg.s[(net * PPO_NL + layer) * 2 + which];
+  *offset = s.off; *rows = which ? 1 : s.K; *cols = s.N;
+  return ODUCK_OK;
+}
+
+static int launch_adam(OduckPpo* h, int update, cudaStream_t st) {
+  const OduckPpoConfig& c = h->cfg;
+  k_ppo_adam<<<h->reduce_blocks, 256, 0, st>>>(h->dseg, h->params, h->grads, h->adam_m, h->adam_v, h->packed, h->sumsq_part, h->reduce_blocks, h->step,
+                                               c.learning_rate, c.adam_b1, c.adam_b2, c.adam_eps, c.max_grad_norm, update);
+  PPO_TRY(cudaGetLastError());
+  h->launches++;
+  return ODUCK_OK;
+}
+
+int oduck_ppo_set_params(OduckPpo* h, const float* flat, int reset_opt, void* stream) {
+  if (!h || !flat) return oduck_fail(ODUCK_ERR_ARG, "oduck_ppo_set_params: bad argument");
+  PPO_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (flat != h->params) PPO_TRY(cudaMemcpyAsync(h->params, flat, (size_t)h->P * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (reset_opt) {
+    PPO_TRY(cudaMemsetAsync(h->adam_m, 0, (size_t)h->P * sizeof(float), st));
+    PPO_TRY(cudaMemsetAsync(h->adam_v, 0, (size_t)h->P * sizeof(float), st));
+    PPO_TRY(cudaMemsetAsync(h->step, 0, 2 * sizeof(int), st));
+  }
+  return launch_adam(h, 0, st);
+}
+
+int oduck_ppo_get_buffer(OduckPpo* h, int id, void** ptr, int64_t* count, int* dtype) {
+  if (!h || !ptr || !count || !dtype) return oduck_fail(ODUCK_ERR_ARG, "oduck_ppo_get_buffer: bad argument");
+  *dtype = ODUCK_DTYPE_F32;
+  switch (id) {
+    case ODUCK_PPO_BUF_PARAMS: *ptr = h->params; *count = h->P; break;
+    case ODUCK_PPO_BUF_GRADS: *ptr = h->grads; *count = h->P; break;
+    case ODUCK_PPO_BUF_ADAM_M: *ptr = h->adam_m; *count = h->P; break;
+    case ODUCK_PPO_BUF_ADAM_V: *ptr = h->adam_v; *count = h->P; break;
+    case ODUCK_PPO_BUF_LOGITS: *ptr = h->net[0].out; *count = (int64_t)h->net[0].Mpad * PPO_HEADW; break;
+    case ODUCK_PPO_BUF_VALUES: *ptr = h->net[1].out; *count = (int64_t)h->net[1].Mpad * PPO_HEADW; break;
+    case ODUCK_PPO_BUF_LOSSES: *ptr = h->losses; *count = 8; *dtype = ODUCK_DTYPE_F64; break;
+    case ODUCK_PPO_BUF_ADV: *ptr = h->adv; *count = (int64_t)h->T * h->B; break;
+    case ODUCK_PPO_BUF_VS: *ptr = h->vs; *count = (int64_t)h->T * h->B; break;
+    case ODUCK_PPO_BUF_STEP: *ptr = h->step; *count = 1; *dtype = ODUCK_DTYPE_I32; break;
+    default: return oduck_fail(ODUCK_ERR_ARG, "oduck_ppo_get_buffer: unknown buffer id");
+  }
+  return ODUCK_OK;
+}
+
+#define GEMM_TRY(call)                                                                                                  \
+  do {                                                                                                                  \
+    cudaError_t e_ = (call);                                                                                            \
+    if (e_ != cudaSuccess) return oduck_fail(ODUCK_ERR_CUDA, std::string("oduck_ppo_minibatch launch: ") + cudaGetErrorString(e_)); \
+    h->launches++;                                                                                                      \
+  } while (0)
+
+static int net_forward(OduckPpo* h, int net, bool simt, cudaStream_t st) {
+  NetBuf& nb = h->net[net];
+  for (int l = 0; l < PPO_NL; ++l) {
+    const Seg& w = h->seg.s[(net * PPO_NL + l) * 2];
+    const Seg& b = h->seg.s[(net * PPO_NL + l) * 2 + 1];
+    GemmParams g;
+    memset(&g, 0, sizeof(g));
+    g.A = nb.Xr[l]; g.B = h->packed + w.wf;
+    g.nchunks = ceil_div(w.K, TC_KC); g.cps = g.nchunks;
+    g.bias = h->params + b.off; g.nvalid = w.N;
+    if (l < PPO_NL - 1) {
+      g.Z = nb.Z[l]; g.ldz = w.N;
+      g.Yr = nb.Xr[l + 1]; g.yr_nch = w.N / TC_KC;
+      g.Yt = nb.Xt[l + 1]; g.yt_nch = nb.Mpad / TC_KC;
+      GEMM_TRY((launch_gemm<128, 3, EPI_FWD>(g, nb.mtiles, w.N / 128, simt, st)));
+    } else {
+      g.out = nb.out; g.ldo = PPO_HEADW;
+      GEMM_TRY((launch_gemm<PPO_HEADW, 4, EPI_OUT>(g, nb.mtiles, 1, simt, st)));
+    }
+  }
+  return ODUCK_OK;
+}
+
+static int net_backward(OduckPpo* h, int net, bool simt, cudaStream_t st) {
+  NetBuf& nb = h->net[net];
+  for (int l = PPO_NL - 1; l >= 0; --l) {
+    const Seg& w = h->seg.s[(net * PPO_NL + l) * 2];
+    {
+      // dW_l = X_l^T dZ_l: rows = in features, columns = out features, contraction over the batch (split-K)
+      GemmParams g;
+      memset(&g, 0, sizeof(g));
+      g.A = nb.Xt[l]; g.B = nb.dZt[l];
+      g.nchunks = nb.Mpad / TC_KC; g.cps = ceil_div(g.nchunks, w.nsplit);
+      g.out = h->partial + w.dwpart; g.ldo = w.ldo; g.out_split = w.split_stride;
+      const int mt = ceil_div(w.K, 128);
+      if (l == PPO_NL - 1) GEMM_TRY((launch_gemm<PPO_HEADW, 4, EPI_DW>(g, mt, 1, simt, st)));
+      else GEMM_TRY((launch_gemm<128, 3, EPI_DW>(g, mt, w.N / 128, simt, st)));
+    }
+    if (l > 0) {
+      // dZ_{l-1} = (dZ_l W_l^T) * swish'(Z_{l-1}): columns = in features of layer l, contraction over its out features
+      const Seg& bprev = h->seg.s[(net * PPO_NL + l - 1) * 2 + 1];
+      GemmParams g;
+      memset(&g, 0, sizeof(g));
+      g.A = nb.dZr[l]; g.B = h->packed + w.wb;
+      g.nchunks = ceil_div(w.N, TC_KC); g.cps = g.nchunks;
+      g.Z = nb.Z[l - 1]; g.ldz = w.K;
+      g.Yr = nb.dZr[l - 1]; g.yr_nch = w.K / TC_KC;
+      g.Yt = nb.dZt[l - 1]; g.yt_nch = nb.Mpad / TC_KC;
+      g.dbpart = h->partial + bprev.dbpart; g.ldb = bprev.ldb;
+      g.nvalid = w.K;
+      GEMM_TRY((launch_gemm<128, 3, EPI_DX>(g, nb.mtiles, w.K / 128, simt, st)));
+    }
+  }
+  return ODUCK_OK;
+}
+
+int oduck_ppo_minibatch(OduckPpo* h, const OduckRollout* ro, const OduckNormalizer* nm, const int32_t* env_idx, const float* noise,
+                        const uint32_t* key, int stages, void* stream) {
+  if (!h || !ro || !nm || !env_idx) return oduck_fail(ODUCK_ERR_ARG, "oduck_ppo_minibatch: bad argument");
+  if (ro->unroll != h->T || ro->num_envs < 1) return oduck_fail(ODUCK_ERR_ARG, "oduck_ppo_minibatch: rollout shape does not match the learner");
+  if ((stages & ODUCK_PPO_STAGE_LOSS) && !noise && !key) return oduck_fail(ODUCK_ERR_ARG, "oduck_ppo_minibatch: entropy term needs noise or a key");
+  PPO_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool simt = (stages & ODUCK_PPO_DEBUG_SIMT) != 0;
+  const OduckPpoConfig& c = h->cfg;
+  NetBuf& np = h->net[0];
+  NetBuf& nv = h->net[1];
+  if (stages & ODUCK_PPO_STAGE_FORWARD) {
+    k_ppo_pack<<<296, 256, 0, st>>>(ro->obs_policy, ro->num_envs, np.dims[0], env_idx, h->B, np.M, np.Mpad, ceil_div(np.dims[0], TC_KC), nm->policy_mean, nm->policy_std, np.Xr[0], np.Xt[0]);
+    GEMM_TRY(cudaGetLastError());
+    k_ppo_pack<<<296, 256, 0, st>>>(ro->obs_value, ro->num_envs, nv.dims[0], env_idx, h->B, nv.M, nv.Mpad, ceil_div(nv.dims[0], TC_KC), nm->value_mean, nm->value_std, nv.Xr[0], nv.Xt[0]);
+    GEMM_TRY(cudaGetLastError());
+    int rc = net_forward(h, 1, simt, st);
+    if (rc) return rc;
+    rc = net_forward(h, 0, simt, st);
+    if (rc) return rc;
+  }
+  if (stages & ODUCK_PPO_STAGE_LOSS) {
+    k_ppo_gae<<<1, 1024, 0, st>>>(nv.out, *ro, env_idx, h->B, h->T, c.discounting, c.gae_lambda, c.reward_scaling, c.normalize_advantage, h->adv, h->vs, h->stats, h->losses);
+    GEMM_TRY(cudaGetLastError());
+    LossParams lp;
+    memset(&lp, 0, sizeof(lp));
+    lp.logits = np.out; lp.values = nv.out; lp.adv = h->adv; lp.vs = h->vs; lp.ro = *ro; lp.idx = env_idx; lp.noise = noise; lp.key = key;
+    lp.B = h->B; lp.T = h->T; lp.na = h->na; lp.Mp = np.M; lp.Mp_pad = np.Mpad; lp.Mv = nv.M; lp.Mv_pad = nv.Mpad;
+    lp.clip_eps = c.clipping_epsilon; lp.entropy_cost = c.entropy_cost;
+    const Seg& bp = h->seg.s[(0 * PPO_NL + PPO_NL - 1) * 2 + 1];
+    const Seg& bv = h->seg.s[(1 * PPO_NL + PPO_NL - 1) * 2 + 1];
+    lp.dZr_p = np.dZr[PPO_NL - 1]; lp.dZt_p = np.dZt[PPO_NL - 1]; lp.db_p = h->partial + bp.dbpart;
+    lp.dZr_v = nv.dZr[PPO_NL - 1]; lp.dZt_v = nv.dZt[PPO_NL - 1]; lp.db_v = h->partial + bv.dbpart;
+    lp.losses = h->losses;
+    k_ppo_loss<<<nv.Mpad / 128, 128, 0, st>>>(lp);
+    GEMM_TRY(cudaGetLastError());
+  }
+  if (stages & ODUCK_PPO_STAGE_BACKWARD) {
+    int rc = net_backward(h, 1, simt, st);
+    if (rc) return rc;
+    rc = net_backward(h, 0, simt, st);
+    if (rc) return rc;
+    k_ppo_grad_reduce<<<h->reduce_blocks, 256, 0, st>>>(h->dseg, h->partial, h->grads, h->sumsq_part);
+    GEMM_TRY(cudaGetLastError());
+  }
+  if (stages & ODUCK_PPO_STAGE_ADAM) {
+    if (!(stages & ODUCK_PPO_STAGE_BACKWARD)) {           // gradients were all-reduced by the caller: recompute their norm
+      k_ppo_gradnorm<<<h->reduce_blocks, 256, 0, st>>>(h->grads, h->P, h->sumsq_part);
+      GEMM_TRY(cudaGetLastError());
+    }
+    return launch_adam(h, 1, st);
+  }
+  return ODUCK_OK;
+}
+
+}  // extern "C"

@@ -30,7 +30,7 @@ from .mjcf import CompiledModel, compile_mjcf
 from .poly_reference_motion import PolyTable
 
 _TORCH_DTYPE = {np.float32: torch.float32, np.int32: torch.int32, np.uint32: torch.int32, np.float64: torch.float64}
-_TYPESTR = {np.float32: "<f4", np.int32: "<i4", np.uint32: "<i4"}
+_TYPESTR = {np.float32: "<f4", np.int32: "<i4", np.uint32: "<i4", np.float64: "<f8"}
 
 
 class _CudaView:

@@ -48,7 +48,10 @@ class PPOConfig:
     update_mode: str = "auto"       # "replicated": all_gather rollouts, identical update on every rank;
                                     # "sharded": every rank updates on its own env shard, gradients all-reduced per minibatch (Brax's pmean);
                                     # "auto": sharded on CUDA with world > 1, else replicated
-    cuda_graph: bool = True         # capture one minibatch update (fwd + bwd + clip + Adam) in a CUDA graph on GPU
+    cuda_graph: bool = True         # (torch learner) capture one minibatch update (fwd + bwd + clip + Adam) in a CUDA graph on GPU
+    learner: str = "auto"           # "device": the fused learner step of include/oduck_ppo.h (tcgen05 GEMMs, fused GAE/loss/Adam kernels);
+                                    # "torch": the PyTorch fp32 twin (the checker of the device learner, and the CPU path of the tests);
+                                    # "auto": device on CUDA, torch otherwise
 
 
 class MLP(torch.nn.Module):
@@ -71,39 +74,41 @@ class MLP(torch.nn.Module):
 
 
 class RunningStats:
-    """brax.training.acme.running_statistics: Welford mean/std per feature (std clipped to [1e-6, 1e6])."""
+    """brax.training.acme.running_statistics.update in its own arithmetic (fp32, batch-Welford): mean/std per feature, std
+    clipped to [1e-6, 1e6]; ``reduce`` merges the ranks' shards (Brax: psum over the pmap axis)."""
 
     def __init__(self, dim, device):
-        self.count = torch.zeros((), device=device, dtype=torch.float64)
-        self.mean = torch.zeros(dim, device=device, dtype=torch.float64)
-        self.m2 = torch.zeros(dim, device=device, dtype=torch.float64)
+        self.count = torch.zeros((), device=device)
+        self.mean = torch.zeros(dim, device=device)
+        self.m2 = torch.zeros(dim, device=device)           # summed_variance
         self.std = torch.ones(dim, device=device)
 
     def update(self, batch: torch.Tensor, reduce: bool = False) -> None:
-        b = batch.reshape(-1, batch.shape[-1]).double()
-        mom = torch.cat([torch.full((1,), float(b.shape[0]), device=b.device, dtype=torch.float64), b.sum(0), (b * b).sum(0)])
-        if reduce:                                           # sharded update: merge the ranks' moments (one small all-reduce)
-            dist.all_reduce(mom)
-        n, bsum, bsq = mom[0], mom[1:1 + b.shape[1]], mom[1 + b.shape[1]:]
-        bmean = bsum / n
-        bm2 = bsq - n * bmean * bmean
-        new_count = self.count + n
-        delta = bmean - self.mean
-        self.m2 += bm2 + delta ** 2 * self.count * n / new_count
-        self.mean += delta * n / new_count
-        self.count = new_count
-        self.std.copy_(torch.sqrt(self.m2 / self.count).clamp(1e-6, 1e6).float())
+        b = batch.reshape(-1, batch.shape[-1])
+        n = torch.full((), float(b.shape[0]), device=b.device)
+        diff_old = b - self.mean
+        dsum = diff_old.sum(0)
+        if reduce:
+            pack = torch.cat([n[None], dsum]); dist.all_reduce(pack); n, dsum = pack[0], pack[1:]
+        self.count = self.count + n
+        self.mean = self.mean + dsum / self.count
+        var_upd = (diff_old * (b - self.mean)).sum(0)
+        if reduce:
+            dist.all_reduce(var_upd)
+        self.m2 = self.m2 + var_upd
+        self.std.copy_(torch.sqrt(self.m2.clamp_min(0.0) / self.count).clamp(1e-6, 1e6))   # rounding can leave a tiny negative sum
 
     @property
     def mean32(self):
-        return self.mean.float()
+        return self.mean
 
 
 class PolicyWeights:
     """Packs a policy MLP + normaliser into ``OduckPolicyWeights`` (row-major [in][out] kernels like flax)."""
 
-    def __init__(self, policy: MLP, obs_dim: int, device):
+    def __init__(self, policy: MLP, obs_dim: int, device, external=None):
         self.policy, self.device = policy, device
+        self.external = external          # [(W [in][out], b)] x 4 views of the device learner's master weights (updated in place)
         self.struct = capi.OduckPolicyWeights()
         self.struct.obs_dim = obs_dim
         hs = [l.out_features for l in policy.layers]
@@ -115,8 +120,11 @@ class PolicyWeights:
     @torch.no_grad()
     def refresh(self, mean: torch.Tensor, std: torch.Tensor) -> None:
         self.mean, self.std = mean.float().contiguous(), std.float().contiguous()
-        self.w = [l.weight.detach().t().contiguous() for l in self.policy.layers]     # [in][out]
-        self.b = [l.bias.detach().contiguous() for l in self.policy.layers]
+        if self.external is not None:
+            self.w, self.b = [w for w, _ in self.external], [b for _, b in self.external]
+        else:
+            self.w = [l.weight.detach().t().contiguous() for l in self.policy.layers]     # [in][out]
+            self.b = [l.bias.detach().contiguous() for l in self.policy.layers]
         self.struct.obs_mean, self.struct.obs_std = self.mean.data_ptr(), self.std.data_ptr()
         for i in range(4):
             self.struct.w[i], self.struct.b[i] = self.w[i].data_ptr(), self.b[i].data_ptr()
@@ -135,8 +143,9 @@ def policy_forward(env, weights: PolicyWeights, keys: Optional[torch.Tensor], de
     return act, raw, logp
 
 
-def torch_policy_logprob(policy: MLP, obs_n: torch.Tensor, raw: torch.Tensor):
-    """log-prob / entropy of ``raw`` (pre-tanh) under NormalTanh(policy(obs)) -- the differentiable twin of the kernel's head."""
+def torch_policy_logprob(policy: MLP, obs_n: torch.Tensor, raw: torch.Tensor, noise: Optional[torch.Tensor] = None):
+    """log-prob / entropy of ``raw`` (pre-tanh) under NormalTanh(policy(obs)) -- the differentiable twin of the kernel's head.
+    ``noise``: standard normals for Brax's sampled entropy term (default: fresh ``randn``)."""
     out = policy(obs_n)
     loc, sp = out.chunk(2, dim=-1)
     scale = torch.nn.functional.softplus(sp) + 0.001
@@ -145,7 +154,7 @@ def torch_policy_logprob(policy: MLP, obs_n: torch.Tensor, raw: torch.Tensor):
     ldj = 2.0 * (math.log(2.0) - raw - torch.nn.functional.softplus(-2.0 * raw))
     logp = (logn - ldj).sum(-1)
     # Brax entropy: normal entropy + E[log det jacobian] estimated at a fresh sample
-    sample = loc + scale * torch.randn_like(loc)
+    sample = loc + scale * (torch.randn_like(loc) if noise is None else noise)
     ent = (0.5 + 0.5 * math.log(2 * math.pi) + torch.log(scale) + 2.0 * (math.log(2.0) - sample - torch.nn.functional.softplus(-2.0 * sample))).sum(-1)
     return logp, ent
 
@@ -185,6 +194,79 @@ def all_gather_rollout(batch: Dict[str, torch.Tensor], world: int) -> Dict[str, 
     return out
 
 
+class DeviceLearner:
+    """Host mirror of include/oduck_ppo.h: one SGD step of Brax PPO per ``minibatch`` call, entirely on the device
+    (gather/pack, tcgen05 forward + backward GEMMs, GAE/loss, clip + Adam).  Master weights live in the library's flat
+    parameter vector (per net, per layer: W[in][out] like flax, then b); ``tensor()`` hands out zero-copy views."""
+
+    def __init__(self, cfg: PPOConfig, policy: MLP, value: MLP, batch_envs: int, num_actions: int, device):
+        from .joystick import _CudaView
+        self._view_cls = _CudaView
+        self.device = torch.device(device)
+        c = capi.OduckPpoConfig()
+        c.batch_envs, c.unroll, c.num_actions = int(batch_envs), int(cfg.unroll_length), int(num_actions)
+        for net, mlp in ((0, policy), (1, value)):
+            dims = [mlp.layers[0].in_features] + [l.out_features for l in mlp.layers]
+            for i, d in enumerate(dims):
+                (c.policy_dims if net == 0 else c.value_dims)[i] = d
+        c.normalize_advantage = 1
+        c.discounting, c.gae_lambda, c.clipping_epsilon, c.entropy_cost = cfg.discounting, cfg.gae_lambda, cfg.clipping_epsilon, cfg.entropy_cost
+        c.reward_scaling, c.learning_rate, c.max_grad_norm = cfg.reward_scaling, cfg.learning_rate, cfg.max_grad_norm if cfg.max_grad_norm else 0.0
+        c.adam_b1, c.adam_b2, c.adam_eps = 0.9, 0.999, 1e-8
+        self.batch_envs = int(batch_envs)
+        self.h = capi.PpoHandle(capi.load_cuda_library(), c, self.device.index or 0)
+        self.params, self.grads = self.view("PARAMS"), self.view("GRADS")
+        self.losses, self.step = self.view("LOSSES"), self.view("STEP")
+        self.load_from(policy, value, reset_opt=True)
+
+    def view(self, name: str) -> torch.Tensor:
+        ptr, count, dt = self.h.buffer_info(name)
+        with torch.cuda.device(self.device):
+            return torch.as_tensor(self._view_cls(ptr, (count,), (1,), dt), device=self.device)
+
+    def tensor(self, net: int, layer: int, which: int) -> torch.Tensor:
+        off, r, c = self.h.param_info(net, layer, which)
+        t = self.params[off:off + r * c]
+        return t.view(r, c) if which == 0 else t
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    @torch.no_grad()
+    def load_from(self, policy: MLP, value: MLP, reset_opt: bool) -> None:
+        for net, mlp in ((0, policy), (1, value)):
+            for l, lin in enumerate(mlp.layers):
+                self.tensor(net, l, 0).copy_(lin.weight.t())
+                self.tensor(net, l, 1).copy_(lin.bias)
+        self.h.set_params(self.params.data_ptr(), reset_opt, self._stream())
+
+    @torch.no_grad()
+    def store_to(self, policy: MLP, value: MLP) -> None:
+        for net, mlp in ((0, policy), (1, value)):
+            for l, lin in enumerate(mlp.layers):
+                lin.weight.copy_(self.tensor(net, l, 0).t())
+                lin.bias.copy_(self.tensor(net, l, 1))
+
+    def policy_views(self):
+        return [(self.tensor(0, l, 0), self.tensor(0, l, 1)) for l in range(4)]
+
+    def minibatch(self, rollout: "capi.OduckRollout", norm: "capi.OduckNormalizer", env_idx: int, noise: int = 0, key: int = 0, stages: int = capi.PPO_ALL) -> None:
+        self.h.minibatch(rollout, norm, env_idx, noise, key, stages, self._stream())
+
+
+def rollout_struct(batch: Dict[str, torch.Tensor]) -> "capi.OduckRollout":
+    """OduckRollout over the trainer's rollout dict (tensors must stay alive while the learner runs)."""
+    T, N = batch["reward"].shape
+    for k, v in batch.items():
+        if not v.is_contiguous() or v.dtype != torch.float32:
+            raise ValueError(f"rollout tensor {k} must be contiguous float32")
+    ro = capi.OduckRollout()
+    ro.num_envs, ro.unroll = int(N), int(T)
+    ro.obs_policy, ro.obs_value, ro.raw_action = batch["obs_p"].data_ptr(), batch["obs_v"].data_ptr(), batch["raw"].data_ptr()
+    ro.log_prob, ro.reward, ro.done, ro.truncation = batch["logp"].data_ptr(), batch["reward"].data_ptr(), batch["done"].data_ptr(), batch["trunc"].data_ptr()
+    return ro
+
+
 class PPOTrainer:
     def __init__(self, env, cfg: PPOConfig, rank: int = 0, world: int = 1, progress_fn: Optional[Callable] = None,
                  policy_params_fn: Optional[Callable] = None):
@@ -199,7 +281,16 @@ class PPOTrainer:
         self.opt = torch.optim.Adam(list(self.policy.parameters()) + list(self.value.parameters()), lr=cfg.learning_rate, capturable=dev.type == "cuda")
         self.stats = {k: RunningStats(env.observation_size[k][0], dev) for k in (cfg.policy_obs_key, cfg.value_obs_key)}
         self._mean32 = {k: torch.zeros(env.observation_size[k][0], device=dev) for k in self.stats}
-        self.weights = PolicyWeights(self.policy, env.observation_size[cfg.policy_obs_key][0], dev)
+        self.learner = cfg.learner if cfg.learner != "auto" else ("device" if dev.type == "cuda" else "torch")
+        self.dev_learner: Optional[DeviceLearner] = None
+        if self.learner == "device":
+            mode = cfg.update_mode if cfg.update_mode != "auto" else ("sharded" if world > 1 else "replicated")
+            n_update = self.n_local if (mode == "sharded" and world > 1) else cfg.num_envs
+            self.dev_learner = DeviceLearner(cfg, self.policy, self.value, n_update // cfg.num_minibatches, na, dev)
+        self.weights = PolicyWeights(self.policy, env.observation_size[cfg.policy_obs_key][0], dev,
+                                     external=self.dev_learner.policy_views() if self.dev_learner else None)
+        self._ones = {k: torch.ones(env.observation_size[k][0], device=dev) for k in self.stats}
+        self._zeros = {k: torch.zeros(env.observation_size[k][0], device=dev) for k in self.stats}
         self.key = jr.PRNGKey(cfg.seed + 17)
         self.env_steps = 0
         env.randomize(shard_keys(cfg.seed + 1, world, rank, self.n_local))
@@ -232,7 +323,7 @@ class PPOTrainer:
         return buf
 
     # ------------------------------------------------------------------ update
-    def _minibatch_loss(self, mb: Dict[str, torch.Tensor]):
+    def _minibatch_loss(self, mb: Dict[str, torch.Tensor], noise: Optional[torch.Tensor] = None):
         cfg = self.cfg
         pk, vk = cfg.policy_obs_key, cfg.value_obs_key
         if cfg.normalize_observations:
@@ -246,8 +337,8 @@ class PPOTrainer:
         termination = done * (1 - trunc)
         rewards = mb["reward"] * cfg.reward_scaling
         vs, adv = compute_gae(trunc, termination, rewards, baseline.detach(), bootstrap.detach(), cfg.gae_lambda, cfg.discounting)
-        adv = (adv - adv.mean()) / (adv.std() + 1e-8)
-        logp, ent = torch_policy_logprob(self.policy, obs_p[:-1], mb["raw"])
+        adv = (adv - adv.mean()) / (adv.std(unbiased=False) + 1e-8)      # jnp.std: population std
+        logp, ent = torch_policy_logprob(self.policy, obs_p[:-1], mb["raw"], noise)
         rho = torch.exp(logp - mb["logp"])
         policy_loss = -torch.min(rho * adv, rho.clamp(1 - cfg.clipping_epsilon, 1 + cfg.clipping_epsilon) * adv).mean()
         v_loss = ((vs - baseline) ** 2).mean() * 0.5 * 0.5
@@ -306,6 +397,8 @@ class PPOTrainer:
             self._mean32[k].copy_(self.stats[k].mean32)
         T, N = batch["reward"].shape
         gen = torch.Generator(device="cpu").manual_seed(cfg.seed + self.env_steps + (self.rank if sharded else 0))
+        if self.dev_learner is not None:
+            return self._update_device(batch, sharded, gen)
         mb = N // cfg.num_minibatches
         use_graph = cfg.cuda_graph and self.env.device.type == "cuda"
         keys = ("obs_p", "obs_v", "raw", "logp", "reward", "done", "trunc")
@@ -340,6 +433,45 @@ class PPOTrainer:
             o = self._out.tolist()
             return dict(loss=o[0], policy_loss=o[1], v_loss=o[2], entropy=o[3])
         return dict(loss=float(loss.detach()), policy_loss=float(pl.detach()), v_loss=float(vl.detach()), entropy=float(en.detach()))
+
+    def _update_device(self, batch: Dict[str, torch.Tensor], sharded: bool, gen: torch.Generator) -> Dict[str, float]:
+        """The update through include/oduck_ppo.h: one library call per minibatch, no host sync until the metrics are read."""
+        cfg, L = self.cfg, self.dev_learner
+        pk, vk = cfg.policy_obs_key, cfg.value_obs_key
+        T, N = batch["reward"].shape
+        B = N // cfg.num_minibatches
+        if B != L.batch_envs:
+            raise ValueError(f"device learner was built for {L.batch_envs} envs per minibatch, got {B}")
+        dev = self.env.device
+        ro = rollout_struct(batch)
+        nm = capi.OduckNormalizer()
+        if cfg.normalize_observations:
+            nm.policy_mean, nm.policy_std, nm.value_mean, nm.value_std = self._mean32[pk].data_ptr(), self.stats[pk].std.data_ptr(), self._mean32[vk].data_ptr(), self.stats[vk].std.data_ptr()
+        else:
+            nm.policy_mean, nm.policy_std, nm.value_mean, nm.value_std = self._zeros[pk].data_ptr(), self._ones[pk].data_ptr(), self._zeros[vk].data_ptr(), self._ones[vk].data_ptr()
+        n_mb = cfg.num_updates_per_batch * cfg.num_minibatches
+        self.key, sub = jr.split(self.key, 2)
+        if sharded:
+            sub = jr.split(sub, self.world)[self.rank]
+        keys = torch.from_numpy(jr.split(sub, n_mb).view(np.int32).copy()).to(dev)        # entropy-sample keys, one per minibatch
+        keep = [keys]
+        for e in range(cfg.num_updates_per_batch):
+            perm = torch.randperm(N, generator=gen).to(torch.int32).to(dev)
+            keep.append(perm)
+            for i in range(cfg.num_minibatches):
+                idx = perm.data_ptr() + 4 * i * B
+                key = keys.data_ptr() + 8 * (e * cfg.num_minibatches + i)
+                if sharded:
+                    L.minibatch(ro, nm, idx, 0, key, capi.PPO_STAGE_FORWARD | capi.PPO_STAGE_LOSS | capi.PPO_STAGE_BACKWARD)
+                    dist.all_reduce(L.grads)
+                    L.grads.div_(self.world)
+                    L.minibatch(ro, nm, idx, 0, key, capi.PPO_STAGE_ADAM)
+                else:
+                    L.minibatch(ro, nm, idx, 0, key, capi.PPO_ALL)
+        self.env.handle.policy_invalidate()                                                # the actor repacks the new weights on its next forward
+        o = L.losses.tolist()                                                              # host sync: the update is done, `keep` may go
+        del keep
+        return dict(loss=o[0], policy_loss=o[1], v_loss=o[2], entropy=o[3], clip_fraction=o[5])
 
     def training_step(self) -> Dict[str, float]:
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if self.env.device.type == "cuda" else None
@@ -378,14 +510,27 @@ class PPOTrainer:
 
     def params(self):
         pk = self.cfg.policy_obs_key
+        if self.dev_learner is not None:
+            self.dev_learner.store_to(self.policy, self.value)
         return {"normalizer": {k: {"mean": s.mean32.cpu(), "std": s.std.cpu(), "count": float(s.count)} for k, s in self.stats.items()},
                 "policy": {k: v.cpu() for k, v in self.policy.state_dict().items()}, "value": {k: v.cpu() for k, v in self.value.state_dict().items()},
-                "optimizer": self.opt.state_dict(), "env_steps": self.env_steps, "policy_obs_key": pk}
+                "optimizer": self.opt.state_dict() if self.dev_learner is None else
+                {"device_adam": {"m": self.dev_learner.view("ADAM_M").cpu(), "v": self.dev_learner.view("ADAM_V").cpu(), "step": int(self.dev_learner.step.item())}},
+                "env_steps": self.env_steps, "policy_obs_key": pk}
 
     def load(self, params) -> None:
-        self.policy.load_state_dict(params["policy"]); self.value.load_state_dict(params["value"]); self.opt.load_state_dict(params["optimizer"])
+        self.policy.load_state_dict(params["policy"]); self.value.load_state_dict(params["value"])
+        if self.dev_learner is not None:
+            L = self.dev_learner
+            L.load_from(self.policy, self.value, reset_opt=True)
+            ad = params["optimizer"].get("device_adam") if isinstance(params["optimizer"], dict) else None
+            if ad is not None:
+                L.view("ADAM_M").copy_(ad["m"].to(self.env.device)); L.view("ADAM_V").copy_(ad["v"].to(self.env.device)); L.step.fill_(int(ad["step"]))
+            self.env.handle.policy_invalidate()
+        else:
+            self.opt.load_state_dict(params["optimizer"])
         for k, s in self.stats.items():
             d = params["normalizer"][k]
-            s.mean = d["mean"].double().to(self.env.device); s.std.copy_(d["std"].to(self.env.device)); s.count = torch.tensor(d["count"], dtype=torch.float64, device=self.env.device)
-            s.m2 = (s.std.double() ** 2) * s.count
+            s.mean = d["mean"].float().to(self.env.device); s.std.copy_(d["std"].to(self.env.device)); s.count = torch.tensor(float(d["count"]), device=self.env.device)
+            s.m2 = (s.std ** 2) * s.count
         self.env_steps = int(params["env_steps"])

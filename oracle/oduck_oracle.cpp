@@ -1395,6 +1395,7 @@ int oduck_create(const OduckModel* model, const OduckEnvConfig* cfg, int num_env
 int oduck_destroy(OduckHandle* h) { delete h; return ODUCK_OK; }
 int oduck_num_envs(const OduckHandle* h) { return h ? h->n : 0; }
 int64_t oduck_launch_count(const OduckHandle* h) { return h ? h->launches : 0; }
+int oduck_policy_invalidate(OduckHandle*) { return ODUCK_OK; }   // no packed copy on the CPU
 
 int oduck_randomize(OduckHandle* h, const uint32_t* keys, void*) {
   if (!h || !keys) return fail(ODUCK_ERR_ARG, "oduck_randomize: bad argument");

@@ -1,0 +1,242 @@
+"""The on-device PPO learner step (include/oduck_ppo.h) against its checker, the PyTorch fp32 twin.
+
+Floating-point path => the oracle is a plain PyTorch fp32 restatement of Brax's compute_ppo_loss + optax clip/Adam
+(ppo.py: compute_gae, torch_policy_logprob; brax/training/agents/ppo/losses.py is an un-vendored dependency of the
+reference, call site playground/common/runner.py:104-118).  Stated tolerances (3xTF32 GEMMs, fp32 everywhere else):
+head outputs 5e-5 abs, losses 1e-5 rel, gradients 2e-4 of the gradient norm per tensor, parameters after Adam 2e-6 abs.
+Every stage is run twice: tensor cores (product path) and the CUDA-core twin of the GEMM (ODUCK_PPO_DEBUG_SIMT), so a
+failure localises to the MMA/descriptor code or to the operand layouts / epilogues.
+"""
+import ctypes as C
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from open_duck_playground_b200 import capi, ppo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "oduck_ppo.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(oduck_ppo_[a-z_]+)\s*\(", text)))
+
+
+def test_cuda_library_exports_the_learner_surface():
+    path = capi.cuda_library_path()
+    if not os.path.exists(path):
+        import __graft_entry__
+        __graft_entry__.build()
+    lib = capi.Library(path, is_device=True)
+    names = _declared()
+    assert "oduck_ppo_minibatch" in names and "oduck_ppo_create" in names and len(names) >= 8
+    for n in names:
+        assert hasattr(lib.lib, n), n
+    assert lib.has_ppo
+
+
+def test_config_struct_matches_header():
+    # field order / count of OduckPpoConfig in the header and in capi.py
+    text = open(os.path.join(ROOT, "include", "oduck_ppo.h")).read()
+    body = text[text.index("typedef struct OduckPpoConfig {"):text.index("} OduckPpoConfig;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.replace("typedef struct OduckPpoConfig {", "").strip()
+        if not decl:
+            continue
+        names = decl.split(None, 1)[1]
+        fields += [re.sub(r"\[.*\]", "", x).strip() for x in names.split(",")]
+    assert fields == [f[0] for f in capi.OduckPpoConfig._fields_]
+
+
+# ----------------------------------------------------------------------------------------------------- GPU parity
+def _make(seed, N, T, nmb, dev):
+    torch.manual_seed(seed)
+    cfg = ppo.PPOConfig(num_envs=N, unroll_length=T, num_minibatches=nmb)
+    policy = ppo.MLP([101, 512, 256, 128, 28]).to(dev)
+    value = ppo.MLP([212, 512, 256, 128, 1]).to(dev)
+    with torch.no_grad():                                        # non-zero biases so that their gradients / updates are exercised
+        for m in (policy, value):
+            for lin in m.layers:
+                lin.bias.uniform_(-0.1, 0.1)
+    g = torch.Generator(device="cpu").manual_seed(seed + 1)
+    r = lambda *s: torch.randn(*s, generator=g)
+    batch = {"obs_p": r(T + 1, N, 101) * 2 + 0.3, "obs_v": r(T + 1, N, 212) * 3 - 0.5, "raw": r(T, N, 14) * 0.8, "logp": r(T, N) * 0.3 - 12.0,
+             "reward": torch.rand(T, N, generator=g) * 0.2, "done": (torch.rand(T, N, generator=g) < 0.1).float(), "trunc": torch.zeros(T, N)}
+    batch["trunc"] = batch["done"] * (torch.rand(T, N, generator=g) < 0.3).float()
+    batch = {k: v.to(dev).contiguous() for k, v in batch.items()}
+    norm = {"pm": (r(101) * 0.2).to(dev), "ps": (torch.rand(101, generator=g) + 0.5).to(dev), "vm": (r(212) * 0.2).to(dev), "vs": (torch.rand(212, generator=g) + 0.5).to(dev)}
+    return cfg, policy, value, batch, norm
+
+
+def _twin_loss(cfg, policy, value, batch, norm, idx, noise):
+    """Brax compute_ppo_loss on the minibatch made of env columns ``idx`` (PyTorch fp32)."""
+    mb = {k: v[:, idx] for k, v in batch.items()}
+    obs_p = (mb["obs_p"] - norm["pm"]) / norm["ps"]
+    obs_v = (mb["obs_v"] - norm["vm"]) / norm["vs"]
+    logits = policy(obs_p[:-1])
+    values = value(obs_v).squeeze(-1)
+    baseline, bootstrap = values[:-1], values[-1]
+    trunc, done = mb["trunc"], mb["done"]
+    termination = done * (1 - trunc)
+    vs, adv_raw = ppo.compute_gae(trunc, termination, mb["reward"] * cfg.reward_scaling, baseline.detach(), bootstrap.detach(), cfg.gae_lambda, cfg.discounting)
+    adv = (adv_raw - adv_raw.mean()) / (adv_raw.std(unbiased=False) + 1e-8)
+    logp, ent = ppo.torch_policy_logprob(policy, obs_p[:-1], mb["raw"], noise)
+    # behaviour log-prob close to the target one so that ratios are O(1) and both clip branches occur
+    rho = torch.exp(logp - mb["logp"])
+    pl = -torch.min(rho * adv, rho.clamp(1 - cfg.clipping_epsilon, 1 + cfg.clipping_epsilon) * adv).mean()
+    vl = ((vs - baseline) ** 2).mean() * 0.25
+    en = ent.mean()
+    return pl + vl - cfg.entropy_cost * en, pl, vl, en, logits, values, adv, vs
+
+
+def _flat(policy, value, grad=False):
+    out = []
+    for m in (policy, value):
+        for lin in m.layers:
+            w, b = (lin.weight.grad, lin.bias.grad) if grad else (lin.weight.detach(), lin.bias.detach())
+            out += [w.t().reshape(-1), b.reshape(-1)]
+    return torch.cat(out)
+
+
+def _segments(L):
+    return [(net, l, which, *L.h.param_info(net, l, which)) for net in (0, 1) for l in range(4) for which in (0, 1)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("simt", [True, False], ids=["cuda-core-twin", "tcgen05"])
+@pytest.mark.parametrize("shape", [(48, 5, 3), (512, 20, 2)], ids=["ragged-M80", "B256xT20"])
+def test_learner_stages_match_torch(simt, shape):
+    N, T, nmb = shape
+    dev = torch.device("cuda:0")
+    cfg, policy, value, batch, norm = _make(3, N, T, nmb, dev)
+    B = N // nmb
+    L = ppo.DeviceLearner(cfg, policy, value, B, 14, dev)
+    assert L.h.num_params == sum(p.numel() for m in (policy, value) for p in m.parameters())
+    assert torch.equal(L.params, _flat(policy, value))
+    # make the behaviour log-prob consistent with the current policy (ratios near 1, some clipped)
+    with torch.no_grad():
+        lp, _ = ppo.torch_policy_logprob(policy, (batch["obs_p"][:-1] - norm["pm"]) / norm["ps"], batch["raw"])
+        batch["logp"] = (lp + 0.25 * torch.randn_like(lp)).contiguous()
+    idx = torch.randperm(N, generator=torch.Generator().manual_seed(5))[:B].to(dev)
+    noise = torch.randn(T * B, 14, generator=torch.Generator().manual_seed(6)).to(dev)
+    ro = ppo.rollout_struct(batch)
+    nm = capi.OduckNormalizer()
+    nm.policy_mean, nm.policy_std, nm.value_mean, nm.value_std = norm["pm"].data_ptr(), norm["ps"].data_ptr(), norm["vm"].data_ptr(), norm["vs"].data_ptr()
+    idx32 = idx.to(torch.int32).contiguous()
+    dbg = capi.PPO_DEBUG_SIMT if simt else 0
+    F, Ls, Bk, Ad = capi.PPO_STAGE_FORWARD, capi.PPO_STAGE_LOSS, capi.PPO_STAGE_BACKWARD, capi.PPO_STAGE_ADAM
+
+    loss, pl, vl, en, logits, values, adv, vs = _twin_loss(cfg, policy, value, batch, norm, idx, noise.view(T, B, 14))
+    loss.backward()
+
+    # ---- forward
+    L.minibatch(ro, nm, idx32.data_ptr(), noise.data_ptr(), 0, F | dbg)
+    torch.cuda.synchronize()
+    lg = L.view("LOGITS").view(-1, 32)[:T * B, :28]
+    vv = L.view("VALUES").view(-1, 32)[:(T + 1) * B, 0]
+    e_lg = (lg - logits.detach().reshape(T * B, 28)).abs().max().item()
+    e_v = (vv - values.detach().reshape(-1)).abs().max().item()
+    print(f"forward: max|dlogits|={e_lg:.2e} max|dvalue|={e_v:.2e}")
+    assert e_lg < 5e-5 and e_v < 5e-5
+    # ---- loss
+    L.minibatch(ro, nm, idx32.data_ptr(), noise.data_ptr(), 0, Ls | dbg)
+    torch.cuda.synchronize()
+    o = L.losses.tolist()
+    e_adv = (L.view("ADV").view(T, B) - adv).abs().max().item()
+    e_vs = (L.view("VS").view(T, B) - vs).abs().max().item()
+    print(f"loss: device {o[:4]} torch {[loss.item(), pl.item(), vl.item(), en.item()]} max|dadv|={e_adv:.2e} max|dvs|={e_vs:.2e}")
+    assert e_adv < 2e-4 and e_vs < 1e-4
+    for a, b in zip(o[:4], (loss, pl, vl, en)):
+        assert abs(a - b.item()) < 1e-5 * max(1.0, abs(b.item())) + 2e-6
+    # ---- backward
+    L.minibatch(ro, nm, idx32.data_ptr(), noise.data_ptr(), 0, Bk | dbg)
+    torch.cuda.synchronize()
+    gref = _flat(policy, value, grad=True)
+    gdev = L.grads.clone()
+    worst = 0.0
+    for net, l, which, off, r, c in _segments(L):
+        a, b = gdev[off:off + r * c], gref[off:off + r * c]
+        rel = ((a - b).norm() / (b.norm() + 1e-12)).item()
+        worst = max(worst, rel)
+        print(f"grad net={net} layer={l} {'b' if which else 'W'}: |ref|={b.norm().item():.3e} rel err={rel:.2e}")
+        assert rel < 2e-4, (net, l, which, rel)
+    # ---- clip + Adam, two steps (bias correction / step counter)
+    params_ref = _flat(policy, value).clone()
+    m1, m2 = torch.zeros_like(params_ref), torch.zeros_like(params_ref)
+    for step in (1, 2):
+        if step == 2:                                           # the second step re-runs the whole pipeline with the updated weights
+            L.store_to(policy, value)
+            for m in (policy, value):
+                m.zero_grad()
+            loss2, *_ = _twin_loss(cfg, policy, value, batch, norm, idx, noise.view(T, B, 14))
+            loss2.backward()
+            gref = _flat(policy, value, grad=True)
+            params_ref = _flat(policy, value).clone()
+            L.minibatch(ro, nm, idx32.data_ptr(), noise.data_ptr(), 0, F | Ls | Bk | dbg)
+        gn = gref.norm()
+        g = gref * (cfg.max_grad_norm / gn) if gn >= cfg.max_grad_norm else gref            # optax.clip_by_global_norm
+        m1 = 0.9 * m1 + 0.1 * g
+        m2 = 0.999 * m2 + 0.001 * g * g
+        upd = cfg.learning_rate * (m1 / (1 - 0.9 ** step)) / (torch.sqrt(m2 / (1 - 0.999 ** step)) + 1e-8)
+        L.minibatch(ro, nm, idx32.data_ptr(), noise.data_ptr(), 0, Ad | dbg)
+        torch.cuda.synchronize()
+        assert int(L.step.item()) == step
+        d = (L.params - (params_ref - upd)).abs()
+        err, frac = d.max().item(), (d > 2e-6).float().mean().item()
+        print(f"adam step {step}: |g|={gn.item():.3e} max|dparam|={err:.2e} fraction>2e-6: {frac:.2e}")
+        # Adam's first steps are sign-like: an element whose gradient is ~1e-6 of the typical size amplifies the GEMM rounding
+        # error, so a handful of the 0.5 M elements may move differently (by at most one lr); everything else agrees to 2e-6
+        assert frac < 1e-4 and err < 1.1 * cfg.learning_rate
+
+
+@pytest.mark.gpu
+def test_in_kernel_entropy_noise_is_standard_normal_and_keyed():
+    dev = torch.device("cuda:0")
+    cfg, policy, value, batch, norm = _make(4, 256, 20, 1, dev)
+    L = ppo.DeviceLearner(cfg, policy, value, 256, 14, dev)
+    ro = ppo.rollout_struct(batch)
+    nm = capi.OduckNormalizer()
+    nm.policy_mean, nm.policy_std, nm.value_mean, nm.value_std = norm["pm"].data_ptr(), norm["ps"].data_ptr(), norm["vm"].data_ptr(), norm["vs"].data_ptr()
+    idx = torch.arange(256, dtype=torch.int32, device=dev)
+    ents = []
+    for k in (1, 1, 2):
+        key = torch.tensor([0, k], dtype=torch.int32, device=dev)
+        L.minibatch(ro, nm, idx.data_ptr(), 0, key.data_ptr(), capi.PPO_STAGE_FORWARD | capi.PPO_STAGE_LOSS)
+        torch.cuda.synchronize()
+        ents.append(L.losses.tolist()[3])
+    assert ents[0] == ents[1] and ents[0] != ents[2]                       # same key -> same draw, new key -> new draw
+    # E[entropy] over fresh normals (torch) agrees with the in-kernel draw within Monte-Carlo error
+    with torch.no_grad():
+        _, ent = ppo.torch_policy_logprob(policy, (batch["obs_p"][:-1] - norm["pm"]) / norm["ps"], batch["raw"])
+    assert abs(ent.mean().item() - ents[0]) < 0.15
+
+
+@pytest.mark.gpu
+def test_trainer_device_learner_tracks_torch_learner():
+    """Same seeds, one training step each: the device learner and the torch twin see the same rollout and the same
+    minibatch permutation; only the entropy-sample noise differs (threefry vs torch.randn), which enters with weight 0.005."""
+    from open_duck_playground_b200.joystick import Joystick
+    res = {}
+    for kind in ("torch", "device"):
+        env = Joystick("flat_terrain_backlash", device="cuda:0")
+        cfg = ppo.PPOConfig(num_envs=512, unroll_length=5, num_minibatches=4, num_updates_per_batch=2, learner=kind, cuda_graph=False)
+        tr = ppo.PPOTrainer(env, cfg)
+        m = tr.training_step()
+        p = tr.params()
+        res[kind] = (m, torch.cat([v.flatten() for v in p["policy"].values()]), torch.cat([v.flatten() for v in p["value"].values()]))
+        assert math.isfinite(m["loss"])
+    mt, pt, vt = res["torch"]
+    md, pd_, vd = res["device"]
+    print("torch", mt, "device", md)
+    assert abs(mt["v_loss"] - md["v_loss"]) < 0.05 * max(1e-3, abs(mt["v_loss"]))
+    # 8 Adam steps of lr 3e-4 move a weight by at most ~2.4e-3; on average the two learners must agree far inside that
+    # (sign-like first steps amplify the entropy-noise difference on individual near-zero-gradient elements)
+    assert (pt - pd_).abs().mean().item() < 1e-4 and (vt - vd).abs().mean().item() < 1e-4
+    assert (pt - pd_).abs().max().item() < 2.5e-3 and (vt - vd).abs().max().item() < 2.5e-3
