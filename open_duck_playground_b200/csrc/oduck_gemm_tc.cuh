@@ -30,7 +30,8 @@ struct GemmParams {
   const float* B;        // [ntiles][nchunks][gblk_b(NT)]
   int nchunks, cps;      // k-chunks of the operands; chunks per split (gridDim.z = ceil(nchunks / cps), no split is empty)
   const float* bias;     // FWD / OUT: [nvalid]
-  float* Z; int ldz;     // FWD: pre-activations written; DX: pre-activations read ([rows][ldz])
+  float* Z; int z_nch;   // FWD: pre-activations written; DX: pre-activations read.  Blocked like R() without the hi/lo split:
+                         // block (mt, n / 32) of 128 x 32 floats, so that a warp's float4 accesses are 128-byte segments
   float* Yr; int yr_nch; // R(Y):   block (mt, n / 32)
   float* Yt; int yt_nch; // R(Y^T): block (n / 128, row / 32), yt_nch = padded rows / 32
   float* out; int ldo;   // OUT: plain [rows][ldo]; DW: partial sums [split][rows][ldo]
@@ -62,6 +63,23 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], const int lane) {
   return v[0];
 }
 
+// In-register 32 x 32 transpose over a warp: in: lane r holds row r (v[c] = X[r][c]); out: lane c holds column c (v[r] = X[r][c]).
+// Five butterfly stages, 16 exchanges each: stage s swaps the off-diagonal blocks selected by bit s of (lane, index).
+__device__ __forceinline__ void warp_transpose32(float (&v)[32], const int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      if ((i & s) == 0) {
+        const float send = up ? v[i] : v[i + s];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, s);
+        if (up) v[i] = recv; else v[i + s] = recv;
+      }
+    }
+  }
+}
+
 // 32 consecutive output columns [n0, n0 + 32) of output row `row` (tile row rt of tile mt), split z.
 template <int EPI>
 __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const int mt, const int rt, const int n0, const int z, const int lane, float (&v)[32]) {
@@ -85,7 +103,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const int mt,
     return;
   }
   // FWD: y = swish(acc + bias), pre-activation kept for the backward pass.  DX: y = acc * swish'(z).
-  float* zrow = p.Z + (size_t)row * p.ldz + n0;
+  float* zblk = p.Z + ((size_t)mt * p.z_nch + (n0 >> 5)) * (TC_M * TC_KC);
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     if (EPI == EPI_FWD) {
@@ -98,9 +116,9 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const int mt,
         pw[e] = zz;
         v[4 * q + e] = zz / (1.f + __expf(-zz));
       }
-      *reinterpret_cast<float4*>(zrow + 4 * q) = w;
+      *reinterpret_cast<float4*>(zblk + gblk_off(rt, 4 * q)) = w;
     } else {
-      const float4 w = *reinterpret_cast<const float4*>(zrow + 4 * q);
+      const float4 w = *reinterpret_cast<const float4*>(zblk + gblk_off(rt, 4 * q));
       const float* pw = reinterpret_cast<const float*>(&w);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -123,20 +141,26 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const int mt,
     }
   }
   {
-    // transposed operand: element (n, row) of Y^T; the warp's 32 rows are exactly one k-chunk of it
+    // transposed operand: element (n, row) of Y^T; the warp's 32 rows are exactly one k-chunk of it.  After the in-register
+    // transpose lane l owns column n0 + l for the warp's 32 rows: 8 float4 stores per half, 128-byte segments per 8 lanes.
+    warp_transpose32(v, lane);
     float* blk = p.Yt + ((size_t)(n0 >> 7) * p.yt_nch + (row >> 5)) * GBLK_A;
-    const int kk = row & 31, nb = n0 & 127;
+    const int nb = (n0 & 127) + lane;
 #pragma unroll
-    for (int e = 0; e < 32; ++e) {
-      float hi, lo;
-      gsplit_tf32(v[e], hi, lo);
-      const int off = gblk_off(nb + e, kk);
-      blk[off] = hi;
-      blk[TC_M * TC_KC + off] = lo;
+    for (int q = 0; q < 8; ++q) {
+      float4 h4, l4;
+      float* ph = reinterpret_cast<float*>(&h4);
+      float* pl = reinterpret_cast<float*>(&l4);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) gsplit_tf32(v[4 * q + e], ph[e], pl[e]);
+      *reinterpret_cast<float4*>(blk + gblk_off(nb, 4 * q)) = h4;
+      *reinterpret_cast<float4*>(blk + TC_M * TC_KC + gblk_off(nb, 4 * q)) = l4;
     }
   }
   if (EPI == EPI_DX) {
-    const float cs = warp_colsum32(v, lane);
+    float cs = 0.f;                                              // column sum over the warp's 32 rows (bias gradient partial)
+#pragma unroll
+    for (int i = 0; i < 32; ++i) cs += v[i];
     p.dbpart[(size_t)(row >> 5) * p.ldb + n0 + lane] = cs;
   }
 }

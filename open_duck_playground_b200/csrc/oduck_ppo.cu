@@ -55,7 +55,7 @@ struct NetBuf {
   int M, Mpad, mtiles;                  // rows of this net's batch
   float* Xr[PPO_NL];                    // R(X_l)   A operand of the forward GEMM of layer l
   float* Xt[PPO_NL];                    // R(X_l^T) A operand of the dW GEMM of layer l
-  float* Z[PPO_NL - 1];                 // pre-activations [Mpad][d_{l+1}]
+  float* Z[PPO_NL - 1];                 // pre-activations, blocked [mtiles][d_{l+1} / 32][128 x 32]
   float* out;                           // head output [Mpad][32]
   float* dZr[PPO_NL];                   // R(dZ_l)   A operand of the dX GEMM
   float* dZt[PPO_NL];                   // R(dZ_l^T) B operand of the dW GEMM
@@ -75,8 +75,10 @@ struct OduckPpo {
   double* stats;            // [4] adv mean, std
   float* sumsq_part;        // [grid of grad_reduce]
   int* step;                // [2]: adam step count, finished-block ticket
-  int reduce_blocks;
+  int reduce_blocks, gae_smem;
   int64_t launches;
+  cudaStream_t side;        // the value net's chain runs here, concurrently with the policy net's chain on the caller's stream
+  cudaEvent_t ev_fork, ev_join;
   std::vector<void*> allocs;
 };
 
@@ -117,29 +119,48 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
 }
 
 // brax losses.compute_gae over one trajectory per thread; one CTA so that the advantage statistics are deterministic.
+// STAGED: the whole CTA first gathers the minibatch's values / rewards / done / truncation into shared memory with
+// independent loads (the scan itself is a chain of T dependent steps; gathering inside it costs T global-load latencies).
+template <bool STAGED>
 __global__ void __launch_bounds__(1024) k_ppo_gae(const float* __restrict__ values /*[Mv_pad][32]*/, OduckRollout ro, const int* __restrict__ idx, int B, int T,
                                                   float discount, float lambda, float reward_scaling, int normalize, float* __restrict__ adv,
                                                   float* __restrict__ vs, double* __restrict__ stats, double* __restrict__ losses) {
+  extern __shared__ float gsm[];                       // STAGED: val[(T + 1) B] | rew[T B] | done[T B] | trunc[T B]
   __shared__ double sh[32];
   if (threadIdx.x < 8) losses[threadIdx.x] = 0.0;
-  double s1 = 0.0, s2 = 0.0;
   const int N = ro.num_envs;
+  float* s_val = gsm;
+  float* s_rew = s_val + (T + 1) * B;
+  float* s_done = s_rew + T * B;
+  float* s_trunc = s_done + T * B;
+  if (STAGED) {
+    for (int i = threadIdx.x; i < (T + 1) * B; i += blockDim.x) s_val[i] = values[(size_t)i * PPO_HEADW];
+    for (int i = threadIdx.x; i < T * B; i += blockDim.x) {
+      const int t = i / B, b = i - t * B;
+      const size_t g = (size_t)t * N + idx[b];
+      s_rew[i] = ro.reward[g]; s_done[i] = ro.done[g]; s_trunc[i] = ro.truncation[g];
+    }
+    __syncthreads();
+  }
+  double s1 = 0.0, s2 = 0.0;
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
     const int env = idx[b];
     float acc = 0.f;
-    const float boot = values[(size_t)(T * B + b) * PPO_HEADW];
+    const float boot = STAGED ? s_val[T * B + b] : values[(size_t)(T * B + b) * PPO_HEADW];
     float v_next = boot, vs_next = boot;
     for (int t = T - 1; t >= 0; --t) {
       const size_t g = (size_t)t * N + env;
-      const float trunc = ro.truncation[g], done = ro.done[g], rew = ro.reward[g] * reward_scaling;
+      const int i = t * B + b;
+      const float trunc = STAGED ? s_trunc[i] : ro.truncation[g], done = STAGED ? s_done[i] : ro.done[g];
+      const float rew = (STAGED ? s_rew[i] : ro.reward[g]) * reward_scaling;
       const float term = done * (1.f - trunc), mask = 1.f - trunc;
-      const float v = values[(size_t)(t * B + b) * PPO_HEADW];
+      const float v = STAGED ? s_val[i] : values[(size_t)i * PPO_HEADW];
       const float delta = (rew + discount * (1.f - term) * v_next - v) * mask;
       acc = delta + discount * (1.f - term) * mask * lambda * acc;
       const float vst = acc + v;
       const float a = (rew + discount * (1.f - term) * vs_next - v) * mask;
-      vs[t * B + b] = vst;
-      adv[t * B + b] = a;
+      vs[i] = vst;
+      adv[i] = a;
       s1 += a; s2 += (double)a * a;
       v_next = v; vs_next = vst;
     }
@@ -185,93 +206,85 @@ struct LossParams {
   double* losses;
 };
 
-// One thread per row: policy rows r < Mp (value baseline rows are the same indices), bootstrap rows Mp <= r < Mv get zero gradient.
-__global__ void __launch_bounds__(128) k_ppo_loss(LossParams p) {
+// Sixteen lanes per row (lane a < na = one action), 16 rows per CTA.  Policy rows r < Mp (the value baseline rows are the same
+// indices); bootstrap rows Mp <= r < Mv get zero gradient.  Outputs are the head gradients already in operand form:
+// R(dZ) (A operand of the dX GEMM), R_32(dZ^T) (B operand of the dW GEMM) and one bias-gradient partial per CTA.
+#define LOSS_ROWS 16
+__global__ void __launch_bounds__(LOSS_ROWS * 16) k_ppo_loss(LossParams p) {
   __shared__ double sh[32];
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31;
+  __shared__ float gp[LOSS_ROWS][PPO_HEADW], gv[LOSS_ROWS];
+  const int sub = threadIdx.x >> 4, a = threadIdx.x & 15;        // row slot in the CTA, action lane
+  const int r = blockIdx.x * LOSS_ROWS + sub;
   double l_pol = 0.0, l_val = 0.0, l_ent = 0.0, l_clip = 0.0, l_adv = 0.0;
   const float invM = 1.f / (float)p.Mp;
+  const bool prow = r < p.Mp_pad;                                // CTA-uniform (Mp_pad is a multiple of 128)
   // ---------------- policy head
-  if (r < p.Mp_pad) {                                   // warp-uniform: Mp_pad is a multiple of 128
-    float g[32];
-#pragma unroll
-    for (int e = 0; e < 32; ++e) g[e] = 0.f;
-    if (r < p.Mp) {
-      const int t = r / p.B, b = r - t * p.B;
-      const size_t gi = (size_t)t * p.ro.num_envs + p.idx[b];
-      const float* lg = p.logits + (size_t)r * PPO_HEADW;
-      const float A = p.adv[r];
-      RKey rowkey; rowkey.a = 0; rowkey.b = 0;
-      if (!p.noise) { RKey k0; k0.a = p.key[0]; k0.b = p.key[1]; rowkey = rblock(k0, (uint32_t)r); }
-      float logp = 0.f, ent = 0.f;
-      float dlp_loc[16], dlp_sc[16], dent_loc[16], dent_sc[16], sig[16];
-#pragma unroll
-      for (int a = 0; a < 16; ++a) {
-        dlp_loc[a] = dlp_sc[a] = dent_loc[a] = dent_sc[a] = sig[a] = 0.f;
-        if (a < p.na) {
-          const float loc = lg[a], sp = lg[p.na + a];
-          const float scale = softplusf(sp) + 0.001f;
-          const float raw = p.ro.raw_action[gi * p.na + a];
-          const float zz = (raw - loc) / scale;
-          logp += -0.5f * zz * zz - logf(scale) - 0.91893853320467f - 2.f * (0.69314718056f - raw - softplusf(-2.f * raw));
-          float eps;
-          if (p.noise) eps = p.noise[(size_t)r * p.na + a];
-          else {
-            RKey bk = rblock(rowkey, (uint32_t)a);
-            const float lo = -0.99999994f;
-            eps = 1.41421356237f * ppo_erfinv(fmaxf(lo, bits_unit(bk.a ^ bk.b) * (1.0f - lo) + lo));
-          }
-          const float x = loc + scale * eps;
-          ent += 0.5f + 0.91893853320467f + logf(scale) + 2.f * (0.69314718056f - x - softplusf(-2.f * x));
-          const float th = tanhf(x);
-          dlp_loc[a] = zz / scale; dlp_sc[a] = (zz * zz - 1.f) / scale;
-          dent_loc[a] = -2.f * th; dent_sc[a] = 1.f / scale - 2.f * th * eps;
-          sig[a] = 1.f / (1.f + expf(-sp));
-        }
+  float g_loc = 0.f, g_sc = 0.f;
+  if (r < p.Mp) {
+    const int t = r / p.B, b = r - t * p.B;
+    const size_t gi = (size_t)t * p.ro.num_envs + p.idx[b];
+    const float* lg = p.logits + (size_t)r * PPO_HEADW;
+    const float A = p.adv[r];
+    float logp = 0.f, ent = 0.f, dlp_loc = 0.f, dlp_sc = 0.f, dent_loc = 0.f, dent_sc = 0.f, sig = 0.f;
+    if (a < p.na) {
+      const float loc = lg[a], sp = lg[p.na + a];
+      const float scale = softplusf(sp) + 0.001f;
+      const float raw = p.ro.raw_action[gi * p.na + a];
+      const float zz = (raw - loc) / scale;
+      logp = -0.5f * zz * zz - logf(scale) - 0.91893853320467f - 2.f * (0.69314718056f - raw - softplusf(-2.f * raw));
+      float eps;
+      if (p.noise) eps = p.noise[(size_t)r * p.na + a];
+      else {
+        RKey k0; k0.a = p.key[0]; k0.b = p.key[1];
+        const RKey bk = rblock(rblock(k0, (uint32_t)r), (uint32_t)a);
+        const float lo = -0.99999994f;
+        eps = 1.41421356237f * ppo_erfinv(fmaxf(lo, bits_unit(bk.a ^ bk.b) * (1.0f - lo) + lo));
       }
-      const float rho = expf(logp - p.ro.log_prob[gi]);
-      const float lo = 1.f - p.clip_eps, hi = 1.f + p.clip_eps;
-      const float s1 = rho * A, s2 = fminf(fmaxf(rho, lo), hi) * A;
-      const bool inr = rho >= lo && rho <= hi;
-      float w = s1 < s2 ? 1.f : (s1 > s2 ? (inr ? 1.f : 0.f) : 0.5f + (inr ? 0.5f : 0.f));   // d min(s1, s2) / d s1-path, ties split like jnp/torch minimum
-      const float glp = -A * rho * w * invM;              // d loss / d logp
-      const float ge = -p.entropy_cost * invM;            // d loss / d entropy_row
-#pragma unroll
-      for (int a = 0; a < 16; ++a) {
-        if (a < p.na) {
-          g[a] = glp * dlp_loc[a] + ge * dent_loc[a];
-          g[p.na + a] = (glp * dlp_sc[a] + ge * dent_sc[a]) * sig[a];
-        }
-      }
-      l_pol = -(double)fminf(s1, s2); l_ent = ent; l_clip = inr ? 0.0 : 1.0; l_adv = fabsf(A);
+      const float x = loc + scale * eps;
+      ent = 0.5f + 0.91893853320467f + logf(scale) + 2.f * (0.69314718056f - x - softplusf(-2.f * x));
+      const float th = tanhf(x);
+      dlp_loc = zz / scale; dlp_sc = (zz * zz - 1.f) / scale;
+      dent_loc = -2.f * th; dent_sc = 1.f / scale - 2.f * th * eps;
+      sig = 1.f / (1.f + expf(-sp));
     }
+    const unsigned hmask = 0xFFFFu << (threadIdx.x & 16);   // this row's half-warp (the other half may be a row >= Mp)
+#pragma unroll
+    for (int o = 8; o; o >>= 1) { logp += __shfl_xor_sync(hmask, logp, o); ent += __shfl_xor_sync(hmask, ent, o); }
+    const float rho = expf(logp - p.ro.log_prob[gi]);
+    const float lo = 1.f - p.clip_eps, hi = 1.f + p.clip_eps;
+    const float s1 = rho * A, s2 = fminf(fmaxf(rho, lo), hi) * A;
+    const bool inr = rho >= lo && rho <= hi;
+    const float w = s1 < s2 ? 1.f : (s1 > s2 ? (inr ? 1.f : 0.f) : 0.5f + (inr ? 0.5f : 0.f));   // ties split like jnp / torch minimum
+    const float glp = -A * rho * w * invM;              // d loss / d logp
+    const float ge = -p.entropy_cost * invM;            // d loss / d entropy_row
+    g_loc = glp * dlp_loc + ge * dent_loc;
+    g_sc = (glp * dlp_sc + ge * dent_sc) * sig;
+    if (a == 0) { l_pol = -(double)fminf(s1, s2); l_ent = ent; l_clip = inr ? 0.0 : 1.0; l_adv = fabsf(A); }
+  }
+  if (prow) {
+    // lane c writes columns c and c + 16 of the padded head: [loc gradients | scale gradients | zeros]
+    const int base = threadIdx.x & 16;                    // first lane of this row's half-warp
     float* blk = p.dZr_p + (size_t)(r >> 7) * GBLK_A;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      float4 h4, l4;
-      float* ph = reinterpret_cast<float*>(&h4);
-      float* pl = reinterpret_cast<float*>(&l4);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) gsplit_tf32(g[4 * q + e], ph[e], pl[e]);
-      *reinterpret_cast<float4*>(blk + gblk_off(r & 127, 4 * q)) = h4;
-      *reinterpret_cast<float4*>(blk + TC_M * TC_KC + gblk_off(r & 127, 4 * q)) = l4;
-    }
     float* bt = p.dZt_p + (size_t)(r >> 5) * gblk_b(PPO_HEADW);
 #pragma unroll
-    for (int e = 0; e < 32; ++e) {
+    for (int h2 = 0; h2 < 2; ++h2) {
+      const int col = a + 16 * h2;
+      const int src = col < p.na ? col : col - p.na;                       // lane holding this column's gradient
+      const float vl = __shfl_sync(0xffffffffu, g_loc, base | (src & 15)), vs2 = __shfl_sync(0xffffffffu, g_sc, base | (src & 15));
+      const float g = col < p.na ? vl : (col < 2 * p.na ? vs2 : 0.f);
       float hi, lo;
-      gsplit_tf32(g[e], hi, lo);
-      const int off = gblk_off(e, r & 31);
+      gsplit_tf32(g, hi, lo);
+      int off = gblk_off(r & 127, col);
+      blk[off] = hi; blk[TC_M * TC_KC + off] = lo;
+      off = gblk_off(col, r & 31);
       bt[off] = hi; bt[PPO_HEADW * TC_KC + off] = lo;
+      gp[sub][col] = g;
     }
-    const float cs = warp_colsum32(g, lane);
-    p.db_p[(size_t)(r >> 5) * PPO_HEADW + lane] = cs;
   }
   // ---------------- value head: v_loss = 0.5 * 0.5 * mean((vs - v)^2)
-  if (r < p.Mv_pad) {
+  {
     float dv = 0.f;
-    if (r < p.Mp) {
+    if (r < p.Mp && a == 0) {
       const float err = p.vs[r] - p.values[(size_t)r * PPO_HEADW];
       dv = -0.5f * err * invM;
       l_val = 0.25 * (double)err * err;
@@ -279,22 +292,33 @@ __global__ void __launch_bounds__(128) k_ppo_loss(LossParams p) {
     float hi, lo;
     gsplit_tf32(dv, hi, lo);
     float* blk = p.dZr_v + (size_t)(r >> 7) * GBLK_A;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 h4 = make_float4(q == 0 ? hi : 0.f, 0.f, 0.f, 0.f), l4 = make_float4(q == 0 ? lo : 0.f, 0.f, 0.f, 0.f);
-      *reinterpret_cast<float4*>(blk + gblk_off(r & 127, 4 * q)) = h4;
-      *reinterpret_cast<float4*>(blk + TC_M * TC_KC + gblk_off(r & 127, 4 * q)) = l4;
-    }
     float* bt = p.dZt_v + (size_t)(r >> 5) * gblk_b(PPO_HEADW);
 #pragma unroll
-    for (int e = 0; e < 32; ++e) {
-      const int off = gblk_off(e, r & 31);
-      bt[off] = e == 0 ? hi : 0.f; bt[PPO_HEADW * TC_KC + off] = e == 0 ? lo : 0.f;
+    for (int h2 = 0; h2 < 2; ++h2) {
+      const int col = a + 16 * h2;
+      const float xh = col == 0 ? hi : 0.f, xl = col == 0 ? lo : 0.f;
+      int off = gblk_off(r & 127, col);
+      blk[off] = xh; blk[TC_M * TC_KC + off] = xl;
+      off = gblk_off(col, r & 31);
+      bt[off] = xh; bt[PPO_HEADW * TC_KC + off] = xl;
     }
-    float s = dv;
+    if (a == 0) gv[sub] = dv;
+  }
+  __syncthreads();
+  if (threadIdx.x < PPO_HEADW) {                          // bias-gradient partials of this CTA's 16 rows
+    const int c = threadIdx.x;
+    if (prow) {
+      float t = 0.f;
 #pragma unroll
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    p.db_v[(size_t)(r >> 5) * PPO_HEADW + lane] = lane == 0 ? s : 0.f;
+      for (int q = 0; q < LOSS_ROWS; ++q) t += gp[q][c];
+      p.db_p[(size_t)blockIdx.x * PPO_HEADW + c] = t;
+    }
+    float t = 0.f;
+    if (c == 0) {
+#pragma unroll
+      for (int q = 0; q < LOSS_ROWS; ++q) t += gv[q];
+    }
+    p.db_v[(size_t)blockIdx.x * PPO_HEADW + c] = t;
   }
   const double inv = 1.0 / (double)p.Mp;
   const double a0 = block_sum(l_pol, sh), a1 = block_sum(l_val, sh), a2 = block_sum(l_ent, sh), a3 = block_sum(l_clip, sh), a4 = block_sum(l_adv, sh);
@@ -418,6 +442,9 @@ int oduck_ppo_destroy(OduckPpo* h) {
   if (!h) return ODUCK_OK;
   cudaSetDevice(h->device);
   for (void* q : h->allocs) cudaFree(q);
+  if (h->side) cudaStreamDestroy(h->side);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   delete h;
   return ODUCK_OK;
 }
@@ -439,6 +466,9 @@ int oduck_ppo_create(const OduckPpoConfig* cfg, int device, OduckPpo** out) {
   PPO_TRY(cudaSetDevice(device));
   OduckPpo* h = new OduckPpo();
   h->cfg = *cfg; h->device = device; h->B = B; h->T = T; h->na = na; h->launches = 0;
+  h->side = nullptr; h->ev_fork = h->ev_join = nullptr;
+  if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) { oduck_ppo_destroy(h); return oduck_fail(ODUCK_ERR_CUDA, "oduck_ppo_create: stream / event creation failed"); }
   // ---- parameter segments, packed-operand and partial-gradient layouts
   SegTable& tb = h->seg;
   memset(&tb, 0, sizeof(tb));
@@ -467,7 +497,7 @@ int oduck_ppo_create(const OduckPpoConfig* cfg, int device, OduckPpo** out) {
       off += (long long)K * N;
       Seg b = w;
       b.off = off; b.bias = 1; b.K = 1; b.wf = b.wb = -1;
-      b.ldb = round_up(N, 32); b.nwarprows = nb.Mpad / 32;
+      b.ldb = round_up(N, 32); b.nwarprows = l == PPO_NL - 1 ? nb.Mpad / LOSS_ROWS : nb.Mpad / 32;   // head partials come from k_ppo_loss
       b.dbpart = goff; goff += (long long)b.ldb * b.nwarprows;
       off += N;
       tb.s[tb.n++] = w; tb.s[tb.n++] = b;
@@ -504,6 +534,9 @@ int oduck_ppo_create(const OduckPpoConfig* cfg, int device, OduckPpo** out) {
   }
   if (!ok) { oduck_ppo_destroy(h); return oduck_fail(ODUCK_ERR_ALLOC, "oduck_ppo_create: cudaMalloc failed"); }
   PPO_TRY(cudaMemcpy(h->dseg, &h->seg, sizeof(SegTable), cudaMemcpyHostToDevice));
+  h->gae_smem = (int)(((size_t)(T + 1) * B + 3 * (size_t)T * B) * sizeof(float));
+  if (h->gae_smem > 200 * 1024) h->gae_smem = 0;                  // does not fit: gather inside the scan instead
+  else PPO_TRY(cudaFuncSetAttribute(k_ppo_gae<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->gae_smem));
   PPO_TRY(cudaDeviceSynchronize());
   *out = h;
   return ODUCK_OK;
@@ -578,7 +611,7 @@ static int net_forward(OduckPpo* h, int net, bool simt, cudaStream_t st) {
     g.nchunks = ceil_div(w.K, TC_KC); g.cps = g.nchunks;
     g.bias = h->params + b.off; g.nvalid = w.N;
     if (l < PPO_NL - 1) {
-      g.Z = nb.Z[l]; g.ldz = w.N;
+      g.Z = nb.Z[l]; g.z_nch = w.N / TC_KC;
       g.Yr = nb.Xr[l + 1]; g.yr_nch = w.N / TC_KC;
       g.Yt = nb.Xt[l + 1]; g.yt_nch = nb.Mpad / TC_KC;
       GEMM_TRY((launch_gemm<128, 3, EPI_FWD>(g, nb.mtiles, w.N / 128, simt, st)));
@@ -612,7 +645,7 @@ static int net_backward(OduckPpo* h, int net, bool simt, cudaStream_t st) {
       memset(&g, 0, sizeof(g));
       g.A = nb.dZr[l]; g.B = h->packed + w.wb;
       g.nchunks = ceil_div(w.N, TC_KC); g.cps = g.nchunks;
-      g.Z = nb.Z[l - 1]; g.ldz = w.K;
+      g.Z = nb.Z[l - 1]; g.z_nch = w.K / TC_KC;
       g.Yr = nb.dZr[l - 1]; g.yr_nch = w.K / TC_KC;
       g.Yt = nb.dZt[l - 1]; g.yt_nch = nb.Mpad / TC_KC;
       g.dbpart = h->partial + bprev.dbpart; g.ldb = bprev.ldb;
@@ -634,18 +667,25 @@ int oduck_ppo_minibatch(OduckPpo* h, const OduckRollout* ro, const OduckNormaliz
   const OduckPpoConfig& c = h->cfg;
   NetBuf& np = h->net[0];
   NetBuf& nv = h->net[1];
+  // The two nets are independent until the loss and again after it: the value chain runs on the side stream, forked from
+  // and joined back into the caller's stream with events (capturable into a CUDA graph like any other launch).
+#define FORK() { PPO_TRY(cudaEventRecord(h->ev_fork, st)); PPO_TRY(cudaStreamWaitEvent(h->side, h->ev_fork, 0)); }
+#define JOIN() { PPO_TRY(cudaEventRecord(h->ev_join, h->side)); PPO_TRY(cudaStreamWaitEvent(st, h->ev_join, 0)); }
   if (stages & ODUCK_PPO_STAGE_FORWARD) {
-    k_ppo_pack<<<296, 256, 0, st>>>(ro->obs_policy, ro->num_envs, np.dims[0], env_idx, h->B, np.M, np.Mpad, ceil_div(np.dims[0], TC_KC), nm->policy_mean, nm->policy_std, np.Xr[0], np.Xt[0]);
+    FORK()
+    k_ppo_pack<<<148, 256, 0, h->side>>>(ro->obs_value, ro->num_envs, nv.dims[0], env_idx, h->B, nv.M, nv.Mpad, ceil_div(nv.dims[0], TC_KC), nm->value_mean, nm->value_std, nv.Xr[0], nv.Xt[0]);
     GEMM_TRY(cudaGetLastError());
-    k_ppo_pack<<<296, 256, 0, st>>>(ro->obs_value, ro->num_envs, nv.dims[0], env_idx, h->B, nv.M, nv.Mpad, ceil_div(nv.dims[0], TC_KC), nm->value_mean, nm->value_std, nv.Xr[0], nv.Xt[0]);
-    GEMM_TRY(cudaGetLastError());
-    int rc = net_forward(h, 1, simt, st);
+    int rc = net_forward(h, 1, simt, h->side);
     if (rc) return rc;
+    k_ppo_pack<<<148, 256, 0, st>>>(ro->obs_policy, ro->num_envs, np.dims[0], env_idx, h->B, np.M, np.Mpad, ceil_div(np.dims[0], TC_KC), nm->policy_mean, nm->policy_std, np.Xr[0], np.Xt[0]);
+    GEMM_TRY(cudaGetLastError());
     rc = net_forward(h, 0, simt, st);
     if (rc) return rc;
+    JOIN()
   }
   if (stages & ODUCK_PPO_STAGE_LOSS) {
-    k_ppo_gae<<<1, 1024, 0, st>>>(nv.out, *ro, env_idx, h->B, h->T, c.discounting, c.gae_lambda, c.reward_scaling, c.normalize_advantage, h->adv, h->vs, h->stats, h->losses);
+    if (h->gae_smem > 0) k_ppo_gae<true><<<1, 1024, h->gae_smem, st>>>(nv.out, *ro, env_idx, h->B, h->T, c.discounting, c.gae_lambda, c.reward_scaling, c.normalize_advantage, h->adv, h->vs, h->stats, h->losses);
+    else k_ppo_gae<false><<<1, 1024, 0, st>>>(nv.out, *ro, env_idx, h->B, h->T, c.discounting, c.gae_lambda, c.reward_scaling, c.normalize_advantage, h->adv, h->vs, h->stats, h->losses);
     GEMM_TRY(cudaGetLastError());
     LossParams lp;
     memset(&lp, 0, sizeof(lp));
@@ -657,14 +697,16 @@ int oduck_ppo_minibatch(OduckPpo* h, const OduckRollout* ro, const OduckNormaliz
     lp.dZr_p = np.dZr[PPO_NL - 1]; lp.dZt_p = np.dZt[PPO_NL - 1]; lp.db_p = h->partial + bp.dbpart;
     lp.dZr_v = nv.dZr[PPO_NL - 1]; lp.dZt_v = nv.dZt[PPO_NL - 1]; lp.db_v = h->partial + bv.dbpart;
     lp.losses = h->losses;
-    k_ppo_loss<<<nv.Mpad / 128, 128, 0, st>>>(lp);
+    k_ppo_loss<<<nv.Mpad / LOSS_ROWS, LOSS_ROWS * 16, 0, st>>>(lp);
     GEMM_TRY(cudaGetLastError());
   }
   if (stages & ODUCK_PPO_STAGE_BACKWARD) {
-    int rc = net_backward(h, 1, simt, st);
+    FORK()
+    int rc = net_backward(h, 1, simt, h->side);
     if (rc) return rc;
     rc = net_backward(h, 0, simt, st);
     if (rc) return rc;
+    JOIN()
     k_ppo_grad_reduce<<<h->reduce_blocks, 256, 0, st>>>(h->dseg, h->partial, h->grads, h->sumsq_part);
     GEMM_TRY(cudaGetLastError());
   }
