@@ -80,9 +80,35 @@ __device__ __forceinline__ void warp_transpose32(float (&v)[32], const int lane)
   }
 }
 
+#define GEMM_THREADS 256                                             // 8 warps: two per TMEM lane quarter, each takes half of the column groups
+#define TP_STRIDE 33                                                 // padded row of the per-warp 32 x 32 transpose scratch (conflict-free both ways)
+
+// 32 x 32 transpose through a per-warp shared-memory scratch: in: lane r holds row r (v[c]); out: lane c holds column c (v[r]).
+// 64 shared-memory instructions instead of the 240 shuffle/select instructions of warp_transpose32.
+__device__ __forceinline__ void smem_transpose32(float (&v)[32], float* __restrict__ scratch, const int lane) {
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < 32; ++c) scratch[lane * TP_STRIDE + c] = v[c];
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < 32; ++r) v[r] = scratch[r * TP_STRIDE + lane];
+}
+
+__device__ __forceinline__ void gemm_load_z(const GemmParams& p, const int mt, const int rt, const int n0, float (&zv)[32]) {
+  const float* zblk = p.Z + ((size_t)mt * p.z_nch + (n0 >> 5)) * (TC_M * TC_KC);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 w = *reinterpret_cast<const float4*>(zblk + gblk_off(rt, 4 * q));
+    zv[4 * q] = w.x; zv[4 * q + 1] = w.y; zv[4 * q + 2] = w.z; zv[4 * q + 3] = w.w;
+  }
+}
+
 // 32 consecutive output columns [n0, n0 + 32) of output row `row` (tile row rt of tile mt), split z.
+// sbias: this CTA's bias slice in shared memory (FWD / OUT), zv: pre-activations of these 32 elements (DX, loaded ahead of use),
+// scratch: per-warp transpose scratch (TP_STRIDE x 32 floats).
 template <int EPI>
-__device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const int mt, const int rt, const int n0, const int z, const int lane, float (&v)[32]) {
+__device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const int mt, const int rt, const int n0, const int z, const int lane, float (&v)[32],
+                                              const float* __restrict__ sbias, const float (&zv)[32], float* __restrict__ scratch) {
   const int row = mt * TC_M + rt;
   if (EPI == EPI_OUT) {
     float* o = p.out + (size_t)row * p.ldo + n0;
@@ -91,7 +117,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const int mt,
       float4 w;
       float* pw = reinterpret_cast<float*>(&w);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) { const int n = n0 + 4 * q + e; pw[e] = n < p.nvalid ? v[4 * q + e] + __ldg(p.bias + n) : 0.f; }
+      for (int e = 0; e < 4; ++e) pw[e] = v[4 * q + e] + sbias[4 * q + e];      // bias slice is zero beyond nvalid
       *reinterpret_cast<float4*>(o + 4 * q) = w;
     }
     return;
@@ -103,28 +129,25 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const int mt,
     return;
   }
   // FWD: y = swish(acc + bias), pre-activation kept for the backward pass.  DX: y = acc * swish'(z).
-  float* zblk = p.Z + ((size_t)mt * p.z_nch + (n0 >> 5)) * (TC_M * TC_KC);
+  if (EPI == EPI_FWD) {
+    float* zblk = p.Z + ((size_t)mt * p.z_nch + (n0 >> 5)) * (TC_M * TC_KC);
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    if (EPI == EPI_FWD) {
+    for (int q = 0; q < 8; ++q) {
       float4 w;
       float* pw = reinterpret_cast<float*>(&w);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int n = n0 + 4 * q + e;
-        const float zz = v[4 * q + e] + (n < p.nvalid ? __ldg(p.bias + n) : 0.f);
+        const float zz = v[4 * q + e] + sbias[4 * q + e];
         pw[e] = zz;
-        v[4 * q + e] = zz / (1.f + __expf(-zz));
+        v[4 * q + e] = __fdividef(zz, 1.f + __expf(-zz));
       }
       *reinterpret_cast<float4*>(zblk + gblk_off(rt, 4 * q)) = w;
-    } else {
-      const float4 w = *reinterpret_cast<const float4*>(zblk + gblk_off(rt, 4 * q));
-      const float* pw = reinterpret_cast<const float*>(&w);
+    }
+  } else {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float zz = pw[e], s = 1.f / (1.f + __expf(-zz));
-        v[4 * q + e] *= s * (1.f + zz * (1.f - s));
-      }
+    for (int e = 0; e < 32; ++e) {
+      const float zz = zv[e], s = __fdividef(1.f, 1.f + __expf(-zz));
+      v[e] *= s * (1.f + zz * (1.f - s));
     }
   }
   {
@@ -141,9 +164,9 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const int mt,
     }
   }
   {
-    // transposed operand: element (n, row) of Y^T; the warp's 32 rows are exactly one k-chunk of it.  After the in-register
-    // transpose lane l owns column n0 + l for the warp's 32 rows: 8 float4 stores per half, 128-byte segments per 8 lanes.
-    warp_transpose32(v, lane);
+    // transposed operand: element (n, row) of Y^T; the warp's 32 rows are exactly one k-chunk of it.  After the transpose
+    // lane l owns column n0 + l for the warp's 32 rows: 8 float4 stores per half, 128-byte segments per 8 lanes.
+    smem_transpose32(v, scratch, lane);
     float* blk = p.Yt + ((size_t)(n0 >> 7) * p.yt_nch + (row >> 5)) * GBLK_A;
     const int nb = (n0 & 127) + lane;
 #pragma unroll
@@ -166,12 +189,14 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const int mt,
 }
 
 template <int NT, int NSTAGE, int EPI>
-__global__ void __launch_bounds__(TC_THREADS) k_gemm_tc(GemmParams p) {
+__global__ void __launch_bounds__(GEMM_THREADS) k_gemm_tc(GemmParams p) {
   extern __shared__ __align__(128) unsigned char raw_smem[];
   __shared__ __align__(8) uint64_t full[NSTAGE], empty[NSTAGE], done;
   __shared__ uint32_t tmem_base_s;
+  __shared__ float s_bias[NT];
   constexpr int BLKB = gblk_b(NT);
   constexpr int STAGE = GBLK_A + BLKB;                            // floats per stage
+  constexpr int NG = NT < 32 ? 1 : NT / 32;                       // column groups of 32
   float* const smem = reinterpret_cast<float*>(raw_smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = blockIdx.x, nt = blockIdx.y, z = blockIdx.z;
@@ -185,6 +210,9 @@ __global__ void __launch_bounds__(TC_THREADS) k_gemm_tc(GemmParams p) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(&done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (EPI == EPI_FWD || EPI == EPI_OUT) {
+    for (int i = threadIdx.x; i < NT; i += GEMM_THREADS) { const int n = nt * NT + i; s_bias[i] = n < p.nvalid ? __ldg(p.bias + n) : 0.f; }
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
@@ -226,34 +254,57 @@ __global__ void __launch_bounds__(TC_THREADS) k_gemm_tc(GemmParams p) {
     umma_commit(&done);
   }
   if (warp == 0) __syncwarp();
+  // epilogue mapping: TMEM lane quarter wq (a warp may only touch lanes 32 (warp % 4) ..), column groups j = wh, wh + 2, ...
+  const int wq = warp & 3, wh = warp >> 2;
+  const int rt = 32 * wq + lane;                                   // output row of the tile = TMEM lane
+  const uint32_t tlane = (uint32_t)(32 * wq) << 16;
+  float zc[32];
+#pragma unroll
+  for (int e = 0; e < 32; ++e) zc[e] = 0.f;
+  if (EPI == EPI_DX && wh < NG) gemm_load_z(p, mt, rt, nt * NT + wh * 32, zc);   // in flight while the MMAs finish
   mbar_wait(&done, 0u);
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-  const int rt = 32 * warp + lane;                                 // output row of the tile = TMEM lane
-  const uint32_t tlane = (uint32_t)(32 * warp) << 16;
+  // every MMA has retired, so the stage buffers are free: per-warp transpose scratch
+  float* scratch = smem + (size_t)warp * (TP_STRIDE * 32);
 #pragma unroll 1
-  for (int j = 0; j < (NT < 32 ? 1 : NT / 32); ++j) {
+  for (int j = wh; j < NG; j += 2) {
     float v[32];
     tmem_ld32(tmem_base + tlane + (uint32_t)(j * 32), v);
-    gemm_epilogue<EPI>(p, mt, rt, nt * NT + j * 32, z, lane, v);
+    float zn[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) zn[e] = 0.f;
+    if (EPI == EPI_DX && j + 2 < NG) gemm_load_z(p, mt, rt, nt * NT + (j + 2) * 32, zn);     // next group's pre-activations
+    gemm_epilogue<EPI>(p, mt, rt, nt * NT + j * 32, z, lane, v, s_bias + j * 32, zc, scratch);
+#pragma unroll
+    for (int e = 0; e < 32; ++e) zc[e] = zn[e];
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(kCols) : "memory");
 }
 
-// CUDA-core twin: same grid, operands and epilogues; fp32 FMAs on hi + lo.  Debug / bisect only.
+// CUDA-core twin: same grid, thread mapping, operands and epilogues; fp32 FMAs on hi + lo.  Debug / bisect only.
 template <int NT, int EPI>
-__global__ void __launch_bounds__(TC_THREADS) k_gemm_simt(GemmParams p) {
+__global__ void __launch_bounds__(GEMM_THREADS) k_gemm_simt(GemmParams p) {
+  __shared__ float s_bias[NT];
+  __shared__ float s_scratch[(GEMM_THREADS / 32) * TP_STRIDE * 32];
   constexpr int BLKB = gblk_b(NT);
+  constexpr int NG = NT < 32 ? 1 : NT / 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = blockIdx.x, nt = blockIdx.y, z = blockIdx.z;
   const int c0 = z * p.cps;
   const int n = min(p.nchunks - c0, p.cps);
-  const int rt = 32 * warp + lane;
-  for (int j = 0; j < (NT < 32 ? 1 : NT / 32); ++j) {
-    float v[32];
+  if (EPI == EPI_FWD || EPI == EPI_OUT) {
+    for (int i = threadIdx.x; i < NT; i += GEMM_THREADS) { const int nn = nt * NT + i; s_bias[i] = nn < p.nvalid ? p.bias[nn] : 0.f; }
+  }
+  __syncthreads();
+  const int wq = warp & 3, wh = warp >> 2;
+  const int rt = 32 * wq + lane;
+  for (int j = wh; j < NG; j += 2) {
+    float v[32], zc[32];
 #pragma unroll
-    for (int e = 0; e < 32; ++e) v[e] = 0.f;
+    for (int e = 0; e < 32; ++e) { v[e] = 0.f; zc[e] = 0.f; }
+    if (EPI == EPI_DX) gemm_load_z(p, mt, rt, nt * NT + j * 32, zc);
     for (int i = 0; i < n; ++i) {
       const float* a = p.A + ((size_t)mt * p.nchunks + c0 + i) * GBLK_A;
       const float* b = p.B + ((size_t)nt * p.nchunks + c0 + i) * BLKB;
@@ -266,7 +317,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_gemm_simt(GemmParams p) {
         }
       }
     }
-    gemm_epilogue<EPI>(p, mt, rt, nt * NT + j * 32, z, lane, v);
+    gemm_epilogue<EPI>(p, mt, rt, nt * NT + j * 32, z, lane, v, s_bias + j * 32, zc, s_scratch + warp * (TP_STRIDE * 32));
   }
 }
 
@@ -275,7 +326,7 @@ static cudaError_t launch_gemm(const GemmParams& p, int mtiles, int ntiles, bool
   const int splits = (p.nchunks + p.cps - 1) / p.cps;
   dim3 grid(mtiles, ntiles, splits);
   if (simt) {
-    k_gemm_simt<NT, EPI><<<grid, TC_THREADS, 0, st>>>(p);
+    k_gemm_simt<NT, EPI><<<grid, GEMM_THREADS, 0, st>>>(p);
     return cudaGetLastError();
   }
   const int smem = NSTAGE * (GBLK_A + gblk_b(NT)) * (int)sizeof(float);
@@ -285,6 +336,6 @@ static cudaError_t launch_gemm(const GemmParams& p, int mtiles, int ntiles, bool
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  k_gemm_tc<NT, NSTAGE, EPI><<<grid, TC_THREADS, smem, st>>>(p);
+  k_gemm_tc<NT, NSTAGE, EPI><<<grid, GEMM_THREADS, smem, st>>>(p);
   return cudaGetLastError();
 }

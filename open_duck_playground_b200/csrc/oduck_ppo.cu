@@ -6,7 +6,7 @@
 // Launch sequence of one minibatch (B trajectories x T steps; Mp = T B policy rows, Mv = (T + 1) B value rows):
 //   k_ppo_pack x2        gather rows by env index, normalise, write R(X0) and R(X0^T) (hi/lo tf32 operand blocks)
 //   k_gemm_tc  x8        forward: 3 x (Dense + swish) + head, per net; epilogues emit the next operands in both orientations
-//   k_ppo_gae            per-trajectory GAE scan, advantage statistics (one CTA, deterministic)
+//   k_ppo_gae            per-trajectory GAE scan, advantage statistics (last-CTA reduction in CTA order: deterministic)
 //   k_ppo_loss           per-row NormalTanh log-prob / ratio / clip / entropy / value error -> head gradients as operands
 //   k_gemm_tc  x14       backward: dW_l = X_l^T dZ_l (split-K over the batch) and dZ_{l-1} = (dZ_l W_l^T) * swish'(Z_{l-1})
 //   k_ppo_grad_reduce    sum split-K / per-warp partials into the flat gradient, partial sums of squares
@@ -70,12 +70,12 @@ struct OduckPpo {
   NetBuf net[2];
   float *params, *grads, *adam_m, *adam_v, *packed, *partial;
   long long P, packed_floats, partial_floats;
-  float *adv, *vs;
+  float *adv, *vs, *adv_norm;
   double* losses;           // [8]
-  double* stats;            // [4] adv mean, std
+  double* stats;            // [4 + 2 * gae CTAs] adv mean, std | per-CTA partial sums
   float* sumsq_part;        // [grid of grad_reduce]
-  int* step;                // [2]: adam step count, finished-block ticket
-  int reduce_blocks, gae_smem;
+  int* step;                // [3]: adam step count, finished-block tickets of k_ppo_adam and k_ppo_gae
+  int reduce_blocks;
   int64_t launches;
   cudaStream_t side;        // the value net's chain runs here, concurrently with the policy net's chain on the caller's stream
   cudaEvent_t ev_fork, ev_join;
@@ -118,61 +118,55 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
   return t;
 }
 
-// brax losses.compute_gae over one trajectory per thread; one CTA so that the advantage statistics are deterministic.
-// STAGED: the whole CTA first gathers the minibatch's values / rewards / done / truncation into shared memory with
-// independent loads (the scan itself is a chain of T dependent steps; gathering inside it costs T global-load latencies).
-template <bool STAGED>
-__global__ void __launch_bounds__(1024) k_ppo_gae(const float* __restrict__ values /*[Mv_pad][32]*/, OduckRollout ro, const int* __restrict__ idx, int B, int T,
-                                                  float discount, float lambda, float reward_scaling, int normalize, float* __restrict__ adv,
-                                                  float* __restrict__ vs, double* __restrict__ stats, double* __restrict__ losses) {
-  extern __shared__ float gsm[];                       // STAGED: val[(T + 1) B] | rew[T B] | done[T B] | trunc[T B]
-  __shared__ double sh[32];
-  if (threadIdx.x < 8) losses[threadIdx.x] = 0.0;
+// brax losses.compute_gae, one trajectory per thread, one warp per CTA (B / 32 CTAs).  The gathers of a trajectory are issued
+// up front into a thread-local window (independent loads, the scan itself is a chain of T dependent steps).  Advantage
+// statistics: every CTA leaves its partial sums, the last CTA to finish adds them in CTA order (deterministic) and publishes
+// mean / std; k_ppo_loss normalises on the fly.
+#define GAE_THREADS 32
+__global__ void __launch_bounds__(GAE_THREADS) k_ppo_gae(const float* __restrict__ values /*[Mv_pad][32]*/, OduckRollout ro, const int* __restrict__ idx, int B, int T,
+                                                         float discount, float lambda, float reward_scaling, float* __restrict__ adv, float* __restrict__ vs,
+                                                         double* __restrict__ stats /*[4 + 2 * gridDim.x]*/, int* __restrict__ ticket, double* __restrict__ losses) {
+  if (blockIdx.x == 0 && threadIdx.x < 8) losses[threadIdx.x] = 0.0;
   const int N = ro.num_envs;
-  float* s_val = gsm;
-  float* s_rew = s_val + (T + 1) * B;
-  float* s_done = s_rew + T * B;
-  float* s_trunc = s_done + T * B;
-  if (STAGED) {
-    for (int i = threadIdx.x; i < (T + 1) * B; i += blockDim.x) s_val[i] = values[(size_t)i * PPO_HEADW];
-    for (int i = threadIdx.x; i < T * B; i += blockDim.x) {
-      const int t = i / B, b = i - t * B;
-      const size_t g = (size_t)t * N + idx[b];
-      s_rew[i] = ro.reward[g]; s_done[i] = ro.done[g]; s_trunc[i] = ro.truncation[g];
-    }
-    __syncthreads();
-  }
+  const int b = blockIdx.x * GAE_THREADS + threadIdx.x;
   double s1 = 0.0, s2 = 0.0;
-  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+  if (b < B) {
     const int env = idx[b];
-    float acc = 0.f;
-    const float boot = STAGED ? s_val[T * B + b] : values[(size_t)(T * B + b) * PPO_HEADW];
-    float v_next = boot, vs_next = boot;
-    for (int t = T - 1; t >= 0; --t) {
+    float lv[PPO_MAXT + 1], lr[PPO_MAXT], ld[PPO_MAXT], lt[PPO_MAXT];
+    for (int t = 0; t < T; ++t) {
       const size_t g = (size_t)t * N + env;
-      const int i = t * B + b;
-      const float trunc = STAGED ? s_trunc[i] : ro.truncation[g], done = STAGED ? s_done[i] : ro.done[g];
-      const float rew = (STAGED ? s_rew[i] : ro.reward[g]) * reward_scaling;
+      lv[t] = values[(size_t)(t * B + b) * PPO_HEADW];
+      lr[t] = ro.reward[g]; ld[t] = ro.done[g]; lt[t] = ro.truncation[g];
+    }
+    lv[T] = values[(size_t)(T * B + b) * PPO_HEADW];
+    float acc = 0.f, v_next = lv[T], vs_next = lv[T];
+    for (int t = T - 1; t >= 0; --t) {
+      const float trunc = lt[t], done = ld[t], rew = lr[t] * reward_scaling;
       const float term = done * (1.f - trunc), mask = 1.f - trunc;
-      const float v = STAGED ? s_val[i] : values[(size_t)i * PPO_HEADW];
+      const float v = lv[t];
       const float delta = (rew + discount * (1.f - term) * v_next - v) * mask;
       acc = delta + discount * (1.f - term) * mask * lambda * acc;
       const float vst = acc + v;
       const float a = (rew + discount * (1.f - term) * vs_next - v) * mask;
-      vs[i] = vst;
-      adv[i] = a;
+      vs[t * B + b] = vst;
+      adv[t * B + b] = a;
       s1 += a; s2 += (double)a * a;
       v_next = v; vs_next = vst;
     }
   }
-  const double S1 = block_sum(s1, sh), S2 = block_sum(s2, sh);
-  const double n = (double)B * T;
-  const double mean = S1 / n, var = fmax(S2 / n - mean * mean, 0.0);
-  const float mf = (float)mean, sf = (float)sqrt(var);
-  if (threadIdx.x == 0) { stats[0] = mean; stats[1] = sqrt(var); }
-  if (normalize) {
-    for (int b = threadIdx.x; b < B; b += blockDim.x)
-      for (int t = 0; t < T; ++t) adv[t * B + b] = (adv[t * B + b] - mf) / (sf + 1e-8f);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+  if (threadIdx.x == 0) {
+    stats[4 + 2 * blockIdx.x] = s1; stats[5 + 2 * blockIdx.x] = s2;
+    __threadfence();
+    if (atomicAdd(ticket, 1) == (int)gridDim.x - 1) {
+      __threadfence();
+      double S1 = 0.0, S2 = 0.0;
+      for (int k = 0; k < (int)gridDim.x; ++k) { S1 += ((volatile double*)stats)[4 + 2 * k]; S2 += ((volatile double*)stats)[5 + 2 * k]; }
+      const double n = (double)B * T, mean = S1 / n, var = fmax(S2 / n - mean * mean, 0.0);
+      stats[0] = mean; stats[1] = sqrt(var);
+      *ticket = 0;
+    }
   }
 }
 
@@ -195,6 +189,9 @@ struct LossParams {
   const float* logits;      // [Mp_pad][32]
   const float* values;      // [Mv_pad][32]
   const float* adv; const float* vs;
+  const double* stats;      // [0] mean, [1] std of the raw advantages (k_ppo_gae)
+  float* adv_norm;          // [Mp] normalised advantages (published for the parity tests)
+  int normalize;
   OduckRollout ro;
   const int* idx;
   const float* noise;       // [Mp][na] or null
@@ -224,7 +221,9 @@ __global__ void __launch_bounds__(LOSS_ROWS * 16) k_ppo_loss(LossParams p) {
     const int t = r / p.B, b = r - t * p.B;
     const size_t gi = (size_t)t * p.ro.num_envs + p.idx[b];
     const float* lg = p.logits + (size_t)r * PPO_HEADW;
-    const float A = p.adv[r];
+    float A = p.adv[r];
+    if (p.normalize) A = (A - (float)p.stats[0]) / ((float)p.stats[1] + 1e-8f);
+    if (a == 0) p.adv_norm[r] = A;
     float logp = 0.f, ent = 0.f, dlp_loc = 0.f, dlp_sc = 0.f, dent_loc = 0.f, dent_sc = 0.f, sig = 0.f;
     if (a < p.na) {
       const float loc = lg[a], sp = lg[p.na + a];
@@ -509,8 +508,8 @@ int oduck_ppo_create(const OduckPpoConfig* cfg, int device, OduckPpo** out) {
   ok = ok && dev_alloc(h, h->dseg, 1) == 0;
   ok = ok && dev_alloc(h, h->params, (size_t)h->P) == 0 && dev_alloc(h, h->grads, (size_t)h->P) == 0 && dev_alloc(h, h->adam_m, (size_t)h->P) == 0 && dev_alloc(h, h->adam_v, (size_t)h->P) == 0;
   ok = ok && dev_alloc(h, h->packed, (size_t)poff) == 0 && dev_alloc(h, h->partial, (size_t)goff) == 0;
-  ok = ok && dev_alloc(h, h->adv, (size_t)T * B) == 0 && dev_alloc(h, h->vs, (size_t)T * B) == 0;
-  ok = ok && dev_alloc(h, h->losses, 8) == 0 && dev_alloc(h, h->stats, 4) == 0 && dev_alloc(h, h->step, 2) == 0;
+  ok = ok && dev_alloc(h, h->adv, (size_t)T * B) == 0 && dev_alloc(h, h->vs, (size_t)T * B) == 0 && dev_alloc(h, h->adv_norm, (size_t)T * B) == 0;
+  ok = ok && dev_alloc(h, h->losses, 8) == 0 && dev_alloc(h, h->stats, 4 + 2 * (size_t)ceil_div(B, GAE_THREADS)) == 0 && dev_alloc(h, h->step, 4) == 0;
   h->reduce_blocks = 296;
   ok = ok && dev_alloc(h, h->sumsq_part, (size_t)h->reduce_blocks) == 0;
   for (int net = 0; net < 2 && ok; ++net) {
@@ -534,9 +533,6 @@ int oduck_ppo_create(const OduckPpoConfig* cfg, int device, OduckPpo** out) {
   }
   if (!ok) { oduck_ppo_destroy(h); return oduck_fail(ODUCK_ERR_ALLOC, "oduck_ppo_create: cudaMalloc failed"); }
   PPO_TRY(cudaMemcpy(h->dseg, &h->seg, sizeof(SegTable), cudaMemcpyHostToDevice));
-  h->gae_smem = (int)(((size_t)(T + 1) * B + 3 * (size_t)T * B) * sizeof(float));
-  if (h->gae_smem > 200 * 1024) h->gae_smem = 0;                  // does not fit: gather inside the scan instead
-  else PPO_TRY(cudaFuncSetAttribute(k_ppo_gae<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->gae_smem));
   PPO_TRY(cudaDeviceSynchronize());
   *out = h;
   return ODUCK_OK;
@@ -569,7 +565,7 @@ int oduck_ppo_set_params(OduckPpo* h, const float* flat, int reset_opt, void* st
   if (reset_opt) {
     PPO_TRY(cudaMemsetAsync(h->adam_m, 0, (size_t)h->P * sizeof(float), st));
     PPO_TRY(cudaMemsetAsync(h->adam_v, 0, (size_t)h->P * sizeof(float), st));
-    PPO_TRY(cudaMemsetAsync(h->step, 0, 2 * sizeof(int), st));
+    PPO_TRY(cudaMemsetAsync(h->step, 0, 4 * sizeof(int), st));
   }
   return launch_adam(h, 0, st);
 }
@@ -585,7 +581,7 @@ int oduck_ppo_get_buffer(OduckPpo* h, int id, void** ptr, int64_t* count, int* d
     case ODUCK_PPO_BUF_LOGITS: *ptr = h->net[0].out; *count = (int64_t)h->net[0].Mpad * PPO_HEADW; break;
     case ODUCK_PPO_BUF_VALUES: *ptr = h->net[1].out; *count = (int64_t)h->net[1].Mpad * PPO_HEADW; break;
     case ODUCK_PPO_BUF_LOSSES: *ptr = h->losses; *count = 8; *dtype = ODUCK_DTYPE_F64; break;
-    case ODUCK_PPO_BUF_ADV: *ptr = h->adv; *count = (int64_t)h->T * h->B; break;
+    case ODUCK_PPO_BUF_ADV: *ptr = h->adv_norm; *count = (int64_t)h->T * h->B; break;
     case ODUCK_PPO_BUF_VS: *ptr = h->vs; *count = (int64_t)h->T * h->B; break;
     case ODUCK_PPO_BUF_STEP: *ptr = h->step; *count = 1; *dtype = ODUCK_DTYPE_I32; break;
     default: return oduck_fail(ODUCK_ERR_ARG, "oduck_ppo_get_buffer: unknown buffer id");
@@ -673,23 +669,22 @@ int oduck_ppo_minibatch(OduckPpo* h, const OduckRollout* ro, const OduckNormaliz
 #define JOIN() { PPO_TRY(cudaEventRecord(h->ev_join, h->side)); PPO_TRY(cudaStreamWaitEvent(st, h->ev_join, 0)); }
   if (stages & ODUCK_PPO_STAGE_FORWARD) {
     FORK()
-    k_ppo_pack<<<148, 256, 0, h->side>>>(ro->obs_value, ro->num_envs, nv.dims[0], env_idx, h->B, nv.M, nv.Mpad, ceil_div(nv.dims[0], TC_KC), nm->value_mean, nm->value_std, nv.Xr[0], nv.Xt[0]);
+    k_ppo_pack<<<296, 256, 0, h->side>>>(ro->obs_value, ro->num_envs, nv.dims[0], env_idx, h->B, nv.M, nv.Mpad, ceil_div(nv.dims[0], TC_KC), nm->value_mean, nm->value_std, nv.Xr[0], nv.Xt[0]);
     GEMM_TRY(cudaGetLastError());
     int rc = net_forward(h, 1, simt, h->side);
     if (rc) return rc;
-    k_ppo_pack<<<148, 256, 0, st>>>(ro->obs_policy, ro->num_envs, np.dims[0], env_idx, h->B, np.M, np.Mpad, ceil_div(np.dims[0], TC_KC), nm->policy_mean, nm->policy_std, np.Xr[0], np.Xt[0]);
+    k_ppo_pack<<<296, 256, 0, st>>>(ro->obs_policy, ro->num_envs, np.dims[0], env_idx, h->B, np.M, np.Mpad, ceil_div(np.dims[0], TC_KC), nm->policy_mean, nm->policy_std, np.Xr[0], np.Xt[0]);
     GEMM_TRY(cudaGetLastError());
     rc = net_forward(h, 0, simt, st);
     if (rc) return rc;
     JOIN()
   }
   if (stages & ODUCK_PPO_STAGE_LOSS) {
-    if (h->gae_smem > 0) k_ppo_gae<true><<<1, 1024, h->gae_smem, st>>>(nv.out, *ro, env_idx, h->B, h->T, c.discounting, c.gae_lambda, c.reward_scaling, c.normalize_advantage, h->adv, h->vs, h->stats, h->losses);
-    else k_ppo_gae<false><<<1, 1024, 0, st>>>(nv.out, *ro, env_idx, h->B, h->T, c.discounting, c.gae_lambda, c.reward_scaling, c.normalize_advantage, h->adv, h->vs, h->stats, h->losses);
+    k_ppo_gae<<<ceil_div(h->B, GAE_THREADS), GAE_THREADS, 0, st>>>(nv.out, *ro, env_idx, h->B, h->T, c.discounting, c.gae_lambda, c.reward_scaling, h->adv, h->vs, h->stats, h->step + 2, h->losses);
     GEMM_TRY(cudaGetLastError());
     LossParams lp;
     memset(&lp, 0, sizeof(lp));
-    lp.logits = np.out; lp.values = nv.out; lp.adv = h->adv; lp.vs = h->vs; lp.ro = *ro; lp.idx = env_idx; lp.noise = noise; lp.key = key;
+    lp.logits = np.out; lp.values = nv.out; lp.adv = h->adv; lp.vs = h->vs; lp.stats = h->stats; lp.adv_norm = h->adv_norm; lp.normalize = c.normalize_advantage; lp.ro = *ro; lp.idx = env_idx; lp.noise = noise; lp.key = key;
     lp.B = h->B; lp.T = h->T; lp.na = h->na; lp.Mp = np.M; lp.Mp_pad = np.Mpad; lp.Mv = nv.M; lp.Mv_pad = nv.Mpad;
     lp.clip_eps = c.clipping_epsilon; lp.entropy_cost = c.entropy_cost;
     const Seg& bp = h->seg.s[(0 * PPO_NL + PPO_NL - 1) * 2 + 1];
