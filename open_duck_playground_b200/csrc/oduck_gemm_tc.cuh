@@ -23,7 +23,7 @@ __device__ __forceinline__ void gsplit_tf32(float v, float& hi, float& lo) {
   lo = v - hi;
 }
 
-enum { EPI_FWD = 0, EPI_OUT = 1, EPI_DX = 2, EPI_DW = 3 };
+enum { EPI_FWD = 0, EPI_OUT = 1, EPI_DX = 2, EPI_DW = 3, EPI_ACT = 4 };   // ACT: FWD without the backward-pass by-products (rollout actor)
 
 struct GemmParams {
   const float* A;        // [mtiles][nchunks][GBLK_A]
@@ -129,8 +129,8 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const int mt,
     return;
   }
   // FWD: y = swish(acc + bias), pre-activation kept for the backward pass.  DX: y = acc * swish'(z).
-  if (EPI == EPI_FWD) {
-    float* zblk = p.Z + ((size_t)mt * p.z_nch + (n0 >> 5)) * (TC_M * TC_KC);
+  if (EPI == EPI_FWD || EPI == EPI_ACT) {
+    float* zblk = EPI == EPI_FWD ? p.Z + ((size_t)mt * p.z_nch + (n0 >> 5)) * (TC_M * TC_KC) : nullptr;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       float4 w;
@@ -141,7 +141,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const int mt,
         pw[e] = zz;
         v[4 * q + e] = __fdividef(zz, 1.f + __expf(-zz));
       }
-      *reinterpret_cast<float4*>(zblk + gblk_off(rt, 4 * q)) = w;
+      if (EPI == EPI_FWD) *reinterpret_cast<float4*>(zblk + gblk_off(rt, 4 * q)) = w;
     }
   } else {
 #pragma unroll
@@ -163,7 +163,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const int mt,
       *reinterpret_cast<float4*>(blk + TC_M * TC_KC + gblk_off(rt, 4 * q)) = l4;
     }
   }
-  {
+  if (EPI != EPI_ACT) {
     // transposed operand: element (n, row) of Y^T; the warp's 32 rows are exactly one k-chunk of it.  After the transpose
     // lane l owns column n0 + l for the warp's 32 rows: 8 float4 stores per half, 128-byte segments per 8 lanes.
     smem_transpose32(v, scratch, lane);
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_gemm_tc(GemmParams p) {
     mbar_init(&done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  if (EPI == EPI_FWD || EPI == EPI_OUT) {
+  if (EPI == EPI_FWD || EPI == EPI_OUT || EPI == EPI_ACT) {
     for (int i = threadIdx.x; i < NT; i += GEMM_THREADS) { const int n = nt * NT + i; s_bias[i] = n < p.nvalid ? __ldg(p.bias + n) : 0.f; }
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_gemm_simt(GemmParams p) {
   const int mt = blockIdx.x, nt = blockIdx.y, z = blockIdx.z;
   const int c0 = z * p.cps;
   const int n = min(p.nchunks - c0, p.cps);
-  if (EPI == EPI_FWD || EPI == EPI_OUT) {
+  if (EPI == EPI_FWD || EPI == EPI_OUT || EPI == EPI_ACT) {
     for (int i = threadIdx.x; i < NT; i += GEMM_THREADS) { const int nn = nt * NT + i; s_bias[i] = nn < p.nvalid ? p.bias[nn] : 0.f; }
   }
   __syncthreads();

@@ -9,6 +9,7 @@
 
 #include "oduck_handle.cuh"
 #include "oduck_policy_tc.cuh"
+#include "oduck_gemm_tc.cuh"
 #include <stdlib.h>
 
 extern int oduck_fail(int code, const std::string& msg);
@@ -266,8 +267,14 @@ extern "C" int oduck_policy_forward(OduckHandle* h, const OduckPolicyWeights* w,
   memset(&d, 0, sizeof(d));
   d.M = h->n;
   for (int l = 0; l < 3 && e == cudaSuccess; l++) {
-    d.Xb = abuf + aoff[l]; d.Wb = wbuf + woff[l]; d.B = w->b[l]; d.Yb = abuf + aoff[l + 1]; d.K = dims[l]; d.N = dims[l + 1];
-    e = launch_dense<128, false>(d, st);
+    // hidden layers: the learner's GEMM kernel (3-stage TMA ring, 8-warp epilogue) with the activation-only epilogue
+    GemmParams g;
+    memset(&g, 0, sizeof(g));
+    g.A = abuf + aoff[l]; g.B = wbuf + woff[l];
+    g.nchunks = (dims[l] + TC_KC - 1) / TC_KC; g.cps = g.nchunks;
+    g.bias = w->b[l]; g.nvalid = dims[l + 1];
+    g.Yr = abuf + aoff[l + 1]; g.yr_nch = dims[l + 1] / TC_KC;
+    e = launch_gemm<128, 3, EPI_ACT>(g, mtiles, dims[l + 1] / 128, false, st);
   }
   d.Xb = abuf + aoff[3]; d.Wb = wbuf + woff[3]; d.B = w->b[3]; d.Yb = nullptr; d.K = dims[3]; d.N = dims[4];
   d.keys = keys; d.action = action; d.raw = raw_action; d.logp = log_prob; d.deterministic = deterministic; d.na = w->out_dim / 2;

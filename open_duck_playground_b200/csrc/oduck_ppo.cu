@@ -15,6 +15,7 @@
 #include <math.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -22,6 +23,7 @@
 #include "../../include/oduck_ppo.h"
 #include "oduck_env.cuh"
 #include "oduck_gemm_tc.cuh"
+#include <cooperative_groups.h>
 
 extern int oduck_fail(int code, const std::string& msg);
 #define PPO_TRY(x)                                                                                             \
@@ -78,7 +80,9 @@ struct OduckPpo {
   int reduce_blocks;
   int64_t launches;
   cudaStream_t side;        // the value net's chain runs here, concurrently with the policy net's chain on the caller's stream
-  cudaEvent_t ev_fork, ev_join;
+  cudaStream_t side_w[2];   // weight-gradient GEMMs of the policy / value net (off the dZ critical path)
+  cudaEvent_t ev_fork, ev_join, ev_join_w[2], ev_dz[2][PPO_NL];
+  int coop_blocks;          // co-resident CTAs of the fused reduce + Adam kernel (0: cooperative launch unavailable)
   std::vector<void*> allocs;
 };
 
@@ -335,6 +339,109 @@ __device__ __forceinline__ const Seg& find_seg(const SegTable& tb, long long i) 
   return tb.s[k];
 }
 
+// gradient of flat element i: sum of its split-K partials (kernels) or per-CTA column sums (biases); four independent
+// accumulators keep four loads in flight per thread
+__device__ __forceinline__ float reduce_partials(const Seg& s, const float* __restrict__ partial, long long j) {
+  const float* q;
+  long long stride;
+  int cnt;
+  if (!s.bias) { const int k = (int)(j / s.N), n = (int)(j - (long long)k * s.N); q = partial + s.dwpart + (size_t)k * s.ldo + n; stride = s.split_stride; cnt = s.nsplit; }
+  else { q = partial + s.dbpart + j; stride = s.ldb; cnt = s.nwarprows; }
+  float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+  int z = 0;
+  for (; z + 4 <= cnt; z += 4) {
+    g0 += q[(size_t)z * stride]; g1 += q[(size_t)(z + 1) * stride]; g2 += q[(size_t)(z + 2) * stride]; g3 += q[(size_t)(z + 3) * stride];
+  }
+  for (; z < cnt; ++z) g0 += q[(size_t)z * stride];
+  return (g0 + g1) + (g2 + g3);
+}
+
+__device__ __forceinline__ void adam_element(const Seg& s, long long i, float g, float scale, float c1, float c2, float lr, float b1, float b2, float eps,
+                                             float* __restrict__ params, float* __restrict__ m1, float* __restrict__ m2, float* __restrict__ packed, bool update) {
+  float w = params[i];
+  if (update) {
+    g *= scale;
+    const float mm = b1 * m1[i] + (1.f - b1) * g, vv = b2 * m2[i] + (1.f - b2) * g * g;
+    m1[i] = mm; m2[i] = vv;
+    w -= lr * (mm * c1) / (sqrtf(vv * c2) + eps);
+    params[i] = w;
+  }
+  if (s.bias) return;
+  const long long j = i - s.off;
+  const int k = (int)(j / s.N), n = (int)(j - (long long)k * s.N);
+  float hi, lo;
+  gsplit_tf32(w, hi, lo);
+  {
+    // forward B operand: R_nt(W^T), rows = out feature n, contraction over the in feature k
+    const int kch = (s.K + TC_KC - 1) / TC_KC;
+    float* blk = packed + s.wf + ((size_t)(n / s.nt) * kch + (k >> 5)) * gblk_b(s.nt);
+    const int off = gblk_off(n % s.nt, k & 31);
+    blk[off] = hi; blk[s.nt * TC_KC + off] = lo;
+  }
+  if (s.wb >= 0) {
+    // dX B operand: R(W), rows = in feature k, contraction over the out feature n
+    const int nch = (s.N + TC_KC - 1) / TC_KC;
+    float* blk = packed + s.wb + ((size_t)(k >> 7) * nch + (n >> 5)) * GBLK_A;
+    const int off = gblk_off(k & 127, n & 31);
+    blk[off] = hi; blk[TC_M * TC_KC + off] = lo;
+  }
+}
+
+// Single-GPU product path: gradient reduce -> grid barrier -> global-norm clip + Adam + repack, one cooperative launch.
+// Every thread keeps the gradients of its (<= RA_MAX) elements in registers across the barrier.
+#define RA_MAX 8
+__global__ void __launch_bounds__(256) k_ppo_reduce_adam(const SegTable* __restrict__ tbp, const float* __restrict__ partial, float* __restrict__ grads,
+                                                         float* __restrict__ sumsq_part, float* __restrict__ params, float* __restrict__ m1, float* __restrict__ m2,
+                                                         float* __restrict__ packed, int* __restrict__ step, float lr, float b1, float b2, float eps, float max_norm) {
+  __shared__ double sh[32];
+  __shared__ SegTable tb;
+  __shared__ float s_scale, s_c1, s_c2;
+  for (int i = threadIdx.x; i < (int)(sizeof(SegTable) / 4); i += blockDim.x) reinterpret_cast<int*>(&tb)[i] = reinterpret_cast<const int*>(tbp)[i];
+  __syncthreads();
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  float g[RA_MAX];
+  double ss = 0.0;
+#pragma unroll
+  for (int e = 0; e < RA_MAX; ++e) {
+    const long long i = tid + (long long)e * nth;
+    g[e] = 0.f;
+    if (i < tb.total) {
+      const Seg& s = find_seg(tb, i);
+      g[e] = reduce_partials(s, partial, i - s.off);
+      grads[i] = g[e];
+      ss += (double)g[e] * g[e];
+    }
+  }
+  for (long long i = tid + (long long)RA_MAX * nth; i < tb.total; i += nth) {      // (only if P > RA_MAX * threads)
+    const Seg& s = find_seg(tb, i);
+    const float x = reduce_partials(s, partial, i - s.off);
+    grads[i] = x;
+    ss += (double)x * x;
+  }
+  const double t = block_sum(ss, sh);
+  if (threadIdx.x == 0) sumsq_part[blockIdx.x] = (float)t;
+  __threadfence();
+  cooperative_groups::this_grid().sync();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int k = 0; k < (int)gridDim.x; ++k) tot += (double)((volatile float*)sumsq_part)[k];
+    const float gn = (float)sqrt(tot);
+    s_scale = (max_norm > 0.f && gn >= max_norm) ? max_norm / gn : 1.f;
+    const int tt = step[0] + 1;
+    s_c1 = 1.f / (1.f - powf(b1, (float)tt));
+    s_c2 = 1.f / (1.f - powf(b2, (float)tt));
+  }
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < RA_MAX; ++e) {
+    const long long i = tid + (long long)e * nth;
+    if (i < tb.total) adam_element(find_seg(tb, i), i, g[e], s_scale, s_c1, s_c2, lr, b1, b2, eps, params, m1, m2, packed, true);
+  }
+  for (long long i = tid + (long long)RA_MAX * nth; i < tb.total; i += nth) adam_element(find_seg(tb, i), i, grads[i], s_scale, s_c1, s_c2, lr, b1, b2, eps, params, m1, m2, packed, true);
+  cooperative_groups::this_grid().sync();
+  if (blockIdx.x == 0 && threadIdx.x == 0) step[0] += 1;
+}
+
 // flat gradient <- split-K partials (kernels) / per-warp column sums (biases); per-block sum of squares for the global norm
 __global__ void __launch_bounds__(256) k_ppo_grad_reduce(const SegTable* __restrict__ tbp, const float* __restrict__ partial, float* __restrict__ grads, float* __restrict__ sumsq_part) {
   __shared__ double sh[32];
@@ -344,16 +451,7 @@ __global__ void __launch_bounds__(256) k_ppo_grad_reduce(const SegTable* __restr
   double ss = 0.0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tb.total; i += (long long)gridDim.x * blockDim.x) {
     const Seg& s = find_seg(tb, i);
-    const long long j = i - s.off;
-    float g = 0.f;
-    if (!s.bias) {
-      const int k = (int)(j / s.N), n = (int)(j % s.N);
-      const float* q = partial + s.dwpart + (size_t)k * s.ldo + n;
-      for (int z = 0; z < s.nsplit; ++z) g += q[(size_t)z * s.split_stride];
-    } else {
-      const float* q = partial + s.dbpart + j;
-      for (int w = 0; w < s.nwarprows; ++w) g += q[(size_t)w * s.ldb];
-    }
+    const float g = reduce_partials(s, partial, i - s.off);
     grads[i] = g;
     ss += (double)g * g;
   }
@@ -444,6 +542,11 @@ int oduck_ppo_destroy(OduckPpo* h) {
   if (h->side) cudaStreamDestroy(h->side);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
+  for (int k = 0; k < 2; ++k) {
+    if (h->side_w[k]) cudaStreamDestroy(h->side_w[k]);
+    if (h->ev_join_w[k]) cudaEventDestroy(h->ev_join_w[k]);
+    for (int l = 0; l < PPO_NL; ++l) if (h->ev_dz[k][l]) cudaEventDestroy(h->ev_dz[k][l]);
+  }
   delete h;
   return ODUCK_OK;
 }
@@ -465,9 +568,17 @@ int oduck_ppo_create(const OduckPpoConfig* cfg, int device, OduckPpo** out) {
   PPO_TRY(cudaSetDevice(device));
   OduckPpo* h = new OduckPpo();
   h->cfg = *cfg; h->device = device; h->B = B; h->T = T; h->na = na; h->launches = 0;
-  h->side = nullptr; h->ev_fork = h->ev_join = nullptr;
-  if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) { oduck_ppo_destroy(h); return oduck_fail(ODUCK_ERR_CUDA, "oduck_ppo_create: stream / event creation failed"); }
+  h->side = nullptr; h->ev_fork = h->ev_join = nullptr; h->coop_blocks = 0;
+  memset(h->side_w, 0, sizeof(h->side_w)); memset(h->ev_join_w, 0, sizeof(h->ev_join_w)); memset(h->ev_dz, 0, sizeof(h->ev_dz));
+  {
+    bool sok = cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+               cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) == cudaSuccess;
+    for (int k = 0; k < 2 && sok; ++k) {
+      sok = cudaStreamCreateWithFlags(&h->side_w[k], cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&h->ev_join_w[k], cudaEventDisableTiming) == cudaSuccess;
+      for (int l = 0; l < PPO_NL && sok; ++l) sok = cudaEventCreateWithFlags(&h->ev_dz[k][l], cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (!sok) { oduck_ppo_destroy(h); return oduck_fail(ODUCK_ERR_CUDA, "oduck_ppo_create: stream / event creation failed"); }
+  }
   // ---- parameter segments, packed-operand and partial-gradient layouts
   SegTable& tb = h->seg;
   memset(&tb, 0, sizeof(tb));
@@ -533,6 +644,13 @@ int oduck_ppo_create(const OduckPpoConfig* cfg, int device, OduckPpo** out) {
   }
   if (!ok) { oduck_ppo_destroy(h); return oduck_fail(ODUCK_ERR_ALLOC, "oduck_ppo_create: cudaMalloc failed"); }
   PPO_TRY(cudaMemcpy(h->dseg, &h->seg, sizeof(SegTable), cudaMemcpyHostToDevice));
+  {
+    int coop = 0, per_sm = 0, sms = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ppo_reduce_adam, 256, 0) == cudaSuccess && per_sm > 0)
+      h->coop_blocks = std::min(h->reduce_blocks, per_sm * sms);
+  }
   PPO_TRY(cudaDeviceSynchronize());
   *out = h;
   return ODUCK_OK;
@@ -619,7 +737,9 @@ static int net_forward(OduckPpo* h, int net, bool simt, cudaStream_t st) {
   return ODUCK_OK;
 }
 
-static int net_backward(OduckPpo* h, int net, bool simt, cudaStream_t st) {
+// Backward of one net on two streams: the dZ chain (dX GEMMs, the critical path) on `sx`, the weight-gradient GEMMs on `sw`;
+// dW_l waits for the event that marks dZ_l complete (dZ of the head layer comes from k_ppo_loss, before the fork).
+static int net_backward(OduckPpo* h, int net, bool simt, cudaStream_t sx, cudaStream_t sw) {
   NetBuf& nb = h->net[net];
   for (int l = PPO_NL - 1; l >= 0; --l) {
     const Seg& w = h->seg.s[(net * PPO_NL + l) * 2];
@@ -631,8 +751,8 @@ static int net_backward(OduckPpo* h, int net, bool simt, cudaStream_t st) {
       g.nchunks = nb.Mpad / TC_KC; g.cps = ceil_div(g.nchunks, w.nsplit);
       g.out = h->partial + w.dwpart; g.ldo = w.ldo; g.out_split = w.split_stride;
       const int mt = ceil_div(w.K, 128);
-      if (l == PPO_NL - 1) GEMM_TRY((launch_gemm<PPO_HEADW, 4, EPI_DW>(g, mt, 1, simt, st)));
-      else GEMM_TRY((launch_gemm<128, 3, EPI_DW>(g, mt, w.N / 128, simt, st)));
+      if (l == PPO_NL - 1) GEMM_TRY((launch_gemm<PPO_HEADW, 4, EPI_DW>(g, mt, 1, simt, sw)));
+      else GEMM_TRY((launch_gemm<128, 3, EPI_DW>(g, mt, w.N / 128, simt, sw)));
     }
     if (l > 0) {
       // dZ_{l-1} = (dZ_l W_l^T) * swish'(Z_{l-1}): columns = in features of layer l, contraction over its out features
@@ -646,7 +766,11 @@ static int net_backward(OduckPpo* h, int net, bool simt, cudaStream_t st) {
       g.Yt = nb.dZt[l - 1]; g.yt_nch = nb.Mpad / TC_KC;
       g.dbpart = h->partial + bprev.dbpart; g.ldb = bprev.ldb;
       g.nvalid = w.K;
-      GEMM_TRY((launch_gemm<128, 3, EPI_DX>(g, nb.mtiles, w.K / 128, simt, st)));
+      GEMM_TRY((launch_gemm<128, 3, EPI_DX>(g, nb.mtiles, w.K / 128, simt, sx)));
+      if (sw != sx) {
+        PPO_TRY(cudaEventRecord(h->ev_dz[net][l - 1], sx));
+        PPO_TRY(cudaStreamWaitEvent(sw, h->ev_dz[net][l - 1], 0));
+      }
     }
   }
   return ODUCK_OK;
@@ -697,11 +821,24 @@ int oduck_ppo_minibatch(OduckPpo* h, const OduckRollout* ro, const OduckNormaliz
   }
   if (stages & ODUCK_PPO_STAGE_BACKWARD) {
     FORK()
-    int rc = net_backward(h, 1, simt, h->side);
+    for (int k = 0; k < 2; ++k) PPO_TRY(cudaStreamWaitEvent(h->side_w[k], h->ev_fork, 0));
+    int rc = net_backward(h, 1, simt, h->side, h->side_w[1]);
     if (rc) return rc;
-    rc = net_backward(h, 0, simt, st);
+    rc = net_backward(h, 0, simt, st, h->side_w[0]);
     if (rc) return rc;
     JOIN()
+    for (int k = 0; k < 2; ++k) { PPO_TRY(cudaEventRecord(h->ev_join_w[k], h->side_w[k])); PPO_TRY(cudaStreamWaitEvent(st, h->ev_join_w[k], 0)); }
+    if ((stages & ODUCK_PPO_STAGE_ADAM) && h->coop_blocks > 0) {
+      // product path on one GPU: gradient reduce, global norm and Adam in one cooperative launch (grid barrier in between)
+      const OduckPpoConfig& cc = h->cfg;
+      const SegTable* a0 = h->dseg; const float* a1 = h->partial; float* a2 = h->grads; float* a3 = h->sumsq_part; float* a4 = h->params; float* a5 = h->adam_m;
+      float* a6 = h->adam_v; float* a7 = h->packed; int* a8 = h->step;
+      float lr = cc.learning_rate, b1 = cc.adam_b1, b2 = cc.adam_b2, eps = cc.adam_eps, mx = cc.max_grad_norm;
+      void* args[] = {&a0, &a1, &a2, &a3, &a4, &a5, &a6, &a7, &a8, &lr, &b1, &b2, &eps, &mx};
+      PPO_TRY(cudaLaunchCooperativeKernel((void*)k_ppo_reduce_adam, dim3(h->coop_blocks), dim3(256), args, 0, st));
+      h->launches++;
+      return ODUCK_OK;
+    }
     k_ppo_grad_reduce<<<h->reduce_blocks, 256, 0, st>>>(h->dseg, h->partial, h->grads, h->sumsq_part);
     GEMM_TRY(cudaGetLastError());
   }

@@ -122,6 +122,7 @@ def test_learner_stages_match_torch(simt, shape):
     cfg, policy, value, batch, norm = _make(3, N, T, nmb, dev)
     B = N // nmb
     L = ppo.DeviceLearner(cfg, policy, value, B, 14, dev)
+    L2 = ppo.DeviceLearner(cfg, policy, value, B, 14, dev)        # takes the same step through the one-call product path
     assert L.h.num_params == sum(p.numel() for m in (policy, value) for p in m.parameters())
     assert torch.equal(L.params, _flat(policy, value))
     # make the behaviour log-prob consistent with the current policy (ratios near 1, some clipped)
@@ -198,6 +199,13 @@ def test_learner_stages_match_torch(simt, shape):
         # Adam's first steps are sign-like: an element whose gradient is ~1e-6 of the typical size amplifies the GEMM rounding
         # error, so a handful of the 0.5 M elements may move differently (by at most two lr: opposite signs); everything else agrees to 2e-6
         assert frac < 3e-4 and err < 2.2 * cfg.learning_rate
+        if step == 1:
+            # ODUCK_PPO_ALL in one call (streams forked/joined inside, fused cooperative reduce + Adam) == the staged calls
+            L2.minibatch(ro, nm, idx32.data_ptr(), noise.data_ptr(), 0, capi.PPO_ALL | dbg)
+            torch.cuda.synchronize()
+            d2 = (L2.params - L.params).abs().max().item()
+            print(f"one-call path vs staged path: max|dparam|={d2:.2e}, step={int(L2.step.item())}")
+            assert d2 < 1e-7 and int(L2.step.item()) == 1
 
 
 @pytest.mark.gpu
