@@ -57,20 +57,26 @@ __global__ void k_pack_weights(const float* __restrict__ W, float* __restrict__ 
     blk[NT * TC_KC + blk_off(r, kk)] = lo;
   }
 }
-// observations -> normalised, blocked hi/lo A operand of the first layer
+// observations -> normalised, blocked hi/lo A operand of the first layer.  One thread per (row, group of 4 k): the blocked
+// layout keeps those 4 values contiguous, so hi and lo go out as one float4 each, 128 bytes per 8 consecutive rows.
 __global__ void k_pack_obs(const float* __restrict__ obs, int ld, const float* __restrict__ mean, const float* __restrict__ stdv, float* __restrict__ out, int M, int K) {
   const int nchunks = (K + TC_KC - 1) / TC_KC, mtiles = (M + TC_M - 1) / TC_M;
-  const int total = mtiles * nchunks * TC_M * TC_KC;
+  const int total = mtiles * nchunks * TC_M * (TC_KC / 4);
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    const int kk = idx % TC_KC, r = (idx / TC_KC) % TC_M, c = (idx / (TC_KC * TC_M)) % nchunks, t = idx / (TC_KC * TC_M * nchunks);
-    const int row = t * TC_M + r, k = c * TC_KC + kk;
-    float v = 0.f;
-    if (row < M && k < K) v = (obs[(size_t)row * ld + k] - mean[k]) / stdv[k];
-    float hi, lo;
-    split_tf32(v, hi, lo);
+    const int r = idx % TC_M, kg = (idx / TC_M) % (TC_KC / 4), c = (idx / (TC_M * (TC_KC / 4))) % nchunks, t = idx / (TC_M * (TC_KC / 4) * nchunks);
+    const int row = t * TC_M + r, k0 = c * TC_KC + 4 * kg;
+    float4 h4, l4;
+    float* ph = reinterpret_cast<float*>(&h4);
+    float* pl = reinterpret_cast<float*>(&l4);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = k0 + e;
+      const float v = (row < M && k < K) ? (obs[(size_t)row * ld + k] - mean[k]) / stdv[k] : 0.f;
+      split_tf32(v, ph[e], pl[e]);
+    }
     float* blk = out + (size_t)(t * nchunks + c) * BLK_A;
-    blk[blk_off(r, kk)] = hi;
-    blk[TC_M * TC_KC + blk_off(r, kk)] = lo;
+    *reinterpret_cast<float4*>(blk + blk_off(r, 4 * kg)) = h4;
+    *reinterpret_cast<float4*>(blk + TC_M * TC_KC + blk_off(r, 4 * kg)) = l4;
   }
 }
 

@@ -88,25 +88,48 @@ struct OduckPpo {
 
 // ------------------------------------------------------------------------------------------------- kernels
 // Gather the minibatch rows (row = t * B + b <- env idx[b] at time t), normalise, emit R(X) and R(X^T).
+// One thread per 4 x 4 micro-tile (4 rows x 4 features): both layouts keep 4 consecutive k (R(X)) / 4 consecutive rows
+// (R(X^T)) contiguous, so every store is a float4.
 __global__ void k_ppo_pack(const float* __restrict__ obs, int N, int K, const int* __restrict__ idx, int B, int M, int Mpad, int kch,
                            const float* __restrict__ mean, const float* __restrict__ stdv, float* __restrict__ Xr, float* __restrict__ Xt) {
-  const int K32 = kch * TC_KC, ytn = Mpad / TC_KC;
-  const long long total = (long long)Mpad * K32;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int row = (int)(i / K32), k = (int)(i % K32);
-    float v = 0.f;
-    if (row < M && k < K) {
-      const int t = row / B, b = row - t * B;
-      v = (obs[((size_t)t * N + idx[b]) * K + k] - mean[k]) / stdv[k];
+  const int K4 = kch * (TC_KC / 4), ytn = Mpad / TC_KC;
+  const int total = (Mpad / 4) * K4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int kg = i % K4, rg = i / K4;                  // consecutive threads: consecutive feature groups of one row group (coalesced gathers)
+    const int row0 = 4 * rg, k0 = 4 * kg;
+    float v[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int row = row0 + a;
+      const float* src = nullptr;
+      if (row < M) { const int t = row / B, b = row - t * B; src = obs + ((size_t)t * N + idx[b]) * K; }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const int k = k0 + e; v[a][e] = (src && k < K) ? (src[k] - mean[k]) / stdv[k] : 0.f; }
     }
-    float hi, lo;
-    gsplit_tf32(v, hi, lo);
-    float* blk = Xr + ((size_t)(row >> 7) * kch + (k >> 5)) * GBLK_A;
-    int off = gblk_off(row & 127, k & 31);
-    blk[off] = hi; blk[TC_M * TC_KC + off] = lo;
-    blk = Xt + ((size_t)(k >> 7) * ytn + (row >> 5)) * GBLK_A;
-    off = gblk_off(k & 127, row & 31);
-    blk[off] = hi; blk[TC_M * TC_KC + off] = lo;
+    float* blk = Xr + ((size_t)(row0 >> 7) * kch + (k0 >> 5)) * GBLK_A;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      float4 h4, l4;
+      float* ph = reinterpret_cast<float*>(&h4);
+      float* pl = reinterpret_cast<float*>(&l4);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) gsplit_tf32(v[a][e], ph[e], pl[e]);
+      const int off = gblk_off((row0 + a) & 127, k0 & 31);
+      *reinterpret_cast<float4*>(blk + off) = h4;
+      *reinterpret_cast<float4*>(blk + TC_M * TC_KC + off) = l4;
+    }
+    blk = Xt + ((size_t)(k0 >> 7) * ytn + (row0 >> 5)) * GBLK_A;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float4 h4, l4;
+      float* ph = reinterpret_cast<float*>(&h4);
+      float* pl = reinterpret_cast<float*>(&l4);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) gsplit_tf32(v[a][e], ph[a], pl[a]);
+      const int off = gblk_off((k0 + e) & 127, row0 & 31);
+      *reinterpret_cast<float4*>(blk + off) = h4;
+      *reinterpret_cast<float4*>(blk + TC_M * TC_KC + off) = l4;
+    }
   }
 }
 
@@ -341,11 +364,12 @@ __device__ __forceinline__ const Seg& find_seg(const SegTable& tb, long long i) 
 
 // gradient of flat element i: sum of its split-K partials (kernels) or per-CTA column sums (biases); four independent
 // accumulators keep four loads in flight per thread
-__device__ __forceinline__ float reduce_partials(const Seg& s, const float* __restrict__ partial, long long j) {
+__device__ __forceinline__ float reduce_partials(const Seg& s, const float* __restrict__ partial, long long jj) {
   const float* q;
   long long stride;
   int cnt;
-  if (!s.bias) { const int k = (int)(j / s.N), n = (int)(j - (long long)k * s.N); q = partial + s.dwpart + (size_t)k * s.ldo + n; stride = s.split_stride; cnt = s.nsplit; }
+  const unsigned j = (unsigned)jj;                             // offsets inside a tensor fit 32 bits: 32-bit division (a 64-bit one costs ~100 instructions)
+  if (!s.bias) { const unsigned k = j / (unsigned)s.N, n = j - k * (unsigned)s.N; q = partial + s.dwpart + (size_t)k * s.ldo + n; stride = s.split_stride; cnt = s.nsplit; }
   else { q = partial + s.dbpart + j; stride = s.ldb; cnt = s.nwarprows; }
   float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
   int z = 0;
@@ -367,15 +391,16 @@ __device__ __forceinline__ void adam_element(const Seg& s, long long i, float g,
     params[i] = w;
   }
   if (s.bias) return;
-  const long long j = i - s.off;
-  const int k = (int)(j / s.N), n = (int)(j - (long long)k * s.N);
+  const unsigned j = (unsigned)(i - s.off);
+  const int k = (int)(j / (unsigned)s.N), n = (int)(j - (unsigned)k * (unsigned)s.N);
   float hi, lo;
   gsplit_tf32(w, hi, lo);
   {
-    // forward B operand: R_nt(W^T), rows = out feature n, contraction over the in feature k
+    // forward B operand: R_nt(W^T), rows = out feature n, contraction over the in feature k (nt is 128 or 32)
     const int kch = (s.K + TC_KC - 1) / TC_KC;
-    float* blk = packed + s.wf + ((size_t)(n / s.nt) * kch + (k >> 5)) * gblk_b(s.nt);
-    const int off = gblk_off(n % s.nt, k & 31);
+    const int ntile = s.nt == 128 ? n >> 7 : n >> 5, nrow = n & (s.nt - 1);
+    float* blk = packed + s.wf + ((size_t)ntile * kch + (k >> 5)) * gblk_b(s.nt);
+    const int off = gblk_off(nrow, k & 31);
     blk[off] = hi; blk[s.nt * TC_KC + off] = lo;
   }
   if (s.wb >= 0) {
@@ -484,36 +509,8 @@ __global__ void __launch_bounds__(256) k_ppo_adam(const SegTable* __restrict__ t
     s_c2 = 1.f / (1.f - powf(b2, (float)t));
   }
   __syncthreads();
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tb.total; i += (long long)gridDim.x * blockDim.x) {
-    float w = params[i];
-    if (update) {
-      const float g = grads[i] * s_scale;
-      const float mm = b1 * m1[i] + (1.f - b1) * g, vv = b2 * m2[i] + (1.f - b2) * g * g;
-      m1[i] = mm; m2[i] = vv;
-      w -= lr * (mm * s_c1) / (sqrtf(vv * s_c2) + eps);
-      params[i] = w;
-    }
-    const Seg& s = find_seg(tb, i);
-    if (s.bias) continue;
-    const long long j = i - s.off;
-    const int k = (int)(j / s.N), n = (int)(j % s.N);
-    float hi, lo;
-    gsplit_tf32(w, hi, lo);
-    {
-      // forward B operand: R_nt(W^T), rows = out feature n, contraction over the in feature k
-      const int kch = (s.K + TC_KC - 1) / TC_KC;
-      float* blk = packed + s.wf + ((size_t)(n / s.nt) * kch + (k >> 5)) * gblk_b(s.nt);
-      const int off = gblk_off(n % s.nt, k & 31);
-      blk[off] = hi; blk[s.nt * TC_KC + off] = lo;
-    }
-    if (s.wb >= 0) {
-      // dX B operand: R(W), rows = in feature k, contraction over the out feature n
-      const int nch = (s.N + TC_KC - 1) / TC_KC;
-      float* blk = packed + s.wb + ((size_t)(k >> 7) * nch + (n >> 5)) * GBLK_A;
-      const int off = gblk_off(k & 127, n & 31);
-      blk[off] = hi; blk[TC_M * TC_KC + off] = lo;
-    }
-  }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tb.total; i += (long long)gridDim.x * blockDim.x)
+    adam_element(find_seg(tb, i), i, update ? grads[i] : 0.f, s_scale, s_c1, s_c2, lr, b1, b2, eps, params, m1, m2, packed, update != 0);
   if (update) {
     __threadfence();
     __syncthreads();
