@@ -9,8 +9,8 @@
  *   oduck_create            OpenDuckMiniV2Env.__init__ + mjx.put_model     open_duck_mini_v2/base.py:44-61
  *                           Joystick._post_init                            open_duck_mini_v2/joystick.py:121-204
  *   oduck_randomize         randomize.domain_randomize                     common/randomize.py:26-146
- *   oduck_reset             Joystick.reset (+ wrapper first_state store)   open_duck_mini_v2/joystick.py:206-321
- *   oduck_step              Joystick.step wrapped by wrap_for_brax_training open_duck_mini_v2/joystick.py:323-481, common/runner.py:117
+ *   oduck_reset             Joystick.reset (+ wrapper first_state store)   open_duck_mini_v2/joystick.py:206-321   (Standing: standing.py:200-318)
+ *   oduck_step              Joystick.step wrapped by wrap_for_brax_training open_duck_mini_v2/joystick.py:323-481, common/runner.py:117   (Standing: standing.py:320-443)
  *   oduck_physics_substeps  mjx_env.step(model, data, ctrl, n_substeps)    open_duck_mini_v2/joystick.py:420
  *   oduck_forward           mjx_env.init's mjx.forward                     open_duck_mini_v2/joystick.py:258
  *   oduck_policy_forward    Brax make_ppo_networks policy apply            common/runner.py:94-100, common/export_onnx.py:64-72
@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define ODUCK_ABI_VERSION 4
+#define ODUCK_ABI_VERSION 5
 
 #define ODUCK_MAX_BODY 20
 #define ODUCK_MAX_JNT 28
@@ -57,9 +57,11 @@ extern "C" {
 #define ODUCK_MAX_CON 12       /* 2 x plane/hfield-foot + 1 x foot-foot */
 #define ODUCK_REF_DIM 40       /* reference-motion frame width */
 #define ODUCK_POLY_DEG 16      /* coefficients per polynomial */
-#define ODUCK_OBS_STATE 101
-#define ODUCK_OBS_PRIV 212
+#define ODUCK_OBS_STATE 101    /* Joystick obs["state"]; also the capacity of the per-env obs records (Standing: 85) */
+#define ODUCK_OBS_PRIV 212     /* Joystick obs["privileged_state"] (Standing: 153) */
 #define ODUCK_NMETRIC 8
+#define ODUCK_TASK_JOYSTICK 0  /* open_duck_mini_v2/joystick.py */
+#define ODUCK_TASK_STANDING 1  /* open_duck_mini_v2/standing.py: same physics, other rewards / observation */
 #define ODUCK_NCMD 7
 
 typedef enum {
@@ -159,6 +161,7 @@ typedef struct OduckModel {
 /* Environment constants: Joystick.default_config() (joystick.py:49-102) plus the
  * tables _post_init derives (joystick.py:121-204). */
 typedef struct OduckEnvConfig {
+  int32_t task;                  /* ODUCK_TASK_*: which env class the step implements */
   int32_t n_substeps;            /* ctrl_dt / sim_dt = 10 */
   int32_t episode_length;        /* 1000 (EpisodeWrapper) */
   int32_t use_imitation_reward;  /* joystick.py:45 */
@@ -176,6 +179,8 @@ typedef struct OduckEnvConfig {
   double qpos_noise_scale[ODUCK_MAX_NU];   /* joystick.py:184-200, quirk #3 of SURVEY 2.1 */
   double scale_tracking_lin_vel, scale_tracking_ang_vel, scale_torques, scale_action_rate;
   double scale_stand_still, scale_alive, scale_imitation;
+  double scale_orientation, scale_head_pos;   /* Standing only (standing.py:75-84; rewards.py:45-46,131-147) */
+  double reset_base_qvel_noise;               /* joystick.py:253: 0.05, standing.py:247: 0.5 */
   double tracking_sigma;
   double push_interval_range[2];
   double push_magnitude_range[2];
@@ -209,12 +214,13 @@ typedef enum {
   ODUCK_BUF_QACC_WARM,       /* f32 [N, nv]  */
   ODUCK_BUF_QACC,            /* f32 [N, nv]  last solver output */
   ODUCK_BUF_CTRL,            /* f32 [N, nu]  motor targets applied */
-  ODUCK_BUF_OBS_STATE,       /* f32 [N, 101] */
-  ODUCK_BUF_OBS_PRIV,        /* f32 [N, 212] */
+  ODUCK_BUF_OBS_STATE,       /* f32 [N, 101]  (Standing: [N, 85], rows 101 apart) */
+  ODUCK_BUF_OBS_PRIV,        /* f32 [N, 212]  (Standing: [N, 153], rows 212 apart) */
   ODUCK_BUF_REWARD,          /* f32 [N]      */
   ODUCK_BUF_DONE,            /* f32 [N]      */
   ODUCK_BUF_TRUNCATION,      /* f32 [N]      */
-  ODUCK_BUF_METRICS,         /* f32 [N, 8]: reward/tracking_lin_vel, reward/tracking_ang_vel, cost/torques, cost/action_rate, cost/stand_still, reward/alive, reward/imitation, swing_peak */
+  ODUCK_BUF_METRICS,         /* f32 [N, 8]: reward/tracking_lin_vel, reward/tracking_ang_vel, cost/torques, cost/action_rate, cost/stand_still, reward/alive, reward/imitation, swing_peak
+                              *   Standing: cost/orientation, cost/torques, cost/action_rate, cost/stand_still, reward/alive, cost/head_pos, swing_peak, (unused) */
   ODUCK_BUF_EFC_FORCE,       /* f32 [N, nefc] rows: friction dofs, joint limits, contacts x4 */
   ODUCK_BUF_CONTACT_DIST,    /* f32 [N, 12]  */
   ODUCK_BUF_SENSORDATA,      /* f32 [N, 24]: gyro3 local_linvel3 accelerometer3 upvector3 global_angvel3 left_foot_linvel3 right_foot_linvel3 pad3 */

@@ -14,7 +14,7 @@ import numpy as np
 
 from .mjcf import CompiledModel
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_BODY, MAX_JNT, MAX_NQ, MAX_NV, MAX_NU, MAX_SITE, MAX_VERT, MAX_FACE, NFEET, NCMD = 20, 28, 36, 32, 16, 8, 32, 64, 2, 7
 OBS_STATE, OBS_PRIV, NMETRIC, REF_DIM, POLY_DEG, MAX_CON = 101, 212, 8, 40, 16, 12
 
@@ -53,14 +53,15 @@ class OduckModel(C.Structure):
 
 class OduckEnvConfig(C.Structure):
     _fields_ = [
-        ("n_substeps", i32), ("episode_length", i32), ("use_imitation_reward", i32), ("use_motor_speed_limits", i32),
+        ("task", i32), ("n_substeps", i32), ("episode_length", i32), ("use_imitation_reward", i32), ("use_motor_speed_limits", i32),
         ("push_enable", i32), ("action_min_delay", i32), ("action_max_delay", i32), ("imu_min_delay", i32),
         ("imu_max_delay", i32), ("auto_reset", i32),
         ("ctrl_dt", d), ("action_scale", d), ("dof_vel_scale", d), ("max_motor_velocity", d), ("noise_level", d),
         ("noise_gyro", d), ("noise_accelerometer", d), ("noise_gravity", d), ("noise_joint_vel", d),
         ("qpos_noise_scale", d * MAX_NU),
         ("scale_tracking_lin_vel", d), ("scale_tracking_ang_vel", d), ("scale_torques", d), ("scale_action_rate", d),
-        ("scale_stand_still", d), ("scale_alive", d), ("scale_imitation", d), ("tracking_sigma", d),
+        ("scale_stand_still", d), ("scale_alive", d), ("scale_imitation", d),
+        ("scale_orientation", d), ("scale_head_pos", d), ("reset_base_qvel_noise", d), ("tracking_sigma", d),
         ("push_interval_range", d * 2), ("push_magnitude_range", d * 2), ("cmd_range", d * 2 * NCMD),
         ("ndx", i32), ("ndy", i32), ("ndth", i32), ("nb_steps_in_period", i32),
         ("dxs", d * 8), ("dys", d * 8), ("dthetas", d * 16),
@@ -112,6 +113,9 @@ BUF = {name: k for k, name in enumerate([
 DTYPE_NP = {0: np.float32, 1: np.int32, 2: np.uint32, 3: np.float64}
 METRIC_NAMES = ["reward/tracking_lin_vel", "reward/tracking_ang_vel", "cost/torques", "cost/action_rate",
                 "cost/stand_still", "reward/alive", "reward/imitation", "swing_peak"]
+METRIC_NAMES_STANDING = ["cost/orientation", "cost/torques", "cost/action_rate", "cost/stand_still", "reward/alive", "cost/head_pos", "swing_peak"]
+TASK_JOYSTICK, TASK_STANDING = 0, 1
+OBS_DIMS = {TASK_JOYSTICK: (OBS_STATE, OBS_PRIV), TASK_STANDING: (85, 153)}
 
 
 def model_to_struct(m: CompiledModel) -> OduckModel:

@@ -92,6 +92,39 @@ def default_config() -> ConfigDict:
     )
 
 
+def standing_default_config() -> ConfigDict:
+    """``default_config()`` of the reference Standing task (open_duck_mini_v2/standing.py:44-102)."""
+    return _cd(
+        ctrl_dt=0.02,
+        sim_dt=0.002,
+        episode_length=1000,
+        action_repeat=1,
+        action_scale=0.25,
+        dof_vel_scale=0.05,
+        history_len=0,
+        soft_joint_pos_limit_factor=0.95,
+        noise_config=_cd(
+            level=1.0,
+            action_min_delay=0,
+            action_max_delay=3,
+            imu_min_delay=0,
+            imu_max_delay=3,
+            scales=_cd(hip_pos=0.03, knee_pos=0.05, ankle_pos=0.08, joint_vel=2.5, gravity=0.1, linvel=0.1, gyro=0.05,
+                       accelerometer=0.005),
+        ),
+        reward_config=_cd(
+            scales=_cd(orientation=-0.5, torques=-1.0e-3, action_rate=-0.375, stand_still=-0.3, alive=20.0, head_pos=-2.0),
+            tracking_sigma=0.01,
+        ),
+        push_config=_cd(enable=True, interval_range=[5.0, 10.0], magnitude_range=[0.1, 1.0]),
+        neck_pitch_range=[-0.34, 1.1],
+        head_pitch_range=[-0.78, 0.78],
+        head_yaw_range=[-2.7, 2.7],
+        head_roll_range=[-0.5, 0.5],
+        head_range_factor=1.0,
+    )
+
+
 def qpos_noise_scale(config: ConfigDict, nu: int) -> np.ndarray:
     """joystick.py:184-200: indices come from the 10-entry JOINTS_ORDER_NO_HEAD but index a 14-long
     per-actuator array, so the scales land on actuator slots 0..9."""
@@ -109,9 +142,14 @@ def qpos_noise_scale(config: ConfigDict, nu: int) -> np.ndarray:
 
 def build_env_config(model: CompiledModel, config: ConfigDict, poly: Optional[PolyTable], auto_reset: bool = True,
                      use_imitation_reward: bool = USE_IMITATION_REWARD,
-                     use_motor_speed_limits: bool = USE_MOTOR_SPEED_LIMITS):
-    """Pack ``config`` into the C struct.  Returns (struct, keepalive) -- keepalive owns the coefficient array."""
+                     use_motor_speed_limits: bool = USE_MOTOR_SPEED_LIMITS, task: int = capi.TASK_JOYSTICK):
+    """Pack ``config`` into the C struct.  Returns (struct, keepalive) -- keepalive owns the coefficient array.
+    ``task``: capi.TASK_JOYSTICK (joystick.py) or capi.TASK_STANDING (standing.py: no imitation reward, no motor speed limits)."""
     c = capi.OduckEnvConfig()
+    c.task = int(task)
+    standing = task == capi.TASK_STANDING
+    if standing:
+        use_imitation_reward, use_motor_speed_limits = False, False
     n_sub = int(round(config.ctrl_dt / config.sim_dt))
     c.n_substeps = n_sub
     c.episode_length = int(config.episode_length)
@@ -125,7 +163,8 @@ def build_env_config(model: CompiledModel, config: ConfigDict, poly: Optional[Po
     c.ctrl_dt = float(config.ctrl_dt)
     c.action_scale = float(config.action_scale)
     c.dof_vel_scale = float(config.dof_vel_scale)
-    c.max_motor_velocity = float(config.max_motor_velocity)
+    c.max_motor_velocity = float(config.get("max_motor_velocity", 0.0))
+    c.reset_base_qvel_noise = 0.5 if standing else 0.05          # standing.py:247 / joystick.py:253
     c.noise_level = float(nc.level)
     c.noise_gyro, c.noise_accelerometer = float(nc.scales.gyro), float(nc.scales.accelerometer)
     c.noise_gravity, c.noise_joint_vel = float(nc.scales.gravity), float(nc.scales.joint_vel)
@@ -133,15 +172,18 @@ def build_env_config(model: CompiledModel, config: ConfigDict, poly: Optional[Po
     for i in range(model.nu):
         c.qpos_noise_scale[i] = qn[i]
     rs = config.reward_config.scales
-    c.scale_tracking_lin_vel, c.scale_tracking_ang_vel = float(rs.tracking_lin_vel), float(rs.tracking_ang_vel)
-    c.scale_torques, c.scale_action_rate = float(rs.torques), float(rs.action_rate)
-    c.scale_stand_still, c.scale_alive, c.scale_imitation = float(rs.stand_still), float(rs.alive), float(rs.imitation)
+    g = lambda k: float(rs.get(k, 0.0))
+    c.scale_tracking_lin_vel, c.scale_tracking_ang_vel = g("tracking_lin_vel"), g("tracking_ang_vel")
+    c.scale_torques, c.scale_action_rate = g("torques"), g("action_rate")
+    c.scale_stand_still, c.scale_alive, c.scale_imitation = g("stand_still"), g("alive"), g("imitation")
+    c.scale_orientation, c.scale_head_pos = g("orientation"), g("head_pos")
     c.tracking_sigma = float(config.reward_config.tracking_sigma)
     for i in range(2):
         c.push_interval_range[i] = float(config.push_config.interval_range[i])
         c.push_magnitude_range[i] = float(config.push_config.magnitude_range[i])
     f = float(config.head_range_factor)
-    ranges = [config.lin_vel_x, config.lin_vel_y, config.ang_vel_yaw,
+    zero = [0.0, 0.0]
+    ranges = [config.get("lin_vel_x", zero), config.get("lin_vel_y", zero), config.get("ang_vel_yaw", zero),
               [config.neck_pitch_range[0] * f, config.neck_pitch_range[1] * f],
               [config.head_pitch_range[0] * f, config.head_pitch_range[1] * f],
               [config.head_yaw_range[0] * f, config.head_yaw_range[1] * f],

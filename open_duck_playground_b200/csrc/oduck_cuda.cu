@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(WPB * 32, CTAS_PER_SM) k_reset(Params p) {
       s.qpos[3] = qn.w; s.qpos[4] = qn.x; s.qpos[5] = qn.y; s.qpos[6] = qn.z;
     }
     if (lane >= 10 && lane < 10 + m.nu) { const int qa = m.act_qadr[lane - 10]; s.qpos[qa] = m.key_qpos[qa] * bits_uniform(bits, 0.5f, 1.5f); }
-    const float bq = bits_uniform(bits, -0.05f, 0.05f);
+    const float bq = bits_uniform(bits, -c.reset_qvel_noise, c.reset_qvel_noise);
     L.qvel = 0.f;
     {
       const float v = __shfl_sync(FULLMASK, bq, 4 + (lane < 6 ? lane : 0));
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(WPB * 32, CTAS_PER_SM) k_reset(Params p) {
     er.cmd = sample_command(c, ks[4], lane);
     if (lane >= 7) er.cmd = 0.f;
     er.last_act[0] = er.last_act[1] = er.last_act[2] = 0.f;
-    er.targets = lane < m.nu ? m.key_ctrl[lane] : 0.f;
+    er.targets = (lane < m.nu && c.task != ODUCK_TASK_STANDING) ? m.key_ctrl[lane] : 0.f;   // standing.py:279 starts them at zero
 #pragma unroll
     for (int k = 0; k < MAX_DELAY; ++k) er.hist[k] = 0.f;
     er.air = er.lastc = er.swing = 0.f;
@@ -357,9 +357,26 @@ __global__ void __launch_bounds__(WPB * 32, CTAS_PER_SM) k_step(Params p) {
       rew *= cmd_norm > 0.01f ? 1.f : 0.f;
       r_imit = nan_to_num(rew);
     }
-    const float sc0 = r_lin * c.sc_lin, sc1 = r_ang * c.sc_ang, sc2 = c_torque * c.sc_torques, sc3 = c_rate * c.sc_rate;
-    const float sc4 = c_still * c.sc_still, sc5 = 1.f * c.sc_alive, sc6 = r_imit * c.sc_imit;
-    const float total = sc0 + sc1 + sc2 + sc3 + sc5 + sc6 + sc4;       // dict order of joystick.py:634-667
+    float scs[7], sg[7], total;
+    if (c.task == ODUCK_TASK_STANDING) {
+      // standing.py:573-606: orientation, torques, action_rate, alive, stand_still (legs only), head_pos
+      const float c_or = nan_to_num(sd[9] * sd[9] + sd[10] * sd[10]);
+      const bool legl = lane < 5 || (lane >= 9 && lane < nu);
+      const float c_still_legs = nan_to_num(wsum(legl ? fabsf(q - dflt) + fabsf(qd) : 0.f)) * (cmd_norm < 0.01f ? 1.f : 0.f);
+      const float hc = __shfl_sync(FULLMASK, er.cmd, (lane >= 5 && lane < 9) ? lane - 2 : 0);       // head joint u <- command[3 + u - 5]
+      const float c_head = nan_to_num(wsum((lane >= 5 && lane < 9) ? (q - hc) * (q - hc) : 0.f)) * (cmd_norm > 0.01f ? 1.f : 0.f);
+      const float s_or = c_or * c.sc_orient, s_tq = c_torque * c.sc_torques, s_ar = c_rate * c.sc_rate, s_al = 1.f * c.sc_alive;
+      const float s_ss = c_still_legs * c.sc_still, s_hp = c_head * c.sc_head;
+      total = s_or + s_tq + s_ar + s_al + s_ss + s_hp;               // dict order of standing.py:585-604
+      scs[0] = s_or; scs[1] = s_tq; scs[2] = s_ar; scs[3] = s_ss; scs[4] = s_al; scs[5] = s_hp; scs[6] = 0.f;
+      sg[0] = c.sc_orient; sg[1] = c.sc_torques; sg[2] = c.sc_rate; sg[3] = c.sc_still; sg[4] = c.sc_alive; sg[5] = c.sc_head; sg[6] = 0.f;
+    } else {
+      const float sc0 = r_lin * c.sc_lin, sc1 = r_ang * c.sc_ang, sc2 = c_torque * c.sc_torques, sc3 = c_rate * c.sc_rate;
+      const float sc4 = c_still * c.sc_still, sc5 = 1.f * c.sc_alive, sc6 = r_imit * c.sc_imit;
+      total = sc0 + sc1 + sc2 + sc3 + sc5 + sc6 + sc4;               // dict order of joystick.py:634-667
+      scs[0] = sc0; scs[1] = sc1; scs[2] = sc2; scs[3] = sc3; scs[4] = sc4; scs[5] = sc5; scs[6] = sc6;
+      sg[0] = c.sc_lin; sg[1] = c.sc_ang; sg[2] = c.sc_torques; sg[3] = c.sc_rate; sg[4] = c.sc_still; sg[5] = c.sc_alive; sg[6] = c.sc_imit;
+    }
     const float reward = fminf(fmaxf(total * dt, 0.f), 10000.f);
     // info updates (joystick.py:449-469)
     er.step += 1;
@@ -373,12 +390,10 @@ __global__ void __launch_bounds__(WPB * 32, CTAS_PER_SM) k_step(Params p) {
     // metrics (joystick.py:470-477): scaled term, sign flipped for costs
     {
       float mv = 0.f;
-      const float scs[7] = {sc0, sc1, sc2, sc3, sc4, sc5, sc6};
-      const float sg[7] = {c.sc_lin, c.sc_ang, c.sc_torques, c.sc_rate, c.sc_still, c.sc_alive, c.sc_imit};
 #pragma unroll
       for (int k = 0; k < 7; ++k) if (lane == k) mv = sg[k] == 0.f ? 0.f : (sg[k] > 0.f ? scs[k] : -scs[k]);
       const float sw = 0.5f * (__shfl_sync(FULLMASK, er.swing, 0) + __shfl_sync(FULLMASK, er.swing, 1));
-      if (lane == 7) mv = sw;
+      if (lane == (c.task == ODUCK_TASK_STANDING ? 6 : 7)) mv = sw;       // swing_peak follows the last reward term
       if (lane < ODUCK_NMETRIC) p.metrics[(size_t)env * ODUCK_NMETRIC + lane] = mv;
     }
     // EpisodeWrapper (action_repeat = 1) + AutoReset
@@ -657,6 +672,7 @@ static int build_dev_model(const OduckModel& M, DevModel& D, std::string& err) {
 
 static void build_dev_cfg(const OduckEnvConfig& C, DevEnvCfg& D) {
   memset(&D, 0, sizeof(D));
+  D.task = C.task; D.sc_orient = (float)C.scale_orientation; D.sc_head = (float)C.scale_head_pos; D.reset_qvel_noise = (float)C.reset_base_qvel_noise;
   D.n_substeps = C.n_substeps; D.episode_length = C.episode_length; D.use_imitation = C.use_imitation_reward; D.use_speed_limits = C.use_motor_speed_limits;
   D.push_enable = C.push_enable; D.act_min_delay = C.action_min_delay; D.act_max_delay = C.action_max_delay; D.imu_min_delay = C.imu_min_delay; D.imu_max_delay = C.imu_max_delay;
   D.auto_reset = C.auto_reset;
@@ -716,6 +732,7 @@ int oduck_destroy(OduckHandle* h) {
 int oduck_create(const OduckModel* model, const OduckEnvConfig* cfg, int num_envs, int device, OduckHandle** out) {
   if (!model || !cfg || !out || num_envs <= 0) return fail(ODUCK_ERR_ARG, "oduck_create: bad argument");
   if (model->abi_version != ODUCK_ABI_VERSION) return fail(ODUCK_ERR_MODEL, "oduck_create: model ABI version mismatch");
+  if (cfg->task != ODUCK_TASK_JOYSTICK && cfg->task != ODUCK_TASK_STANDING) return fail(ODUCK_ERR_ARG, "oduck_create: unknown task");
   if (model->floor_is_hfield) return fail(ODUCK_ERR_UNSUPPORTED, "oduck_create: height-field floor not implemented yet");
   if (cfg->action_max_delay > MAX_DELAY || cfg->imu_max_delay * 3 > 16 || cfg->action_max_delay < 1) return fail(ODUCK_ERR_ARG, "oduck_create: delay history out of range");
   int ndev = 0;
@@ -867,8 +884,8 @@ int oduck_get_buffer(OduckHandle* h, int id, void** ptr, int64_t* shape, int64_t
     case ODUCK_BUF_CONTACT_DIST: REC(h->out, OUT_STRIDE, OUT_CDIST, 12) break;
     case ODUCK_BUF_ACTUATOR_FORCE: REC(h->out, OUT_STRIDE, OUT_AFRC, m.nu) break;
     case ODUCK_BUF_SITE_XPOS_FEET: REC(h->out, OUT_STRIDE, OUT_FEET, 6) break;
-    case ODUCK_BUF_OBS_STATE: REC(h->obs_state, ODUCK_OBS_STATE, 0, ODUCK_OBS_STATE) break;
-    case ODUCK_BUF_OBS_PRIV: REC(h->obs_priv, ODUCK_OBS_PRIV, 0, ODUCK_OBS_PRIV) break;
+    case ODUCK_BUF_OBS_STATE: REC(h->obs_state, ODUCK_OBS_STATE, 0, h->hcfg.task == ODUCK_TASK_STANDING ? 85 : ODUCK_OBS_STATE) break;
+    case ODUCK_BUF_OBS_PRIV: REC(h->obs_priv, ODUCK_OBS_PRIV, 0, h->hcfg.task == ODUCK_TASK_STANDING ? 153 : ODUCK_OBS_PRIV) break;
     case ODUCK_BUF_REWARD: REC(h->reward, 1, 0, 0) break;
     case ODUCK_BUF_DONE: REC(h->done, 1, 0, 0) break;
     case ODUCK_BUF_TRUNCATION: REC(h->trunc, 1, 0, 0) break;
@@ -893,8 +910,8 @@ int oduck_get_buffer(OduckHandle* h, int id, void** ptr, int64_t* shape, int64_t
     case ODUCK_BUF_DR_PARAMS: REC(h->dr, DR_STRIDE, 0, DR_STRIDE) break;
     case ODUCK_BUF_FIRST_QPOS: REC(h->first_phys, PHYS_STRIDE, 0, m.nq) break;
     case ODUCK_BUF_FIRST_QVEL: REC(h->first_phys, PHYS_STRIDE, PHYS_QVEL, m.nv) break;
-    case ODUCK_BUF_FIRST_OBS_STATE: REC(h->first_obs_state, ODUCK_OBS_STATE, 0, ODUCK_OBS_STATE) break;
-    case ODUCK_BUF_FIRST_OBS_PRIV: REC(h->first_obs_priv, ODUCK_OBS_PRIV, 0, ODUCK_OBS_PRIV) break;
+    case ODUCK_BUF_FIRST_OBS_STATE: REC(h->first_obs_state, ODUCK_OBS_STATE, 0, h->hcfg.task == ODUCK_TASK_STANDING ? 85 : ODUCK_OBS_STATE) break;
+    case ODUCK_BUF_FIRST_OBS_PRIV: REC(h->first_obs_priv, ODUCK_OBS_PRIV, 0, h->hcfg.task == ODUCK_TASK_STANDING ? 153 : ODUCK_OBS_PRIV) break;
     default: return fail(ODUCK_ERR_ARG, "oduck_get_buffer: unknown buffer id");
   }
 #undef REC

@@ -27,6 +27,8 @@
 #define MAX_DELAY 4
 
 struct DevEnvCfg {
+  int task;                  // ODUCK_TASK_JOYSTICK / ODUCK_TASK_STANDING
+  float sc_orient, sc_head, reset_qvel_noise;
   int n_substeps, episode_length, use_imitation, use_speed_limits, push_enable, act_min_delay, act_max_delay, imu_min_delay, imu_max_delay, auto_reset;
   float ctrl_dt, action_scale, dof_vel_scale, max_motor_velocity, noise_level, noise_gyro, noise_acc, noise_gravity, noise_joint_vel;
   float qpos_noise_scale[16];
@@ -78,6 +80,7 @@ __device__ __forceinline__ float sample_command(const DevEnvCfg& c, RKey rng, in
   const uint32_t mybits = __shfl_sync(FULLMASK, bits, which & 7);
   const int ci = lane < 7 ? lane : 6;
   float v = bits_uniform(mybits, c.cmd_range[ci][0], c.cmd_range[ci][1]);
+  if (c.task == 1 && lane < 3) v = 0.f;                          // standing.py:648-655: no velocity command (same key usage)
   return (u4 < 0.1f) ? 0.f : v;
 }
 
@@ -177,6 +180,7 @@ __device__ __forceinline__ void write_obs(const DevModel& m, const DevEnvCfg& c,
   }
   const float dflt = lane < m.nu ? m.key_ctrl[lane] : 0.f;
   const int nu = m.nu;
+  const bool standing = c.task == 1;   // standing.py:526-566: no motor_targets / imitation_phase, empty reference motion
   if (lane < 6) { ost[lane] = noisy9; opr[lane] = noisy9; }
   if (lane < 7) { ost[6 + lane] = er.cmd; opr[6 + lane] = er.cmd; }
   if (lane < nu) {
@@ -187,15 +191,15 @@ __device__ __forceinline__ void write_obs(const DevModel& m, const DevEnvCfg& c,
     ost[p + lane] = v; opr[p + lane] = v; p += nu;
 #pragma unroll
     for (int k = 0; k < 3; ++k) { ost[p + lane] = er.last_act[k]; opr[p + lane] = er.last_act[k]; p += nu; }
-    ost[p + lane] = er.targets; opr[p + lane] = er.targets;
+    if (!standing) { ost[p + lane] = er.targets; opr[p + lane] = er.targets; }
   }
-  const int p2 = 13 + 6 * nu;
+  const int p2 = 13 + (standing ? 5 : 6) * nu;
   if (lane < 2) {
     ost[p2 + lane] = contact; opr[p2 + lane] = contact;
-    ost[p2 + 2 + lane] = er.phase; opr[p2 + 2 + lane] = er.phase;
+    if (!standing) { ost[p2 + 2 + lane] = er.phase; opr[p2 + 2 + lane] = er.phase; }
   }
   // privileged tail
-  int r = p2 + 4;
+  int r = p2 + (standing ? 2 : 4);
   if (lane < 3) {
     opr[r + lane] = sd[lane];                         // gyro
     opr[r + 3 + lane] = sd[6 + lane];                 // accelerometer
@@ -216,6 +220,7 @@ __device__ __forceinline__ void write_obs(const DevModel& m, const DevEnvCfg& c,
   r += 6;
   if (lane < 2) opr[r + lane] = er.air;
   r += 2;
+  if (standing) return;
   opr[r + lane] = er.ref_lo;
   if (lane < 8) opr[r + 32 + lane] = er.ref_hi;
   r += 40;

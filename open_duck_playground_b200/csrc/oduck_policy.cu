@@ -268,7 +268,7 @@ extern "C" int oduck_policy_forward(OduckHandle* h, const OduckPolicyWeights* w,
     }
     h->policy_packed_for = w->w[0];
   }
-  if (e == cudaSuccess) { k_pack_obs<<<128, 256, 0, st>>>(obs_in, w->obs_dim, w->obs_mean, w->obs_std, abuf + aoff[0], h->n, dims[0]); e = cudaGetLastError(); }
+  if (e == cudaSuccess) { k_pack_obs<<<128, 256, 0, st>>>(obs_in, obs ? w->obs_dim : ODUCK_OBS_STATE /* the handle's records are ODUCK_OBS_STATE apart */, w->obs_mean, w->obs_std, abuf + aoff[0], h->n, dims[0]); e = cudaGetLastError(); }
   DenseParams d;
   memset(&d, 0, sizeof(d));
   d.M = h->n;

@@ -87,11 +87,15 @@ _INFO_BUFFERS = {
 class Joystick:
     """Track a joystick command (batched; reference class: joystick.py:105)."""
 
+    TASK = capi.TASK_JOYSTICK                      # which env class of the reference the library steps (ODUCK_TASK_*)
+    METRICS = capi.METRIC_NAMES
+    DEFAULT_CONFIG = staticmethod(default_config)
+
     def __init__(self, task: str = "flat_terrain", config: Optional[ConfigDict] = None,
                  config_overrides: Optional[Dict[str, Union[str, int, list]]] = None, *, num_envs: Optional[int] = None,
                  device: Union[str, int, torch.device] = "cuda:0", xml_path: Optional[str] = None,
                  library: Optional[capi.Library] = None, auto_reset: bool = True):
-        self._config = copy.deepcopy(config) if config is not None else default_config()
+        self._config = copy.deepcopy(config) if config is not None else self.DEFAULT_CONFIG()
         if config_overrides:
             self._config.update_from_flattened_dict(config_overrides)
         self._task = task
@@ -102,7 +106,8 @@ class Joystick:
             self._xml_path = constants.task_to_xml(task)          # KeyError on unknown task, like the reference
             self._mj_model = CompiledModel.load(constants.task_to_blob(task))
             self._mj_model.arrays["timestep"] = np.array(float(self._config.sim_dt))   # base.py:56
-        self.PRM = PolyTable.load(constants.POLY_BLOB) if config_mod.USE_IMITATION_REWARD else None
+        self._use_imitation = config_mod.USE_IMITATION_REWARD and self.TASK == capi.TASK_JOYSTICK       # standing.py:42: False
+        self.PRM = PolyTable.load(constants.POLY_BLOB) if self._use_imitation else None
         self._lib = library if library is not None else capi.load_cuda_library()
         self._device = torch.device(device) if self._lib.is_device else torch.device("cpu")
         self._auto_reset = auto_reset
@@ -144,7 +149,8 @@ class Joystick:
 
     @property
     def observation_size(self) -> Dict[str, tuple]:
-        return {"state": (capi.OBS_STATE,), "privileged_state": (capi.OBS_PRIV,)}
+        ds, dp = capi.OBS_DIMS[self.TASK]
+        return {"state": (ds,), "privileged_state": (dp,)}
 
     @property
     def unwrapped(self) -> "Joystick":
@@ -168,8 +174,8 @@ class Joystick:
     def _create(self, n: int) -> None:
         ms = capi.model_to_struct(self._mj_model)
         cs, self._keep = config_mod.build_env_config(self._mj_model, self._config, self.PRM, auto_reset=self._auto_reset,
-                                                     use_imitation_reward=config_mod.USE_IMITATION_REWARD,
-                                                     use_motor_speed_limits=config_mod.USE_MOTOR_SPEED_LIMITS)
+                                                     use_imitation_reward=self._use_imitation,
+                                                     use_motor_speed_limits=config_mod.USE_MOTOR_SPEED_LIMITS, task=self.TASK)
         dev = self._device.index or 0 if self._lib.is_device else 0
         self._handle = self._lib.create(ms, cs, n, dev)
         self._views = {}
@@ -253,7 +259,7 @@ class Joystick:
     def _state(self) -> State:
         b = self.buffer
         met = b("METRICS")
-        metrics = {name: met[:, i] for i, name in enumerate(capi.METRIC_NAMES)}
+        metrics = {name: met[:, i] for i, name in enumerate(self.METRICS)}
         info = {k: b(v) for k, v in _INFO_BUFFERS.items()}
         la = b("INFO_LAST_ACT")
         info.update(last_act=la[:, 0], last_last_act=la[:, 1], last_last_last_act=la[:, 2],

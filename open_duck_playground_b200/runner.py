@@ -12,7 +12,7 @@ from pathlib import Path
 import torch
 import torch.distributed as dist
 
-from . import joystick, randomize
+from . import joystick, randomize, standing
 from .ppo import PPOConfig, PPOTrainer
 
 
@@ -63,7 +63,7 @@ class BaseRunner:
 class OpenDuckMiniV2Runner(BaseRunner):
     def __init__(self, args):
         super().__init__(args)
-        available_envs = {"joystick": (joystick, joystick.Joystick)}   # "standing" is out of scope for this tier
+        available_envs = {"joystick": (joystick, joystick.Joystick), "standing": (standing, standing.Standing)}   # open_duck_mini_v2/runner.py:14-17
         if args.env not in available_envs:
             raise ValueError(f"Unknown env {args.env}")
         self.env_file = available_envs[args.env]

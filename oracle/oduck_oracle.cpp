@@ -1046,6 +1046,7 @@ static void sample_command(const OduckHandle& h, Key rng, real* cmd) {  // joyst
   for (int i = 0; i < 8; i++) k[i] = key_split(rng, i);
   const int which[7] = {0, 1, 2, 4, 5, 6, 7};
   for (int i = 0; i < 7; i++) cmd[i] = key_uniform(k[which[i]], 0, (real)c.cmd_range[i][0], (real)c.cmd_range[i][1]);
+  if (c.task == ODUCK_TASK_STANDING) cmd[0] = cmd[1] = cmd[2] = 0;   // standing.py:648-655: no velocity command, same key usage
   bool zero = key_uniform(k[3], 0, 0, 1) < (real)0.1;
   if (zero) for (int i = 0; i < 7; i++) cmd[i] = 0;
 }
@@ -1107,6 +1108,31 @@ static void compute_rewards(const OduckHandle& h, const real* command, const rea
   }
 }
 
+// The six reward terms of Standing._get_reward (standing.py:573-606), unscaled, in the order of its dict:
+//   [orientation, torques, action_rate, alive, stand_still (ignore_head=True), head_pos]
+// rewards.py:45-46 (cost_orientation), :68-79, :93-117, :124-125, :131-147 (cost_head_pos).  Checked against the NumPy twins
+// (tests/golden/rewards_standing.npz).
+static void compute_rewards_standing(const OduckHandle& h, const real* command, const real* upvector, const real* actuator_force, const real* action,
+                                     const real* last_act, const real* q, const real* qd, real* out) {
+  const OduckModel& m = h.m;
+  out[0] = nan_to_num(upvector[0] * upvector[0] + upvector[1] * upvector[1]);
+  real c_torque = 0, c_rate = 0;
+  for (int u = 0; u < m.nu; u++) { c_torque += actuator_force[u] * actuator_force[u]; real d = action[u] - last_act[u]; c_rate += d * d; }
+  out[1] = nan_to_num(c_torque);
+  out[2] = nan_to_num(c_rate);
+  out[3] = 1;
+  real cmd_norm = std::sqrt(command[0] * command[0] + command[1] * command[1] + command[2] * command[2]);
+  real pose = 0, vel = 0;
+  for (int u = 0; u < m.nu; u++) {
+    if (u >= 5 && u < 9) continue;                     // qpos[:5] and qpos[9:]: the head joints are ignored
+    pose += std::fabs(q[u] - (real)m.key_ctrl[u]); vel += std::fabs(qd[u]);
+  }
+  out[4] = nan_to_num(pose + vel) * (cmd_norm < (real)0.01 ? 1 : 0);
+  real herr = 0;
+  for (int k = 0; k < 4; k++) { real d = q[5 + k] - command[3 + k]; herr += d * d; }
+  out[5] = nan_to_num(herr) * (cmd_norm > (real)0.01 ? 1 : 0);
+}
+
 // joystick.py:487-620.  Advances e.rng exactly as the reference (5 splits).
 static void get_obs(const OduckHandle& h, EnvState& e, const real* contact) {
   const OduckModel& m = h.m;
@@ -1146,10 +1172,11 @@ static void get_obs(const OduckHandle& h, EnvState& e, const real* contact) {
   for (int i = 0; i < 7; i++) o[p++] = e.command[i];
   for (int u = 0; u < m.nu; u++) o[p++] = nja[u] - (real)m.key_ctrl[u];
   for (int u = 0; u < m.nu; u++) o[p++] = njv[u] * (real)c.dof_vel_scale;
+  const bool standing = c.task == ODUCK_TASK_STANDING;     // standing.py:526-542: no motor_targets / phase; the reference motion is empty
   for (int k = 0; k < 3; k++) for (int u = 0; u < m.nu; u++) o[p++] = e.last_act[k][u];
-  for (int u = 0; u < m.nu; u++) o[p++] = e.motor_targets[u];
+  if (!standing) for (int u = 0; u < m.nu; u++) o[p++] = e.motor_targets[u];
   for (int i = 0; i < 2; i++) o[p++] = contact[i];
-  for (int i = 0; i < 2; i++) o[p++] = e.imitation_phase[i];
+  if (!standing) for (int i = 0; i < 2; i++) o[p++] = e.imitation_phase[i];
   real* pr = e.obs_priv;
   int r = 0;
   for (int i = 0; i < p; i++) pr[r++] = o[i];
@@ -1165,9 +1192,13 @@ static void get_obs(const OduckHandle& h, EnvState& e, const real* contact) {
   for (int i = 0; i < 2; i++) pr[r++] = contact[i];
   for (int i = 0; i < 6; i++) pr[r++] = sd[15 + i];  // [left, right] foot linvel (joystick.py:173-181)
   for (int i = 0; i < 2; i++) pr[r++] = e.feet_air_time[i];
-  for (int i = 0; i < ODUCK_REF_DIM; i++) pr[r++] = e.ref_motion[i];
-  pr[r++] = (real)e.imitation_i;
-  for (int i = 0; i < 2; i++) pr[r++] = e.imitation_phase[i];
+  if (!standing) {
+    for (int i = 0; i < ODUCK_REF_DIM; i++) pr[r++] = e.ref_motion[i];
+    pr[r++] = (real)e.imitation_i;
+    for (int i = 0; i < 2; i++) pr[r++] = e.imitation_phase[i];
+  }
+  for (int i = p; i < ODUCK_OBS_STATE; i++) o[i] = 0;
+  for (int i = r; i < ODUCK_OBS_PRIV; i++) pr[i] = 0;
 }
 
 static void geoms_colliding(const EnvState& e, real* contact) {
@@ -1195,7 +1226,7 @@ static void env_reset(OduckHandle& h, EnvState& e, Key rng) {  // joystick.py:20
   key = key_split(rng, 1); rng = key_split(rng, 0);
   for (int u = 0; u < m.nu; u++) { int qa = m.jnt_qposadr[m.act_jntid[u]]; e.qpos[qa] = e.qpos[qa] * key_uniform(key, u, (real)0.5, (real)1.5); }
   key = key_split(rng, 1); rng = key_split(rng, 0);
-  for (int i = 0; i < 6; i++) e.qvel[i] = key_uniform(key, i, (real)-0.05, (real)0.05);
+  for (int i = 0; i < 6; i++) e.qvel[i] = key_uniform(key, i, -(real)c.reset_base_qvel_noise, (real)c.reset_base_qvel_noise);
   for (int u = 0; u < m.nu; u++) e.ctrl[u] = e.qpos[m.jnt_qposadr[m.act_jntid[u]]];
   forward(h, e, s);  // mjx_env.init
   Key cmd_rng = key_split(rng, 1); rng = key_split(rng, 0);
@@ -1208,7 +1239,7 @@ static void env_reset(OduckHandle& h, EnvState& e, Key rng) {  // joystick.py:20
   e.rng = rng;
   e.step = 0; e.steps = 0; e.push_step = 0; e.imitation_i = 0;
   for (int k = 0; k < 3; k++) for (int u = 0; u < NU; u++) e.last_act[k][u] = 0;
-  for (int u = 0; u < m.nu; u++) e.motor_targets[u] = (real)m.key_ctrl[u];
+  for (int u = 0; u < m.nu; u++) e.motor_targets[u] = c.task == ODUCK_TASK_STANDING ? (real)0 : (real)m.key_ctrl[u];   // standing.py:279
   for (int i = 0; i < 2; i++) { e.feet_air_time[i] = 0; e.last_contact[i] = 0; e.swing_peak[i] = 0; e.push[i] = 0; e.imitation_phase[i] = 0; }
   for (int i = 0; i < 8 * NU; i++) e.action_history[i] = 0;
   for (int i = 0; i < 24; i++) e.imu_history[i] = 0;
@@ -1283,13 +1314,27 @@ static void env_step(OduckHandle& h, EnvState& e, const float* action_f) {  // j
   // rewards (common/rewards.py, custom_rewards.py)
   real q[NU], qd[NU];
   actuated(m, e.qpos, e.qvel, q, qd);
-  real terms[7];
-  compute_rewards(h, e.command, e.sensordata + 3, e.sensordata, e.actuator_force, action, e.last_act[0], e.qvel, q, qd, contact, e.ref_motion, terms);
-  const real r_lin = terms[0], r_ang = terms[1], c_torque = terms[2], c_rate = terms[3], c_still = terms[4], r_alive = terms[5], r_imit = terms[6];
-  real sc[7] = {r_lin * (real)c.scale_tracking_lin_vel, r_ang * (real)c.scale_tracking_ang_vel, c_torque * (real)c.scale_torques,
-                c_rate * (real)c.scale_action_rate, c_still * (real)c.scale_stand_still, r_alive * (real)c.scale_alive, r_imit * (real)c.scale_imitation};
-  // sum order of the rewards dict (joystick.py:634-667): lin, ang, torques, action_rate, alive, imitation, stand_still
-  real total = sc[0] + sc[1] + sc[2] + sc[3] + sc[5] + sc[6] + sc[4];
+  real sc[7] = {0, 0, 0, 0, 0, 0, 0}, total;
+  double scales[7] = {0, 0, 0, 0, 0, 0, 0};   // metric slots: config order of reward_config.scales
+  if (c.task == ODUCK_TASK_STANDING) {
+    real t6[6];
+    compute_rewards_standing(h, e.command, e.sensordata + 9, e.actuator_force, action, e.last_act[0], q, qd, t6);
+    const real s_or = t6[0] * (real)c.scale_orientation, s_tq = t6[1] * (real)c.scale_torques, s_ar = t6[2] * (real)c.scale_action_rate;
+    const real s_al = t6[3] * (real)c.scale_alive, s_ss = t6[4] * (real)c.scale_stand_still, s_hp = t6[5] * (real)c.scale_head_pos;
+    total = s_or + s_tq + s_ar + s_al + s_ss + s_hp;          // sum order of the rewards dict (standing.py:585-604)
+    sc[0] = s_or; sc[1] = s_tq; sc[2] = s_ar; sc[3] = s_ss; sc[4] = s_al; sc[5] = s_hp;
+    scales[0] = c.scale_orientation; scales[1] = c.scale_torques; scales[2] = c.scale_action_rate; scales[3] = c.scale_stand_still; scales[4] = c.scale_alive; scales[5] = c.scale_head_pos;
+  } else {
+    real terms[7];
+    compute_rewards(h, e.command, e.sensordata + 3, e.sensordata, e.actuator_force, action, e.last_act[0], e.qvel, q, qd, contact, e.ref_motion, terms);
+    const real r_lin = terms[0], r_ang = terms[1], c_torque = terms[2], c_rate = terms[3], c_still = terms[4], r_alive = terms[5], r_imit = terms[6];
+    sc[0] = r_lin * (real)c.scale_tracking_lin_vel; sc[1] = r_ang * (real)c.scale_tracking_ang_vel; sc[2] = c_torque * (real)c.scale_torques;
+    sc[3] = c_rate * (real)c.scale_action_rate; sc[4] = c_still * (real)c.scale_stand_still; sc[5] = r_alive * (real)c.scale_alive; sc[6] = r_imit * (real)c.scale_imitation;
+    // sum order of the rewards dict (joystick.py:634-667): lin, ang, torques, action_rate, alive, imitation, stand_still
+    total = sc[0] + sc[1] + sc[2] + sc[3] + sc[5] + sc[6] + sc[4];
+    scales[0] = c.scale_tracking_lin_vel; scales[1] = c.scale_tracking_ang_vel; scales[2] = c.scale_torques; scales[3] = c.scale_action_rate;
+    scales[4] = c.scale_stand_still; scales[5] = c.scale_alive; scales[6] = c.scale_imitation;
+  }
   real reward = std::min(std::max(total * dt, (real)0), (real)10000);
   for (int i = 0; i < 2; i++) e.push[i] = push[i];
   e.step += 1;
@@ -1305,10 +1350,10 @@ static void env_step(OduckHandle& h, EnvState& e, const float* action_f) {  // j
     e.last_contact[i] = contact[i];
     e.swing_peak[i] *= nc;
   }
-  // metrics: reward/<k> = v, cost/<k> = -v for negative scales (joystick.py:470-477)
-  const double scales[7] = {c.scale_tracking_lin_vel, c.scale_tracking_ang_vel, c.scale_torques, c.scale_action_rate, c.scale_stand_still, c.scale_alive, c.scale_imitation};
+  // metrics: reward/<k> = v, cost/<k> = -v for negative scales (joystick.py:470-477); swing_peak follows the last term
   for (int k = 0; k < 7; k++) e.metrics[k] = scales[k] == 0 ? 0 : (scales[k] > 0 ? sc[k] : -sc[k]);
-  e.metrics[7] = (e.swing_peak[0] + e.swing_peak[1]) / 2;
+  if (c.task == ODUCK_TASK_STANDING) { e.metrics[6] = (e.swing_peak[0] + e.swing_peak[1]) / 2; e.metrics[7] = 0; }
+  else e.metrics[7] = (e.swing_peak[0] + e.swing_peak[1]) / 2;
   e.reward = reward;
   // EpisodeWrapper.step (action_repeat = 1)
   e.steps += 1;
@@ -1516,6 +1561,19 @@ int oduck_test_rewards(OduckHandle* h, const double* in, double* out7) {
   return ODUCK_OK;
 }
 
+// in: command[7] upvector[3] actuator_force[nu] action[nu] last_act[nu] q[nu] qd[nu]; out: the six Standing terms (dict order)
+int oduck_test_rewards_standing(OduckHandle* h, const double* in, double* out6) {
+  if (!h || !in || !out6) return fail(ODUCK_ERR_ARG, "oduck_test_rewards_standing: bad argument");
+  const int nu = h->m.nu;
+  std::vector<real> v(in, in + 7 + 3 + 5 * nu);
+  const real* p = v.data();
+  const real *cmd = p, *up = p + 7, *af = p + 10, *ac = af + nu, *la = ac + nu, *q = la + nu, *qd = q + nu;
+  real o[6];
+  compute_rewards_standing(*h, cmd, up, af, ac, la, q, qd, o);
+  for (int k = 0; k < 6; k++) out6[k] = o[k];
+  return ODUCK_OK;
+}
+
 // Diagnostic twin of liboduck_cuda's oduck_debug_forward: same layout (DBG_STRIDE reals per env), values in double.
 int oduck_debug_stride(void) { return 5120; }
 int oduck_debug_forward(OduckHandle* h, double* out) {
@@ -1566,8 +1624,8 @@ int oduck_get_buffer(OduckHandle* h, int id, void** ptr, int64_t* shape, int64_t
     case ODUCK_BUF_QACC_WARM: FIELD(qacc_warm, m.nv) break;
     case ODUCK_BUF_QACC: FIELD(qacc, m.nv) break;
     case ODUCK_BUF_CTRL: FIELD(ctrl, m.nu) break;
-    case ODUCK_BUF_OBS_STATE: FIELD(obs_state, ODUCK_OBS_STATE) break;
-    case ODUCK_BUF_OBS_PRIV: FIELD(obs_priv, ODUCK_OBS_PRIV) break;
+    case ODUCK_BUF_OBS_STATE: FIELD(obs_state, h->cfg.task == ODUCK_TASK_STANDING ? 85 : ODUCK_OBS_STATE) break;
+    case ODUCK_BUF_OBS_PRIV: FIELD(obs_priv, h->cfg.task == ODUCK_TASK_STANDING ? 153 : ODUCK_OBS_PRIV) break;
     case ODUCK_BUF_REWARD: p = &e0->reward; break;
     case ODUCK_BUF_DONE: p = &e0->done; break;
     case ODUCK_BUF_TRUNCATION: p = &e0->truncation; break;
@@ -1597,8 +1655,8 @@ int oduck_get_buffer(OduckHandle* h, int id, void** ptr, int64_t* shape, int64_t
     case ODUCK_BUF_DR_PARAMS: p = &e0->dr_geom_friction0; d1 = (int64_t)(offsetof(EnvState, sensordata) - offsetof(EnvState, dr_geom_friction0)) / (int64_t)sizeof(real); break;
     case ODUCK_BUF_FIRST_QPOS: FIELD(first_qpos, m.nq) break;
     case ODUCK_BUF_FIRST_QVEL: FIELD(first_qvel, m.nv) break;
-    case ODUCK_BUF_FIRST_OBS_STATE: FIELD(first_obs_state, ODUCK_OBS_STATE) break;
-    case ODUCK_BUF_FIRST_OBS_PRIV: FIELD(first_obs_priv, ODUCK_OBS_PRIV) break;
+    case ODUCK_BUF_FIRST_OBS_STATE: FIELD(first_obs_state, h->cfg.task == ODUCK_TASK_STANDING ? 85 : ODUCK_OBS_STATE) break;
+    case ODUCK_BUF_FIRST_OBS_PRIV: FIELD(first_obs_priv, h->cfg.task == ODUCK_TASK_STANDING ? 153 : ODUCK_OBS_PRIV) break;
     default: return fail(ODUCK_ERR_ARG, "oduck_get_buffer: unknown buffer id");
   }
 #undef FIELD

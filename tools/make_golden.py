@@ -60,4 +60,19 @@ for k in range(K):
 np.savez_compressed(os.path.join(out, "rewards.npz"), command=cmd, local_linvel=linvel, gyro=gyro, actuator_force=force, action=act,
                     last_act=last, base_qpos=base_qpos, base_qvel=base_qvel, q=q, qd=qd, contact=contact, ref=refm, terms=terms,
                     tracking_sigma=sigma, default_pose=default_pose)
+
+# ---- Standing task (open_duck_mini_v2/standing.py:573-606): orientation, torques, action_rate, alive, stand_still(ignore_head=True), head_pos
+K = 256
+cmd_s = rng.uniform(-1, 1, (K, 7)) * np.array([0.15, 0.2, 1.0, 1.1, 0.78, 2.7, 0.5])
+cmd_s[::2, :3] = 0.0                # the Standing env itself always commands zero velocity (standing.py:648-655)
+cmd_s[1::11, :3] *= 0.02
+up = rng.normal(0, 0.3, (K, 3)); up[:, 2] = 1.0; up /= np.linalg.norm(up, axis=1, keepdims=True)
+force_s = rng.uniform(-3.23, 3.23, (K, 14)); act_s = rng.uniform(-1, 1, (K, 14)); last_s = rng.uniform(-1, 1, (K, 14))
+q_s = default_pose + rng.normal(0, 0.3, (K, 14)); qd_s = rng.normal(0, 2.0, (K, 14))
+terms_s = np.zeros((K, 6))
+for k in range(K):
+    terms_s[k] = [R.cost_orientation(up[k]), R.cost_torques(force_s[k]), R.cost_action_rate(act_s[k], last_s[k]), R.reward_alive(),
+                  R.cost_stand_still(cmd_s[k], q_s[k], qd_s[k], default_pose, True), R.cost_head_pos(q_s[k], qd_s[k], cmd_s[k])]
+np.savez_compressed(os.path.join(out, "rewards_standing.npz"), command=cmd_s, upvector=up, actuator_force=force_s, action=act_s, last_act=last_s,
+                    q=q_s, qd=qd_s, terms=terms_s, default_pose=default_pose)
 print("golden written:", sorted(os.listdir(out)))
