@@ -371,13 +371,18 @@ __device__ __forceinline__ float reduce_partials(const Seg& s, const float* __re
   const unsigned j = (unsigned)jj;                             // offsets inside a tensor fit 32 bits: 32-bit division (a 64-bit one costs ~100 instructions)
   if (!s.bias) { const unsigned k = j / (unsigned)s.N, n = j - k * (unsigned)s.N; q = partial + s.dwpart + (size_t)k * s.ldo + n; stride = s.split_stride; cnt = s.nsplit; }
   else { q = partial + s.dbpart + j; stride = s.ldb; cnt = s.nwarprows; }
-  float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+  // even splits into g0, odd splits into g1, eight loads in flight: the same summation order as reduce_quad
+  float g0 = 0.f, g1 = 0.f;
   int z = 0;
-  for (; z + 4 <= cnt; z += 4) {
-    g0 += q[(size_t)z * stride]; g1 += q[(size_t)(z + 1) * stride]; g2 += q[(size_t)(z + 2) * stride]; g3 += q[(size_t)(z + 3) * stride];
+  for (; z + 8 <= cnt; z += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldcg(q + (size_t)(z + u) * stride);
+#pragma unroll
+    for (int u = 0; u < 8; u += 2) { g0 += v[u]; g1 += v[u + 1]; }
   }
-  for (; z < cnt; ++z) g0 += q[(size_t)z * stride];
-  return (g0 + g1) + (g2 + g3);
+  for (; z < cnt; ++z) g0 += __ldcg(q + (size_t)z * stride);
+  return g0 + g1;
 }
 
 __device__ __forceinline__ void adam_element(const Seg& s, long long i, float g, float scale, float c1, float c2, float lr, float b1, float b2, float eps,
@@ -412,9 +417,54 @@ __device__ __forceinline__ void adam_element(const Seg& s, long long i, float g,
   }
 }
 
+// sum of the per-block partial sums of squares, by one warp in a fixed order (deterministic); every lane gets the total
+__device__ __forceinline__ double warp_total(const float* __restrict__ part, int n, int lane) {
+  double t = 0.0;
+  for (int k = lane; k < n; k += 32) t += (double)__ldcg(part + k);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  return t;
+}
+
 // Single-GPU product path: gradient reduce -> grid barrier -> global-norm clip + Adam + repack, one cooperative launch.
-// Every thread keeps the gradients of its (<= RA_MAX) elements in registers across the barrier.
-#define RA_MAX 8
+// Work unit = a quad of 4 consecutive flat elements (every tensor starts 4-aligned and, except the 1-wide value head, has a
+// multiple-of-4 row length): the split-K partials come in as float4 loads, all splits of a quad in flight at once (the
+// phase is latency-bound otherwise), and the gradients stay in registers across the barrier.
+#define RA_QUADS 2
+__device__ __forceinline__ float4 reduce_quad(const SegTable& tb, const float* __restrict__ partial, long long i0, bool& vec) {
+  const Seg& s = find_seg(tb, i0);
+  const unsigned j = (unsigned)(i0 - s.off);
+  const unsigned len = s.bias ? (unsigned)s.N : (unsigned)s.K * (unsigned)s.N;
+  vec = (s.N & 3) == 0 && (j & 3) == 0 && j + 4 <= len;
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (vec) {
+    const float* q; long long stride; int cnt;
+    if (!s.bias) { const unsigned k = j / (unsigned)s.N, n = j - k * (unsigned)s.N; q = partial + s.dwpart + (size_t)k * s.ldo + n; stride = s.split_stride; cnt = s.nsplit; }
+    else { q = partial + s.dbpart + j; stride = s.ldb; cnt = s.nwarprows; }
+    float4 a0 = g, a1 = g;
+    int z = 0;
+    for (; z + 8 <= cnt; z += 8) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcg(reinterpret_cast<const float4*>(q + (size_t)(z + u) * stride));
+#pragma unroll
+      for (int u = 0; u < 8; u += 2) {
+        a0.x += v[u].x; a0.y += v[u].y; a0.z += v[u].z; a0.w += v[u].w;
+        a1.x += v[u + 1].x; a1.y += v[u + 1].y; a1.z += v[u + 1].z; a1.w += v[u + 1].w;
+      }
+    }
+    for (; z < cnt; ++z) { const float4 v = __ldcg(reinterpret_cast<const float4*>(q + (size_t)z * stride)); a0.x += v.x; a0.y += v.y; a0.z += v.z; a0.w += v.w; }
+    g = make_float4(a0.x + a1.x, a0.y + a1.y, a0.z + a1.z, a0.w + a1.w);
+  } else {
+    float* pg = reinterpret_cast<float*>(&g);
+    for (int e = 0; e < 4; ++e) {
+      const long long i = i0 + e;
+      if (i < tb.total) { const Seg& se = find_seg(tb, i); pg[e] = reduce_partials(se, partial, i - se.off); }
+    }
+  }
+  return g;
+}
+
 __global__ void __launch_bounds__(256) k_ppo_reduce_adam(const SegTable* __restrict__ tbp, const float* __restrict__ partial, float* __restrict__ grads,
                                                          float* __restrict__ sumsq_part, float* __restrict__ params, float* __restrict__ m1, float* __restrict__ m2,
                                                          float* __restrict__ packed, int* __restrict__ step, float lr, float b1, float b2, float eps, float max_norm) {
@@ -424,45 +474,58 @@ __global__ void __launch_bounds__(256) k_ppo_reduce_adam(const SegTable* __restr
   for (int i = threadIdx.x; i < (int)(sizeof(SegTable) / 4); i += blockDim.x) reinterpret_cast<int*>(&tb)[i] = reinterpret_cast<const int*>(tbp)[i];
   __syncthreads();
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
-  float g[RA_MAX];
+  const long long nquad = (tb.total + 3) >> 2;
+  float4 g[RA_QUADS];
   double ss = 0.0;
+  auto quad_grad = [&](long long qd) {
+    bool vec;
+    const float4 x = reduce_quad(tb, partial, qd * 4, vec);
+    const float* px = reinterpret_cast<const float*>(&x);
+    if (qd * 4 + 4 <= tb.total) *reinterpret_cast<float4*>(grads + qd * 4) = x;
+    else for (int e = 0; e < 4; ++e) if (qd * 4 + e < tb.total) grads[qd * 4 + e] = px[e];
+    for (int e = 0; e < 4; ++e) if (qd * 4 + e < tb.total) ss += (double)px[e] * px[e];
+    return x;
+  };
 #pragma unroll
-  for (int e = 0; e < RA_MAX; ++e) {
-    const long long i = tid + (long long)e * nth;
-    g[e] = 0.f;
-    if (i < tb.total) {
-      const Seg& s = find_seg(tb, i);
-      g[e] = reduce_partials(s, partial, i - s.off);
-      grads[i] = g[e];
-      ss += (double)g[e] * g[e];
-    }
+  for (int u = 0; u < RA_QUADS; ++u) {
+    const long long qd = tid + (long long)u * nth;
+    g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (qd < nquad) g[u] = quad_grad(qd);
   }
-  for (long long i = tid + (long long)RA_MAX * nth; i < tb.total; i += nth) {      // (only if P > RA_MAX * threads)
-    const Seg& s = find_seg(tb, i);
-    const float x = reduce_partials(s, partial, i - s.off);
-    grads[i] = x;
-    ss += (double)x * x;
-  }
+  for (long long qd = tid + (long long)RA_QUADS * nth; qd < nquad; qd += nth) quad_grad(qd);      // (only if P > 4 RA_QUADS threads)
   const double t = block_sum(ss, sh);
   if (threadIdx.x == 0) sumsq_part[blockIdx.x] = (float)t;
   __threadfence();
   cooperative_groups::this_grid().sync();
-  if (threadIdx.x == 0) {
-    double tot = 0.0;
-    for (int k = 0; k < (int)gridDim.x; ++k) tot += (double)((volatile float*)sumsq_part)[k];
-    const float gn = (float)sqrt(tot);
-    s_scale = (max_norm > 0.f && gn >= max_norm) ? max_norm / gn : 1.f;
-    const int tt = step[0] + 1;
-    s_c1 = 1.f / (1.f - powf(b1, (float)tt));
-    s_c2 = 1.f / (1.f - powf(b2, (float)tt));
+  if (threadIdx.x < 32) {
+    const double tot = warp_total(sumsq_part, (int)gridDim.x, threadIdx.x);
+    if (threadIdx.x == 0) {
+      const float gn = (float)sqrt(tot);
+      s_scale = (max_norm > 0.f && gn >= max_norm) ? max_norm / gn : 1.f;
+      const int tt = step[0] + 1;
+      s_c1 = 1.f / (1.f - powf(b1, (float)tt));
+      s_c2 = 1.f / (1.f - powf(b2, (float)tt));
+    }
   }
   __syncthreads();
+  auto quad_adam = [&](long long qd, const float4& x) {
+    const float* px = reinterpret_cast<const float*>(&x);
+    for (int e = 0; e < 4; ++e) {
+      const long long i = qd * 4 + e;
+      if (i < tb.total) adam_element(find_seg(tb, i), i, px[e], s_scale, s_c1, s_c2, lr, b1, b2, eps, params, m1, m2, packed, true);
+    }
+  };
 #pragma unroll
-  for (int e = 0; e < RA_MAX; ++e) {
-    const long long i = tid + (long long)e * nth;
-    if (i < tb.total) adam_element(find_seg(tb, i), i, g[e], s_scale, s_c1, s_c2, lr, b1, b2, eps, params, m1, m2, packed, true);
+  for (int u = 0; u < RA_QUADS; ++u) {
+    const long long qd = tid + (long long)u * nth;
+    if (qd < nquad) quad_adam(qd, g[u]);
   }
-  for (long long i = tid + (long long)RA_MAX * nth; i < tb.total; i += nth) adam_element(find_seg(tb, i), i, grads[i], s_scale, s_c1, s_c2, lr, b1, b2, eps, params, m1, m2, packed, true);
+  for (long long qd = tid + (long long)RA_QUADS * nth; qd < nquad; qd += nth) {
+    float4 x;
+    float* px = reinterpret_cast<float*>(&x);
+    for (int e = 0; e < 4; ++e) px[e] = qd * 4 + e < tb.total ? grads[qd * 4 + e] : 0.f;
+    quad_adam(qd, x);
+  }
   cooperative_groups::this_grid().sync();
   if (blockIdx.x == 0 && threadIdx.x == 0) step[0] += 1;
 }
@@ -499,14 +562,15 @@ __global__ void __launch_bounds__(256) k_ppo_adam(const SegTable* __restrict__ t
   __shared__ SegTable tb;
   __shared__ float s_scale, s_c1, s_c2;
   for (int i = threadIdx.x; i < (int)(sizeof(SegTable) / 4); i += blockDim.x) reinterpret_cast<int*>(&tb)[i] = reinterpret_cast<const int*>(tbp)[i];
-  if (threadIdx.x == 0 && update) {
-    double ss = 0.0;
-    for (int k = 0; k < nparts; ++k) ss += (double)sumsq_part[k];
-    const float gn = (float)sqrt(ss);
-    s_scale = (max_norm > 0.f && gn >= max_norm) ? max_norm / gn : 1.f;
-    const int t = step[0] + 1;
-    s_c1 = 1.f / (1.f - powf(b1, (float)t));
-    s_c2 = 1.f / (1.f - powf(b2, (float)t));
+  if (threadIdx.x < 32 && update) {
+    const double ss = warp_total(sumsq_part, nparts, threadIdx.x);
+    if (threadIdx.x == 0) {
+      const float gn = (float)sqrt(ss);
+      s_scale = (max_norm > 0.f && gn >= max_norm) ? max_norm / gn : 1.f;
+      const int t = step[0] + 1;
+      s_c1 = 1.f / (1.f - powf(b1, (float)t));
+      s_c2 = 1.f / (1.f - powf(b2, (float)t));
+    }
   }
   __syncthreads();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tb.total; i += (long long)gridDim.x * blockDim.x)
