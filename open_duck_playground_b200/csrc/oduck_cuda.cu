@@ -67,6 +67,7 @@ __device__ __forceinline__ void load_env(const DevModel& m, WarpSmem& s, Lane& L
   L.floss = isd ? dr[DR_FLOSS + lane] : 0.f;
   L.arm = isd ? dr[DR_ARM + lane] : 0.f;
   L.mass = lane < m.nbody ? dr[lane] : 0.f;
+  L.imt = 1.f / fmaxf(wsum(L.mass), 1e-15f);
   for (int i = lane; i < 528; i += 32) s.A[i] = 0.f;   // structural zeros of M (only ancestor pairs are rewritten each substep)
   L.ipos = v3(m.b_ipos[0][lane], m.b_ipos[1][lane], m.b_ipos[2][lane]);
   if (lane == 1) L.ipos = v3(dr[DR_IPOS1], dr[DR_IPOS1 + 1], dr[DR_IPOS1 + 2]);   // TORSO_BODY_ID = 1 (randomize.py:23)
@@ -629,6 +630,31 @@ static int build_dev_model(const OduckModel& M, DevModel& D, std::string& err) {
     for (int j = i; j >= 0; j = M.dof_parentid[j]) D.mpair[D.n_mpairs++] = (unsigned short)((i << 8) | j);
   D.body_rounds = 0;
   while ((1 << D.body_rounds) < D.maxdepth) D.body_rounds++;
+  {
+    // chain-scan plan for subtree sums over the moving bodies 1..nbody-1 (world excluded; children of the world are roots)
+    int nchild[32] = {0}, only[32];
+    for (int b = 0; b < 32; b++) { only[b] = -1; D.b_next[b] = -1; }
+    for (int b = 1; b < M.nbody; b++) { int p = M.body_parentid[b]; if (p > 0) { nchild[p]++; only[p] = b; } }
+    int maxchain = 1;
+    bool ok = true;
+    D.n_branch = 0;
+    for (int b = 1; b < M.nbody; b++) if (nchild[b] == 1) D.b_next[b] = only[b];
+    for (int b = 1; b < M.nbody; b++) { int len = 1; for (int x = b; D.b_next[x] >= 0; x = D.b_next[x]) len++; maxchain = std::max(maxchain, len); }
+    D.scan_rounds = 0;
+    while ((1 << D.scan_rounds) < maxchain) D.scan_rounds++;
+    // branching bodies, deepest first (body ids grow with depth along a path, so descending id order is a valid order)
+    for (int b = M.nbody - 1; b >= 1 && ok; b--) {
+      if (nchild[b] < 2) continue;
+      if (D.n_branch >= 4 || nchild[b] > 4) { ok = false; break; }
+      const int k = D.n_branch++;
+      D.br_nchild[k] = 0;
+      for (int c = 1; c < M.nbody; c++) if (M.body_parentid[c] == b) D.br_child[k][D.br_nchild[k]++] = c;
+      int mask = 1 << b;                                   // the chain that ends in b: b and its single-child ancestors
+      for (int x = M.body_parentid[b]; x > 0 && nchild[x] == 1; x = M.body_parentid[x]) mask |= 1 << x;
+      D.br_chain[k] = mask;
+    }
+    D.scan_ok = ok ? 1 : 0;
+  }
   for (int b = 0; b < M.nbody; b++) {
     int j0 = M.body_jntadr[b];
     D.b_sameaxis[b] = (M.body_jntnum[b] == 2 && M.jnt_axis[j0][0] == M.jnt_axis[j0 + 1][0] && M.jnt_axis[j0][1] == M.jnt_axis[j0 + 1][1] && M.jnt_axis[j0][2] == M.jnt_axis[j0 + 1][2]);

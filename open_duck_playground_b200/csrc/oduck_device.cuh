@@ -80,6 +80,11 @@ struct DevModel {
   unsigned short mpair[512];     // structural non-zeros of M: (i << 8 | j), j an ancestor of i or i itself
   int n_mpairs, body_rounds;
   int b_sameaxis[NLANE];
+  // subtree sums by chain scan: b_next = the only child of a body (-1: leaf or branching), scan_rounds = log2 of the longest
+  // single-child chain; branching bodies deepest first with their children and the bodies of the chain that ends in them
+  int scan_ok, scan_rounds, n_branch;
+  int b_next[NLANE];
+  int br_nchild[4], br_child[4][4], br_chain[4];
 };
 
 // per-warp shared memory
@@ -137,36 +142,25 @@ __device__ __forceinline__ float wfold(float (&v)[K], const int lane) { return W
 __device__ __forceinline__ float wfold_get(const float t, const int k) { return __shfl_sync(FULLMASK, t, k); }
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
+// Warp max on the redux unit (sm_100a: redux.sync.max.f32 -> CREDUX.MAX.F32, one instruction instead of a 5-step shuffle
+// butterfly; NaN lanes are ignored).
 __device__ __forceinline__ float wmaxf(float v) {
-#pragma unroll
-  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULLMASK, v, o));
-  return v;
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
 }
-// argmax with first-index tie break (jp.argmax semantics); every lane gets the winner
+// argmax with first-index tie break (jp.argmax semantics); every lane gets the winner: max on the redux unit, then the
+// lowest lane that holds it (ballot + ffs) -- 2 instructions on the shuffle/vote path instead of 10 shuffles
 __device__ __forceinline__ int wargmax(float v, int lane) {
-  int idx = lane;
-#pragma unroll
-  for (int o = 16; o; o >>= 1) {
-    float ov = __shfl_xor_sync(FULLMASK, v, o);
-    int oi = __shfl_xor_sync(FULLMASK, idx, o);
-    bool take = (ov > v) || (ov == v && oi < idx);
-    v = take ? ov : v;
-    idx = take ? oi : idx;
-  }
-  return idx;
+  const float m = wmaxf(v);
+  const unsigned b = __ballot_sync(FULLMASK, v == m);
+  return b ? __ffs(b) - 1 : 0;
 }
 __device__ __forceinline__ float wargmax_val(float v, int lane, int* out_idx) {
-  int idx = lane;
-#pragma unroll
-  for (int o = 16; o; o >>= 1) {
-    float ov = __shfl_xor_sync(FULLMASK, v, o);
-    int oi = __shfl_xor_sync(FULLMASK, idx, o);
-    bool take = (ov > v) || (ov == v && oi < idx);
-    v = take ? ov : v;
-    idx = take ? oi : idx;
-  }
-  *out_idx = idx;
-  return v;
+  const float m = wmaxf(v);
+  const unsigned b = __ballot_sync(FULLMASK, v == m);
+  *out_idx = b ? __ffs(b) - 1 : 0;
+  return m;
 }
 
 struct V3 { float x, y, z; };

@@ -10,6 +10,7 @@
 struct Lane {
   float qvel, qaccw, qacc, ctrl, kp, floss, arm;   // dof role (ctrl/kp: the dof's actuator, if any)
   float mass;                                     // body role
+  float imt;                                      // 1 / total mass (constant over the substeps of a launch)
   V3 ipos;
 };
 
@@ -112,9 +113,13 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
              xp.y + R[3] * L.ipos.x + R[4] * L.ipos.y + R[5] * L.ipos.z,
              xp.z + R[6] * L.ipos.x + R[7] * L.ipos.y + R[8] * L.ipos.z);
   const float ms = L.mass;
-  const float mt = wsum(ms);
-  const float imt = 1.f / fmaxf(mt, 1e-15f);
-  const V3 com = v3(wsum(ms * xi.x) * imt, wsum(ms * xi.y) * imt, wsum(ms * xi.z) * imt);
+  const float imt = L.imt;
+  V3 com;
+  {
+    float mx[3] = {ms * xi.x, ms * xi.y, ms * xi.z};
+    const float t = wfold<3>(mx, lane);
+    com = v3(wfold_get(t, 0) * imt, wfold_get(t, 1) * imt, wfold_get(t, 2) * imt);
+  }
   I10 cin;
   {
     // body-frame inertia about its COM (constant) rotated into the world, shifted to the common reference point
@@ -154,9 +159,37 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
   __syncwarp();
 
   // ------------------------------------------------------------------ crb: subtree sums of cinert (lane = body)
-  I10 crb;
-  crb.xx = crb.yy = crb.zz = crb.xy = crb.xz = crb.yz = crb.hx = crb.hy = crb.hz = crb.m = 0.f;
-  {
+  I10 crb = cin;
+  if (m.scan_ok) {
+    // Subtree sums without visiting every body: (1) suffix sums along the single-child chains by pointer jumping (log2 of the
+    // longest chain rounds), (2) every branching body, deepest first, collects its children's totals and hands them to the
+    // chain that ends in it.  63 shuffles for the duck (three chains under the trunk) instead of 170.
+    int nx = m.b_next[lane];
+    for (int r = 0; r < m.scan_rounds; ++r) {
+      const int src = nx < 0 ? 0 : nx;
+#define ACC(f) { const float v = __shfl_sync(FULLMASK, crb.f, src); if (nx >= 0) crb.f += v; }
+      ACC(xx) ACC(yy) ACC(zz) ACC(xy) ACC(xz) ACC(yz) ACC(hx) ACC(hy) ACC(hz) ACC(m)
+#undef ACC
+      const int nn = __shfl_sync(FULLMASK, nx, src);
+      if (nx >= 0) nx = nn;
+    }
+    for (int k = 0; k < m.n_branch; ++k) {
+      I10 x;
+      x.xx = x.yy = x.zz = x.xy = x.xz = x.yz = x.hx = x.hy = x.hz = x.m = 0.f;
+      for (int c = 0; c < m.br_nchild[k]; ++c) {
+        const int ch = m.br_child[k][c];
+#define ACC(f) x.f += __shfl_sync(FULLMASK, crb.f, ch);
+        ACC(xx) ACC(yy) ACC(zz) ACC(xy) ACC(xz) ACC(yz) ACC(hx) ACC(hy) ACC(hz) ACC(m)
+#undef ACC
+      }
+      if ((m.br_chain[k] >> lane) & 1) {
+#define ACC(f) crb.f += x.f;
+        ACC(xx) ACC(yy) ACC(zz) ACC(xy) ACC(xz) ACC(yz) ACC(hx) ACC(hy) ACC(hz) ACC(m)
+#undef ACC
+      }
+    }
+  } else {
+    crb.xx = crb.yy = crb.zz = crb.xy = crb.xz = crb.yz = crb.hx = crb.hy = crb.hz = crb.m = 0.f;
     const int sub = m.b_submask[lane];
     for (int c = 1; c < nb; ++c) {
       const bool in = (sub >> c) & 1;
@@ -226,10 +259,29 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
     if (lastd < 0) cacc = s6zero();
     cacc.l0 -= m.gravity[0]; cacc.l1 -= m.gravity[1]; cacc.l2 -= m.gravity[2];
     S6 cfrc = s6add(inert_mul(cin, cacc), cross_force(cvel, inert_mul(cin, cvel)));
-    const int bsub = m.d_bsubmask[lane];
-    for (int b = 1; b < nb; ++b) {
-      S6 f = s6shfl(cfrc, b);
-      if ((bsub >> b) & 1) qfrc_bias += s6dot(cd, f);
+    if (m.scan_ok) {
+      // subtree-summed force per body (same chain scan as the composite inertias), then one fetch per dof lane
+      if (lane == 0 || lane >= nb) cfrc = s6zero();
+      int nx = m.b_next[lane];
+      for (int r = 0; r < m.scan_rounds; ++r) {
+        const int src = nx < 0 ? 0 : nx;
+        const S6 o = s6shfl(cfrc, src);
+        const int nn = __shfl_sync(FULLMASK, nx, src);
+        if (nx >= 0) { cfrc = s6add(cfrc, o); nx = nn; }
+      }
+      for (int k = 0; k < m.n_branch; ++k) {
+        S6 x = s6zero();
+        for (int c = 0; c < m.br_nchild[k]; ++c) x = s6add(x, s6shfl(cfrc, m.br_child[k][c]));
+        if ((m.br_chain[k] >> lane) & 1) cfrc = s6add(cfrc, x);
+      }
+      const S6 f = s6shfl(cfrc, dbody);
+      qfrc_bias = lane < nv ? s6dot(cd, f) : 0.f;
+    } else {
+      const int bsub = m.d_bsubmask[lane];
+      for (int b = 1; b < nb; ++b) {
+        S6 f = s6shfl(cfrc, b);
+        if ((bsub >> b) & 1) qfrc_bias += s6dot(cd, f);
+      }
     }
   }
   // ------------------------------------------------------------------ passive + actuation + smooth acceleration (lane = dof)
@@ -417,11 +469,12 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
     for (int r = 0; r < 4; ++r) { Jcw[r] -= arefc[r]; Jcs[r] -= arefc[r]; }
     const float Jfw = qw - areff, Jfs = as - areff;
     const float Jlw = lsign * qw - arefl, Jls = lsign * as - arefl;
-    float cw = 0.5f * (Maw - fs) * (qw - as), cs = 0.f;
-    const float gw = wsum(cw);
+    float gwl = 0.5f * (Maw - fs) * (qw - as), cw = 0.f, cs = 0.f;
     ROW_COST(Jfw, Jlw, Jcw, cw)
     ROW_COST(Jfs, Jls, Jcs, cs)
-    const float costw = wsum(cw), costs = wsum(cs);
+    float c3[3] = {gwl, cw, cs};
+    const float ct = wfold<3>(c3, lane);
+    const float gw = wfold_get(ct, 0), costw = gw + wfold_get(ct, 1), costs = wfold_get(ct, 2);
     const bool usew = costw < costs;
     qacc = usew ? qw : as;
     Ma = usew ? Maw : fs;
