@@ -91,10 +91,10 @@ struct DevModel {
 struct WarpSmem {
   float A[528];               // M, packed lower
   float H[528];               // chol(M), then H = M + J^T D J and its factor
-  float bf[8][NLANE];         // staging: crb[body_i] * cdof_i and armature for the M pair pass
+  float bf[NLANE][8];         // staging for the M pair pass, one 32-byte record per dof: crb[body_i] * cdof_i (6) | armature | -
   float xpos[3][NLANE];
   float xmat[9][NLANE];
-  float cdof[6][NLANE];
+  float cdof[NLANE][8];       // motion axis per dof, one 32-byte record: ang (3), lin (3), - , -  (read back as two float4)
   float qpos[36];
   float qpos0[36];
   // contact records, read back as float4 broadcasts: [0] dist, [1..3] pos | [4..6] force (n, t1, t2) | [8..12] Hessian
@@ -102,6 +102,7 @@ struct WarpSmem {
   float con[NCON_ALL][CON_STRIDE];
   float misc[64];
   float rhs[NLANE];            // right-hand side swept leaf-to-root inside chol_rev
+  float rowbuf[NLANE];         // pivot rows of the register-blocked factorisation (one 16-float row per half-warp), float4-aligned
   float outrec[OUT_STRIDE];     // staged outputs of the last forward (copied to HBM once per launch)
 };
 
@@ -285,8 +286,11 @@ static __device__ __noinline__ void chol_rev(const DevModel& m, float* A, float*
 // its Schur-complement contribution to the root block (accumulated from zero) in a[0..5]; the root block is finished last.
 // Same arithmetic as chol_rev(tree = true) up to summation order; rhs is swept leaf-to-root alongside.
 #define CH_NB 6
+// The row of the pivot (L[k][0..k-1], one value per column lane) is handed to all columns through a 16-float shared-memory
+// row per half-warp and read back as float4 broadcasts: 1 store + ceil(k/4) loads on the shuffle/shared-memory pipe instead
+// of k shuffles (that pipe, not the FP32 pipes, bounds the step kernel).
 template <int NLOC>
-__device__ __forceinline__ void branch_elim(float* H, float* rhs, const int lane, const int gstart, const bool store, float (&a)[NLOC], float& r) {
+__device__ __forceinline__ void branch_elim(float* H, float* rhs, const int lane, const int gstart, const bool store, float (&a)[NLOC], float& r, float* rowbuf) {
   const int j = lane & 15, hb = lane & 16;
   const int gj = j < CH_NB ? j : gstart + j - CH_NB;
   const bool col = j < NLOC;
@@ -304,8 +308,17 @@ __device__ __forceinline__ void branch_elim(float* H, float* rhs, const int lane
     a[k] = j == k ? akk * inv : lk;
     const float yk = __shfl_sync(FULLMASK, r, hb | k) * inv;
     r = j == k ? yk : r - lk * yk;
+    __syncwarp();                                               // the previous pivot's row has been read by every lane
+    rowbuf[hb | j] = lk;                                        // zero for j >= k: rows >= k are not touched below
+    __syncwarp();
 #pragma unroll
-    for (int i = 0; i < k; ++i) a[i] = fmaf(-__shfl_sync(FULLMASK, lk, hb | i), lk, a[i]);   // A[i][j] -= L[k][i] L[k][j]
+    for (int i4 = 0; i4 < (k + 3) / 4; ++i4) {                  // A[i][j] -= L[k][i] L[k][j]
+      const float4 v = lds4(rowbuf + hb + 4 * i4);
+      a[4 * i4] = fmaf(-v.x, lk, a[4 * i4]);
+      if (4 * i4 + 1 < NLOC) a[4 * i4 + 1] = fmaf(-v.y, lk, a[4 * i4 + 1]);
+      if (4 * i4 + 2 < NLOC) a[4 * i4 + 2] = fmaf(-v.z, lk, a[4 * i4 + 2]);
+      if (4 * i4 + 3 < NLOC) a[4 * i4 + 3] = fmaf(-v.w, lk, a[4 * i4 + 3]);
+    }
   }
   if (store && col) {
 #pragma unroll
@@ -316,19 +329,19 @@ __device__ __forceinline__ void branch_elim(float* H, float* rhs, const int lane
 }
 
 template <int NPAIR, int NSINGLE>   // branch lengths
-static __device__ __noinline__ void chol_rev_chain(const DevModel& m, float* H, float* rhs, const int lane) {
+static __device__ __noinline__ void chol_rev_chain(const DevModel& m, float* H, float* rhs, const int lane, float* rowbuf) {
   const int j = lane & 15;
   float db[CH_NB], dr;
   {
     float a[CH_NB + NPAIR], r;
-    branch_elim<CH_NB + NPAIR>(H, rhs, lane, m.plan_pair_start[lane >> 4], true, a, r);
+    branch_elim<CH_NB + NPAIR>(H, rhs, lane, m.plan_pair_start[lane >> 4], true, a, r, rowbuf);
 #pragma unroll
     for (int i = 0; i < CH_NB; ++i) db[i] = a[i] + __shfl_xor_sync(FULLMASK, a[i], 16);
     dr = r + __shfl_xor_sync(FULLMASK, r, 16);
   }
   if (NSINGLE > 0) {
     float a[CH_NB + (NSINGLE > 0 ? NSINGLE : 1)], r;
-    branch_elim<CH_NB + (NSINGLE > 0 ? NSINGLE : 1)>(H, rhs, lane, m.plan_single_start, lane < 16, a, r);   // both halves compute, half 0 stores
+    branch_elim<CH_NB + (NSINGLE > 0 ? NSINGLE : 1)>(H, rhs, lane, m.plan_single_start, lane < 16, a, r, rowbuf);   // both halves compute, half 0 stores
 #pragma unroll
     for (int i = 0; i < CH_NB; ++i) db[i] += a[i];
     dr += r;
@@ -360,9 +373,9 @@ static __device__ __noinline__ void chol_rev_chain(const DevModel& m, float* H, 
   __syncwarp();
 }
 // factorise + sweep: register-blocked chains when the model matches a compiled plan, else the generic pair-table version
-__device__ __forceinline__ void chol_rev_tree(const DevModel& m, float* H, float* rhs, int n, int lane) {
-  if (m.plan_ok == 1) chol_rev_chain<10, 4>(m, H, rhs, lane);
-  else if (m.plan_ok == 2) chol_rev_chain<5, 4>(m, H, rhs, lane);
+__device__ __forceinline__ void chol_rev_tree(const DevModel& m, float* H, float* rhs, int n, int lane, float* rowbuf) {
+  if (m.plan_ok == 1) chol_rev_chain<10, 4>(m, H, rhs, lane, rowbuf);
+  else if (m.plan_ok == 2) chol_rev_chain<5, 4>(m, H, rhs, lane, rowbuf);
   else chol_rev(m, H, rhs, n, lane, true);
 }
 
@@ -389,16 +402,27 @@ static __device__ __noinline__ float chol_rev_back(const DevModel& m, const floa
   }
   return y;
 }
-// y = A x for the packed symmetric matrix; one element per lane.
-static __device__ __noinline__ float symv(const float* A, int n, int lane, float x) {
+// y = A x for the packed symmetric matrix; one element per lane.  x is handed to all lanes through a 32-float shared-memory
+// row read back as float4 broadcasts (8 loads instead of 30 shuffles).
+static __device__ __noinline__ float symv(const float* A, int n, int lane, float x, float* xbuf) {
   float acc = 0.f;
   const int ri = TRI(lane);
-  for (int j = 0; j < n; ++j) {
-    float xj = __shfl_sync(FULLMASK, x, j);
-    int idx = (j <= lane) ? ri + j : TRI(j) + lane;
-    float a = A[idx];
-    acc = fmaf(a, xj, acc);
+  __syncwarp();
+  xbuf[lane] = lane < n ? x : 0.f;
+  __syncwarp();
+  for (int j4 = 0; 4 * j4 < n; ++j4) {
+    const float4 xv = lds4(xbuf + 4 * j4);
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = 4 * j4 + e;
+      if (j < n) {
+        const int idx = (j <= lane) ? ri + j : TRI(j) + lane;
+        acc = fmaf(A[idx], xs[e], acc);
+      }
+    }
   }
+  __syncwarp();
   return lane < n ? acc : 0.f;
 }
 // constraint.py _kbi impedance for a signed distance

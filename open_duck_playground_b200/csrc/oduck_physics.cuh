@@ -97,13 +97,13 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
     if (jt == 1) {
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        s.cdof[0][da + k] = 0.f; s.cdof[1][da + k] = 0.f; s.cdof[2][da + k] = 0.f;
-        s.cdof[3][da + k] = (k == 0); s.cdof[4][da + k] = (k == 1); s.cdof[5][da + k] = (k == 2);
-        s.cdof[0][da + 3 + k] = R[k]; s.cdof[1][da + 3 + k] = R[3 + k]; s.cdof[2][da + 3 + k] = R[6 + k];
+        *reinterpret_cast<float4*>(&s.cdof[da + k][0]) = make_float4(0.f, 0.f, 0.f, k == 0);
+        *reinterpret_cast<float4*>(&s.cdof[da + k][4]) = make_float4(k == 1, k == 2, 0.f, 0.f);
+        *reinterpret_cast<float4*>(&s.cdof[da + 3 + k][0]) = make_float4(R[k], R[3 + k], R[6 + k], 0.f);
       }
     } else if (jt >= 2) {
-      s.cdof[0][da] = ax0w.x; s.cdof[1][da] = ax0w.y; s.cdof[2][da] = ax0w.z;
-      if (jt == 3) { s.cdof[0][da + 1] = ax1w.x; s.cdof[1][da + 1] = ax1w.y; s.cdof[2][da + 1] = ax1w.z; }
+      *reinterpret_cast<float4*>(&s.cdof[da][0]) = make_float4(ax0w.x, ax0w.y, ax0w.z, 0.f);
+      if (jt == 3) *reinterpret_cast<float4*>(&s.cdof[da + 1][0]) = make_float4(ax1w.x, ax1w.y, ax1w.z, 0.f);
     }
   }
   __syncwarp();
@@ -146,14 +146,17 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
   const int dbody = m.d_body[lane];
   S6 cd = s6zero();
   if (lane < nv) {
-    cd.a0 = s.cdof[0][lane]; cd.a1 = s.cdof[1][lane]; cd.a2 = s.cdof[2][lane];
+    const float4 c0 = lds4(&s.cdof[lane][0]);
+    cd.a0 = c0.x; cd.a1 = c0.y; cd.a2 = c0.z;
     if (flags & DF_TRANS) {
-      cd.l0 = s.cdof[3][lane]; cd.l1 = s.cdof[4][lane]; cd.l2 = s.cdof[5][lane];
+      const float4 c1 = lds4(&s.cdof[lane][4]);
+      cd.l0 = c0.w; cd.l1 = c1.x; cd.l2 = c1.y;
     } else {
       V3 off = com - v3(s.xpos[0][dbody], s.xpos[1][dbody], s.xpos[2][dbody]);
       V3 l = cross(v3(cd.a0, cd.a1, cd.a2), off);
       cd.l0 = l.x; cd.l1 = l.y; cd.l2 = l.z;
-      s.cdof[3][lane] = l.x; s.cdof[4][lane] = l.y; s.cdof[5][lane] = l.z;
+      s.cdof[lane][3] = l.x;
+      *reinterpret_cast<float4*>(&s.cdof[lane][4]) = make_float4(l.y, l.z, 0.f, 0.f);
     }
   }
   __syncwarp();
@@ -205,16 +208,15 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
     GET(xx) GET(yy) GET(zz) GET(xy) GET(xz) GET(yz) GET(hx) GET(hy) GET(hz) GET(m)
 #undef GET
     const S6 buf = inert_mul(cb, cd);                                   // crb[body_i] * cdof_i, staged for the pair pass
-    float (*bf)[NLANE] = s.bf;
-    bf[0][lane] = buf.a0; bf[1][lane] = buf.a1; bf[2][lane] = buf.a2; bf[3][lane] = buf.l0; bf[4][lane] = buf.l1; bf[5][lane] = buf.l2;
-    bf[6][lane] = L.arm;
+    *reinterpret_cast<float4*>(&s.bf[lane][0]) = make_float4(buf.a0, buf.a1, buf.a2, buf.l0);
+    *reinterpret_cast<float4*>(&s.bf[lane][4]) = make_float4(buf.l1, buf.l2, L.arm, 0.f);
     __syncwarp();
     for (int pp = lane; pp < m.n_mpairs; pp += 32) {
       const unsigned ij = m.mpair[pp];
       const int i = ij >> 8, j = ij & 255;
-      float v = s.cdof[0][j] * bf[0][i] + s.cdof[1][j] * bf[1][i] + s.cdof[2][j] * bf[2][i] + s.cdof[3][j] * bf[3][i] + s.cdof[4][j] * bf[4][i] +
-                s.cdof[5][j] * bf[5][i];
-      if (i == j) v += bf[6][i];
+      const float4 c0 = lds4(&s.cdof[j][0]), c1 = lds4(&s.cdof[j][4]), b0 = lds4(&s.bf[i][0]), b1 = lds4(&s.bf[i][4]);
+      float v = c0.x * b0.x + c0.y * b0.y + c0.z * b0.z + c0.w * b0.w + c1.x * b1.x + c1.y * b1.y;
+      if (i == j) v += b1.z;
       s.A[TRI(i) + j] = v;
     }
   }
@@ -294,10 +296,10 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
     aforce = fminf(fmaxf(f, m.d_flo[lane]), m.d_fhi[lane]);
   }
   const float fs = lane < nv ? (-m.d_damping[lane] * L.qvel - qfrc_bias + aforce) : 0.f;   // qfrc_smooth
-  for (int idx = lane; idx < TRI(nv); idx += 32) s.H[idx] = s.A[idx];
+  for (int idx = lane; 4 * idx < TRI(nv); idx += 32) reinterpret_cast<float4*>(s.H)[idx] = reinterpret_cast<const float4*>(s.A)[idx];   // float4 copy (both 16-byte aligned, 528 floats)
   s.rhs[lane] = fs;
   __syncwarp();
-  chol_rev_tree(m, s.H, s.rhs, nv, lane);                                                   // factor_m + L^-T qfrc_smooth
+  chol_rev_tree(m, s.H, s.rhs, nv, lane, s.rowbuf);                                         // factor_m + L^-T qfrc_smooth
   const float as = chol_rev_back(m, s.H, nv, lane, s.rhs[lane], true);                      // qacc_smooth
 
   PHASE_SYNC(2, true)
@@ -461,7 +463,7 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
   float qacc, Ma, Jf, Jl, Jc[4], gauss;
   {
     const float qw = lane < nv ? L.qaccw : 0.f;
-    const float Maw = symv(s.A, nv, lane, qw);
+    const float Maw = symv(s.A, nv, lane, qw, s.rowbuf);
     float Jcw[4], Jcs[4];
     CONTACT_PRODUCTS(qw, Jcw)
     CONTACT_PRODUCTS(as, Jcs)
@@ -546,7 +548,7 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
     }
     grad = lane < nv ? Ma - fs - qfc : 0.f;
     // H = M + J^T D J
-    for (int idx = lane; idx < TRI(nv); idx += 32) s.H[idx] = s.A[idx];
+    for (int idx = lane; 4 * idx < TRI(nv); idx += 32) reinterpret_cast<float4*>(s.H)[idx] = reinterpret_cast<const float4*>(s.A)[idx];   // float4 copy (both 16-byte aligned, 528 floats)
     __syncwarp();
     if (lane < nv) s.H[TRI(lane) + lane] += (fquad ? Df : 0.f) + (lon ? Dl : 0.f);
     if (anyc) {
@@ -557,7 +559,8 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
       for (int lev = 0; lev <= m.max_dof_depth; ++lev) {
         if (lev <= dep) {
           const int j = lev < dep ? al[lev] : lane;
-          Hi[j] += z.a0 * s.cdof[0][j] + z.a1 * s.cdof[1][j] + z.a2 * s.cdof[2][j] + z.l0 * s.cdof[3][j] + z.l1 * s.cdof[4][j] + z.l2 * s.cdof[5][j];
+          const float4 c0 = lds4(&s.cdof[j][0]), c1 = lds4(&s.cdof[j][4]);
+          Hi[j] += z.a0 * c0.x + z.a1 * c0.y + z.a2 * c0.z + z.l0 * c0.w + z.l1 * c1.x + z.l2 * c1.y;
         }
       }
     }
@@ -587,7 +590,7 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
     s.rhs[lane] = grad;
     __syncwarp();
     if (FF && ffact) chol_rev(m, s.H, s.rhs, nv, lane, false);
-    else chol_rev_tree(m, s.H, s.rhs, nv, lane);
+    else chol_rev_tree(m, s.H, s.rhs, nv, lane, s.rowbuf);
     search = -chol_rev_back(m, s.H, nv, lane, s.rhs[lane], !(FF && ffact));
     if (lane >= nv) search = 0.f;
   }
@@ -597,7 +600,7 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
   // the rows that are active AT alpha).  The three trial points of an iteration are evaluated lane-locally and their six
   // sums folded in one butterfly (wfold); costs are only needed to choose between the final bracket ends and the start.
   {
-    const float Mv = symv(s.A, nv, lane, search);
+    const float Mv = symv(s.A, nv, lane, search, s.rowbuf);
     float jvc[4];
     CONTACT_PRODUCTS(search, jvc)
     const float jvf = search, jvl = lsign * search;
