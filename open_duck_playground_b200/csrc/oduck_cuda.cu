@@ -16,7 +16,9 @@
 #ifndef WPB
 #define WPB 8   // warps (= envs in flight) per CTA
 #endif
+#ifndef CTAS_PER_SM
 #define CTAS_PER_SM (WPB <= 8 ? 2 : 1)
+#endif
 // Thread ids behind an opaque move: ptxas otherwise rematerialises lane / warp / the warp's smem base (S2R + shifts + IMAD)
 // dozens of times per substep instead of keeping them in registers.
 __device__ __forceinline__ int opaque(int x) {

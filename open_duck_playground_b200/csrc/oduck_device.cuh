@@ -90,8 +90,8 @@ struct DevModel {
 // per-warp shared memory
 struct WarpSmem {
   float A[528];               // M, packed lower
-  float H[528];               // chol(M), then H = M + J^T D J and its factor
-  float bf[NLANE][8];         // staging for the M pair pass, one 32-byte record per dof: crb[body_i] * cdof_i (6) | armature | -
+  float H[528];               // chol(M), then H = M + J^T D J and its factor.  Its first 256 floats double as the staging records
+                              // of the M pair pass (crb[body_i] * cdof_i (6) | armature | - per dof): H is not live before M exists
   float xpos[3][NLANE];
   float xmat[9][NLANE];
   float cdof[NLANE][8];       // motion axis per dof, one 32-byte record: ang (3), lin (3), - , -  (read back as two float4)

@@ -208,13 +208,14 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
     GET(xx) GET(yy) GET(zz) GET(xy) GET(xz) GET(yz) GET(hx) GET(hy) GET(hz) GET(m)
 #undef GET
     const S6 buf = inert_mul(cb, cd);                                   // crb[body_i] * cdof_i, staged for the pair pass
-    *reinterpret_cast<float4*>(&s.bf[lane][0]) = make_float4(buf.a0, buf.a1, buf.a2, buf.l0);
-    *reinterpret_cast<float4*>(&s.bf[lane][4]) = make_float4(buf.l1, buf.l2, L.arm, 0.f);
+    float (*bf)[8] = reinterpret_cast<float (*)[8]>(s.H);           // staging records alias H (see WarpSmem)
+    *reinterpret_cast<float4*>(&bf[lane][0]) = make_float4(buf.a0, buf.a1, buf.a2, buf.l0);
+    *reinterpret_cast<float4*>(&bf[lane][4]) = make_float4(buf.l1, buf.l2, L.arm, 0.f);
     __syncwarp();
     for (int pp = lane; pp < m.n_mpairs; pp += 32) {
       const unsigned ij = m.mpair[pp];
       const int i = ij >> 8, j = ij & 255;
-      const float4 c0 = lds4(&s.cdof[j][0]), c1 = lds4(&s.cdof[j][4]), b0 = lds4(&s.bf[i][0]), b1 = lds4(&s.bf[i][4]);
+      const float4 c0 = lds4(&s.cdof[j][0]), c1 = lds4(&s.cdof[j][4]), b0 = lds4(&bf[i][0]), b1 = lds4(&bf[i][4]);
       float v = c0.x * b0.x + c0.y * b0.y + c0.z * b0.z + c0.w * b0.w + c1.x * b1.x + c1.y * b1.y;
       if (i == j) v += b1.z;
       s.A[TRI(i) + j] = v;

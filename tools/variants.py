@@ -17,16 +17,11 @@ sys.path.insert(0, ROOT)
 
 
 def build(specs):
-    from __graft_entry__ import NVCC_FLAGS
+    from __graft_entry__ import compile_library
     os.makedirs(VDIR, exist_ok=True)
-    cus = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")]
-    procs = []
     for spec in specs:
         name, _, flags = spec.partition("=")
-        out = os.path.join(VDIR, f"liboduck_cuda_{name}.so")
-        procs.append((name, subprocess.Popen(["nvcc", *NVCC_FLAGS, *flags.split(), "-o", out, *cus])))
-    for name, p in procs:
-        assert p.wait() == 0, name
+        compile_library(os.path.join(VDIR, f"liboduck_cuda_{name}.so"), flags.split())
         print("built", name)
 
 
