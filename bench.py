@@ -204,8 +204,20 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")        # keep stdout to the one JSON line if the box sets NCCL_DEBUG
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner to stdout when NCCL_DEBUG is set on the box: park fd 1 on stderr while the
+        # communicator comes up (device_id => eager init), so that stdout carries the one JSON line only
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     n = args.envs_per_gpu
     if args.mode == "ppo":
         return run_ppo(args, rank, world, dev)
