@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define ODUCK_ABI_VERSION 5
+#define ODUCK_ABI_VERSION 6
 
 #define ODUCK_MAX_BODY 20
 #define ODUCK_MAX_JNT 28
@@ -206,6 +206,8 @@ typedef struct OduckPolicyWeights {
   const float* obs_std;          /* [obs_dim] */
   const float* w[4];
   const float* b[4];
+  const float* packed[4];        /* optional (CUDA library): the kernels already in tensor-core operand form, as kept up to date by
+                                  * the device learner (oduck_ppo_packed_weights); NULL = the library packs w[] itself and caches it */
 } OduckPolicyWeights;
 
 typedef enum {

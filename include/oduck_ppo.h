@@ -95,6 +95,9 @@ int64_t oduck_ppo_num_params(const OduckPpo* p);
 int oduck_ppo_param_info(const OduckPpo* p, int net, int layer, int which, int64_t* offset, int64_t* rows, int64_t* cols);
 /* Copy flat parameters in (device pointer, layout above), reset Adam state if reset_opt != 0, and repack the GEMM operands. */
 int oduck_ppo_set_params(OduckPpo* p, const float* flat_params, int reset_opt, void* stream);
+/* The forward-pass operand form of one kernel matrix (hi/lo tf32 blocks), rewritten by every Adam step: hand it to
+ * OduckPolicyWeights.packed[] and the rollout actor reads the learner's weights without a repack or a copy. */
+int oduck_ppo_packed_weights(OduckPpo* p, int net, int layer, const float** ptr);
 /* Zero-copy view of a learner buffer: ptr, element count, dtype (ODUCK_DTYPE_*). */
 int oduck_ppo_get_buffer(OduckPpo* p, int id, void** ptr, int64_t* count, int* dtype);
 /* One SGD step on the minibatch made of env trajectories env_idx[0..B) (i32, device).  entropy_noise: optional f32

@@ -14,7 +14,7 @@ import numpy as np
 
 from .mjcf import CompiledModel
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_BODY, MAX_JNT, MAX_NQ, MAX_NV, MAX_NU, MAX_SITE, MAX_VERT, MAX_FACE, NFEET, NCMD = 20, 28, 36, 32, 16, 8, 32, 64, 2, 7
 OBS_STATE, OBS_PRIV, NMETRIC, REF_DIM, POLY_DEG, MAX_CON = 101, 212, 8, 40, 16, 12
 
@@ -73,7 +73,7 @@ class OduckEnvConfig(C.Structure):
 class OduckPolicyWeights(C.Structure):
     _fields_ = [
         ("obs_dim", i32), ("hidden", i32 * 3), ("out_dim", i32),
-        ("obs_mean", C.c_void_p), ("obs_std", C.c_void_p), ("w", C.c_void_p * 4), ("b", C.c_void_p * 4),
+        ("obs_mean", C.c_void_p), ("obs_std", C.c_void_p), ("w", C.c_void_p * 4), ("b", C.c_void_p * 4), ("packed", C.c_void_p * 4),
     ]
 
 
@@ -177,6 +177,7 @@ class Library:
             L.oduck_ppo_set_params.argtypes = [vp, vp, C.c_int, vp]
             L.oduck_ppo_get_buffer.argtypes = [vp, C.c_int, p(vp), p(C.c_int64), p(C.c_int)]
             L.oduck_ppo_minibatch.argtypes = [vp, p(OduckRollout), p(OduckNormalizer), vp, vp, vp, C.c_int, vp]
+            L.oduck_ppo_packed_weights.argtypes = [vp, C.c_int, C.c_int, p(vp)]
         if L.oduck_abi_version() != ABI_VERSION:
             raise OduckError(f"{path}: ABI version {L.oduck_abi_version()} != {ABI_VERSION}")
         if L.oduck_sizeof_model() != C.sizeof(OduckModel) or L.oduck_sizeof_env_config() != C.sizeof(OduckEnvConfig):
@@ -283,6 +284,11 @@ class PpoHandle:
         off, r, c = C.c_int64(), C.c_int64(), C.c_int64()
         self.L.check(self.L.lib.oduck_ppo_param_info(self.h, net, layer, which, C.byref(off), C.byref(r), C.byref(c)))
         return off.value, r.value, c.value
+
+    def packed_weights(self, net: int, layer: int) -> int:
+        ptr = C.c_void_p()
+        self.L.check(self.L.lib.oduck_ppo_packed_weights(self.h, net, layer, C.byref(ptr)))
+        return ptr.value
 
     def set_params(self, flat: int, reset_opt: bool, stream: int = 0):
         self.L.check(self.L.lib.oduck_ppo_set_params(self.h, flat, int(reset_opt), stream))

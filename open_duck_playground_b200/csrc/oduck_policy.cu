@@ -260,7 +260,8 @@ extern "C" int oduck_policy_forward(OduckHandle* h, const OduckPolicyWeights* w,
   }
   float* wbuf = h->policy_scratch; float* abuf = wbuf + woff[4];
   cudaError_t e = cudaSuccess;
-  if (h->policy_packed_for != w->w[0]) {          // new weight buffers (PolicyWeights.refresh hands out fresh ones): repack once
+  const bool prepacked = w->packed[0] && w->packed[1] && w->packed[2] && w->packed[3];   // the learner's operand blocks, always current
+  if (!prepacked && h->policy_packed_for != w->w[0]) {          // new weight buffers (PolicyWeights.refresh hands out fresh ones): repack once
     for (int l = 0; l < 4 && e == cudaSuccess; l++) {
       k_pack_weights<<<64, 256, 0, st>>>(w->w[l], wbuf + woff[l], dims[l], dims[l + 1], nts[l]);
       e = cudaGetLastError();
@@ -276,13 +277,13 @@ extern "C" int oduck_policy_forward(OduckHandle* h, const OduckPolicyWeights* w,
     // hidden layers: the learner's GEMM kernel (3-stage TMA ring, 8-warp epilogue) with the activation-only epilogue
     GemmParams g;
     memset(&g, 0, sizeof(g));
-    g.A = abuf + aoff[l]; g.B = wbuf + woff[l];
+    g.A = abuf + aoff[l]; g.B = prepacked ? w->packed[l] : wbuf + woff[l];
     g.nchunks = (dims[l] + TC_KC - 1) / TC_KC; g.cps = g.nchunks;
     g.bias = w->b[l]; g.nvalid = dims[l + 1];
     g.Yr = abuf + aoff[l + 1]; g.yr_nch = dims[l + 1] / TC_KC;
     e = launch_gemm<128, 3, EPI_ACT>(g, mtiles, dims[l + 1] / 128, false, st);
   }
-  d.Xb = abuf + aoff[3]; d.Wb = wbuf + woff[3]; d.B = w->b[3]; d.Yb = nullptr; d.K = dims[3]; d.N = dims[4];
+  d.Xb = abuf + aoff[3]; d.Wb = prepacked ? w->packed[3] : wbuf + woff[3]; d.B = w->b[3]; d.Yb = nullptr; d.K = dims[3]; d.N = dims[4];
   d.keys = keys; d.action = action; d.raw = raw_action; d.logp = log_prob; d.deterministic = deterministic; d.na = w->out_dim / 2;
   if (e == cudaSuccess) e = launch_dense<32, true>(d, st);
   if (e != cudaSuccess) return oduck_fail(ODUCK_ERR_CUDA, std::string("oduck_policy_forward launch: ") + cudaGetErrorString(e));

@@ -727,6 +727,12 @@ int oduck_ppo_param_info(const OduckPpo* h, int net, int layer, int which, int64
   return ODUCK_OK;
 }
 
+int oduck_ppo_packed_weights(OduckPpo* h, int net, int layer, const float** ptr) {
+  if (!h || net < 0 || net > 1 || layer < 0 || layer >= PPO_NL || !ptr) return oduck_fail(ODUCK_ERR_ARG, "oduck_ppo_packed_weights: bad argument");
+  *ptr = h->packed + h->seg.s[(net * PPO_NL + layer) * 2].wf;
+  return ODUCK_OK;
+}
+
 static int launch_adam(OduckPpo* h, int update, cudaStream_t st) {
   const OduckPpoConfig& c = h->cfg;
   k_ppo_adam<<<h->reduce_blocks, 256, 0, st>>>(h->dseg, h->params, h->grads, h->adam_m, h->adam_v, h->packed, h->sumsq_part, h->reduce_blocks, h->step,

@@ -106,9 +106,10 @@ class RunningStats:
 class PolicyWeights:
     """Packs a policy MLP + normaliser into ``OduckPolicyWeights`` (row-major [in][out] kernels like flax)."""
 
-    def __init__(self, policy: MLP, obs_dim: int, device, external=None):
+    def __init__(self, policy: MLP, obs_dim: int, device, external=None, packed=None):
         self.policy, self.device = policy, device
         self.external = external          # [(W [in][out], b)] x 4 views of the device learner's master weights (updated in place)
+        self.packed = packed              # [ptr] x 4: the learner's tensor-core operand blocks (always current: no repack, no copy)
         self.struct = capi.OduckPolicyWeights()
         self.struct.obs_dim = obs_dim
         hs = [l.out_features for l in policy.layers]
@@ -128,6 +129,7 @@ class PolicyWeights:
         self.struct.obs_mean, self.struct.obs_std = self.mean.data_ptr(), self.std.data_ptr()
         for i in range(4):
             self.struct.w[i], self.struct.b[i] = self.w[i].data_ptr(), self.b[i].data_ptr()
+            self.struct.packed[i] = self.packed[i] if self.packed else None
 
 
 def policy_forward(env, weights: PolicyWeights, keys: Optional[torch.Tensor], deterministic: bool, obs: Optional[torch.Tensor] = None):
@@ -250,6 +252,9 @@ class DeviceLearner:
     def policy_views(self):
         return [(self.tensor(0, l, 0), self.tensor(0, l, 1)) for l in range(4)]
 
+    def policy_packed(self):
+        return [self.h.packed_weights(0, l) for l in range(4)]
+
     def minibatch(self, rollout: "capi.OduckRollout", norm: "capi.OduckNormalizer", env_idx: int, noise: int = 0, key: int = 0, stages: int = capi.PPO_ALL) -> None:
         self.h.minibatch(rollout, norm, env_idx, noise, key, stages, self._stream())
 
@@ -288,7 +293,9 @@ class PPOTrainer:
             n_update = self.n_local if (mode == "sharded" and world > 1) else cfg.num_envs
             self.dev_learner = DeviceLearner(cfg, self.policy, self.value, n_update // cfg.num_minibatches, na, dev)
         self.weights = PolicyWeights(self.policy, env.observation_size[cfg.policy_obs_key][0], dev,
-                                     external=self.dev_learner.policy_views() if self.dev_learner else None)
+                                     external=self.dev_learner.policy_views() if self.dev_learner else None,
+                                     packed=self.dev_learner.policy_packed() if self.dev_learner else None)
+        self._roll = None                 # persistent rollout buffers + CUDA graphs (device learner on CUDA)
         self._ones = {k: torch.ones(env.observation_size[k][0], device=dev) for k in self.stats}
         self._zeros = {k: torch.zeros(env.observation_size[k][0], device=dev) for k in self.stats}
         self.key = jr.PRNGKey(cfg.seed + 17)
@@ -298,27 +305,77 @@ class PPOTrainer:
         self.timing = {"rollout_ms": 0.0, "gather_ms": 0.0, "update_ms": 0.0}
 
     # ------------------------------------------------------------------ A17: unroll
+    def _rollout_keys(self) -> np.ndarray:
+        """Sampling keys of one unroll, [T, n_local, 2]: split(step_key_t, world * n) sliced per rank (independent of the GPU count)."""
+        T, n = self.cfg.unroll_length, self.n_local
+        self.key, sub = jr.split(self.key, 2)
+        step_keys = jr.split(sub, T)
+        return np.ascontiguousarray(jr.split(step_keys, self.world * n)[:, self.rank * n:(self.rank + 1) * n]).view(np.int32)
+
+    def _new_buffers(self) -> Dict[str, torch.Tensor]:
+        cfg, env = self.cfg, self.env
+        T, n, dev = cfg.unroll_length, self.n_local, env.device
+        pk, vk = cfg.policy_obs_key, cfg.value_obs_key
+        return {"obs_p": torch.empty(T + 1, n, env.observation_size[pk][0], device=dev), "obs_v": torch.empty(T + 1, n, env.observation_size[vk][0], device=dev),
+                "raw": torch.empty(T, n, env.action_size, device=dev), "logp": torch.empty(T, n, device=dev), "reward": torch.empty(T, n, device=dev),
+                "done": torch.empty(T, n, device=dev), "trunc": torch.empty(T, n, device=dev)}
+
+    def _rollout_step(self, buf, t, st, keys_t):
+        pk, vk = self.cfg.policy_obs_key, self.cfg.value_obs_key
+        buf["obs_p"][t].copy_(st.obs[pk]); buf["obs_v"][t].copy_(st.obs[vk])
+        act, raw, logp = policy_forward(self.env, self.weights, keys_t, deterministic=False)
+        st = self.env.step(st, act)
+        buf["raw"][t].copy_(raw); buf["logp"][t].copy_(logp)
+        buf["reward"][t].copy_(st.reward); buf["done"][t].copy_(st.done); buf["trunc"][t].copy_(st.info["truncation"])
+        return st
+
     def rollout(self) -> Dict[str, torch.Tensor]:
         cfg, env = self.cfg, self.env
         T, n = cfg.unroll_length, self.n_local
-        dev = env.device
         pk, vk = cfg.policy_obs_key, cfg.value_obs_key
-        buf = {"obs_p": torch.empty(T + 1, n, env.observation_size[pk][0], device=dev), "obs_v": torch.empty(T + 1, n, env.observation_size[vk][0], device=dev),
-               "raw": torch.empty(T, n, env.action_size, device=dev), "logp": torch.empty(T, n, device=dev), "reward": torch.empty(T, n, device=dev),
-               "done": torch.empty(T, n, device=dev), "trunc": torch.empty(T, n, device=dev)}
-        st = self.state
-        mean, std = (self.stats[pk].mean32, self.stats[pk].std) if cfg.normalize_observations else (torch.zeros_like(self.stats[pk].std), torch.ones_like(self.stats[pk].std))
+        graphed = self.dev_learner is not None and cfg.cuda_graph and env.device.type == "cuda"
+        if graphed:
+            # static normaliser buffers (updated in place by update()), static weights (the learner's own): capturable
+            mean, std = (self._mean32[pk], self.stats[pk].std) if cfg.normalize_observations else (self._zeros[pk], self._ones[pk])
+        else:
+            mean, std = (self.stats[pk].mean32, self.stats[pk].std) if cfg.normalize_observations else (torch.zeros_like(self.stats[pk].std), torch.ones_like(self.stats[pk].std))
         self.weights.refresh(mean, std)
-        self.key, sub = jr.split(self.key, 2)
-        step_keys = jr.split(sub, T)
-        for t in range(T):
-            buf["obs_p"][t].copy_(st.obs[pk]); buf["obs_v"][t].copy_(st.obs[vk])
-            keys = jr.split(step_keys[t], self.world * n)[self.rank * n:(self.rank + 1) * n]
-            act, raw, logp = policy_forward(env, self.weights, torch.from_numpy(keys.view(np.int32)), deterministic=False)
-            st = env.step(st, act)
-            buf["raw"][t].copy_(raw); buf["logp"][t].copy_(logp)
-            buf["reward"][t].copy_(st.reward); buf["done"][t].copy_(st.done); buf["trunc"][t].copy_(st.info["truncation"])
-        buf["obs_p"][T].copy_(st.obs[pk]); buf["obs_v"][T].copy_(st.obs[vk])
+        keys = self._rollout_keys()
+        st = self.state
+        if not graphed:
+            buf = self._new_buffers()
+            for t in range(T):
+                st = self._rollout_step(buf, t, st, torch.from_numpy(keys[t]))
+            buf["obs_p"][T].copy_(st.obs[pk]); buf["obs_v"][T].copy_(st.obs[vk])
+            self.state = st
+            return buf
+        # CUDA-graph path: the T steps of an unroll are captured once (per-step graphs over persistent buffers); an unroll is
+        # then one key upload + T replays, which keeps the ranks kernel-bound when many of them share the host's cores
+        if self._roll is None:
+            R = {"buf": self._new_buffers(), "keys": torch.empty(T, n, 2, dtype=torch.int32, device=env.device),
+                 "host_keys": torch.empty(T, n, 2, dtype=torch.int32).pin_memory(), "graphs": None}
+            self._roll = R
+        R = self._roll
+        R["host_keys"].copy_(torch.from_numpy(keys))
+        R["keys"].copy_(R["host_keys"], non_blocking=True)
+        buf = R["buf"]
+        if R["graphs"] is None:
+            for t in range(T):                               # first unroll: eager (also warms every kernel up before the capture)
+                st = self._rollout_step(buf, t, st, R["keys"][t])
+            buf["obs_p"][T].copy_(st.obs[pk]); buf["obs_v"][T].copy_(st.obs[vk])
+            torch.cuda.synchronize(env.device)
+            pool, graphs = torch.cuda.graph_pool_handle(), []
+            for t in range(T):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    self._rollout_step(buf, t, st, R["keys"][t])
+                    if t == T - 1:
+                        buf["obs_p"][T].copy_(st.obs[pk]); buf["obs_v"][T].copy_(st.obs[vk])
+                graphs.append(g)
+            R["graphs"] = graphs
+        else:
+            for g in R["graphs"]:
+                g.replay()
         self.state = st
         return buf
 

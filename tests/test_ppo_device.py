@@ -253,3 +253,21 @@ def test_trainer_device_learner_tracks_torch_learner():
     # (sign-like first steps amplify the entropy-noise difference on individual near-zero-gradient elements)
     assert (pt - pd_).abs().mean().item() < 1e-4 and (vt - vd).abs().mean().item() < 1e-4
     assert (pt - pd_).abs().max().item() < 2.5e-3 and (vt - vd).abs().max().item() < 2.5e-3
+
+
+@pytest.mark.gpu
+def test_graphed_rollout_equals_eager_rollout():
+    """The CUDA-graph unroll (per-step graphs over persistent buffers, the learner's packed weights shared with the actor)
+    replays the same launches as the eager loop: identical parameters after three training steps."""
+    from open_duck_playground_b200.joystick import Joystick
+    out = {}
+    for graph in (False, True):
+        env = Joystick("flat_terrain_backlash", device="cuda:0")
+        cfg = ppo.PPOConfig(num_envs=256, unroll_length=4, num_minibatches=2, num_updates_per_batch=1, learner="device", cuda_graph=graph)
+        tr = ppo.PPOTrainer(env, cfg)
+        for _ in range(3):
+            m = tr.training_step()
+        torch.cuda.synchronize()
+        out[graph] = (tr.dev_learner.params.clone(), tr._roll["buf"]["reward"].clone() if graph else None, m)
+        assert math.isfinite(m["loss"])
+    assert torch.equal(out[False][0], out[True][0])
