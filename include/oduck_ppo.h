@@ -73,6 +73,8 @@ typedef struct OduckPpo OduckPpo;
 #define ODUCK_PPO_STAGE_ADAM 8      /* global-norm clip + Adam + weight repack       -> buffer PARAMS */
 #define ODUCK_PPO_ALL 15
 #define ODUCK_PPO_DEBUG_SIMT 256    /* run the GEMMs on CUDA cores (same operands, same epilogues): bisects tcgen05 problems */
+#define ODUCK_PPO_NO_COOP 512       /* use the two-kernel reduce + Adam tail instead of the fused cooperative launch (for callers
+                                     * that capture the call into a CUDA graph and prefer plain kernel nodes) */
 
 typedef enum {
   ODUCK_PPO_BUF_PARAMS = 0,   /* f32 [P]  master weights, flat: for net in (policy, value): for layer: W[in][out] (flax), b[out] */

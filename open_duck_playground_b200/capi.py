@@ -100,7 +100,7 @@ class OduckNormalizer(C.Structure):
     _fields_ = [("policy_mean", C.c_void_p), ("policy_std", C.c_void_p), ("value_mean", C.c_void_p), ("value_std", C.c_void_p)]
 
 
-PPO_STAGE_FORWARD, PPO_STAGE_LOSS, PPO_STAGE_BACKWARD, PPO_STAGE_ADAM, PPO_ALL, PPO_DEBUG_SIMT = 1, 2, 4, 8, 15, 256
+PPO_STAGE_FORWARD, PPO_STAGE_LOSS, PPO_STAGE_BACKWARD, PPO_STAGE_ADAM, PPO_ALL, PPO_DEBUG_SIMT, PPO_NO_COOP = 1, 2, 4, 8, 15, 256, 512
 PPO_BUF = {name: k for k, name in enumerate(["PARAMS", "GRADS", "ADAM_M", "ADAM_V", "LOGITS", "VALUES", "LOSSES", "ADV", "VS", "STEP"])}
 
 BUF = {name: k for k, name in enumerate([

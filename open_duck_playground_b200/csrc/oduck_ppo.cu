@@ -895,7 +895,7 @@ int oduck_ppo_minibatch(OduckPpo* h, const OduckRollout* ro, const OduckNormaliz
     if (rc) return rc;
     JOIN()
     for (int k = 0; k < 2; ++k) { PPO_TRY(cudaEventRecord(h->ev_join_w[k], h->side_w[k])); PPO_TRY(cudaStreamWaitEvent(st, h->ev_join_w[k], 0)); }
-    if ((stages & ODUCK_PPO_STAGE_ADAM) && h->coop_blocks > 0) {
+    if ((stages & ODUCK_PPO_STAGE_ADAM) && h->coop_blocks > 0 && !(stages & ODUCK_PPO_NO_COOP)) {
       // product path on one GPU: gradient reduce, global norm and Adam in one cooperative launch (grid barrier in between)
       const OduckPpoConfig& cc = h->cfg;
       const SegTable* a0 = h->dseg; const float* a1 = h->partial; float* a2 = h->grads; float* a3 = h->sumsq_part; float* a4 = h->params; float* a5 = h->adam_m;

@@ -512,14 +512,47 @@ class PPOTrainer:
             sub = jr.split(sub, self.world)[self.rank]
         keys = torch.from_numpy(jr.split(sub, n_mb).view(np.int32).copy()).to(dev)        # entropy-sample keys, one per minibatch
         keep = [keys]
+        FLB = capi.PPO_STAGE_FORWARD | capi.PPO_STAGE_LOSS | capi.PPO_STAGE_BACKWARD
+        # The minibatch step reads a static index / key buffer and is captured once into CUDA graphs (the library forks and
+        # joins its side streams inside the capture); a minibatch is then two small copies + one replay (two around the
+        # gradient all-reduce when sharded).  Only with the persistent rollout buffers of the graphed unroll (static pointers).
+        graphed = cfg.cuda_graph and self._roll is not None and batch is self._roll["buf"]
+        if graphed and getattr(self, "_upd", None) is None:
+            U = {"idx": torch.zeros(B, dtype=torch.int32, device=dev), "key": torch.zeros(2, dtype=torch.int32, device=dev), "ro": ro, "nm": nm}
+            stages = [FLB, capi.PPO_STAGE_ADAM] if sharded else [capi.PPO_ALL | capi.PPO_NO_COOP]     # plain kernel nodes only
+            try:
+                L.minibatch(ro, nm, U["idx"].data_ptr(), 0, U["key"].data_ptr(), capi.PPO_STAGE_FORWARD)    # warm-up outside the capture
+                torch.cuda.synchronize(dev)
+                U["graphs"] = []
+                for stg in stages:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        L.minibatch(ro, nm, U["idx"].data_ptr(), 0, U["key"].data_ptr(), stg)
+                    U["graphs"].append(g)
+            except Exception as e:                                                       # capture unsupported (e.g. cooperative launch): stay eager
+                import sys
+                print(f"[ppo] minibatch graph capture unavailable ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
+                U["graphs"] = None
+            self._upd = U
+        U = getattr(self, "_upd", None) if graphed else None
         for e in range(cfg.num_updates_per_batch):
             perm = torch.randperm(N, generator=gen).to(torch.int32).to(dev)
             keep.append(perm)
             for i in range(cfg.num_minibatches):
+                j = e * cfg.num_minibatches + i
+                if U is not None and U["graphs"]:
+                    U["idx"].copy_(perm[i * B:(i + 1) * B], non_blocking=True)
+                    U["key"].copy_(keys[j], non_blocking=True)
+                    U["graphs"][0].replay()
+                    if sharded:
+                        dist.all_reduce(L.grads)
+                        L.grads.div_(self.world)
+                        U["graphs"][1].replay()
+                    continue
                 idx = perm.data_ptr() + 4 * i * B
-                key = keys.data_ptr() + 8 * (e * cfg.num_minibatches + i)
+                key = keys.data_ptr() + 8 * j
                 if sharded:
-                    L.minibatch(ro, nm, idx, 0, key, capi.PPO_STAGE_FORWARD | capi.PPO_STAGE_LOSS | capi.PPO_STAGE_BACKWARD)
+                    L.minibatch(ro, nm, idx, 0, key, FLB)
                     dist.all_reduce(L.grads)
                     L.grads.div_(self.world)
                     L.minibatch(ro, nm, idx, 0, key, capi.PPO_STAGE_ADAM)
