@@ -258,7 +258,7 @@ def test_trainer_device_learner_tracks_torch_learner():
 @pytest.mark.gpu
 def test_graphed_rollout_equals_eager_rollout():
     """The CUDA-graph unroll (per-step graphs over persistent buffers, the learner's packed weights shared with the actor)
-    replays the same launches as the eager loop: identical parameters after three training steps."""
+    replays the same launches as the eager loop: the same parameters after three training steps."""
     from open_duck_playground_b200.joystick import Joystick
     out = {}
     for graph in (False, True):
@@ -270,4 +270,5 @@ def test_graphed_rollout_equals_eager_rollout():
         torch.cuda.synchronize()
         out[graph] = (tr.dev_learner.params.clone(), tr._roll["buf"]["reward"].clone() if graph else None, m)
         assert math.isfinite(m["loss"])
-    assert torch.equal(out[False][0], out[True][0])
+    # (the graphed update uses the two-kernel reduce + Adam tail: same gradients, the global norm is summed in another grouping)
+    assert (out[False][0] - out[True][0]).abs().max().item() < 1e-6
