@@ -307,6 +307,10 @@ class PPOTrainer:
     # ------------------------------------------------------------------ A17: unroll
     def _rollout_keys(self) -> np.ndarray:
         """Sampling keys of one unroll, [T, n_local, 2]: split(step_key_t, world * n) sliced per rank (independent of the GPU count)."""
+        pre = getattr(self, "_prefetched_keys", None)
+        if pre is not None:                                   # made while the GPU was busy with the previous update
+            self._prefetched_keys = None
+            return pre
         T, n = self.cfg.unroll_length, self.n_local
         self.key, sub = jr.split(self.key, 2)
         step_keys = jr.split(sub, T)
@@ -559,6 +563,7 @@ class PPOTrainer:
                 else:
                     L.minibatch(ro, nm, idx, 0, key, capi.PPO_ALL)
         self.env.handle.policy_invalidate()                                                # the actor repacks the new weights on its next forward
+        self._prefetched_keys = self._rollout_keys()                                       # host work of the next unroll, under the GPU's update
         o = L.losses.tolist()                                                              # host sync: the update is done, `keep` may go
         del keep
         return dict(loss=o[0], policy_loss=o[1], v_loss=o[2], entropy=o[3], clip_fraction=o[5])
