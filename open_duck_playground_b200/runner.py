@@ -47,6 +47,11 @@ class BaseRunner:
         path = f"{self.output_dir}/{d}_{current_step}.pt"
         print(f"Saving checkpoint (step: {current_step}): {path}")
         torch.save(params, path)
+        # deployment format like common/runner.py:76-84: an ONNX policy next to every checkpoint (input obs[1, obs_size])
+        from .export_onnx import brax_param_tree, export_onnx
+        hidden = [int(v.shape[0]) for k, v in params["policy"].items() if k.endswith(".weight")][:-1]
+        export_onnx(brax_param_tree(params, params.get("policy_obs_key", "state")), self.action_size, hidden, self.obs_size,
+                    output_path=f"{self.output_dir}/{d}_{current_step}.onnx", obs_key=params.get("policy_obs_key", "state"))
 
     def train(self) -> None:
         cfg = PPOConfig(num_timesteps=self.num_timesteps)      # BerkeleyHumanoidJoystickFlatTerrain table (common/runner.py:87-89)
