@@ -12,6 +12,7 @@
 
 #include "../../include/oduck.h"
 #include "oduck_env.cuh"
+#include "oduck_policy_tc.cuh"   // mbarrier helpers
 
 #ifndef WPB
 #define WPB 8   // warps (= envs in flight) per CTA
@@ -43,17 +44,24 @@ static int fail(int code, const std::string& msg) { return oduck_fail(code, msg)
 __device__ __forceinline__ size_t smem_model_bytes() { return (sizeof(DevModel) + 15) & ~(size_t)15; }
 __device__ __forceinline__ size_t smem_cfg_bytes() { return (sizeof(DevEnvCfg) + 15) & ~(size_t)15; }
 
+// Batch-shared tables (DevModel ~18 KB, DevEnvCfg) -> shared memory: two TMA bulk copies issued by one thread, completion on
+// an mbarrier (cp.async.bulk + expect_tx; SASS UBLKCP) instead of an 18-trip load/store loop in all 256 threads.
 __device__ __forceinline__ void block_load_tables(const Params& p, unsigned char* raw, DevModel*& m, DevEnvCfg*& c, WarpSmem*& ws) {
+  __shared__ __align__(8) uint64_t bar;
   m = reinterpret_cast<DevModel*>(raw);
   c = reinterpret_cast<DevEnvCfg*>(raw + smem_model_bytes());
   ws = reinterpret_cast<WarpSmem*>(raw + smem_model_bytes() + smem_cfg_bytes());
-  const int* gm = reinterpret_cast<const int*>(p.model);
-  int* sm = reinterpret_cast<int*>(m);
-  for (int i = threadIdx.x; i < (int)(sizeof(DevModel) / 4); i += blockDim.x) sm[i] = gm[i];
-  const int* gc = reinterpret_cast<const int*>(p.cfg);
-  int* sc = reinterpret_cast<int*>(c);
-  for (int i = threadIdx.x; i < (int)(sizeof(DevEnvCfg) / 4); i += blockDim.x) sc[i] = gc[i];
-  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(&bar)), "r"((uint32_t)(sizeof(DevModel) + sizeof(DevEnvCfg))) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(m)), "l"(p.model), "r"((uint32_t)sizeof(DevModel)), "r"(smem_u32(&bar)) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(c)), "l"(p.cfg), "r"((uint32_t)sizeof(DevEnvCfg)), "r"(smem_u32(&bar)) : "memory");
+  }
+  __syncthreads();                                     // the barrier is initialised before anyone polls it
+  mbar_wait(&bar, 0u);
 }
 
 __device__ __forceinline__ void load_env(const DevModel& m, WarpSmem& s, Lane& L, int lane, const float* __restrict__ ph, const float* __restrict__ dr) {

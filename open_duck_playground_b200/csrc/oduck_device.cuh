@@ -47,7 +47,7 @@
 #define DF_LIMITED 8
 #define DF_FLOSS 16
 
-struct DevModel {
+struct alignas(16) DevModel {   // 16-byte multiple: staged into shared memory with one TMA bulk copy per CTA
   int nbody, njnt, nq, nv, nu, maxdepth, prefix_rounds, nfr, nlim, nvert, enable_ff;
   int imu_body, foot_body[2], foot_site_body[2], foot_chain[2];  // foot_chain: dof bitmask of the foot's ancestor chain
   int imu_chain;

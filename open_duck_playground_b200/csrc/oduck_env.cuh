@@ -26,7 +26,7 @@
 #define INFO_PHASE 208
 #define MAX_DELAY 4
 
-struct DevEnvCfg {
+struct alignas(16) DevEnvCfg {
   int task;                  // ODUCK_TASK_JOYSTICK / ODUCK_TASK_STANDING
   float sc_orient, sc_head, reset_qvel_noise;
   int n_substeps, episode_length, use_imitation, use_speed_limits, push_enable, act_min_delay, act_max_delay, imu_min_delay, imu_max_delay, auto_reset;

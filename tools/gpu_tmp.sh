@@ -1,3 +1,1 @@
-timeout 900 python -m pytest tests/test_ppo_device.py -m gpu -q > gpurun_out/r01q_pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/r01q_pytest_gpu.log; tail -6 gpurun_out/r01q_pytest_gpu.log
-python bench.py --mode ppo --steps 100 --warmup 2 2>gpurun_out/r01q_ppo.err | tee gpurun_out/r01q_bench_ppo.json; tail -3 gpurun_out/r01q_ppo.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --mode ppo --steps 100 --warmup 2 2> gpurun_out/r01q_bench_ppo_n2.err | tee gpurun_out/r01q_bench_ppo_n2.json; tail -3 gpurun_out/r01q_bench_ppo_n2.err | cut -c1-300
+python tools/variants.py bench --steps 200 --warmup 20 --no-cpu-baseline
