@@ -243,7 +243,6 @@ def main():
     # e2e staging: per step the host receives obs["state"] (what a host-side learner stores per transition) and
     # [raw action 14 | log-prob | reward | done]; two device staging slots + two pinned host slots so that the D2H of step k
     # (copy stream) overlaps the compute of step k+1 -- the host still consumes every step's result inside the timed region.
-    stage = [torch.empty(n, 101 + 17, device=dev) for _ in range(2)]
     host_out = [torch.empty(n, 101 + 17).pin_memory() for _ in range(2)]
     copy_stream = torch.cuda.Stream(device=dev)
     ev_ready = [torch.cuda.Event() for _ in range(2)]
@@ -288,19 +287,30 @@ def main():
         ev_done[slot].synchronize()
         host_sink = host_sink + host_out[slot][0, 101 + 15]              # the host reads the delivered result (a reward)
 
+    # e2e step: the device part (actor + env.step + packing of the outgoing record) is a CUDA graph per env set as well; around it
+    # the step uploads this step's keys from pinned memory and downloads the record of the step on the copy stream
+    stage_set = [torch.empty(n, 101 + 17, device=dev) for _ in range(n_sets)]
+    graphs_e2e = []
+
+    def capture_graphs_e2e():
+        for s_ in range(n_sets):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                act, raw, logp = ppo.policy_forward(envs[s_], weights, key_static, deterministic=False)
+                st = envs[s_].step(None, act)
+                sg = stage_set[s_]
+                sg[:, :101] = st.obs["state"]; sg[:, 101:115] = raw; sg[:, 115] = logp; sg[:, 116] = st.reward; sg[:, 117] = st.done
+            graphs_e2e.append(g)
+
     def step_e2e(k):
-        e = envs[k % n_sets]
         slot = k & 1
         main = torch.cuda.current_stream(dev)
-        kd = host_keys[k % n_keys].to(dev, non_blocking=True)           # H2D: this step's sampling keys (pinned)
-        act, raw, logp = ppo.policy_forward(e, weights, kd, deterministic=False)
-        st = e.step(None, act)
-        sg = stage[slot]                                                # its previous D2H (step k-2) was consumed at step k-1
-        sg[:, :101] = st.obs["state"]; sg[:, 101:115] = raw; sg[:, 115] = logp; sg[:, 116] = st.reward; sg[:, 117] = st.done
+        key_static.copy_(host_keys[k % n_keys], non_blocking=True)      # H2D: this step's sampling keys (pinned)
+        graphs_e2e[k % n_sets].replay()
         ev_ready[slot].record(main)
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(ev_ready[slot])
-            host_out[slot].copy_(sg, non_blocking=True)                 # D2H on the copy stream
+            host_out[slot].copy_(stage_set[k % n_sets], non_blocking=True)   # D2H on the copy stream (pinned)
             ev_done[slot].record(copy_stream)
         if k > 0:
             consume(slot ^ 1)                                           # host waits for (and reads) step k-1 while step k runs
@@ -345,6 +355,7 @@ def main():
     timed(step_eager, eager_steps)
     ms_kstep = sum(a.elapsed_time(b) for a, b in kstep_events) / len(kstep_events)   # average k_step launch duration, on its stream
     launches = (sum(e.handle.launch_count() for e in envs) - l0) * args.steps // eager_steps
+    capture_graphs_e2e()
     for k in range(4):
         step_e2e(k)
     torch.cuda.synchronize()
