@@ -338,8 +338,8 @@ def main():
     except Exception:
         pass
     sampler = ClockSampler(local, uuid)
-    for k in range(max(3, args.warmup)):
-        step_eager(k)
+    for k in range(max(3, args.warmup, n_sets)):                        # every env set runs eagerly at least once before the capture
+        step_eager(k)                                                   # (first use of a handle sizes its actor scratch: an allocation)
     torch.cuda.synchronize()
     capture_graphs()
     for k in range(n_sets):
