@@ -1,4 +1,5 @@
-timeout 900 python -m pytest tests/test_parity_gpu.py tests/test_standing.py -m gpu -q > gpurun_out/r01r_pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/r01r_pytest_gpu.log; tail -4 gpurun_out/r01r_pytest_gpu.log
-python bench.py --steps 300 --warmup 30 --no-cpu-baseline > gpurun_out/r01r_bench_n1.json 2>gpurun_out/r01r_bench_n1.err; python -c "
-import json; d=json.loads([l for l in open('gpurun_out/r01r_bench_n1.json') if l.startswith('{')][-1]); print('value', d['value'], 'ms', d['ms_per_step'], 'kstep', d['roofline']['kernel_ms'], 'e2e', d['e2e']['value'])"
-python tools/variants.py bench --steps 200 --warmup 20 --no-cpu-baseline
+o=gpurun_out; tag=r01z
+timeout 600 python tools/sweep.py > $o/${tag}_sweep_n1.jsonl 2> $o/${tag}_sweep_n1.err; cat $o/${tag}_sweep_n1.jsonl | cut -c1-200
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $o/${tag}_launches_rollout.csv python bench.py --steps 8 --warmup 3 --no-cpu-baseline > $o/${tag}_launches_rollout.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_step -s 12 -c 1 -o $o/${tag}_k_step -f python bench.py --steps 6 --warmup 3 --no-cpu-baseline > $o/${tag}_ncu_k_step.log 2>&1
+ls -la $o | grep ${tag}_k_step
