@@ -426,21 +426,44 @@ __device__ __forceinline__ double warp_total(const float* __restrict__ part, int
   return t;
 }
 
+// Bias gradients: element j of a bias tensor is the sum of one partial per producer row block (168 - 336 of them); one warp
+// per element, partial rows spread over the lanes, shuffle tree in a fixed order (deterministic).  A thread-per-element loop
+// would chain up to 42 dependent load batches on the few threads that own a bias element.
+__device__ __forceinline__ void reduce_biases(const SegTable& tb, const float* __restrict__ partial, float* __restrict__ grads, double& ss) {
+  const int lane = threadIdx.x & 31;
+  const int wid = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), nw = (int)((gridDim.x * blockDim.x) >> 5);
+  int total = 0;
+  for (int k = 0; k < tb.n; ++k) if (tb.s[k].bias) total += tb.s[k].N;
+  for (int b = wid; b < total; b += nw) {
+    int k = 0, j = b;
+    for (;; ++k) { if (!tb.s[k].bias) continue; if (j < tb.s[k].N) break; j -= tb.s[k].N; }
+    const Seg& sg = tb.s[k];
+    const float* q = partial + sg.dbpart + j;
+    float g = 0.f;
+    for (int w = lane; w < sg.nwarprows; w += 32) g += __ldcg(q + (size_t)w * sg.ldb);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+    if (lane == 0) { grads[sg.off + j] = g; ss += (double)g * g; }
+  }
+}
+
 // Single-GPU product path: gradient reduce -> grid barrier -> global-norm clip + Adam + repack, one cooperative launch.
 // Work unit = a quad of 4 consecutive flat elements (every tensor starts 4-aligned and, except the 1-wide value head, has a
 // multiple-of-4 row length): the split-K partials come in as float4 loads, all splits of a quad in flight at once (the
 // phase is latency-bound otherwise), and the gradients stay in registers across the barrier.
 #define RA_QUADS 2
-__device__ __forceinline__ float4 reduce_quad(const SegTable& tb, const float* __restrict__ partial, long long i0, bool& vec) {
+// kernel-matrix elements only: bias elements return 0 with their bit set in `skip` (reduce_biases owns them)
+__device__ __forceinline__ float4 reduce_quad(const SegTable& tb, const float* __restrict__ partial, long long i0, unsigned& skip) {
   const Seg& s = find_seg(tb, i0);
   const unsigned j = (unsigned)(i0 - s.off);
   const unsigned len = s.bias ? (unsigned)s.N : (unsigned)s.K * (unsigned)s.N;
-  vec = (s.N & 3) == 0 && (j & 3) == 0 && j + 4 <= len;
+  const bool vec = (s.N & 3) == 0 && (j & 3) == 0 && j + 4 <= len;
   float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+  skip = 0u;
+  if (vec && s.bias) { skip = 15u; return g; }
   if (vec) {
     const float* q; long long stride; int cnt;
-    if (!s.bias) { const unsigned k = j / (unsigned)s.N, n = j - k * (unsigned)s.N; q = partial + s.dwpart + (size_t)k * s.ldo + n; stride = s.split_stride; cnt = s.nsplit; }
-    else { q = partial + s.dbpart + j; stride = s.ldb; cnt = s.nwarprows; }
+    { const unsigned k = j / (unsigned)s.N, n = j - k * (unsigned)s.N; q = partial + s.dwpart + (size_t)k * s.ldo + n; stride = s.split_stride; cnt = s.nsplit; }
     float4 a0 = g, a1 = g;
     int z = 0;
     for (; z + 8 <= cnt; z += 8) {
@@ -459,7 +482,10 @@ __device__ __forceinline__ float4 reduce_quad(const SegTable& tb, const float* _
     float* pg = reinterpret_cast<float*>(&g);
     for (int e = 0; e < 4; ++e) {
       const long long i = i0 + e;
-      if (i < tb.total) { const Seg& se = find_seg(tb, i); pg[e] = reduce_partials(se, partial, i - se.off); }
+      if (i >= tb.total) { skip |= 1u << e; continue; }
+      const Seg& se = find_seg(tb, i);
+      if (se.bias) skip |= 1u << e;
+      else pg[e] = reduce_partials(se, partial, i - se.off);
     }
   }
   return g;
@@ -478,12 +504,12 @@ __global__ void __launch_bounds__(256) k_ppo_reduce_adam(const SegTable* __restr
   float4 g[RA_QUADS];
   double ss = 0.0;
   auto quad_grad = [&](long long qd) {
-    bool vec;
-    const float4 x = reduce_quad(tb, partial, qd * 4, vec);
+    unsigned skip;
+    const float4 x = reduce_quad(tb, partial, qd * 4, skip);
     const float* px = reinterpret_cast<const float*>(&x);
-    if (qd * 4 + 4 <= tb.total) *reinterpret_cast<float4*>(grads + qd * 4) = x;
-    else for (int e = 0; e < 4; ++e) if (qd * 4 + e < tb.total) grads[qd * 4 + e] = px[e];
-    for (int e = 0; e < 4; ++e) if (qd * 4 + e < tb.total) ss += (double)px[e] * px[e];
+    if (skip == 0u) *reinterpret_cast<float4*>(grads + qd * 4) = x;
+    else for (int e = 0; e < 4; ++e) if (!((skip >> e) & 1u)) grads[qd * 4 + e] = px[e];
+    for (int e = 0; e < 4; ++e) if (!((skip >> e) & 1u)) ss += (double)px[e] * px[e];
     return x;
   };
 #pragma unroll
@@ -493,6 +519,7 @@ __global__ void __launch_bounds__(256) k_ppo_reduce_adam(const SegTable* __restr
     if (qd < nquad) g[u] = quad_grad(qd);
   }
   for (long long qd = tid + (long long)RA_QUADS * nth; qd < nquad; qd += nth) quad_grad(qd);      // (only if P > 4 RA_QUADS threads)
+  reduce_biases(tb, partial, grads, ss);
   const double t = block_sum(ss, sh);
   if (threadIdx.x == 0) sumsq_part[blockIdx.x] = (float)t;
   __threadfence();
@@ -512,7 +539,9 @@ __global__ void __launch_bounds__(256) k_ppo_reduce_adam(const SegTable* __restr
     const float* px = reinterpret_cast<const float*>(&x);
     for (int e = 0; e < 4; ++e) {
       const long long i = qd * 4 + e;
-      if (i < tb.total) adam_element(find_seg(tb, i), i, px[e], s_scale, s_c1, s_c2, lr, b1, b2, eps, params, m1, m2, packed, true);
+      if (i >= tb.total) continue;
+      const Seg& se = find_seg(tb, i);
+      adam_element(se, i, se.bias ? __ldcg(grads + i) : px[e], s_scale, s_c1, s_c2, lr, b1, b2, eps, params, m1, m2, packed, true);   // bias gradients were reduced by other warps
     }
   };
 #pragma unroll
@@ -539,10 +568,12 @@ __global__ void __launch_bounds__(256) k_ppo_grad_reduce(const SegTable* __restr
   double ss = 0.0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tb.total; i += (long long)gridDim.x * blockDim.x) {
     const Seg& s = find_seg(tb, i);
+    if (s.bias) continue;                                  // reduce_biases owns the bias elements
     const float g = reduce_partials(s, partial, i - s.off);
     grads[i] = g;
     ss += (double)g * g;
   }
+  reduce_biases(tb, partial, grads, ss);
   const double t = block_sum(ss, sh);
   if (threadIdx.x == 0) sumsq_part[blockIdx.x] = (float)t;
 }
