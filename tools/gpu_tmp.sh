@@ -1,5 +1,3 @@
-o=gpurun_out; tag=r01z
-timeout 600 python tools/sweep.py > $o/${tag}_sweep_n1.jsonl 2> $o/${tag}_sweep_n1.err; cat $o/${tag}_sweep_n1.jsonl | cut -c1-200
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $o/${tag}_launches_rollout.csv python bench.py --steps 8 --warmup 3 --no-cpu-baseline > $o/${tag}_launches_rollout.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_step -s 12 -c 1 -o $o/${tag}_k_step -f python bench.py --steps 6 --warmup 3 --no-cpu-baseline > $o/${tag}_ncu_k_step.log 2>&1
-ls -la $o | grep ${tag}_k_step
+timeout 600 python -m pytest tests/test_ppo_device.py -m gpu -q > gpurun_out/r01s_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/r01s_pytest.log; tail -3 gpurun_out/r01s_pytest.log
+python bench.py --mode ppo --steps 100 --warmup 2 2>/dev/null | tee gpurun_out/r01s_bench_ppo.json | grep -o '"value.\{20\}\|"split.*'
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 600 -c 300 --csv --log-file gpurun_out/r01s_launches_ppo.csv python bench.py --mode ppo --steps 20 --warmup 1 > /dev/null 2>&1
