@@ -330,11 +330,13 @@ static cudaError_t launch_gemm(const GemmParams& p, int mtiles, int ntiles, bool
     return cudaGetLastError();
   }
   const int smem = NSTAGE * (GBLK_A + gblk_b(NT)) * (int)sizeof(float);
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr_done = 0ull;                      // one bit per device: the opt-in is per device (context)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!((attr_done >> (dev & 63)) & 1ull)) {
     cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<NT, NSTAGE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    attr = true;
+    attr_done |= 1ull << (dev & 63);
   }
   k_gemm_tc<NT, NSTAGE, EPI><<<grid, GEMM_THREADS, smem, st>>>(p);
   return cudaGetLastError();

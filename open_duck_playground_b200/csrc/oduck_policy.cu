@@ -219,8 +219,10 @@ __global__ void __launch_bounds__(TC_THREADS) k_dense_tc(DenseParams p) {
 template <int NT, bool HEAD>
 static cudaError_t launch_dense(const DenseParams& p, cudaStream_t st) {
   const int smem = 2 * (BLK_A + blk_b(NT)) * (int)sizeof(float);
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(k_dense_tc<NT, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+  static unsigned long long attr_done = 0ull;                      // one bit per device: the opt-in is per device (context)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!((attr_done >> (dev & 63)) & 1ull)) { cudaFuncSetAttribute(k_dense_tc<NT, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_done |= 1ull << (dev & 63); }
   dim3 grid((p.M + TC_M - 1) / TC_M, (p.N + NT - 1) / NT);
   k_dense_tc<NT, HEAD><<<grid, TC_THREADS, smem, st>>>(p);
   return cudaGetLastError();
