@@ -57,11 +57,11 @@ def test_config_struct_matches_header():
 
 
 # ----------------------------------------------------------------------------------------------------- GPU parity
-def _make(seed, N, T, nmb, dev):
+def _make(seed, N, T, nmb, dev, dp=101, dv=212):
     torch.manual_seed(seed)
     cfg = ppo.PPOConfig(num_envs=N, unroll_length=T, num_minibatches=nmb)
-    policy = ppo.MLP([101, 512, 256, 128, 28]).to(dev)
-    value = ppo.MLP([212, 512, 256, 128, 1]).to(dev)
+    policy = ppo.MLP([dp, 512, 256, 128, 28]).to(dev)
+    value = ppo.MLP([dv, 512, 256, 128, 1]).to(dev)
     with torch.no_grad():                                        # non-zero biases so that their gradients / updates are exercised
         for m in (policy, value):
             for lin in m.layers:
@@ -71,11 +71,11 @@ def _make(seed, N, T, nmb, dev):
         policy.layers[-1].weight.mul_(0.05)
     g = torch.Generator(device="cpu").manual_seed(seed + 1)
     r = lambda *s: torch.randn(*s, generator=g)
-    batch = {"obs_p": r(T + 1, N, 101) * 2 + 0.3, "obs_v": r(T + 1, N, 212) * 3 - 0.5, "raw": r(T, N, 14) * 0.8, "logp": r(T, N) * 0.3 - 12.0,
+    batch = {"obs_p": r(T + 1, N, dp) * 2 + 0.3, "obs_v": r(T + 1, N, dv) * 3 - 0.5, "raw": r(T, N, 14) * 0.8, "logp": r(T, N) * 0.3 - 12.0,
              "reward": torch.rand(T, N, generator=g) * 0.2, "done": (torch.rand(T, N, generator=g) < 0.1).float(), "trunc": torch.zeros(T, N)}
     batch["trunc"] = batch["done"] * (torch.rand(T, N, generator=g) < 0.3).float()
     batch = {k: v.to(dev).contiguous() for k, v in batch.items()}
-    norm = {"pm": (r(101) * 0.2).to(dev), "ps": (torch.rand(101, generator=g) + 0.5).to(dev), "vm": (r(212) * 0.2).to(dev), "vs": (torch.rand(212, generator=g) + 0.5).to(dev)}
+    norm = {"pm": (r(dp) * 0.2).to(dev), "ps": (torch.rand(dp, generator=g) + 0.5).to(dev), "vm": (r(dv) * 0.2).to(dev), "vs": (torch.rand(dv, generator=g) + 0.5).to(dev)}
     return cfg, policy, value, batch, norm
 
 
@@ -115,11 +115,11 @@ def _segments(L):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("simt", [True, False], ids=["cuda-core-twin", "tcgen05"])
-@pytest.mark.parametrize("shape", [(48, 5, 3), (512, 20, 2)], ids=["ragged-M80", "B256xT20"])
+@pytest.mark.parametrize("shape", [(48, 5, 3, 101, 212), (512, 20, 2, 101, 212), (96, 7, 2, 85, 153)], ids=["ragged-M80", "B256xT20", "standing-dims-85-153"])
 def test_learner_stages_match_torch(simt, shape):
-    N, T, nmb = shape
+    N, T, nmb, dp, dv = shape
     dev = torch.device("cuda:0")
-    cfg, policy, value, batch, norm = _make(3, N, T, nmb, dev)
+    cfg, policy, value, batch, norm = _make(3, N, T, nmb, dev, dp, dv)
     B = N // nmb
     L = ppo.DeviceLearner(cfg, policy, value, B, 14, dev)
     L2 = ppo.DeviceLearner(cfg, policy, value, B, 14, dev)        # takes the same step through the one-call product path
@@ -272,3 +272,34 @@ def test_graphed_rollout_equals_eager_rollout():
         assert math.isfinite(m["loss"])
     # (the graphed update uses the two-kernel reduce + Adam tail: same gradients, the global norm is summed in another grouping)
     assert (out[False][0] - out[True][0]).abs().max().item() < 1e-6
+
+
+@pytest.mark.gpu
+def test_device_learner_checkpoint_roundtrip_and_standing_training():
+    """params() / load() carry the device learner's weights and Adam state; the Standing task (85 / 153-wide observations) trains
+    through the same learner."""
+    from open_duck_playground_b200.joystick import Joystick
+    from open_duck_playground_b200.standing import Standing
+    cfg = ppo.PPOConfig(num_envs=256, unroll_length=4, num_minibatches=2, num_updates_per_batch=1, learner="device")
+    tr = ppo.PPOTrainer(Joystick("flat_terrain_backlash", device="cuda:0"), cfg)
+    for _ in range(2):
+        tr.training_step()
+    ck = tr.params()
+    tr2 = ppo.PPOTrainer(Joystick("flat_terrain_backlash", device="cuda:0"), cfg)
+    tr2.load(ck)
+    torch.cuda.synchronize()
+    assert torch.equal(tr2.dev_learner.params, tr.dev_learner.params)
+    assert torch.equal(tr2.dev_learner.view("ADAM_M"), tr.dev_learner.view("ADAM_M")) and torch.equal(tr2.dev_learner.view("ADAM_V"), tr.dev_learner.view("ADAM_V"))
+    assert int(tr2.dev_learner.step.item()) == int(tr.dev_learner.step.item()) == 4 and tr2.env_steps == tr.env_steps
+    # the restored actor acts like the original one on the same observations
+    obs = tr.state.obs["state"].contiguous()
+    for t_ in (tr, tr2):
+        t_.weights.refresh(t_._mean32["state"], t_.stats["state"].std)
+    a1, _, _ = ppo.policy_forward(tr.env, tr.weights, None, True, obs=obs)
+    a2, _, _ = ppo.policy_forward(tr2.env, tr2.weights, None, True, obs=obs)
+    assert torch.equal(a1, a2)
+    ts = ppo.PPOTrainer(Standing("flat_terrain_backlash", device="cuda:0"), cfg)
+    assert ts.policy.layers[0].in_features == 85 and ts.value.layers[0].in_features == 153
+    for _ in range(3):
+        m = ts.training_step()
+    assert math.isfinite(m["loss"]) and math.isfinite(m["v_loss"]) and 0.0 <= m["clip_fraction"] <= 1.0
