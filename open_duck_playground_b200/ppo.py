@@ -628,4 +628,5 @@ class PPOTrainer:
             d = params["normalizer"][k]
             s.mean = d["mean"].float().to(self.env.device); s.std.copy_(d["std"].to(self.env.device)); s.count = torch.tensor(float(d["count"]), device=self.env.device)
             s.m2 = (s.std ** 2) * s.count
+            self._mean32[k].copy_(s.mean32)                   # the static buffer the graphs / the learner read
         self.env_steps = int(params["env_steps"])
