@@ -34,7 +34,7 @@ sys.path.insert(0, ROOT)
 
 TASK = "flat_terrain_backlash"
 BYTES_PER_ENV_STEP = 3400          # 309 words read + 541 written
-FLOP_PER_ENV_STEP = 1.0e6          # planning figure, SURVEY.md 8d (physics only)
+FLOP_PER_ENV_STEP = 9.39e5         # counted: op-counter build of the oracle (tools/count_flops.py): 938 666 flop per env-step of the backlash model
 L2_BYTES = 126e6
 STATE_BYTES_PER_ENV = 4 * (128 + 144 + 224 + 256 + 101 + 212 + 16)   # records one step touches (csrc/oduck_device.cuh)
 

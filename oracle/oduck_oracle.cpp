@@ -35,10 +35,63 @@
 
 #include "../include/oduck.h"
 
+#ifdef ODUCK_COUNT_FLOPS
+// Op-counter build ("count from the oracle with an op-counter build"): `real` is a double that counts every
+// arithmetic operation the restated algorithm executes (+ - * / and sqrt = 1 flop, transcendental = 1, comparisons / moves = 0).
+// Single-threaded use only (ODUCK_THREADS=1); read with oduck_flop_count().
+static uint64_t g_flops = 0;
+struct CountReal {
+  double v;
+  CountReal() = default;
+  CountReal(double x) : v(x) {}
+  CountReal(float x) : v(x) {}
+  CountReal(int x) : v(x) {}
+  CountReal(unsigned x) : v(x) {}
+  CountReal(long x) : v((double)x) {}
+  CountReal(long long x) : v((double)x) {}
+  explicit operator double() const { return v; }
+  explicit operator float() const { return (float)v; }
+  explicit operator int() const { return (int)v; }
+  explicit operator bool() const { return v != 0.0; }
+  CountReal operator-() const { return CountReal(-v); }
+  CountReal& operator+=(CountReal o) { ++g_flops; v += o.v; return *this; }
+  CountReal& operator-=(CountReal o) { ++g_flops; v -= o.v; return *this; }
+  CountReal& operator*=(CountReal o) { ++g_flops; v *= o.v; return *this; }
+  CountReal& operator/=(CountReal o) { ++g_flops; v /= o.v; return *this; }
+};
+#define CR_BIN(op) \
+  inline CountReal operator op(CountReal a, CountReal b) { ++g_flops; return CountReal(a.v op b.v); } \
+  inline CountReal operator op(CountReal a, double b) { ++g_flops; return CountReal(a.v op b); } \
+  inline CountReal operator op(double a, CountReal b) { ++g_flops; return CountReal(a op b.v); } \
+  inline CountReal operator op(CountReal a, int b) { ++g_flops; return CountReal(a.v op b); } \
+  inline CountReal operator op(int a, CountReal b) { ++g_flops; return CountReal(a op b.v); }
+CR_BIN(+) CR_BIN(-) CR_BIN(*) CR_BIN(/)
+#undef CR_BIN
+#define CR_CMP(op) \
+  inline bool operator op(CountReal a, CountReal b) { return a.v op b.v; } \
+  inline bool operator op(CountReal a, double b) { return a.v op b; } \
+  inline bool operator op(double a, CountReal b) { return a op b.v; } \
+  inline bool operator op(CountReal a, int b) { return a.v op b; } \
+  inline bool operator op(int a, CountReal b) { return a op b.v; }
+CR_CMP(<) CR_CMP(>) CR_CMP(<=) CR_CMP(>=) CR_CMP(==) CR_CMP(!=)
+#undef CR_CMP
+namespace std {
+#define CR_FN1(f) inline CountReal f(CountReal x) { ++g_flops; return CountReal(f(x.v)); }
+CR_FN1(sqrt) CR_FN1(sin) CR_FN1(cos) CR_FN1(exp) CR_FN1(log) CR_FN1(log1p) CR_FN1(tanh)
+#undef CR_FN1
+inline CountReal fabs(CountReal x) { return CountReal(fabs(x.v)); }
+inline CountReal nearbyint(CountReal x) { return CountReal(nearbyint(x.v)); }
+inline CountReal pow(CountReal a, CountReal b) { ++g_flops; return CountReal(pow(a.v, b.v)); }
+inline bool isnan(CountReal x) { return isnan(x.v); }
+inline bool isinf(CountReal x) { return isinf(x.v); }
+}  // namespace std
+typedef CountReal real;
+#else
 #ifndef ODUCK_REAL
 #define ODUCK_REAL double
 #endif
 typedef ODUCK_REAL real;
+#endif
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -1407,6 +1460,10 @@ static void env_nominal(const OduckHandle& h, EnvState& e) {
 extern "C" {
 
 int oduck_abi_version(void) { return ODUCK_ABI_VERSION; }
+#ifdef ODUCK_COUNT_FLOPS
+uint64_t oduck_flop_count(void) { return g_flops; }
+void oduck_flop_reset(void) { g_flops = 0; }
+#endif
 int oduck_sizeof_model(void) { return (int)sizeof(OduckModel); }
 int oduck_sizeof_env_config(void) { return (int)sizeof(OduckEnvConfig); }
 const char* oduck_last_error(void) { return g_err.c_str(); }
@@ -1545,7 +1602,7 @@ int oduck_test_reference_motion(OduckHandle* h, double dx, double dy, double dth
   if (!h || !out40) return fail(ODUCK_ERR_ARG, "oduck_test_reference_motion: bad argument");
   real o[ODUCK_REF_DIM];
   poly_reference_motion(*h, (real)dx, (real)dy, (real)dth, i, o);
-  for (int k = 0; k < ODUCK_REF_DIM; k++) out40[k] = o[k];
+  for (int k = 0; k < ODUCK_REF_DIM; k++) out40[k] = (double)(o[k]);
   return ODUCK_OK;
 }
 // in: command[7] local_linvel[3] gyro[3] actuator_force[nu] action[nu] last_act[nu] base_qvel[6] q[nu] qd[nu] contact[2] ref[40]
@@ -1557,7 +1614,7 @@ int oduck_test_rewards(OduckHandle* h, const double* in, double* out7) {
   const real *cmd = p, *lv = p + 7, *gy = p + 10, *af = p + 13, *ac = af + nu, *la = ac + nu, *bq = la + nu, *q = bq + 6, *qd = q + nu, *ct = qd + nu, *rf = ct + 2;
   real o[7];
   compute_rewards(*h, cmd, lv, gy, af, ac, la, bq, q, qd, ct, rf, o);
-  for (int k = 0; k < 7; k++) out7[k] = o[k];
+  for (int k = 0; k < 7; k++) out7[k] = (double)(o[k]);
   return ODUCK_OK;
 }
 
@@ -1570,7 +1627,7 @@ int oduck_test_rewards_standing(OduckHandle* h, const double* in, double* out6) 
   const real *cmd = p, *up = p + 7, *af = p + 10, *ac = af + nu, *la = ac + nu, *q = la + nu, *qd = q + nu;
   real o[6];
   compute_rewards_standing(*h, cmd, up, af, ac, la, q, qd, o);
-  for (int k = 0; k < 6; k++) out6[k] = o[k];
+  for (int k = 0; k < 6; k++) out6[k] = (double)(o[k]);
   return ODUCK_OK;
 }
 
@@ -1583,25 +1640,25 @@ int oduck_debug_forward(OduckHandle* h, double* out) {
     static thread_local Scratch s;
     EnvState e = h->env[i];   // copy: diagnostic forward does not advance the warm start
     double* d = out + (size_t)i * 5120;
-    for (int k = 0; k < 5120; k++) d[k] = 0;
+    for (int k = 0; k < 5120; k++) d[k] = (double)(0);
     g_dbg.on = true;
     forward(*h, e, s);
     g_dbg.on = false;
     h->env[i] = e;
-    for (int a = 0; a < m.nv; a++) for (int b = 0; b < m.nv; b++) { d[a * 32 + b] = s.M[a][b]; d[4096 + a * 32 + b] = g_dbg.H[a][b]; }
+    for (int a = 0; a < m.nv; a++) for (int b = 0; b < m.nv; b++) { d[a * 32 + b] = (double)(s.M[a][b]); d[4096 + a * 32 + b] = (double)(g_dbg.H[a][b]); }
     for (int a = 0; a < m.nv; a++) {
-      d[1024 + a] = s.qfrc_bias[a]; d[1056 + a] = s.qfrc_smooth[a]; d[1088 + a] = s.qacc_smooth[a];
-      d[1376 + a] = g_dbg.search[a]; d[1408 + a] = g_dbg.grad[a]; d[1736 + a] = e.qacc[a];
-      for (int k = 0; k < 6; k++) d[1540 + a * 6 + k] = s.cdof[a][k];
+      d[1024 + a] = (double)(s.qfrc_bias[a]); d[1056 + a] = (double)(s.qfrc_smooth[a]); d[1088 + a] = (double)(s.qacc_smooth[a]);
+      d[1376 + a] = (double)(g_dbg.search[a]); d[1408 + a] = (double)(g_dbg.grad[a]); d[1736 + a] = (double)(e.qacc[a]);
+      for (int k = 0; k < 6; k++) d[1540 + a * 6 + k] = (double)(s.cdof[a][k]);
     }
-    for (int c = 0; c < NCON; c++) { d[1120 + c] = s.con_dist[c]; for (int k = 0; k < 3; k++) { d[1136 + 3 * c + k] = s.con_pos[c][k]; d[2560 + 3 * c + k] = s.con_frame[c][k]; } }
+    for (int c = 0; c < NCON; c++) { d[1120 + c] = (double)(s.con_dist[c]); for (int k = 0; k < 3; k++) { d[1136 + 3 * c + k] = (double)(s.con_pos[c][k]); d[2560 + 3 * c + k] = (double)(s.con_frame[c][k]); } }
     int r = 0;
-    for (int k = 0; k < h->nefc_fr; k++, r++) { d[1184 + h->fr_dof[k]] = s.D[r]; d[1264 + h->fr_dof[k]] = s.aref[r]; }
-    for (int k = 0; k < h->nefc_lim; k++, r++) { int dd = m.jnt_dofadr[h->lim_jnt[k]]; d[1216 + dd] = s.D[r]; d[1296 + dd] = s.aref[r]; }
-    for (int c = 0; c < NCON && r + 3 < s.nefc + 4; c++) { d[1248 + c] = s.D[r]; for (int k = 0; k < 4; k++, r++) d[1328 + 4 * c + k] = r < s.nefc ? s.aref[r] : 0; }
-    for (int b = 0; b < m.nbody; b++) for (int k = 0; k < 3; k++) d[1440 + 3 * b + k] = s.xpos[b][k];
-    for (int k = 0; k < 3; k++) d[1536 + k] = s.com[k];
-    d[2536] = g_dbg.costw; d[2537] = g_dbg.costs; d[2538] = g_dbg.alpha; d[2539] = g_dbg.ls_it;
+    for (int k = 0; k < h->nefc_fr; k++, r++) { d[1184 + h->fr_dof[k]] = (double)(s.D[r]); d[1264 + h->fr_dof[k]] = (double)(s.aref[r]); }
+    for (int k = 0; k < h->nefc_lim; k++, r++) { int dd = m.jnt_dofadr[h->lim_jnt[k]]; d[1216 + dd] = (double)(s.D[r]); d[1296 + dd] = (double)(s.aref[r]); }
+    for (int c = 0; c < NCON && r + 3 < s.nefc + 4; c++) { d[1248 + c] = (double)(s.D[r]); for (int k = 0; k < 4; k++, r++) d[1328 + 4 * c + k] = r < s.nefc ? (double)(s.aref[r]) : 0.0; }
+    for (int b = 0; b < m.nbody; b++) for (int k = 0; k < 3; k++) d[1440 + 3 * b + k] = (double)(s.xpos[b][k]);
+    for (int k = 0; k < 3; k++) d[1536 + k] = (double)(s.com[k]);
+    d[2536] = (double)(g_dbg.costw); d[2537] = (double)(g_dbg.costs); d[2538] = (double)(g_dbg.alpha); d[2539] = (double)(g_dbg.ls_it);
   }
   return ODUCK_OK;
 }
