@@ -40,6 +40,8 @@ class PPOConfig:
     normalize_observations: bool = True
     episode_length: int = 1000
     num_evals: int = 15
+    num_eval_envs: int = 128        # Brax ppo.train default: evaluation episodes run on their own envs (rank 0); 0 = estimate from the rollout
+    deterministic_eval: bool = False   # Brax default: the evaluator samples actions like the behaviour policy
     policy_hidden_layer_sizes: Tuple[int, ...] = (512, 256, 128)
     value_hidden_layer_sizes: Tuple[int, ...] = (512, 256, 128)
     policy_obs_key: str = "state"
@@ -272,6 +274,46 @@ def rollout_struct(batch: Dict[str, torch.Tensor]) -> "capi.OduckRollout":
     return ro
 
 
+class Evaluator:
+    """Brax ``acting.Evaluator`` + ``EvalWrapper`` for the fused env: ``num_eval_envs`` episodes of ``episode_length`` steps on
+    their own env instance; rewards and metrics are summed per env while its FIRST episode is active (``active *= 1 - done``),
+    exactly what ``eval/episode_reward`` / ``eval/episode_<metric>`` / ``eval/avg_episode_length`` report in the reference's
+    progress callback (common/runner.py:56-66)."""
+
+    def __init__(self, env, cfg: PPOConfig):
+        self.cfg = cfg
+        self.env = type(env)(task=env._task, config=env._config, device=env.device, library=env._lib)
+        self.n = cfg.num_eval_envs
+        self.key = jr.PRNGKey(cfg.seed + 101)
+        self.env.randomize(jr.split(jr.PRNGKey(cfg.seed + 102), self.n))
+
+    @torch.no_grad()
+    def run(self, weights: "PolicyWeights") -> Dict[str, float]:
+        env, n, T = self.env, self.n, self.cfg.episode_length
+        dev = env.device
+        self.key, k_reset, k_act = jr.split(self.key, 3)
+        st = env.reset(jr.split(k_reset, n))
+        step_keys = jr.split(jr.split(k_act, T), n).view(np.int32)              # [T, n, 2]
+        keys = torch.from_numpy(np.ascontiguousarray(step_keys)).to(dev)
+        active = torch.ones(n, device=dev)
+        ep_reward = torch.zeros(n, device=dev)
+        ep_steps = torch.zeros(n, device=dev)
+        ep_metrics = torch.zeros(n, len(env.METRICS), device=dev)
+        met = env.buffer("METRICS")
+        for t in range(T):
+            act, _, _ = policy_forward(env, weights, None if self.cfg.deterministic_eval else keys[t], deterministic=self.cfg.deterministic_eval)
+            st = env.step(st, act)
+            ep_reward += st.reward.float() * active
+            ep_metrics += met[:, :len(env.METRICS)].float() * active[:, None]
+            ep_steps += active
+            active = active * (1.0 - st.done.float())
+        out = {"eval/episode_reward": float(ep_reward.mean()), "eval/episode_reward_std": float(ep_reward.std(unbiased=False)),
+               "eval/avg_episode_length": float(ep_steps.mean())}
+        for i, name in enumerate(env.METRICS):
+            out[f"eval/episode_{name}"] = float(ep_metrics[:, i].mean())
+        return out
+
+
 class PPOTrainer:
     def __init__(self, env, cfg: PPOConfig, rank: int = 0, world: int = 1, progress_fn: Optional[Callable] = None,
                  policy_params_fn: Optional[Callable] = None):
@@ -303,6 +345,7 @@ class PPOTrainer:
         env.randomize(shard_keys(cfg.seed + 1, world, rank, self.n_local))
         self.state = env.reset(shard_keys(cfg.seed, world, rank, self.n_local))
         self.timing = {"rollout_ms": 0.0, "gather_ms": 0.0, "update_ms": 0.0}
+        self.evaluator = Evaluator(env, cfg) if (rank == 0 and cfg.num_eval_envs > 0) else None
 
     # ------------------------------------------------------------------ A17: unroll
     def _rollout_keys(self) -> np.ndarray:
@@ -588,6 +631,16 @@ class PPOTrainer:
         m["episode_done_rate"] = float(batch["done"].mean())
         return m
 
+    def evaluate(self) -> Dict[str, float]:
+        """One evaluation epoch with the current policy and normaliser (rank 0; Brax ``evaluator.run_evaluation``)."""
+        pk = self.cfg.policy_obs_key
+        if self.dev_learner is None:
+            mean, std = (self.stats[pk].mean32, self.stats[pk].std) if self.cfg.normalize_observations else (self._zeros[pk], self._ones[pk])
+        else:
+            mean, std = (self._mean32[pk], self.stats[pk].std) if self.cfg.normalize_observations else (self._zeros[pk], self._ones[pk])
+        self.weights.refresh(mean, std)
+        return self.evaluator.run(self.weights)
+
     def train(self):
         cfg = self.cfg
         n_steps = max(1, cfg.num_timesteps // (cfg.num_envs * cfg.unroll_length))
@@ -595,8 +648,11 @@ class PPOTrainer:
         for it in range(n_steps):
             m = self.training_step()
             if self.rank == 0 and (it % eval_every == 0 or it == n_steps - 1):
-                metrics = {"eval/episode_reward": m["reward_per_step"] * cfg.episode_length, "eval/episode_reward_std": 0.0, **{f"training/{k}": v for k, v in m.items()},
-                           **{f"time/{k}": v for k, v in self.timing.items()}}
+                if self.evaluator is not None:
+                    ev = self.evaluate()
+                else:                                        # no eval envs: extrapolate the behaviour policy's mean step reward
+                    ev = {"eval/episode_reward": m["reward_per_step"] * cfg.episode_length, "eval/episode_reward_std": 0.0}
+                metrics = {**ev, **{f"training/{k}": v for k, v in m.items()}, **{f"time/{k}": v for k, v in self.timing.items()}}
                 if self.progress_fn:
                     self.progress_fn(self.env_steps, metrics)
                 if self.policy_params_fn:

@@ -88,3 +88,25 @@ def test_training_step_runs_and_learns_signal(oracle):
     tr2 = ppo.PPOTrainer(Joystick("flat_terrain_backlash", library=oracle), cfg)
     tr2.load(p)
     assert all(torch.equal(a, b) for a, b in zip(tr.policy.state_dict().values(), tr2.policy.state_dict().values()))
+
+
+def test_evaluator_reports_first_episode_sums(oracle):
+    """Brax EvalWrapper semantics: per-env sums over the first episode only, averaged over the eval envs."""
+    env = Joystick("flat_terrain_backlash", library=oracle)
+    cfg = ppo.PPOConfig(num_envs=8, unroll_length=3, num_minibatches=2, num_updates_per_batch=1, num_eval_envs=6, episode_length=15)
+    tr = ppo.PPOTrainer(env, cfg)
+    ev = tr.evaluate()
+    assert {"eval/episode_reward", "eval/episode_reward_std", "eval/avg_episode_length", "eval/episode_reward/alive", "eval/episode_swing_peak"} <= set(ev)
+    assert 1.0 <= ev["eval/avg_episode_length"] <= 15.0
+    # alive pays 20 per active step, so its episode sum is 20 x the episode length (joystick.py:83)
+    assert abs(ev["eval/episode_reward/alive"] - 20.0 * ev["eval/avg_episode_length"]) < 1e-3
+    assert ev["eval/episode_reward"] >= 0.0 and math.isfinite(ev["eval/episode_reward_std"])
+    # the evaluator owns its envs: the training envs' state is untouched
+    before = tr.state.data.qpos.clone()
+    tr.evaluate()
+    assert torch.equal(before, tr.state.data.qpos)
+    m = []
+    tr.progress_fn = lambda steps, metrics: m.append(metrics)
+    tr.cfg.num_timesteps = 8 * 3 * 2
+    tr.train()
+    assert m and "eval/episode_reward" in m[-1] and "training/loss" in m[-1] and "eval/avg_episode_length" in m[-1]
