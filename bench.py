@@ -145,6 +145,56 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def run_physics(args, rank, world, dev):
+    """SURVEY 8d config 2 read literally: ``mjx_env.step(model, data, ctrl, 10)`` alone -- ``oduck_physics_substeps(n = 10)`` with
+    ctrl = home + 0.25 U(-1, 1) redrawn every control step, no env logic, no policy (algorithmic bytes: 1 096 B / env-step)."""
+    import torch
+    import torch.distributed as dist
+    from open_duck_playground_b200 import rng as jr
+    from open_duck_playground_b200.joystick import Joystick
+    n = args.envs_per_gpu
+    n_sets = max(3, int(np.ceil(1.3 * L2_BYTES / (n * 4 * (128 + 144 + 224)))))
+    envs = []
+    for s in range(n_sets):
+        e = Joystick(TASK, device=dev)
+        e.randomize(jr.split(jr.PRNGKey(2), world * n)[rank * n:(rank + 1) * n])
+        e.reset(jr.split(jr.PRNGKey(100 + s), world * n)[rank * n:(rank + 1) * n])
+        envs.append(e)
+    home = torch.tensor(envs[0]._mj_model.key_ctrl[:14], dtype=torch.float32, device=dev)
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    ctrls = [(home + 0.25 * (2 * torch.rand(n, 14, device=dev, generator=g) - 1)).contiguous() for _ in range(8)]
+    def step(k):
+        envs[k % n_sets].physics_substeps(ctrls[k % 8], 10)
+    for k in range(max(3, args.warmup, n_sets)):
+        step(k)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for k in range(args.steps):
+        step(k)
+    t1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    if rank == 0:
+        hbm, kind, _ = _peaks()
+        ach = 1096 * n / (ms / args.steps * 1e-3) / 1e9
+        print(json.dumps({"metric": "env-steps/sec (physics only: 10 x mjx.step per env-step)", "value": world * n * args.steps / (ms * 1e-3), "unit": "env-steps/s", "n_gpus": world,
+                          "steps": args.steps, "warmup": max(3, args.warmup, n_sets), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": f"{TASK} oduck_physics_substeps(n=10), {n} envs per GPU, domain randomisation on (SURVEY 8d config 2)", "envs_per_gpu": n,
+                                     "l2": f"{n_sets} env sets rotated"},
+                          "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None, "algorithmic_bytes_per_env_step": 1096,
+                                       "kernel": "k_physics", "peak_source": kind},
+                          "physics_substeps_per_s": world * n * args.steps * 10 / (ms * 1e-3), "gpu_launches": args.steps}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_ppo(args, rank, world, dev):
     """BASELINE configs[2]: full PPO (8192 envs x unroll 20 per training step), timed end to end with the rollout / gather / update split."""
     import torch
@@ -187,7 +237,8 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=4096)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default="rollout", choices=["rollout", "ppo"], help="ppo = BASELINE configs[2]: full PPO training steps (rollout / gather / update split)")
+    ap.add_argument("--mode", default="rollout", choices=["rollout", "ppo", "physics"],
+                    help="ppo = BASELINE configs[2]: full PPO training steps (rollout / gather / update split); physics = oduck_physics_substeps(10) alone")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
@@ -221,6 +272,8 @@ def main():
     n = args.envs_per_gpu
     if args.mode == "ppo":
         return run_ppo(args, rank, world, dev)
+    if args.mode == "physics":
+        return run_physics(args, rank, world, dev)
     # env sets rotated so that the working set exceeds L2 (timing rule: inputs larger than L2)
     n_sets = max(3, int(np.ceil(1.3 * L2_BYTES / (n * STATE_BYTES_PER_ENV))))
     # per-rank keys: split(seed, world*n) then sliced, so results do not depend on the GPU count
