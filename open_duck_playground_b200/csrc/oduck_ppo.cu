@@ -83,6 +83,7 @@ struct OduckPpo {
   cudaStream_t side_w[2];   // weight-gradient GEMMs of the policy / value net (off the dZ critical path)
   cudaEvent_t ev_fork, ev_join, ev_join_w[2], ev_dz[2][PPO_NL];
   int coop_blocks;          // co-resident CTAs of the fused reduce + Adam kernel (0: cooperative launch unavailable)
+  int num_sms;
   std::vector<void*> allocs;
 };
 
@@ -740,6 +741,7 @@ int oduck_ppo_create(const OduckPpoConfig* cfg, int device, OduckPpo** out) {
     int coop = 0, per_sm = 0, sms = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    h->num_sms = sms > 0 ? sms : 148;
     if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ppo_reduce_adam, 256, 0) == cudaSuccess && per_sm > 0)
       h->coop_blocks = std::min(h->reduce_blocks, per_sm * sms);
   }
@@ -826,7 +828,9 @@ static int net_forward(OduckPpo* h, int net, bool simt, cudaStream_t st) {
       g.Z = nb.Z[l]; g.z_nch = w.N / TC_KC;
       g.Yr = nb.Xr[l + 1]; g.yr_nch = w.N / TC_KC;
       g.Yt = nb.Xt[l + 1]; g.yt_nch = nb.Mpad / TC_KC;
-      GEMM_TRY((launch_gemm<128, 3, EPI_FWD>(g, nb.mtiles, w.N / 128, simt, st)));
+      // more CTAs than SMs (the 512-wide layer): single-stage instance, 64 KB of shared memory, three CTAs per SM -> one wave
+      if (nb.mtiles * (w.N / 128) > h->num_sms) GEMM_TRY((launch_gemm<128, 1, EPI_FWD>(g, nb.mtiles, w.N / 128, simt, st)));
+      else GEMM_TRY((launch_gemm<128, 3, EPI_FWD>(g, nb.mtiles, w.N / 128, simt, st)));
     } else {
       g.out = nb.out; g.ldo = PPO_HEADW;
       GEMM_TRY((launch_gemm<PPO_HEADW, 4, EPI_OUT>(g, nb.mtiles, 1, simt, st)));
@@ -864,7 +868,8 @@ static int net_backward(OduckPpo* h, int net, bool simt, cudaStream_t sx, cudaSt
       g.Yt = nb.dZt[l - 1]; g.yt_nch = nb.Mpad / TC_KC;
       g.dbpart = h->partial + bprev.dbpart; g.ldb = bprev.ldb;
       g.nvalid = w.K;
-      GEMM_TRY((launch_gemm<128, 3, EPI_DX>(g, nb.mtiles, w.K / 128, simt, sx)));
+      if (nb.mtiles * (w.K / 128) > h->num_sms) GEMM_TRY((launch_gemm<128, 1, EPI_DX>(g, nb.mtiles, w.K / 128, simt, sx)));
+      else GEMM_TRY((launch_gemm<128, 3, EPI_DX>(g, nb.mtiles, w.K / 128, simt, sx)));
       if (sw != sx) {
         PPO_TRY(cudaEventRecord(h->ev_dz[net][l - 1], sx));
         PPO_TRY(cudaStreamWaitEvent(sw, h->ev_dz[net][l - 1], 0));
