@@ -104,7 +104,9 @@ __global__ void __launch_bounds__(WPB * 32, CTAS_PER_SM) k_physics(Params p) {
   const DevModel& m = *mp;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WarpSmem& s = ws[warp];
-  for (int env = blockIdx.x * WPB + warp; env < p.N; env += gridDim.x * WPB) {
+  for (int env0 = blockIdx.x * WPB; env0 < p.N; env0 += gridDim.x * WPB) {
+    const int env = env0 + warp;
+    if (env >= p.N) { if (!DBG) substep_idle_barriers(p.nsub); continue; }     // the CTA's other warps synchronise inside the substeps
     Lane L;
     float* ph = p.phys + (size_t)env * PHYS_STRIDE;
     load_env(m, s, L, lane, ph, p.dr + (size_t)env * DR_STRIDE);
@@ -112,7 +114,8 @@ __global__ void __launch_bounds__(WPB * 32, CTAS_PER_SM) k_physics(Params p) {
     for (int i = lane; i < OUT_STRIDE; i += 32) s.outrec[i] = 0.f;
     __syncwarp();
     float* dbg = DBG ? p.dbg + (size_t)env * DBG_STRIDE : nullptr;
-    for (int k = 0; k < p.nsub; ++k) forward_euler<DBG>(m, s, L, lane, k == p.nsub - 1, p.integrate != 0, s.outrec, dbg, p.ffmodel, p.ffscratch + (size_t)env * (FFJ_SIZE + FFV_SIZE));
+    // like k_step: one CTA barrier per substep keeps the CTA's warps on the same stretch of the instruction stream
+    for (int k = 0; k < p.nsub; ++k) forward_euler<DBG, !DBG>(m, s, L, lane, k == p.nsub - 1, p.integrate != 0, s.outrec, dbg, p.ffmodel, p.ffscratch + (size_t)env * (FFJ_SIZE + FFV_SIZE));
     __syncwarp();
     store_phys(m, s, L, lane, ph);
     store_out(s, lane, p.out + (size_t)env * OUT_STRIDE);
