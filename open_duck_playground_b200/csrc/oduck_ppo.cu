@@ -828,9 +828,7 @@ static int net_forward(OduckPpo* h, int net, bool simt, cudaStream_t st) {
       g.Z = nb.Z[l]; g.z_nch = w.N / TC_KC;
       g.Yr = nb.Xr[l + 1]; g.yr_nch = w.N / TC_KC;
       g.Yt = nb.Xt[l + 1]; g.yt_nch = nb.Mpad / TC_KC;
-      // more CTAs than SMs (the 512-wide layer): single-stage instance, 64 KB of shared memory, three CTAs per SM -> one wave
-      if (nb.mtiles * (w.N / 128) > h->num_sms) GEMM_TRY((launch_gemm<128, 1, EPI_FWD>(g, nb.mtiles, w.N / 128, simt, st)));
-      else GEMM_TRY((launch_gemm<128, 3, EPI_FWD>(g, nb.mtiles, w.N / 128, simt, st)));
+      GEMM_TRY((launch_gemm<128, 3, EPI_FWD>(g, nb.mtiles, w.N / 128, simt, st)));
     } else {
       g.out = nb.out; g.ldo = PPO_HEADW;
       GEMM_TRY((launch_gemm<PPO_HEADW, 4, EPI_OUT>(g, nb.mtiles, 1, simt, st)));
@@ -868,8 +866,7 @@ static int net_backward(OduckPpo* h, int net, bool simt, cudaStream_t sx, cudaSt
       g.Yt = nb.dZt[l - 1]; g.yt_nch = nb.Mpad / TC_KC;
       g.dbpart = h->partial + bprev.dbpart; g.ldb = bprev.ldb;
       g.nvalid = w.K;
-      if (nb.mtiles * (w.K / 128) > h->num_sms) GEMM_TRY((launch_gemm<128, 1, EPI_DX>(g, nb.mtiles, w.K / 128, simt, sx)));
-      else GEMM_TRY((launch_gemm<128, 3, EPI_DX>(g, nb.mtiles, w.K / 128, simt, sx)));
+      GEMM_TRY((launch_gemm<128, 3, EPI_DX>(g, nb.mtiles, w.K / 128, simt, sx)));
       if (sw != sx) {
         PPO_TRY(cudaEventRecord(h->ev_dz[net][l - 1], sx));
         PPO_TRY(cudaStreamWaitEvent(sw, h->ev_dz[net][l - 1], 0));
