@@ -193,8 +193,10 @@ __device__ __forceinline__ Q4 qnormalize(Q4 q) {
   return q;
 }
 __device__ __forceinline__ Q4 axis_angle(V3 ax, float ang) {
+  // half joint angles stay within (-pi, pi): the fast-path intrinsic (abs error 2^-21.4 there) without sincosf's out-of-line
+  // argument reduction (~850 instructions of code per inlined call)
   float s, c;
-  sincosf(0.5f * ang, &s, &c);
+  __sincosf(0.5f * ang, &s, &c);
   Q4 q; q.w = c; q.x = s * ax.x; q.y = s * ax.y; q.z = s * ax.z;
   return q;
 }
@@ -425,17 +427,19 @@ static __device__ __noinline__ float symv(const float* A, int n, int lane, float
   __syncwarp();
   return lane < n ? acc : 0.f;
 }
-// constraint.py _kbi impedance for a signed distance
+// constraint.py _kbi impedance for a signed distance.  The general-power branch (two powf expansions, ~1.5 k instructions each
+// time it is inlined) is never taken by the reference scenes (solimp power = 2): it lives out of line so that the substep's hot
+// instruction stream, which already exceeds the instruction cache, does not carry it twice.
+static __device__ __noinline__ float impedance_general_power(float x, float mid, float power) {
+  const float ia = (1.f / powf(mid, power - 1.f)) * powf(x, power);
+  const float ib = 1.f - (1.f / powf(1.f - mid, power - 1.f)) * powf(1.f - x, power);
+  return x < mid ? ia : ib;
+}
 __device__ __forceinline__ float impedance(const DevModel& m, float pos) {
   float x = fabsf(pos) / m.width;
   float y;
-  if (m.power == 2.f) {
-    y = x < m.mid ? x * x / m.mid : 1.f - (1.f - x) * (1.f - x) / (1.f - m.mid);
-  } else {
-    float ia = (1.f / powf(m.mid, m.power - 1.f)) * powf(x, m.power);
-    float ib = 1.f - (1.f / powf(1.f - m.mid, m.power - 1.f)) * powf(1.f - x, m.power);
-    y = x < m.mid ? ia : ib;
-  }
+  if (m.power == 2.f) y = x < m.mid ? x * x / m.mid : 1.f - (1.f - x) * (1.f - x) / (1.f - m.mid);
+  else y = impedance_general_power(x, m.mid, m.power);
   float imp = m.dmin + y * (m.dmax - m.dmin);
   imp = fminf(fmaxf(imp, m.dmin), m.dmax);
   if (x > 1.f) imp = m.dmax;
