@@ -52,3 +52,28 @@ def test_onnx_matches_library_actor(oracle, tmp_path):
     path = ex.export_onnx(ex.brax_param_tree(params), 14, (512, 256, 128), 101, str(tmp_path / "p.onnx"))
     out = np.concatenate([ex.run_onnx(path, st.obs["state"][i:i + 1].float().numpy()) for i in range(4)])
     assert np.abs(out - act.numpy()).max() < 1e-5
+
+
+def test_headless_inference_loop(oracle, tmp_path):
+    """Checkpoint -> ONNX -> sim-to-sim loop (the role of mujoco_infer.py), on the oracle env: the exported policy drives the env
+    exactly like the library's deterministic actor."""
+    from open_duck_playground_b200 import infer
+    pol, mean, std, params = _checkpoint(3)
+    with torch.no_grad():
+        pol.layers[-1].weight.mul_(0.05)                                  # small actions: the duck keeps standing for the test's 12 steps
+        params["policy"] = {k: v for k, v in pol.state_dict().items()}
+    path = ex.export_onnx(ex.brax_param_tree(params), 14, (512, 256, 128), 101, str(tmp_path / "p.onnx"))
+    env = Joystick("flat_terrain_backlash", library=oracle)
+    out = infer.run_policy(env, path, steps=12, seed=5, command=[0.1, 0, 0, 0, 0, 0, 0], num_envs=2)
+    assert out["steps"] == 12 and np.isfinite(out["mean_step_reward"]) and 0.05 < out["final_base_height"] < 0.3
+    assert torch.allclose(env.buffer("INFO_COMMAND")[:, 0].double(), torch.full((2,), 0.1, dtype=torch.float64), atol=1e-6)
+    # same rollout with the library actor (deterministic) from the same reset: identical trajectory
+    env2 = Joystick("flat_terrain_backlash", library=oracle)
+    st = env2.reset(jr.split(jr.PRNGKey(5), 2))
+    w = ppo.PolicyWeights(pol, 101, env2.device)
+    w.refresh(mean, std)
+    for _ in range(12):
+        st.info["command"][:] = torch.tensor([0.1, 0, 0, 0, 0, 0, 0], dtype=st.info["command"].dtype)
+        act, _, _ = ppo.policy_forward(env2, w, None, deterministic=True)
+        st = env2.step(st, act)
+    assert torch.allclose(env.buffer("QPOS").double(), env2.buffer("QPOS").double(), atol=1e-4)
