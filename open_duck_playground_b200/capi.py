@@ -14,7 +14,7 @@ import numpy as np
 
 from .mjcf import CompiledModel
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAX_BODY, MAX_JNT, MAX_NQ, MAX_NV, MAX_NU, MAX_SITE, MAX_VERT, MAX_FACE, NFEET, NCMD = 20, 28, 36, 32, 16, 8, 32, 64, 2, 7
 OBS_STATE, OBS_PRIV, NMETRIC, REF_DIM, POLY_DEG, MAX_CON = 101, 212, 8, 40, 16, 12
 
@@ -48,6 +48,7 @@ class OduckModel(C.Structure):
         ("timestep", d), ("gravity", d * 3), ("tolerance", d), ("ls_tolerance", d), ("impratio", d), ("meaninertia", d),
         ("iterations", i32), ("ls_iterations", i32), ("solref", d * 2), ("solimp", d * 5),
         ("key_qpos", d * MAX_NQ), ("key_ctrl", d * MAX_NU),
+        ("hfield_nrow", i32), ("hfield_ncol", i32), ("hfield_size", d * 4), ("hfield_data", C.POINTER(C.c_float)),
     ]
 
 
@@ -125,6 +126,16 @@ def model_to_struct(m: CompiledModel) -> OduckModel:
         setattr(s, k, int(getattr(m, k)))
     for name, ctype in OduckModel._fields_:
         if name in ("abi_version", "nbody", "njnt", "nq", "nv", "nu", "nsite"):
+            continue
+        if name.startswith("hfield_"):                       # optional height-field asset (rough terrain scenes)
+            if "hfield_data" in m.arrays and name == "hfield_data":
+                data = np.ascontiguousarray(m.arrays["hfield_data"], dtype=np.float32)
+                s._hfield_keep = data                        # the struct holds a pointer: keep the array alive with it
+                s.hfield_data = data.ctypes.data_as(C.POINTER(C.c_float))
+                s.hfield_nrow, s.hfield_ncol = int(data.shape[0]), int(data.shape[1])
+            elif name == "hfield_size" and "hfield_size" in m.arrays:
+                for k in range(4):
+                    s.hfield_size[k] = float(m.arrays["hfield_size"][k])
             continue
         a = m.arrays[name]
         if isinstance(getattr(s, name), (int, float)):

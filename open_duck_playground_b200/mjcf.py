@@ -190,6 +190,70 @@ class _Defaults:
         return out
 
 
+def _read_png_gray(path: str) -> np.ndarray:
+    """Minimal PNG decoder (8-bit, non-interlaced, grey / grey+alpha / RGB / RGBA) -> uint8 [height, width].
+    Colour images are reduced to their RED channel, which is what MuJoCo's height-field loader gets from lodepng's LCT_GREY
+    conversion (user_objects.cc mjCHField::LoadPNG) **[upstream-memory]**.  PIL is not available in this image."""
+    import struct
+    import zlib
+    raw = open(path, "rb").read()
+    if raw[:8] != b"\x89PNG\r\n\x1a\n":
+        raise ValueError(f"{path}: not a PNG file")
+    pos, idat, hdr = 8, [], None
+    while pos < len(raw):
+        ln, typ = struct.unpack(">I4s", raw[pos:pos + 8])
+        body = raw[pos + 8:pos + 8 + ln]
+        if typ == b"IHDR":
+            hdr = struct.unpack(">IIBBBBB", body)
+        elif typ == b"IDAT":
+            idat.append(body)
+        elif typ == b"IEND":
+            break
+        pos += 12 + ln
+    w, h, depth, ctype, _, _, interlace = hdr
+    nch = {0: 1, 2: 3, 4: 2, 6: 4}.get(ctype)
+    if depth != 8 or nch is None or interlace:
+        raise ValueError(f"{path}: only 8-bit non-interlaced grey/RGB(A) PNGs are supported")
+    data = zlib.decompress(b"".join(idat))
+    stride = w * nch
+    out = np.zeros((h, stride), np.uint8)
+    prev = np.zeros(stride, np.int32)
+    for r in range(h):
+        f = data[r * (stride + 1)]
+        line = np.frombuffer(data, np.uint8, stride, r * (stride + 1) + 1).astype(np.int32)
+        cur = np.zeros(stride, np.int32)
+        if f == 0:
+            cur = line
+        elif f == 2:
+            cur = (line + prev) & 255
+        else:                                   # Sub / Average / Paeth depend on the pixel to the left: sequential per channel byte
+            for i in range(stride):
+                a = cur[i - nch] if i >= nch else 0
+                b = prev[i]
+                c = prev[i - nch] if i >= nch else 0
+                if f == 1:
+                    pr = a
+                elif f == 3:
+                    pr = (a + b) >> 1
+                elif f == 4:
+                    pa, pb, pc = abs(b - c), abs(a - c), abs(a + b - 2 * c)
+                    pr = a if (pa <= pb and pa <= pc) else (b if pb <= pc else c)
+                else:
+                    raise ValueError(f"{path}: bad PNG filter {f}")
+                cur[i] = (line[i] + pr) & 255
+        out[r] = cur
+        prev = cur
+    return out.reshape(h, w, nch)[:, :, 0].copy()
+
+
+def load_hfield_png(path: str) -> np.ndarray:
+    """Height-field elevation data as MuJoCo stores it: image rows flipped (row 0 = minimum y), normalised to [0, 1] by the
+    data range (mjCHField: ``data = (data - min) / (max - min)``) **[upstream-memory]**.  float32 [nrow, ncol]."""
+    img = _read_png_gray(path).astype(np.float64)[::-1]
+    lo, hi = img.min(), img.max()
+    return ((img - lo) / (hi - lo) if hi > lo else np.zeros_like(img)).astype(np.float32)
+
+
 def _read_stl(path: str) -> np.ndarray:
     b = open(path, "rb").read()
     n = struct.unpack("<I", b[80:84])[0]
@@ -528,6 +592,7 @@ def compile_mjcf(xml_path: str, timestep: float = 0.002) -> CompiledModel:
     if hfield is not None and A["floor_is_hfield"]:
         A["hfield_size"] = _vec(hfield["size"], None)
         A["hfield_file"] = np.array(os.path.join(xml_dir, hfield["file"]))
+        A["hfield_data"] = load_hfield_png(os.path.join(xml_dir, hfield["file"]))
 
     # options ----------------------------------------------------------------
     A["timestep"] = np.array(float(timestep))

@@ -249,6 +249,7 @@ struct OduckHandle {
   OduckModel m;
   OduckEnvConfig cfg;
   std::vector<double> poly;
+  std::vector<float> hfield;   // [nrow][ncol] elevation in [0, 1] (floor_is_hfield)
   int n;
   std::vector<EnvState> env;
   int nefc_fr, nefc_lim;  // static row counts
@@ -569,98 +570,96 @@ static void plane_convex(const OduckModel& m, const Scratch& s, int k, int slot0
 }
 
 
-// Convex-convex narrow phase for the two feet (the mesh-mesh pair MJX instantiates: both collision meshes have
-// contype = conaffinity = 1).  PARITY UNPINNED like the rest of the physics: MJX's convex_convex source is
-// not available, so this is a restatement of the documented scheme -- separating-axis test over the face normals of
-// both hulls and the cross products of edge pairs, then a clipped-polygon manifold of at most 4 points:
+// Convex-convex narrow phase (MJX collision_convex.py _convex_convex scheme) between two convex polytopes given by their
+// world-frame vertices, polygon faces (outward normals, CCW vertex loops) and edges (vertex pair + the two adjacent faces).
+// Used for the two feet (the mesh-mesh pair MJX instantiates: both collision meshes have contype = conaffinity = 1,
+// SURVEY.md 2.1).  PARITY UNPINNED like the rest of the
+// physics: MJX's source is not available, so this is a restatement of the documented scheme -- separating-axis test over
+// the face normals of both hulls and the cross products of edge pairs, then a clipped-polygon manifold of at most 4 points:
 //   * face axes: signed distance of the other hull's deepest vertex to every polygon face,
 //   * edge axes: only edge pairs that span a face of the Minkowski difference (Gauss-map arc test), distance between the
 //     two edge lines along their common normal,
 //   * face contact: the incident face (most anti-parallel) is Sutherland-Hodgman clipped against the side planes of the
 //     reference face; dist = signed distance to the reference plane, pos = midway; >4 points -> _manifold_points,
 //   * edge contact (chosen only if it separates 0.1 mm better than the best face): closest points of the two edges.
-// Normal points from geom1 (left foot) to geom2 (right foot).
-static void convex_convex(const OduckModel& m, const Scratch& s, Scratch& out) {
-  const int bA = m.foot_body[0], bB = m.foot_body[1], nvt = m.foot_nvert, np_ = m.foot_nplane, ne = m.foot_nedge;
-  for (int c = 8; c < 12; c++) { out.con_dist[c] = 1; out.con_b1[c] = bA; out.con_b2[c] = bB; out.con_mu[c] = (real)m.foot_friction; }
-  real VA[ODUCK_MAX_VERT][3], VB[ODUCK_MAX_VERT][3], nrmA[ODUCK_MAX_PLANE][3], nrmB[ODUCK_MAX_PLANE][3], cA[3], cB[3];
-  auto xform = [&](int b, const double* v, real* o) { real t[3] = {(real)v[0], (real)v[1], (real)v[2]}; mat_vec(s.xmat[b], t, o); for (int i = 0; i < 3; i++) o[i] += s.xpos[b][i]; };
-  xform(bA, m.foot_center[0], cA);
-  xform(bB, m.foot_center[1], cB);
-  real dc[3] = {cB[0] - cA[0], cB[1] - cA[1], cB[2] - cA[2]};
-  if (std::sqrt(dot3(dc, dc)) > 2 * (real)m.foot_radius) return;                      // bounding spheres apart: no contact
-  for (int i = 0; i < nvt; i++) { xform(bA, m.foot_vert[0][i], VA[i]); xform(bB, m.foot_vert[1][i], VB[i]); }
-  for (int q = 0; q < np_; q++) {
-    real a[3] = {(real)m.foot_plane_normal[0][q][0], (real)m.foot_plane_normal[0][q][1], (real)m.foot_plane_normal[0][q][2]};
-    real b[3] = {(real)m.foot_plane_normal[1][q][0], (real)m.foot_plane_normal[1][q][1], (real)m.foot_plane_normal[1][q][2]};
-    mat_vec(s.xmat[bA], a, nrmA[q]);
-    mat_vec(s.xmat[bB], b, nrmB[q]);
-  }
+// Normal points from hull A (geom1) to hull B (geom2).
+#define HULL_MAXV ODUCK_MAX_VERT
+#define HULL_MAXP ODUCK_MAX_PLANE
+#define HULL_MAXE ODUCK_MAX_EDGE
+struct Hull {
+  int nv, np, ne;
+  real V[HULL_MAXV][3], N[HULL_MAXP][3], c[3];
+  int pnv[HULL_MAXP], pv[HULL_MAXP][ODUCK_MAX_PVERT], ev[HULL_MAXE][2], ep[HULL_MAXE][2];
+};
+struct HullContacts { real dist[4], pos[4][3], frame[9]; };   // dist = 1: inactive slot
+
+static bool hull_hull(const Hull& A, const Hull& B, HullContacts& out) {
+  for (int c = 0; c < 4; c++) { out.dist[c] = 1; out.pos[c][0] = out.pos[c][1] = out.pos[c][2] = 0; }
+  for (int i = 0; i < 9; i++) out.frame[i] = (i == 0 || i == 4 || i == 8) ? 1 : 0;
   const real ninf = -std::numeric_limits<real>::infinity();
   real face_sep = ninf; int face_hull = 0, face_idx = 0;
-  for (int h = 0; h < 2; h++)
-    for (int q = 0; q < np_; q++) {
-      const real* n = h ? nrmB[q] : nrmA[q];
-      const real (*Vr)[3] = h ? VB : VA; const real (*Vo)[3] = h ? VA : VB;
-      real off = dot3(n, Vr[m.foot_plane_vert[q][0]]), mn = std::numeric_limits<real>::infinity();
-      for (int j = 0; j < nvt; j++) mn = std::min(mn, dot3(n, Vo[j]));
+  for (int h = 0; h < 2; h++) {
+    const Hull& R = h ? B : A; const Hull& O = h ? A : B;
+    for (int q = 0; q < R.np; q++) {
+      const real* n = R.N[q];
+      real off = dot3(n, R.V[R.pv[q][0]]), mn = std::numeric_limits<real>::infinity();
+      for (int j = 0; j < O.nv; j++) mn = std::min(mn, dot3(n, O.V[j]));
       if (mn - off > face_sep) { face_sep = mn - off; face_hull = h; face_idx = q; }
     }
-  if (face_sep > 0) return;
+  }
+  if (face_sep > 0) return false;
   real edge_sep = ninf, edge_n[3] = {0, 0, 1}; int eA_best = -1, eB_best = -1;
-  for (int ea = 0; ea < ne; ea++) {
-    const real *a = nrmA[m.foot_edge_plane[ea][0]], *b = nrmA[m.foot_edge_plane[ea][1]];
-    const real *pa0 = VA[m.foot_edge_vert[ea][0]], *pa1 = VA[m.foot_edge_vert[ea][1]];
+  for (int ea = 0; ea < A.ne; ea++) {
+    const real *a = A.N[A.ep[ea][0]], *b = A.N[A.ep[ea][1]];
+    const real *pa0 = A.V[A.ev[ea][0]], *pa1 = A.V[A.ev[ea][1]];
     real dA[3] = {pa1[0] - pa0[0], pa1[1] - pa0[1], pa1[2] - pa0[2]}, bxa[3];
     cross3(b, a, bxa);
-    for (int eb = 0; eb < ne; eb++) {
+    for (int eb = 0; eb < B.ne; eb++) {
       real c[3], d[3], dxc[3];
-      for (int i = 0; i < 3; i++) { c[i] = -nrmB[m.foot_edge_plane[eb][0]][i]; d[i] = -nrmB[m.foot_edge_plane[eb][1]][i]; }
+      for (int i = 0; i < 3; i++) { c[i] = -B.N[B.ep[eb][0]][i]; d[i] = -B.N[B.ep[eb][1]][i]; }
       cross3(d, c, dxc);
       real cba = dot3(c, bxa), dba = dot3(d, bxa), adc = dot3(a, dxc), bdc = dot3(b, dxc);
       if (!(cba * dba < 0 && adc * bdc < 0 && cba * bdc > 0)) continue;            // the two arcs do not cross on the Gauss map
-      const real *pb0 = VB[m.foot_edge_vert[eb][0]], *pb1 = VB[m.foot_edge_vert[eb][1]];
+      const real *pb0 = B.V[B.ev[eb][0]], *pb1 = B.V[B.ev[eb][1]];
       real dB[3] = {pb1[0] - pb0[0], pb1[1] - pb0[1], pb1[2] - pb0[2]}, n[3];
       cross3(dA, dB, n);
       real len2 = dot3(n, n);
       if (len2 < (real)1e-10 * dot3(dA, dA) * dot3(dB, dB)) continue;                  // parallel edges
       real inv = 1 / std::sqrt(len2);
       for (int i = 0; i < 3; i++) n[i] *= inv;
-      real rel[3] = {pa0[0] - cA[0], pa0[1] - cA[1], pa0[2] - cA[2]};
+      real rel[3] = {pa0[0] - A.c[0], pa0[1] - A.c[1], pa0[2] - A.c[2]};
       if (dot3(n, rel) < 0) for (int i = 0; i < 3; i++) n[i] = -n[i];                 // away from hull A
       real w[3] = {pb0[0] - pa0[0], pb0[1] - pa0[1], pb0[2] - pa0[2]};
       real sep = dot3(n, w);
       if (sep > edge_sep) { edge_sep = sep; eA_best = ea; eB_best = eb; for (int i = 0; i < 3; i++) edge_n[i] = n[i]; }
     }
   }
-  if (edge_sep > 0) return;
+  if (edge_sep > 0) return false;
   if (eA_best >= 0 && edge_sep > face_sep + (real)1e-4) {
     // closest points of the two supporting edges
-    const real *p1 = VA[m.foot_edge_vert[eA_best][0]], *q1 = VA[m.foot_edge_vert[eA_best][1]], *p2 = VB[m.foot_edge_vert[eB_best][0]], *q2 = VB[m.foot_edge_vert[eB_best][1]];
+    const real *p1 = A.V[A.ev[eA_best][0]], *q1 = A.V[A.ev[eA_best][1]], *p2 = B.V[B.ev[eB_best][0]], *q2 = B.V[B.ev[eB_best][1]];
     real d1[3], d2[3], r[3];
     for (int i = 0; i < 3; i++) { d1[i] = q1[i] - p1[i]; d2[i] = q2[i] - p2[i]; r[i] = p1[i] - p2[i]; }
     real a = dot3(d1, d1), e = dot3(d2, d2), f = dot3(d2, r), c = dot3(d1, r), b = dot3(d1, d2), den = a * e - b * b;
     real sA = den > (real)1e-18 ? std::min(std::max((b * f - c * e) / den, (real)0), (real)1) : 0;
     real tB = std::min(std::max((b * sA + f) / e, (real)0), (real)1);
     sA = std::min(std::max((b * tB - c) / a, (real)0), (real)1);
-    out.con_dist[8] = edge_sep;
-    for (int i = 0; i < 3; i++) out.con_pos[8][i] = (real)0.5 * (p1[i] + sA * d1[i] + p2[i] + tB * d2[i]);
-    make_frame(edge_n, out.con_frame[8]);
-    for (int c2 = 9; c2 < 12; c2++) for (int i = 0; i < 9; i++) out.con_frame[c2][i] = out.con_frame[8][i];
-    return;
+    out.dist[0] = edge_sep;
+    for (int i = 0; i < 3; i++) out.pos[0][i] = (real)0.5 * (p1[i] + sA * d1[i] + p2[i] + tB * d2[i]);
+    make_frame(edge_n, out.frame);
+    return true;
   }
   // face contact: reference face on hull `face_hull`, incident face = most anti-parallel face of the other hull
-  const real (*Vr)[3] = face_hull ? VB : VA; const real (*Vi)[3] = face_hull ? VA : VB;
-  const real (*Ni)[3] = face_hull ? nrmA : nrmB;
-  const real* nref = face_hull ? nrmB[face_idx] : nrmA[face_idx];
+  const Hull& Rh = face_hull ? B : A; const Hull& Ih = face_hull ? A : B;
+  const real* nref = Rh.N[face_idx];
   int inc = 0; real best = std::numeric_limits<real>::infinity();
-  for (int q = 0; q < np_; q++) { real v = dot3(Ni[q], nref); if (v < best) { best = v; inc = q; } }
+  for (int q = 0; q < Ih.np; q++) { real v = dot3(Ih.N[q], nref); if (v < best) { best = v; inc = q; } }
   real poly[2][2 * ODUCK_MAX_PVERT + 2][3];
-  int cur = 0, cnt = m.foot_plane_nvert[inc];
-  for (int k = 0; k < cnt; k++) for (int i = 0; i < 3; i++) poly[0][k][i] = Vi[m.foot_plane_vert[inc][k]][i];
-  const int nr = m.foot_plane_nvert[face_idx];
+  int cur = 0, cnt = Ih.pnv[inc];
+  for (int k = 0; k < cnt; k++) for (int i = 0; i < 3; i++) poly[0][k][i] = Ih.V[Ih.pv[inc][k]][i];
+  const int nr = Rh.pnv[face_idx];
   for (int k = 0; k < nr && cnt > 0; k++) {
-    const real *r0 = Vr[m.foot_plane_vert[face_idx][k]], *r1 = Vr[m.foot_plane_vert[face_idx][(k + 1) % nr]];
+    const real *r0 = Rh.V[Rh.pv[face_idx][k]], *r1 = Rh.V[Rh.pv[face_idx][(k + 1) % nr]];
     real e[3] = {r1[0] - r0[0], r1[1] - r0[1], r1[2] - r0[2]}, sd[3];
     cross3(e, nref, sd);                                                              // outward side-plane normal (loop is CCW from outside)
     int no = 0;
@@ -673,24 +672,159 @@ static void convex_convex(const OduckModel& m, const Scratch& s, Scratch& out) {
     }
     cur = 1 - cur; cnt = no;
   }
-  if (cnt == 0) return;
+  if (cnt == 0) return false;
   real dist[2 * ODUCK_MAX_PVERT + 2];
   bool mask[2 * ODUCK_MAX_PVERT + 2];
-  const real* r0 = Vr[m.foot_plane_vert[face_idx][0]];
+  const real* r0 = Rh.V[Rh.pv[face_idx][0]];
   for (int v = 0; v < cnt; v++) { real w[3] = {poly[cur][v][0] - r0[0], poly[cur][v][1] - r0[1], poly[cur][v][2] - r0[2]}; dist[v] = dot3(nref, w); mask[v] = dist[v] < 0; }
   int idx[4] = {0, 1, 2, 3};
   if (cnt > 4) manifold_points(cnt, poly[cur], mask, nref, idx);
   real n12[3] = {face_hull ? -nref[0] : nref[0], face_hull ? -nref[1] : nref[1], face_hull ? -nref[2] : nref[2]};   // geom1 -> geom2
-  real frame[9];
-  make_frame(n12, frame);
+  make_frame(n12, out.frame);
   for (int c = 0; c < 4; c++) {
-    int sl = 8 + c, v = idx[c];
+    int v = idx[c];
     bool ok = v < cnt;
     for (int p2 = 0; p2 < c && ok; p2++) ok = idx[p2] != v;                           // duplicates (cnt > 4 selection) are inactive
-    for (int i = 0; i < 9; i++) out.con_frame[sl][i] = frame[i];
     if (!ok) continue;
-    out.con_dist[sl] = dist[v];
-    for (int i = 0; i < 3; i++) out.con_pos[sl][i] = poly[cur][v][i] - (real)0.5 * dist[v] * nref[i];
+    out.dist[c] = dist[v];
+    for (int i = 0; i < 3; i++) out.pos[c][i] = poly[cur][v][i] - (real)0.5 * dist[v] * nref[i];
+  }
+  return true;
+}
+
+// world-frame polytope of foot k
+static void foot_hull(const OduckModel& m, const Scratch& s, int k, Hull& H) {
+  const int b = m.foot_body[k];
+  auto xform = [&](const double* v, real* o) { real t[3] = {(real)v[0], (real)v[1], (real)v[2]}; mat_vec(s.xmat[b], t, o); for (int i = 0; i < 3; i++) o[i] += s.xpos[b][i]; };
+  H.nv = m.foot_nvert; H.np = m.foot_nplane; H.ne = m.foot_nedge;
+  xform(m.foot_center[k], H.c);
+  for (int i = 0; i < H.nv; i++) xform(m.foot_vert[k][i], H.V[i]);
+  for (int q = 0; q < H.np; q++) {
+    real a[3] = {(real)m.foot_plane_normal[k][q][0], (real)m.foot_plane_normal[k][q][1], (real)m.foot_plane_normal[k][q][2]};
+    mat_vec(s.xmat[b], a, H.N[q]);
+    H.pnv[q] = m.foot_plane_nvert[q];
+    for (int j = 0; j < H.pnv[q]; j++) H.pv[q][j] = m.foot_plane_vert[q][j];
+  }
+  for (int e = 0; e < H.ne; e++) for (int j = 0; j < 2; j++) { H.ev[e][j] = m.foot_edge_vert[e][j]; H.ep[e][j] = m.foot_edge_plane[e][j]; }
+}
+
+// the two feet against each other: contact slots 8..11
+static void convex_convex(const OduckModel& m, const Scratch& s, Scratch& out) {
+  const int bA = m.foot_body[0], bB = m.foot_body[1];
+  for (int c = 8; c < 12; c++) { out.con_dist[c] = 1; out.con_b1[c] = bA; out.con_b2[c] = bB; out.con_mu[c] = (real)m.foot_friction; }
+  static thread_local Hull A, B;
+  foot_hull(m, s, 0, A);
+  foot_hull(m, s, 1, B);
+  real dc[3] = {B.c[0] - A.c[0], B.c[1] - A.c[1], B.c[2] - A.c[2]};
+  if (std::sqrt(dot3(dc, dc)) > 2 * (real)m.foot_radius) return;                      // bounding spheres apart: no contact
+  HullContacts hc;
+  if (!hull_hull(A, B, hc)) return;
+  for (int c = 0; c < 4; c++) {
+    out.con_dist[8 + c] = hc.dist[c];
+    for (int i = 0; i < 3; i++) out.con_pos[8 + c][i] = hc.pos[c][i];
+    for (int i = 0; i < 9; i++) out.con_frame[8 + c][i] = hc.frame[i];
+  }
+}
+
+// Height-field floor vs foot k.  MuJoCo / MJX treat a height field as a union of triangular prisms: every grid cell is split
+// along the diagonal (c, r) - (c + 1, r + 1) into two triangles, each extruded down to z = -size[3]
+// (engine_collision_convex.c mjc_ConvexHField; collision_convex.py hfield_convex **[upstream-memory]**).  PARITY UNPINNED, and
+// here a deliberate simplification as well: a general convex-convex test of a prism against the foot also offers
+// the prism's vertical side walls (and the foot's side faces) as contact axes, which yields horizontal contact normals
+// whenever a foot overlaps a neighbouring prism by less than its penetration depth -- on perfectly flat ground too.  The side
+// walls are interior to the terrain, so this restatement uses the terrain surface only:
+//   * for every triangle under the foot's bounding sphere, every foot face that looks down onto it (face normal . triangle
+//     normal < 0) is Sutherland-Hodgman clipped against the three vertical planes through the triangle's edges (all of
+//     them rather than one "incident" face: the sole is several nearly coplanar polygons, and a single pick would flip);
+//   * each clipped point below the triangle plane is a candidate: dist = signed distance to the plane, pos = midway, normal
+//     = the triangle normal (terrain = geom1, so it points from the terrain into the foot);
+//   * 4 of the candidates within 1 mm of the deepest one (plane_convex's support threshold) are kept by _manifold_points
+//     with the mean candidate normal, exactly like the plane and mesh colliders; repeated picks are inactive.
+// On an all-zero field this reduces to the plane collider's candidate set (sole vertices below z = 0) plus points on cell
+// borders.  The hfield sits at the world origin (checked by the MJCF compiler).
+static void hfield_convex(const OduckHandle& h, const Scratch& s, int k, int slot0, Scratch& out) {
+  const OduckModel& m = h.m;
+  const int b = m.foot_body[k], nrow = m.hfield_nrow, ncol = m.hfield_ncol;
+  const real sx = (real)m.hfield_size[0], sy = (real)m.hfield_size[1], sz = (real)m.hfield_size[2];
+  static thread_local Hull F;
+  foot_hull(m, s, k, F);
+  real frame0[9];
+  real up[3] = {0, 0, 1};
+  make_frame(up, frame0);
+  for (int c = 0; c < 4; c++) {
+    const int sl = slot0 + c;
+    out.con_dist[sl] = 1; out.con_b1[sl] = 0; out.con_b2[sl] = b; out.con_mu[sl] = (real)m.floor_friction;
+    for (int i = 0; i < 3; i++) out.con_pos[sl][i] = 0;
+    for (int i = 0; i < 9; i++) out.con_frame[sl][i] = frame0[i];
+  }
+  const real dx = 2 * sx / (ncol - 1), dy = 2 * sy / (nrow - 1), rb = (real)m.foot_radius;
+  int cmin = (int)std::floor((double)((F.c[0] - rb + sx) / dx)), cmax = (int)std::floor((double)((F.c[0] + rb + sx) / dx));
+  int rmin = (int)std::floor((double)((F.c[1] - rb + sy) / dy)), rmax = (int)std::floor((double)((F.c[1] + rb + sy) / dy));
+  cmin = std::max(cmin, 0); rmin = std::max(rmin, 0); cmax = std::min(cmax, ncol - 2); rmax = std::min(rmax, nrow - 2);
+  constexpr int MAXC = 2048, MAXP = ODUCK_MAX_PVERT + 4;
+  static thread_local real cd[MAXC], cp[MAXC][3], cn[MAXC][3];
+  static thread_local bool cm[MAXC];
+  int nc = 0;
+  real nmean[3] = {0, 0, 0};
+  auto H = [&](int r, int c) { return (real)h.hfield[(size_t)r * ncol + c] * sz; };
+  for (int r = rmin; r <= rmax; r++)
+    for (int c = cmin; c <= cmax; c++) {
+      const real x0 = c * dx - sx, x1 = (c + 1) * dx - sx, y0 = r * dy - sy, y1 = (r + 1) * dy - sy;
+      const real t[2][3][3] = {{{x0, y1, H(r + 1, c)}, {x0, y0, H(r, c)}, {x1, y1, H(r + 1, c + 1)}},       // counter-clockwise seen from above
+                               {{x0, y0, H(r, c)}, {x1, y0, H(r, c + 1)}, {x1, y1, H(r + 1, c + 1)}}};
+      for (int i = 0; i < 2; i++) {
+        const real (*T)[3] = t[i];
+        real top = std::max(T[0][2], std::max(T[1][2], T[2][2]));
+        if (F.c[2] - rb > top) continue;                             // the foot's bounding sphere is above this triangle
+        real e1[3], e2[3], n[3];
+        for (int a = 0; a < 3; a++) { e1[a] = T[1][a] - T[0][a]; e2[a] = T[2][a] - T[0][a]; }
+        cross3(e1, e2, n);
+        real ln = std::sqrt(dot3(n, n));
+        for (int a = 0; a < 3; a++) n[a] /= ln;
+        for (int q = 0; q < F.np; q++) {
+          if (!(dot3(F.N[q], n) < 0)) continue;                      // only the faces that look down onto the triangle
+          real poly[2][MAXP][3];
+          int cur = 0, cnt = F.pnv[q];
+          for (int v = 0; v < cnt; v++) for (int a = 0; a < 3; a++) poly[0][v][a] = F.V[F.pv[q][v]][a];
+          for (int e = 0; e < 3 && cnt > 0; e++) {
+            const real *r0 = T[e], *r1 = T[(e + 1) % 3];
+            const real sd[2] = {r1[1] - r0[1], -(r1[0] - r0[0])};     // outward normal of the vertical plane through the edge
+            int no = 0;
+            for (int v = 0; v < cnt; v++) {
+              const real *p0 = poly[cur][v], *p1 = poly[cur][(v + 1) % cnt];
+              real d0 = sd[0] * (p0[0] - r0[0]) + sd[1] * (p0[1] - r0[1]), d1 = sd[0] * (p1[0] - r0[0]) + sd[1] * (p1[1] - r0[1]);
+              if (d0 <= 0) { for (int a = 0; a < 3; a++) poly[1 - cur][no][a] = p0[a]; no++; }
+              if ((d0 <= 0) != (d1 <= 0)) { real tt = d0 / (d0 - d1); for (int a = 0; a < 3; a++) poly[1 - cur][no][a] = p0[a] + tt * (p1[a] - p0[a]); no++; }
+            }
+            cur = 1 - cur; cnt = no;
+          }
+          for (int v = 0; v < cnt && nc < MAXC; v++) {
+            real w[3] = {poly[cur][v][0] - T[0][0], poly[cur][v][1] - T[0][1], poly[cur][v][2] - T[0][2]};
+            real dist = dot3(n, w);
+            if (!(dist < 0)) continue;
+            cd[nc] = dist; cm[nc] = true;
+            for (int a = 0; a < 3; a++) { cp[nc][a] = poly[cur][v][a] - (real)0.5 * dist * n[a]; cn[nc][a] = n[a]; nmean[a] += n[a]; }
+            nc++;
+          }
+        }
+      }
+    }
+  if (nc == 0) return;
+  real nn = std::sqrt(dot3(nmean, nmean));
+  for (int a = 0; a < 3; a++) nmean[a] /= nn;                        // every triangle normal has n_z > 0
+  real deepest = 0;
+  for (int v = 0; v < nc; v++) deepest = std::min(deepest, cd[v]);
+  for (int v = 0; v < nc; v++) cm[v] = cd[v] < std::min((real)0, deepest + (real)1e-3);   // plane_convex's rule: within 1 mm of the deepest
+  int idx[4];
+  manifold_points(nc, cp, cm, nmean, idx);
+  for (int c = 0; c < 4; c++) {
+    const int sl = slot0 + c, v = idx[c];
+    bool unique = true;
+    for (int p2 = 0; p2 < c; p2++) unique &= idx[p2] != v;
+    if (!unique) continue;
+    out.con_dist[sl] = cd[v];
+    for (int i = 0; i < 3; i++) out.con_pos[sl][i] = cp[v][i];
+    make_frame(cn[v], out.con_frame[sl]);
   }
 }
 
@@ -1022,10 +1156,8 @@ static void forward(const OduckHandle& h, EnvState& e, Scratch& s) {
   // collision
   int ncon = ODUCK_CON_PER_PAIR * (2 + (m.enable_foot_foot ? 1 : 0));
   for (int c = 0; c < NCON; c++) { s.con_dist[c] = 1; s.con_b1[c] = s.con_b2[c] = 0; s.con_mu[c] = 0; for (int i = 0; i < 3; i++) s.con_pos[c][i] = 0; for (int i = 0; i < 9; i++) s.con_frame[c][i] = (i % 4 == 0); }
-  if (!m.floor_is_hfield) {
-    plane_convex(m, s, 0, 0, s);
-    plane_convex(m, s, 1, 4, s);
-  }
+  if (m.floor_is_hfield) { hfield_convex(h, s, 0, 0, s); hfield_convex(h, s, 1, 4, s); }
+  else { plane_convex(m, s, 0, 0, s); plane_convex(m, s, 1, 4, s); }
   if (m.enable_foot_foot) convex_convex(m, s, s);
   (void)ncon;
   make_constraint(h, e, s);
@@ -1473,7 +1605,8 @@ int oduck_create(const OduckModel* model, const OduckEnvConfig* cfg, int num_env
   if (!model || !cfg || !out || num_envs <= 0) return fail(ODUCK_ERR_ARG, "oduck_create: bad argument");
   if (model->abi_version != ODUCK_ABI_VERSION) return fail(ODUCK_ERR_MODEL, "oduck_create: model ABI version mismatch");
   if (model->nv > NV || model->nq > NQ || model->nbody > NB || model->nu > NU) return fail(ODUCK_ERR_MODEL, "oduck_create: model too large");
-  if (model->floor_is_hfield) return fail(ODUCK_ERR_UNSUPPORTED, "oduck_create: height-field floor not implemented yet");
+  if (model->floor_is_hfield && (!model->hfield_data || model->hfield_nrow < 2 || model->hfield_ncol < 2))
+    return fail(ODUCK_ERR_MODEL, "oduck_create: height-field floor without elevation data");
   if (cfg->action_max_delay > 8 || cfg->imu_max_delay > 8) return fail(ODUCK_ERR_ARG, "oduck_create: delay history too long");
   OduckHandle* h = new OduckHandle();
   h->m = *model;
@@ -1484,6 +1617,8 @@ int oduck_create(const OduckModel* model, const OduckEnvConfig* cfg, int num_env
     h->poly.assign(cfg->poly_coef, cfg->poly_coef + npoly);
   }
   h->cfg.poly_coef = nullptr;
+  if (model->floor_is_hfield) h->hfield.assign(model->hfield_data, model->hfield_data + (size_t)model->hfield_nrow * model->hfield_ncol);
+  h->m.hfield_data = nullptr;
   h->n = num_envs;
   h->launches = 0;
   h->nefc_fr = h->nefc_lim = 0;

@@ -1,0 +1,228 @@
+"""Height-field floor (rough_terrain scenes, reference xmls/scene_mjx_rough_terrain*.xml): the PNG asset
+decoder, and the CPU oracle's prism-vs-foot collision checked against the plane path and first principles.  The CUDA library
+still answers ODUCK_ERR_UNSUPPORTED for these scenes this round."""
+import copy
+import ctypes as C
+import os
+import struct
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import make_handle
+from open_duck_playground_b200 import capi, constants, mjcf
+from open_duck_playground_b200.mjcf import CompiledModel
+
+G = 9.81
+
+
+def _dump(lib, h):
+    out = np.zeros((h.n, lib.lib.oduck_debug_stride()))
+    lib.lib.oduck_debug_forward.argtypes = [C.c_void_p, C.c_void_p]
+    lib.check(lib.lib.oduck_debug_forward(h.h, out.ctypes.data))
+    return out
+
+
+def _png(a: np.ndarray, color_type: int, filt: int) -> bytes:
+    """Minimal PNG writer (8 bit, one filter type for every scanline) to feed the decoder."""
+    h, w = a.shape[:2]
+    ch = {0: 1, 2: 3, 4: 2, 6: 4}[color_type]
+    px = a.reshape(h, w, ch).astype(np.uint8)
+    raw = bytearray()
+    prev = np.zeros(w * ch, np.int32)
+    for r in range(h):
+        line = px[r].reshape(-1).astype(np.int32)
+        left = np.concatenate([np.zeros(ch, np.int32), line[:-ch]])
+        ul = np.concatenate([np.zeros(ch, np.int32), prev[:-ch]])
+        if filt == 0:
+            pred = 0
+        elif filt == 1:
+            pred = left
+        elif filt == 2:
+            pred = prev
+        elif filt == 3:
+            pred = (left + prev) // 2
+        else:
+            p = left + prev - ul
+            pa, pb, pc = np.abs(p - left), np.abs(p - prev), np.abs(p - ul)
+            pred = np.where((pa <= pb) & (pa <= pc), left, np.where(pb <= pc, prev, ul))
+        raw.append(filt)
+        raw += bytes(((line - pred) & 255).astype(np.uint8))
+        prev = line
+
+    def chunk(tag, data):
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data))
+    return (b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, color_type, 0, 0, 0)) +
+            chunk(b"IDAT", zlib.compress(bytes(raw))) + chunk(b"IEND", b""))
+
+
+@pytest.mark.parametrize("color_type", [0, 2, 6])
+@pytest.mark.parametrize("filt", [0, 1, 2, 3, 4])
+def test_png_decoder_roundtrip(tmp_path, color_type, filt):
+    rs = np.random.default_rng(color_type * 8 + filt)
+    ch = {0: 1, 2: 3, 6: 4}[color_type]
+    img = rs.integers(0, 256, (9, 13, ch), dtype=np.uint8)
+    p = tmp_path / "t.png"
+    p.write_bytes(_png(img, color_type, filt))
+    got = mjcf._read_png_gray(str(p))
+    assert got.shape == (9, 13) and np.array_equal(got, img[:, :, 0])
+    # MuJoCo's hfield convention: image rows are flipped (row 0 = -y edge) and the data normalised to [0, 1]
+    h = mjcf.load_hfield_png(str(p))
+    lo, hi = float(img[:, :, 0].min()), float(img[:, :, 0].max())
+    assert h.dtype == np.float32 and h.min() == 0.0 and h.max() == 1.0
+    assert np.allclose(h, (img[::-1, :, 0].astype(np.float64) - lo) / (hi - lo), atol=1e-7)
+
+
+def test_rough_terrain_blob_carries_the_hfield():
+    m = CompiledModel.load(constants.task_to_blob("rough_terrain_backlash"))
+    A = m.arrays
+    assert int(A["floor_is_hfield"]) == 1 and A["hfield_data"].shape == (256, 256)
+    assert np.allclose(A["hfield_size"], [10, 10, 0.01, 0.1])            # scene_mjx_rough_terrain*.xml <hfield size=...>
+    assert A["hfield_data"].min() == 0.0 and A["hfield_data"].max() == 1.0
+    s = capi.model_to_struct(m)
+    assert s.hfield_nrow == 256 and s.hfield_ncol == 256 and s.hfield_size[2] == 0.01 and bool(s.hfield_data)
+    flat = capi.model_to_struct(CompiledModel.load(constants.task_to_blob("flat_terrain_backlash")))
+    assert flat.hfield_nrow == 0 and not bool(flat.hfield_data)
+
+
+def _hfield_model(model, data, size=(10.0, 10.0, 0.01, 0.1)):
+    m = copy.deepcopy(model)
+    m.arrays["floor_is_hfield"] = np.array(1, np.int32)
+    m.arrays["hfield_data"] = np.ascontiguousarray(data, np.float32)
+    m.arrays["hfield_size"] = np.array(size, np.float64)
+    return m
+
+
+def _poses(model, n, seed, tilt=0.15, dz=(-0.01, 0.03)):
+    """Keyframe poses with small tilts and heights that straddle first touch."""
+    rs = np.random.default_rng(seed)
+    q = np.tile(model.key_qpos[: model.nq], (n, 1)).astype(np.float32)
+    q[:, 0:2] = rs.uniform(-3, 3, (n, 2))
+    q[:, 2] += rs.uniform(dz[0], dz[1], n)
+    ax = rs.normal(size=(n, 3)); ax /= np.linalg.norm(ax, axis=1, keepdims=True)
+    ang = rs.uniform(0, tilt, n)
+    q[:, 3] = np.cos(ang / 2); q[:, 4:7] = ax * np.sin(ang / 2)[:, None]
+    q[:, 7:] += rs.uniform(-0.1, 0.1, (n, model.nq - 7)).astype(np.float32)
+    return q
+
+
+def _lowest_foot_vertex(model, q):
+    """z of the lowest hull vertex of each foot (the true penetration of a z = 0 floor), from the independent numpy kinematics."""
+    z = np.zeros((len(q), 2))
+    nvt = int(model.arrays["foot_nvert"])
+    for i in range(len(q)):
+        xpos, xmat, _, _ = mjcf.world_kinematics(model, q[i].astype(np.float64))
+        for k in range(2):
+            b = int(model.arrays["foot_body"][k])
+            z[i, k] = (xpos[b] + model.arrays["foot_vert"][k][:nvt] @ xmat[b].T)[:, 2].min()
+    return z
+
+
+def test_flat_hfield_matches_the_plane(oracle, model_backlash, poly_table):
+    """An all-zero height field is the z = 0 plane: same touch / no-touch answer, the deepest contact is the lowest hull vertex
+    whenever the sole lies inside one prism, contacts point up, and the resulting motion agrees with the plane path."""
+    n = 96
+    hf = _hfield_model(model_backlash, np.zeros((64, 64)))
+    hp, hh = make_handle(oracle, model_backlash, poly_table, n), make_handle(oracle, hf, poly_table, n)
+    q = _poses(model_backlash, n, 0, tilt=0.06, dz=(-0.004, 0.02))
+    v = np.zeros((n, model_backlash.nv), np.float32)
+    for h in (hp, hh):
+        h.set_state(q.ctypes.data, v.ctypes.data, v.ctypes.data)
+    dp, dh = _dump(oracle, hp), _dump(oracle, hh)
+    nrm = dh[:, 2560:2560 + 24].reshape(n, 8, 3)
+    dp, dh = dp[:, 1120:1128], dh[:, 1120:1128]
+    zmin = _lowest_foot_vertex(model_backlash, q)
+    touching = (dp < 0).any(axis=1)
+    assert 10 < touching.sum() and (~touching).sum() > 3
+    exact = total = 0
+    for k in range(2):
+        a, b = dp[:, 4 * k:4 * k + 4].min(axis=1), dh[:, 4 * k:4 * k + 4].min(axis=1)
+        hit = zmin[:, k] < 0
+        assert np.array_equal(hit, a < 0) and np.array_equal(hit, b < 0)          # same touch / no-touch answer as the plane
+        assert np.all(b[hit] >= zmin[hit, k] - 1e-7)                               # never deeper than the real penetration
+        assert np.all(b[hit] <= zmin[hit, k] + 1e-3) and np.all(a[hit] <= zmin[hit, k] + 1e-3)   # kept contacts: within 1 mm of it
+        exact += int((np.abs(b[hit] - a[hit]) < 1e-7).sum()); total += int(hit.sum())
+    assert exact > 0.5 * total                                                     # mostly the very same deepest pick as the plane
+    act = dh < 0
+    assert (nrm[act][:, 2] > 0.99).mean() > 0.9 and np.all(nrm[act][:, 2] > -1e-9)
+    # dynamics: the resulting motion agrees (the manifolds may pick different points of the same sole)
+    for h in (hp, hh):
+        h.physics_substeps(0, 5)
+    qp, qh = hp.buffer_numpy("QPOS"), hh.buffer_numpy("QPOS")
+    assert np.median(np.abs(qp - qh)[:, :3]) < 2e-4 and np.median(np.abs(qp - qh)) < 5e-4 and np.abs(qp - qh).max() < 2e-2
+    # settled: same standing height and the same total normal force (= weight) on both floors
+    for h in (hp, hh):
+        h.physics_substeps(0, 1000)
+    up = (hp.buffer_numpy("SENSORDATA")[:, 11] > 0.98) & (hh.buffer_numpy("SENSORDATA")[:, 11] > 0.98)     # still upright on both
+    assert up.sum() > 0.8 * n
+    zp, zh = hp.buffer_numpy("QPOS")[up, 2], hh.buffer_numpy("QPOS")[up, 2]
+    assert np.median(np.abs(zp - zh)) < 1e-3 and np.abs(zp - zh).max() < 5e-3     # rest poses differ within the joint backlash
+    fp, fh = hp.buffer_numpy("EFC_FORCE")[up, 38:70].sum(axis=1), hh.buffer_numpy("EFC_FORCE")[up, 38:70].sum(axis=1)
+    assert np.median(np.abs(fp - fh) / fp) < 0.01
+
+
+def test_tilted_hfield_normals_and_signs(oracle, model_backlash, poly_table):
+    """A ramp z = a x: every contact normal is the ramp normal and points from the terrain into the foot."""
+    n = 32
+    nrow = ncol = 41
+    x = np.linspace(0, 1, ncol)[None, :].repeat(nrow, 0)          # elevation 0..1 across x -> z = sz * (x + sx) / (2 sx)
+    size = (4.0, 4.0, 0.8, 0.1)
+    hf = _hfield_model(model_backlash, x, size)
+    hf.arrays["act_kp"][:] = 0
+    h = make_handle(oracle, hf, poly_table, n)
+    slope = size[2] / (2 * size[0])
+    q = _poses(model_backlash, n, 1)
+    q[:, 2] += (q[:, 0] + size[0]) * slope + 0.012
+    v = np.zeros((n, model_backlash.nv), np.float32)
+    h.set_state(q.ctypes.data, v.ctypes.data, v.ctypes.data)
+    out = _dump(oracle, h)
+    dist = out[:, 1120:1128]
+    pos = out[:, 1136:1136 + 24].reshape(n, 8, 3)
+    nrm = out[:, 2560:2560 + 24].reshape(n, 8, 3)
+    want = np.array([-slope, 0, 1]) / np.sqrt(1 + slope * slope)
+    act = dist < 0
+    assert act.sum() > 20
+    assert np.abs(nrm[act] - want).max() < 1e-6
+    # contact points lie within the penetration depth of the ramp surface
+    surf = (pos[act][:, 0] + size[0]) * slope
+    assert np.abs(pos[act][:, 2] - surf).max() < np.abs(dist[act]).max() + 1e-6
+    assert dist[act].min() > -0.05
+
+
+def test_duck_stands_on_rough_terrain(oracle, poly_table):
+    """The shipped rough-terrain scene: the duck settles on the 1 cm noise field and the contact forces carry its weight."""
+    m = CompiledModel.load(constants.task_to_blob("rough_terrain_backlash"))
+    h = make_handle(oracle, m, poly_table, 2)
+    q = np.tile(m.key_qpos[: m.nq], (2, 1)).astype(np.float32)
+    q[1, 0:2] = [2.37, -4.11]                                       # a second patch of the terrain
+    q[:, 2] += 0.01
+    v = np.zeros((2, m.nv), np.float32)
+    h.set_state(q.ctypes.data, v.ctypes.data, v.ctypes.data)
+    h.physics_substeps(0, 1000)
+    f = h.buffer_numpy("EFC_FORCE")
+    dist = h.buffer_numpy("CONTACT_DIST")
+    weight = m.body_mass[: m.nbody].sum() * G
+    qpos = h.buffer_numpy("QPOS")
+    assert np.all(np.isfinite(qpos))
+    for e in range(2):
+        assert (dist[e, :8] < 0).sum() >= 3
+        # pyramid edges: normal component of every edge force is the edge force itself; normals tilt by < ~30 deg on this field
+        normal = f[e, 38:70].sum()
+        assert 0.85 * weight < normal < 1.1 * weight
+        assert 0.12 < qpos[e, 2] < 0.22 and abs(np.linalg.norm(qpos[e, 3:7]) - 1) < 1e-9
+    qv = h.buffer_numpy("QVEL")
+    assert np.abs(qv[:, :6]).max() < 0.2                             # at rest
+
+
+def test_hfield_env_step_runs(oracle, poly_table):
+    """reset + step of the Joystick env on the rough-terrain task through the oracle library."""
+    from open_duck_playground_b200 import rng as jr
+    from open_duck_playground_b200.joystick import Joystick
+    import torch
+    env = Joystick("rough_terrain_backlash", library=oracle)
+    st = env.reset(jr.split(jr.PRNGKey(0), 4))
+    for _ in range(3):
+        st = env.step(st, torch.zeros(4, 14))
+    assert torch.isfinite(st.reward).all() and torch.isfinite(st.obs["state"]).all()
+    assert float(st.done.max()) == 0.0
