@@ -13,7 +13,7 @@
 //   geoms_colliding                  open_duck_mini_v2/joystick.py:313-318,424-429
 //   get_sensor_data                  open_duck_mini_v2/base.py:234-264
 // PINNED parts (checked against the reference's own NumPy twins / data in tests/):
-//   rewards            common/rewards.py:11-125           (twin: common/rewards_numpy.py)
+//   rewards            common/rewards.py:11-241           (twin: common/rewards_numpy.py)
 //   imitation reward   open_duck_mini_v2/custom_rewards.py:4-149 (twin: custom_rewards_numpy.py)
 //   reference motion   common/poly_reference_motion.py:148-168   (twin: poly_reference_motion_numpy.py)
 // The env logic follows open_duck_mini_v2/joystick.py:206-725 line by line, jax.random is restated as
@@ -1318,6 +1318,70 @@ static void compute_rewards_standing(const OduckHandle& h, const real* command, 
   out[5] = nan_to_num(herr) * (cmd_norm > (real)0.01 ? 1 : 0);
 }
 
+// The rest of the reward library (common/rewards.py:37-90,120,152-241; twin common/rewards_numpy.py): terms that neither
+// Joystick nor Standing wires in.  Pure functions of one env's quantities, argument for argument like the
+// reference; checked against the NumPy twins (tests/golden/rewards_library.npz).  Not yet reachable from OduckEnvConfig.
+struct RewardLibrary {
+  static real sq(real x) { return x * x; }
+  static real cost_lin_vel_z(const real* global_linvel) { return nan_to_num(sq(global_linvel[2])); }                       // :37-38
+  static real cost_ang_vel_xy(const real* global_angvel) { return nan_to_num(sq(global_angvel[0]) + sq(global_angvel[1])); }   // :41-42
+  static real cost_base_height(real base_height, real target) { return nan_to_num(sq(base_height - target)); }              // :49-50
+  static real reward_base_y_swing(real base_y_speed, real freq, real amplitude, real t, real tracking_sigma) {              // :53-65
+    const real target = amplitude * std::sin(2 * (real)M_PI * freq * t);
+    return nan_to_num(std::exp(-sq(target - base_y_speed) / tracking_sigma));
+  }
+  static real cost_energy(int n, const real* qvel, const real* qfrc_actuator) {                                             // :73-74
+    real a = 0;
+    for (int i = 0; i < n; i++) a += std::fabs(qvel[i]) * std::fabs(qfrc_actuator[i]);
+    return nan_to_num(a);
+  }
+  static real cost_joint_pos_limits(int n, const real* qpos, const real* soft_lowers, const real* soft_uppers) {            // :85-90
+    real a = 0;
+    for (int i = 0; i < n; i++) a += -std::min(qpos[i] - soft_lowers[i], (real)0) + std::max(qpos[i] - soft_uppers[i], (real)0);
+    return nan_to_num(a);
+  }
+  static real cost_termination(real done) { return done; }                                                                   // :120-121
+  static real cost_joint_deviation_hip(const real* qpos, const real* cmd, int n_hip, const int* hip, const real* default_pose) {   // :152-158
+    real a = 0;
+    for (int i = 0; i < n_hip; i++) a += std::fabs(qpos[hip[i]] - default_pose[hip[i]]);
+    return nan_to_num(a * (std::fabs(cmd[1]) > (real)0.1 ? 1 : 0));
+  }
+  static real cost_joint_deviation_knee(const real* qpos, int n_knee, const int* knee, const real* default_pose) {          // :161-167
+    real a = 0;
+    for (int i = 0; i < n_knee; i++) a += std::fabs(qpos[knee[i]] - default_pose[knee[i]]);
+    return nan_to_num(a);
+  }
+  static real cost_pose(int n, const real* qpos, const real* default_pose, const real* weights) {                           // :170-175
+    real a = 0;
+    for (int i = 0; i < n; i++) a += sq(qpos[i] - default_pose[i]) * weights[i];
+    return nan_to_num(a);
+  }
+  // :180-183 -- as written upstream: the norm of the BASE's horizontal velocity, counted once per foot in contact
+  static real cost_feet_slip(const real* contact, const real* global_linvel) {
+    const real v = std::sqrt(sq(global_linvel[0]) + sq(global_linvel[1]));
+    return nan_to_num(v * contact[0] + v * contact[1]);
+  }
+  static real cost_feet_clearance(const real (*feet_vel)[3], const real (*foot_pos)[3], real max_foot_height) {             // :187-198
+    real a = 0;
+    for (int f = 0; f < 2; f++) a += std::fabs(foot_pos[f][2] - max_foot_height) * std::sqrt(std::sqrt(sq(feet_vel[f][0]) + sq(feet_vel[f][1])));
+    return nan_to_num(a);
+  }
+  static real cost_feet_height(const real* swing_peak, const real* first_contact, real max_foot_height) {                   // :202-208
+    real a = 0;
+    for (int f = 0; f < 2; f++) a += sq(swing_peak[f] / max_foot_height - 1) * first_contact[f];
+    return nan_to_num(a);
+  }
+  static real reward_feet_air_time(const real* air_time, const real* first_contact, const real* commands, real threshold_min, real threshold_max) {   // :212-224
+    const real cmd_norm = std::sqrt(sq(commands[0]) + sq(commands[1]) + sq(commands[2]));
+    real a = 0;
+    for (int f = 0; f < 2; f++) a += std::min((air_time[f] - threshold_min) * first_contact[f], threshold_max - threshold_min);
+    return nan_to_num(a * (cmd_norm > (real)0.01 ? 1 : 0));
+  }
+  static real reward_feet_phase(const real (*foot_pos)[3], const real* rz) {                                                // :228-241
+    return nan_to_num(std::exp(-(sq(foot_pos[0][2] - rz[0]) + sq(foot_pos[1][2] - rz[1])) / (real)0.01));
+  }
+};
+
 // joystick.py:487-620.  Advances e.rng exactly as the reference (5 splits).
 static void get_obs(const OduckHandle& h, EnvState& e, const real* contact) {
   const OduckModel& m = h.m;
@@ -1763,6 +1827,37 @@ int oduck_test_rewards_standing(OduckHandle* h, const double* in, double* out6) 
   real o[6];
   compute_rewards_standing(*h, cmd, up, af, ac, la, q, qd, o);
   for (int k = 0; k < 6; k++) out6[k] = (double)(o[k]);
+  return ODUCK_OK;
+}
+
+// Reward-library terms (RewardLibrary above), one env per call.  `in` (doubles), nu = ODUCK joints:
+//   global_linvel[3] global_angvel[3] base_height target base_y_speed freq amplitude t tracking_sigma qvel[nu] qfrc_actuator[nu]
+//   qpos[nu] soft_lowers[nu] soft_uppers[nu] done command[7] default_pose[nu] n_hip hip[4] n_knee knee[4] weights[nu] contact[2]
+//   feet_vel[2][3] foot_pos[2][3] max_foot_height swing_peak[2] first_contact[2] air_time[2] threshold_min threshold_max rz[2]
+// out15: lin_vel_z ang_vel_xy base_height base_y_swing energy joint_pos_limits termination joint_deviation_hip
+//        joint_deviation_knee pose feet_slip feet_clearance feet_height feet_air_time feet_phase
+int oduck_test_reward_library(int nu, const double* in, double* out15) {
+  if (!in || !out15 || nu < 1 || nu > ODUCK_MAX_NU) return fail(ODUCK_ERR_ARG, "oduck_test_reward_library: bad argument");
+  const int total = 13 + 5 * nu + 1 + 7 + nu + 10 + nu + 2 + 12 + 1 + 6 + 2 + 2;
+  std::vector<real> v(in, in + total);
+  const real* p = v.data();
+  auto take = [&](int n) { const real* q = p; p += n; return q; };
+  const real *glv = take(3), *gav = take(3), *sc = take(7), *qvel = take(nu), *qfrc = take(nu), *qpos = take(nu), *lo = take(nu), *hi = take(nu);
+  const real *done = take(1), *cmd = take(7), *dflt = take(nu), *hipr = take(5), *kneer = take(5), *w = take(nu), *contact = take(2);
+  const real (*feet_vel)[3] = reinterpret_cast<const real (*)[3]>(take(6));
+  const real (*foot_pos)[3] = reinterpret_cast<const real (*)[3]>(take(6));
+  const real *mfh = take(1), *peak = take(2), *first = take(2), *air = take(2), *thr = take(2), *rz = take(2);
+  int hip[4], knee[4];
+  const int n_hip = (int)hipr[0], n_knee = (int)kneer[0];
+  if (n_hip < 0 || n_hip > 4 || n_knee < 0 || n_knee > 4) return fail(ODUCK_ERR_ARG, "oduck_test_reward_library: at most 4 hip / knee indices");
+  for (int i = 0; i < 4; i++) { hip[i] = (int)hipr[1 + i]; knee[i] = (int)kneer[1 + i]; }
+  typedef RewardLibrary R;
+  const real o[15] = {R::cost_lin_vel_z(glv), R::cost_ang_vel_xy(gav), R::cost_base_height(sc[0], sc[1]), R::reward_base_y_swing(sc[2], sc[3], sc[4], sc[5], sc[6]),
+                      R::cost_energy(nu, qvel, qfrc), R::cost_joint_pos_limits(nu, qpos, lo, hi), R::cost_termination(done[0]),
+                      R::cost_joint_deviation_hip(qpos, cmd, n_hip, hip, dflt), R::cost_joint_deviation_knee(qpos, n_knee, knee, dflt), R::cost_pose(nu, qpos, dflt, w),
+                      R::cost_feet_slip(contact, glv), R::cost_feet_clearance(feet_vel, foot_pos, mfh[0]), R::cost_feet_height(peak, first, mfh[0]),
+                      R::reward_feet_air_time(air, first, cmd, thr[0], thr[1]), R::reward_feet_phase(foot_pos, rz)};
+  for (int k = 0; k < 15; k++) out15[k] = (double)(o[k]);
   return ODUCK_OK;
 }
 

@@ -48,3 +48,35 @@ def test_reward_terms_match_numpy_twins(oracle, model_backlash, poly_table):
     # the fixture exercises the gates: zero commands give stand_still > 0 and imitation == 0
     zero = np.linalg.norm(g["command"][:, :3], axis=1) < 0.01
     assert zero.any() and np.all(g["terms"][zero, 6] == 0) and np.all(g["terms"][zero, 4] > 0)
+
+
+LIBRARY_TERMS = ["lin_vel_z", "ang_vel_xy", "base_height", "base_y_swing", "energy", "joint_pos_limits", "termination", "joint_deviation_hip",
+                 "joint_deviation_knee", "pose", "feet_slip", "feet_clearance", "feet_height", "feet_air_time", "feet_phase"]
+
+
+def test_reward_library_matches_numpy_twins(oracle):
+    """The reward-library terms no shipped env wires in (rewards.py:37-90,120,152-241) against the reference's
+    NumPy twins, argument for argument."""
+    g = np.load(os.path.join(GOLD, "rewards_library.npz"))
+    fn = oracle.lib.oduck_test_reward_library
+    fn.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+    nu = 14
+    pad4 = lambda a: np.concatenate([[len(a)], a, np.zeros(4 - len(a))]).astype(np.float64)   # noqa: E731
+    out, worst = np.zeros(15), np.zeros(15)
+    for k in range(len(g["terms"])):
+        vec = np.concatenate([
+            g["global_linvel"][k], g["global_angvel"][k],
+            [g["base_height"][k], g["base_height_target"][k], g["base_y_speed"][k], g["freq"][k], g["amplitude"][k], g["t"][k], g["tracking_sigma"][k]],
+            g["qvel"][k], g["qfrc_actuator"][k], g["qpos"][k], g["soft_lowers"], g["soft_uppers"], [g["done"][k]], g["command"][k], g["default_pose"],
+            pad4(g["hip_indices"]), pad4(g["knee_indices"]), g["weights"], g["contact"][k], g["feet_vel"][k].ravel(), g["foot_pos"][k].ravel(),
+            [g["max_foot_height"][k]], g["swing_peak"][k], g["first_contact"][k], g["air_time"][k], [g["threshold_min"][k], g["threshold_max"][k]], g["rz"][k]])
+        oracle.check(fn(nu, vec.ctypes.data, out.ctypes.data))
+        worst = np.maximum(worst, np.abs(out - g["terms"][k]) / np.maximum(1.0, np.abs(g["terms"][k])))
+    assert np.all(worst < 1e-12), dict(zip(LIBRARY_TERMS, worst))
+    t = g["terms"]
+    # every gate is hit from both sides in the vectors
+    for name in ("termination", "joint_deviation_hip", "feet_slip", "feet_height", "feet_air_time"):
+        col = t[:, LIBRARY_TERMS.index(name)]
+        assert (col == 0).any() and (col != 0).any(), name
+    assert (t[:, LIBRARY_TERMS.index("feet_air_time")] < 0).any()          # air time below threshold_min is a penalty (rewards.py:220)
+    assert np.isclose(t[:, LIBRARY_TERMS.index("feet_air_time")].max(), 0.8) or t[:, LIBRARY_TERMS.index("feet_air_time")].max() < 0.8   # clip at max - min per foot
