@@ -96,7 +96,7 @@ __device__ __forceinline__ void store_out(const WarpSmem& s, int lane, float* __
 
 // ------------------------------------------------------------------------------------------------- kernels
 // A8 / A9 of SURVEY 8a: n x (forward + euler), or one forward without integration (mjx_env.init's forward).
-template <bool DBG>
+template <bool DBG, bool HF>
 __global__ void __launch_bounds__(WPB * 32, CTAS_PER_SM) k_physics(Params p) {
   extern __shared__ __align__(16) unsigned char raw[];
   DevModel* mp; DevEnvCfg* cp; WarpSmem* ws;
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(WPB * 32, CTAS_PER_SM) k_physics(Params p) {
     __syncwarp();
     float* dbg = DBG ? p.dbg + (size_t)env * DBG_STRIDE : nullptr;
     // like k_step: one CTA barrier per substep keeps the CTA's warps on the same stretch of the instruction stream
-    for (int k = 0; k < p.nsub; ++k) forward_euler<DBG, !DBG>(m, s, L, lane, k == p.nsub - 1, p.integrate != 0, s.outrec, dbg, p.ffmodel, p.ffscratch + (size_t)env * (FFJ_SIZE + FFV_SIZE));
+    for (int k = 0; k < p.nsub; ++k) forward_euler<DBG, !DBG, HF>(m, s, L, lane, k == p.nsub - 1, p.integrate != 0, s.outrec, dbg, p.ffmodel, p.ffscratch + (size_t)env * (FFJ_SIZE + FFV_SIZE), p.hfmodel, HF ? p.hfscratch + (size_t)env * HF_SCRATCH : nullptr);
     __syncwarp();
     store_phys(m, s, L, lane, ph);
     store_out(s, lane, p.out + (size_t)env * OUT_STRIDE);
@@ -171,6 +171,7 @@ __device__ __forceinline__ float feet_contact(const WarpSmem& s, int lane) {   /
 }
 
 // A2 (+A9, first_state store): Joystick.reset for the masked envs.
+template <bool HF>
 __global__ void __launch_bounds__(WPB * 32, CTAS_PER_SM) k_reset(Params p) {
   extern __shared__ __align__(16) unsigned char raw[];
   DevModel* mp; DevEnvCfg* cp; WarpSmem* ws;
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(WPB * 32, CTAS_PER_SM) k_reset(Params p) {
     { const int a = m.d_act[lane]; L.ctrl = a >= 0 ? s.qpos[m.act_qadr[a]] : 0.f; }
     for (int i = lane; i < OUT_STRIDE; i += 32) s.outrec[i] = 0.f;
     __syncwarp();
-    forward_euler<false>(m, s, L, lane, true, false, s.outrec, nullptr, p.ffmodel, p.ffscratch + (size_t)env * (FFJ_SIZE + FFV_SIZE));   // mjx_env.init
+    forward_euler<false, false, HF>(m, s, L, lane, true, false, s.outrec, nullptr, p.ffmodel, p.ffscratch + (size_t)env * (FFJ_SIZE + FFV_SIZE), p.hfmodel, HF ? p.hfscratch + (size_t)env * HF_SCRATCH : nullptr);   // mjx_env.init
     __syncwarp();
     EnvRegs er;
     er.rng = rng;
@@ -264,7 +265,8 @@ __global__ void __launch_bounds__(WPB * 32, CTAS_PER_SM) k_reset(Params p) {
   }
 }
 
-// A1 + A16: Joystick.step fused with EpisodeWrapper + AutoResetWrapper.
+// A1 + A16: Joystick.step fused with EpisodeWrapper + AutoResetWrapper.  HF = height-field floor (rough_terrain scenes).
+template <bool HF>
 __global__ void __launch_bounds__(WPB * 32, CTAS_PER_SM) k_step(Params p) {
   extern __shared__ __align__(16) unsigned char raw[];
   DevModel* mp; DevEnvCfg* cp; WarpSmem* ws;
@@ -323,7 +325,7 @@ __global__ void __launch_bounds__(WPB * 32, CTAS_PER_SM) k_step(Params p) {
     { const int a = m.d_act[lane]; const float t = __shfl_sync(FULLMASK, tgt, a < 0 ? 0 : a); if (a >= 0) L.ctrl = t; }
     // physics: n_substeps x mjx.step (joystick.py:420)
     for (int k = 0; k < c.n_substeps; ++k)
-      forward_euler<false, true>(m, s, L, lane, k == c.n_substeps - 1, true, s.outrec, nullptr, p.ffmodel, p.ffscratch + (size_t)env * (FFJ_SIZE + FFV_SIZE));
+      forward_euler<false, true, HF>(m, s, L, lane, k == c.n_substeps - 1, true, s.outrec, nullptr, p.ffmodel, p.ffscratch + (size_t)env * (FFJ_SIZE + FFV_SIZE), p.hfmodel, HF ? p.hfscratch + (size_t)env * HF_SCRATCH : nullptr);
     __syncwarp();
     er.targets = tgt;
     // contacts / air time / swing peak (joystick.py:424-435)
@@ -736,6 +738,7 @@ static Params make_params(OduckHandle* h) {
   p.reward = h->reward; p.done = h->done; p.trunc = h->trunc; p.metrics = h->metrics;
   p.first_phys = h->first_phys; p.first_obs_state = h->first_obs_state; p.first_obs_priv = h->first_obs_priv; p.dbg = h->dbg;
   p.ffmodel = h->dff; p.ffscratch = h->ffscratch;
+  p.hfmodel = h->dhf; p.hfscratch = h->hfscratch;
   p.N = h->n;
   return p;
 }
@@ -762,7 +765,7 @@ int oduck_destroy(OduckHandle* h) {
   if (!h) return ODUCK_OK;
   cudaSetDevice(h->device);
   void* ptrs[] = {h->dmodel, h->dcfg, h->poly, h->phys, h->dr, h->out, h->info, h->obs_state, h->obs_priv, h->reward, h->done, h->trunc,
-                  h->metrics, h->first_phys, h->first_obs_state, h->first_obs_priv, h->dbg, h->policy_scratch, h->dff, h->ffscratch};
+                  h->metrics, h->first_phys, h->first_obs_state, h->first_obs_priv, h->dbg, h->policy_scratch, h->dff, h->ffscratch, h->dhf, h->hfdata, h->hfscratch};
   for (void* q : ptrs) if (q) cudaFree(q);
   delete h;
   return ODUCK_OK;
@@ -772,7 +775,8 @@ int oduck_create(const OduckModel* model, const OduckEnvConfig* cfg, int num_env
   if (!model || !cfg || !out || num_envs <= 0) return fail(ODUCK_ERR_ARG, "oduck_create: bad argument");
   if (model->abi_version != ODUCK_ABI_VERSION) return fail(ODUCK_ERR_MODEL, "oduck_create: model ABI version mismatch");
   if (cfg->task != ODUCK_TASK_JOYSTICK && cfg->task != ODUCK_TASK_STANDING) return fail(ODUCK_ERR_ARG, "oduck_create: unknown task");
-  if (model->floor_is_hfield) return fail(ODUCK_ERR_UNSUPPORTED, "oduck_create: height-field floor not implemented yet");
+  if (model->floor_is_hfield && (!model->hfield_data || model->hfield_nrow < 2 || model->hfield_ncol < 2))
+    return fail(ODUCK_ERR_MODEL, "oduck_create: height-field floor without elevation data");
   if (cfg->action_max_delay > MAX_DELAY || cfg->imu_max_delay * 3 > 16 || cfg->action_max_delay < 1) return fail(ODUCK_ERR_ARG, "oduck_create: delay history out of range");
   int ndev = 0;
   CUDA_TRY(cudaGetDeviceCount(&ndev));
@@ -811,6 +815,20 @@ int oduck_create(const OduckModel* model, const OduckEnvConfig* cfg, int num_env
     CUDA_TRY(cudaMemcpy(h->dff, &f, sizeof(DevFF), cudaMemcpyHostToDevice));
   }
   ALLOC(h->ffscratch, N * (FFJ_SIZE + FFV_SIZE));
+  if (model->floor_is_hfield) {
+    const size_t ns = (size_t)model->hfield_nrow * model->hfield_ncol;
+    ALLOC(h->hfdata, ns);
+    CUDA_TRY(cudaMemcpy(h->hfdata, model->hfield_data, ns * sizeof(float), cudaMemcpyHostToDevice));
+    ALLOC(h->hfscratch, N * HF_SCRATCH);
+    DevHF d;
+    d.nrow = model->hfield_nrow; d.ncol = model->hfield_ncol;
+    d.sx = (float)model->hfield_size[0]; d.sy = (float)model->hfield_size[1]; d.sz = (float)model->hfield_size[2];
+    d.dx = (float)(2.0 * model->hfield_size[0] / (model->hfield_ncol - 1)); d.dy = (float)(2.0 * model->hfield_size[1] / (model->hfield_nrow - 1));
+    d.data = h->hfdata;
+    if (cudaMalloc((void**)&h->dhf, sizeof(DevHF)) != cudaSuccess) { oduck_destroy(h); return fail(ODUCK_ERR_ALLOC, "oduck_create: cudaMalloc failed"); }
+    CUDA_TRY(cudaMemcpy(h->dhf, &d, sizeof(DevHF), cudaMemcpyHostToDevice));
+  }
+  h->hm.hfield_data = nullptr;      // the caller's array is not kept
   ALLOC(h->phys, N * PHYS_STRIDE); ALLOC(h->dr, N * DR_STRIDE); ALLOC(h->out, N * OUT_STRIDE); ALLOC(h->info, N * INFO_STRIDE);
   ALLOC(h->obs_state, N * ODUCK_OBS_STATE); ALLOC(h->obs_priv, N * ODUCK_OBS_PRIV);
   ALLOC(h->reward, N); ALLOC(h->done, N); ALLOC(h->trunc, N); ALLOC(h->metrics, N * ODUCK_NMETRIC);
@@ -836,10 +854,17 @@ int oduck_create(const OduckModel* model, const OduckEnvConfig* cfg, int num_env
     CUDA_TRY(fill(h->phys, ph)); CUDA_TRY(fill(h->first_phys, ph)); CUDA_TRY(fill(h->dr, dr)); CUDA_TRY(fill(h->info, inf));
   }
   h->smem_bytes = (int)(((sizeof(DevModel) + 15) & ~15u) + ((sizeof(DevEnvCfg) + 15) & ~15u) + WPB * sizeof(WarpSmem));
-  CUDA_TRY(cudaFuncSetAttribute(k_physics<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
-  CUDA_TRY(cudaFuncSetAttribute(k_physics<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
-  CUDA_TRY(cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
-  CUDA_TRY(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+  if (model->floor_is_hfield) {
+    CUDA_TRY(cudaFuncSetAttribute(k_physics<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+    CUDA_TRY(cudaFuncSetAttribute(k_physics<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+    CUDA_TRY(cudaFuncSetAttribute(k_reset<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+    CUDA_TRY(cudaFuncSetAttribute(k_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+  } else {
+    CUDA_TRY(cudaFuncSetAttribute(k_physics<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+    CUDA_TRY(cudaFuncSetAttribute(k_physics<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+    CUDA_TRY(cudaFuncSetAttribute(k_reset<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+    CUDA_TRY(cudaFuncSetAttribute(k_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+  }
   CUDA_TRY(cudaFuncSetAttribute(k_randomize, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
   h->grid = (num_envs + WPB - 1) / WPB;
   CUDA_TRY(cudaDeviceSynchronize());
@@ -857,25 +882,25 @@ int oduck_reset(OduckHandle* h, const uint32_t* keys, const uint8_t* mask, void*
   if (!h || !keys) return fail(ODUCK_ERR_ARG, "oduck_reset: bad argument");
   Params p = make_params(h);
   p.keys = keys; p.mask = mask;
-  return launch(h, k_reset, p, stream);
+  return h->dhf ? launch(h, k_reset<true>, p, stream) : launch(h, k_reset<false>, p, stream);
 }
 int oduck_step(OduckHandle* h, const float* action, void* stream) {
   if (!h || !action) return fail(ODUCK_ERR_ARG, "oduck_step: bad argument");
   Params p = make_params(h);
   p.action = action;
-  return launch(h, k_step, p, stream);
+  return h->dhf ? launch(h, k_step<true>, p, stream) : launch(h, k_step<false>, p, stream);
 }
 int oduck_physics_substeps(OduckHandle* h, const float* ctrl, int n, void* stream) {
   if (!h || n < 0) return fail(ODUCK_ERR_ARG, "oduck_physics_substeps: bad argument");
   Params p = make_params(h);
   p.action = ctrl; p.nsub = n; p.integrate = 1;
-  return launch(h, k_physics<false>, p, stream);
+  return h->dhf ? launch(h, k_physics<false, true>, p, stream) : launch(h, k_physics<false, false>, p, stream);
 }
 int oduck_forward(OduckHandle* h, void* stream) {
   if (!h) return fail(ODUCK_ERR_ARG, "oduck_forward: bad argument");
   Params p = make_params(h);
   p.nsub = 1; p.integrate = 0;
-  return launch(h, k_physics<false>, p, stream);
+  return h->dhf ? launch(h, k_physics<false, true>, p, stream) : launch(h, k_physics<false, false>, p, stream);
 }
 // Diagnostic (not part of the reference surface): one forward with every intermediate dumped, DBG_STRIDE floats per env
 // copied to host memory `out`.  Used by tests/test_parity_gpu.py to localise a parity failure.
@@ -886,7 +911,7 @@ int oduck_debug_forward(OduckHandle* h, float* out_host) {
   CUDA_TRY(cudaMemset(h->dbg, 0, (size_t)h->n * DBG_STRIDE * sizeof(float)));
   Params p = make_params(h);
   p.nsub = 1; p.integrate = 0;
-  int rc = launch(h, k_physics<true>, p, nullptr);
+  int rc = h->dhf ? launch(h, k_physics<true, true>, p, nullptr) : launch(h, k_physics<true, false>, p, nullptr);
   if (rc) return rc;
   CUDA_TRY(cudaDeviceSynchronize());
   CUDA_TRY(cudaMemcpy(out_host, h->dbg, (size_t)h->n * DBG_STRIDE * sizeof(float), cudaMemcpyDeviceToHost));

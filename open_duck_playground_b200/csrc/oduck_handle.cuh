@@ -17,6 +17,8 @@ struct Params {
   const DevFF* ffmodel;
   float* ffscratch;
   int N, nsub, integrate;
+  const DevHF* hfmodel;    // height-field floor (HF kernel instantiations only); last, so that the flat kernels' argument layout is unchanged
+  float* hfscratch;        // per env: HF_SCRATCH floats of contact candidates
 };
 
 struct OduckHandle {
@@ -33,6 +35,9 @@ struct OduckHandle {
   int64_t launches;
   DevFF* dff;
   float* ffscratch;               // per env: 12 x 32 foot-foot Jacobian rows + SAT operands (rare path)
+  DevHF* dhf;                     // height-field floor: descriptor, elevation samples, per-env candidate lists
+  float* hfdata;
+  float* hfscratch;
   float* policy_scratch;          // hidden activations of the actor MLP (tensor-core path)
   size_t policy_scratch_floats;
   const float* policy_packed_for;  // w[0] pointer the packed weight copy was made from

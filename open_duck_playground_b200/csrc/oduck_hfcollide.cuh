@@ -1,0 +1,191 @@
+// oduck_hfcollide.cuh -- height-field floor vs one convex foot hull (rough_terrain scenes; only the HF = true kernel
+// instantiations contain this code, the flat-floor instantiations are unchanged).  Same scheme as
+// oracle/oduck_oracle.cpp hfield_convex: for every terrain triangle under the foot's bounding sphere, every foot face that
+// looks down onto it is clipped to the triangle's vertical column; clipped points below the triangle plane are candidates
+// (dist along the triangle normal, pos midway, normal = triangle normal); 4 of the candidates within 1 mm of the deepest one
+// are kept by _manifold_points with the mean normal.  Warp mapping: lane = hull face for the clipping (each lane clips its
+// own <= 8-gon in local memory), candidates are appended in the oracle's order (triangle, face, polygon vertex) to a per-env
+// HBM scratch list with a warp prefix sum, and the manifold selection runs over that list 32 candidates at a time with the
+// same first-index arg-max as the plane collider.
+#pragma once
+#include "oduck_ffcollide.cuh"
+
+struct DevHF {   // global memory
+  int nrow, ncol;
+  float sx, sy, sz, dx, dy;     // radii, elevation scale, grid pitch
+  const float* data;            // [nrow][ncol] elevation in [0, 1]
+};
+
+#define HF_CAP 512             // candidates kept per foot (the oracle keeps all; a resting foot has a few dozen)
+#define HF_REC 8               // dist, pos[3], normal[3], -
+#define HF_SCRATCH (HF_CAP * HF_REC)
+#define HF_MAXP 12             // 8-gon clipped by 3 planes: at most 11 vertices
+
+// Sutherland-Hodgman: keep the part of the polygon on the inner side (d <= 0) of the vertical plane through r0 -> r1
+__device__ __forceinline__ int hf_clip(const float (*in)[3], int cnt, float (*out)[3], const float r0x, const float r0y, const float sdx, const float sdy) {
+  int no = 0;
+  for (int v = 0; v < cnt; ++v) {
+    const int w = v + 1 == cnt ? 0 : v + 1;
+    const float d0 = sdx * (in[v][0] - r0x) + sdy * (in[v][1] - r0y), d1 = sdx * (in[w][0] - r0x) + sdy * (in[w][1] - r0y);
+    if (d0 <= 0.f) { out[no][0] = in[v][0]; out[no][1] = in[v][1]; out[no][2] = in[v][2]; ++no; }
+    if ((d0 <= 0.f) != (d1 <= 0.f)) {
+      const float t = d0 / (d0 - d1);
+      out[no][0] = in[v][0] + t * (in[w][0] - in[v][0]); out[no][1] = in[v][1] + t * (in[w][1] - in[v][1]); out[no][2] = in[v][2] + t * (in[w][2] - in[v][2]);
+      ++no;
+    }
+  }
+  return no;
+}
+
+// Writes the four contact records of foot f: s.con[4 f + c][0] = dist (1: inactive), [1..3] = pos, [13..15] = normal.
+static __device__ __noinline__ void hf_collide(const DevModel& m, const DevFF* __restrict__ ff, const DevHF* __restrict__ hf, WarpSmem& s,
+                                               const int lane, const int f, float* __restrict__ cand) {
+  const int fb = m.foot_body[f];
+  float R[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) R[k] = s.xmat[k][fb];
+  const V3 p0 = v3(s.xpos[0][fb], s.xpos[1][fb], s.xpos[2][fb]);
+  auto rot = [&](V3 v) { return v3(R[0] * v.x + R[1] * v.y + R[2] * v.z, R[3] * v.x + R[4] * v.y + R[5] * v.z, R[6] * v.x + R[7] * v.y + R[8] * v.z); };
+  if (lane < 4) {
+    float* cc = s.con[4 * f + lane];
+    cc[0] = 1.f; cc[1] = cc[2] = cc[3] = 0.f; cc[13] = 0.f; cc[14] = 0.f; cc[15] = 1.f;
+  }
+  __syncwarp();
+  const V3 C = p0 + rot(v3(ff->center[f][0], ff->center[f][1], ff->center[f][2]));
+  const float rb = ff->radius;
+  const int nrow = hf->nrow, ncol = hf->ncol;
+  const float sx = hf->sx, sy = hf->sy, sz = hf->sz, dx = hf->dx, dy = hf->dy;
+  const float* __restrict__ data = hf->data;
+  int cmin = (int)floorf((C.x - rb + sx) / dx), cmax = (int)floorf((C.x + rb + sx) / dx);
+  int rmin = (int)floorf((C.y - rb + sy) / dy), rmax = (int)floorf((C.y + rb + sy) / dy);
+  cmin = max(cmin, 0); rmin = max(rmin, 0); cmax = min(cmax, ncol - 2); rmax = min(rmax, nrow - 2);
+  // this lane's face: world normal and world polygon
+  const bool has = lane < ff->nplane;
+  const int q = has ? lane : 0;
+  const V3 Nw = rot(v3(ff->plane_normal[f][0][q], ff->plane_normal[f][1][q], ff->plane_normal[f][2][q]));
+  const int cnt0 = has ? ff->plane_nvert[q] : 0;
+  float P0[8][3];
+  for (int v = 0; v < cnt0; ++v) {
+    const int vid = ff->plane_vert[q][v];
+    const V3 w = p0 + rot(v3(m.vert[f][0][vid], m.vert[f][1][vid], m.vert[f][2][vid]));
+    P0[v][0] = w.x; P0[v][1] = w.y; P0[v][2] = w.z;
+  }
+  int nc = 0;                      // candidates so far (warp-uniform)
+  V3 nsum = v3(0.f, 0.f, 0.f);     // sum of the candidates' normals (warp-uniform)
+  float deep = 0.f;                // lane-local deepest candidate
+  for (int r = rmin; r <= rmax; ++r)
+    for (int c = cmin; c <= cmax; ++c) {
+      const float x0 = c * dx - sx, x1 = (c + 1) * dx - sx, y0 = r * dy - sy, y1 = (r + 1) * dy - sy;
+      const float h00 = data[(size_t)r * ncol + c] * sz, h01 = data[(size_t)r * ncol + c + 1] * sz;
+      const float h10 = data[(size_t)(r + 1) * ncol + c] * sz, h11 = data[(size_t)(r + 1) * ncol + c + 1] * sz;
+#pragma unroll 1
+      for (int i = 0; i < 2; ++i) {
+        // counter-clockwise seen from above; the cell is split along (c, r) - (c + 1, r + 1)
+        const V3 T0 = i == 0 ? v3(x0, y1, h10) : v3(x0, y0, h00);
+        const V3 T1 = i == 0 ? v3(x0, y0, h00) : v3(x1, y0, h01);
+        const V3 T2 = v3(x1, y1, h11);
+        const float top = fmaxf(T0.z, fmaxf(T1.z, T2.z));
+        if (C.z - rb > top) continue;                                   // warp-uniform
+        V3 n = cross(T1 - T0, T2 - T0);
+        n = (1.f / sqrtf(dot(n, n))) * n;
+        float A[HF_MAXP][3], B[HF_MAXP][3];
+        int cnt = 0;
+        if (has && dot(Nw, n) < 0.f) {                                  // only the faces that look down onto the triangle
+          cnt = hf_clip(P0, cnt0, A, T0.x, T0.y, T1.y - T0.y, -(T1.x - T0.x));
+          if (cnt > 0) cnt = hf_clip(A, cnt, B, T1.x, T1.y, T2.y - T1.y, -(T2.x - T1.x));
+          if (cnt > 0) cnt = hf_clip(B, cnt, A, T2.x, T2.y, T0.y - T2.y, -(T0.x - T2.x));
+        }
+        int k = 0;
+        for (int v = 0; v < cnt; ++v) {
+          const float dist = n.x * (A[v][0] - T0.x) + n.y * (A[v][1] - T0.y) + n.z * (A[v][2] - T0.z);
+          if (dist < 0.f) ++k;
+        }
+        int incl = k;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULLMASK, incl, o); if (lane >= o) incl += t; }
+        const int total = __shfl_sync(FULLMASK, incl, 31);
+        if (total == 0) continue;                                       // warp-uniform
+        int at = nc + incl - k;
+        for (int v = 0; v < cnt; ++v) {
+          const float dist = n.x * (A[v][0] - T0.x) + n.y * (A[v][1] - T0.y) + n.z * (A[v][2] - T0.z);
+          if (!(dist < 0.f)) continue;
+          if (at < HF_CAP) {
+            float* rec = cand + at * HF_REC;
+            rec[0] = dist; rec[1] = A[v][0] - 0.5f * dist * n.x; rec[2] = A[v][1] - 0.5f * dist * n.y; rec[3] = A[v][2] - 0.5f * dist * n.z;
+            rec[4] = n.x; rec[5] = n.y; rec[6] = n.z;
+            deep = fminf(deep, dist);
+          }
+          ++at;
+        }
+        nsum = nsum + (float)total * n;
+        nc += total;
+      }
+    }
+  if (nc == 0) return;
+  nc = min(nc, HF_CAP);
+  __syncwarp();
+  const float deepest = -wmaxf(-deep);
+  const float thr = fminf(0.f, deepest + 1e-3f);                        // plane_convex's rule: within 1 mm of the deepest
+  const V3 nm = (1.f / sqrtf(dot(nsum, nsum))) * nsum;                  // every triangle normal has n_z > 0
+  const float ninf = -__int_as_float(0x7f800000);
+  // point i of the list as seen by this lane in the chunk starting at `base`
+#define HF_LOAD(base, P_, dm_)                                                                                         \
+  V3 P_ = v3(0.f, 0.f, 0.f); float dm_ = ninf;                                                                          \
+  {                                                                                                                    \
+    const int i_ = (base) + lane;                                                                                      \
+    if (i_ < nc) { const float* rec = cand + i_ * HF_REC; P_ = v3(rec[1], rec[2], rec[3]); dm_ = rec[0] < thr ? 0.f : -1e6f; }   \
+  }
+  auto point = [&](int i) { const float* rec = cand + i * HF_REC; return v3(rec[1], rec[2], rec[3]); };
+  int idx[4] = {0, 0, 0, 0};
+  for (int base = 0; base < nc; base += 32) {                           // a: the first candidate inside the threshold
+    HF_LOAD(base, P, dm)
+    const unsigned bm = __ballot_sync(FULLMASK, dm == 0.f);
+    if (bm) { idx[0] = base + __ffs(bm) - 1; break; }
+  }
+  const V3 pa = point(idx[0]);
+  {
+    float best = ninf;                                                   // b: farthest from a
+    for (int base = 0; base < nc; base += 32) {
+      HF_LOAD(base, P, dm)
+      const V3 ap = pa - P;
+      int li; const float v = wargmax_val(dot(ap, ap) + dm, lane, &li);
+      if (v > best) { best = v; idx[1] = base + li; }
+    }
+  }
+  const V3 pb = point(idx[1]);
+  const V3 ab = cross(nm, pa - pb);
+  {
+    float best = ninf;                                                   // c: farthest from the line a b
+    for (int base = 0; base < nc; base += 32) {
+      HF_LOAD(base, P, dm)
+      int li; const float v = wargmax_val(fabsf(dot(pa - P, ab)) + dm, lane, &li);
+      if (v > best) { best = v; idx[2] = base + li; }
+    }
+  }
+  const V3 pc = point(idx[2]);
+  const V3 ac = cross(nm, pa - pc), bc = cross(nm, pb - pc);
+  {
+    float b1 = ninf, b2 = ninf; int i1 = 0, i2 = 0;                     // d: farthest from the edges b c and a c
+    for (int base = 0; base < nc; base += 32) {
+      HF_LOAD(base, P, dm)
+      int li; float v = wargmax_val(fabsf(dot(pb - P, bc)) + dm, lane, &li);
+      if (v > b1) { b1 = v; i1 = base + li; }
+      v = wargmax_val(fabsf(dot(pa - P, ac)) + dm, lane, &li);
+      if (v > b2) { b2 = v; i2 = base + li; }
+    }
+    idx[3] = b1 >= b2 ? i1 : i2;
+  }
+#undef HF_LOAD
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    bool uniq = true;
+#pragma unroll
+    for (int p = 0; p < c; ++p) uniq = uniq && (idx[p] != idx[c]);
+    if (uniq && lane == c) {
+      const float* rec = cand + idx[c] * HF_REC;
+      float* cc = s.con[4 * f + c];
+      cc[0] = rec[0]; cc[1] = rec[1]; cc[2] = rec[2]; cc[3] = rec[3]; cc[13] = rec[4]; cc[14] = rec[5]; cc[15] = rec[6];
+    }
+  }
+  __syncwarp();
+}

@@ -5,6 +5,7 @@
 #pragma once
 #include "oduck_device.cuh"
 #include "oduck_ffcollide.cuh"
+#include "oduck_hfcollide.cuh"
 
 // per-thread state that persists across the substeps of one launch
 struct Lane {
@@ -31,10 +32,11 @@ __device__ __forceinline__ void substep_idle_barriers(int substeps) {
   for (int k = 0; k < substeps * __popc(ODUCK_BARRIERS & 0x3f); ++k) __syncthreads();
 }
 
-template <bool DBG, bool FF, bool BAR>
+template <bool DBG, bool FF, bool BAR, bool HF>
 __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& s, Lane& L, const int lane, const bool last,
                                               const bool integrate, float* __restrict__ out, float* __restrict__ dbg,
-                                              const DevFF* __restrict__ ffm, float* __restrict__ ffs) {
+                                              const DevFF* __restrict__ ffm, float* __restrict__ ffs,
+                                              const DevHF* __restrict__ hfm, float* __restrict__ hfs) {
   const int nv = m.nv, nb = m.nbody;
   PHASE_SYNC(0, true)
   // ------------------------------------------------------------------ kinematics (lane = body)
@@ -305,6 +307,11 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
 
   PHASE_SYNC(2, true)
   // ------------------------------------------------------------------ collision: plane (z = 0) vs convex foot hulls (lane = vertex)
+  if constexpr (HF) {
+    // height-field floor (HF instantiations only): terrain triangles vs foot faces, oduck_hfcollide.cuh
+    hf_collide(m, ffm, hfm, s, lane, 0, hfs);
+    hf_collide(m, ffm, hfm, s, lane, 1, hfs);
+  } else
   for (int f = 0; f < 2; ++f) {
     const int fb = m.foot_body[f];
     float Rf[9];
@@ -392,11 +399,20 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
   const bool cact = lane < NCON_ALL && cdist < 0.f;
   const float mu = cl < NCON_FLOOR ? m.floor_mu : m.foot_mu;
   const V3 coff = v3(s.con[cs][1], s.con[cs][2], s.con[cs][3]) - com;     // contact lane: its point relative to the com
+  // contact frame of this lane's floor contact: the flat floor has the fixed (n, t1, t2) = (+z, +y, -x) = make_frame(+z); a
+  // height-field contact carries its triangle normal in the contact record
+  V3 frn = v3(0.f, 0.f, 1.f), frt1 = v3(0.f, 1.f, 0.f), frt2 = v3(-1.f, 0.f, 0.f);
+  if constexpr (HF) {
+    float fr_[9];
+    ff_make_frame(v3(s.con[cs][13], s.con[cs][14], s.con[cs][15]), fr_);
+    frn = v3(fr_[0], fr_[1], fr_[2]); frt1 = v3(fr_[3], fr_[4], fr_[5]); frt2 = v3(fr_[6], fr_[7], fr_[8]);
+  }
   // rows (n, t1, t2) of this lane's floor contact applied to the foot's spatial vector [a; l]
 #define POINT_ROWS(a_, l_, pn_, p1_, p2_)                                                                               \
   {                                                                                                                    \
     const V3 jp_ = (l_) + cross((a_), coff);                                                                           \
-    pn_ = jp_.z; p1_ = jp_.y; p2_ = -jp_.x;                                                                            \
+    if constexpr (HF) { pn_ = dot(frn, jp_); p1_ = dot(frt1, jp_); p2_ = dot(frt2, jp_); }                              \
+    else { pn_ = jp_.z; p1_ = jp_.y; p2_ = -jp_.x; }                                                                   \
   }
   float Dc = 0.f, arefc[4] = {0.f, 0.f, 0.f, 0.f};
   {
@@ -534,10 +550,18 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
         const V3 off = v3(r0.y, r0.z, r0.w) - com;
         V3 jp = lin + cross(ang, off);
         if (!(c < 4 ? inF0 : inF1)) jp = v3(0.f, 0.f, 0.f);
-        const float jn = jp.z, j1 = jp.y, j2 = -jp.x;
+        float jn = jp.z, j1 = jp.y, j2 = -jp.x;
+        V3 cn = v3(0.f, 0.f, 1.f), ct1 = v3(0.f, 1.f, 0.f), ct2 = v3(-1.f, 0.f, 0.f);
+        if constexpr (HF) {
+          float fr_[9];
+          ff_make_frame(v3(s.con[c][13], s.con[c][14], s.con[c][15]), fr_);
+          cn = v3(fr_[0], fr_[1], fr_[2]); ct1 = v3(fr_[3], fr_[4], fr_[5]); ct2 = v3(fr_[6], fr_[7], fr_[8]);
+          jn = dot(cn, jp); j1 = dot(ct1, jp); j2 = dot(ct2, jp);
+        }
         qfc += jn * r1.x + j1 * r1.y + j2 * r1.z;
         const float un = r2.x * jn + r2.y * j1 + r2.z * j2, u1 = r2.y * jn + r2.w * j1, u2 = r2.z * jn + w22 * j2;
-        const V3 U = v3(-u2, u1, un);                                       // back to world axes
+        V3 U = v3(-u2, u1, un);                                             // back to world axes
+        if constexpr (HF) U = un * cn + u1 * ct1 + u2 * ct2;
         const V3 oxU = cross(off, U);
         z.a0 += oxU.x; z.a1 += oxU.y; z.a2 += oxU.z; z.l0 += U.x; z.l1 += U.y; z.l2 += U.z;
       }
@@ -809,6 +833,7 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
       dbg[1136 + 3 * lane] = s.con[lane][1]; dbg[1137 + 3 * lane] = s.con[lane][2]; dbg[1138 + 3 * lane] = s.con[lane][3];
       dbg[1248 + lane] = Dc;
       dbg[2560 + 3 * lane] = lane < NCON_FLOOR ? 0.f : ((FF && ffact) ? s.misc[0] : 1.f); dbg[2561 + 3 * lane] = lane < NCON_FLOOR ? 0.f : ((FF && ffact) ? s.misc[1] : 0.f); dbg[2562 + 3 * lane] = lane < NCON_FLOOR ? 1.f : ((FF && ffact) ? s.misc[2] : 0.f);
+      if constexpr (HF) { if (lane < NCON_FLOOR) { dbg[2560 + 3 * lane] = s.con[lane][13]; dbg[2561 + 3 * lane] = s.con[lane][14]; dbg[2562 + 3 * lane] = s.con[lane][15]; } }
       for (int r = 0; r < 4; ++r) dbg[1328 + 4 * lane + r] = arefc[r];
     }
     if (lane < nb) { dbg[1440 + 3 * lane] = xp.x; dbg[1441 + 3 * lane] = xp.y; dbg[1442 + 3 * lane] = xp.z; }
@@ -816,7 +841,14 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
     for (int c = 0; c < NCON_FLOOR; ++c) {
       V3 jp = v3(0.f, 0.f, 0.f);
       if (s.con[c][0] < 0.f && (c < 4 ? inF0 : inF1)) jp = v3(cd.l0, cd.l1, cd.l2) + cross(v3(cd.a0, cd.a1, cd.a2), v3(s.con[c][1], s.con[c][2], s.con[c][3]) - com);
-      dbg[1768 + (3 * c) * 32 + lane] = jp.z; dbg[1768 + (3 * c + 1) * 32 + lane] = jp.y; dbg[1768 + (3 * c + 2) * 32 + lane] = -jp.x;
+      if constexpr (HF) {
+        float fr_[9];
+        ff_make_frame(v3(s.con[c][13], s.con[c][14], s.con[c][15]), fr_);
+        dbg[1768 + (3 * c) * 32 + lane] = dot(v3(fr_[0], fr_[1], fr_[2]), jp); dbg[1768 + (3 * c + 1) * 32 + lane] = dot(v3(fr_[3], fr_[4], fr_[5]), jp);
+        dbg[1768 + (3 * c + 2) * 32 + lane] = dot(v3(fr_[6], fr_[7], fr_[8]), jp);
+      } else {
+        dbg[1768 + (3 * c) * 32 + lane] = jp.z; dbg[1768 + (3 * c + 1) * 32 + lane] = jp.y; dbg[1768 + (3 * c + 2) * 32 + lane] = -jp.x;
+      }
     }
   }
   __syncwarp();
@@ -849,9 +881,10 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
   return false;
 }
 
-template <bool DBG, bool BAR = false>
+template <bool DBG, bool BAR = false, bool HF = false>
 __device__ __forceinline__ void forward_euler(const DevModel& m, WarpSmem& s, Lane& L, const int lane, const bool last, const bool integrate,
-                                              float* __restrict__ out, float* __restrict__ dbg, const DevFF* __restrict__ ffm, float* __restrict__ ffs) {
-  if (forward_euler_impl<DBG, false, BAR>(m, s, L, lane, last, integrate, out, dbg, ffm, ffs))
-    forward_euler_impl<DBG, true, BAR>(m, s, L, lane, last, integrate, out, dbg, ffm, ffs);
+                                              float* __restrict__ out, float* __restrict__ dbg, const DevFF* __restrict__ ffm, float* __restrict__ ffs,
+                                              const DevHF* __restrict__ hfm = nullptr, float* __restrict__ hfs = nullptr) {
+  if (forward_euler_impl<DBG, false, BAR, HF>(m, s, L, lane, last, integrate, out, dbg, ffm, ffs, hfm, hfs))
+    forward_euler_impl<DBG, true, BAR, HF>(m, s, L, lane, last, integrate, out, dbg, ffm, ffs, hfm, hfs);
 }

@@ -1,6 +1,6 @@
 """Height-field floor (rough_terrain scenes, reference xmls/scene_mjx_rough_terrain*.xml): the PNG asset
-decoder, and the CPU oracle's prism-vs-foot collision checked against the plane path and first principles.  The CUDA library
-still answers ODUCK_ERR_UNSUPPORTED for these scenes this round."""
+decoder, the CPU oracle's terrain-vs-foot collision checked against the plane path and first principles, and (-m gpu) the
+HF instantiations of the CUDA kernels against the oracle."""
 import copy
 import ctypes as C
 import os
@@ -226,3 +226,92 @@ def test_hfield_env_step_runs(oracle, poly_table):
         st = env.step(st, torch.zeros(4, 14))
     assert torch.isfinite(st.reward).all() and torch.isfinite(st.obs["state"]).all()
     assert float(st.done.max()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------------- CUDA vs oracle (B200 box)
+def _gpu_pair(oracle, n):
+    import torch
+    from open_duck_playground_b200 import rng as jr
+    from open_duck_playground_b200.joystick import Joystick
+    gpu, ref = Joystick("rough_terrain_backlash", device="cuda:0"), Joystick("rough_terrain_backlash", library=oracle)
+    for e in (gpu, ref):
+        e.randomize(jr.split(jr.PRNGKey(11), n))
+    keys = jr.split(jr.PRNGKey(0), n)
+    sg, sr = gpu.reset(keys), ref.reset(keys)
+    torch.cuda.synchronize()
+    return gpu, ref, sg, sr
+
+
+@pytest.mark.gpu
+def test_hfield_gpu_collision_parity(oracle):
+    """One forward on the shipped rough terrain, poses spread over the field: the k_physics<HF> instantiation's contacts
+    (distances, points, triangle normals) and the solver outputs against the oracle."""
+    import torch
+    from test_parity_gpu import Checks, _np
+    n = 512
+    gpu, ref, _, _ = _gpu_pair(oracle, n)
+    m = gpu.mj_model
+    q = _poses(m, n, 7, tilt=0.08, dz=(-0.004, 0.012))
+    q[:, 0:2] = np.random.default_rng(8).uniform(-9.0, 9.0, (n, 2))
+    v = np.zeros((n, m.nv), np.float32)
+    gpu.set_state(torch.from_numpy(q), torch.from_numpy(v), torch.from_numpy(v))
+    ref.set_state(torch.from_numpy(q), torch.from_numpy(v), torch.from_numpy(v))
+    outs = []
+    for env, dt in ((gpu, np.float32), (ref, np.float64)):
+        L = env.handle.L.lib
+        buf = np.zeros((n, L.oduck_debug_stride()), dt)
+        L.oduck_debug_forward.argtypes = [C.c_void_p, C.c_void_p]
+        env.handle.L.check(L.oduck_debug_forward(env.handle.h, buf.ctypes.data))
+        outs.append(buf.astype(np.float64))
+    g, r = outs
+    dg, dr = g[:, 1120:1128], r[:, 1120:1128]
+    c = Checks()
+    c.OUTLIER_FRAC = 0.04                 # manifold picks among near-equal candidates flip between fp32 and fp64 more often than on the plane
+    assert (dr < 0).any(axis=1).mean() > 0.5
+    c.mostly_equal(dg < 0, dr < 0, "active contact set")
+    both = (dg < 0) & (dr < 0)
+    c.rows(torch.from_numpy(np.where(both, dg, 0)), torch.from_numpy(np.where(both, dr, 0)), 2e-6, what="contact dist")
+    pos_g, pos_r = g[:, 1136:1160].reshape(n, 8, 3), r[:, 1136:1160].reshape(n, 8, 3)
+    nrm_g, nrm_r = g[:, 2560:2584].reshape(n, 8, 3), r[:, 2560:2584].reshape(n, 8, 3)
+    c.rows(torch.from_numpy(np.where(both[..., None], pos_g, 0)), torch.from_numpy(np.where(both[..., None], pos_r, 0)), 5e-6, what="contact pos")
+    c.rows(torch.from_numpy(np.where(both[..., None], nrm_g, 0)), torch.from_numpy(np.where(both[..., None], nrm_r, 0)), 2e-5, what="contact normal")
+    assert np.abs(nrm_r[dr < 0][:, :2]).max() > 0.02                       # the terrain really tilts the normals
+    c.rows(torch.from_numpy(g[:, 1248:1256]), torch.from_numpy(r[:, 1248:1256]), 1e-3, 1e-3, what="D_con")
+    c.rows(torch.from_numpy(g[:, 1328:1360]), torch.from_numpy(r[:, 1328:1360]), 1e-2, 1e-3, what="aref_con")
+    c.rows(torch.from_numpy(g[:, 1736:1768]), torch.from_numpy(r[:, 1736:1768]), 1e-3, 2e-3, what="qacc")
+    c.done()
+
+
+@pytest.mark.gpu
+def test_hfield_gpu_env_step_parity(oracle):
+    """reset + control steps of the Joystick env on rough_terrain_backlash (k_reset<HF>, k_step<HF>) against the oracle."""
+    import torch
+    from test_parity_gpu import Checks, _np, _sync_from_ref
+    n = 256
+    gpu, ref, sg, sr = _gpu_pair(oracle, n)
+    c = Checks()
+    c.OUTLIER_FRAC = 0.04
+    c.equal(gpu.buffer("INFO_RNG").cpu().numpy(), ref.buffer("INFO_RNG").numpy(), "rng key stream")
+    c.close(sg.data.qpos, sr.data.qpos, 1e-6, what="reset qpos")
+    c.rows(sg.data.efc_force, sr.data.efc_force, 1e-3, 1e-2, what="reset efc_force")
+    c.rows(sg.obs["state"], sr.obs["state"], 2e-3, 2e-3, what="reset obs state")
+    rs = np.random.default_rng(2)
+    for t in range(6):
+        act = rs.uniform(-1, 1, (n, gpu.action_size)).astype(np.float32)
+        _sync_from_ref(gpu, ref)
+        sg, sr = gpu.step(sg, torch.from_numpy(act).cuda()), ref.step(sr, torch.from_numpy(act))
+        torch.cuda.synchronize()
+        for name in ("INFO_RNG", "INFO_STEP", "INFO_STEPS", "INFO_PUSH_STEP", "INFO_IMITATION_I"):
+            c.equal(gpu.buffer(name).cpu().numpy(), ref.buffer(name).numpy(), f"[{t}] {name}")
+        c.close(sg.data.qpos, sr.data.qpos, 1e-4, what=f"[{t}] qpos")
+        c.rows(sg.data.qvel, sr.data.qvel, 2e-3, 1e-3, what=f"[{t}] qvel")
+        c.close(sg.reward, sr.reward, 2e-4, what=f"[{t}] reward")
+        c.mostly_equal(_np(sg.done), _np(sr.done), f"[{t}] done")
+        c.rows(gpu.buffer("METRICS"), ref.buffer("METRICS"), 1e-3, 2e-3, what=f"[{t}] metrics")
+        c.rows(sg.obs["state"], sr.obs["state"], 2e-3, 2e-3, what=f"[{t}] obs state")
+        c.rows(sg.obs["privileged_state"], sr.obs["privileged_state"], 2e-3, 2e-3, what=f"[{t}] obs privileged")
+        dgc, drc = _np(sg.data.contact_dist), _np(sr.data.contact_dist)
+        c.mostly_equal(dgc < 0, drc < 0, f"[{t}] active contact set")
+        for k in ("command", "motor_targets", "feet_air_time", "last_contact", "push"):
+            c.close(sg.info[k], sr.info[k], 1e-5, what=f"[{t}] {k}")
+    c.done()
