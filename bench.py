@@ -230,6 +230,7 @@ def run_ppo(args, rank, world, dev):
 
 
 def main():
+    global TASK
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -237,9 +238,11 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=4096)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--task", default=TASK, help="scene: flat_terrain_backlash (the metric's config), flat_terrain, rough_terrain_backlash (height-field floor, BASELINE configs[3])")
     ap.add_argument("--mode", default="rollout", choices=["rollout", "ppo", "physics"],
                     help="ppo = BASELINE configs[2]: full PPO training steps (rollout / gather / update split); physics = oduck_physics_substeps(10) alone")
     args = ap.parse_args()
+    TASK = args.task
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
         run_reference(args, rank, world)
@@ -426,12 +429,12 @@ def main():
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(f"k_step_{n}")
+            traffic = json.load(open(tpath)).get(f"k_step_{n}" if TASK.startswith("flat") else f"k_step_hf_{n}")
         line = {
             "metric": "env-steps/sec (batched physics+rollout)", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"{TASK} joystick rollout step = actor-MLP forward + env.step (10 substeps + obs/reward/auto-reset), {n} envs per GPU, domain randomisation on, no PPO update (BASELINE configs[1])",
+            "config": {"workload": f"{TASK} joystick rollout step = actor-MLP forward + env.step (10 substeps + obs/reward/auto-reset), {n} envs per GPU, domain randomisation on, no PPO update (BASELINE configs[{1 if TASK.startswith('flat') else 3}])",
                        "task": TASK, "envs_per_gpu": n, "global_envs": world * n, "substeps_per_step": 10, "parallelism": f"env-shard x{world}",
                        "l2": f"{n_sets} env sets rotated, {n_sets * n * STATE_BYTES_PER_ENV / 1e6:.0f} MB working set > L2",
                        "launch": "one CUDA graph per env set (actor kernels + k_step), replayed per step"},

@@ -290,7 +290,11 @@ def test_hfield_gpu_env_step_parity(oracle):
     n = 256
     gpu, ref, sg, sr = _gpu_pair(oracle, n)
     c = Checks()
-    c.OUTLIER_FRAC = 0.04
+    # A control step is 10 substeps x 2 feet of manifold selection among near-coincident candidates (points on an edge shared by
+    # two terrain triangles appear once per triangle, a few 1e-7 m apart and with different normals): fp32 and fp64 pick a
+    # different one in ~0.6 % of the forwards (test above), i.e. in 2-9 % of the envs per control step (measured on B200).
+    # Those envs are counted and reported; every other env must meet the flat-floor tolerances (medians sit at < 1 % of them).
+    c.OUTLIER_FRAC = 0.12
     c.equal(gpu.buffer("INFO_RNG").cpu().numpy(), ref.buffer("INFO_RNG").numpy(), "rng key stream")
     c.close(sg.data.qpos, sr.data.qpos, 1e-6, what="reset qpos")
     c.rows(sg.data.efc_force, sr.data.efc_force, 1e-3, 1e-2, what="reset efc_force")
