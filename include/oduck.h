@@ -158,8 +158,8 @@ typedef struct OduckModel {
   double key_ctrl[ODUCK_MAX_NU];
   /* height-field floor (floor_is_hfield; rough_terrain scenes, xmls/scene_rough_terrain_backlash.xml:22-27): MuJoCo hfield asset,
    * grid x in [-size[0], size[0]] over ncol samples, y in [-size[1], size[1]] over nrow samples, height = data * size[2],
-   * solid down to -size[3].  Implemented by the CPU oracle (foot faces clipped to the terrain triangles under the foot); the CUDA library
-   * still answers ODUCK_ERR_UNSUPPORTED for such models. */
+   * solid down to -size[3].  Both libraries collide the foot faces with the terrain triangles under the foot;
+   * the CUDA library runs the HF instantiations of its kernels for such models. */
   int32_t hfield_nrow, hfield_ncol;
   double hfield_size[4];         /* radius_x, radius_y, elevation_z, base_z */
   const float* hfield_data;      /* HOST pointer, elevation normalised to [0, 1], row-major [nrow][ncol]; copied by oduck_create */
