@@ -70,12 +70,37 @@ static __device__ __noinline__ void hf_collide(const DevModel& m, const DevFF* _
     const V3 w = p0 + rot(v3(m.vert[f][0][vid], m.vert[f][1][vid], m.vert[f][2][vid]));
     P0[v][0] = w.x; P0[v][1] = w.y; P0[v][2] = w.z;
   }
+#ifdef ODUCK_HF_CULL
+  // Result-preserving culls (measured next round; off by default so that the verified build is unchanged): the world box of the
+  // hull (lane = vertex, redux min / max) rejects cells it does not overlap and triangles that lie wholly below its lowest
+  // vertex (a candidate needs a hull point BELOW the triangle plane, whose height never exceeds the triangle's top); the box
+  // of this lane's face rejects the clipping.  1e-6 m margins keep the culls conservative under fp32 rounding of the clipped points.
+  float bx0, bx1, by0, by1, bz0;
+  {
+    const bool vv = lane < m.nvert;
+    const int vl = vv ? lane : 0;
+    const V3 w = p0 + rot(v3(m.vert[f][0][vl], m.vert[f][1][vl], m.vert[f][2][vl]));
+    const float inf = __int_as_float(0x7f800000);
+    bx1 = wmaxf(vv ? w.x : -inf) + 1e-6f; bx0 = -wmaxf(vv ? -w.x : -inf) - 1e-6f;
+    by1 = wmaxf(vv ? w.y : -inf) + 1e-6f; by0 = -wmaxf(vv ? -w.y : -inf) - 1e-6f;
+    bz0 = -wmaxf(vv ? -w.z : -inf) - 1e-6f;
+  }
+  float fx0 = 0.f, fx1 = 0.f, fy0 = 0.f, fy1 = 0.f;
+  if (cnt0 > 0) {
+    fx0 = fx1 = P0[0][0]; fy0 = fy1 = P0[0][1];
+    for (int v = 1; v < cnt0; ++v) { fx0 = fminf(fx0, P0[v][0]); fx1 = fmaxf(fx1, P0[v][0]); fy0 = fminf(fy0, P0[v][1]); fy1 = fmaxf(fy1, P0[v][1]); }
+    fx0 -= 1e-6f; fx1 += 1e-6f; fy0 -= 1e-6f; fy1 += 1e-6f;
+  }
+#endif
   int nc = 0;                      // candidates so far (warp-uniform)
   V3 nsum = v3(0.f, 0.f, 0.f);     // sum of the candidates' normals (warp-uniform)
   float deep = 0.f;                // lane-local deepest candidate
   for (int r = rmin; r <= rmax; ++r)
     for (int c = cmin; c <= cmax; ++c) {
       const float x0 = c * dx - sx, x1 = (c + 1) * dx - sx, y0 = r * dy - sy, y1 = (r + 1) * dy - sy;
+#ifdef ODUCK_HF_CULL
+      if (x1 < bx0 || x0 > bx1 || y1 < by0 || y0 > by1) continue;      // warp-uniform: the cell misses the hull's box
+#endif
       const float h00 = data[(size_t)r * ncol + c] * sz, h01 = data[(size_t)r * ncol + c + 1] * sz;
       const float h10 = data[(size_t)(r + 1) * ncol + c] * sz, h11 = data[(size_t)(r + 1) * ncol + c + 1] * sz;
 #pragma unroll 1
@@ -86,11 +111,18 @@ static __device__ __noinline__ void hf_collide(const DevModel& m, const DevFF* _
         const V3 T2 = v3(x1, y1, h11);
         const float top = fmaxf(T0.z, fmaxf(T1.z, T2.z));
         if (C.z - rb > top) continue;                                   // warp-uniform
+#ifdef ODUCK_HF_CULL
+        if (bz0 > top) continue;                                        // warp-uniform: the whole hull is above this triangle
+#endif
         V3 n = cross(T1 - T0, T2 - T0);
         n = (1.f / sqrtf(dot(n, n))) * n;
         float A[HF_MAXP][3], B[HF_MAXP][3];
         int cnt = 0;
+#ifdef ODUCK_HF_CULL
+        if (has && dot(Nw, n) < 0.f && !(x1 < fx0 || x0 > fx1 || y1 < fy0 || y0 > fy1)) {
+#else
         if (has && dot(Nw, n) < 0.f) {                                  // only the faces that look down onto the triangle
+#endif
           cnt = hf_clip(P0, cnt0, A, T0.x, T0.y, T1.y - T0.y, -(T1.x - T0.x));
           if (cnt > 0) cnt = hf_clip(A, cnt, B, T1.x, T1.y, T2.y - T1.y, -(T2.x - T1.x));
           if (cnt > 0) cnt = hf_clip(B, cnt, A, T2.x, T2.y, T0.y - T2.y, -(T0.x - T2.x));
