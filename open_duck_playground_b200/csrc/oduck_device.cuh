@@ -412,6 +412,23 @@ static __device__ __noinline__ float symv(const float* A, int n, int lane, float
   __syncwarp();
   xbuf[lane] = lane < n ? x : 0.f;
   __syncwarp();
+#ifdef ODUCK_SYMV_ILP
+  // variant for an A/B run (tools/variants.py): four independent FMA chains instead of one (changes the summation order)
+  float acc4[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int j4 = 0; 4 * j4 < n; ++j4) {
+    const float4 xv = lds4(xbuf + 4 * j4);
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = 4 * j4 + e;
+      if (j < n) {
+        const int idx = (j <= lane) ? ri + j : TRI(j) + lane;
+        acc4[e] = fmaf(A[idx], xs[e], acc4[e]);
+      }
+    }
+  }
+  acc = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
+#else
   for (int j4 = 0; 4 * j4 < n; ++j4) {
     const float4 xv = lds4(xbuf + 4 * j4);
     const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
@@ -424,6 +441,7 @@ static __device__ __noinline__ float symv(const float* A, int n, int lane, float
       }
     }
   }
+#endif
   __syncwarp();
   return lane < n ? acc : 0.f;
 }
