@@ -761,7 +761,10 @@ static void hfield_convex(const OduckHandle& h, const Scratch& s, int k, int slo
   int cmin = (int)std::floor((double)((F.c[0] - rb + sx) / dx)), cmax = (int)std::floor((double)((F.c[0] + rb + sx) / dx));
   int rmin = (int)std::floor((double)((F.c[1] - rb + sy) / dy)), rmax = (int)std::floor((double)((F.c[1] + rb + sy) / dy));
   cmin = std::max(cmin, 0); rmin = std::max(rmin, 0); cmax = std::min(cmax, ncol - 2); rmax = std::min(rmax, nrow - 2);
-  constexpr int MAXC = 2048, MAXP = ODUCK_MAX_PVERT + 4;
+  // MAXC: the candidate list is bounded like the CUDA library's (HF_CAP in csrc/oduck_hfcollide.cuh): later candidates are
+  // dropped but still count in the mean normal.  A resting foot has a few dozen; the cap is only reached by a foot sunk deep
+  // below the terrain (a fallen robot just before its episode ends).
+  constexpr int MAXC = 512, MAXP = ODUCK_MAX_PVERT + 4;
   static thread_local real cd[MAXC], cp[MAXC][3], cn[MAXC][3];
   static thread_local bool cm[MAXC];
   int nc = 0;
@@ -798,12 +801,14 @@ static void hfield_convex(const OduckHandle& h, const Scratch& s, int k, int slo
             }
             cur = 1 - cur; cnt = no;
           }
-          for (int v = 0; v < cnt && nc < MAXC; v++) {
+          for (int v = 0; v < cnt; v++) {
             real w[3] = {poly[cur][v][0] - T[0][0], poly[cur][v][1] - T[0][1], poly[cur][v][2] - T[0][2]};
             real dist = dot3(n, w);
             if (!(dist < 0)) continue;
+            for (int a = 0; a < 3; a++) nmean[a] += n[a];
+            if (nc >= MAXC) continue;
             cd[nc] = dist; cm[nc] = true;
-            for (int a = 0; a < 3; a++) { cp[nc][a] = poly[cur][v][a] - (real)0.5 * dist * n[a]; cn[nc][a] = n[a]; nmean[a] += n[a]; }
+            for (int a = 0; a < 3; a++) { cp[nc][a] = poly[cur][v][a] - (real)0.5 * dist * n[a]; cn[nc][a] = n[a]; }
             nc++;
           }
         }
