@@ -742,6 +742,7 @@ static void convex_convex(const OduckModel& m, const Scratch& s, Scratch& out) {
 //     with the mean candidate normal, exactly like the plane and mesh colliders; repeated picks are inactive.
 // On an all-zero field this reduces to the plane collider's candidate set (sole vertices below z = 0) plus points on cell
 // borders.  The hfield sits at the world origin (checked by the MJCF compiler).
+static int g_hf_max_candidates = 0;   // largest candidate count seen by hfield_convex (tests: how far below MAXC the scenes stay)
 static void hfield_convex(const OduckHandle& h, const Scratch& s, int k, int slot0, Scratch& out) {
   const OduckModel& m = h.m;
   const int b = m.foot_body[k], nrow = m.hfield_nrow, ncol = m.hfield_ncol;
@@ -767,7 +768,7 @@ static void hfield_convex(const OduckHandle& h, const Scratch& s, int k, int slo
   constexpr int MAXC = 512, MAXP = ODUCK_MAX_PVERT + 4;
   static thread_local real cd[MAXC], cp[MAXC][3], cn[MAXC][3];
   static thread_local bool cm[MAXC];
-  int nc = 0;
+  int nc = 0, nc_all = 0;
   real nmean[3] = {0, 0, 0};
   auto H = [&](int r, int c) { return (real)h.hfield[(size_t)r * ncol + c] * sz; };
   for (int r = rmin; r <= rmax; r++)
@@ -806,6 +807,7 @@ static void hfield_convex(const OduckHandle& h, const Scratch& s, int k, int slo
             real dist = dot3(n, w);
             if (!(dist < 0)) continue;
             for (int a = 0; a < 3; a++) nmean[a] += n[a];
+            nc_all++;
             if (nc >= MAXC) continue;
             cd[nc] = dist; cm[nc] = true;
             for (int a = 0; a < 3; a++) { cp[nc][a] = poly[cur][v][a] - (real)0.5 * dist * n[a]; cn[nc][a] = n[a]; }
@@ -815,6 +817,7 @@ static void hfield_convex(const OduckHandle& h, const Scratch& s, int k, int slo
       }
     }
   if (nc == 0) return;
+  if (nc_all > g_hf_max_candidates) g_hf_max_candidates = nc_all;   // diagnostic (racy max across worker threads: good enough)
   real nn = std::sqrt(dot3(nmean, nmean));
   for (int a = 0; a < 3; a++) nmean[a] /= nn;                        // every triangle normal has n_z > 0
   real deepest = 0;
@@ -1865,6 +1868,8 @@ int oduck_test_reward_library(int nu, const double* in, double* out15) {
   for (int k = 0; k < 15; k++) out15[k] = (double)(o[k]);
   return ODUCK_OK;
 }
+
+int oduck_test_hf_max_candidates(int reset) { int v = g_hf_max_candidates; if (reset) g_hf_max_candidates = 0; return v; }
 
 // Diagnostic twin of liboduck_cuda's oduck_debug_forward: same layout (DBG_STRIDE reals per env), values in double.
 int oduck_debug_stride(void) { return 5120; }

@@ -213,6 +213,8 @@ def test_duck_stands_on_rough_terrain(oracle, poly_table):
         assert 0.12 < qpos[e, 2] < 0.22 and abs(np.linalg.norm(qpos[e, 3:7]) - 1) < 1e-9
     qv = h.buffer_numpy("QVEL")
     assert np.abs(qv[:, :6]).max() < 0.2                             # at rest
+    # the candidate lists stay well inside the bound both libraries share (HF_CAP = 512)
+    assert 0 < oracle.lib.oduck_test_hf_max_candidates(1) < 512
 
 
 def test_hfield_env_step_runs(oracle, poly_table):
