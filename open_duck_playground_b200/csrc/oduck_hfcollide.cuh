@@ -18,7 +18,13 @@ struct DevHF {   // global memory
 
 #define HF_CAP 512             // candidates kept per foot (the oracle keeps all; a resting foot has a few dozen)
 #define HF_REC 8               // dist, pos[3], normal[3], -
+#ifdef ODUCK_HF_PAIRS
+#define HF_MAXT 32             // triangles per batch of the pair list
+#define HF_MAXPAIR 256         // (triangle, face) pairs per batch
+#define HF_SCRATCH (HF_CAP * HF_REC + 96 + HF_MAXT * 12 + HF_MAXPAIR)   // + world vertices, triangle table, pair list
+#else
 #define HF_SCRATCH (HF_CAP * HF_REC)
+#endif
 #define HF_MAXP 12             // 8-gon clipped by 3 planes: at most 11 vertices
 
 // Sutherland-Hodgman: keep the part of the polygon on the inner side (d <= 0) of the vertical plane through r0 -> r1
@@ -95,6 +101,116 @@ static __device__ __noinline__ void hf_collide(const DevModel& m, const DevFF* _
   int nc = 0;                      // candidates so far (warp-uniform)
   V3 nsum = v3(0.f, 0.f, 0.f);     // sum of the candidates' normals (warp-uniform)
   float deep = 0.f;                // lane-local deepest candidate
+#ifdef ODUCK_HF_PAIRS
+  // Variant for an A/B run (tools/variants.py): instead of every lane clipping ITS face against every triangle in turn (a
+  // handful of lanes busy, ~18 sequential rounds), the (triangle, face) pairs that survive the box culls are listed first and
+  // then clipped 32 pairs at a time, lane = pair.  The candidate order (triangle, face, polygon vertex) is unchanged.
+  float* wv = cand + HF_CAP * HF_REC;                                   // world vertices [32][3]
+  float* wt = wv + 96;                                                   // triangles [HF_MAXT][12]: T0, T1, T2, n
+  int* wp = reinterpret_cast<int*>(wt + HF_MAXT * 12);                   // pairs [HF_MAXPAIR]: triangle << 5 | face
+  float hx0, hx1, hy0, hy1, hz0;                                          // box of the hull, 1e-6 m margins
+  {
+    const bool vv = lane < m.nvert;
+    const int vl = vv ? lane : 0;
+    const V3 w = p0 + rot(v3(m.vert[f][0][vl], m.vert[f][1][vl], m.vert[f][2][vl]));
+    if (vv) { wv[3 * lane] = w.x; wv[3 * lane + 1] = w.y; wv[3 * lane + 2] = w.z; }
+    const float inf = __int_as_float(0x7f800000);
+    hx1 = wmaxf(vv ? w.x : -inf) + 1e-6f; hx0 = -wmaxf(vv ? -w.x : -inf) - 1e-6f;
+    hy1 = wmaxf(vv ? w.y : -inf) + 1e-6f; hy0 = -wmaxf(vv ? -w.y : -inf) - 1e-6f;
+    hz0 = -wmaxf(vv ? -w.z : -inf) - 1e-6f;
+  }
+  __syncwarp();
+  float gx0 = 0.f, gx1 = 0.f, gy0 = 0.f, gy1 = 0.f;                       // box of this lane's face
+  if (cnt0 > 0) {
+    gx0 = gx1 = P0[0][0]; gy0 = gy1 = P0[0][1];
+    for (int v = 1; v < cnt0; ++v) { gx0 = fminf(gx0, P0[v][0]); gx1 = fmaxf(gx1, P0[v][0]); gy0 = fminf(gy0, P0[v][1]); gy1 = fmaxf(gy1, P0[v][1]); }
+    gx0 -= 1e-6f; gx1 += 1e-6f; gy0 -= 1e-6f; gy1 += 1e-6f;
+  }
+  int nt = 0, np = 0;                                                    // triangles / pairs in the current batch (warp-uniform)
+  auto flush = [&]() {
+    __syncwarp();
+    for (int base = 0; base < np; base += 32) {
+      const int i = base + lane;
+      float A[HF_MAXP][3], B[HF_MAXP][3];
+      int cnt = 0;
+      V3 T0 = v3(0.f, 0.f, 0.f), n = v3(0.f, 0.f, 1.f);
+      if (i < np) {
+        const int pr = wp[i];
+        const float* tr = wt + (pr >> 5) * 12;
+        const int qq = pr & 31;
+        T0 = v3(tr[0], tr[1], tr[2]);
+        const V3 T1 = v3(tr[3], tr[4], tr[5]), T2 = v3(tr[6], tr[7], tr[8]);
+        n = v3(tr[9], tr[10], tr[11]);
+        const int c0 = ff->plane_nvert[qq];
+        float P[8][3];
+        for (int v = 0; v < c0; ++v) {
+          const int vid = ff->plane_vert[qq][v];
+          P[v][0] = wv[3 * vid]; P[v][1] = wv[3 * vid + 1]; P[v][2] = wv[3 * vid + 2];
+        }
+        cnt = hf_clip(P, c0, A, T0.x, T0.y, T1.y - T0.y, -(T1.x - T0.x));
+        if (cnt > 0) cnt = hf_clip(A, cnt, B, T1.x, T1.y, T2.y - T1.y, -(T2.x - T1.x));
+        if (cnt > 0) cnt = hf_clip(B, cnt, A, T2.x, T2.y, T0.y - T2.y, -(T0.x - T2.x));
+      }
+      int k = 0;
+      for (int v = 0; v < cnt; ++v) {
+        const float dist = n.x * (A[v][0] - T0.x) + n.y * (A[v][1] - T0.y) + n.z * (A[v][2] - T0.z);
+        if (dist < 0.f) ++k;
+      }
+      int incl = k;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULLMASK, incl, o); if (lane >= o) incl += t; }
+      const int total = __shfl_sync(FULLMASK, incl, 31);
+      if (total == 0) continue;                                         // warp-uniform
+      int at = nc + incl - k;
+      for (int v = 0; v < cnt; ++v) {
+        const float dist = n.x * (A[v][0] - T0.x) + n.y * (A[v][1] - T0.y) + n.z * (A[v][2] - T0.z);
+        if (!(dist < 0.f)) continue;
+        if (at < HF_CAP) {
+          float* rec = cand + at * HF_REC;
+          rec[0] = dist; rec[1] = A[v][0] - 0.5f * dist * n.x; rec[2] = A[v][1] - 0.5f * dist * n.y; rec[3] = A[v][2] - 0.5f * dist * n.z;
+          rec[4] = n.x; rec[5] = n.y; rec[6] = n.z;
+          deep = fminf(deep, dist);
+        }
+        ++at;
+      }
+      const float kf = (float)k;
+      nsum = nsum + v3(wsum(kf * n.x), wsum(kf * n.y), wsum(kf * n.z));
+      nc += total;
+    }
+    __syncwarp();
+    nt = 0; np = 0;
+  };
+  for (int r = rmin; r <= rmax; ++r)
+    for (int c = cmin; c <= cmax; ++c) {
+      const float x0 = c * dx - sx, x1 = (c + 1) * dx - sx, y0 = r * dy - sy, y1 = (r + 1) * dy - sy;
+      if (x1 < hx0 || x0 > hx1 || y1 < hy0 || y0 > hy1) continue;      // warp-uniform: the cell misses the hull's box
+      const float h00 = data[(size_t)r * ncol + c] * sz, h01 = data[(size_t)r * ncol + c + 1] * sz;
+      const float h10 = data[(size_t)(r + 1) * ncol + c] * sz, h11 = data[(size_t)(r + 1) * ncol + c + 1] * sz;
+#pragma unroll 1
+      for (int i = 0; i < 2; ++i) {
+        const V3 T0 = i == 0 ? v3(x0, y1, h10) : v3(x0, y0, h00);
+        const V3 T1 = i == 0 ? v3(x0, y0, h00) : v3(x1, y0, h01);
+        const V3 T2 = v3(x1, y1, h11);
+        const float top = fmaxf(T0.z, fmaxf(T1.z, T2.z));
+        if (C.z - rb > top || hz0 > top) continue;                      // warp-uniform
+        V3 n = cross(T1 - T0, T2 - T0);
+        n = (1.f / sqrtf(dot(n, n))) * n;
+        const bool act = has && dot(Nw, n) < 0.f && !(x1 < gx0 || x0 > gx1 || y1 < gy0 || y0 > gy1);
+        const unsigned bm = __ballot_sync(FULLMASK, act);
+        if (!bm) continue;                                              // warp-uniform
+        if (nt == HF_MAXT || np + 32 > HF_MAXPAIR) flush();
+        if (lane == 0) {
+          float* tr = wt + nt * 12;
+          tr[0] = T0.x; tr[1] = T0.y; tr[2] = T0.z; tr[3] = T1.x; tr[4] = T1.y; tr[5] = T1.z; tr[6] = T2.x; tr[7] = T2.y; tr[8] = T2.z;
+          tr[9] = n.x; tr[10] = n.y; tr[11] = n.z;
+        }
+        if (act) wp[np + __popc(bm & ((1u << lane) - 1u))] = (nt << 5) | lane;
+        np += __popc(bm);
+        ++nt;
+      }
+    }
+  flush();
+#else
   for (int r = rmin; r <= rmax; ++r)
     for (int c = cmin; c <= cmax; ++c) {
       const float x0 = c * dx - sx, x1 = (c + 1) * dx - sx, y0 = r * dy - sy, y1 = (r + 1) * dy - sy;
@@ -153,6 +269,7 @@ static __device__ __noinline__ void hf_collide(const DevModel& m, const DevFF* _
         nc += total;
       }
     }
+#endif
   if (nc == 0) return;
   nc = min(nc, HF_CAP);
   __syncwarp();

@@ -1,7 +1,7 @@
 #!/bin/bash
 # First GPU call of the next round: verify the shipped state, then A/B the variants prepared at the end of round 1.
 # Before calling (CPU, builds travel with the snapshot):
-#   python tools/variants.py build hfcull=-DODUCK_HF_CULL symvilp=-DODUCK_SYMV_ILP
+#   python tools/variants.py build hfcull=-DODUCK_HF_CULL hfpairs=-DODUCK_HF_PAIRS symvilp=-DODUCK_SYMV_ILP
 # Usage on the box: bash tools/gpu_round2_first.sh r02a
 tag=${1:-r02a}
 o=gpurun_out
@@ -10,7 +10,7 @@ V=open_duck_playground_b200/csrc/variants
 python -c "import __graft_entry__ as g; g.smoke()" > $o/${tag}_smoke.log 2>&1; tail -1 $o/${tag}_smoke.log
 timeout 600 python -m pytest tests -m gpu -q > $o/${tag}_pytest_gpu.log 2>&1; echo "pytest exit $?" >> $o/${tag}_pytest_gpu.log; grep -E "passed|failed|pytest exit" $o/${tag}_pytest_gpu.log | tail -3
 # parity of each variant library through the same tests (ODUCK_CUDA_LIB selects the build, capi.py)
-for v in hfcull symvilp; do
+for v in hfcull hfpairs symvilp; do
   [ -f $V/liboduck_cuda_$v.so ] || continue
   ODUCK_CUDA_LIB=$V/liboduck_cuda_$v.so timeout 600 python -m pytest tests -m gpu -q > $o/${tag}_pytest_gpu_$v.log 2>&1; echo "$v pytest exit $?" >> $o/${tag}_pytest_gpu_$v.log; tail -2 $o/${tag}_pytest_gpu_$v.log
 done
@@ -18,7 +18,9 @@ done
 timeout 300 python bench.py --steps 200 --warmup 20 --no-cpu-baseline > $o/${tag}_bench_n1.json 2> $o/${tag}_bench_n1.err; cut -c1-220 $o/${tag}_bench_n1.json
 [ -f $V/liboduck_cuda_symvilp.so ] && ODUCK_CUDA_LIB=$V/liboduck_cuda_symvilp.so timeout 300 python bench.py --steps 200 --warmup 20 --no-cpu-baseline > $o/${tag}_bench_n1_symvilp.json 2> $o/${tag}_bench_n1_symvilp.err; cut -c1-220 $o/${tag}_bench_n1_symvilp.json
 timeout 300 python bench.py --task rough_terrain_backlash --steps 100 --warmup 10 --no-cpu-baseline > $o/${tag}_bench_rough.json 2> $o/${tag}_bench_rough.err; cut -c1-220 $o/${tag}_bench_rough.json
-[ -f $V/liboduck_cuda_hfcull.so ] && ODUCK_CUDA_LIB=$V/liboduck_cuda_hfcull.so timeout 300 python bench.py --task rough_terrain_backlash --steps 100 --warmup 10 --no-cpu-baseline > $o/${tag}_bench_rough_hfcull.json 2> $o/${tag}_bench_rough_hfcull.err; cut -c1-220 $o/${tag}_bench_rough_hfcull.json
+for v in hfcull hfpairs; do
+  [ -f $V/liboduck_cuda_$v.so ] && ODUCK_CUDA_LIB=$V/liboduck_cuda_$v.so timeout 300 python bench.py --task rough_terrain_backlash --steps 100 --warmup 10 --no-cpu-baseline > $o/${tag}_bench_rough_$v.json 2> $o/${tag}_bench_rough_$v.err; cut -c1-220 $o/${tag}_bench_rough_$v.json
+done
 # the capture round 1 had no budget left for
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_step -s 4 -c 1 -o $o/${tag}_k_step_hf -f python bench.py --task rough_terrain_backlash --steps 6 --warmup 3 --no-cpu-baseline > $o/${tag}_ncu_k_step_hf.log 2>&1; tail -1 $o/${tag}_ncu_k_step_hf.log | cut -c1-200
 ls $o | grep ${tag}
