@@ -146,9 +146,13 @@ __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cas
 // Warp max on the redux unit (sm_100a: redux.sync.max.f32 -> CREDUX.MAX.F32, one instruction instead of a 5-step shuffle
 // butterfly; NaN lanes are ignored).
 __device__ __forceinline__ float wmaxf(float v) {
+#ifdef ODUCK_WARP_EMU   // tests/emu: CPU emulation of one warp (test infrastructure)
+  return emu_wmaxf(v);
+#else
   float r;
   asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
   return r;
+#endif
 }
 // argmax with first-index tie break (jp.argmax semantics); every lane gets the winner: max on the redux unit, then the
 // lowest lane that holds it (ballot + ffs) -- 2 instructions on the shuffle/vote path instead of 10 shuffles
