@@ -888,3 +888,34 @@ __device__ __forceinline__ void forward_euler(const DevModel& m, WarpSmem& s, La
   if (forward_euler_impl<DBG, false, BAR, HF>(m, s, L, lane, last, integrate, out, dbg, ffm, ffs, hfm, hfs))
     forward_euler_impl<DBG, true, BAR, HF>(m, s, L, lane, last, integrate, out, dbg, ffm, ffs, hfm, hfs);
 }
+
+// per-env state record (HBM) <-> the warp's shared memory / registers
+__device__ __forceinline__ void load_env(const DevModel& m, WarpSmem& s, Lane& L, int lane, const float* __restrict__ ph, const float* __restrict__ dr) {
+  if (lane < m.nq) { s.qpos[lane] = ph[lane]; s.qpos0[lane] = dr[DR_QPOS0 + lane]; }
+  if (lane + 32 < m.nq) { s.qpos[lane + 32] = ph[lane + 32]; s.qpos0[lane + 32] = dr[DR_QPOS0 + lane + 32]; }
+  const bool isd = lane < m.nv;
+  L.qvel = isd ? ph[PHYS_QVEL + lane] : 0.f;
+  L.qaccw = isd ? ph[PHYS_QACCW + lane] : 0.f;
+  L.qacc = 0.f;
+  const int a = m.d_act[lane];
+  L.ctrl = a >= 0 ? ph[PHYS_CTRL + a] : 0.f;
+  L.kp = a >= 0 ? dr[DR_KP + a] : 0.f;
+  L.floss = isd ? dr[DR_FLOSS + lane] : 0.f;
+  L.arm = isd ? dr[DR_ARM + lane] : 0.f;
+  L.mass = lane < m.nbody ? dr[lane] : 0.f;
+  L.imt = 1.f / fmaxf(wsum(L.mass), 1e-15f);
+  for (int i = lane; i < 528; i += 32) s.A[i] = 0.f;   // structural zeros of M (only ancestor pairs are rewritten each substep)
+  L.ipos = v3(m.b_ipos[0][lane], m.b_ipos[1][lane], m.b_ipos[2][lane]);
+  if (lane == 1) L.ipos = v3(dr[DR_IPOS1], dr[DR_IPOS1 + 1], dr[DR_IPOS1 + 2]);   // TORSO_BODY_ID = 1 (randomize.py:23)
+  __syncwarp();
+}
+__device__ __forceinline__ void store_phys(const DevModel& m, const WarpSmem& s, const Lane& L, int lane, float* __restrict__ ph) {
+  if (lane < m.nq) ph[lane] = s.qpos[lane];
+  if (lane + 32 < m.nq) ph[lane + 32] = s.qpos[lane + 32];
+  if (lane < m.nv) { ph[PHYS_QVEL + lane] = L.qvel; ph[PHYS_QACCW + lane] = L.qaccw; }
+  const int a = m.d_act[lane];
+  if (a >= 0) ph[PHYS_CTRL + a] = L.ctrl;
+}
+__device__ __forceinline__ void store_out(const WarpSmem& s, int lane, float* __restrict__ o) {
+  for (int i = lane; i < OUT_STRIDE; i += 32) o[i] = s.outrec[i];
+}

@@ -60,3 +60,6 @@ inline float __fdividef(float a, float b) { return a / b; }
 inline float __expf(float a) { return std::exp(a); }
 using std::max;
 using std::min;
+inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+inline void __syncthreads() {}      // one warp per emulated CTA (the kernels' CTA barriers only align instruction streams)
+inline void sincosf(float a, float* s, float* c) { *s = std::sin(a); *c = std::cos(a); }
