@@ -12,7 +12,9 @@
 
 #include "../../include/oduck.h"
 #include "oduck_env.cuh"
+#ifndef ODUCK_WARP_EMU
 #include "oduck_policy_tc.cuh"   // mbarrier helpers
+#endif
 
 #ifndef WPB
 #define WPB 8   // warps (= envs in flight) per CTA
@@ -28,6 +30,13 @@ __device__ __forceinline__ int opaque(int x) {
 #endif
   return x;
 }
+
+// dynamic shared memory of a kernel (tests/emu runs the kernels on CPU threads and hands them a heap block instead)
+#ifdef ODUCK_WARP_EMU
+#define ODUCK_SMEM_RAW(name) unsigned char* name = warp_emu::smem
+#else
+#define ODUCK_SMEM_RAW(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
 
 static thread_local std::string g_err;
 int oduck_fail(int code, const std::string& msg) { g_err = msg; return code; }   // shared with oduck_policy.cu
@@ -47,10 +56,14 @@ __device__ __forceinline__ size_t smem_cfg_bytes() { return (sizeof(DevEnvCfg) +
 // Batch-shared tables (DevModel ~18 KB, DevEnvCfg) -> shared memory: two TMA bulk copies issued by one thread, completion on
 // an mbarrier (cp.async.bulk + expect_tx; SASS UBLKCP) instead of an 18-trip load/store loop in all 256 threads.
 __device__ __forceinline__ void block_load_tables(const Params& p, unsigned char* raw, DevModel*& m, DevEnvCfg*& c, WarpSmem*& ws) {
-  __shared__ __align__(8) uint64_t bar;
   m = reinterpret_cast<DevModel*>(raw);
   c = reinterpret_cast<DevEnvCfg*>(raw + smem_model_bytes());
   ws = reinterpret_cast<WarpSmem*>(raw + smem_model_bytes() + smem_cfg_bytes());
+#ifdef ODUCK_WARP_EMU
+  if (threadIdx.x == 0) { memcpy(m, p.model, sizeof(DevModel)); memcpy(c, p.cfg, sizeof(DevEnvCfg)); }
+  __syncwarp();
+#else
+  __shared__ __align__(8) uint64_t bar;
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -62,13 +75,14 @@ __device__ __forceinline__ void block_load_tables(const Params& p, unsigned char
   }
   __syncthreads();                                     // the barrier is initialised before anyone polls it
   mbar_wait(&bar, 0u);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------- kernels
 // A8 / A9 of SURVEY 8a: n x (forward + euler), or one forward without integration (mjx_env.init's forward).
 template <bool DBG, bool HF>
 __global__ void __launch_bounds__(WPB * 32, CTAS_PER_SM) k_physics(Params p) {
-  extern __shared__ __align__(16) unsigned char raw[];
+  ODUCK_SMEM_RAW(raw);
   DevModel* mp; DevEnvCfg* cp; WarpSmem* ws;
   block_load_tables(p, raw, mp, cp, ws);
   const DevModel& m = *mp;
@@ -143,7 +157,7 @@ __device__ __forceinline__ float feet_contact(const WarpSmem& s, int lane) {   /
 // A2 (+A9, first_state store): Joystick.reset for the masked envs.
 template <bool HF>
 __global__ void __launch_bounds__(WPB * 32, CTAS_PER_SM) k_reset(Params p) {
-  extern __shared__ __align__(16) unsigned char raw[];
+  ODUCK_SMEM_RAW(raw);
   DevModel* mp; DevEnvCfg* cp; WarpSmem* ws;
   block_load_tables(p, raw, mp, cp, ws);
   const DevModel& m = *mp;
@@ -238,7 +252,7 @@ __global__ void __launch_bounds__(WPB * 32, CTAS_PER_SM) k_reset(Params p) {
 // A1 + A16: Joystick.step fused with EpisodeWrapper + AutoResetWrapper.  HF = height-field floor (rough_terrain scenes).
 template <bool HF>
 __global__ void __launch_bounds__(WPB * 32, CTAS_PER_SM) k_step(Params p) {
-  extern __shared__ __align__(16) unsigned char raw[];
+  ODUCK_SMEM_RAW(raw);
   DevModel* mp; DevEnvCfg* cp; WarpSmem* ws;
   block_load_tables(p, raw, mp, cp, ws);
   const DevModel& m = *mp;
@@ -409,7 +423,7 @@ __global__ void __launch_bounds__(WPB * 32, CTAS_PER_SM) k_step(Params p) {
 
 // A14: domain_randomize (common/randomize.py:39-106), one warp per env, one round per split.
 __global__ void __launch_bounds__(WPB * 32, CTAS_PER_SM) k_randomize(Params p) {
-  extern __shared__ __align__(16) unsigned char raw[];
+  ODUCK_SMEM_RAW(raw);
   DevModel* mp; DevEnvCfg* cp; WarpSmem* ws;
   block_load_tables(p, raw, mp, cp, ws);
   const DevModel& m = *mp;
@@ -481,7 +495,12 @@ static Params make_params(OduckHandle* h) {
 template <typename K>
 static int launch(OduckHandle* h, K kernel, const Params& p, void* stream) {
   CUDA_TRY(cudaSetDevice(h->device));
+#ifdef ODUCK_WARP_EMU
+  warp_emu::launch(kernel, h->grid, (size_t)h->smem_bytes, p);
+  (void)stream;
+#else
   kernel<<<h->grid, WPB * 32, h->smem_bytes, (cudaStream_t)stream>>>(p);
+#endif
   CUDA_TRY(cudaGetLastError());
   h->launches++;
   return ODUCK_OK;

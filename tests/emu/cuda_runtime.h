@@ -63,3 +63,58 @@ using std::min;
 inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 inline void __syncthreads() {}      // one warp per emulated CTA (the kernels' CTA barriers only align instruction streams)
 inline void sincosf(float a, float* s, float* c) { *s = std::sin(a); *c = std::cos(a); }
+
+// ---- what a whole translation unit of the library (csrc/oduck_cuda.cu) needs: launch geometry, runtime API, kernel launch
+#include <cstdlib>
+#include <thread>
+#include <vector>
+#define __align__(n) alignas(n)
+struct uint3 { unsigned x, y, z; };
+inline thread_local uint3 threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0};
+inline uint3 gridDim = {1, 1, 1}, blockDim = {32, 1, 1};
+typedef int cudaError_t;
+typedef void* cudaStream_t;
+enum { cudaSuccess = 0 };
+enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+inline cudaError_t cudaMalloc(void** p, size_t n) { *p = std::aligned_alloc(256, (n + 255) / 256 * 256); return *p ? cudaSuccess : 2; }
+inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
+inline cudaError_t cudaMemset(void* p, int v, size_t n) { std::memset(p, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memcpy(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind, cudaStream_t) {
+  for (size_t r = 0; r < h; r++) std::memcpy((char*)d + r * dp, (const char*)s + r * sp, w);
+  return cudaSuccess;
+}
+template <class F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
+inline float __uint_as_float(unsigned u) { return warp_emu::flt(u); }
+template <class T> inline T __ldg(const T* p) { return *p; }
+
+namespace warp_emu {
+inline unsigned char* smem = nullptr;
+// kernel<<<grid, 32, smem_bytes>>>(p): the blocks run one after the other, each as 32 threads (WPB = 1: one warp per block)
+template <class K, class P>
+inline void launch(K kernel, int grid, size_t smem_bytes, const P& p) {
+  std::vector<unsigned char> mem(smem_bytes + 64);
+  smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(mem.data()) + 63) & ~(uintptr_t)63);
+  gridDim.x = (unsigned)grid;
+  std::barrier<> b(32);
+  bar = &b;
+  std::vector<std::thread> th;
+  for (int l = 0; l < 32; l++)
+    th.emplace_back([&, l]() {
+      lane = l;
+      threadIdx.x = (unsigned)l;
+      for (int blk = 0; blk < grid; blk++) {
+        blockIdx.x = (unsigned)blk;
+        kernel(p);
+        sync();                       // the next block reuses the shared-memory block
+      }
+    });
+  for (auto& t : th) t.join();
+}
+}  // namespace warp_emu
