@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define ODUCK_ABI_VERSION 7
+#define ODUCK_ABI_VERSION 8
 
 #define ODUCK_MAX_BODY 20
 #define ODUCK_MAX_JNT 28
@@ -167,6 +167,36 @@ typedef struct OduckModel {
 
 /* Environment constants: Joystick.default_config() (joystick.py:49-102) plus the
  * tables _post_init derives (joystick.py:121-204). */
+/* Reward library: the terms of common/rewards.py that neither Joystick nor Standing wires in (rewards.py:37-90,120,152-224),
+ * selectable per task like the reference selects terms -- by a non-zero entry of reward_config.scales.  Inputs follow the
+ * reference's accessors (open_duck_mini_v2/base.py:193-271): "joints" are the nu actuated joints, sensors are the imu-site
+ * sensors, feet are the two foot sites.  Scaled terms are added to the task's own sum in enum order, before `* dt` and the
+ * clip (joystick.py:444-447).  reward_base_y_swing and reward_feet_phase need a gait clock the reference does not define
+ * and are not offered.  The terms are not reported in the metrics buffer. */
+enum OduckLibTerm {
+  ODUCK_LIB_ORIENTATION = 0,       /* cost_orientation(gravity sensor)          -- Joystick (joystick.py:645, commented out upstream) */
+  ODUCK_LIB_LIN_VEL_Z,             /* cost_lin_vel_z(global_linvel)             rewards.py:37 */
+  ODUCK_LIB_ANG_VEL_XY,            /* cost_ang_vel_xy(global_angvel)            rewards.py:41 */
+  ODUCK_LIB_BASE_HEIGHT,           /* cost_base_height(qpos[2], target)         rewards.py:49 */
+  ODUCK_LIB_ENERGY,                /* cost_energy(joint qvel, actuator_force)   rewards.py:73 */
+  ODUCK_LIB_JOINT_POS_LIMITS,      /* cost_joint_pos_limits(joint qpos, soft)   rewards.py:85 */
+  ODUCK_LIB_TERMINATION,           /* cost_termination(done)                    rewards.py:120 */
+  ODUCK_LIB_JOINT_DEVIATION_HIP,   /* rewards.py:152 */
+  ODUCK_LIB_JOINT_DEVIATION_KNEE,  /* rewards.py:161 */
+  ODUCK_LIB_POSE,                  /* cost_pose(joint qpos, default, weights)   rewards.py:170 */
+  ODUCK_LIB_FEET_SLIP,             /* cost_feet_slip(contact, global_linvel)    rewards.py:180 */
+  ODUCK_LIB_FEET_CLEARANCE,        /* cost_feet_clearance(feet linvel sensors, feet site pos, max_foot_height)  rewards.py:187 */
+  ODUCK_LIB_FEET_HEIGHT,           /* cost_feet_height(swing_peak, first_contact, max_foot_height)              rewards.py:202 */
+  ODUCK_LIB_FEET_AIR_TIME,         /* reward_feet_air_time(feet_air_time, first_contact, command, thresholds)   rewards.py:212 */
+  ODUCK_NLIBTERM
+};
+typedef struct OduckRewardLibrary {
+  double scale[ODUCK_NLIBTERM];    /* 0 = term off (the default: the shipped tasks use none) */
+  double base_height_target, max_foot_height, air_time_threshold_min, air_time_threshold_max;
+  double soft_lowers[ODUCK_MAX_NU], soft_uppers[ODUCK_MAX_NU], pose_weights[ODUCK_MAX_NU];
+  int32_t n_hip, hip_indices[4], n_knee, knee_indices[4];   /* actuator indices */
+} OduckRewardLibrary;
+
 typedef struct OduckEnvConfig {
   int32_t task;                  /* ODUCK_TASK_*: which env class the step implements */
   int32_t n_substeps;            /* ctrl_dt / sim_dt = 10 */
@@ -198,6 +228,7 @@ typedef struct OduckEnvConfig {
   double dxs[8], dys[8], dthetas[16];
   double dx_range[2], dy_range[2], dtheta_range[2];  /* ranges include 0 (poly_reference_motion.py:59-61,105-110) */
   const double* poly_coef;
+  OduckRewardLibrary lib;
 } OduckEnvConfig;
 
 typedef struct OduckHandle OduckHandle;

@@ -14,7 +14,7 @@ import numpy as np
 
 from .mjcf import CompiledModel
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 MAX_BODY, MAX_JNT, MAX_NQ, MAX_NV, MAX_NU, MAX_SITE, MAX_VERT, MAX_FACE, NFEET, NCMD = 20, 28, 36, 32, 16, 8, 32, 64, 2, 7
 OBS_STATE, OBS_PRIV, NMETRIC, REF_DIM, POLY_DEG, MAX_CON = 101, 212, 8, 40, 16, 12
 
@@ -52,6 +52,19 @@ class OduckModel(C.Structure):
     ]
 
 
+LIB_TERMS = ["orientation", "lin_vel_z", "ang_vel_xy", "base_height", "energy", "joint_pos_limits", "termination", "joint_deviation_hip",
+             "joint_deviation_knee", "pose", "feet_slip", "feet_clearance", "feet_height", "feet_air_time"]          # enum OduckLibTerm
+
+
+class OduckRewardLibrary(C.Structure):
+    _fields_ = [
+        ("scale", d * len(LIB_TERMS)),
+        ("base_height_target", d), ("max_foot_height", d), ("air_time_threshold_min", d), ("air_time_threshold_max", d),
+        ("soft_lowers", d * MAX_NU), ("soft_uppers", d * MAX_NU), ("pose_weights", d * MAX_NU),
+        ("n_hip", i32), ("hip_indices", i32 * 4), ("n_knee", i32), ("knee_indices", i32 * 4),
+    ]
+
+
 class OduckEnvConfig(C.Structure):
     _fields_ = [
         ("task", i32), ("n_substeps", i32), ("episode_length", i32), ("use_imitation_reward", i32), ("use_motor_speed_limits", i32),
@@ -68,6 +81,7 @@ class OduckEnvConfig(C.Structure):
         ("dxs", d * 8), ("dys", d * 8), ("dthetas", d * 16),
         ("dx_range", d * 2), ("dy_range", d * 2), ("dtheta_range", d * 2),
         ("poly_coef", C.POINTER(d)),
+        ("lib", OduckRewardLibrary),
     ]
 
 

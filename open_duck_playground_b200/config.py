@@ -140,6 +140,47 @@ def qpos_noise_scale(config: ConfigDict, nu: int) -> np.ndarray:
     return out
 
 
+TASK_TERMS = {"tracking_lin_vel", "tracking_ang_vel", "torques", "action_rate", "stand_still", "alive", "imitation", "head_pos"}
+
+
+def _fill_reward_library(lib, model: CompiledModel, rc: ConfigDict, standing: bool) -> None:
+    """Any other key of ``reward_config.scales`` selects a term of the reward library (include/oduck.h OduckRewardLibrary;
+    common/rewards.py:37-224), the way the reference selects terms by listing them in ``scales``.  Parameters come from
+    ``reward_config`` with the defaults of the functions' signatures / of this robot: ``base_height_target`` (keyframe
+    height), ``max_foot_height`` (0.03 m), ``air_time_threshold_min/max`` (0.1 / 0.5 s, rewards.py:216-217),
+    ``soft_joint_pos_limit_factor`` (0.95 of the actuator ranges about their centres), ``pose_weights`` (ones),
+    ``hip_joints`` (hip yaw + roll) and ``knee_joints`` (actuator names)."""
+    for k, v in rc.scales.items():
+        if k in TASK_TERMS or (k == "orientation" and standing):
+            continue
+        if k not in capi.LIB_TERMS:
+            raise ValueError(f"reward_config.scales: unknown term {k!r} (task terms {sorted(TASK_TERMS)}, library terms {capi.LIB_TERMS})")
+        lib.scale[capi.LIB_TERMS.index(k)] = float(v)
+    nu = model.nu
+    lib.base_height_target = float(rc.get("base_height_target", model.key_qpos[2]))
+    lib.max_foot_height = float(rc.get("max_foot_height", 0.03))
+    lib.air_time_threshold_min = float(rc.get("air_time_threshold_min", 0.1))
+    lib.air_time_threshold_max = float(rc.get("air_time_threshold_max", 0.5))
+    factor = float(rc.get("soft_joint_pos_limit_factor", 0.95))
+    lo, hi = np.asarray(model.act_ctrlrange[:nu, 0], np.float64), np.asarray(model.act_ctrlrange[:nu, 1], np.float64)   # inheritrange: ctrlrange = joint range
+    mid, half = 0.5 * (lo + hi), 0.5 * (hi - lo) * factor
+    w = np.asarray(rc.get("pose_weights", np.ones(nu)), np.float64)
+    if w.shape != (nu,):
+        raise ValueError(f"reward_config.pose_weights must have {nu} entries")
+    for i in range(nu):
+        lib.soft_lowers[i], lib.soft_uppers[i], lib.pose_weights[i] = float(mid[i] - half[i]), float(mid[i] + half[i]), float(w[i])
+    names = list(model.actuator_names)
+    hips = [names.index(j) for j in rc.get("hip_joints", [n for n in names if n.endswith(("hip_yaw", "hip_roll"))])]
+    knees = [names.index(j) for j in rc.get("knee_joints", [n for n in names if n.endswith("knee")])]
+    if len(hips) > 4 or len(knees) > 4:
+        raise ValueError("at most 4 hip and 4 knee joints")
+    lib.n_hip, lib.n_knee = len(hips), len(knees)
+    for i, j in enumerate(hips):
+        lib.hip_indices[i] = j
+    for i, j in enumerate(knees):
+        lib.knee_indices[i] = j
+
+
 def build_env_config(model: CompiledModel, config: ConfigDict, poly: Optional[PolyTable], auto_reset: bool = True,
                      use_imitation_reward: bool = USE_IMITATION_REWARD,
                      use_motor_speed_limits: bool = USE_MOTOR_SPEED_LIMITS, task: int = capi.TASK_JOYSTICK):
@@ -176,8 +217,9 @@ def build_env_config(model: CompiledModel, config: ConfigDict, poly: Optional[Po
     c.scale_tracking_lin_vel, c.scale_tracking_ang_vel = g("tracking_lin_vel"), g("tracking_ang_vel")
     c.scale_torques, c.scale_action_rate = g("torques"), g("action_rate")
     c.scale_stand_still, c.scale_alive, c.scale_imitation = g("stand_still"), g("alive"), g("imitation")
-    c.scale_orientation, c.scale_head_pos = g("orientation"), g("head_pos")
+    c.scale_orientation, c.scale_head_pos = (g("orientation") if standing else 0.0), g("head_pos")
     c.tracking_sigma = float(config.reward_config.tracking_sigma)
+    _fill_reward_library(c.lib, model, config.reward_config, standing)
     for i in range(2):
         c.push_interval_range[i] = float(config.push_config.interval_range[i])
         c.push_magnitude_range[i] = float(config.push_config.magnitude_range[i])

@@ -532,6 +532,9 @@ int oduck_create(const OduckModel* model, const OduckEnvConfig* cfg, int num_env
   if (model->floor_is_hfield && (!model->hfield_data || model->hfield_nrow < 2 || model->hfield_ncol < 2))
     return fail(ODUCK_ERR_MODEL, "oduck_create: height-field floor without elevation data");
   if (cfg->action_max_delay > MAX_DELAY || cfg->imu_max_delay * 3 > 16 || cfg->action_max_delay < 1) return fail(ODUCK_ERR_ARG, "oduck_create: delay history out of range");
+  bool use_lib = false;
+  for (int k = 0; k < ODUCK_NLIBTERM; k++) use_lib |= cfg->lib.scale[k] != 0.0;
+  if (use_lib) return fail(ODUCK_ERR_UNSUPPORTED, "oduck_create: reward-library terms are not implemented on the device yet");
   int ndev = 0;
   CUDA_TRY(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return fail(ODUCK_ERR_CUDA, "oduck_create: no such CUDA device");

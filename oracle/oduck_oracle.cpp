@@ -1390,6 +1390,46 @@ struct RewardLibrary {
   }
 };
 
+// The library terms a task switched on through OduckEnvConfig.lib.scale (include/oduck.h), scaled and summed in enum order.
+// Inputs follow the reference's accessors: joints = the nu actuated joints (base.py:193-215), imu-site sensors
+// (base.py:234-264; global_linvel = site_xmat * local_linvel), feet sites (base.py:266-271), step-local contact /
+// first_contact / feet_air_time (after `+= dt`) / swing_peak (joystick.py:424-435).
+static real reward_library_sum(const OduckHandle& h, const EnvState& e, const real* q, const real* qd, const real* contact,
+                               const real* first_contact, bool done) {
+  const OduckModel& m = h.m;
+  const OduckRewardLibrary& L = h.cfg.lib;
+  bool any = false;
+  for (int k = 0; k < ODUCK_NLIBTERM; k++) any |= L.scale[k] != 0;
+  if (!any) return 0;
+  typedef RewardLibrary R;
+  const real* sd = e.sensordata;
+  real glv[3];
+  for (int i = 0; i < 3; i++) glv[i] = e.imu_xmat[3 * i] * sd[3] + e.imu_xmat[3 * i + 1] * sd[4] + e.imu_xmat[3 * i + 2] * sd[5];
+  real lo[NU], hi[NU], w[NU], dflt[NU];
+  for (int u = 0; u < m.nu; u++) { lo[u] = (real)L.soft_lowers[u]; hi[u] = (real)L.soft_uppers[u]; w[u] = (real)L.pose_weights[u]; dflt[u] = (real)m.key_ctrl[u]; }
+  real feet_vel[2][3], foot_pos[2][3];
+  for (int f = 0; f < 2; f++) for (int i = 0; i < 3; i++) { feet_vel[f][i] = sd[15 + 3 * f + i]; foot_pos[f][i] = e.site_xpos_feet[3 * f + i]; }
+  const real up2[3] = {sd[9], sd[10], sd[11]};
+  real t[ODUCK_NLIBTERM];
+  t[ODUCK_LIB_ORIENTATION] = nan_to_num(up2[0] * up2[0] + up2[1] * up2[1]);                 // rewards.py:45-46
+  t[ODUCK_LIB_LIN_VEL_Z] = R::cost_lin_vel_z(glv);
+  t[ODUCK_LIB_ANG_VEL_XY] = R::cost_ang_vel_xy(sd + 12);
+  t[ODUCK_LIB_BASE_HEIGHT] = R::cost_base_height(e.qpos[2], (real)L.base_height_target);
+  t[ODUCK_LIB_ENERGY] = R::cost_energy(m.nu, qd, e.actuator_force);
+  t[ODUCK_LIB_JOINT_POS_LIMITS] = R::cost_joint_pos_limits(m.nu, q, lo, hi);
+  t[ODUCK_LIB_TERMINATION] = R::cost_termination(done ? (real)1 : (real)0);
+  t[ODUCK_LIB_JOINT_DEVIATION_HIP] = R::cost_joint_deviation_hip(q, e.command, L.n_hip, L.hip_indices, dflt);
+  t[ODUCK_LIB_JOINT_DEVIATION_KNEE] = R::cost_joint_deviation_knee(q, L.n_knee, L.knee_indices, dflt);
+  t[ODUCK_LIB_POSE] = R::cost_pose(m.nu, q, dflt, w);
+  t[ODUCK_LIB_FEET_SLIP] = R::cost_feet_slip(contact, glv);
+  t[ODUCK_LIB_FEET_CLEARANCE] = R::cost_feet_clearance(feet_vel, foot_pos, (real)L.max_foot_height);
+  t[ODUCK_LIB_FEET_HEIGHT] = R::cost_feet_height(e.swing_peak, first_contact, (real)L.max_foot_height);
+  t[ODUCK_LIB_FEET_AIR_TIME] = R::reward_feet_air_time(e.feet_air_time, first_contact, e.command, (real)L.air_time_threshold_min, (real)L.air_time_threshold_max);
+  real sum = 0;
+  for (int k = 0; k < ODUCK_NLIBTERM; k++) if (L.scale[k] != 0) sum += t[k] * (real)L.scale[k];
+  return sum;
+}
+
 // joystick.py:487-620.  Advances e.rng exactly as the reference (5 splits).
 static void get_obs(const OduckHandle& h, EnvState& e, const real* contact) {
   const OduckModel& m = h.m;
@@ -1562,7 +1602,6 @@ static void env_step(OduckHandle& h, EnvState& e, const float* action_f) {  // j
     e.feet_air_time[i] += dt;
     e.swing_peak[i] = std::max(e.swing_peak[i], e.site_xpos_feet[3 * i + 2]);
   }
-  (void)first_contact;
   get_obs(h, e, contact);
   bool nan_state = false;
   for (int i = 0; i < m.nq; i++) nan_state |= std::isnan(e.qpos[i]);
@@ -1592,6 +1631,7 @@ static void env_step(OduckHandle& h, EnvState& e, const float* action_f) {  // j
     scales[0] = c.scale_tracking_lin_vel; scales[1] = c.scale_tracking_ang_vel; scales[2] = c.scale_torques; scales[3] = c.scale_action_rate;
     scales[4] = c.scale_stand_still; scales[5] = c.scale_alive; scales[6] = c.scale_imitation;
   }
+  total += reward_library_sum(h, e, q, qd, contact, first_contact, done);
   real reward = std::min(std::max(total * dt, (real)0), (real)10000);
   for (int i = 0; i < 2; i++) e.push[i] = push[i];
   e.step += 1;
