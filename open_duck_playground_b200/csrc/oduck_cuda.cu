@@ -250,7 +250,8 @@ __global__ void __launch_bounds__(WPB * 32, CTAS_PER_SM) k_reset(Params p) {
 }
 
 // A1 + A16: Joystick.step fused with EpisodeWrapper + AutoResetWrapper.  HF = height-field floor (rough_terrain scenes).
-template <bool HF>
+// RL = reward-library terms switched on (OduckEnvConfig.lib; the shipped tasks use none).
+template <bool HF, bool RL>
 __global__ void __launch_bounds__(WPB * 32, CTAS_PER_SM) k_step(Params p) {
   ODUCK_SMEM_RAW(raw);
   DevModel* mp; DevEnvCfg* cp; WarpSmem* ws;
@@ -314,6 +315,8 @@ __global__ void __launch_bounds__(WPB * 32, CTAS_PER_SM) k_step(Params p) {
     er.targets = tgt;
     // contacts / air time / swing peak (joystick.py:424-435)
     const float contact = feet_contact(s, lane);
+    float first_contact = 0.f;                                       // lane k < 2 (joystick.py:430-431); only the library terms read it
+    if constexpr (RL) first_contact = (er.air > 0.f && (contact != 0.f || er.lastc != 0.f)) ? 1.f : 0.f;
     er.air += dt;
     if (lane < 2) er.swing = fmaxf(er.swing, s.outrec[OUT_FEET + 3 * lane + 2]);
     float* ost = p.obs_state + (size_t)env * ODUCK_OBS_STATE;
@@ -376,6 +379,44 @@ __global__ void __launch_bounds__(WPB * 32, CTAS_PER_SM) k_step(Params p) {
       total = sc0 + sc1 + sc2 + sc3 + sc5 + sc6 + sc4;               // dict order of joystick.py:634-667
       scs[0] = sc0; scs[1] = sc1; scs[2] = sc2; scs[3] = sc3; scs[4] = sc4; scs[5] = sc5; scs[6] = sc6;
       sg[0] = c.sc_lin; sg[1] = c.sc_ang; sg[2] = c.sc_torques; sg[3] = c.sc_rate; sg[4] = c.sc_still; sg[5] = c.sc_alive; sg[6] = c.sc_imit;
+    }
+    if constexpr (RL) {
+      // reward library (include/oduck.h OduckLibTerm; oracle reward_library_sum): scaled terms added in enum order
+      const DevRewardLib& R = *p.rlib;
+      const float* Rs = s.outrec + OUT_IMUMAT;                       // imu site_xmat of the last forward: global_linvel = Rs * local_linvel
+      const float gx = Rs[0] * sd[3] + Rs[1] * sd[4] + Rs[2] * sd[5], gy = Rs[3] * sd[3] + Rs[4] * sd[4] + Rs[5] * sd[5], gz = Rs[6] * sd[3] + Rs[7] * sd[4] + Rs[8] * sd[5];
+      const bool u = lane < nu;
+      const float lo = u ? R.soft_lo[lane] : 0.f, hi = u ? R.soft_hi[lane] : 0.f, pw = u ? R.pose_w[lane] : 0.f;
+      float t[ODUCK_NLIBTERM];
+      t[ODUCK_LIB_ORIENTATION] = nan_to_num(sd[9] * sd[9] + sd[10] * sd[10]);
+      t[ODUCK_LIB_LIN_VEL_Z] = nan_to_num(gz * gz);
+      t[ODUCK_LIB_ANG_VEL_XY] = nan_to_num(sd[12] * sd[12] + sd[13] * sd[13]);
+      { const float dh = s.qpos[2] - R.base_height_target; t[ODUCK_LIB_BASE_HEIGHT] = nan_to_num(dh * dh); }
+      t[ODUCK_LIB_ENERGY] = nan_to_num(wsum(u ? fabsf(qd) * fabsf(afrc) : 0.f));
+      t[ODUCK_LIB_JOINT_POS_LIMITS] = nan_to_num(wsum(u ? -fminf(q - lo, 0.f) + fmaxf(q - hi, 0.f) : 0.f));
+      t[ODUCK_LIB_TERMINATION] = done ? 1.f : 0.f;
+      t[ODUCK_LIB_JOINT_DEVIATION_HIP] = nan_to_num(wsum((u && ((R.hip_mask >> lane) & 1u)) ? fabsf(q - dflt) : 0.f) * (fabsf(c1) > 0.1f ? 1.f : 0.f));
+      t[ODUCK_LIB_JOINT_DEVIATION_KNEE] = nan_to_num(wsum((u && ((R.knee_mask >> lane) & 1u)) ? fabsf(q - dflt) : 0.f));
+      t[ODUCK_LIB_POSE] = nan_to_num(wsum(u ? (q - dflt) * (q - dflt) * pw : 0.f));
+      {
+        const float v = sqrtf(gx * gx + gy * gy);
+        t[ODUCK_LIB_FEET_SLIP] = nan_to_num(v * __shfl_sync(FULLMASK, contact, 0) + v * __shfl_sync(FULLMASK, contact, 1));
+      }
+      {
+        const int f = lane & 1;                                       // lane k < 2: foot k
+        const float vx = sd[15 + 3 * f], vy = sd[16 + 3 * f], fz = s.outrec[OUT_FEET + 3 * f + 2];
+        const float clr = fabsf(fz - R.max_foot_height) * sqrtf(sqrtf(vx * vx + vy * vy));
+        const float eh = er.swing / R.max_foot_height - 1.f;
+        const float at = fminf((er.air - R.air_thr_min) * first_contact, R.air_thr_max - R.air_thr_min);
+        const bool ft = lane < 2;
+        t[ODUCK_LIB_FEET_CLEARANCE] = nan_to_num(wsum(ft ? clr : 0.f));
+        t[ODUCK_LIB_FEET_HEIGHT] = nan_to_num(wsum(ft ? eh * eh * first_contact : 0.f));
+        t[ODUCK_LIB_FEET_AIR_TIME] = nan_to_num(wsum(ft ? at : 0.f) * (cmd_norm > 0.01f ? 1.f : 0.f));
+      }
+      float libsum = 0.f;
+#pragma unroll
+      for (int k = 0; k < ODUCK_NLIBTERM; ++k) if (R.scale[k] != 0.f) libsum += t[k] * R.scale[k];
+      total += libsum;
     }
     const float reward = fminf(fmaxf(total * dt, 0.f), 10000.f);
     // info updates (joystick.py:449-469)
@@ -487,7 +528,7 @@ static Params make_params(OduckHandle* h) {
   p.reward = h->reward; p.done = h->done; p.trunc = h->trunc; p.metrics = h->metrics;
   p.first_phys = h->first_phys; p.first_obs_state = h->first_obs_state; p.first_obs_priv = h->first_obs_priv; p.dbg = h->dbg;
   p.ffmodel = h->dff; p.ffscratch = h->ffscratch;
-  p.hfmodel = h->dhf; p.hfscratch = h->hfscratch;
+  p.hfmodel = h->dhf; p.hfscratch = h->hfscratch; p.rlib = h->drlib;
   p.N = h->n;
   return p;
 }
@@ -519,7 +560,7 @@ int oduck_destroy(OduckHandle* h) {
   if (!h) return ODUCK_OK;
   cudaSetDevice(h->device);
   void* ptrs[] = {h->dmodel, h->dcfg, h->poly, h->phys, h->dr, h->out, h->info, h->obs_state, h->obs_priv, h->reward, h->done, h->trunc,
-                  h->metrics, h->first_phys, h->first_obs_state, h->first_obs_priv, h->dbg, h->policy_scratch, h->dff, h->ffscratch, h->dhf, h->hfdata, h->hfscratch};
+                  h->metrics, h->first_phys, h->first_obs_state, h->first_obs_priv, h->dbg, h->policy_scratch, h->dff, h->ffscratch, h->dhf, h->hfdata, h->hfscratch, h->drlib};
   for (void* q : ptrs) if (q) cudaFree(q);
   delete h;
   return ODUCK_OK;
@@ -534,7 +575,7 @@ int oduck_create(const OduckModel* model, const OduckEnvConfig* cfg, int num_env
   if (cfg->action_max_delay > MAX_DELAY || cfg->imu_max_delay * 3 > 16 || cfg->action_max_delay < 1) return fail(ODUCK_ERR_ARG, "oduck_create: delay history out of range");
   bool use_lib = false;
   for (int k = 0; k < ODUCK_NLIBTERM; k++) use_lib |= cfg->lib.scale[k] != 0.0;
-  if (use_lib) return fail(ODUCK_ERR_UNSUPPORTED, "oduck_create: reward-library terms are not implemented on the device yet");
+  if (use_lib && (cfg->lib.n_hip < 0 || cfg->lib.n_hip > 4 || cfg->lib.n_knee < 0 || cfg->lib.n_knee > 4)) return fail(ODUCK_ERR_ARG, "oduck_create: at most 4 hip / knee joints");
   int ndev = 0;
   CUDA_TRY(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return fail(ODUCK_ERR_CUDA, "oduck_create: no such CUDA device");
@@ -582,6 +623,19 @@ int oduck_create(const OduckModel* model, const OduckEnvConfig* cfg, int num_env
     CUDA_TRY(cudaMemcpy(h->dhf, &d, sizeof(DevHF), cudaMemcpyHostToDevice));
   }
   h->hm.hfield_data = nullptr;      // the caller's array is not kept
+  if (use_lib) {
+    DevRewardLib r;
+    memset(&r, 0, sizeof(r));
+    const OduckRewardLibrary& L = cfg->lib;
+    for (int k = 0; k < ODUCK_NLIBTERM; k++) r.scale[k] = (float)L.scale[k];
+    r.base_height_target = (float)L.base_height_target; r.max_foot_height = (float)L.max_foot_height;
+    r.air_thr_min = (float)L.air_time_threshold_min; r.air_thr_max = (float)L.air_time_threshold_max;
+    for (int u = 0; u < model->nu; u++) { r.soft_lo[u] = (float)L.soft_lowers[u]; r.soft_hi[u] = (float)L.soft_uppers[u]; r.pose_w[u] = (float)L.pose_weights[u]; }
+    for (int i = 0; i < L.n_hip; i++) r.hip_mask |= 1u << L.hip_indices[i];
+    for (int i = 0; i < L.n_knee; i++) r.knee_mask |= 1u << L.knee_indices[i];
+    if (cudaMalloc((void**)&h->drlib, sizeof(DevRewardLib)) != cudaSuccess) { oduck_destroy(h); return fail(ODUCK_ERR_ALLOC, "oduck_create: cudaMalloc failed"); }
+    CUDA_TRY(cudaMemcpy(h->drlib, &r, sizeof(DevRewardLib), cudaMemcpyHostToDevice));
+  }
   ALLOC(h->phys, N * PHYS_STRIDE); ALLOC(h->dr, N * DR_STRIDE); ALLOC(h->out, N * OUT_STRIDE); ALLOC(h->info, N * INFO_STRIDE);
   ALLOC(h->obs_state, N * ODUCK_OBS_STATE); ALLOC(h->obs_priv, N * ODUCK_OBS_PRIV);
   ALLOC(h->reward, N); ALLOC(h->done, N); ALLOC(h->trunc, N); ALLOC(h->metrics, N * ODUCK_NMETRIC);
@@ -611,12 +665,14 @@ int oduck_create(const OduckModel* model, const OduckEnvConfig* cfg, int num_env
     CUDA_TRY(cudaFuncSetAttribute(k_physics<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
     CUDA_TRY(cudaFuncSetAttribute(k_physics<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
     CUDA_TRY(cudaFuncSetAttribute(k_reset<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
-    CUDA_TRY(cudaFuncSetAttribute(k_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+    CUDA_TRY(cudaFuncSetAttribute(k_step<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+    CUDA_TRY(cudaFuncSetAttribute(k_step<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
   } else {
     CUDA_TRY(cudaFuncSetAttribute(k_physics<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
     CUDA_TRY(cudaFuncSetAttribute(k_physics<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
     CUDA_TRY(cudaFuncSetAttribute(k_reset<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
-    CUDA_TRY(cudaFuncSetAttribute(k_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+    CUDA_TRY(cudaFuncSetAttribute(k_step<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+    CUDA_TRY(cudaFuncSetAttribute(k_step<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
   }
   CUDA_TRY(cudaFuncSetAttribute(k_randomize, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
   h->grid = (num_envs + WPB - 1) / WPB;
@@ -641,7 +697,8 @@ int oduck_step(OduckHandle* h, const float* action, void* stream) {
   if (!h || !action) return fail(ODUCK_ERR_ARG, "oduck_step: bad argument");
   Params p = make_params(h);
   p.action = action;
-  return h->dhf ? launch(h, k_step<true>, p, stream) : launch(h, k_step<false>, p, stream);
+  if (h->drlib) return h->dhf ? launch(h, k_step<true, true>, p, stream) : launch(h, k_step<false, true>, p, stream);
+  return h->dhf ? launch(h, k_step<true, false>, p, stream) : launch(h, k_step<false, false>, p, stream);
 }
 int oduck_physics_substeps(OduckHandle* h, const float* ctrl, int n, void* stream) {
   if (!h || n < 0) return fail(ODUCK_ERR_ARG, "oduck_physics_substeps: bad argument");

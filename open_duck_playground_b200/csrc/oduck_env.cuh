@@ -38,6 +38,14 @@ struct alignas(16) DevEnvCfg {
   float dxs[8], dys[8], dths[16], dx_range[2], dy_range[2], dth_range[2];
 };
 
+// Reward-library parameters (include/oduck.h OduckRewardLibrary) for the RL instantiations of k_step; global memory
+struct DevRewardLib {
+  float scale[ODUCK_NLIBTERM];
+  float base_height_target, max_foot_height, air_thr_min, air_thr_max;
+  float soft_lo[16], soft_hi[16], pose_w[16];
+  unsigned hip_mask, knee_mask;       // actuator lanes
+};
+
 // ---------------------------------------------------------------------------------- jax.random
 __device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
 __device__ __forceinline__ void threefry2x32(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1, uint32_t& o0, uint32_t& o1) {

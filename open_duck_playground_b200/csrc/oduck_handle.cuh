@@ -19,6 +19,7 @@ struct Params {
   int N, nsub, integrate;
   const DevHF* hfmodel;    // height-field floor (HF kernel instantiations only); last, so that the flat kernels' argument layout is unchanged
   float* hfscratch;        // per env: HF_SCRATCH floats of contact candidates
+  const DevRewardLib* rlib;   // reward-library parameters (RL kernel instantiations only)
 };
 
 struct OduckHandle {
@@ -38,6 +39,7 @@ struct OduckHandle {
   DevHF* dhf;                     // height-field floor: descriptor, elevation samples, per-env candidate lists
   float* hfdata;
   float* hfscratch;
+  DevRewardLib* drlib;            // reward-library parameters; null when no library term is switched on
   float* policy_scratch;          // hidden activations of the actor MLP (tensor-core path)
   size_t policy_scratch_floats;
   const float* policy_packed_for;  // w[0] pointer the packed weight copy was made from

@@ -19,14 +19,18 @@ EMU = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu")
 CSRC = os.path.join(os.path.dirname(EMU), "..", "open_duck_playground_b200", "csrc")
 
 
-@pytest.fixture(scope="module")
-def emu_lib():
+def build_emu_library():
     out = os.path.join(EMU, "_build", "liboduck_emu.so")
     srcs = [os.path.join(EMU, f) for f in ("oduck_emu.cpp", "cuda_runtime.h")] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-fPIC", "-shared", f"-I{EMU}", "-DWPB=1", "-x", "c++", os.path.join(EMU, "oduck_emu.cpp"), "-o", out])
     return capi.Library(out, is_device=False)
+
+
+@pytest.fixture(scope="module")
+def emu_lib():
+    return build_emu_library()
 
 
 def _np(t):

@@ -9,6 +9,7 @@ mkdir -p $o
 V=open_duck_playground_b200/csrc/variants
 python -c "import __graft_entry__ as g; g.smoke()" > $o/${tag}_smoke.log 2>&1; tail -1 $o/${tag}_smoke.log
 timeout 600 python -m pytest tests -m gpu -q > $o/${tag}_pytest_gpu.log 2>&1; echo "pytest exit $?" >> $o/${tag}_pytest_gpu.log; grep -E "passed|failed|pytest exit" $o/${tag}_pytest_gpu.log | tail -3
+# (before calling: drop the skip marker of tests/test_reward_library.py::test_library_terms_gpu_parity -- its first GPU run)
 # parity of each variant library through the same tests (ODUCK_CUDA_LIB selects the build, capi.py)
 for v in hfcull hfpairs symvilp; do
   [ -f $V/liboduck_cuda_$v.so ] || continue
