@@ -1,0 +1,30 @@
+"""GPU tests of kernel instantiations that were written after the round's GPU budget was spent and have therefore never run
+on hardware (their logic is covered on CPU threads by tests/emu).  The file sorts last and every case runs in a CHILD process
+with a time limit: a fault or a hang in such a kernel ends the child, not the CUDA context of the suite.  Non-strict xfail:
+the outcome (xpassed / xfailed) is the record of the first run; once a case has passed on a B200 it moves to its proper file
+as a plain test."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run_child(code: str, limit: int = 420):
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([ROOT, os.path.join(ROOT, "tests"), os.environ.get("PYTHONPATH", "")]))
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=limit)
+    sys.stdout.write(r.stdout[-4000:])
+    sys.stderr.write(r.stderr[-4000:])
+    return r.returncode
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="first GPU run of k_step<HF, RL = true> (reward-library terms, DESIGN.md 3f)")
+def test_library_terms_gpu_parity_first_run():
+    code = ("from oracle import oracle_lib\n"
+            "import test_reward_library as t\n"
+            "t.library_terms_gpu_parity(oracle_lib.load())\n"
+            "print('library terms: CUDA == oracle')\n")
+    assert _run_child(code) == 0

@@ -9,7 +9,8 @@ mkdir -p $o
 V=open_duck_playground_b200/csrc/variants
 python -c "import __graft_entry__ as g; g.smoke()" > $o/${tag}_smoke.log 2>&1; tail -1 $o/${tag}_smoke.log
 timeout 600 python -m pytest tests -m gpu -q > $o/${tag}_pytest_gpu.log 2>&1; echo "pytest exit $?" >> $o/${tag}_pytest_gpu.log; grep -E "passed|failed|pytest exit" $o/${tag}_pytest_gpu.log | tail -3
-# (before calling: drop the skip marker of tests/test_reward_library.py::test_library_terms_gpu_parity -- its first GPU run)
+# (tests/test_zz_first_gpu_runs.py holds the first GPU run of k_step<HF, RL = true>: -rxX prints its outcome)
+timeout 600 python -m pytest tests/test_zz_first_gpu_runs.py -m gpu -q -rxX > $o/${tag}_pytest_first_runs.log 2>&1; tail -4 $o/${tag}_pytest_first_runs.log
 # parity of each variant library through the same tests (ODUCK_CUDA_LIB selects the build, capi.py)
 for v in hfcull hfpairs symvilp; do
   [ -f $V/liboduck_cuda_$v.so ] || continue
