@@ -85,6 +85,11 @@ struct alignas(16) DevModel {   // 16-byte multiple: staged into shared memory w
   int scan_ok, scan_rounds, n_branch;
   int b_next[NLANE];
   int br_nchild[4], br_child[4][4], br_chain[4];
+#ifdef ODUCK_ANC_PIPE
+  // variant for an A/B run (tools/variants.py): anc transposed, anc_t[l][k] = anc[k][l].  A warp that reads "my ancestor at depth
+  // l" touches 32 consecutive bytes (one wavefront) instead of 32 rows 32 bytes apart (8 lanes per bank)
+  unsigned char anc_t[NLANE][NLANE];
+#endif
 };
 
 // per-warp shared memory
@@ -306,6 +311,31 @@ __device__ __forceinline__ void branch_elim(float* H, float* rhs, const int lane
     a[i] = (i >= CH_NB && j <= i && col) ? H[TRI(gi) + gj] : 0.f;
   }
   r = (j >= CH_NB && col) ? rhs[gj] : 0.f;
+#ifdef ODUCK_CHOL_LDL
+  // Variant for an A/B run (tools/variants.py): square-root-free form.  The pivot row stays unnormalised (u_kj, u_kk = d_k), so
+  // its hand-over through shared memory no longer waits for the pivot's broadcast and reciprocal root: per pivot the chain
+  // SHFL -> RSQ -> MUL -> STS -> LDS -> FMA becomes max(SHFL -> RCP -> MUL, STS -> LDS) -> FMA.  H then holds U with
+  // M = U^T D^-1 U and rhs the unscaled sweep r = sqrt(D) y; chol_rev_back reads both forms with the same code
+  // (x_k = (r_k - sum_j u_kj x_j) / u_kk), and nothing else consumes the factor.
+#pragma unroll
+  for (int k = NLOC - 1; k >= CH_NB; --k) {
+    const float uk = j < k ? a[k] : 0.f;                       // u_kj, final
+    __syncwarp();                                               // the previous pivot's row has been read by every lane
+    rowbuf[hb | j] = uk;
+    const float invd = 1.f / __shfl_sync(FULLMASK, a[k], hb | k);
+    const float w = uk * invd;                                  // u_kj / d_k, zero for j >= k
+    r = fmaf(-w, __shfl_sync(FULLMASK, r, hb | k), r);
+    __syncwarp();
+#pragma unroll
+    for (int i4 = 0; i4 < (k + 3) / 4; ++i4) {                  // A[i][j] -= u_ki u_kj / d_k
+      const float4 v = lds4(rowbuf + hb + 4 * i4);
+      a[4 * i4] = fmaf(-v.x, w, a[4 * i4]);
+      if (4 * i4 + 1 < NLOC) a[4 * i4 + 1] = fmaf(-v.y, w, a[4 * i4 + 1]);
+      if (4 * i4 + 2 < NLOC) a[4 * i4 + 2] = fmaf(-v.z, w, a[4 * i4 + 2]);
+      if (4 * i4 + 3 < NLOC) a[4 * i4 + 3] = fmaf(-v.w, w, a[4 * i4 + 3]);
+    }
+  }
+#else
 #pragma unroll
   for (int k = NLOC - 1; k >= CH_NB; --k) {
     const float akk = __shfl_sync(FULLMASK, a[k], hb | k);
@@ -326,6 +356,7 @@ __device__ __forceinline__ void branch_elim(float* H, float* rhs, const int lane
       if (4 * i4 + 3 < NLOC) a[4 * i4 + 3] = fmaf(-v.w, lk, a[4 * i4 + 3]);
     }
   }
+#endif
   if (store && col) {
 #pragma unroll
     for (int i = CH_NB; i < NLOC; ++i)
@@ -359,6 +390,16 @@ static __device__ __noinline__ void chol_rev_chain(const DevModel& m, float* H, 
   for (int i = 0; i < CH_NB; ++i) b[i] = (j <= i && j < CH_NB) ? H[TRI(i) + j] + db[i] : 0.f;
   if (j < CH_NB) rb = rhs[j] + dr;
   const int hb = lane & 16;
+#ifdef ODUCK_CHOL_LDL
+#pragma unroll
+  for (int k = CH_NB - 1; k >= 0; --k) {
+    const float uk = j < k ? b[k] : 0.f;
+    const float w = uk * (1.f / __shfl_sync(FULLMASK, b[k], hb | k));
+    rb = fmaf(-w, __shfl_sync(FULLMASK, rb, hb | k), rb);
+#pragma unroll
+    for (int i = 0; i < k; ++i) b[i] = fmaf(-__shfl_sync(FULLMASK, uk, hb | i), w, b[i]);   // the row's hand-over does not wait for the reciprocal
+  }
+#else
 #pragma unroll
   for (int k = CH_NB - 1; k >= 0; --k) {
     const float akk = __shfl_sync(FULLMASK, b[k], hb | k);
@@ -370,6 +411,7 @@ static __device__ __noinline__ void chol_rev_chain(const DevModel& m, float* H, 
 #pragma unroll
     for (int i = 0; i < k; ++i) b[i] = fmaf(-__shfl_sync(FULLMASK, lk, hb | i), lk, b[i]);
   }
+#endif
   if (lane < CH_NB) {
 #pragma unroll
     for (int i = 0; i < CH_NB; ++i)
@@ -393,12 +435,29 @@ static __device__ __noinline__ float chol_rev_back(const DevModel& m, const floa
     const float invd = lane < n ? 1.f / L[TRI(lane) + lane] : 0.f;
     const unsigned char* al = m.anc[lane];
     const int ri = TRI(lane);
+#ifdef ODUCK_ANC_PIPE
+    // same arithmetic, software-pipelined: the ancestor index and the factor entry of level lev + 1 are fetched while level lev
+    // is in flight, so the serial chain of a level is SHFL -> FFMA instead of LDS.U8 -> SHFL -> LDS -> FFMA
+    (void)al;
+    int j = dep > 0 ? m.anc_t[0][lane] : lane;
+    float l = dep > 0 ? L[ri + j] : 0.f;
+    for (int lev = 0; lev <= m.max_dof_depth; ++lev) {
+      const bool nx = dep > lev + 1;
+      const int jn = nx ? m.anc_t[lev + 1][lane] : lane;
+      const float ln = nx ? L[ri + jn] : 0.f;
+      if (dep == lev) y *= invd;
+      const float xj = __shfl_sync(FULLMASK, y, j);
+      if (dep > lev) y -= l * xj;
+      j = jn; l = ln;
+    }
+#else
     for (int lev = 0; lev <= m.max_dof_depth; ++lev) {
       if (dep == lev) y *= invd;
       const int j = dep > lev ? al[lev] : lane;
       const float xj = __shfl_sync(FULLMASK, y, j);
       if (dep > lev) y -= L[ri + j] * xj;
     }
+#endif
     return y;
   }
   for (int j = 0; j < n; ++j) {
@@ -416,7 +475,29 @@ static __device__ __noinline__ float symv(const float* A, int n, int lane, float
   __syncwarp();
   xbuf[lane] = lane < n ? x : 0.f;
   __syncwarp();
-#ifdef ODUCK_SYMV_ILP
+#if defined(ODUCK_SYMV_UNROLL)
+  // variant for an A/B run (tools/variants.py): the column loop fully unrolled and branch-free on four independent FMA chains.
+  // j is a compile-time constant, so TRI(j) and both address forms fold into LDS immediates (the rolled loop spends ~14 issue
+  // slots per element on index arithmetic and divergence bookkeeping for the j < n test).  No per-element bound test: columns
+  // n .. 4 ceil(n / 4) - 1 multiply x = 0 (xbuf is zero-padded) with the zero padding rows of A (load_env clears all 528
+  // floats and only ancestor pairs are rewritten), both addresses stay inside the 528-float triangle for every lane.
+  float acc4[4] = {0.f, 0.f, 0.f, 0.f};
+  const float* Arow = A + ri;
+  const float* Acol = A + lane;
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    if (4 * j4 >= n) break;                                    // warp-uniform
+    const float4 xv = lds4(xbuf + 4 * j4);
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = 4 * j4 + e;
+      const float* pj = (j <= lane) ? Arow + j : Acol + TRI(j);
+      acc4[e] = fmaf(*pj, xs[e], acc4[e]);
+    }
+  }
+  acc = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
+#elif defined(ODUCK_SYMV_ILP)
   // variant for an A/B run (tools/variants.py): four independent FMA chains instead of one (changes the summation order)
   float acc4[4] = {0.f, 0.f, 0.f, 0.f};
   for (int j4 = 0; 4 * j4 < n; ++j4) {
