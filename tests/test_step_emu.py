@@ -130,3 +130,10 @@ def test_prepared_variants(emu, oracle, poly_table, flag):
         assert all(np.array_equal(got[k], base[k]) for k in got)        # culls skip work / prefetches reorder loads: never change a number
     elif flag == "-DODUCK_HF_PAIRS":
         assert np.abs(got["QVEL"] - base["QVEL"]).max(axis=1).mean() < 1e-4   # same candidates; the mean normal is summed in another order
+
+
+def test_prepared_variants_combined(oracle, model_backlash, poly_table):
+    """The three k_step variants together (the `fast1` build of tools/gpu_round2_first.sh), flat floor, one control step."""
+    var = load_emu("step_emu_fast1", ("-DODUCK_CHOL_LDL", "-DODUCK_SYMV_UNROLL", "-DODUCK_ANC_PIPE"))
+    got, ref = _run_pair(var, oracle, model_backlash, poly_table, n=16, nsub=10, seed=500)
+    _check(got, ref, min_ok=0.9)
