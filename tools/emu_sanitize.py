@@ -2,6 +2,7 @@
 -fsanitize=bounds and with -fsanitize=address and drives reset / step / physics of every task flavour through it.
 
     python tools/emu_sanitize.py            # prints one line per configuration; sanitizer reports go to stderr
+    python tools/emu_sanitize.py -DODUCK_CHOL_LDL -DODUCK_SYMV_UNROLL -DODUCK_ANC_PIPE     # the same for a variant build
 
 A CPU analogue of `compute-sanitizer --tool memcheck` for the kernels' indexing (shared-memory records are plain arrays in the
 emulation, so UBSan's bounds checker sees every `s.con[lane][k]`-style access; ASan guards the HBM-side buffers)."""
@@ -35,10 +36,12 @@ for cls, task, cfg in ((Joystick, "flat_terrain_backlash", None), (Joystick, "fl
 
 def main():
     rc = 0
+    extra = [a for a in sys.argv[1:] if a.startswith("-D")]
+    suffix = "".join("_" + a[3:].lower() for a in extra)
     for tag, flag in (("ubsan-bounds", "-fsanitize=bounds"), ("asan", "-fsanitize=address")):
-        lib = os.path.join(EMU, "_build", f"liboduck_emu_{tag}.so")
+        lib = os.path.join(EMU, "_build", f"liboduck_emu_{tag}{suffix}.so")
         os.makedirs(os.path.dirname(lib), exist_ok=True)
-        subprocess.check_call(["g++", "-std=c++20", "-O1", "-g", "-pthread", "-fPIC", "-shared", f"-I{EMU}", "-DWPB=1", flag, "-x", "c++", os.path.join(EMU, "oduck_emu.cpp"), "-o", lib])
+        subprocess.check_call(["g++", "-std=c++20", "-O1", "-g", "-pthread", "-fPIC", "-shared", f"-I{EMU}", "-DWPB=1", flag, *extra, "-x", "c++", os.path.join(EMU, "oduck_emu.cpp"), "-o", lib])
         env = dict(os.environ, ASAN_OPTIONS="detect_leaks=0", UBSAN_OPTIONS="print_stacktrace=1")
         if tag == "asan":
             env["LD_PRELOAD"] = subprocess.check_output(["g++", "-print-file-name=libasan.so"], text=True).strip()
