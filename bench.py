@@ -195,6 +195,102 @@ def run_physics(args, rank, world, dev):
         dist.destroy_process_group()
 
 
+def run_rollout_pipelined(args, rank, world, dev):
+    """Experiment for the round-2 A/B (--pipeline P, off by default): the rollout step of one env batch as P independent sub-batches,
+    each with its own library handle, CUDA graph and stream.  Envs are independent and the actor only reads its own sub-batch's
+    observations, so sub-batch 0 may start step k + 1 while the tail CTAs of sub-batch P - 1's step k still run.  At 4096 envs
+    k_step is 512 CTAs over 296 resident slots = 1.73 waves, and a latency-bound wave costs the same full or not: one stream pays
+    for two waves per step, P streams keep the slots full (the per-env rate of the 64 k-env line).  Every env still takes one
+    actor forward + one env.step per step, in order; results per env are those of the single-stream run (same keys, same slices)."""
+    import torch
+    import torch.distributed as dist
+    from open_duck_playground_b200 import ppo, rng as jr
+    from open_duck_playground_b200.joystick import Joystick
+    P, n = args.pipeline, args.envs_per_gpu
+    if n % P:
+        raise SystemExit("--envs-per-gpu must be a multiple of --pipeline")
+    m = n // P
+    n_sets = max(3, int(np.ceil(1.3 * L2_BYTES / (n * STATE_BYTES_PER_ENV))))
+    all_dr = jr.split(jr.PRNGKey(2), world * n)
+    envs = []                                                           # envs[set][sub-batch]
+    for s_ in range(n_sets):
+        rk = jr.split(jr.PRNGKey(100 + s_), world * n)
+        row = []
+        for q in range(P):
+            sl = slice(rank * n + q * m, rank * n + (q + 1) * m)
+            e = Joystick(TASK, device=dev)
+            e.randomize(all_dr[sl])
+            e.reset(rk[sl])
+            row.append(e)
+        envs.append(row)
+    torch.manual_seed(0)
+    policy = ppo.MLP([101, 512, 256, 128, 28]).to(dev)
+    weights = ppo.PolicyWeights(policy, 101, dev)
+    n_keys = 8
+    keys = [torch.from_numpy(jr.split(jr.PRNGKey(1000 + k), world * n)[rank * n:(rank + 1) * n].view(np.int32).copy()).to(dev) for k in range(n_keys)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(P)]
+    key_static = [torch.empty(m, 2, dtype=torch.int32, device=dev) for _ in range(P)]
+    for k in range(max(3, args.warmup, n_sets)):                        # eager warm-up of every handle (sizes its actor scratch)
+        for q in range(P):
+            e = envs[k % n_sets][q]
+            act, _, _ = ppo.policy_forward(e, weights, keys[k % n_keys][q * m:(q + 1) * m].contiguous(), deterministic=False)
+            e.step(None, act)
+    torch.cuda.synchronize()
+    graphs = []
+    for s_ in range(n_sets):
+        row = []
+        for q in range(P):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=streams[q]):
+                act, raw, logp = ppo.policy_forward(envs[s_][q], weights, key_static[q], deterministic=False)
+                envs[s_][q].step(None, act)
+            row.append((g, act, raw, logp))
+        graphs.append(row)
+    torch.cuda.synchronize()
+
+    def step(k):
+        for q in range(P):
+            with torch.cuda.stream(streams[q]):
+                key_static[q].copy_(keys[k % n_keys][q * m:(q + 1) * m], non_blocking=True)
+                graphs[k % n_sets][q][0].replay()
+
+    def timed(steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        main = torch.cuda.current_stream(dev)
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record(main)
+        for st in streams:
+            st.wait_event(t0)
+        for k in range(steps):
+            step(k)
+        for st in streams:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            main.wait_event(ev)
+        t1.record(main)
+        torch.cuda.synchronize()
+        ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    timed(n_sets)
+    ms_total = timed(args.steps)
+    if rank == 0:
+        value = world * n * args.steps / (ms_total * 1e-3)
+        print(json.dumps({"metric": "env-steps/sec (batched physics+rollout)", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+                          "warmup": max(3, args.warmup, n_sets), "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": f"{TASK} joystick rollout step = actor-MLP forward + env.step, {n} envs per GPU as {P} sub-batches of {m} on {P} streams (experiment)",
+                                     "task": TASK, "envs_per_gpu": n, "pipeline": P, "l2": f"{n_sets} env sets rotated",
+                                     "launch": "one CUDA graph per (env set, sub-batch), each sub-batch replayed on its own stream"},
+                          "gpu_launches": 6 * P * args.steps, "physics_substeps_per_s": value * 10}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_ppo(args, rank, world, dev):
     """BASELINE configs[2]: full PPO (8192 envs x unroll 20 per training step), timed end to end with the rollout / gather / update split."""
     import torch
@@ -239,6 +335,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--task", default=TASK, help="scene: flat_terrain_backlash (the metric's config), flat_terrain, rough_terrain_backlash (height-field floor, BASELINE configs[3])")
+    ap.add_argument("--pipeline", type=int, default=1, help="experiment: split the env batch into P sub-batches, one CUDA graph and stream each (rollout mode)")
     ap.add_argument("--mode", default="rollout", choices=["rollout", "ppo", "physics"],
                     help="ppo = BASELINE configs[2]: full PPO training steps (rollout / gather / update split); physics = oduck_physics_substeps(10) alone")
     args = ap.parse_args()
@@ -277,6 +374,8 @@ def main():
         return run_ppo(args, rank, world, dev)
     if args.mode == "physics":
         return run_physics(args, rank, world, dev)
+    if args.pipeline > 1:
+        return run_rollout_pipelined(args, rank, world, dev)
     # env sets rotated so that the working set exceeds L2 (timing rule: inputs larger than L2)
     n_sets = max(3, int(np.ceil(1.3 * L2_BYTES / (n * STATE_BYTES_PER_ENV))))
     # per-rank keys: split(seed, world*n) then sliced, so results do not depend on the GPU count

@@ -23,6 +23,11 @@ timeout 300 python bench.py --steps 200 --warmup 20 --no-cpu-baseline > $o/${tag
 for v in symvilp cholldl symvunroll ancpipe fast1; do
   [ -f $V/liboduck_cuda_$v.so ] && ODUCK_CUDA_LIB=$V/liboduck_cuda_$v.so timeout 300 python bench.py --steps 200 --warmup 20 --no-cpu-baseline > $o/${tag}_bench_n1_$v.json 2> $o/${tag}_bench_n1_$v.err; cut -c1-220 $o/${tag}_bench_n1_$v.json
 done
+# sub-batch pipelining of the rollout step (bench.py --pipeline P: P handles / graphs / streams; fills the 0.73-wave tail of k_step at 4096 envs)
+for P in 2 4; do
+  timeout 300 python bench.py --pipeline $P --steps 200 --warmup 20 > $o/${tag}_bench_n1_pipe$P.json 2> $o/${tag}_bench_n1_pipe$P.err; cut -c1-220 $o/${tag}_bench_n1_pipe$P.json
+done
+[ -f $V/liboduck_cuda_fast1.so ] && ODUCK_CUDA_LIB=$V/liboduck_cuda_fast1.so timeout 300 python bench.py --pipeline 2 --steps 200 --warmup 20 > $o/${tag}_bench_n1_pipe2_fast1.json 2> $o/${tag}_bench_n1_pipe2_fast1.err
 timeout 300 python bench.py --task rough_terrain_backlash --steps 100 --warmup 10 --no-cpu-baseline > $o/${tag}_bench_rough.json 2> $o/${tag}_bench_rough.err; cut -c1-220 $o/${tag}_bench_rough.json
 for v in hfcull hfpairs fast1hf; do
   [ -f $V/liboduck_cuda_$v.so ] && ODUCK_CUDA_LIB=$V/liboduck_cuda_$v.so timeout 300 python bench.py --task rough_terrain_backlash --steps 100 --warmup 10 --no-cpu-baseline > $o/${tag}_bench_rough_$v.json 2> $o/${tag}_bench_rough_$v.err; cut -c1-220 $o/${tag}_bench_rough_$v.json
