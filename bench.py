@@ -298,7 +298,7 @@ def run_ppo(args, rank, world, dev):
     from open_duck_playground_b200 import ppo
     from open_duck_playground_b200.joystick import Joystick
     n_total = 8192 if args.envs_per_gpu == 4096 else args.envs_per_gpu * world
-    cfg = ppo.PPOConfig(num_envs=n_total)
+    cfg = ppo.PPOConfig(num_envs=n_total, rollout_pipeline=args.pipeline)
     tr = ppo.PPOTrainer(Joystick(TASK, device=dev), cfg, rank=rank, world=world)
     for _ in range(max(1, min(args.warmup, 3))):
         tr.training_step()
@@ -319,7 +319,7 @@ def run_ppo(args, rank, world, dev):
     if rank == 0:
         print(json.dumps({"metric": "env-steps/sec (full PPO: rollout + gather + update)", "value": steps * cfg.num_envs * cfg.unroll_length / dt, "unit": "env-steps/s",
                           "n_gpus": world, "steps": steps, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "strong", "dtype": "f32", "data": "synthetic",
-                          "config": {"workload": f"{TASK} full PPO, {cfg.num_envs} envs x unroll {cfg.unroll_length}, 4 epochs x 32 minibatches (BASELINE configs[2])"},
+                          "config": {"workload": f"{TASK} full PPO, {cfg.num_envs} envs x unroll {cfg.unroll_length}, 4 epochs x 32 minibatches (BASELINE configs[2])", "rollout_pipeline": cfg.rollout_pipeline},
                           "split_ms_per_training_step": {k: v / steps for k, v in split.items()}}))
     if world > 1:
         dist.destroy_process_group()
@@ -335,7 +335,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--task", default=TASK, help="scene: flat_terrain_backlash (the metric's config), flat_terrain, rough_terrain_backlash (height-field floor, BASELINE configs[3])")
-    ap.add_argument("--pipeline", type=int, default=1, help="experiment: split the env batch into P sub-batches, one CUDA graph and stream each (rollout mode)")
+    ap.add_argument("--pipeline", type=int, default=1, help="experiment: split the env batch into P sub-batches, one CUDA graph chain and stream each (rollout and ppo modes)")
     ap.add_argument("--mode", default="rollout", choices=["rollout", "ppo", "physics"],
                     help="ppo = BASELINE configs[2]: full PPO training steps (rollout / gather / update split); physics = oduck_physics_substeps(10) alone")
     args = ap.parse_args()

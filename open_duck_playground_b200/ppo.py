@@ -51,6 +51,9 @@ class PPOConfig:
                                     # "sharded": every rank updates on its own env shard, gradients all-reduced per minibatch (Brax's pmean);
                                     # "auto": sharded on CUDA with world > 1, else replicated
     cuda_graph: bool = True         # (torch learner) capture one minibatch update (fwd + bwd + clip + Adam) in a CUDA graph on GPU
+    rollout_pipeline: int = 1       # experiment: the rank's envs as P sub-batches with their own handle, CUDA graphs and
+                                    # stream, so that sub-batch 0 starts unroll step t + 1 under the partial last wave of sub-batch P - 1's
+                                    # step t (8192 envs = 3.46 waves of k_step).  Same transitions as P = 1 (envs are independent, keys sliced)
     learner: str = "auto"           # "device": the fused learner step of include/oduck_ppo.h (tcgen05 GEMMs, fused GAE/loss/Adam kernels);
                                     # "torch": the PyTorch fp32 twin (the checker of the device learner, and the CPU path of the tests);
                                     # "auto": device on CUDA, torch otherwise
@@ -342,8 +345,21 @@ class PPOTrainer:
         self._zeros = {k: torch.zeros(env.observation_size[k][0], device=dev) for k in self.stats}
         self.key = jr.PRNGKey(cfg.seed + 17)
         self.env_steps = 0
-        env.randomize(shard_keys(cfg.seed + 1, world, rank, self.n_local))
-        self.state = env.reset(shard_keys(cfg.seed, world, rank, self.n_local))
+        self.P = max(1, int(cfg.rollout_pipeline))
+        if self.P == 1:
+            self._envs = [env]
+            env.randomize(shard_keys(cfg.seed + 1, world, rank, self.n_local))
+            self.state = env.reset(shard_keys(cfg.seed, world, rank, self.n_local))
+        else:
+            if self.n_local % self.P:
+                raise ValueError("num_envs per rank must be a multiple of rollout_pipeline")
+            m = self.n_local // self.P
+            dr, rk = shard_keys(cfg.seed + 1, world, rank, self.n_local), shard_keys(cfg.seed, world, rank, self.n_local)
+            self._envs = [type(env)(task=env._task, config=env._config, device=env.device, library=env._lib) for _ in range(self.P)]
+            self.state = []
+            for q, e in enumerate(self._envs):
+                e.randomize(dr[q * m:(q + 1) * m])
+                self.state.append(e.reset(rk[q * m:(q + 1) * m]))
         self.timing = {"rollout_ms": 0.0, "gather_ms": 0.0, "update_ms": 0.0}
         self.evaluator = Evaluator(env, cfg) if (rank == 0 and cfg.num_eval_envs > 0) else None
 
@@ -388,6 +404,8 @@ class PPOTrainer:
             mean, std = (self.stats[pk].mean32, self.stats[pk].std) if cfg.normalize_observations else (torch.zeros_like(self.stats[pk].std), torch.ones_like(self.stats[pk].std))
         self.weights.refresh(mean, std)
         keys = self._rollout_keys()
+        if self.P > 1:
+            return self._rollout_pipelined(keys, graphed)
         st = self.state
         if not graphed:
             buf = self._new_buffers()
@@ -424,6 +442,72 @@ class PPOTrainer:
             for g in R["graphs"]:
                 g.replay()
         self.state = st
+        return buf
+
+    def _sub_step(self, buf, t, q, st, keys_t):
+        """_rollout_step for sub-batch q: its env handle, its slice of the rollout buffers."""
+        pk, vk = self.cfg.policy_obs_key, self.cfg.value_obs_key
+        m = self.n_local // self.P
+        sl = slice(q * m, (q + 1) * m)
+        e = self._envs[q]
+        buf["obs_p"][t, sl].copy_(st.obs[pk]); buf["obs_v"][t, sl].copy_(st.obs[vk])
+        act, raw, logp = policy_forward(e, self.weights, keys_t[sl], deterministic=False)
+        st = e.step(st, act)
+        buf["raw"][t, sl].copy_(raw); buf["logp"][t, sl].copy_(logp)
+        buf["reward"][t, sl].copy_(st.reward); buf["done"][t, sl].copy_(st.done); buf["trunc"][t, sl].copy_(st.info["truncation"])
+        if t == self.cfg.unroll_length - 1:
+            buf["obs_p"][t + 1, sl].copy_(st.obs[pk]); buf["obs_v"][t + 1, sl].copy_(st.obs[vk])
+        return st
+
+    def _rollout_pipelined(self, keys: np.ndarray, graphed: bool) -> Dict[str, torch.Tensor]:
+        """rollout() for rollout_pipeline = P > 1: every sub-batch runs its own chain of T (actor forward + env.step) steps; on CUDA
+        each chain is T graphs replayed on the sub-batch's stream, forked from / joined to the caller's stream with events."""
+        T, P, dev = self.cfg.unroll_length, self.P, self.env.device
+        if not graphed:
+            buf = self._new_buffers()
+            for t in range(T):
+                kt = torch.from_numpy(keys[t])
+                for q in range(P):
+                    self.state[q] = self._sub_step(buf, t, q, self.state[q], kt)
+            return buf
+        if self._roll is None:
+            self._roll = {"buf": self._new_buffers(), "keys": torch.empty(T, self.n_local, 2, dtype=torch.int32, device=dev),
+                          "host_keys": torch.empty(T, self.n_local, 2, dtype=torch.int32).pin_memory(), "graphs": None,
+                          "streams": [torch.cuda.Stream(device=dev) for _ in range(P)]}
+        R = self._roll
+        R["host_keys"].copy_(torch.from_numpy(keys))
+        R["keys"].copy_(R["host_keys"], non_blocking=True)
+        buf = R["buf"]
+        if R["graphs"] is None:
+            for t in range(T):                               # first unroll: eager on the caller's stream (warms every kernel up)
+                for q in range(P):
+                    self.state[q] = self._sub_step(buf, t, q, self.state[q], R["keys"][t])
+            torch.cuda.synchronize(dev)
+            graphs = []
+            for q in range(P):
+                pool, chain = torch.cuda.graph_pool_handle(), []
+                for t in range(T):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, pool=pool, stream=R["streams"][q]):
+                        self._sub_step(buf, t, q, self.state[q], R["keys"][t])
+                    chain.append(g)
+                graphs.append(chain)
+            R["graphs"] = graphs
+            torch.cuda.synchronize(dev)
+            return buf
+        main = torch.cuda.current_stream(dev)
+        fork = torch.cuda.Event()
+        fork.record(main)                                    # after the key upload and the previous update
+        for t in range(T):
+            for q in range(P):
+                with torch.cuda.stream(R["streams"][q]):
+                    if t == 0:
+                        R["streams"][q].wait_event(fork)
+                    R["graphs"][q][t].replay()
+        for q in range(P):
+            join = torch.cuda.Event()
+            join.record(R["streams"][q])
+            main.wait_event(join)
         return buf
 
     # ------------------------------------------------------------------ update
@@ -605,7 +689,7 @@ class PPOTrainer:
                     L.minibatch(ro, nm, idx, 0, key, capi.PPO_STAGE_ADAM)
                 else:
                     L.minibatch(ro, nm, idx, 0, key, capi.PPO_ALL)
-        self.env.handle.policy_invalidate()                                                # the actor repacks the new weights on its next forward
+        [e.handle.policy_invalidate() for e in self._envs]                                                # the actor repacks the new weights on its next forward
         self._prefetched_keys = self._rollout_keys()                                       # host work of the next unroll, under the GPU's update
         o = L.losses.tolist()                                                              # host sync: the update is done, `keep` may go
         del keep
@@ -677,7 +761,7 @@ class PPOTrainer:
             ad = params["optimizer"].get("device_adam") if isinstance(params["optimizer"], dict) else None
             if ad is not None:
                 L.view("ADAM_M").copy_(ad["m"].to(self.env.device)); L.view("ADAM_V").copy_(ad["v"].to(self.env.device)); L.step.fill_(int(ad["step"]))
-            self.env.handle.policy_invalidate()
+            [e.handle.policy_invalidate() for e in self._envs]
         else:
             self.opt.load_state_dict(params["optimizer"])
         for k, s in self.stats.items():

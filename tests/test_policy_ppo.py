@@ -110,3 +110,21 @@ def test_evaluator_reports_first_episode_sums(oracle):
     tr.cfg.num_timesteps = 8 * 3 * 2
     tr.train()
     assert m and "eval/episode_reward" in m[-1] and "training/loss" in m[-1] and "eval/avg_episode_length" in m[-1]
+
+
+def test_pipelined_rollout_equals_plain_rollout(oracle):
+    """PPOConfig.rollout_pipeline = P: the rank's envs as P sub-batches with their own handles.  Envs are independent
+    and the keys are sliced, so transitions and the parameters after a training step equal the single-batch trainer's bit for bit."""
+    kw = dict(num_envs=12, unroll_length=3, num_minibatches=2, num_updates_per_batch=1, num_eval_envs=0)
+    plain = ppo.PPOTrainer(Joystick("flat_terrain_backlash", library=oracle), ppo.PPOConfig(**kw))
+    piped = ppo.PPOTrainer(Joystick("flat_terrain_backlash", library=oracle), ppo.PPOConfig(rollout_pipeline=3, **kw))
+    for _ in range(2):
+        a, b = plain.rollout(), piped.rollout()
+        for k in a:
+            assert torch.equal(a[k], b[k]), k
+    torch.manual_seed(5); plain.training_step()                       # the torch learner draws its permutation / entropy noise from the global generator
+    torch.manual_seed(5); piped.training_step()
+    for pa, pb in zip(plain.policy.parameters(), piped.policy.parameters()):
+        assert torch.equal(pa, pb)
+    with pytest.raises(ValueError, match="multiple of rollout_pipeline"):
+        ppo.PPOTrainer(Joystick("flat_terrain_backlash", library=oracle), ppo.PPOConfig(rollout_pipeline=5, **kw))

@@ -27,6 +27,9 @@ done
 for P in 2 4; do
   timeout 300 python bench.py --pipeline $P --steps 200 --warmup 20 > $o/${tag}_bench_n1_pipe$P.json 2> $o/${tag}_bench_n1_pipe$P.err; cut -c1-220 $o/${tag}_bench_n1_pipe$P.json
 done
+for P in 1 2; do
+  timeout 600 python bench.py --mode ppo --pipeline $P --steps 100 --warmup 2 > $o/${tag}_bench_ppo_n1_pipe$P.json 2> $o/${tag}_bench_ppo_n1_pipe$P.err; cut -c1-160 $o/${tag}_bench_ppo_n1_pipe$P.json; grep -o '"split_ms.*' $o/${tag}_bench_ppo_n1_pipe$P.json
+done
 [ -f $V/liboduck_cuda_fast1.so ] && ODUCK_CUDA_LIB=$V/liboduck_cuda_fast1.so timeout 300 python bench.py --pipeline 2 --steps 200 --warmup 20 > $o/${tag}_bench_n1_pipe2_fast1.json 2> $o/${tag}_bench_n1_pipe2_fast1.err
 timeout 300 python bench.py --task rough_terrain_backlash --steps 100 --warmup 10 --no-cpu-baseline > $o/${tag}_bench_rough.json 2> $o/${tag}_bench_rough.err; cut -c1-220 $o/${tag}_bench_rough.json
 for v in hfcull hfpairs fast1hf; do
