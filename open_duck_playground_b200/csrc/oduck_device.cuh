@@ -436,19 +436,20 @@ static __device__ __noinline__ float chol_rev_back(const DevModel& m, const floa
     const unsigned char* al = m.anc[lane];
     const int ri = TRI(lane);
 #ifdef ODUCK_ANC_PIPE
-    // same arithmetic, software-pipelined: the ancestor index and the factor entry of level lev + 1 are fetched while level lev
-    // is in flight, so the serial chain of a level is SHFL -> FFMA instead of LDS.U8 -> SHFL -> LDS -> FFMA
+    // same arithmetic, software-pipelined: the ancestor index is fetched two levels ahead and the factor entry one level ahead,
+    // so no instruction of a level waits for a load issued in that level (in-order issue) and the serial chain of a level is
+    // SHFL -> FFMA instead of LDS.U8 -> SHFL -> LDS -> FFMA
     (void)al;
     int j = dep > 0 ? m.anc_t[0][lane] : lane;
+    int j1 = dep > 1 ? m.anc_t[1][lane] : lane;
     float l = dep > 0 ? L[ri + j] : 0.f;
     for (int lev = 0; lev <= m.max_dof_depth; ++lev) {
-      const bool nx = dep > lev + 1;
-      const int jn = nx ? m.anc_t[lev + 1][lane] : lane;
-      const float ln = nx ? L[ri + jn] : 0.f;
+      const int j2 = dep > lev + 2 ? m.anc_t[lev + 2][lane] : lane;
+      const float ln = dep > lev + 1 ? L[ri + j1] : 0.f;
       if (dep == lev) y *= invd;
       const float xj = __shfl_sync(FULLMASK, y, j);
       if (dep > lev) y -= l * xj;
-      j = jn; l = ln;
+      j = j1; j1 = j2; l = ln;
     }
 #else
     for (int lev = 0; lev <= m.max_dof_depth; ++lev) {

@@ -581,19 +581,20 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
       const unsigned char* al = m.anc[lane];
       float* Hi = s.H + TRI(lane);
 #ifdef ODUCK_ANC_PIPE
-      // same arithmetic, software-pipelined: index and motion axis of level lev + 1 are fetched while level lev is summed
+      // same arithmetic, software-pipelined: the ancestor index is fetched two levels ahead, the motion axis and the H entry's
+      // address one level ahead, so a level's sum does not wait for a load issued in that level
       (void)al;
       int j = 0 < dep ? m.anc_t[0][lane] : lane;
+      int j1 = 1 < dep ? m.anc_t[1][lane] : lane;
       float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
       if (0 <= dep) { c0 = lds4(&s.cdof[j][0]); c1 = lds4(&s.cdof[j][4]); }
 #pragma unroll 1
       for (int lev = 0; lev <= m.max_dof_depth; ++lev) {
-        const bool nx = lev + 1 <= dep;
-        const int jn = lev + 1 < dep ? m.anc_t[lev + 1][lane] : lane;
+        const int j2 = lev + 2 < dep ? m.anc_t[lev + 2][lane] : lane;
         float4 n0 = c0, n1 = c1;
-        if (nx) { n0 = lds4(&s.cdof[jn][0]); n1 = lds4(&s.cdof[jn][4]); }
+        if (lev + 1 <= dep) { n0 = lds4(&s.cdof[j1][0]); n1 = lds4(&s.cdof[j1][4]); }
         if (lev <= dep) Hi[j] += z.a0 * c0.x + z.a1 * c0.y + z.a2 * c0.z + z.l0 * c0.w + z.l1 * c1.x + z.l2 * c1.y;
-        j = jn; c0 = n0; c1 = n1;
+        j = j1; j1 = j2; c0 = n0; c1 = n1;
       }
 #else
 #pragma unroll 1
