@@ -14,6 +14,8 @@
  *   oduck_physics_substeps  mjx_env.step(model, data, ctrl, n_substeps)    open_duck_mini_v2/joystick.py:420
  *   oduck_forward           mjx_env.init's mjx.forward                     open_duck_mini_v2/joystick.py:258
  *   oduck_policy_forward    Brax make_ppo_networks policy apply            common/runner.py:94-100, common/export_onnx.py:64-72
+ *   oduck_rollout_step      one step of Brax generate_unroll (policy +     common/runner.py:104-118
+ *   oduck_set_rollout_sink    env.step + Transition store) of ppo.train
  *   oduck_get_buffer        attribute access on mjx.Data / State / info    open_duck_mini_v2/joystick.py:278-321
  *   oduck_set_state         state.data.replace(qpos=..., qvel=...)         open_duck_mini_v2/joystick.py:399
  *
@@ -39,7 +41,7 @@
 extern "C" {
 #endif
 
-#define ODUCK_ABI_VERSION 8
+#define ODUCK_ABI_VERSION 9
 
 #define ODUCK_MAX_BODY 20
 #define ODUCK_MAX_JNT 28
@@ -248,6 +250,27 @@ typedef struct OduckPolicyWeights {
                                   * the device learner (oduck_ppo_packed_weights); NULL = the library packs w[] itself and caches it */
 } OduckPolicyWeights;
 
+/* Rollout sink (A17: the PPO unroll of common/runner.py:104-118 -> Brax acting.generate_unroll stores a Transition per step).
+ * Caller-owned buffers in the library's memory space, time-major like Brax's stacked Transition; when a sink is attached,
+ * oduck_rollout_step makes the KERNELS write each step's transition straight into slot t (no pack / copy pass): the actor's
+ * head writes raw_action / log_prob, the step kernel writes reward / done / truncation of slot t and the NEW observations into
+ * slot t + 1 (after auto-reset: the first observation of the next episode, as Brax's AutoResetWrapper returns it).  Slot 0 of
+ * the observations is filled from the handle's current observations when t == 0.  `num_envs` / `env_offset` place the handle's
+ * envs inside wider buffers (several handles of one rank, or a rank's slice of the all-gather buffer of SURVEY.md 8e). */
+typedef struct OduckRolloutSink {
+  int32_t unroll;                /* T */
+  int32_t num_envs;              /* env count of the buffers (>= env_offset + the handle's envs) */
+  int32_t env_offset;            /* first env of this handle inside the buffers */
+  int32_t policy_dim, value_dim; /* row widths: Joystick 101 / 212, Standing 85 / 153 */
+  float* obs_policy;             /* [T + 1][num_envs][policy_dim]  <- obs["state"] */
+  float* obs_value;              /* [T + 1][num_envs][value_dim]   <- obs["privileged_state"] */
+  float* raw_action;             /* [T][num_envs][nu]  pre-tanh sample */
+  float* log_prob;               /* [T][num_envs] */
+  float* reward;                 /* [T][num_envs] */
+  float* done;                   /* [T][num_envs] */
+  float* truncation;             /* [T][num_envs] */
+} OduckRolloutSink;
+
 typedef enum {
   ODUCK_BUF_QPOS = 0,        /* f32 [N, nq]  */
   ODUCK_BUF_QVEL,            /* f32 [N, nv]  */
@@ -324,6 +347,11 @@ int oduck_policy_forward(OduckHandle* h, const OduckPolicyWeights* w, const floa
 /* The library caches a tensor-core repack of the weights keyed by w->w[0]; call this after the weights behind the same
  * pointers changed in place (the device learner of oduck_ppo.h updates them every SGD step). */
 int oduck_policy_invalidate(OduckHandle* h);
+/* Attach (or with NULL detach) the rollout buffers.  The struct is copied; the buffers must outlive the attachment. */
+int oduck_set_rollout_sink(OduckHandle* h, const OduckRolloutSink* sink);
+/* Step t (0 <= t < sink.unroll) of the unroll: sample an action from the handle's own obs["state"] with `w` / `keys`
+ * (u32 [N,2]), step the envs with it, store the transition in the sink.  Same kernels as oduck_policy_forward + oduck_step. */
+int oduck_rollout_step(OduckHandle* h, const OduckPolicyWeights* w, const uint32_t* keys, int t, void* stream);
 /* Zero-copy view.  shape[4] (unused dims = 0), strides in ELEMENTS. */
 int oduck_get_buffer(OduckHandle* h, int id, void** ptr, int64_t* shape, int64_t* strides, int* dtype);
 /* Number of kernels this library has launched on the handle since create (bench `gpu_launches`). */

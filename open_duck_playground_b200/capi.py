@@ -14,7 +14,7 @@ import numpy as np
 
 from .mjcf import CompiledModel
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 MAX_BODY, MAX_JNT, MAX_NQ, MAX_NV, MAX_NU, MAX_SITE, MAX_VERT, MAX_FACE, NFEET, NCMD = 20, 28, 36, 32, 16, 8, 32, 64, 2, 7
 OBS_STATE, OBS_PRIV, NMETRIC, REF_DIM, POLY_DEG, MAX_CON = 101, 212, 8, 40, 16, 12
 
@@ -89,6 +89,15 @@ class OduckPolicyWeights(C.Structure):
     _fields_ = [
         ("obs_dim", i32), ("hidden", i32 * 3), ("out_dim", i32),
         ("obs_mean", C.c_void_p), ("obs_std", C.c_void_p), ("w", C.c_void_p * 4), ("b", C.c_void_p * 4), ("packed", C.c_void_p * 4),
+    ]
+
+
+class OduckRolloutSink(C.Structure):
+    """include/oduck.h: caller-owned rollout buffers the kernels of oduck_rollout_step write into."""
+    _fields_ = [
+        ("unroll", i32), ("num_envs", i32), ("env_offset", i32), ("policy_dim", i32), ("value_dim", i32),
+        ("obs_policy", C.c_void_p), ("obs_value", C.c_void_p), ("raw_action", C.c_void_p), ("log_prob", C.c_void_p),
+        ("reward", C.c_void_p), ("done", C.c_void_p), ("truncation", C.c_void_p),
     ]
 
 
@@ -190,6 +199,8 @@ class Library:
         L.oduck_launch_count.argtypes = [vp]
         L.oduck_launch_count.restype = C.c_int64
         L.oduck_policy_invalidate.argtypes = [vp]
+        L.oduck_set_rollout_sink.argtypes = [vp, p(OduckRolloutSink)]
+        L.oduck_rollout_step.argtypes = [vp, p(OduckPolicyWeights), vp, C.c_int, vp]
         self.has_ppo = hasattr(L, "oduck_ppo_create")            # the device learner (include/oduck_ppo.h) exists in the CUDA library only
         if self.has_ppo:
             L.oduck_ppo_create.argtypes = [p(OduckPpoConfig), C.c_int, p(vp)]
@@ -257,6 +268,12 @@ class Handle:
                        raw_action: int, log_prob: int, stream: int = 0):
         self.L.check(self.L.lib.oduck_policy_forward(self.h, C.byref(w), obs or None, keys or None, int(deterministic),
                                                      action or None, raw_action or None, log_prob or None, stream))
+
+    def set_rollout_sink(self, sink: Optional[OduckRolloutSink]) -> None:
+        self.L.check(self.L.lib.oduck_set_rollout_sink(self.h, C.byref(sink) if sink is not None else None))
+
+    def rollout_step(self, w: OduckPolicyWeights, keys: int, t: int, stream: int = 0) -> None:
+        self.L.check(self.L.lib.oduck_rollout_step(self.h, C.byref(w), keys, int(t), stream))
 
     def launch_count(self) -> int:
         return int(self.L.lib.oduck_launch_count(self.h))

@@ -128,9 +128,6 @@ static int build_dev_model(const OduckModel& M, DevModel& D, std::string& err) {
     D.d_depth[d] = cnt;
     D.max_dof_depth = std::max(D.max_dof_depth, cnt);
     for (int t = 0; t < cnt; t++) D.anc[d][t] = (unsigned char)tmp[cnt - 1 - t];   // root first
-#ifdef ODUCK_ANC_PIPE
-    for (int t = 0; t < cnt; t++) D.anc_t[t][d] = D.anc[d][t];
-#endif
   }
   for (int a = 0, p = 0; a < 32 && p < 512; a++)
     for (int b = 0; b <= a && p < 512; b++, p++) D.pair_ab[p] = (unsigned short)((a << 8) | b);

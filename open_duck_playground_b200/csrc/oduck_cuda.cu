@@ -459,6 +459,25 @@ __global__ void __launch_bounds__(WPB * 32, CTAS_PER_SM) k_step(Params p) {
       store_phys(m, s, L, lane, ph);
     }
     __syncwarp();
+    if (p.sk_obs_p) {
+      // A17: this step's Transition goes straight into the caller's rollout buffers (oduck_rollout_step): reward / done /
+      // truncation of slot t, the observations the NEXT action is computed from (after auto-reset) into slot t + 1.  The rows
+      // were written by this warp just above (L1 / L2 hits); the policy's raw action / log-prob were written by the actor's head.
+      if (lane == 0) { p.sk_reward[env] = reward; p.sk_done[env] = done_f; p.sk_trunc[env] = trunc ? 1.f - d : 0.f; }
+      float* so = p.sk_obs_p + (size_t)env * p.sk_dp;
+      for (int i = lane; i < p.sk_dp; i += 32) so[i] = ost[i];
+      float* sv = p.sk_obs_v + (size_t)env * p.sk_dv;
+      for (int i = lane; i < p.sk_dv; i += 32) sv[i] = opr[i];
+    }
+  }
+}
+
+// slot 0 of the sink's observations <- the handle's current observations (first step of an unroll)
+__global__ void k_sink_obs0(const float* __restrict__ ost, const float* __restrict__ opr, float* __restrict__ dp_, float* __restrict__ dv_, int N, int dp, int dv) {
+  const int tot = N * (dp + dv);
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < tot; idx += gridDim.x * blockDim.x) {
+    if (idx < N * dp) { const int e = idx / dp, k = idx - e * dp; dp_[idx] = ost[(size_t)e * ODUCK_OBS_STATE + k]; }
+    else { const int r = idx - N * dp, e = r / dv, k = r - e * dv; dv_[r] = opr[(size_t)e * ODUCK_OBS_PRIV + k]; }
   }
 }
 
@@ -560,7 +579,7 @@ int oduck_destroy(OduckHandle* h) {
   if (!h) return ODUCK_OK;
   cudaSetDevice(h->device);
   void* ptrs[] = {h->dmodel, h->dcfg, h->poly, h->phys, h->dr, h->out, h->info, h->obs_state, h->obs_priv, h->reward, h->done, h->trunc,
-                  h->metrics, h->first_phys, h->first_obs_state, h->first_obs_priv, h->dbg, h->policy_scratch, h->dff, h->ffscratch, h->dhf, h->hfdata, h->hfscratch, h->drlib};
+                  h->metrics, h->first_phys, h->first_obs_state, h->first_obs_priv, h->dbg, h->policy_scratch, h->dff, h->ffscratch, h->dhf, h->hfdata, h->hfscratch, h->drlib, h->act_buf};
   for (void* q : ptrs) if (q) cudaFree(q);
   delete h;
   return ODUCK_OK;
@@ -639,6 +658,7 @@ int oduck_create(const OduckModel* model, const OduckEnvConfig* cfg, int num_env
   ALLOC(h->phys, N * PHYS_STRIDE); ALLOC(h->dr, N * DR_STRIDE); ALLOC(h->out, N * OUT_STRIDE); ALLOC(h->info, N * INFO_STRIDE);
   ALLOC(h->obs_state, N * ODUCK_OBS_STATE); ALLOC(h->obs_priv, N * ODUCK_OBS_PRIV);
   ALLOC(h->reward, N); ALLOC(h->done, N); ALLOC(h->trunc, N); ALLOC(h->metrics, N * ODUCK_NMETRIC);
+  ALLOC(h->act_buf, N * ODUCK_MAX_NU);
   ALLOC(h->first_phys, N * PHYS_STRIDE); ALLOC(h->first_obs_state, N * ODUCK_OBS_STATE); ALLOC(h->first_obs_priv, N * ODUCK_OBS_PRIV);
 #undef ALLOC
   // nominal state and nominal (un-randomised) per-env model
@@ -697,6 +717,44 @@ int oduck_step(OduckHandle* h, const float* action, void* stream) {
   if (!h || !action) return fail(ODUCK_ERR_ARG, "oduck_step: bad argument");
   Params p = make_params(h);
   p.action = action;
+  if (h->drlib) return h->dhf ? launch(h, k_step<true, true>, p, stream) : launch(h, k_step<false, true>, p, stream);
+  return h->dhf ? launch(h, k_step<true, false>, p, stream) : launch(h, k_step<false, false>, p, stream);
+}
+int oduck_set_rollout_sink(OduckHandle* h, const OduckRolloutSink* sink) {
+  if (!h) return fail(ODUCK_ERR_ARG, "oduck_set_rollout_sink: bad argument");
+  if (!sink) { memset(&h->sink, 0, sizeof(h->sink)); return ODUCK_OK; }
+  const int dp = h->hcfg.task == ODUCK_TASK_STANDING ? 85 : ODUCK_OBS_STATE, dv = h->hcfg.task == ODUCK_TASK_STANDING ? 153 : ODUCK_OBS_PRIV;
+  if (sink->unroll < 1 || sink->env_offset < 0 || sink->env_offset + h->n > sink->num_envs) return fail(ODUCK_ERR_ARG, "oduck_set_rollout_sink: the handle's envs do not fit into the buffers");
+  if (sink->policy_dim != dp || sink->value_dim != dv) return fail(ODUCK_ERR_ARG, "oduck_set_rollout_sink: obs row widths must be those of the task (Joystick 101 / 212, Standing 85 / 153)");
+  if (!sink->obs_policy || !sink->obs_value || !sink->raw_action || !sink->log_prob || !sink->reward || !sink->done || !sink->truncation)
+    return fail(ODUCK_ERR_ARG, "oduck_set_rollout_sink: null buffer");
+  h->sink = *sink;
+  return ODUCK_OK;
+}
+// oduck_step with the transition of unroll step t stored in the attached sink (called by oduck_rollout_step, oduck_policy.cu)
+int oduck_step_into_sink(OduckHandle* h, const float* action, int t, void* stream) {
+  const OduckRolloutSink& k = h->sink;
+  if (!k.obs_policy || t < 0 || t >= k.unroll) return fail(ODUCK_ERR_ARG, "oduck_rollout_step: no sink attached or t outside the unroll");
+  Params p = make_params(h);
+  p.action = action;
+  const size_t row = (size_t)t * k.num_envs + k.env_offset, next = row + k.num_envs;
+  p.sk_obs_p = k.obs_policy + next * k.policy_dim; p.sk_obs_v = k.obs_value + next * k.value_dim;
+  p.sk_reward = k.reward + row; p.sk_done = k.done + row; p.sk_trunc = k.truncation + row;
+  p.sk_dp = k.policy_dim; p.sk_dv = k.value_dim;
+  if (t == 0) {
+    CUDA_TRY(cudaSetDevice(h->device));
+#ifndef ODUCK_WARP_EMU
+    k_sink_obs0<<<148, 256, 0, (cudaStream_t)stream>>>(h->obs_state, h->obs_priv, k.obs_policy + (size_t)k.env_offset * k.policy_dim,
+                                                       k.obs_value + (size_t)k.env_offset * k.value_dim, h->n, k.policy_dim, k.value_dim);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+#else   // tests/emu: device memory is host memory
+    for (int e = 0; e < h->n; e++) {
+      for (int c = 0; c < k.policy_dim; c++) k.obs_policy[(size_t)(k.env_offset + e) * k.policy_dim + c] = h->obs_state[(size_t)e * ODUCK_OBS_STATE + c];
+      for (int c = 0; c < k.value_dim; c++) k.obs_value[(size_t)(k.env_offset + e) * k.value_dim + c] = h->obs_priv[(size_t)e * ODUCK_OBS_PRIV + c];
+    }
+#endif
+  }
   if (h->drlib) return h->dhf ? launch(h, k_step<true, true>, p, stream) : launch(h, k_step<false, true>, p, stream);
   return h->dhf ? launch(h, k_step<true, false>, p, stream) : launch(h, k_step<false, false>, p, stream);
 }

@@ -85,11 +85,6 @@ struct alignas(16) DevModel {   // 16-byte multiple: staged into shared memory w
   int scan_ok, scan_rounds, n_branch;
   int b_next[NLANE];
   int br_nchild[4], br_child[4][4], br_chain[4];
-#ifdef ODUCK_ANC_PIPE
-  // variant for an A/B run (tools/variants.py): anc transposed, anc_t[l][k] = anc[k][l].  A warp that reads "my ancestor at depth
-  // l" touches 32 consecutive bytes (one wavefront) instead of 32 rows 32 bytes apart (8 lanes per bank)
-  unsigned char anc_t[NLANE][NLANE];
-#endif
 };
 
 // per-warp shared memory
@@ -435,30 +430,12 @@ static __device__ __noinline__ float chol_rev_back(const DevModel& m, const floa
     const float invd = lane < n ? 1.f / L[TRI(lane) + lane] : 0.f;
     const unsigned char* al = m.anc[lane];
     const int ri = TRI(lane);
-#ifdef ODUCK_ANC_PIPE
-    // same arithmetic, software-pipelined: the ancestor index is fetched two levels ahead and the factor entry one level ahead,
-    // so no instruction of a level waits for a load issued in that level (in-order issue) and the serial chain of a level is
-    // SHFL -> FFMA instead of LDS.U8 -> SHFL -> LDS -> FFMA
-    (void)al;
-    int j = dep > 0 ? m.anc_t[0][lane] : lane;
-    int j1 = dep > 1 ? m.anc_t[1][lane] : lane;
-    float l = dep > 0 ? L[ri + j] : 0.f;
-    for (int lev = 0; lev <= m.max_dof_depth; ++lev) {
-      const int j2 = dep > lev + 2 ? m.anc_t[lev + 2][lane] : lane;
-      const float ln = dep > lev + 1 ? L[ri + j1] : 0.f;
-      if (dep == lev) y *= invd;
-      const float xj = __shfl_sync(FULLMASK, y, j);
-      if (dep > lev) y -= l * xj;
-      j = j1; j1 = j2; l = ln;
-    }
-#else
     for (int lev = 0; lev <= m.max_dof_depth; ++lev) {
       if (dep == lev) y *= invd;
       const int j = dep > lev ? al[lev] : lane;
       const float xj = __shfl_sync(FULLMASK, y, j);
       if (dep > lev) y -= L[ri + j] * xj;
     }
-#endif
     return y;
   }
   for (int j = 0; j < n; ++j) {
@@ -471,15 +448,14 @@ static __device__ __noinline__ float chol_rev_back(const DevModel& m, const floa
 // y = A x for the packed symmetric matrix; one element per lane.  x is handed to all lanes through a 32-float shared-memory
 // row read back as float4 broadcasts (8 loads instead of 30 shuffles).
 static __device__ __noinline__ float symv(const float* A, int n, int lane, float x, float* xbuf) {
-  float acc = 0.f;
   const int ri = TRI(lane);
   __syncwarp();
   xbuf[lane] = lane < n ? x : 0.f;
   __syncwarp();
-#if defined(ODUCK_SYMV_UNROLL)
-  // variant for an A/B run (tools/variants.py): the column loop fully unrolled and branch-free on four independent FMA chains.
-  // j is a compile-time constant, so TRI(j) and both address forms fold into LDS immediates (the rolled loop spends ~14 issue
-  // slots per element on index arithmetic and divergence bookkeeping for the j < n test).  No per-element bound test: columns
+  // The column loop is fully unrolled and branch-free on four independent FMA chains: j is a compile-time constant, so TRI(j)
+  // and both address forms fold into LDS immediates (a rolled loop spends ~14 issue slots per element on index arithmetic and
+  // divergence bookkeeping for the j < n test: measured on B200 at 4096 envs, k_step 0.666 -> 0.621 ms, profiles/r02a_*; a
+  // rolled four-chain loop gained nothing, 0.667 ms).  No per-element bound test: columns
   // n .. 4 ceil(n / 4) - 1 multiply x = 0 (xbuf is zero-padded) with the zero padding rows of A (load_env clears all 528
   // floats and only ancestor pairs are rewritten), both addresses stay inside the 528-float triangle for every lane.
   float acc4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -497,37 +473,7 @@ static __device__ __noinline__ float symv(const float* A, int n, int lane, float
       acc4[e] = fmaf(*pj, xs[e], acc4[e]);
     }
   }
-  acc = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
-#elif defined(ODUCK_SYMV_ILP)
-  // variant for an A/B run (tools/variants.py): four independent FMA chains instead of one (changes the summation order)
-  float acc4[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int j4 = 0; 4 * j4 < n; ++j4) {
-    const float4 xv = lds4(xbuf + 4 * j4);
-    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int j = 4 * j4 + e;
-      if (j < n) {
-        const int idx = (j <= lane) ? ri + j : TRI(j) + lane;
-        acc4[e] = fmaf(A[idx], xs[e], acc4[e]);
-      }
-    }
-  }
-  acc = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
-#else
-  for (int j4 = 0; 4 * j4 < n; ++j4) {
-    const float4 xv = lds4(xbuf + 4 * j4);
-    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int j = 4 * j4 + e;
-      if (j < n) {
-        const int idx = (j <= lane) ? ri + j : TRI(j) + lane;
-        acc = fmaf(A[idx], xs[e], acc);
-      }
-    }
-  }
-#endif
+  const float acc = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
   __syncwarp();
   return lane < n ? acc : 0.f;
 }

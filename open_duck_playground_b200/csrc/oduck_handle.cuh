@@ -20,6 +20,10 @@ struct Params {
   const DevHF* hfmodel;    // height-field floor (HF kernel instantiations only); last, so that the flat kernels' argument layout is unchanged
   float* hfscratch;        // per env: HF_SCRATCH floats of contact candidates
   const DevRewardLib* rlib;   // reward-library parameters (RL kernel instantiations only)
+  // rollout sink (oduck_rollout_step): rows of THIS step, already offset to the handle's first env; null = no sink
+  float *sk_obs_p, *sk_obs_v;      // slot t + 1, row widths sk_dp / sk_dv
+  float *sk_reward, *sk_done, *sk_trunc;   // slot t
+  int sk_dp, sk_dv;
 };
 
 struct OduckHandle {
@@ -43,5 +47,7 @@ struct OduckHandle {
   float* policy_scratch;          // hidden activations of the actor MLP (tensor-core path)
   size_t policy_scratch_floats;
   const float* policy_packed_for;  // w[0] pointer the packed weight copy was made from
+  OduckRolloutSink sink;          // attached rollout buffers (sink.obs_policy == null: none)
+  float* act_buf;                 // [N, nu] squashed actions between the actor's head and k_step inside oduck_rollout_step
 };
 

@@ -580,23 +580,6 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
       const int dep = lane < nv ? m.d_depth[lane] : -1;
       const unsigned char* al = m.anc[lane];
       float* Hi = s.H + TRI(lane);
-#ifdef ODUCK_ANC_PIPE
-      // same arithmetic, software-pipelined: the ancestor index is fetched two levels ahead, the motion axis and the H entry's
-      // address one level ahead, so a level's sum does not wait for a load issued in that level
-      (void)al;
-      int j = 0 < dep ? m.anc_t[0][lane] : lane;
-      int j1 = 1 < dep ? m.anc_t[1][lane] : lane;
-      float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
-      if (0 <= dep) { c0 = lds4(&s.cdof[j][0]); c1 = lds4(&s.cdof[j][4]); }
-#pragma unroll 1
-      for (int lev = 0; lev <= m.max_dof_depth; ++lev) {
-        const int j2 = lev + 2 < dep ? m.anc_t[lev + 2][lane] : lane;
-        float4 n0 = c0, n1 = c1;
-        if (lev + 1 <= dep) { n0 = lds4(&s.cdof[j1][0]); n1 = lds4(&s.cdof[j1][4]); }
-        if (lev <= dep) Hi[j] += z.a0 * c0.x + z.a1 * c0.y + z.a2 * c0.z + z.l0 * c0.w + z.l1 * c1.x + z.l2 * c1.y;
-        j = j1; j1 = j2; c0 = n0; c1 = n1;
-      }
-#else
 #pragma unroll 1
       for (int lev = 0; lev <= m.max_dof_depth; ++lev) {
         if (lev <= dep) {
@@ -605,7 +588,6 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
           Hi[j] += z.a0 * c0.x + z.a1 * c0.y + z.a2 * c0.z + z.l0 * c0.w + z.l1 * c1.x + z.l2 * c1.y;
         }
       }
-#endif
     }
     if (FF && ffact) {
       // foot-foot rows couple the two legs: dense update (every i >= j), dense factorisation below

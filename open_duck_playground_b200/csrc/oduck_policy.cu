@@ -292,3 +292,18 @@ extern "C" int oduck_policy_forward(OduckHandle* h, const OduckPolicyWeights* w,
   h->launches += 5;
   return ODUCK_OK;
 }
+
+// A17: one step of the PPO unroll (common/runner.py:104-118 -> Brax generate_unroll): sample from the handle's own obs["state"],
+// step, store the Transition in the attached sink.  The actor's head writes raw action / log-prob into slot t, k_step the rest.
+extern "C" int oduck_step_into_sink(OduckHandle* h, const float* action, int t, void* stream);
+extern "C" int oduck_rollout_step(OduckHandle* h, const OduckPolicyWeights* w, const uint32_t* keys, int t, void* stream) {
+  if (!h || !w || !keys) return oduck_fail(ODUCK_ERR_ARG, "oduck_rollout_step: bad argument");
+  const OduckRolloutSink& k = h->sink;
+  if (!k.obs_policy || t < 0 || t >= k.unroll) return oduck_fail(ODUCK_ERR_ARG, "oduck_rollout_step: no sink attached or t outside the unroll");
+  if (w->obs_dim != k.policy_dim) return oduck_fail(ODUCK_ERR_ARG, "oduck_rollout_step: the policy's input width is not the sink's policy_dim");
+  const int nu = w->out_dim / 2;
+  const size_t row = (size_t)t * k.num_envs + k.env_offset;
+  int rc = oduck_policy_forward(h, w, nullptr, keys, 0, h->act_buf, k.raw_action + row * nu, k.log_prob + row, stream);
+  if (rc) return rc;
+  return oduck_step_into_sink(h, h->act_buf, t, stream);
+}

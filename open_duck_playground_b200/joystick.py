@@ -118,6 +118,18 @@ class Joystick:
         if num_envs is not None:
             self._create(int(num_envs))
 
+    def spawn(self, num_envs: Optional[int] = None) -> "Joystick":
+        """A second env of the same class over the SAME compiled model, config, scene path, library, device and auto-reset
+        setting (its own library handle and state).  The evaluator's envs and the rollout's sub-batch envs are made this way, so
+        an env built from a user MJCF (``xml_path=``) is evaluated and trained on that model, not on the shipped blob."""
+        e = type(self).__new__(type(self))
+        e.__dict__.update({k: v for k, v in self.__dict__.items() if k not in ("_handle", "_views", "_keep", "_live")})
+        e._config = copy.deepcopy(self._config)
+        e._handle, e._views = None, {}
+        if num_envs is not None:
+            e._create(int(num_envs))
+        return e
+
     # ------------------------------------------------------------------ reference accessors (base.py:277-291 + MjxEnv)
     @property
     def xml_path(self) -> str:

@@ -10,6 +10,7 @@ then a replicated (bit-identical) update.
 """
 from __future__ import annotations
 
+import copy
 import ctypes as C
 import math
 from dataclasses import dataclass, field
@@ -54,6 +55,8 @@ class PPOConfig:
     rollout_pipeline: int = 1       # experiment: the rank's envs as P sub-batches with their own handle, CUDA graphs and
                                     # stream, so that sub-batch 0 starts unroll step t + 1 under the partial last wave of sub-batch P - 1's
                                     # step t (8192 envs = 3.46 waves of k_step).  Same transitions as P = 1 (envs are independent, keys sliced)
+    kernel_rollout_writes: bool = True   # the step / actor kernels store each Transition in the rollout buffers themselves
+                                    # (oduck_rollout_step); False = the 7 torch copies per step of round 1 (kept as the checker)
     learner: str = "auto"           # "device": the fused learner step of include/oduck_ppo.h (tcgen05 GEMMs, fused GAE/loss/Adam kernels);
                                     # "torch": the PyTorch fp32 twin (the checker of the device learner, and the CPU path of the tests);
                                     # "auto": device on CUDA, torch otherwise
@@ -121,16 +124,27 @@ class PolicyWeights:
         for i in range(3):
             self.struct.hidden[i] = hs[i]
         self.struct.out_dim = hs[3]
+        self.version = 0                  # bumped by every refresh(); policy_forward() invalidates a handle's repack cache when it changes
+        self.w = self.b = None
         self.refresh(torch.zeros(obs_dim, device=device), torch.ones(obs_dim, device=device))
 
     @torch.no_grad()
     def refresh(self, mean: torch.Tensor, std: torch.Tensor) -> None:
         self.mean, self.std = mean.float().contiguous(), std.float().contiguous()
+        self.version += 1
         if self.external is not None:
             self.w, self.b = [w for w, _ in self.external], [b for _, b in self.external]
-        else:
+        elif self.w is None:
             self.w = [l.weight.detach().t().contiguous() for l in self.policy.layers]     # [in][out]
-            self.b = [l.bias.detach().contiguous() for l in self.policy.layers]
+            self.b = [l.bias.detach().clone().contiguous() for l in self.policy.layers]
+        else:
+            # persistent buffers rewritten in place: the addresses in the struct (and in any captured CUDA graph) stay valid, and
+            # the library's repack cache -- keyed on the w[0] address -- is invalidated through the version tag, never by the
+            # accident of the caching allocator handing out a new address
+            for dst, l in zip(self.w, self.policy.layers):
+                dst.copy_(l.weight.detach().t())
+            for dst, l in zip(self.b, self.policy.layers):
+                dst.copy_(l.bias.detach())
         self.struct.obs_mean, self.struct.obs_std = self.mean.data_ptr(), self.std.data_ptr()
         for i in range(4):
             self.struct.w[i], self.struct.b[i] = self.w[i].data_ptr(), self.b[i].data_ptr()
@@ -146,8 +160,50 @@ def policy_forward(env, weights: PolicyWeights, keys: Optional[torch.Tensor], de
     logp = torch.empty(n, device=dev)
     kp = 0 if keys is None else env._ptr(keys, torch.int32, (n, 2))
     op = 0 if obs is None else env._ptr(obs, torch.float32, (n, weights.struct.obs_dim))
+    if obs is None and weights.struct.obs_dim > env.observation_size["state"][0]:
+        raise ValueError(f"policy reads {weights.struct.obs_dim} features but the handle's own obs['state'] records hold "
+                         f"{env.observation_size['state'][0]}: pass obs= explicitly (e.g. state.obs['privileged_state'])")
+    tag = (id(weights), weights.version)
+    if getattr(env, "_policy_tag", None) != tag:             # weights behind the same addresses changed (or another weight set): drop
+        env.handle.policy_invalidate()                       # this handle's cached tensor-core repack (rarely used handles included)
+        env._policy_tag = tag
     env.handle.policy_forward(weights.struct, op, kp, deterministic, act.data_ptr(), raw.data_ptr(), logp.data_ptr(), env._stream())
     return act, raw, logp
+
+
+def attach_rollout_sink(env, buf: Optional[Dict[str, torch.Tensor]], env_offset: int = 0) -> None:
+    """Point the env's kernels at rollout buffers ``buf`` ([T(+1), n, ...], as made by ``PPOTrainer._new_buffers``): from now on
+    ``rollout_step`` stores every Transition there itself (include/oduck.h OduckRolloutSink).  ``None`` detaches."""
+    if buf is None:
+        env.handle.set_rollout_sink(None)
+        env._sink_keep = None
+        return
+    T, n = buf["reward"].shape
+    sk = capi.OduckRolloutSink()
+    sk.unroll, sk.num_envs, sk.env_offset = int(T), int(n), int(env_offset)
+    sk.policy_dim, sk.value_dim = int(buf["obs_p"].shape[-1]), int(buf["obs_v"].shape[-1])
+    for field, key in (("obs_policy", "obs_p"), ("obs_value", "obs_v"), ("raw_action", "raw"), ("log_prob", "logp"), ("reward", "reward"),
+                       ("done", "done"), ("truncation", "trunc")):
+        t = buf[key]
+        if not t.is_contiguous() or t.dtype != torch.float32 or t.device != env.device:
+            raise ValueError(f"rollout buffer {key} must be a contiguous float32 tensor on {env.device}")
+        setattr(sk, field, t.data_ptr())
+    env.handle.set_rollout_sink(sk)
+    env._sink_keep = (sk, buf)               # the library holds raw pointers: keep the tensors alive with the env
+
+
+def rollout_step(env, weights: PolicyWeights, keys: torch.Tensor, t: int):
+    """A17 through the C-ABI (``oduck_rollout_step``): sample an action from the env's own obs["state"], step, and let the kernels
+    write the Transition into the attached sink -- raw action / log-prob by the actor's head, reward / done / truncation and the
+    next observations by the step kernel.  No per-step copies."""
+    n = env.handle.n
+    kp = env._ptr(keys, torch.int32, (n, 2))
+    tag = (id(weights), weights.version)
+    if getattr(env, "_policy_tag", None) != tag:
+        env.handle.policy_invalidate()
+        env._policy_tag = tag
+    env.handle.rollout_step(weights.struct, kp, t, env._stream())
+    return env._state()
 
 
 def torch_policy_logprob(policy: MLP, obs_n: torch.Tensor, raw: torch.Tensor, noise: Optional[torch.Tensor] = None):
@@ -285,7 +341,7 @@ class Evaluator:
 
     def __init__(self, env, cfg: PPOConfig):
         self.cfg = cfg
-        self.env = type(env)(task=env._task, config=env._config, device=env.device, library=env._lib)
+        self.env = env.spawn()            # same compiled model (incl. a user xml_path), config, library, auto-reset
         self.n = cfg.num_eval_envs
         self.key = jr.PRNGKey(cfg.seed + 101)
         self.env.randomize(jr.split(jr.PRNGKey(cfg.seed + 102), self.n))
@@ -304,7 +360,8 @@ class Evaluator:
         ep_metrics = torch.zeros(n, len(env.METRICS), device=dev)
         met = env.buffer("METRICS")
         for t in range(T):
-            act, _, _ = policy_forward(env, weights, None if self.cfg.deterministic_eval else keys[t], deterministic=self.cfg.deterministic_eval)
+            act, _, _ = policy_forward(env, weights, None if self.cfg.deterministic_eval else keys[t], deterministic=self.cfg.deterministic_eval,
+                                       obs=None if self.cfg.policy_obs_key == "state" else st.obs[self.cfg.policy_obs_key])
             st = env.step(st, act)
             ep_reward += st.reward.float() * active
             ep_metrics += met[:, :len(env.METRICS)].float() * active[:, None]
@@ -355,11 +412,15 @@ class PPOTrainer:
                 raise ValueError("num_envs per rank must be a multiple of rollout_pipeline")
             m = self.n_local // self.P
             dr, rk = shard_keys(cfg.seed + 1, world, rank, self.n_local), shard_keys(cfg.seed, world, rank, self.n_local)
-            self._envs = [type(env)(task=env._task, config=env._config, device=env.device, library=env._lib) for _ in range(self.P)]
+            self._envs = [env.spawn() for _ in range(self.P)]
             self.state = []
             for q, e in enumerate(self._envs):
                 e.randomize(dr[q * m:(q + 1) * m])
                 self.state.append(e.reset(rk[q * m:(q + 1) * m]))
+        # kernels write the rollout buffers themselves (OduckRolloutSink) when the nets read the observations the step kernel
+        # produces under those names; any other pairing keeps the copy path
+        self._use_sink = cfg.policy_obs_key == "state" and cfg.value_obs_key == "privileged_state" and cfg.kernel_rollout_writes
+        self._sink_buf = None
         self.timing = {"rollout_ms": 0.0, "gather_ms": 0.0, "update_ms": 0.0}
         self.evaluator = Evaluator(env, cfg) if (rank == 0 and cfg.num_eval_envs > 0) else None
 
@@ -383,10 +444,20 @@ class PPOTrainer:
                 "raw": torch.empty(T, n, env.action_size, device=dev), "logp": torch.empty(T, n, device=dev), "reward": torch.empty(T, n, device=dev),
                 "done": torch.empty(T, n, device=dev), "trunc": torch.empty(T, n, device=dev)}
 
+    def _attach(self, buf) -> None:
+        if self._sink_buf is not buf:
+            m = self.n_local // self.P
+            for q, e in enumerate(self._envs):
+                attach_rollout_sink(e, buf, q * m)
+            self._sink_buf = buf
+
     def _rollout_step(self, buf, t, st, keys_t):
         pk, vk = self.cfg.policy_obs_key, self.cfg.value_obs_key
+        if self._use_sink:
+            self._attach(buf)
+            return rollout_step(self.env, self.weights, keys_t, t)
         buf["obs_p"][t].copy_(st.obs[pk]); buf["obs_v"][t].copy_(st.obs[vk])
-        act, raw, logp = policy_forward(self.env, self.weights, keys_t, deterministic=False)
+        act, raw, logp = policy_forward(self.env, self.weights, keys_t, deterministic=False, obs=None if pk == "state" else st.obs[pk])
         st = self.env.step(st, act)
         buf["raw"][t].copy_(raw); buf["logp"][t].copy_(logp)
         buf["reward"][t].copy_(st.reward); buf["done"][t].copy_(st.done); buf["trunc"][t].copy_(st.info["truncation"])
@@ -411,7 +482,8 @@ class PPOTrainer:
             buf = self._new_buffers()
             for t in range(T):
                 st = self._rollout_step(buf, t, st, torch.from_numpy(keys[t]))
-            buf["obs_p"][T].copy_(st.obs[pk]); buf["obs_v"][T].copy_(st.obs[vk])
+            if not self._use_sink:
+                buf["obs_p"][T].copy_(st.obs[pk]); buf["obs_v"][T].copy_(st.obs[vk])
             self.state = st
             return buf
         # CUDA-graph path: the T steps of an unroll are captured once (per-step graphs over persistent buffers); an unroll is
@@ -427,14 +499,15 @@ class PPOTrainer:
         if R["graphs"] is None:
             for t in range(T):                               # first unroll: eager (also warms every kernel up before the capture)
                 st = self._rollout_step(buf, t, st, R["keys"][t])
-            buf["obs_p"][T].copy_(st.obs[pk]); buf["obs_v"][T].copy_(st.obs[vk])
+            if not self._use_sink:
+                buf["obs_p"][T].copy_(st.obs[pk]); buf["obs_v"][T].copy_(st.obs[vk])
             torch.cuda.synchronize(env.device)
             pool, graphs = torch.cuda.graph_pool_handle(), []
             for t in range(T):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, pool=pool):
                     self._rollout_step(buf, t, st, R["keys"][t])
-                    if t == T - 1:
+                    if t == T - 1 and not self._use_sink:
                         buf["obs_p"][T].copy_(st.obs[pk]); buf["obs_v"][T].copy_(st.obs[vk])
                 graphs.append(g)
             R["graphs"] = graphs
@@ -450,8 +523,11 @@ class PPOTrainer:
         m = self.n_local // self.P
         sl = slice(q * m, (q + 1) * m)
         e = self._envs[q]
+        if self._use_sink:
+            self._attach(buf)
+            return rollout_step(e, self.weights, keys_t[sl], t)
         buf["obs_p"][t, sl].copy_(st.obs[pk]); buf["obs_v"][t, sl].copy_(st.obs[vk])
-        act, raw, logp = policy_forward(e, self.weights, keys_t[sl], deterministic=False)
+        act, raw, logp = policy_forward(e, self.weights, keys_t[sl], deterministic=False, obs=None if pk == "state" else st.obs[pk])
         st = e.step(st, act)
         buf["raw"][t, sl].copy_(raw); buf["logp"][t, sl].copy_(logp)
         buf["reward"][t, sl].copy_(st.reward); buf["done"][t, sl].copy_(st.done); buf["trunc"][t, sl].copy_(st.info["truncation"])
@@ -546,9 +622,24 @@ class PPOTrainer:
         self._static = {k: torch.zeros(shp, device=dev) for k, shp in mb_shapes.items()}
         self._out = torch.zeros(4, device=dev)
         snap = [p.detach().clone() for p in self._params()]
-        opt_state = self.opt.state_dict()
         for prm in self._params():
             prm.grad = torch.zeros_like(prm)
+        # The Adam state must EXIST before the capture (the captured step updates these very tensors by address) and must never be
+        # replaced afterwards.  A fresh optimiser has none yet: one throw-away step on zero gradients creates it; then the state
+        # is snapshotted by VALUE (state_dict() hands out references), warm-up + capture run, and the snapshot is copied back in
+        # place -- zero moments / step 0 for a fresh optimiser, the loaded moments after load().
+        fresh = len(self.opt.state) == 0
+        if fresh:
+            self.opt.step()
+            with torch.no_grad():
+                for prm, sv in zip(self._params(), snap):
+                    prm.copy_(sv)
+        opt_snap = {prm: {k: (v.detach().clone() if torch.is_tensor(v) else copy.deepcopy(v)) for k, v in self.opt.state[prm].items()} for prm in self._params()}
+        if fresh:
+            for st_ in opt_snap.values():
+                for v in st_.values():
+                    if torch.is_tensor(v):
+                        v.zero_()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -571,7 +662,12 @@ class PPOTrainer:
         with torch.no_grad():                                    # undo the warm-up / capture-time updates
             for prm, sv in zip(self._params(), snap):
                 prm.copy_(sv)
-        self.opt.load_state_dict(opt_state)
+            for prm, saved in opt_snap.items():                  # in place: the graph keeps updating these tensors
+                for k, v in saved.items():
+                    if torch.is_tensor(v):
+                        self.opt.state[prm][k].copy_(v)
+                    else:
+                        self.opt.state[prm][k] = v
         self._graph_sharded = sharded
 
     def update(self, batch: Dict[str, torch.Tensor], sharded: bool = False) -> Dict[str, float]:

@@ -255,6 +255,8 @@ struct OduckHandle {
   int nefc_fr, nefc_lim;  // static row counts
   int fr_dof[NV], lim_jnt[NJ];
   int64_t launches;
+  OduckRolloutSink sink = {};   // attached rollout buffers (obs_policy == null: none)
+  std::vector<float> act_buf;
 };
 
 // ------------------------------------------------------------------------------------ physics scratch
@@ -1761,6 +1763,44 @@ int oduck_step(OduckHandle* h, const float* action, void*) {
   pfor(h->n, [&](int i) { env_step(*h, h->env[i], action + (size_t)i * h->m.nu); });
   return ODUCK_OK;
 }
+int oduck_set_rollout_sink(OduckHandle* h, const OduckRolloutSink* sink) {
+  if (!h) return fail(ODUCK_ERR_ARG, "oduck_set_rollout_sink: bad argument");
+  if (!sink) { h->sink = OduckRolloutSink{}; return ODUCK_OK; }
+  const int dp = h->cfg.task == ODUCK_TASK_STANDING ? 85 : ODUCK_OBS_STATE, dv = h->cfg.task == ODUCK_TASK_STANDING ? 153 : ODUCK_OBS_PRIV;
+  if (sink->unroll < 1 || sink->env_offset < 0 || sink->env_offset + h->n > sink->num_envs) return fail(ODUCK_ERR_ARG, "oduck_set_rollout_sink: the handle's envs do not fit into the buffers");
+  if (sink->policy_dim != dp || sink->value_dim != dv) return fail(ODUCK_ERR_ARG, "oduck_set_rollout_sink: obs row widths must be those of the task (Joystick 101 / 212, Standing 85 / 153)");
+  if (!sink->obs_policy || !sink->obs_value || !sink->raw_action || !sink->log_prob || !sink->reward || !sink->done || !sink->truncation)
+    return fail(ODUCK_ERR_ARG, "oduck_set_rollout_sink: null buffer");
+  h->sink = *sink;
+  return ODUCK_OK;
+}
+int oduck_policy_forward(OduckHandle* h, const OduckPolicyWeights* w, const float* obs, const uint32_t* keys, int deterministic,
+                         float* action, float* raw_action, float* log_prob, void*);
+// A17: one step of Brax generate_unroll (common/runner.py:104-118): Transition(observation = obs before the step, action,
+// reward, discount / truncation, policy extras = raw action + log-prob); the observation after the step is the next slot's.
+int oduck_rollout_step(OduckHandle* h, const OduckPolicyWeights* w, const uint32_t* keys, int t, void* stream) {
+  if (!h || !w || !keys) return fail(ODUCK_ERR_ARG, "oduck_rollout_step: bad argument");
+  const OduckRolloutSink& k = h->sink;
+  if (!k.obs_policy || t < 0 || t >= k.unroll) return fail(ODUCK_ERR_ARG, "oduck_rollout_step: no sink attached or t outside the unroll");
+  if (w->obs_dim != k.policy_dim) return fail(ODUCK_ERR_ARG, "oduck_rollout_step: the policy's input width is not the sink's policy_dim");
+  const int nu = h->m.nu;
+  const size_t row = (size_t)t * k.num_envs + k.env_offset;
+  auto put_obs = [&](size_t r0) {
+    for (int i = 0; i < h->n; i++) {
+      for (int c = 0; c < k.policy_dim; c++) k.obs_policy[(r0 + i) * k.policy_dim + c] = (float)h->env[i].obs_state[c];
+      for (int c = 0; c < k.value_dim; c++) k.obs_value[(r0 + i) * k.value_dim + c] = (float)h->env[i].obs_priv[c];
+    }
+  };
+  if (t == 0) put_obs((size_t)k.env_offset);
+  h->act_buf.resize((size_t)h->n * nu);
+  int rc = oduck_policy_forward(h, w, nullptr, keys, 0, h->act_buf.data(), k.raw_action + row * nu, k.log_prob + row, stream);
+  if (rc) return rc;
+  rc = oduck_step(h, h->act_buf.data(), stream);
+  if (rc) return rc;
+  for (int i = 0; i < h->n; i++) { k.reward[row + i] = (float)h->env[i].reward; k.done[row + i] = (float)h->env[i].done; k.truncation[row + i] = (float)h->env[i].truncation; }
+  put_obs(row + k.num_envs);
+  return ODUCK_OK;
+}
 int oduck_physics_substeps(OduckHandle* h, const float* ctrl, int n, void*) {
   if (!h || n < 0) return fail(ODUCK_ERR_ARG, "oduck_physics_substeps: bad argument");
   pfor(h->n, [&](int i) {
@@ -1801,12 +1841,17 @@ int oduck_policy_forward(OduckHandle* h, const OduckPolicyWeights* w, const floa
       x[k] = (o - (real)w->obs_mean[k]) / (real)w->obs_std[k];
     }
     for (int l = 0; l < 4; l++) {
-      y.assign(dims[l + 1], 0);
-      for (int o = 0; o < dims[l + 1]; o++) {
-        real acc = (real)w->b[l][o];
-        for (int k = 0; k < dims[l]; k++) acc += x[k] * (real)w->w[l][(size_t)k * dims[l + 1] + o];
-        y[o] = l < 3 ? acc / (1 + std::exp(-acc)) : acc;
+      // y[o] = b[o] + sum_k x[k] W[k][o], accumulated over k in order for every o (row-wise axpy: contiguous, vectorisable --
+      // the same additions in the same order as the textbook o-outer loop)
+      const int no = dims[l + 1];
+      y.resize(no);
+      for (int o = 0; o < no; o++) y[o] = (real)w->b[l][o];
+      for (int k = 0; k < dims[l]; k++) {
+        const real xk = x[k];
+        const float* wr = w->w[l] + (size_t)k * no;
+        for (int o = 0; o < no; o++) y[o] += xk * (real)wr[o];
       }
+      if (l < 3) for (int o = 0; o < no; o++) y[o] = y[o] / (1 + std::exp(-y[o]));
       x = y;
     }
     real lp = 0;

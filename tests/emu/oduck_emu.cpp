@@ -11,4 +11,9 @@ int oduck_policy_forward(OduckHandle*, const OduckPolicyWeights*, const float*, 
   return oduck_fail(ODUCK_ERR_UNSUPPORTED, "oduck_policy_forward: not part of the CPU emulation");
 }
 int oduck_policy_invalidate(OduckHandle*) { return ODUCK_OK; }
+// the env half of oduck_rollout_step (oduck_step_into_sink: k_step writing the Transition into the attached sink) IS part of the
+// emulation and is what tests/test_env_emu.py drives; the actor half is a tensor-core kernel
+int oduck_rollout_step(OduckHandle*, const OduckPolicyWeights*, const uint32_t*, int, void*) {
+  return oduck_fail(ODUCK_ERR_UNSUPPORTED, "oduck_rollout_step: the actor is not part of the CPU emulation (use oduck_step_into_sink)");
+}
 }

@@ -97,3 +97,53 @@ def test_emulated_standing_step(emu_lib, oracle):
 def test_emulated_height_field_step(emu_lib, oracle):
     emu, ref, sg, sr = _pair(Joystick, "rough_terrain_backlash", emu_lib, oracle, 8)
     _step_and_compare(emu, ref, sg, sr, steps=1, seed=4, min_ok=0.75)       # manifold branch flips, see tests/test_hfield.py
+
+
+@pytest.mark.parametrize("task", ["flat_terrain_backlash", "flat_terrain"])
+def test_domain_randomize_every_column_matches_oracle(emu_lib, oracle, task):
+    """A14 column by column (common/randomize.py:43-95): friction, frictionloss, armature, torso COM, masses, qpos0, kp -- the
+    device code's k_randomize against the oracle, the same comparison tests/test_parity_gpu.py makes on the GPU."""
+    from test_parity_gpu import _dr_columns
+    emu, ref, _, _ = _pair(Joystick, task, emu_lib, oracle, 6)
+    cols = _dr_columns(emu, ref)
+    assert set(cols) == {"geom_friction0", "body_mass", "body_ipos[1]", "dof_frictionloss", "dof_armature", "qpos0", "actuator kp"}
+    m = emu.mj_model
+    for name, (g, r) in cols.items():
+        g, r = _np(g), _np(r)
+        assert (np.abs(g - r) <= 1e-6 + 3e-7 * np.abs(r)).all(), name
+        assert np.abs(r).max() > 0 and (name in ("dof_frictionloss",) or np.std(r, axis=0).max() > 0), f"{name}: column is not randomised"
+    # and the columns really are the randomised ones: mass within +-10 % (+-0.1 kg on the torso) of the model's
+    mass = _np(cols["body_mass"][1])
+    mm = np.asarray(m.body_mass[:m.nbody])
+    heavy = np.flatnonzero(mm > 0)[1:]                                   # all but the torso (body 1), which also gets +-0.1 kg
+    assert (np.abs(mass[:, heavy] / mm[heavy] - 1.0) <= 0.1 + 1e-9).all()
+    kp = _np(cols["actuator kp"][1])
+    assert (np.abs(kp / np.asarray(m.act_kp[:m.nu]) - 1.0) <= 0.1 + 1e-9).all()
+
+
+def test_step_kernel_writes_the_transition_into_the_rollout_sink(emu_lib):
+    """A17, device code on CPU threads: k_step with a sink attached (oduck_step_into_sink, the env half of oduck_rollout_step)
+    stores reward / done / truncation of slot t and the new observations of slot t + 1 at the handle's env offset -- through an
+    episode end, where the stored observation is the auto-reset one -- and fills slot 0 from the current observations at t = 0."""
+    import ctypes as C
+    n, T, off, wide = 3, 3, 2, 6
+    env = Joystick("flat_terrain_backlash", library=emu_lib, config_overrides={"episode_length": 2})
+    st = env.reset(jr.split(jr.PRNGKey(3), n))
+    buf = {"obs_p": torch.zeros(T + 1, wide, 101), "obs_v": torch.zeros(T + 1, wide, 212), "raw": torch.zeros(T, wide, 14), "logp": torch.zeros(T, wide),
+           "reward": torch.full((T, wide), -1.0), "done": torch.full((T, wide), -1.0), "trunc": torch.full((T, wide), -1.0)}
+    from open_duck_playground_b200 import ppo
+    ppo.attach_rollout_sink(env, buf, env_offset=off)
+    L = emu_lib.lib
+    L.oduck_step_into_sink.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    obs0 = st.obs["state"].clone()
+    rs = np.random.default_rng(0)
+    for t in range(T):
+        act = torch.from_numpy(rs.uniform(-1, 1, (n, 14)).astype(np.float32))
+        emu_lib.check(L.oduck_step_into_sink(env.handle.h, act.data_ptr(), t, None))
+        s = env._state()
+        assert torch.equal(buf["obs_p"][t + 1, off:off + n], s.obs["state"]) and torch.equal(buf["obs_v"][t + 1, off:off + n], s.obs["privileged_state"])
+        assert torch.equal(buf["reward"][t, off:off + n], s.reward) and torch.equal(buf["done"][t, off:off + n], s.done)
+        assert torch.equal(buf["trunc"][t, off:off + n], s.info["truncation"])
+    assert torch.equal(buf["obs_p"][0, off:off + n], obs0)
+    assert (buf["trunc"][1, off:off + n] == 1).all() and torch.equal(buf["obs_p"][2, off:off + n], env.buffer("FIRST_OBS_STATE"))   # episode_length 2
+    assert (buf["reward"][:, :off] == -1).all() and (buf["reward"][:, off + n:] == -1).all() and (buf["obs_p"][:, :off] == 0).all()

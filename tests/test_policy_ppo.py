@@ -128,3 +128,103 @@ def test_pipelined_rollout_equals_plain_rollout(oracle):
         assert torch.equal(pa, pb)
     with pytest.raises(ValueError, match="multiple of rollout_pipeline"):
         ppo.PPOTrainer(Joystick("flat_terrain_backlash", library=oracle), ppo.PPOConfig(rollout_pipeline=5, **kw))
+
+
+def test_refresh_rewrites_weights_in_place_and_invalidates_every_handle(oracle):
+    """the library caches the repacked weights per handle keyed on the w[0] address; refresh() must keep the address
+    (persistent buffers) and make EVERY env that uses the weights drop its cache, however rarely it runs a forward."""
+    a = Joystick("flat_terrain_backlash", library=oracle); a.reset(jr.split(jr.PRNGKey(0), 4))
+    b = a.spawn(); b.reset(jr.split(jr.PRNGKey(0), 4))
+    pol, w = _weights(a)
+    ptrs = [t.data_ptr() for t in w.w + w.b]
+    calls = []
+    for e, name in ((a, "a"), (b, "b")):
+        orig = e.handle.policy_invalidate
+        e.handle.policy_invalidate = (lambda o=orig, n=name: (calls.append(n), o())[1])
+    ppo.policy_forward(a, w, None, deterministic=True); ppo.policy_forward(b, w, None, deterministic=True)
+    assert calls == ["a", "b"]
+    ppo.policy_forward(a, w, None, deterministic=True)
+    assert calls == ["a", "b"]                                           # unchanged weights: the cache stays
+    with torch.no_grad():
+        for lin in pol.layers:
+            lin.weight.mul_(0.5); lin.bias.add_(0.1)
+    w.refresh(w.mean, w.std)
+    assert [t.data_ptr() for t in w.w + w.b] == ptrs                     # same buffers, new contents
+    assert torch.equal(w.w[0], pol.layers[0].weight.detach().t()) and torch.equal(w.b[3], pol.layers[3].bias.detach())
+    act_b, _, _ = ppo.policy_forward(b, w, None, deterministic=True)     # b first this time: it must not run stale weights
+    assert calls == ["a", "b", "b"]
+    x = (b.buffer("OBS_STATE").float() - w.mean) / w.std
+    assert torch.allclose(act_b, torch.tanh(pol(x)[:, :14]), atol=2e-5)
+
+
+def test_spawn_keeps_model_config_and_autoreset(oracle):
+    e = Joystick("flat_terrain_backlash", library=oracle, auto_reset=False, config_overrides={"noise_config.level": 0.0})
+    e.reset(jr.split(jr.PRNGKey(0), 3))
+    s = e.spawn()
+    assert s._mj_model is e._mj_model and s._xml_path == e._xml_path and s._auto_reset is False and s._lib is e._lib
+    assert s._config.noise_config.level == 0.0 and s._config is not e._config and s._handle is None
+    s.reset(jr.split(jr.PRNGKey(0), 5))
+    assert s.num_envs == 5 and e.num_envs == 3
+    from open_duck_playground_b200.standing import Standing
+    st = Standing("flat_terrain_backlash", library=oracle)
+    assert type(st.spawn()) is Standing
+
+
+def test_policy_obs_key_other_than_state_is_passed_explicitly(oracle):
+    """with policy_obs_key='privileged_state' the policy is 212 wide; the rollout must hand those observations to the
+    library instead of letting it read 212 floats out of the 101-wide obs['state'] records."""
+    env = Joystick("flat_terrain_backlash", library=oracle)
+    cfg = ppo.PPOConfig(num_envs=8, unroll_length=2, num_minibatches=2, num_updates_per_batch=1, num_eval_envs=0, policy_obs_key="privileged_state", learner="torch")
+    tr = ppo.PPOTrainer(env, cfg)
+    assert tr.policy.layers[0].in_features == 212
+    buf = tr.rollout()
+    x = (buf["obs_p"][0] - tr.stats["privileged_state"].mean32) / tr.stats["privileged_state"].std
+    lp, _ = ppo.torch_policy_logprob(tr.policy, x, buf["raw"][0])
+    assert torch.allclose(lp.detach(), buf["logp"][0], atol=2e-3)
+    with pytest.raises(ValueError, match="pass obs="):
+        ppo.policy_forward(env, tr.weights, None, deterministic=True)
+
+
+@pytest.mark.parametrize("P", [1, 2])
+def test_kernel_side_rollout_writes_equal_the_copy_path(oracle, P):
+    """A17: with a rollout sink attached the library stores every Transition itself (oduck_rollout_step); the buffers must equal
+    the ones the round-1 path filled with seven copies per step -- over two unrolls (slot 0 of the second comes from the handle's
+    observations), single batch and sub-batches with env offsets."""
+    kw = dict(num_envs=12, unroll_length=4, num_minibatches=2, num_updates_per_batch=1, num_eval_envs=0, learner="torch", rollout_pipeline=P,
+              episode_length=6)
+    outs = []
+    for sink in (False, True):
+        env = Joystick("flat_terrain_backlash", library=oracle, config_overrides={"episode_length": 6})   # auto-reset inside the second unroll
+        tr = ppo.PPOTrainer(env, ppo.PPOConfig(kernel_rollout_writes=sink, **kw))
+        assert tr._use_sink is sink
+        outs.append([{k: v.clone() for k, v in tr.rollout().items()} for _ in range(2)])
+    for a, b in zip(*outs):
+        for k in a:
+            assert torch.equal(a[k], b[k]), k
+    assert outs[1][1]["done"].sum() > 0 and outs[1][1]["trunc"].sum() > 0          # the truncation / auto-reset rows were exercised
+
+
+def test_rollout_sink_argument_checks(oracle):
+    env = Joystick("flat_terrain_backlash", library=oracle)
+    env.reset(jr.split(jr.PRNGKey(0), 4))
+    _, w = _weights(env)
+    keys = torch.from_numpy(jr.split(jr.PRNGKey(5), 4).view(np.int32))
+    with pytest.raises(Exception, match="no sink attached"):
+        ppo.rollout_step(env, w, keys, 0)
+    T = 3
+    mk = lambda n, dp=101: {"obs_p": torch.zeros(T + 1, n, dp), "obs_v": torch.zeros(T + 1, n, 212), "raw": torch.zeros(T, n, 14), "logp": torch.zeros(T, n),   # noqa: E731
+                            "reward": torch.zeros(T, n), "done": torch.zeros(T, n), "trunc": torch.zeros(T, n)}
+    with pytest.raises(Exception, match="do not fit"):
+        ppo.attach_rollout_sink(env, mk(6), env_offset=3)
+    with pytest.raises(Exception, match="row widths"):
+        ppo.attach_rollout_sink(env, mk(4, dp=85))
+    buf = mk(6)
+    ppo.attach_rollout_sink(env, buf, env_offset=2)
+    with pytest.raises(Exception, match="outside the unroll"):
+        ppo.rollout_step(env, w, keys, T)
+    st = ppo.rollout_step(env, w, keys, 1)
+    assert torch.equal(buf["obs_p"][2, 2:6], st.obs["state"].float()) and torch.equal(buf["reward"][1, 2:6], st.reward.float())
+    assert (buf["obs_p"][2, :2] == 0).all() and (buf["obs_p"][0] == 0).all()       # other envs' rows / slot 0 untouched at t = 1
+    ppo.attach_rollout_sink(env, None)
+    with pytest.raises(Exception, match="no sink attached"):
+        ppo.rollout_step(env, w, keys, 0)
