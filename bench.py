@@ -634,6 +634,7 @@ def main():
     ap.add_argument("--task", default=TASK, help="scene: flat_terrain_backlash (the metric's config), flat_terrain, rough_terrain_backlash (height-field floor, BASELINE configs[3])")
     ap.add_argument("--pipeline", type=int, default=DEFAULT_PIPELINE, help="sub-batches per GPU, each with its own handle, CUDA-graph chain and stream (1 = one batch)")
     ap.add_argument("--ppo-pipeline", type=int, default=2, help="PPOConfig.rollout_pipeline of the ppo leg / mode")
+    ap.add_argument("--rough-envs", type=int, default=16384, help="total envs of the rough leg / mode (BASELINE configs[3]: 16384, split over the ranks)")
     ap.add_argument("--update-mode", default="auto", choices=["auto", "sharded", "replicated"], help="ppo mode at N > 1")
     ap.add_argument("--mode", default="rollout", choices=["rollout", "ppo", "physics", "rough"],
                     help="ppo = BASELINE configs[2] alone; physics = oduck_physics_substeps(10) alone; rough = configs[3] alone")
@@ -683,14 +684,14 @@ def main():
     if args.mode == "physics":
         return finish(as_line(leg_physics(args, rank, world, dev), "env-steps/sec (physics only: 10 x mjx.step per env-step)"))
     if args.mode == "rough":
-        return finish(as_line(leg_rough(args, rank, world, dev, steps=args.steps), METRIC))
+        return finish(as_line(leg_rough(args, rank, world, dev, total_envs=args.rough_envs, steps=args.steps), METRIC))
 
     line = run_rollout(args, rank, world, dev, local)
     if not args.no_extra:
         # BASELINE configs[1] literal, [2], [3] as extra keys of the one line (short legs, all ranks take part)
         for key, fn in (("physics_only", lambda: leg_physics(args, rank, world, dev, steps=30)),
                         ("ppo", lambda: leg_ppo(args, rank, world, dev)),
-                        ("rough", lambda: leg_rough(args, rank, world, dev))):
+                        ("rough", lambda: leg_rough(args, rank, world, dev, total_envs=args.rough_envs))):
             try:
                 torch.cuda.empty_cache()
                 leg = fn()

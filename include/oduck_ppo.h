@@ -43,6 +43,11 @@ typedef struct OduckPpoConfig {
   float learning_rate;          /* 3e-4 */
   float max_grad_norm;          /* 1.0; <= 0 disables clipping */
   float adam_b1, adam_b2, adam_eps;   /* optax.adam defaults 0.9, 0.999, 1e-8 */
+  int32_t matmul_tf32;          /* 0 (default): fp32-faithful GEMMs, 3 tensor-core passes on hi / lo tf32 halves (the parity-tested mode).
+                                 * 1: ONE tf32 pass (operands truncated to tf32, fp32 accumulate) -- what XLA runs for f32 dots on NVIDIA
+                                 * GPUs at jax's default matmul precision, i.e. the reference's own arithmetic for ppo.train
+                                 * (common/runner.py:104-118); a third of the MMAs and half the operand traffic.  The rollout actor
+                                 * always runs the fp32-faithful form (its log-prob must match the learner's recomputation). */
 } OduckPpoConfig;
 
 /* The rollout of one training step, time-major like Brax's Transition pytree: [T(+1)][N][...]. */

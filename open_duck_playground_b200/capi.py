@@ -108,7 +108,7 @@ class OduckPpoConfig(C.Structure):
         ("normalize_advantage", i32),
         ("discounting", C.c_float), ("gae_lambda", C.c_float), ("clipping_epsilon", C.c_float), ("entropy_cost", C.c_float),
         ("reward_scaling", C.c_float), ("learning_rate", C.c_float), ("max_grad_norm", C.c_float),
-        ("adam_b1", C.c_float), ("adam_b2", C.c_float), ("adam_eps", C.c_float),
+        ("adam_b1", C.c_float), ("adam_b2", C.c_float), ("adam_eps", C.c_float), ("matmul_tf32", i32),
     ]
 
 

@@ -407,6 +407,8 @@ static __device__ __noinline__ void chol_rev_chain(const DevModel& m, float* H, 
     for (int i = 0; i < k; ++i) b[i] = fmaf(-__shfl_sync(FULLMASK, lk, hb | i), lk, b[i]);
   }
 #endif
+  __syncwarp();                          // both half-warps have read the root block (lanes 16..21 mirror lanes 0..5) before it is overwritten:
+                                         // the shuffles above converge the warp but are no memory barrier (compute-sanitizer racecheck, r02b)
   if (lane < CH_NB) {
 #pragma unroll
     for (int i = 0; i < CH_NB; ++i)
@@ -442,6 +444,27 @@ static __device__ __noinline__ float chol_rev_back(const DevModel& m, const floa
     float xj = __shfl_sync(FULLMASK, y, j) / L[TRI(j) + j];
     if (lane == j) y = xj;
     else if (lane > j && lane < n) y -= L[TRI(lane) + j] * xj;
+  }
+  return y;
+}
+// chol_rev_back for the chain plan (root chain of CH_NB dofs + pure chains attached to its last dof): the ancestor of a dof at
+// level lev is lev itself on the root chain and (first dof of the lane's chain) + lev - CH_NB below it, so the sweep needs no
+// ancestor table -- the byte reads of m.anc were an 8-way shared-memory bank conflict per level (lanes 32 B apart) -- and the
+// fully unrolled loop lets the factor entries be fetched ahead of the dependent shuffle / FMA chain.  Same arithmetic, same order.
+template <int NCHAIN>
+static __device__ __noinline__ float chol_rev_back_chain(const DevModel& m, const float* L, int n, int lane, float y) {
+  const int dep = lane < n ? m.d_depth[lane] : -1;
+  const float* Lr = L + TRI(lane);
+  const float invd = lane < n ? 1.f / Lr[lane] : 0.f;
+  const int cs = lane - (dep - CH_NB);                          // first dof of this lane's chain (meaningful for dep >= CH_NB)
+#pragma unroll
+  for (int lev = 0; lev < CH_NB + NCHAIN; ++lev) {
+    if (dep == lev) y *= invd;
+    const int j = lev < CH_NB ? lev : cs + (lev - CH_NB);
+    const bool below = dep > lev;
+    const float l = below ? Lr[j] : 0.f;
+    const float xj = __shfl_sync(FULLMASK, y, below ? j : lane);
+    y = fmaf(-l, xj, y);
   }
   return y;
 }

@@ -38,6 +38,7 @@ struct GemmParams {
   long long out_split;   // DW: floats between splits
   float* dbpart; int ldb;// DX: per-warp column sums [rows / 32][ldb]  (bias gradients)
   int nvalid;            // valid output columns (bias reads are guarded)
+  int single;            // 1: one tf32 pass on the hi halves (OduckPpoConfig.matmul_tf32): half the copies, a third of the MMAs, no lo stores
 };
 
 __device__ __forceinline__ void gbulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -160,7 +161,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const int mt,
 #pragma unroll
       for (int e = 0; e < 4; ++e) gsplit_tf32(v[4 * q + e], ph[e], pl[e]);
       *reinterpret_cast<float4*>(blk + gblk_off(rt, 4 * q)) = h4;
-      *reinterpret_cast<float4*>(blk + TC_M * TC_KC + gblk_off(rt, 4 * q)) = l4;
+      if (!p.single) *reinterpret_cast<float4*>(blk + TC_M * TC_KC + gblk_off(rt, 4 * q)) = l4;
     }
   }
   if (EPI != EPI_ACT) {
@@ -177,7 +178,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, const int mt,
 #pragma unroll
       for (int e = 0; e < 4; ++e) gsplit_tf32(v[4 * q + e], ph[e], pl[e]);
       *reinterpret_cast<float4*>(blk + gblk_off(nb, 4 * q)) = h4;
-      *reinterpret_cast<float4*>(blk + TC_M * TC_KC + gblk_off(nb, 4 * q)) = l4;
+      if (!p.single) *reinterpret_cast<float4*>(blk + TC_M * TC_KC + gblk_off(nb, 4 * q)) = l4;
     }
   }
   if (EPI == EPI_DX) {
@@ -224,12 +225,14 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_gemm_tc(GemmParams p) {
     const uint32_t idesc = umma_idesc_tf32(NT);
     const float* xa = p.A + ((size_t)mt * p.nchunks + c0) * GBLK_A;
     const float* wb = p.B + ((size_t)nt * p.nchunks + c0) * BLKB;
+    const int sh = p.single ? 1 : 0;
     auto issue = [&](int i) {
       const int s = i % NSTAGE;
       float* st = smem + (size_t)s * STAGE;
-      gmbar_expect_tx(&full[s], (uint32_t)(STAGE * sizeof(float)));
-      gbulk_g2s(st, xa + (size_t)i * GBLK_A, GBLK_A * sizeof(float), &full[s]);
-      gbulk_g2s(st + GBLK_A, wb + (size_t)i * BLKB, BLKB * sizeof(float), &full[s]);
+      // (single pass: only the hi half of each block -- the first half of its bytes -- is fetched)
+      gmbar_expect_tx(&full[s], (uint32_t)((STAGE >> sh) * sizeof(float)));
+      gbulk_g2s(st, xa + (size_t)i * GBLK_A, (GBLK_A >> sh) * sizeof(float), &full[s]);
+      gbulk_g2s(st + GBLK_A, wb + (size_t)i * BLKB, (BLKB >> sh) * sizeof(float), &full[s]);
     };
     for (int i = 0; i < NSTAGE - 1 && i < n; ++i) issue(i);
     for (int i = 0; i < n; ++i) {
@@ -246,8 +249,10 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_gemm_tc(GemmParams p) {
       for (int kk = 0; kk < TC_KC / 8; ++kk) {
         const uint32_t o = kk * 256;
         umma_tf32(tmem_base, umma_smem_desc(a_hi + o, 128, 1024), umma_smem_desc(b_hi + o, 128, 1024), idesc, (i > 0 || kk > 0) ? 1u : 0u);
-        umma_tf32(tmem_base, umma_smem_desc(a_lo + o, 128, 1024), umma_smem_desc(b_hi + o, 128, 1024), idesc, 1u);
-        umma_tf32(tmem_base, umma_smem_desc(a_hi + o, 128, 1024), umma_smem_desc(b_lo + o, 128, 1024), idesc, 1u);
+        if (!sh) {
+          umma_tf32(tmem_base, umma_smem_desc(a_lo + o, 128, 1024), umma_smem_desc(b_hi + o, 128, 1024), idesc, 1u);
+          umma_tf32(tmem_base, umma_smem_desc(a_hi + o, 128, 1024), umma_smem_desc(b_lo + o, 128, 1024), idesc, 1u);
+        }
       }
       umma_commit(&empty[s]);
     }
@@ -309,11 +314,11 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_gemm_simt(GemmParams p) {
       const float* a = p.A + ((size_t)mt * p.nchunks + c0 + i) * GBLK_A;
       const float* b = p.B + ((size_t)nt * p.nchunks + c0 + i) * BLKB;
       for (int kk = 0; kk < TC_KC; ++kk) {
-        const float av = a[gblk_off(rt, kk)] + a[TC_M * TC_KC + gblk_off(rt, kk)];
+        const float av = a[gblk_off(rt, kk)] + (p.single ? 0.f : a[TC_M * TC_KC + gblk_off(rt, kk)]);
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
           const int off = gblk_off(j * 32 + e, kk);
-          v[e] = fmaf(av, b[off] + b[NT * TC_KC + off], v[e]);
+          v[e] = fmaf(av, b[off] + (p.single ? 0.f : b[NT * TC_KC + off]), v[e]);
         }
       }
     }

@@ -3,10 +3,8 @@
 // oracle/oduck_oracle.cpp hfield_convex: for every terrain triangle under the foot's bounding sphere, every foot face that
 // looks down onto it is clipped to the triangle's vertical column; clipped points below the triangle plane are candidates
 // (dist along the triangle normal, pos midway, normal = triangle normal); 4 of the candidates within 1 mm of the deepest one
-// are kept by _manifold_points with the mean normal.  Warp mapping: lane = hull face for the clipping (each lane clips its
-// own <= 8-gon in local memory), candidates are appended in the oracle's order (triangle, face, polygon vertex) to a per-env
-// HBM scratch list with a warp prefix sum, and the manifold selection runs over that list 32 candidates at a time with the
-// same first-index arg-max as the plane collider.
+// are kept by _manifold_points with the mean normal (copies of one point on a shared triangle edge masked first).  Warp mapping:
+// see hf_collide.
 #pragma once
 #include "oduck_ffcollide.cuh"
 
@@ -16,34 +14,53 @@ struct DevHF {   // global memory
   const float* data;            // [nrow][ncol] elevation in [0, 1]
 };
 
-#define HF_CAP 512             // candidates kept per foot (the oracle keeps all; a resting foot has a few dozen)
-#define HF_REC 8               // dist, pos[3], normal[3], -
-#ifdef ODUCK_HF_PAIRS
-#define HF_MAXT 32             // triangles per batch of the pair list
-#define HF_MAXPAIR 256         // (triangle, face) pairs per batch
-#define HF_SCRATCH (HF_CAP * HF_REC + 96 + HF_MAXT * 12 + HF_MAXPAIR)   // + world vertices, triangle table, pair list
-#else
+#define HF_CAP 512             // candidates kept per foot (the oracle keeps as many; a resting foot has a few dozen)
+#define HF_REC 8               // dist, pos[3], normal[3], twin flag
 #define HF_SCRATCH (HF_CAP * HF_REC)
-#endif
-#define HF_MAXP 12             // 8-gon clipped by 3 planes: at most 11 vertices
+#define HF_MAXP 11             // 8-gon clipped by 3 half-planes: at most 11 vertices
+#define HF_LANES 13            // (triangle, face) pairs clipped per round: one 33-float polygon per lane in shared memory
+#define HF_MAXPAIR 64          // pair list of a batch (the rhs + rowbuf rows of WarpSmem)
+#define HF_TWIN 1e-5f          // clipped points closer than this (max-norm) are copies of one point on a shared triangle edge
 
-// Sutherland-Hodgman: keep the part of the polygon on the inner side (d <= 0) of the vertical plane through r0 -> r1
-__device__ __forceinline__ int hf_clip(const float (*in)[3], int cnt, float (*out)[3], const float r0x, const float r0y, const float sdx, const float sdy) {
+// Sutherland-Hodgman IN PLACE: keep the part of the polygon P[cnt][3] on the inner side (d <= 0) of the vertical plane through
+// r0 with outward normal (sdx, sdy).  One buffer suffices because an output slot never overtakes the input: the vertex after
+// the current one is held in registers (and the first vertex for the wrap-around), and before iteration v at most v + 1 points
+// have been written -- v + 1 only when vertex v itself is outside (a convex polygon crosses the plane at most twice).  The same
+// arithmetic, in the same order, as the two-buffer form of oracle/oduck_oracle.cpp hfield_convex.  The polygons live in shared
+// memory: with the kernel's shared-memory carve-out the L1 that would back per-lane local arrays is ~20 KB per SM, and the
+// first version of this collider spent 60 % of k_step<HF> waiting for local-memory loads (ncu r02a, profiles/).
+__device__ __forceinline__ int hf_clip(float* __restrict__ P, const int cnt, const float r0x, const float r0y, const float sdx, const float sdy) {
+  if (cnt <= 0) return 0;
+  const float fx = P[0], fy = P[1], fz = P[2];
+  float cx = fx, cy = fy, cz = fz;
+  const float dfirst = sdx * (cx - r0x) + sdy * (cy - r0y);
+  float d0 = dfirst;
   int no = 0;
   for (int v = 0; v < cnt; ++v) {
-    const int w = v + 1 == cnt ? 0 : v + 1;
-    const float d0 = sdx * (in[v][0] - r0x) + sdy * (in[v][1] - r0y), d1 = sdx * (in[w][0] - r0x) + sdy * (in[w][1] - r0y);
-    if (d0 <= 0.f) { out[no][0] = in[v][0]; out[no][1] = in[v][1]; out[no][2] = in[v][2]; ++no; }
-    if ((d0 <= 0.f) != (d1 <= 0.f)) {
+    float nx, ny, nz, d1;
+    if (v + 1 == cnt) { nx = fx; ny = fy; nz = fz; d1 = dfirst; }
+    else { nx = P[3 * v + 3]; ny = P[3 * v + 4]; nz = P[3 * v + 5]; d1 = sdx * (nx - r0x) + sdy * (ny - r0y); }
+    if (d0 <= 0.f && no < HF_MAXP) { P[3 * no] = cx; P[3 * no + 1] = cy; P[3 * no + 2] = cz; ++no; }
+    if ((d0 <= 0.f) != (d1 <= 0.f) && no < HF_MAXP && no <= v + 1) {
       const float t = d0 / (d0 - d1);
-      out[no][0] = in[v][0] + t * (in[w][0] - in[v][0]); out[no][1] = in[v][1] + t * (in[w][1] - in[v][1]); out[no][2] = in[v][2] + t * (in[w][2] - in[v][2]);
+      P[3 * no] = cx + t * (nx - cx); P[3 * no + 1] = cy + t * (ny - cy); P[3 * no + 2] = cz + t * (nz - cz);
       ++no;
     }
+    cx = nx; cy = ny; cz = nz; d0 = d1;
   }
   return no;
 }
 
 // Writes the four contact records of foot f: s.con[4 f + c][0] = dist (1: inactive), [1..3] = pos, [13..15] = normal.
+// Three stages per foot.  (1) The terrain triangles under the hull's box are enumerated by the whole warp (warp-uniform loops);
+// lane = hull face decides whether its face looks down onto the triangle and overlaps its cell, and the surviving (triangle,
+// face) pairs are appended to a list in shared memory -- cells the hull's box misses and triangles wholly below its lowest
+// vertex are skipped (a candidate needs a hull point BELOW the triangle plane, which never rises above the triangle's top;
+// 1e-6 m margins keep the culls conservative under fp32 rounding).  (2) The pairs are clipped HF_LANES at a time, lane =
+// pair, each lane in its own shared-memory polygon; clipped points below the triangle plane are appended to the env's
+// candidate list in the oracle's order (triangle, face, polygon vertex) with a warp prefix sum.  (3) Twins are masked and the
+// manifold is selected over the list 32 candidates at a time with the plane collider's first-index arg-max.
+// Shared memory borrowed from WarpSmem while the Hessian does not exist: H (world vertices + polygons), rhs + rowbuf (pairs).
 static __device__ __noinline__ void hf_collide(const DevModel& m, const DevFF* __restrict__ ff, const DevHF* __restrict__ hf, WarpSmem& s,
                                                const int lane, const int f, float* __restrict__ cand) {
   const int fb = m.foot_body[f];
@@ -56,7 +73,6 @@ static __device__ __noinline__ void hf_collide(const DevModel& m, const DevFF* _
     float* cc = s.con[4 * f + lane];
     cc[0] = 1.f; cc[1] = cc[2] = cc[3] = 0.f; cc[13] = 0.f; cc[14] = 0.f; cc[15] = 1.f;
   }
-  __syncwarp();
   const V3 C = p0 + rot(v3(ff->center[f][0], ff->center[f][1], ff->center[f][2]));
   const float rb = ff->radius;
   const int nrow = hf->nrow, ncol = hf->ncol;
@@ -65,54 +81,15 @@ static __device__ __noinline__ void hf_collide(const DevModel& m, const DevFF* _
   int cmin = (int)floorf((C.x - rb + sx) / dx), cmax = (int)floorf((C.x + rb + sx) / dx);
   int rmin = (int)floorf((C.y - rb + sy) / dy), rmax = (int)floorf((C.y + rb + sy) / dy);
   cmin = max(cmin, 0); rmin = max(rmin, 0); cmax = min(cmax, ncol - 2); rmax = min(rmax, nrow - 2);
-  // this lane's face: world normal and world polygon
-  const bool has = lane < ff->nplane;
-  const int q = has ? lane : 0;
-  const V3 Nw = rot(v3(ff->plane_normal[f][0][q], ff->plane_normal[f][1][q], ff->plane_normal[f][2][q]));
-  const int cnt0 = has ? ff->plane_nvert[q] : 0;
-  float P0[8][3];
-  for (int v = 0; v < cnt0; ++v) {
-    const int vid = ff->plane_vert[q][v];
-    const V3 w = p0 + rot(v3(m.vert[f][0][vid], m.vert[f][1][vid], m.vert[f][2][vid]));
-    P0[v][0] = w.x; P0[v][1] = w.y; P0[v][2] = w.z;
-  }
-#ifdef ODUCK_HF_CULL
-  // Result-preserving culls (measured next round; off by default so that the verified build is unchanged): the world box of the
-  // hull (lane = vertex, redux min / max) rejects cells it does not overlap and triangles that lie wholly below its lowest
-  // vertex (a candidate needs a hull point BELOW the triangle plane, whose height never exceeds the triangle's top); the box
-  // of this lane's face rejects the clipping.  1e-6 m margins keep the culls conservative under fp32 rounding of the clipped points.
-  float bx0, bx1, by0, by1, bz0;
+  float* wv = s.H;                                                       // world hull vertices [32][3]
+  float* poly = s.H + 96 + 3 * HF_MAXP * (lane < HF_LANES ? lane : 0);    // this lane's polygon
+  int* wp = reinterpret_cast<int*>(s.rhs);                               // pair list: (cell * 2 + half) << 5 | face
+  float hx0, hx1, hy0, hy1, hz0;                                          // box of the hull
   {
     const bool vv = lane < m.nvert;
     const int vl = vv ? lane : 0;
     const V3 w = p0 + rot(v3(m.vert[f][0][vl], m.vert[f][1][vl], m.vert[f][2][vl]));
-    const float inf = __int_as_float(0x7f800000);
-    bx1 = wmaxf(vv ? w.x : -inf) + 1e-6f; bx0 = -wmaxf(vv ? -w.x : -inf) - 1e-6f;
-    by1 = wmaxf(vv ? w.y : -inf) + 1e-6f; by0 = -wmaxf(vv ? -w.y : -inf) - 1e-6f;
-    bz0 = -wmaxf(vv ? -w.z : -inf) - 1e-6f;
-  }
-  float fx0 = 0.f, fx1 = 0.f, fy0 = 0.f, fy1 = 0.f;
-  if (cnt0 > 0) {
-    fx0 = fx1 = P0[0][0]; fy0 = fy1 = P0[0][1];
-    for (int v = 1; v < cnt0; ++v) { fx0 = fminf(fx0, P0[v][0]); fx1 = fmaxf(fx1, P0[v][0]); fy0 = fminf(fy0, P0[v][1]); fy1 = fmaxf(fy1, P0[v][1]); }
-    fx0 -= 1e-6f; fx1 += 1e-6f; fy0 -= 1e-6f; fy1 += 1e-6f;
-  }
-#endif
-  int nc = 0;                      // candidates so far (warp-uniform)
-  V3 nsum = v3(0.f, 0.f, 0.f);     // sum of the candidates' normals (warp-uniform)
-  float deep = 0.f;                // lane-local deepest candidate
-#ifdef ODUCK_HF_PAIRS
-  // Variant for an A/B run (tools/variants.py): instead of every lane clipping ITS face against every triangle in turn (a
-  // handful of lanes busy, ~18 sequential rounds), the (triangle, face) pairs that survive the box culls are listed first and
-  // then clipped 32 pairs at a time, lane = pair.  The candidate order (triangle, face, polygon vertex) is unchanged.
-  float* wv = cand + HF_CAP * HF_REC;                                   // world vertices [32][3]
-  float* wt = wv + 96;                                                   // triangles [HF_MAXT][12]: T0, T1, T2, n
-  int* wp = reinterpret_cast<int*>(wt + HF_MAXT * 12);                   // pairs [HF_MAXPAIR]: triangle << 5 | face
-  float hx0, hx1, hy0, hy1, hz0;                                          // box of the hull, 1e-6 m margins
-  {
-    const bool vv = lane < m.nvert;
-    const int vl = vv ? lane : 0;
-    const V3 w = p0 + rot(v3(m.vert[f][0][vl], m.vert[f][1][vl], m.vert[f][2][vl]));
+    __syncwarp();                                                         // (H's previous readers are done)
     if (vv) { wv[3 * lane] = w.x; wv[3 * lane + 1] = w.y; wv[3 * lane + 2] = w.z; }
     const float inf = __int_as_float(0x7f800000);
     hx1 = wmaxf(vv ? w.x : -inf) + 1e-6f; hx0 = -wmaxf(vv ? -w.x : -inf) - 1e-6f;
@@ -120,40 +97,56 @@ static __device__ __noinline__ void hf_collide(const DevModel& m, const DevFF* _
     hz0 = -wmaxf(vv ? -w.z : -inf) - 1e-6f;
   }
   __syncwarp();
-  float gx0 = 0.f, gx1 = 0.f, gy0 = 0.f, gy1 = 0.f;                       // box of this lane's face
-  if (cnt0 > 0) {
-    gx0 = gx1 = P0[0][0]; gy0 = gy1 = P0[0][1];
-    for (int v = 1; v < cnt0; ++v) { gx0 = fminf(gx0, P0[v][0]); gx1 = fmaxf(gx1, P0[v][0]); gy0 = fminf(gy0, P0[v][1]); gy1 = fmaxf(gy1, P0[v][1]); }
+  // this lane's face: world normal and xy box
+  const bool has = lane < ff->nplane;
+  const int q = has ? lane : 0;
+  const V3 Nw = rot(v3(ff->plane_normal[f][0][q], ff->plane_normal[f][1][q], ff->plane_normal[f][2][q]));
+  float gx0 = 0.f, gx1 = 0.f, gy0 = 0.f, gy1 = 0.f;
+  if (has) {
+    const int cnt0 = ff->plane_nvert[q];
+    for (int v = 0; v < cnt0; ++v) {
+      const int vid = ff->plane_vert[q][v];
+      const float x = wv[3 * vid], y = wv[3 * vid + 1];
+      if (v == 0) { gx0 = gx1 = x; gy0 = gy1 = y; }
+      else { gx0 = fminf(gx0, x); gx1 = fmaxf(gx1, x); gy0 = fminf(gy0, y); gy1 = fmaxf(gy1, y); }
+    }
     gx0 -= 1e-6f; gx1 += 1e-6f; gy0 -= 1e-6f; gy1 += 1e-6f;
   }
-  int nt = 0, np = 0;                                                    // triangles / pairs in the current batch (warp-uniform)
+  int nc = 0;                      // candidates so far (warp-uniform)
+  V3 nsum = v3(0.f, 0.f, 0.f);     // sum of the candidates' normals (warp-uniform)
+  float deep = 0.f;                // lane-local deepest candidate
+  int np = 0;                      // pairs in the list (warp-uniform)
   auto flush = [&]() {
     __syncwarp();
-    for (int base = 0; base < np; base += 32) {
+    for (int base = 0; base < np; base += HF_LANES) {
       const int i = base + lane;
-      float A[HF_MAXP][3], B[HF_MAXP][3];
       int cnt = 0;
       V3 T0 = v3(0.f, 0.f, 0.f), n = v3(0.f, 0.f, 1.f);
-      if (i < np) {
+      if (lane < HF_LANES && i < np) {
         const int pr = wp[i];
-        const float* tr = wt + (pr >> 5) * 12;
-        const int qq = pr & 31;
-        T0 = v3(tr[0], tr[1], tr[2]);
-        const V3 T1 = v3(tr[3], tr[4], tr[5]), T2 = v3(tr[6], tr[7], tr[8]);
-        n = v3(tr[9], tr[10], tr[11]);
+        const int qq = pr & 31, half = (pr >> 5) & 1, cell = pr >> 6;
+        const int r = cell / ncol, c = cell - r * ncol;
+        // the triangle, by the expressions of the enumeration below (the same floats)
+        const float x0 = c * dx - sx, x1 = (c + 1) * dx - sx, y0 = r * dy - sy, y1 = (r + 1) * dy - sy;
+        const float h00 = data[(size_t)r * ncol + c] * sz, h01 = data[(size_t)r * ncol + c + 1] * sz;
+        const float h10 = data[(size_t)(r + 1) * ncol + c] * sz, h11 = data[(size_t)(r + 1) * ncol + c + 1] * sz;
+        T0 = half == 0 ? v3(x0, y1, h10) : v3(x0, y0, h00);
+        const V3 T1 = half == 0 ? v3(x0, y0, h00) : v3(x1, y0, h01);
+        const V3 T2 = v3(x1, y1, h11);
+        n = cross(T1 - T0, T2 - T0);
+        n = (1.f / sqrtf(dot(n, n))) * n;
         const int c0 = ff->plane_nvert[qq];
-        float P[8][3];
         for (int v = 0; v < c0; ++v) {
           const int vid = ff->plane_vert[qq][v];
-          P[v][0] = wv[3 * vid]; P[v][1] = wv[3 * vid + 1]; P[v][2] = wv[3 * vid + 2];
+          poly[3 * v] = wv[3 * vid]; poly[3 * v + 1] = wv[3 * vid + 1]; poly[3 * v + 2] = wv[3 * vid + 2];
         }
-        cnt = hf_clip(P, c0, A, T0.x, T0.y, T1.y - T0.y, -(T1.x - T0.x));
-        if (cnt > 0) cnt = hf_clip(A, cnt, B, T1.x, T1.y, T2.y - T1.y, -(T2.x - T1.x));
-        if (cnt > 0) cnt = hf_clip(B, cnt, A, T2.x, T2.y, T0.y - T2.y, -(T0.x - T2.x));
+        cnt = hf_clip(poly, c0, T0.x, T0.y, T1.y - T0.y, -(T1.x - T0.x));
+        cnt = hf_clip(poly, cnt, T1.x, T1.y, T2.y - T1.y, -(T2.x - T1.x));
+        cnt = hf_clip(poly, cnt, T2.x, T2.y, T0.y - T2.y, -(T0.x - T2.x));
       }
       int k = 0;
       for (int v = 0; v < cnt; ++v) {
-        const float dist = n.x * (A[v][0] - T0.x) + n.y * (A[v][1] - T0.y) + n.z * (A[v][2] - T0.z);
+        const float dist = n.x * (poly[3 * v] - T0.x) + n.y * (poly[3 * v + 1] - T0.y) + n.z * (poly[3 * v + 2] - T0.z);
         if (dist < 0.f) ++k;
       }
       int incl = k;
@@ -163,22 +156,25 @@ static __device__ __noinline__ void hf_collide(const DevModel& m, const DevFF* _
       if (total == 0) continue;                                         // warp-uniform
       int at = nc + incl - k;
       for (int v = 0; v < cnt; ++v) {
-        const float dist = n.x * (A[v][0] - T0.x) + n.y * (A[v][1] - T0.y) + n.z * (A[v][2] - T0.z);
+        const float px = poly[3 * v], py = poly[3 * v + 1], pz = poly[3 * v + 2];
+        const float dist = n.x * (px - T0.x) + n.y * (py - T0.y) + n.z * (pz - T0.z);
         if (!(dist < 0.f)) continue;
         if (at < HF_CAP) {
           float* rec = cand + at * HF_REC;
-          rec[0] = dist; rec[1] = A[v][0] - 0.5f * dist * n.x; rec[2] = A[v][1] - 0.5f * dist * n.y; rec[3] = A[v][2] - 0.5f * dist * n.z;
-          rec[4] = n.x; rec[5] = n.y; rec[6] = n.z;
+          rec[0] = dist; rec[1] = px - 0.5f * dist * n.x; rec[2] = py - 0.5f * dist * n.y; rec[3] = pz - 0.5f * dist * n.z;
+          rec[4] = n.x; rec[5] = n.y; rec[6] = n.z; rec[7] = 0.f;
           deep = fminf(deep, dist);
         }
         ++at;
       }
       const float kf = (float)k;
-      nsum = nsum + v3(wsum(kf * n.x), wsum(kf * n.y), wsum(kf * n.z));
+      float ns[3] = {kf * n.x, kf * n.y, kf * n.z};
+      const float tt = wfold<3>(ns, lane);
+      nsum = nsum + v3(wfold_get(tt, 0), wfold_get(tt, 1), wfold_get(tt, 2));
       nc += total;
     }
     __syncwarp();
-    nt = 0; np = 0;
+    np = 0;
   };
   for (int r = rmin; r <= rmax; ++r)
     for (int c = cmin; c <= cmax; ++c) {
@@ -188,88 +184,23 @@ static __device__ __noinline__ void hf_collide(const DevModel& m, const DevFF* _
       const float h10 = data[(size_t)(r + 1) * ncol + c] * sz, h11 = data[(size_t)(r + 1) * ncol + c + 1] * sz;
 #pragma unroll 1
       for (int i = 0; i < 2; ++i) {
-        const V3 T0 = i == 0 ? v3(x0, y1, h10) : v3(x0, y0, h00);
-        const V3 T1 = i == 0 ? v3(x0, y0, h00) : v3(x1, y0, h01);
-        const V3 T2 = v3(x1, y1, h11);
-        const float top = fmaxf(T0.z, fmaxf(T1.z, T2.z));
-        if (C.z - rb > top || hz0 > top) continue;                      // warp-uniform
-        V3 n = cross(T1 - T0, T2 - T0);
-        n = (1.f / sqrtf(dot(n, n))) * n;
-        const bool act = has && dot(Nw, n) < 0.f && !(x1 < gx0 || x0 > gx1 || y1 < gy0 || y0 > gy1);
-        const unsigned bm = __ballot_sync(FULLMASK, act);
-        if (!bm) continue;                                              // warp-uniform
-        if (nt == HF_MAXT || np + 32 > HF_MAXPAIR) flush();
-        if (lane == 0) {
-          float* tr = wt + nt * 12;
-          tr[0] = T0.x; tr[1] = T0.y; tr[2] = T0.z; tr[3] = T1.x; tr[4] = T1.y; tr[5] = T1.z; tr[6] = T2.x; tr[7] = T2.y; tr[8] = T2.z;
-          tr[9] = n.x; tr[10] = n.y; tr[11] = n.z;
-        }
-        if (act) wp[np + __popc(bm & ((1u << lane) - 1u))] = (nt << 5) | lane;
-        np += __popc(bm);
-        ++nt;
-      }
-    }
-  flush();
-#else
-  for (int r = rmin; r <= rmax; ++r)
-    for (int c = cmin; c <= cmax; ++c) {
-      const float x0 = c * dx - sx, x1 = (c + 1) * dx - sx, y0 = r * dy - sy, y1 = (r + 1) * dy - sy;
-#ifdef ODUCK_HF_CULL
-      if (x1 < bx0 || x0 > bx1 || y1 < by0 || y0 > by1) continue;      // warp-uniform: the cell misses the hull's box
-#endif
-      const float h00 = data[(size_t)r * ncol + c] * sz, h01 = data[(size_t)r * ncol + c + 1] * sz;
-      const float h10 = data[(size_t)(r + 1) * ncol + c] * sz, h11 = data[(size_t)(r + 1) * ncol + c + 1] * sz;
-#pragma unroll 1
-      for (int i = 0; i < 2; ++i) {
         // counter-clockwise seen from above; the cell is split along (c, r) - (c + 1, r + 1)
         const V3 T0 = i == 0 ? v3(x0, y1, h10) : v3(x0, y0, h00);
         const V3 T1 = i == 0 ? v3(x0, y0, h00) : v3(x1, y0, h01);
         const V3 T2 = v3(x1, y1, h11);
         const float top = fmaxf(T0.z, fmaxf(T1.z, T2.z));
-        if (C.z - rb > top) continue;                                   // warp-uniform
-#ifdef ODUCK_HF_CULL
-        if (bz0 > top) continue;                                        // warp-uniform: the whole hull is above this triangle
-#endif
+        if (C.z - rb > top || hz0 > top) continue;                      // warp-uniform: the hull is above this triangle
         V3 n = cross(T1 - T0, T2 - T0);
         n = (1.f / sqrtf(dot(n, n))) * n;
-        float A[HF_MAXP][3], B[HF_MAXP][3];
-        int cnt = 0;
-#ifdef ODUCK_HF_CULL
-        if (has && dot(Nw, n) < 0.f && !(x1 < fx0 || x0 > fx1 || y1 < fy0 || y0 > fy1)) {
-#else
-        if (has && dot(Nw, n) < 0.f) {                                  // only the faces that look down onto the triangle
-#endif
-          cnt = hf_clip(P0, cnt0, A, T0.x, T0.y, T1.y - T0.y, -(T1.x - T0.x));
-          if (cnt > 0) cnt = hf_clip(A, cnt, B, T1.x, T1.y, T2.y - T1.y, -(T2.x - T1.x));
-          if (cnt > 0) cnt = hf_clip(B, cnt, A, T2.x, T2.y, T0.y - T2.y, -(T0.x - T2.x));
-        }
-        int k = 0;
-        for (int v = 0; v < cnt; ++v) {
-          const float dist = n.x * (A[v][0] - T0.x) + n.y * (A[v][1] - T0.y) + n.z * (A[v][2] - T0.z);
-          if (dist < 0.f) ++k;
-        }
-        int incl = k;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULLMASK, incl, o); if (lane >= o) incl += t; }
-        const int total = __shfl_sync(FULLMASK, incl, 31);
-        if (total == 0) continue;                                       // warp-uniform
-        int at = nc + incl - k;
-        for (int v = 0; v < cnt; ++v) {
-          const float dist = n.x * (A[v][0] - T0.x) + n.y * (A[v][1] - T0.y) + n.z * (A[v][2] - T0.z);
-          if (!(dist < 0.f)) continue;
-          if (at < HF_CAP) {
-            float* rec = cand + at * HF_REC;
-            rec[0] = dist; rec[1] = A[v][0] - 0.5f * dist * n.x; rec[2] = A[v][1] - 0.5f * dist * n.y; rec[3] = A[v][2] - 0.5f * dist * n.z;
-            rec[4] = n.x; rec[5] = n.y; rec[6] = n.z;
-            deep = fminf(deep, dist);
-          }
-          ++at;
-        }
-        nsum = nsum + (float)total * n;
-        nc += total;
+        const bool act = has && dot(Nw, n) < 0.f && !(x1 < gx0 || x0 > gx1 || y1 < gy0 || y0 > gy1);   // the face looks down onto the triangle
+        const unsigned bm = __ballot_sync(FULLMASK, act);
+        if (!bm) continue;                                              // warp-uniform
+        if (np + __popc(bm) > HF_MAXPAIR) flush();
+        if (act) wp[np + __popc(bm & ((1u << lane) - 1u))] = ((((r * ncol + c) << 1) | i) << 5) | lane;
+        np += __popc(bm);
       }
     }
-#endif
+  flush();
   if (nc == 0) return;
   nc = min(nc, HF_CAP);
   __syncwarp();
@@ -277,12 +208,44 @@ static __device__ __noinline__ void hf_collide(const DevModel& m, const DevFF* _
   const float thr = fminf(0.f, deepest + 1e-3f);                        // plane_convex's rule: within 1 mm of the deepest
   const V3 nm = (1.f / sqrtf(dot(nsum, nsum))) * nsum;                  // every triangle normal has n_z > 0
   const float ninf = -__int_as_float(0x7f800000);
+  // Twins (oracle hfield_convex): an in-threshold candidate whose clipped point lies within HF_TWIN of an EARLIER in-threshold
+  // candidate is a copy of the same point seen through a neighbouring triangle; it is masked out, so the arg-max passes below
+  // never choose between copies that differ only by rounding and by the triangle normal they carry.
+  for (int base = 0; base < nc; base += 32) {
+    const int j = base + lane;
+    V3 pj = v3(0.f, 0.f, 0.f);
+    bool inj = false;
+    if (j < nc) {
+      const float* rec = cand + j * HF_REC;
+      inj = rec[0] < thr;
+      pj = v3(rec[1] + 0.5f * rec[0] * rec[4], rec[2] + 0.5f * rec[0] * rec[5], rec[3] + 0.5f * rec[0] * rec[6]);   // the clipped point itself
+    }
+    bool tw = false;
+    for (int ib = 0; ib <= base; ib += 32) {
+      V3 po = pj;
+      bool ino = inj;
+      if (ib != base) {
+        const float* rec = cand + (ib + lane) * HF_REC;                  // earlier chunks are full
+        ino = rec[0] < thr;
+        po = v3(rec[1] + 0.5f * rec[0] * rec[4], rec[2] + 0.5f * rec[0] * rec[5], rec[3] + 0.5f * rec[0] * rec[6]);
+      }
+      unsigned bm = __ballot_sync(FULLMASK, ino);
+      while (bm) {                                                       // warp-uniform
+        const int l = __ffs(bm) - 1;
+        bm &= bm - 1;
+        const float ox = __shfl_sync(FULLMASK, po.x, l), oy = __shfl_sync(FULLMASK, po.y, l), oz = __shfl_sync(FULLMASK, po.z, l);
+        if (inj && ib + l < j && fmaxf(fabsf(pj.x - ox), fmaxf(fabsf(pj.y - oy), fabsf(pj.z - oz))) < HF_TWIN) tw = true;
+      }
+    }
+    if (j < nc && tw) cand[j * HF_REC + 7] = 1.f;
+  }
+  __syncwarp();
   // point i of the list as seen by this lane in the chunk starting at `base`
 #define HF_LOAD(base, P_, dm_)                                                                                         \
   V3 P_ = v3(0.f, 0.f, 0.f); float dm_ = ninf;                                                                          \
   {                                                                                                                    \
     const int i_ = (base) + lane;                                                                                      \
-    if (i_ < nc) { const float* rec = cand + i_ * HF_REC; P_ = v3(rec[1], rec[2], rec[3]); dm_ = rec[0] < thr ? 0.f : -1e6f; }   \
+    if (i_ < nc) { const float* rec = cand + i_ * HF_REC; P_ = v3(rec[1], rec[2], rec[3]); dm_ = (rec[0] < thr && rec[7] == 0.f) ? 0.f : -1e6f; }   \
   }
   auto point = [&](int i) { const float* rec = cand + i * HF_REC; return v3(rec[1], rec[2], rec[3]); };
   int idx[4] = {0, 0, 0, 0};

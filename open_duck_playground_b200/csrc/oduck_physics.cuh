@@ -27,9 +27,19 @@ struct LSPoint { float alpha, d0, d1; };
 #ifndef ODUCK_BARRIERS
 #define ODUCK_BARRIERS 0x01
 #endif
-#define PHASE_SYNC(bit, pre_exit) { if (BAR && ((ODUCK_BARRIERS >> (bit)) & 1) && (!(pre_exit) || !FF)) __syncthreads(); }
+#ifndef ODUCK_PHASE_MARK
+#define ODUCK_PHASE_MARK(bit)      // tests/emu counts warp exchanges per phase through this hook
+#endif
+#define PHASE_SYNC(bit, pre_exit) { ODUCK_PHASE_MARK(bit) if (BAR && ((ODUCK_BARRIERS >> (bit)) & 1) && (!(pre_exit) || !FF)) __syncthreads(); }
 __device__ __forceinline__ void substep_idle_barriers(int substeps) {
   for (int k = 0; k < substeps * __popc(ODUCK_BARRIERS & 0x3f); ++k) __syncthreads();
+}
+
+// root-to-leaf sweep after chol_rev_tree: table-free on the chain plans, level-parallel with the ancestor table otherwise
+__device__ __forceinline__ float back_tree(const DevModel& m, const float* L, int n, int lane, float y) {
+  if (m.plan_ok == 1) return chol_rev_back_chain<10>(m, L, n, lane, y);
+  if (m.plan_ok == 2) return chol_rev_back_chain<5>(m, L, n, lane, y);
+  return chol_rev_back(m, L, n, lane, y, true);
 }
 
 template <bool DBG, bool FF, bool BAR, bool HF>
@@ -303,7 +313,7 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
   s.rhs[lane] = fs;
   __syncwarp();
   chol_rev_tree(m, s.H, s.rhs, nv, lane, s.rowbuf);                                         // factor_m + L^-T qfrc_smooth
-  const float as = chol_rev_back(m, s.H, nv, lane, s.rhs[lane], true);                      // qacc_smooth
+  const float as = back_tree(m, s.H, nv, lane, s.rhs[lane]);                                // qacc_smooth
 
   PHASE_SYNC(2, true)
   // ------------------------------------------------------------------ collision: plane (z = 0) vs convex foot hulls (lane = vertex)
@@ -578,14 +588,31 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
     if (lane < nv) s.H[TRI(lane) + lane] += (fquad ? Df : 0.f) + (lon ? Dl : 0.f);
     if (anyc) {
       const int dep = lane < nv ? m.d_depth[lane] : -1;
-      const unsigned char* al = m.anc[lane];
       float* Hi = s.H + TRI(lane);
+      if (m.plan_ok) {
+        // chain plan (see chol_rev_back_chain): ancestor at level lev = lev on the root chain, chain start + lev - CH_NB below it; no
+        // table, root-chain axes are warp-wide broadcasts, and the lane's own term uses the axis it already holds in registers
+        const int cs = lane - (dep - CH_NB);
+        const int nlev = m.max_dof_depth;                                 // levels of proper ancestors: 0 .. max_dof_depth - 1
+        if (dep >= 0) Hi[lane] += z.a0 * cd.a0 + z.a1 * cd.a1 + z.a2 * cd.a2 + z.l0 * cd.l0 + z.l1 * cd.l1 + z.l2 * cd.l2;
+#pragma unroll
+        for (int lev = 0; lev < CH_NB + 10; ++lev) {
+          if (lev >= nlev) break;                                        // warp-uniform
+          if (lev < dep) {
+            const int j = lev < CH_NB ? lev : cs + (lev - CH_NB);
+            const float4 c0 = lds4(&s.cdof[j][0]), c1 = lds4(&s.cdof[j][4]);
+            Hi[j] += z.a0 * c0.x + z.a1 * c0.y + z.a2 * c0.z + z.l0 * c0.w + z.l1 * c1.x + z.l2 * c1.y;
+          }
+        }
+      } else {
+        const unsigned char* al = m.anc[lane];
 #pragma unroll 1
-      for (int lev = 0; lev <= m.max_dof_depth; ++lev) {
-        if (lev <= dep) {
-          const int j = lev < dep ? al[lev] : lane;
-          const float4 c0 = lds4(&s.cdof[j][0]), c1 = lds4(&s.cdof[j][4]);
-          Hi[j] += z.a0 * c0.x + z.a1 * c0.y + z.a2 * c0.z + z.l0 * c0.w + z.l1 * c1.x + z.l2 * c1.y;
+        for (int lev = 0; lev <= m.max_dof_depth; ++lev) {
+          if (lev <= dep) {
+            const int j = lev < dep ? al[lev] : lane;
+            const float4 c0 = lds4(&s.cdof[j][0]), c1 = lds4(&s.cdof[j][4]);
+            Hi[j] += z.a0 * c0.x + z.a1 * c0.y + z.a2 * c0.z + z.l0 * c0.w + z.l1 * c1.x + z.l2 * c1.y;
+          }
         }
       }
     }
@@ -616,7 +643,7 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
     __syncwarp();
     if (FF && ffact) chol_rev(m, s.H, s.rhs, nv, lane, false);
     else chol_rev_tree(m, s.H, s.rhs, nv, lane, s.rowbuf);
-    search = -chol_rev_back(m, s.H, nv, lane, s.rhs[lane], !(FF && ffact));
+    search = -((FF && ffact) ? chol_rev_back(m, s.H, nv, lane, s.rhs[lane], false) : back_tree(m, s.H, nv, lane, s.rhs[lane]));
     if (lane >= nv) search = 0.f;
   }
   PHASE_SYNC(4, false)

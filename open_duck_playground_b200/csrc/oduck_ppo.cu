@@ -821,6 +821,7 @@ static int net_forward(OduckPpo* h, int net, bool simt, cudaStream_t st) {
     const Seg& b = h->seg.s[(net * PPO_NL + l) * 2 + 1];
     GemmParams g;
     memset(&g, 0, sizeof(g));
+    g.single = h->cfg.matmul_tf32 ? 1 : 0;
     g.A = nb.Xr[l]; g.B = h->packed + w.wf;
     g.nchunks = ceil_div(w.K, TC_KC); g.cps = g.nchunks;
     g.bias = h->params + b.off; g.nvalid = w.N;
@@ -847,6 +848,7 @@ static int net_backward(OduckPpo* h, int net, bool simt, cudaStream_t sx, cudaSt
       // dW_l = X_l^T dZ_l: rows = in features, columns = out features, contraction over the batch (split-K)
       GemmParams g;
       memset(&g, 0, sizeof(g));
+    g.single = h->cfg.matmul_tf32 ? 1 : 0;
       g.A = nb.Xt[l]; g.B = nb.dZt[l];
       g.nchunks = nb.Mpad / TC_KC; g.cps = ceil_div(g.nchunks, w.nsplit);
       g.out = h->partial + w.dwpart; g.ldo = w.ldo; g.out_split = w.split_stride;
@@ -859,6 +861,7 @@ static int net_backward(OduckPpo* h, int net, bool simt, cudaStream_t sx, cudaSt
       const Seg& bprev = h->seg.s[(net * PPO_NL + l - 1) * 2 + 1];
       GemmParams g;
       memset(&g, 0, sizeof(g));
+    g.single = h->cfg.matmul_tf32 ? 1 : 0;
       g.A = nb.dZr[l]; g.B = h->packed + w.wb;
       g.nchunks = ceil_div(w.N, TC_KC); g.cps = g.nchunks;
       g.Z = nb.Z[l - 1]; g.z_nch = w.K / TC_KC;

@@ -58,6 +58,8 @@ class PPOConfig:
                                     # 0 = auto: 2 on CUDA from 2048 envs per rank (measured on B200: rollout 26.9 -> 25.8 ms at 8192), else 1
     kernel_rollout_writes: bool = True   # the step / actor kernels store each Transition in the rollout buffers themselves
                                     # (oduck_rollout_step); False = the 7 torch copies per step of round 1 (kept as the checker)
+    learner_matmul: str = "fp32"    # device learner GEMMs: "fp32" = fp32-faithful (3 tf32 tensor-core passes; the parity-tested default),
+                                    # "tf32" = one tf32 pass, XLA's default arithmetic for f32 dots on NVIDIA GPUs (the reference's own)
     learner: str = "auto"           # "device": the fused learner step of include/oduck_ppo.h (tcgen05 GEMMs, fused GAE/loss/Adam kernels);
                                     # "torch": the PyTorch fp32 twin (the checker of the device learner, and the CPU path of the tests);
                                     # "auto": device on CUDA, torch otherwise
@@ -277,6 +279,9 @@ class DeviceLearner:
         c.discounting, c.gae_lambda, c.clipping_epsilon, c.entropy_cost = cfg.discounting, cfg.gae_lambda, cfg.clipping_epsilon, cfg.entropy_cost
         c.reward_scaling, c.learning_rate, c.max_grad_norm = cfg.reward_scaling, cfg.learning_rate, cfg.max_grad_norm if cfg.max_grad_norm else 0.0
         c.adam_b1, c.adam_b2, c.adam_eps = 0.9, 0.999, 1e-8
+        if cfg.learner_matmul not in ("fp32", "tf32"):
+            raise ValueError("learner_matmul must be 'fp32' or 'tf32'")
+        c.matmul_tf32 = 1 if cfg.learner_matmul == "tf32" else 0
         self.batch_envs = int(batch_envs)
         self.h = capi.PpoHandle(capi.load_cuda_library(), c, self.device.index or 0)
         self.params, self.grads = self.view("PARAMS"), self.view("GRADS")
@@ -749,20 +754,26 @@ class PPOTrainer:
         graphed = cfg.cuda_graph and self._roll is not None and batch is self._roll["buf"]
         if graphed and getattr(self, "_upd", None) is None:
             U = {"idx": torch.zeros(B, dtype=torch.int32, device=dev), "key": torch.zeros(2, dtype=torch.int32, device=dev), "ro": ro, "nm": nm}
-            stages = [FLB, capi.PPO_STAGE_ADAM] if sharded else [capi.PPO_ALL | capi.PPO_NO_COOP]     # plain kernel nodes only
-            try:
-                L.minibatch(ro, nm, U["idx"].data_ptr(), 0, U["key"].data_ptr(), capi.PPO_STAGE_FORWARD)    # warm-up outside the capture
-                torch.cuda.synchronize(dev)
-                U["graphs"] = []
-                for stg in stages:
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
-                        L.minibatch(ro, nm, U["idx"].data_ptr(), 0, U["key"].data_ptr(), stg)
-                    U["graphs"].append(g)
-            except Exception as e:                                                       # capture unsupported (e.g. cooperative launch): stay eager
-                import sys
-                print(f"[ppo] minibatch graph capture unavailable ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
-                U["graphs"] = None
+            # single GPU: the fused cooperative reduce + clip + Adam launch as a graph node (a kernel node with the cooperative
+            # attribute); if this driver / runtime cannot capture it, the two-kernel tail (plain kernel nodes)
+            variants = [[FLB, capi.PPO_STAGE_ADAM]] if sharded else [[capi.PPO_ALL], [capi.PPO_ALL | capi.PPO_NO_COOP]]
+            U["graphs"], U["coop_in_graph"] = None, False
+            for stages in variants:
+                try:
+                    L.minibatch(ro, nm, U["idx"].data_ptr(), 0, U["key"].data_ptr(), capi.PPO_STAGE_FORWARD)    # warm-up outside the capture
+                    torch.cuda.synchronize(dev)
+                    graphs = []
+                    for stg in stages:
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g):
+                            L.minibatch(ro, nm, U["idx"].data_ptr(), 0, U["key"].data_ptr(), stg)
+                        graphs.append(g)
+                    U["graphs"], U["coop_in_graph"] = graphs, stages == [capi.PPO_ALL]
+                    break
+                except Exception as e:                                                   # capture of this form unsupported: next form, else eager
+                    import sys
+                    print(f"[ppo] minibatch graph capture (stages {stages}) unavailable ({type(e).__name__}: {str(e)[:120]})", file=sys.stderr)
+                    torch.cuda.synchronize(dev)
             self._upd = U
         U = getattr(self, "_upd", None) if graphed else None
         for e in range(cfg.num_updates_per_batch):

@@ -825,6 +825,29 @@ static void hfield_convex(const OduckHandle& h, const Scratch& s, int k, int slo
   real deepest = 0;
   for (int v = 0; v < nc; v++) deepest = std::min(deepest, cd[v]);
   for (int v = 0; v < nc; v++) cm[v] = cd[v] < std::min((real)0, deepest + (real)1e-3);   // plane_convex's rule: within 1 mm of the deepest
+  // Twins: a clipped point on an edge shared by two terrain triangles (or on a cell border) is emitted once per triangle, the
+  // copies ~1e-7 m apart but with different triangle normals.  Which twin a later arg-max picks would be decided by rounding,
+  // and the pick matters through the normal.  An in-threshold candidate whose clipped point lies within HF_TWIN = 1e-5 m
+  // (max-norm; hull vertices are millimetres apart) of an EARLIER in-threshold candidate is therefore masked out before the
+  // manifold selection -- the first copy in list order (triangle, face, polygon vertex) stands for all of them.
+  {
+    const real HF_TWIN = (real)1e-5;
+    static thread_local bool twin[MAXC];
+    for (int j = 0; j < nc; j++) {
+      twin[j] = false;
+      if (!cm[j]) continue;
+      for (int i = 0; i < j && !twin[j]; i++) {
+        if (!cm[i]) continue;
+        real dmax = 0;
+        for (int a = 0; a < 3; a++) {
+          const real pj = cp[j][a] + (real)0.5 * cd[j] * cn[j][a], pi = cp[i][a] + (real)0.5 * cd[i] * cn[i][a];   // the clipped points themselves
+          dmax = std::max(dmax, std::fabs(pj - pi));
+        }
+        if (dmax < HF_TWIN) twin[j] = true;
+      }
+    }
+    for (int j = 0; j < nc; j++) if (twin[j]) cm[j] = false;
+  }
   int idx[4];
   manifold_points(nc, cp, cm, nmean, idx);
   for (int c = 0; c < 4; c++) {

@@ -24,8 +24,13 @@ inline std::barrier<>* bar = nullptr;          // one warp at a time
 inline uint32_t xchg[32];
 inline thread_local int lane = 0;
 inline void sync() { bar->arrive_and_wait(); }
+// tools/emu_shuffle_count.py: warp exchanges (= SHFL / VOTE / REDUX instructions of the real kernel) per phase of the substep
+inline long long exchanges[16] = {0};
+inline int phase = 15;
+#define ODUCK_PHASE_MARK(bit) { if (warp_emu::lane == 0) warp_emu::phase = (bit); }
 template <typename F>
 inline uint32_t exchange(uint32_t mine, F pick) {   // every lane publishes `mine`, then reads what `pick` selects
+  if (lane == 0) ++exchanges[phase & 15];
   xchg[lane] = mine;
   sync();
   uint32_t r = pick(xchg);

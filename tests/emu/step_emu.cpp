@@ -9,6 +9,7 @@
 #include "../../open_duck_playground_b200/csrc/oduck_build.h"
 #include "../../open_duck_playground_b200/csrc/oduck_physics.cuh"
 
+extern "C" int emu_exchange_counts(long long* out, int reset) { for (int i = 0; i < 16; i++) { out[i] = warp_emu::exchanges[i]; if (reset) warp_emu::exchanges[i] = 0; } return 0; }
 extern "C" int emu_strides(int* out) { out[0] = PHYS_STRIDE; out[1] = DR_STRIDE; out[2] = OUT_STRIDE; out[3] = PHYS_QVEL; out[4] = PHYS_QACCW; out[5] = PHYS_CTRL; out[6] = OUT_QACC; out[7] = OUT_SENS; out[8] = OUT_EFC; out[9] = OUT_CDIST; out[10] = OUT_AFRC; return 0; }
 
 // phys [PHYS_STRIDE] in/out (qpos | qvel | qacc_warm | ctrl), ctrl [nu] or null, out [OUT_STRIDE].  Returns 0, or -1 with a bad model.

@@ -285,7 +285,7 @@ def test_hfield_gpu_collision_parity(oracle):
     g, r = outs
     dg, dr = g[:, 1120:1128], r[:, 1120:1128]
     c = Checks()
-    c.OUTLIER_FRAC = 0.04                 # manifold picks among near-equal candidates flip between fp32 and fp64 more often than on the plane
+    c.OUTLIER_FRAC = 0.015                # (round 1: 4 %; copies of one point on a shared triangle edge are masked now, oracle hfield_convex "Twins")
     assert (dr < 0).any(axis=1).mean() > 0.5
     c.mostly_equal(dg < 0, dr < 0, "active contact set")
     both = (dg < 0) & (dr < 0)
@@ -309,11 +309,12 @@ def test_hfield_gpu_env_step_parity(oracle):
     n = 256
     gpu, ref, sg, sr = _gpu_pair(oracle, n)
     c = Checks()
-    # A control step is 10 substeps x 2 feet of manifold selection among near-coincident candidates (points on an edge shared by
-    # two terrain triangles appear once per triangle, a few 1e-7 m apart and with different normals): fp32 and fp64 pick a
-    # different one in ~0.6 % of the forwards (test above), i.e. in 2-9 % of the envs per control step (measured on B200).
-    # Those envs are counted and reported; every other env must meet the flat-floor tolerances (medians sit at < 1 % of them).
-    c.OUTLIER_FRAC = 0.12
+    # A control step is 10 substeps x 2 feet of manifold selection.  Round 1 allowed 12 % of the envs to take another branch:
+    # points on an edge shared by two terrain triangles appeared once per triangle, a few 1e-7 m apart with different normals,
+    # and fp32 / fp64 picked different copies.  The copies are masked now (oracle hfield_convex "Twins"); what remains is the
+    # flat floor's kind of disagreement (a candidate within rounding of the 1 mm threshold or of dist = 0), compounded over 10
+    # substeps.  Those envs are counted and reported; every other env must meet the flat-floor tolerances.
+    c.OUTLIER_FRAC = 0.03
     c.equal(gpu.buffer("INFO_RNG").cpu().numpy(), ref.buffer("INFO_RNG").numpy(), "rng key stream")
     c.close(sg.data.qpos, sr.data.qpos, 1e-6, what="reset qpos")
     c.rows(sg.data.efc_force, sr.data.efc_force, 1e-3, 1e-2, what="reset efc_force")

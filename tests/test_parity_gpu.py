@@ -37,10 +37,14 @@ class Checks:
     Continuous quantities are judged PER ENV: an env agrees when max_j |a_ij - b_ij| <= atol + rtol * max_j |b_ij|.  The
     step contains discontinuous decisions (contact active iff dist < 0, the 1 mm manifold skin, limit activation, line-search
     bracket choices); fp32 and fp64 take different branches in a small fraction of envs, exactly as the fp32 and fp64 builds of
-    the CPU oracle do against each other.  Up to OUTLIER_FRAC of the envs may therefore disagree; they are counted and
-    reported ("active-set disagreements counted and reported"), all others must meet the tolerance.
+    the CPU oracle do against each other.  Up to OUTLIER_FRAC of the envs (never fewer than MIN_ALLOWED envs: small batches) may
+    therefore disagree; they are counted and reported ("active-set disagreements counted and reported"), all
+    others must meet the tolerance.  Measured on B200 at the BASELINE size (4096 envs, profiles/r02b_pytest_gpu.log): 1 - 6
+    envs of 4096 (<= 0.15 %) per quantity and control step outside tolerance, 0 of ~15 000 active contacts with a different
+    active state (SURVEY's bound: < 0.1 % of the contacts, checked by ``contacts``); 0 - 3 envs of 256 in the small tests.
     """
-    OUTLIER_FRAC = 0.015
+    OUTLIER_FRAC = 0.004
+    MIN_ALLOWED = 3
 
     def __init__(self):
         self.fail, self.log = [], []
@@ -50,7 +54,7 @@ class Checks:
         a, b = a.reshape(a.shape[0], -1), b.reshape(b.shape[0], -1)
         err = np.abs(a - b).max(axis=1)
         lim = atol + rtol * np.abs(b).max(axis=1)
-        nbad, allowed = int((err > lim).sum()), max(1, int(self.OUTLIER_FRAC * a.shape[0]))
+        nbad, allowed = int((err > lim).sum()), max(self.MIN_ALLOWED, int(self.OUTLIER_FRAC * a.shape[0]))
         self.log.append(f"{what}: median err/limit={np.median(err / lim):.3f}  p99={np.quantile(err / lim, 0.99):.2f}  outlier envs={nbad}/{a.shape[0]}")
         if nbad > allowed:
             k = int(np.argmax(err / lim))
@@ -65,7 +69,7 @@ class Checks:
     def mostly_equal(self, a, b, what=""):
         a, b = np.asarray(a), np.asarray(b)
         a, b = a.reshape(a.shape[0], -1), b.reshape(b.shape[0], -1)
-        nbad, allowed = int((a != b).any(axis=1).sum()), max(1, int(self.OUTLIER_FRAC * a.shape[0]))
+        nbad, allowed = int((a != b).any(axis=1).sum()), max(self.MIN_ALLOWED, int(self.OUTLIER_FRAC * a.shape[0]))
         self.log.append(f"{what}: envs differing={nbad}/{a.shape[0]}")
         if nbad > allowed:
             self.fail.append(f"{what}: {nbad} envs differ (allowed {allowed})")

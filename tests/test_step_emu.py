@@ -117,7 +117,7 @@ def test_emulated_foot_foot_path(emu, oracle, model_backlash, poly_table):
     assert ok[hit].mean() >= 0.75
 
 
-@pytest.mark.parametrize("flag", ["-DODUCK_HF_CULL", "-DODUCK_HF_PAIRS", "-DODUCK_CHOL_LDL"])
+@pytest.mark.parametrize("flag", ["-DODUCK_CHOL_LDL"])
 def test_prepared_variants(emu, oracle, poly_table, flag):
     """The kernel variants kept behind compile-time flags for A/B runs on the GPU box pass the same comparison,
     and the result-preserving ones reproduce the default build's numbers."""
@@ -126,10 +126,7 @@ def test_prepared_variants(emu, oracle, poly_table, flag):
     got, ref = _run_pair(var, oracle, model, poly_table, n=12, nsub=5, seed=400)
     _check(got, ref, min_ok=0.8)
     base, _ = _run_pair(emu, oracle, model, poly_table, n=12, nsub=5, seed=400)
-    if flag == "-DODUCK_HF_CULL":
-        assert all(np.array_equal(got[k], base[k]) for k in got)        # culls skip work / prefetches reorder loads: never change a number
-    elif flag == "-DODUCK_HF_PAIRS":
-        assert np.abs(got["QVEL"] - base["QVEL"]).max(axis=1).mean() < 1e-4   # same candidates; the mean normal is summed in another order
+    assert np.abs(got["QVEL"] - base["QVEL"]).max(axis=1).mean() < 1e-3   # same algorithm, other rounding
 
 
 def test_prepared_variants_combined(oracle, model_backlash, poly_table):
