@@ -333,13 +333,14 @@ def leg_rough(args, rank, world, dev, total_envs=16384, steps=20):
             "l2": f"{n_sets} env sets rotated", "gpu_launches": 6 * steps}
 
 
-def leg_ppo(args, rank, world, dev, num_envs=8192, steps=3, warmup=2, pipeline=None, update_mode="auto"):
+def leg_ppo(args, rank, world, dev, num_envs=8192, steps=3, warmup=2, pipeline=None, update_mode="auto", matmul=None):
     """BASELINE configs[2]: full PPO (8192 envs x unroll 20 per training step, 4 epochs x 32 minibatches), timed end to end with the
     rollout / gather / update split.  Strong scaling: the 8192 envs are split over the ranks."""
     import torch
     from open_duck_playground_b200 import ppo
     from open_duck_playground_b200.joystick import Joystick
-    cfg = ppo.PPOConfig(num_envs=num_envs, rollout_pipeline=pipeline or args.ppo_pipeline, num_eval_envs=0, update_mode=update_mode)
+    cfg = ppo.PPOConfig(num_envs=num_envs, rollout_pipeline=pipeline or args.ppo_pipeline, num_eval_envs=0, update_mode=update_mode,
+                        learner_matmul=matmul or args.learner_matmul)
     tr = ppo.PPOTrainer(Joystick(TASK, device=dev), cfg, rank=rank, world=world)
     for _ in range(max(1, warmup)):
         tr.training_step()
@@ -357,7 +358,7 @@ def leg_ppo(args, rank, world, dev, num_envs=8192, steps=3, warmup=2, pipeline=N
     del tr
     return {"value": steps * cfg.num_envs * cfg.unroll_length / dt, "unit": "env-steps/s", "steps": steps, "warmup": max(1, warmup), "ms_per_step": dt / steps * 1e3,
             "workload": f"{TASK} full PPO, {cfg.num_envs} envs x unroll {cfg.unroll_length}, 4 epochs x 32 minibatches over {world} GPU(s) (BASELINE configs[2])",
-            "scaling": "strong", "update_mode": mode, "rollout_pipeline": cfg.rollout_pipeline,
+            "scaling": "strong", "update_mode": mode, "rollout_pipeline": cfg.rollout_pipeline, "learner_matmul": cfg.learner_matmul,
             "split_ms_per_training_step": {k: v / steps for k, v in split.items()}, "learner_launches_total": launches}
 
 
@@ -635,6 +636,7 @@ def main():
     ap.add_argument("--pipeline", type=int, default=DEFAULT_PIPELINE, help="sub-batches per GPU, each with its own handle, CUDA-graph chain and stream (1 = one batch)")
     ap.add_argument("--ppo-pipeline", type=int, default=2, help="PPOConfig.rollout_pipeline of the ppo leg / mode")
     ap.add_argument("--rough-envs", type=int, default=16384, help="total envs of the rough leg / mode (BASELINE configs[3]: 16384, split over the ranks)")
+    ap.add_argument("--learner-matmul", default="fp32", choices=["fp32", "tf32"], help="PPOConfig.learner_matmul of the ppo leg / mode")
     ap.add_argument("--update-mode", default="auto", choices=["auto", "sharded", "replicated"], help="ppo mode at N > 1")
     ap.add_argument("--mode", default="rollout", choices=["rollout", "ppo", "physics", "rough"],
                     help="ppo = BASELINE configs[2] alone; physics = oduck_physics_substeps(10) alone; rough = configs[3] alone")

@@ -173,8 +173,13 @@ typedef struct OduckModel {
  * selectable per task like the reference selects terms -- by a non-zero entry of reward_config.scales.  Inputs follow the
  * reference's accessors (open_duck_mini_v2/base.py:193-271): "joints" are the nu actuated joints, sensors are the imu-site
  * sensors, feet are the two foot sites.  Scaled terms are added to the task's own sum in enum order, before `* dt` and the
- * clip (joystick.py:444-447).  reward_base_y_swing and reward_feet_phase need a gait clock the reference does not define
- * and are not offered.  The terms are not reported in the metrics buffer. */
+ * clip (joystick.py:444-447).  The terms are not reported in the metrics buffer.
+ * reward_base_y_swing and reward_feet_phase take a time / a per-foot target height that no reference task computes (neither is
+ * called anywhere in the reference; the second carries a FIXME).  They are offered with an EXPLICIT gait clock: the env's own
+ * reference-motion phase counter i = info["imitation_i"] after this step's increment (joystick.py:352-356, period
+ * nb_steps_in_period control steps = 0.54 s; 0 when the imitation reward is off).  t = i * ctrl_dt;  foot k's phase
+ * phi_k = wrap(2 pi i / period + k pi) in [-pi, pi), rz_k = mujoco_playground gait.get_rz(phi_k, swing_height = max_foot_height)
+ * (cubic Bezier 0 -> h over the first half period, h -> 0 over the second; restated from upstream). */
 enum OduckLibTerm {
   ODUCK_LIB_ORIENTATION = 0,       /* cost_orientation(gravity sensor)          -- Joystick (joystick.py:645, commented out upstream) */
   ODUCK_LIB_LIN_VEL_Z,             /* cost_lin_vel_z(global_linvel)             rewards.py:37 */
@@ -190,11 +195,14 @@ enum OduckLibTerm {
   ODUCK_LIB_FEET_CLEARANCE,        /* cost_feet_clearance(feet linvel sensors, feet site pos, max_foot_height)  rewards.py:187 */
   ODUCK_LIB_FEET_HEIGHT,           /* cost_feet_height(swing_peak, first_contact, max_foot_height)              rewards.py:202 */
   ODUCK_LIB_FEET_AIR_TIME,         /* reward_feet_air_time(feet_air_time, first_contact, command, thresholds)   rewards.py:212 */
+  ODUCK_LIB_BASE_Y_SWING,          /* reward_base_y_swing(local_linvel y, freq, amplitude, t, tracking_sigma)    rewards.py:53; t = gait clock (below) */
+  ODUCK_LIB_FEET_PHASE,            /* reward_feet_phase(feet site pos, rz)                                        rewards.py:228; rz from the gait clock */
   ODUCK_NLIBTERM
 };
 typedef struct OduckRewardLibrary {
   double scale[ODUCK_NLIBTERM];    /* 0 = term off (the default: the shipped tasks use none) */
   double base_height_target, max_foot_height, air_time_threshold_min, air_time_threshold_max;
+  double base_y_swing_freq, base_y_swing_amplitude;   /* Hz (default 1 / gait period), m/s */
   double soft_lowers[ODUCK_MAX_NU], soft_uppers[ODUCK_MAX_NU], pose_weights[ODUCK_MAX_NU];
   int32_t n_hip, hip_indices[4], n_knee, knee_indices[4];   /* actuator indices */
 } OduckRewardLibrary;

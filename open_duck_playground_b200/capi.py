@@ -53,13 +53,14 @@ class OduckModel(C.Structure):
 
 
 LIB_TERMS = ["orientation", "lin_vel_z", "ang_vel_xy", "base_height", "energy", "joint_pos_limits", "termination", "joint_deviation_hip",
-             "joint_deviation_knee", "pose", "feet_slip", "feet_clearance", "feet_height", "feet_air_time"]          # enum OduckLibTerm
+             "joint_deviation_knee", "pose", "feet_slip", "feet_clearance", "feet_height", "feet_air_time", "base_y_swing", "feet_phase"]   # enum OduckLibTerm
 
 
 class OduckRewardLibrary(C.Structure):
     _fields_ = [
         ("scale", d * len(LIB_TERMS)),
         ("base_height_target", d), ("max_foot_height", d), ("air_time_threshold_min", d), ("air_time_threshold_max", d),
+        ("base_y_swing_freq", d), ("base_y_swing_amplitude", d),
         ("soft_lowers", d * MAX_NU), ("soft_uppers", d * MAX_NU), ("pose_weights", d * MAX_NU),
         ("n_hip", i32), ("hip_indices", i32 * 4), ("n_knee", i32), ("knee_indices", i32 * 4),
     ]

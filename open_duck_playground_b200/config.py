@@ -149,6 +149,7 @@ def _fill_reward_library(lib, model: CompiledModel, rc: ConfigDict, standing: bo
     ``reward_config`` with the defaults of the functions' signatures / of this robot: ``base_height_target`` (keyframe
     height), ``max_foot_height`` (0.03 m), ``air_time_threshold_min/max`` (0.1 / 0.5 s, rewards.py:216-217),
     ``soft_joint_pos_limit_factor`` (0.95 of the actuator ranges about their centres), ``pose_weights`` (ones),
+    ``base_y_swing_freq`` / ``base_y_swing_amplitude`` (one sway per 0.54 s gait period, 0.05 m/s),
     ``hip_joints`` (hip yaw + roll) and ``knee_joints`` (actuator names)."""
     for k, v in rc.scales.items():
         if k in TASK_TERMS or (k == "orientation" and standing):
@@ -161,6 +162,9 @@ def _fill_reward_library(lib, model: CompiledModel, rc: ConfigDict, standing: bo
     lib.max_foot_height = float(rc.get("max_foot_height", 0.03))
     lib.air_time_threshold_min = float(rc.get("air_time_threshold_min", 0.1))
     lib.air_time_threshold_max = float(rc.get("air_time_threshold_max", 0.5))
+    # gait-clocked terms (include/oduck.h): lateral sway once per gait period unless told otherwise (0.54 s: poly_reference_motion.py:54-60)
+    lib.base_y_swing_freq = float(rc.get("base_y_swing_freq", 1.0 / 0.54))
+    lib.base_y_swing_amplitude = float(rc.get("base_y_swing_amplitude", 0.05))
     factor = float(rc.get("soft_joint_pos_limit_factor", 0.95))
     lo, hi = np.asarray(model.act_ctrlrange[:nu, 0], np.float64), np.asarray(model.act_ctrlrange[:nu, 1], np.float64)   # inheritrange: ctrlrange = joint range
     mid, half = 0.5 * (lo + hi), 0.5 * (hi - lo) * factor

@@ -412,6 +412,17 @@ __global__ void __launch_bounds__(WPB * 32, CTAS_PER_SM) k_step(Params p) {
         t[ODUCK_LIB_FEET_CLEARANCE] = nan_to_num(wsum(ft ? clr : 0.f));
         t[ODUCK_LIB_FEET_HEIGHT] = nan_to_num(wsum(ft ? eh * eh * first_contact : 0.f));
         t[ODUCK_LIB_FEET_AIR_TIME] = nan_to_num(wsum(ft ? at : 0.f) * (cmd_norm > 0.01f ? 1.f : 0.f));
+        // gait-clocked terms (include/oduck.h): clock = the reference-motion phase counter after this step's increment
+        const float tt = (float)er.imitation_i * dt;
+        const float tgt = R.swing_amp * sinf(2.f * PI * R.swing_freq * tt);
+        t[ODUCK_LIB_BASE_Y_SWING] = nan_to_num(expf(-((tgt - sd[4]) * (tgt - sd[4])) / c.tracking_sigma));
+        float phi = 2.f * PI * (float)er.imitation_i / (float)c.nb_steps + (float)f * PI;
+        phi -= 2.f * PI * floorf((phi + PI) / (2.f * PI));                                   // wrap to [-pi, pi)
+        const float xg = (phi + PI) / (2.f * PI);                                            // gait.get_rz: cubic Bezier 0 -> h -> 0
+        const float xb = xg <= 0.5f ? 2.f * xg : 2.f * xg - 1.f;
+        const float bz = xb * xb * xb + 3.f * (xb * xb * (1.f - xb));
+        const float rz = xg <= 0.5f ? R.max_foot_height * bz : R.max_foot_height + (0.f - R.max_foot_height) * bz;
+        t[ODUCK_LIB_FEET_PHASE] = nan_to_num(expf(-wsum(ft ? (fz - rz) * (fz - rz) : 0.f) / 0.01f));
       }
       float libsum = 0.f;
 #pragma unroll
@@ -649,6 +660,7 @@ int oduck_create(const OduckModel* model, const OduckEnvConfig* cfg, int num_env
     for (int k = 0; k < ODUCK_NLIBTERM; k++) r.scale[k] = (float)L.scale[k];
     r.base_height_target = (float)L.base_height_target; r.max_foot_height = (float)L.max_foot_height;
     r.air_thr_min = (float)L.air_time_threshold_min; r.air_thr_max = (float)L.air_time_threshold_max;
+    r.swing_freq = (float)L.base_y_swing_freq; r.swing_amp = (float)L.base_y_swing_amplitude;
     for (int u = 0; u < model->nu; u++) { r.soft_lo[u] = (float)L.soft_lowers[u]; r.soft_hi[u] = (float)L.soft_uppers[u]; r.pose_w[u] = (float)L.pose_weights[u]; }
     for (int i = 0; i < L.n_hip; i++) r.hip_mask |= 1u << L.hip_indices[i];
     for (int i = 0; i < L.n_knee; i++) r.knee_mask |= 1u << L.knee_indices[i];

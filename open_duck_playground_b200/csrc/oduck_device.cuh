@@ -306,8 +306,7 @@ __device__ __forceinline__ void branch_elim(float* H, float* rhs, const int lane
     a[i] = (i >= CH_NB && j <= i && col) ? H[TRI(gi) + gj] : 0.f;
   }
   r = (j >= CH_NB && col) ? rhs[gj] : 0.f;
-#ifdef ODUCK_CHOL_LDL
-  // Variant for an A/B run (tools/variants.py): square-root-free form.  The pivot row stays unnormalised (u_kj, u_kk = d_k), so
+  // Square-root-free form (measured on B200: +0.5 % env-steps/s over the Cholesky form, profiles/r02c).  The pivot row stays unnormalised (u_kj, u_kk = d_k), so
   // its hand-over through shared memory no longer waits for the pivot's broadcast and reciprocal root: per pivot the chain
   // SHFL -> RSQ -> MUL -> STS -> LDS -> FMA becomes max(SHFL -> RCP -> MUL, STS -> LDS) -> FMA.  H then holds U with
   // M = U^T D^-1 U and rhs the unscaled sweep r = sqrt(D) y; chol_rev_back reads both forms with the same code
@@ -330,28 +329,6 @@ __device__ __forceinline__ void branch_elim(float* H, float* rhs, const int lane
       if (4 * i4 + 3 < NLOC) a[4 * i4 + 3] = fmaf(-v.w, w, a[4 * i4 + 3]);
     }
   }
-#else
-#pragma unroll
-  for (int k = NLOC - 1; k >= CH_NB; --k) {
-    const float akk = __shfl_sync(FULLMASK, a[k], hb | k);
-    const float inv = rsqrtf(akk);
-    const float lk = j < k ? a[k] * inv : 0.f;                 // L[k][j]
-    a[k] = j == k ? akk * inv : lk;
-    const float yk = __shfl_sync(FULLMASK, r, hb | k) * inv;
-    r = j == k ? yk : r - lk * yk;
-    __syncwarp();                                               // the previous pivot's row has been read by every lane
-    rowbuf[hb | j] = lk;                                        // zero for j >= k: rows >= k are not touched below
-    __syncwarp();
-#pragma unroll
-    for (int i4 = 0; i4 < (k + 3) / 4; ++i4) {                  // A[i][j] -= L[k][i] L[k][j]
-      const float4 v = lds4(rowbuf + hb + 4 * i4);
-      a[4 * i4] = fmaf(-v.x, lk, a[4 * i4]);
-      if (4 * i4 + 1 < NLOC) a[4 * i4 + 1] = fmaf(-v.y, lk, a[4 * i4 + 1]);
-      if (4 * i4 + 2 < NLOC) a[4 * i4 + 2] = fmaf(-v.z, lk, a[4 * i4 + 2]);
-      if (4 * i4 + 3 < NLOC) a[4 * i4 + 3] = fmaf(-v.w, lk, a[4 * i4 + 3]);
-    }
-  }
-#endif
   if (store && col) {
 #pragma unroll
     for (int i = CH_NB; i < NLOC; ++i)
@@ -385,7 +362,6 @@ static __device__ __noinline__ void chol_rev_chain(const DevModel& m, float* H, 
   for (int i = 0; i < CH_NB; ++i) b[i] = (j <= i && j < CH_NB) ? H[TRI(i) + j] + db[i] : 0.f;
   if (j < CH_NB) rb = rhs[j] + dr;
   const int hb = lane & 16;
-#ifdef ODUCK_CHOL_LDL
 #pragma unroll
   for (int k = CH_NB - 1; k >= 0; --k) {
     const float uk = j < k ? b[k] : 0.f;
@@ -394,19 +370,6 @@ static __device__ __noinline__ void chol_rev_chain(const DevModel& m, float* H, 
 #pragma unroll
     for (int i = 0; i < k; ++i) b[i] = fmaf(-__shfl_sync(FULLMASK, uk, hb | i), w, b[i]);   // the row's hand-over does not wait for the reciprocal
   }
-#else
-#pragma unroll
-  for (int k = CH_NB - 1; k >= 0; --k) {
-    const float akk = __shfl_sync(FULLMASK, b[k], hb | k);
-    const float inv = rsqrtf(akk);
-    const float lk = j < k ? b[k] * inv : 0.f;
-    b[k] = j == k ? akk * inv : lk;
-    const float yk = __shfl_sync(FULLMASK, rb, hb | k) * inv;
-    rb = j == k ? yk : rb - lk * yk;
-#pragma unroll
-    for (int i = 0; i < k; ++i) b[i] = fmaf(-__shfl_sync(FULLMASK, lk, hb | i), lk, b[i]);
-  }
-#endif
   __syncwarp();                          // both half-warps have read the root block (lanes 16..21 mirror lanes 0..5) before it is overwritten:
                                          // the shuffles above converge the warp but are no memory barrier (compute-sanitizer racecheck, r02b)
   if (lane < CH_NB) {

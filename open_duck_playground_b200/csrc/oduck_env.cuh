@@ -41,7 +41,7 @@ struct alignas(16) DevEnvCfg {
 // Reward-library parameters (include/oduck.h OduckRewardLibrary) for the RL instantiations of k_step; global memory
 struct DevRewardLib {
   float scale[ODUCK_NLIBTERM];
-  float base_height_target, max_foot_height, air_thr_min, air_thr_max;
+  float base_height_target, max_foot_height, air_thr_min, air_thr_max, swing_freq, swing_amp;
   float soft_lo[16], soft_hi[16], pose_w[16];
   unsigned hip_mask, knee_mask;       // actuator lanes
 };

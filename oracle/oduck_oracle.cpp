@@ -1415,6 +1415,15 @@ struct RewardLibrary {
   }
 };
 
+// mujoco_playground gait.get_rz(phi, swing_height) restated from upstream (not vendored in the reference): desired foot height over
+// the gait phase phi in [-pi, pi) -- cubic Bezier 0 -> h over the first half of the period, h -> 0 over the second.
+static real gait_rz(real phi, real swing_height) {
+  auto bezier = [](real y0, real y1, real x) { return y0 + (y1 - y0) * (x * x * x + 3 * (x * x * (1 - x))); };
+  const real x = (phi + (real)M_PI) / (2 * (real)M_PI);
+  return x <= (real)0.5 ? bezier(0, swing_height, 2 * x) : bezier(swing_height, 0, 2 * x - 1);
+}
+extern "C" double oduck_test_gait_rz(double phi, double swing_height) { return (double)gait_rz((real)phi, (real)swing_height); }
+
 // The library terms a task switched on through OduckEnvConfig.lib.scale (include/oduck.h), scaled and summed in enum order.
 // Inputs follow the reference's accessors: joints = the nu actuated joints (base.py:193-215), imu-site sensors
 // (base.py:234-264; global_linvel = site_xmat * local_linvel), feet sites (base.py:266-271), step-local contact /
@@ -1450,6 +1459,19 @@ static real reward_library_sum(const OduckHandle& h, const EnvState& e, const re
   t[ODUCK_LIB_FEET_CLEARANCE] = R::cost_feet_clearance(feet_vel, foot_pos, (real)L.max_foot_height);
   t[ODUCK_LIB_FEET_HEIGHT] = R::cost_feet_height(e.swing_peak, first_contact, (real)L.max_foot_height);
   t[ODUCK_LIB_FEET_AIR_TIME] = R::reward_feet_air_time(e.feet_air_time, first_contact, e.command, (real)L.air_time_threshold_min, (real)L.air_time_threshold_max);
+  {
+    // gait clock (include/oduck.h): the reference-motion phase counter after this step's increment (joystick.py:352-356)
+    const int period = h.cfg.nb_steps_in_period > 0 ? h.cfg.nb_steps_in_period : 1;
+    const real tt = (real)e.imitation_i * (real)h.cfg.ctrl_dt;
+    t[ODUCK_LIB_BASE_Y_SWING] = R::reward_base_y_swing(sd[4], (real)L.base_y_swing_freq, (real)L.base_y_swing_amplitude, tt, (real)h.cfg.tracking_sigma);
+    real rz[2];
+    for (int k = 0; k < 2; k++) {
+      real phi = 2 * (real)M_PI * (real)e.imitation_i / (real)period + (real)k * (real)M_PI;
+      phi -= 2 * (real)M_PI * std::floor((phi + (real)M_PI) / (2 * (real)M_PI));           // wrap to [-pi, pi)
+      rz[k] = gait_rz(phi, (real)L.max_foot_height);
+    }
+    t[ODUCK_LIB_FEET_PHASE] = R::reward_feet_phase(foot_pos, rz);
+  }
   real sum = 0;
   for (int k = 0; k < ODUCK_NLIBTERM; k++) if (L.scale[k] != 0) sum += t[k] * (real)L.scale[k];
   return sum;

@@ -12,7 +12,8 @@ from open_duck_playground_b200 import capi, config as config_mod, mjcf, rng as j
 from open_duck_playground_b200.joystick import Joystick, default_config
 
 LIB_SCALES = {"orientation": -1.3, "lin_vel_z": -0.7, "ang_vel_xy": -0.11, "base_height": -40.0, "energy": -0.02, "joint_pos_limits": -2.0, "termination": -3.0,
-              "joint_deviation_hip": -0.5, "joint_deviation_knee": -0.3, "pose": -0.8, "feet_slip": -0.9, "feet_clearance": -6.0, "feet_height": -1.5, "feet_air_time": 4.0}
+              "joint_deviation_hip": -0.5, "joint_deviation_knee": -0.3, "pose": -0.8, "feet_slip": -0.9, "feet_clearance": -6.0, "feet_height": -1.5, "feet_air_time": 4.0,
+              "base_y_swing": 0.6, "feet_phase": 0.9}
 
 
 def library_config():
@@ -25,6 +26,8 @@ def library_config():
     cfg.reward_config.air_time_threshold_max = 0.2
     cfg.reward_config.soft_joint_pos_limit_factor = 0.5            # tight enough for random actions to reach
     cfg.reward_config.pose_weights = [0.2 + 0.05 * i for i in range(14)]
+    cfg.reward_config.base_y_swing_freq = 2.2
+    cfg.reward_config.base_y_swing_amplitude = 0.07
     return cfg
 
 
@@ -38,7 +41,7 @@ def test_config_mapping(model_backlash):
     plain, _ = config_mod.build_env_config(model_backlash, default_config(), None, use_imitation_reward=False)
     assert all(plain.lib.scale[i] == 0.0 for i in range(len(capi.LIB_TERMS)))          # the shipped tasks use none
     bad = default_config()
-    bad.reward_config.scales["feet_phase"] = 1.0
+    bad.reward_config.scales["feet_yaw"] = 1.0
     with pytest.raises(ValueError, match="unknown term"):
         config_mod.build_env_config(model_backlash, bad, None, use_imitation_reward=False)
 
@@ -59,8 +62,12 @@ def _library_sum(oracle, env, model, pre, contact_now, done, cfg):
     pad4 = lambda a, k: np.concatenate([[k], a[:4]]).astype(np.float64)       # noqa: E731
     imu = int(A["imu_site"])
     out, sums = np.zeros(15), np.zeros(n)
-    order = ["lin_vel_z", "ang_vel_xy", "base_height", None, "energy", "joint_pos_limits", "termination", "joint_deviation_hip", "joint_deviation_knee", "pose",
-             "feet_slip", "feet_clearance", "feet_height", "feet_air_time", None]              # columns of oduck_test_reward_library
+    order = ["lin_vel_z", "ang_vel_xy", "base_height", "base_y_swing", "energy", "joint_pos_limits", "termination", "joint_deviation_hip", "joint_deviation_knee", "pose",
+             "feet_slip", "feet_clearance", "feet_height", "feet_air_time", "feet_phase"]      # columns of oduck_test_reward_library
+    rzf = oracle.lib.oduck_test_gait_rz
+    rzf.argtypes, rzf.restype = [C.c_double, C.c_double], C.c_double
+    imit = env.buffer("INFO_IMITATION_I").numpy()                   # the gait clock (include/oduck.h): phase counter after this step's increment
+    period = int(env.PRM.nb_steps_in_period)
     for i in range(n):
         # sensors belong to the last forward, i.e. to the pose BEFORE the last Euler step: undo its rotation of the base (the imu
         # site sits on the free body); global_linvel = site_xmat @ local_linvel (velocimeter = site_xmat.T @ framelinvel)
@@ -73,11 +80,13 @@ def _library_sum(oracle, env, model, pre, contact_now, done, cfg):
         air = pre["air"][i] + dt
         swing = np.maximum(pre["swing"][i], feet[i].reshape(2, 3)[:, 2])
         vec = np.concatenate([
-            glv, sd[i, 12:15], [qpos[i, 2], lib.base_height_target, 0, 0, 0, 0, 1.0], qvel[i, jd], af[i], qpos[i, jq],
+            glv, sd[i, 12:15], [qpos[i, 2], lib.base_height_target, sd[i, 4], lib.base_y_swing_freq, lib.base_y_swing_amplitude, imit[i] * dt, float(cfg.reward_config.tracking_sigma)],
+            qvel[i, jd], af[i], qpos[i, jq],
             [lib.soft_lowers[u] for u in range(nu)], [lib.soft_uppers[u] for u in range(nu)], [done[i]], cmd[i], model.key_ctrl[:nu],
             pad4(np.array(list(lib.hip_indices), float), lib.n_hip), pad4(np.array(list(lib.knee_indices), float), lib.n_knee),
             [lib.pose_weights[u] for u in range(nu)], contact_now[i], sd[i, 15:21], feet[i], [lib.max_foot_height], swing, first.astype(float), air,
-            [lib.air_time_threshold_min, lib.air_time_threshold_max], [0, 0]])
+            [lib.air_time_threshold_min, lib.air_time_threshold_max],
+            [rzf(((2 * np.pi * imit[i] / period + k * np.pi + np.pi) % (2 * np.pi)) - np.pi, lib.max_foot_height) for k in range(2)]])
         oracle.check(fn(nu, vec.ctypes.data, out.ctypes.data))
         s = LIB_SCALES["orientation"] * (sd[i, 9] ** 2 + sd[i, 10] ** 2)
         for col, name in enumerate(order):

@@ -115,22 +115,3 @@ def test_emulated_foot_foot_path(emu, oracle, model_backlash, poly_table):
     assert hit.sum() >= 3                                               # the rare path is exercised
     ok = _check(got, ref, min_ok=0.9)
     assert ok[hit].mean() >= 0.75
-
-
-@pytest.mark.parametrize("flag", ["-DODUCK_CHOL_LDL"])
-def test_prepared_variants(emu, oracle, poly_table, flag):
-    """The kernel variants kept behind compile-time flags for A/B runs on the GPU box pass the same comparison,
-    and the result-preserving ones reproduce the default build's numbers."""
-    var = load_emu("step_emu_" + flag[3:].lower(), (flag,))
-    model = CompiledModel.load(constants.task_to_blob("rough_terrain_backlash"))
-    got, ref = _run_pair(var, oracle, model, poly_table, n=12, nsub=5, seed=400)
-    _check(got, ref, min_ok=0.8)
-    base, _ = _run_pair(emu, oracle, model, poly_table, n=12, nsub=5, seed=400)
-    assert np.abs(got["QVEL"] - base["QVEL"]).max(axis=1).mean() < 1e-3   # same algorithm, other rounding
-
-
-def test_prepared_variants_combined(oracle, model_backlash, poly_table):
-    """The square-root-free chain factorisation on top of the default build (unrolled symv), flat floor, one control step."""
-    var = load_emu("step_emu_ldl", ("-DODUCK_CHOL_LDL",))
-    got, ref = _run_pair(var, oracle, model_backlash, poly_table, n=16, nsub=10, seed=500)
-    _check(got, ref, min_ok=0.9)
