@@ -27,7 +27,8 @@ every unroll boundary (where a PPO update would sit) and at the end of the timed
              (oracle/mujoco_ref.py: kind "reference"); otherwise -- this image has none -- the C++ oracle port (fp32,
              -O3 -march=native, std::thread over envs: kind "port") on this box's host cores, at the FULL config (4096 envs
              per GPU), same step (actor + env.step).
-Extra keys (BASELINE configs[1] literal, [2], [3]): ``physics_only_env_steps_per_s``, ``ppo_env_steps_per_s``,
+Extra keys (BASELINE configs[1] literal, [2], [3]): ``physics_only_env_steps_per_s``, ``ppo_env_steps_per_s`` (fp32-faithful learner
+GEMMs) and ``ppo_tf32_env_steps_per_s`` (learner GEMMs at XLA's default f32 precision on NVIDIA GPUs, the reference's),
 ``rough_env_steps_per_s`` -- short legs after the headline's timed region (``--no-extra`` skips them).
 """
 import argparse
@@ -232,23 +233,6 @@ def capture_graph(stream, pool, fn):
     return g
 
 
-class RolloutBuffers:
-    """One flat fp32 allocation holding a rank's rollout buffers (so that the exchange of SURVEY 8e is ONE all-gather), with the
-    per-field views ``ppo.attach_rollout_sink`` takes."""
-
-    def __init__(self, n, dev, T=UNROLL, dp=101, dv=212, na=14):
-        import torch
-        sizes = [("obs_p", (T + 1, n, dp)), ("obs_v", (T + 1, n, dv)), ("raw", (T, n, na)), ("logp", (T, n)), ("reward", (T, n)), ("done", (T, n)), ("trunc", (T, n))]
-        total = sum(int(np.prod(s)) for _, s in sizes)
-        self.flat = torch.zeros(total, device=dev)
-        self.views, off = {}, 0
-        for k, s in sizes:
-            cnt = int(np.prod(s))
-            self.views[k] = self.flat[off:off + cnt].view(*s)
-            off += cnt
-        self.bytes = total * 4
-
-
 # ----------------------------------------------------------------------------------------------------- legs
 def leg_physics(args, rank, world, dev, steps=None):
     """SURVEY 8d config 2 read literally: ``mjx_env.step(model, data, ctrl, 10)`` alone -- ``oduck_physics_substeps(n = 10)`` with
@@ -310,9 +294,9 @@ def leg_rough(args, rank, world, dev, total_envs=16384, steps=20):
     torch.manual_seed(0)
     weights = ppo.PolicyWeights(ppo.MLP([101, 512, 256, 128, 28]).to(dev), 101, dev)
     keys = [torch.from_numpy(jr.split(jr.PRNGKey(2000 + k), world * n)[rank * n:(rank + 1) * n].view(np.int32).copy()).to(dev) for k in range(4)]
-    roll = RolloutBuffers(n, dev)
+    roll = ppo.RolloutBuffers(UNROLL, n, 101, 212, 14, dev)
     for e in envs:
-        ppo.attach_rollout_sink(e, roll.views, 0)
+        ppo.attach_rollout_sink(e, roll, 0)
 
     def step(k):
         ppo.rollout_step(envs[k % n_sets], weights, keys[k % 4], k % UNROLL)
@@ -392,11 +376,11 @@ def run_rollout(args, rank, world, dev, local):
     keys = [torch.from_numpy(jr.split(jr.PRNGKey(1000 + k), world * n)[rank * n:(rank + 1) * n].view(np.int32).copy()).to(dev) for k in range(n_keys)]   # resident in HBM
     host_keys = [k.cpu().pin_memory() for k in keys]
     key_static = torch.empty_like(keys[0])
-    roll = RolloutBuffers(n, dev)                                        # the rank's rollout buffers: the kernels write them
+    roll = ppo.RolloutBuffers(UNROLL, n, 101, 212, 14, dev)              # the rank's rollout buffers: the kernels write them
     gathered = torch.empty(world * roll.flat.numel(), device=dev) if world > 1 else None
     for row in envs:
         for q, e in enumerate(row):
-            ppo.attach_rollout_sink(e, roll.views, q * m)
+            ppo.attach_rollout_sink(e, roll, q * m)
     streams = [torch.cuda.Stream(device=dev) for _ in range(P)]
     main = torch.cuda.current_stream(dev)
 
@@ -693,6 +677,7 @@ def main():
         # BASELINE configs[1] literal, [2], [3] as extra keys of the one line (short legs, all ranks take part)
         for key, fn in (("physics_only", lambda: leg_physics(args, rank, world, dev, steps=30)),
                         ("ppo", lambda: leg_ppo(args, rank, world, dev)),
+                        ("ppo_tf32", lambda: leg_ppo(args, rank, world, dev, steps=2, warmup=1, matmul="tf32")),
                         ("rough", lambda: leg_rough(args, rank, world, dev, total_envs=args.rough_envs))):
             try:
                 torch.cuda.empty_cache()

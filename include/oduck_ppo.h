@@ -61,6 +61,12 @@ typedef struct OduckRollout {
   const float* reward;          /* [T][N] */
   const float* done;            /* [T][N]       1 - discount */
   const float* truncation;      /* [T][N] */
+  /* Blocked layout (the buffer one NCCL all-gather leaves behind): the N envs come as N / block_envs blocks of
+   * block_envs envs, block b = one rank's rollout buffers, every field [T(+1)][block_envs][...] inside it, the blocks
+   * block_stride floats apart; the pointers above address block 0.  Env e of field f at time t:
+   * f + (e / block_envs) * block_stride + (t * block_envs + e % block_envs) * width.  block_envs = 0: one block of N envs. */
+  int32_t block_envs;
+  int64_t block_stride;
 } OduckRollout;
 
 /* Observation normaliser (brax running_statistics): obs_n = (obs - mean) / std per feature. */

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(WPB * 32, CTAS_PER_SM) k_physics(Params p) {
   WarpSmem& s = ws[warp];
   for (int env0 = blockIdx.x * WPB; env0 < p.N; env0 += gridDim.x * WPB) {
     const int env = env0 + warp;
-    if (env >= p.N) { if (!DBG) substep_idle_barriers(p.nsub); continue; }     // the CTA's other warps synchronise inside the substeps
+    if (env >= p.N) { if (!DBG) substep_idle_barriers<HF>(p.nsub); continue; }     // the CTA's other warps synchronise inside the substeps
     Lane L;
     float* ph = p.phys + (size_t)env * PHYS_STRIDE;
     load_env(m, s, L, lane, ph, p.dr + (size_t)env * DR_STRIDE);
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(WPB * 32, CTAS_PER_SM) k_step(Params p) {
   const float PI = 3.14159265358979323846f;
   for (int env0 = blockIdx.x * WPB; env0 < p.N; env0 += gridDim.x * WPB) {
     const int env = env0 + warp;
-    if (env >= p.N) { substep_idle_barriers(c.n_substeps); continue; }   // the CTA's other warps synchronise inside the substeps
+    if (env >= p.N) { substep_idle_barriers<HF>(c.n_substeps); continue; }   // the CTA's other warps synchronise inside the substeps
     Lane L;
     float* ph = p.phys + (size_t)env * PHYS_STRIDE;
     load_env(m, s, L, lane, ph, p.dr + (size_t)env * DR_STRIDE);

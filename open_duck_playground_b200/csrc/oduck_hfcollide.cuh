@@ -17,10 +17,17 @@ struct DevHF {   // global memory
 #define HF_CAP 512             // candidates kept per foot (the oracle keeps as many; a resting foot has a few dozen)
 #define HF_REC 8               // dist, pos[3], normal[3], twin flag
 #define HF_SCRATCH (HF_CAP * HF_REC)
+#define HF_MARGIN 2e-5f        // box-cull slack: 20 ulp of a 10 m coordinate (the field is 20 m wide); a 1e-6 slack culled faces that the
+                               // fp64 oracle clips to a sliver at |x| ~ 9 m
 #define HF_MAXP 11             // 8-gon clipped by 3 half-planes: at most 11 vertices
 #define HF_LANES 13            // (triangle, face) pairs clipped per round: one 33-float polygon per lane in shared memory
 #define HF_MAXPAIR 64          // pair list of a batch (the rhs + rowbuf rows of WarpSmem)
-#define HF_TWIN 1e-5f          // clipped points closer than this (max-norm) are copies of one point on a shared triangle edge
+#ifdef ODUCK_HF_NO_TWIN
+#define HF_TWIN -1.f
+#else
+#define HF_TWIN 1e-5f
+#endif
+//         // clipped points closer than this (max-norm) are copies of one point on a shared triangle edge
 
 // Sutherland-Hodgman IN PLACE: keep the part of the polygon P[cnt][3] on the inner side (d <= 0) of the vertical plane through
 // r0 with outward normal (sdx, sdy).  One buffer suffices because an output slot never overtakes the input: the vertex after
@@ -56,7 +63,7 @@ __device__ __forceinline__ int hf_clip(float* __restrict__ P, const int cnt, con
 // lane = hull face decides whether its face looks down onto the triangle and overlaps its cell, and the surviving (triangle,
 // face) pairs are appended to a list in shared memory -- cells the hull's box misses and triangles wholly below its lowest
 // vertex are skipped (a candidate needs a hull point BELOW the triangle plane, which never rises above the triangle's top;
-// 1e-6 m margins keep the culls conservative under fp32 rounding).  (2) The pairs are clipped HF_LANES at a time, lane =
+// HF_MARGIN keeps the culls conservative under fp32 rounding).  (2) The pairs are clipped HF_LANES at a time, lane =
 // pair, each lane in its own shared-memory polygon; clipped points below the triangle plane are appended to the env's
 // candidate list in the oracle's order (triangle, face, polygon vertex) with a warp prefix sum.  (3) Twins are masked and the
 // manifold is selected over the list 32 candidates at a time with the plane collider's first-index arg-max.
@@ -85,16 +92,18 @@ static __device__ __noinline__ void hf_collide(const DevModel& m, const DevFF* _
   float* poly = s.H + 96 + 3 * HF_MAXP * (lane < HF_LANES ? lane : 0);    // this lane's polygon
   int* wp = reinterpret_cast<int*>(s.rhs);                               // pair list: (cell * 2 + half) << 5 | face
   float hx0, hx1, hy0, hy1, hz0;                                          // box of the hull
+  const bool vv = lane < m.nvert;                                         // lane = hull vertex (world position wl kept for the plane-side cull)
+  V3 wl;
   {
-    const bool vv = lane < m.nvert;
     const int vl = vv ? lane : 0;
     const V3 w = p0 + rot(v3(m.vert[f][0][vl], m.vert[f][1][vl], m.vert[f][2][vl]));
+    wl = w;
     __syncwarp();                                                         // (H's previous readers are done)
     if (vv) { wv[3 * lane] = w.x; wv[3 * lane + 1] = w.y; wv[3 * lane + 2] = w.z; }
     const float inf = __int_as_float(0x7f800000);
-    hx1 = wmaxf(vv ? w.x : -inf) + 1e-6f; hx0 = -wmaxf(vv ? -w.x : -inf) - 1e-6f;
-    hy1 = wmaxf(vv ? w.y : -inf) + 1e-6f; hy0 = -wmaxf(vv ? -w.y : -inf) - 1e-6f;
-    hz0 = -wmaxf(vv ? -w.z : -inf) - 1e-6f;
+    hx1 = wmaxf(vv ? w.x : -inf) + HF_MARGIN; hx0 = -wmaxf(vv ? -w.x : -inf) - HF_MARGIN;
+    hy1 = wmaxf(vv ? w.y : -inf) + HF_MARGIN; hy0 = -wmaxf(vv ? -w.y : -inf) - HF_MARGIN;
+    hz0 = -wmaxf(vv ? -w.z : -inf) - HF_MARGIN;
   }
   __syncwarp();
   // this lane's face: world normal and xy box
@@ -102,15 +111,17 @@ static __device__ __noinline__ void hf_collide(const DevModel& m, const DevFF* _
   const int q = has ? lane : 0;
   const V3 Nw = rot(v3(ff->plane_normal[f][0][q], ff->plane_normal[f][1][q], ff->plane_normal[f][2][q]));
   float gx0 = 0.f, gx1 = 0.f, gy0 = 0.f, gy1 = 0.f;
+  unsigned fmask = 0u;                                                    // this face's vertices as a bit mask over the hull vertices
   if (has) {
     const int cnt0 = ff->plane_nvert[q];
     for (int v = 0; v < cnt0; ++v) {
       const int vid = ff->plane_vert[q][v];
+      fmask |= 1u << vid;
       const float x = wv[3 * vid], y = wv[3 * vid + 1];
       if (v == 0) { gx0 = gx1 = x; gy0 = gy1 = y; }
       else { gx0 = fminf(gx0, x); gx1 = fmaxf(gx1, x); gy0 = fminf(gy0, y); gy1 = fmaxf(gy1, y); }
     }
-    gx0 -= 1e-6f; gx1 += 1e-6f; gy0 -= 1e-6f; gy1 += 1e-6f;
+    gx0 -= HF_MARGIN; gx1 += HF_MARGIN; gy0 -= HF_MARGIN; gy1 += HF_MARGIN;
   }
   int nc = 0;                      // candidates so far (warp-uniform)
   V3 nsum = v3(0.f, 0.f, 0.f);     // sum of the candidates' normals (warp-uniform)
@@ -192,7 +203,12 @@ static __device__ __noinline__ void hf_collide(const DevModel& m, const DevFF* _
         if (C.z - rb > top || hz0 > top) continue;                      // warp-uniform: the hull is above this triangle
         V3 n = cross(T1 - T0, T2 - T0);
         n = (1.f / sqrtf(dot(n, n))) * n;
-        const bool act = has && dot(Nw, n) < 0.f && !(x1 < gx0 || x0 > gx1 || y1 < gy0 || y0 > gy1);   // the face looks down onto the triangle
+        // plane-side cull: a clipped point is a convex combination of its face's vertices, so a face none of whose vertices lies
+        // below the triangle's plane (HF_MARGIN slack) yields no candidate.  Lane = hull vertex tests ITS vertex, one ballot hands
+        // every face lane the set; a swing foot drops out here entirely, a resting one keeps the faces around its sole.
+        const unsigned below = __ballot_sync(FULLMASK, vv && dot(n, wl - T0) < HF_MARGIN);
+        if (!below) continue;                                           // warp-uniform
+        const bool act = has && (fmask & below) != 0u && dot(Nw, n) < 0.f && !(x1 < gx0 || x0 > gx1 || y1 < gy0 || y0 > gy1);   // the face looks down onto the triangle
         const unsigned bm = __ballot_sync(FULLMASK, act);
         if (!bm) continue;                                              // warp-uniform
         if (np + __popc(bm) > HF_MAXPAIR) flush();

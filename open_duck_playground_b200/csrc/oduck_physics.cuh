@@ -30,9 +30,17 @@ struct LSPoint { float alpha, d0, d1; };
 #ifndef ODUCK_PHASE_MARK
 #define ODUCK_PHASE_MARK(bit)      // tests/emu counts warp exchanges per phase through this hook
 #endif
-#define PHASE_SYNC(bit, pre_exit) { ODUCK_PHASE_MARK(bit) if (BAR && ((ODUCK_BARRIERS >> (bit)) & 1) && (!(pre_exit) || !FF)) __syncthreads(); }
+// Height-field instantiations: the collider's work varies from warp to warp (a swing foot costs nothing, a foot lying on a cell
+// border clips dozens of pairs), so a CTA barrier makes seven warps wait for the slowest one every substep (ncu r02d: 20 % of
+// k_step<HF>'s stall samples); ODUCK_HF_BARRIERS selects the barrier points of those instantiations separately (A/B on B200).
+#ifndef ODUCK_HF_BARRIERS
+#define ODUCK_HF_BARRIERS ODUCK_BARRIERS
+#endif
+#define PHASE_MASK (HF ? (ODUCK_HF_BARRIERS) : (ODUCK_BARRIERS))
+#define PHASE_SYNC(bit, pre_exit) { ODUCK_PHASE_MARK(bit) if (BAR && ((PHASE_MASK >> (bit)) & 1) && (!(pre_exit) || !FF)) __syncthreads(); }
+template <bool HF>
 __device__ __forceinline__ void substep_idle_barriers(int substeps) {
-  for (int k = 0; k < substeps * __popc(ODUCK_BARRIERS & 0x3f); ++k) __syncthreads();
+  for (int k = 0; k < substeps * __popc(PHASE_MASK & 0x3f); ++k) __syncthreads();
 }
 
 // root-to-leaf sweep after chol_rev_tree: table-free on the chain plans, level-parallel with the ancestor table otherwise

@@ -88,10 +88,15 @@ struct OduckPpo {
 };
 
 // ------------------------------------------------------------------------------------------------- kernels
+// float offset of (time t, env e) in a rollout field whose rows are `width` floats wide (blocked layout: include/oduck_ppo.h)
+__device__ __forceinline__ size_t ro_off(const int be, const long long bstride, const int t, const int e, const int width) {
+  const int blk = e / be, el = e - blk * be;
+  return (size_t)blk * (size_t)bstride + ((size_t)t * be + el) * width;
+}
 // Gather the minibatch rows (row = t * B + b <- env idx[b] at time t), normalise, emit R(X) and R(X^T).
 // One thread per 4 x 4 micro-tile (4 rows x 4 features): both layouts keep 4 consecutive k (R(X)) / 4 consecutive rows
 // (R(X^T)) contiguous, so every store is a float4.
-__global__ void k_ppo_pack(const float* __restrict__ obs, int N, int K, const int* __restrict__ idx, int B, int M, int Mpad, int kch,
+__global__ void k_ppo_pack(const float* __restrict__ obs, int be, long long bstride, int K, const int* __restrict__ idx, int B, int M, int Mpad, int kch,
                            const float* __restrict__ mean, const float* __restrict__ stdv, float* __restrict__ Xr, float* __restrict__ Xt) {
   const int K4 = kch * (TC_KC / 4), ytn = Mpad / TC_KC;
   const int total = (Mpad / 4) * K4;
@@ -103,7 +108,7 @@ __global__ void k_ppo_pack(const float* __restrict__ obs, int N, int K, const in
     for (int a = 0; a < 4; ++a) {
       const int row = row0 + a;
       const float* src = nullptr;
-      if (row < M) { const int t = row / B, b = row - t * B; src = obs + ((size_t)t * N + idx[b]) * K; }
+      if (row < M) { const int t = row / B, b = row - t * B; src = obs + ro_off(be, bstride, t, idx[b], K); }
 #pragma unroll
       for (int e = 0; e < 4; ++e) { const int k = k0 + e; v[a][e] = (src && k < K) ? (src[k] - mean[k]) / stdv[k] : 0.f; }
     }
@@ -155,14 +160,14 @@ __global__ void __launch_bounds__(GAE_THREADS) k_ppo_gae(const float* __restrict
                                                          float discount, float lambda, float reward_scaling, float* __restrict__ adv, float* __restrict__ vs,
                                                          double* __restrict__ stats /*[4 + 2 * gridDim.x]*/, int* __restrict__ ticket, double* __restrict__ losses) {
   if (blockIdx.x == 0 && threadIdx.x < 8) losses[threadIdx.x] = 0.0;
-  const int N = ro.num_envs;
+  const int be = ro.block_envs > 0 ? ro.block_envs : ro.num_envs;
   const int b = blockIdx.x * GAE_THREADS + threadIdx.x;
   double s1 = 0.0, s2 = 0.0;
   if (b < B) {
     const int env = idx[b];
     float lv[PPO_MAXT + 1], lr[PPO_MAXT], ld[PPO_MAXT], lt[PPO_MAXT];
     for (int t = 0; t < T; ++t) {
-      const size_t g = (size_t)t * N + env;
+      const size_t g = ro_off(be, ro.block_stride, t, env, 1);
       lv[t] = values[(size_t)(t * B + b) * PPO_HEADW];
       lr[t] = ro.reward[g]; ld[t] = ro.done[g]; lt[t] = ro.truncation[g];
     }
@@ -247,7 +252,9 @@ __global__ void __launch_bounds__(LOSS_ROWS * 16) k_ppo_loss(LossParams p) {
   float g_loc = 0.f, g_sc = 0.f;
   if (r < p.Mp) {
     const int t = r / p.B, b = r - t * p.B;
-    const size_t gi = (size_t)t * p.ro.num_envs + p.idx[b];
+    const int be = p.ro.block_envs > 0 ? p.ro.block_envs : p.ro.num_envs;
+    const size_t gi = ro_off(be, p.ro.block_stride, t, p.idx[b], 1);
+    const size_t ga = ro_off(be, p.ro.block_stride, t, p.idx[b], p.na);
     const float* lg = p.logits + (size_t)r * PPO_HEADW;
     float A = p.adv[r];
     if (p.normalize) A = (A - (float)p.stats[0]) / ((float)p.stats[1] + 1e-8f);
@@ -256,7 +263,7 @@ __global__ void __launch_bounds__(LOSS_ROWS * 16) k_ppo_loss(LossParams p) {
     if (a < p.na) {
       const float loc = lg[a], sp = lg[p.na + a];
       const float scale = softplusf(sp) + 0.001f;
-      const float raw = p.ro.raw_action[gi * p.na + a];
+      const float raw = p.ro.raw_action[ga + a];
       const float zz = (raw - loc) / scale;
       logp = -0.5f * zz * zz - logf(scale) - 0.91893853320467f - 2.f * (0.69314718056f - raw - softplusf(-2.f * raw));
       float eps;
@@ -883,6 +890,8 @@ int oduck_ppo_minibatch(OduckPpo* h, const OduckRollout* ro, const OduckNormaliz
                         const uint32_t* key, int stages, void* stream) {
   if (!h || !ro || !nm || !env_idx) return oduck_fail(ODUCK_ERR_ARG, "oduck_ppo_minibatch: bad argument");
   if (ro->unroll != h->T || ro->num_envs < 1) return oduck_fail(ODUCK_ERR_ARG, "oduck_ppo_minibatch: rollout shape does not match the learner");
+  if (ro->block_envs < 0 || (ro->block_envs > 0 && ro->num_envs % ro->block_envs)) return oduck_fail(ODUCK_ERR_ARG, "oduck_ppo_minibatch: num_envs must be a multiple of block_envs");
+  const int be = ro->block_envs > 0 ? ro->block_envs : ro->num_envs;
   if ((stages & ODUCK_PPO_STAGE_LOSS) && !noise && !key) return oduck_fail(ODUCK_ERR_ARG, "oduck_ppo_minibatch: entropy term needs noise or a key");
   PPO_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
@@ -896,11 +905,11 @@ int oduck_ppo_minibatch(OduckPpo* h, const OduckRollout* ro, const OduckNormaliz
 #define JOIN() { PPO_TRY(cudaEventRecord(h->ev_join, h->side)); PPO_TRY(cudaStreamWaitEvent(st, h->ev_join, 0)); }
   if (stages & ODUCK_PPO_STAGE_FORWARD) {
     FORK()
-    k_ppo_pack<<<296, 256, 0, h->side>>>(ro->obs_value, ro->num_envs, nv.dims[0], env_idx, h->B, nv.M, nv.Mpad, ceil_div(nv.dims[0], TC_KC), nm->value_mean, nm->value_std, nv.Xr[0], nv.Xt[0]);
+    k_ppo_pack<<<296, 256, 0, h->side>>>(ro->obs_value, be, ro->block_stride, nv.dims[0], env_idx, h->B, nv.M, nv.Mpad, ceil_div(nv.dims[0], TC_KC), nm->value_mean, nm->value_std, nv.Xr[0], nv.Xt[0]);
     GEMM_TRY(cudaGetLastError());
     int rc = net_forward(h, 1, simt, h->side);
     if (rc) return rc;
-    k_ppo_pack<<<296, 256, 0, st>>>(ro->obs_policy, ro->num_envs, np.dims[0], env_idx, h->B, np.M, np.Mpad, ceil_div(np.dims[0], TC_KC), nm->policy_mean, nm->policy_std, np.Xr[0], np.Xt[0]);
+    k_ppo_pack<<<296, 256, 0, st>>>(ro->obs_policy, be, ro->block_stride, np.dims[0], env_idx, h->B, np.M, np.Mpad, ceil_div(np.dims[0], TC_KC), nm->policy_mean, nm->policy_std, np.Xr[0], np.Xt[0]);
     GEMM_TRY(cudaGetLastError());
     rc = net_forward(h, 0, simt, st);
     if (rc) return rc;

@@ -247,17 +247,73 @@ def shard_keys(seed: int, world: int, rank: int, n_per_rank: int) -> np.ndarray:
     return jr.split(jr.PRNGKey(seed), world * n_per_rank)[rank * n_per_rank:(rank + 1) * n_per_rank]
 
 
-def all_gather_rollout(batch: Dict[str, torch.Tensor], world: int) -> Dict[str, torch.Tensor]:
-    """The one exchange of a training step: every rank contributes its env shard ([T, n, ...] -> [T, world * n, ...])."""
+class RolloutBuffers(dict):
+    """A rank's rollout buffers ([T(+1), n, ...] per field, time-major like Brax's stacked Transition) as views of ONE flat fp32
+    allocation, so that the exchange of SURVEY.md 8e is one ``all_gather_into_tensor`` of ``flat`` and nothing is packed."""
+
+    FIELDS = ("obs_p", "obs_v", "raw", "logp", "reward", "done", "trunc")
+
+    def __init__(self, T: int, n: int, dp: int, dv: int, na: int, device):
+        shapes = {"obs_p": (T + 1, n, dp), "obs_v": (T + 1, n, dv), "raw": (T, n, na), "logp": (T, n), "reward": (T, n), "done": (T, n), "trunc": (T, n)}
+        total = sum(int(np.prod(sh)) for sh in shapes.values())
+        self.flat = torch.zeros(total, device=device)
+        self.offsets, off = {}, 0
+        super().__init__()
+        for k in self.FIELDS:
+            cnt = int(np.prod(shapes[k]))
+            self[k] = self.flat[off:off + cnt].view(*shapes[k])
+            self.offsets[k] = (off, shapes[k])
+            off += cnt
+        self.bytes = total * 4
+        self.T, self.n = T, n
+
+
+class GatheredRollout:
+    """What one all-gather of every rank's ``RolloutBuffers.flat`` leaves behind: ``world`` blocks, block r = rank r's buffers.
+    The device learner reads it in place (OduckRollout.block_envs / block_stride); ``[key]`` builds the time-major
+    [T, world * n, ...] tensor of a field on demand (PyTorch twin learner, scalar summaries)."""
+
+    def __init__(self, gathered: torch.Tensor, local: RolloutBuffers, world: int):
+        self.flat, self.local, self.world = gathered, local, world
+        self.block_stride = local.flat.numel()
+        self._cache: Dict[str, torch.Tensor] = {}
+
+    def blocks(self, key: str) -> torch.Tensor:
+        """[world, T(+1), n, ...] view of a field."""
+        off, shape = self.local.offsets[key]
+        cnt = int(np.prod(shape))
+        return self.flat.view(self.world, self.block_stride)[:, off:off + cnt].view(self.world, *shape)
+
+    def __getitem__(self, key: str) -> torch.Tensor:
+        if key not in self._cache:
+            b = self.blocks(key)                                        # [world, T, n, ...] -> [T, world * n, ...]
+            self._cache[key] = b.transpose(0, 1).reshape(b.shape[1], self.world * b.shape[2], *b.shape[3:]).contiguous()
+        return self._cache[key]
+
+    def keys(self):
+        return self.local.keys()
+
+    def items(self):
+        return ((k, self[k]) for k in self.local.keys())
+
+
+def all_gather_rollout(batch, world: int, out: Optional[torch.Tensor] = None):
+    """The one exchange of a training step: every rank contributes its env shard.  ``RolloutBuffers`` are gathered
+    with ONE collective on their flat allocation and stay in rank-major blocks (``GatheredRollout``); a plain dict of tensors is
+    gathered field by field into [T, world * n, ...]."""
     if world == 1:
         return batch
-    out = {}
+    if isinstance(batch, RolloutBuffers):
+        g = out if out is not None else torch.empty(world * batch.flat.numel(), device=batch.flat.device)
+        dist.all_gather_into_tensor(g, batch.flat)
+        return GatheredRollout(g, batch, world)
+    res = {}
     for k, v in batch.items():
         v = v.contiguous()
         parts = [torch.empty_like(v) for _ in range(world)]
         dist.all_gather(parts, v)
-        out[k] = torch.cat(parts, dim=1)
-    return out
+        res[k] = torch.cat(parts, dim=1)
+    return res
 
 
 class DeviceLearner:
@@ -326,16 +382,24 @@ class DeviceLearner:
         self.h.minibatch(rollout, norm, env_idx, noise, key, stages, self._stream())
 
 
-def rollout_struct(batch: Dict[str, torch.Tensor]) -> "capi.OduckRollout":
-    """OduckRollout over the trainer's rollout dict (tensors must stay alive while the learner runs)."""
-    T, N = batch["reward"].shape
-    for k, v in batch.items():
-        if not v.is_contiguous() or v.dtype != torch.float32:
-            raise ValueError(f"rollout tensor {k} must be contiguous float32")
+def rollout_struct(batch) -> "capi.OduckRollout":
+    """OduckRollout over the trainer's rollout buffers -- a dict of [T(+1), N, ...] tensors, or a ``GatheredRollout`` read in place
+    as rank-major blocks (tensors must stay alive while the learner runs)."""
     ro = capi.OduckRollout()
-    ro.num_envs, ro.unroll = int(N), int(T)
-    ro.obs_policy, ro.obs_value, ro.raw_action = batch["obs_p"].data_ptr(), batch["obs_v"].data_ptr(), batch["raw"].data_ptr()
-    ro.log_prob, ro.reward, ro.done, ro.truncation = batch["logp"].data_ptr(), batch["reward"].data_ptr(), batch["done"].data_ptr(), batch["trunc"].data_ptr()
+    if isinstance(batch, GatheredRollout):
+        src = batch.local
+        T, n = src["reward"].shape
+        ro.num_envs, ro.unroll, ro.block_envs, ro.block_stride = int(batch.world * n), int(T), int(n), int(batch.block_stride)
+        ptr = lambda k: batch.flat.data_ptr() + 4 * src.offsets[k][0]                    # noqa: E731  (block 0's field)
+    else:
+        T, N = batch["reward"].shape
+        for k, v in batch.items():
+            if not v.is_contiguous() or v.dtype != torch.float32:
+                raise ValueError(f"rollout tensor {k} must be contiguous float32")
+        ro.num_envs, ro.unroll, ro.block_envs, ro.block_stride = int(N), int(T), 0, 0
+        ptr = lambda k: batch[k].data_ptr()                                               # noqa: E731
+    ro.obs_policy, ro.obs_value, ro.raw_action = ptr("obs_p"), ptr("obs_v"), ptr("raw")
+    ro.log_prob, ro.reward, ro.done, ro.truncation = ptr("logp"), ptr("reward"), ptr("done"), ptr("trunc")
     return ro
 
 
@@ -444,13 +508,10 @@ class PPOTrainer:
         step_keys = jr.split(sub, T)
         return np.ascontiguousarray(jr.split(step_keys, self.world * n)[:, self.rank * n:(self.rank + 1) * n]).view(np.int32)
 
-    def _new_buffers(self) -> Dict[str, torch.Tensor]:
+    def _new_buffers(self) -> RolloutBuffers:
         cfg, env = self.cfg, self.env
-        T, n, dev = cfg.unroll_length, self.n_local, env.device
-        pk, vk = cfg.policy_obs_key, cfg.value_obs_key
-        return {"obs_p": torch.empty(T + 1, n, env.observation_size[pk][0], device=dev), "obs_v": torch.empty(T + 1, n, env.observation_size[vk][0], device=dev),
-                "raw": torch.empty(T, n, env.action_size, device=dev), "logp": torch.empty(T, n, device=dev), "reward": torch.empty(T, n, device=dev),
-                "done": torch.empty(T, n, device=dev), "trunc": torch.empty(T, n, device=dev)}
+        return RolloutBuffers(cfg.unroll_length, self.n_local, env.observation_size[cfg.policy_obs_key][0], env.observation_size[cfg.value_obs_key][0],
+                              env.action_size, env.device)
 
     def _attach(self, buf) -> None:
         if self._sink_buf is not buf:
@@ -683,11 +744,16 @@ class PPOTrainer:
         gradients are averaged over ranks (Brax's pmean); otherwise ``batch`` is the gathered global batch and every rank does the same update."""
         cfg = self.cfg
         pk, vk = cfg.policy_obs_key, cfg.value_obs_key
+        blocked = isinstance(batch, GatheredRollout)
         if cfg.normalize_observations:
-            self.stats[pk].update(batch["obs_p"][:-1], reduce=sharded); self.stats[vk].update(batch["obs_v"][:-1], reduce=sharded)
+            if blocked and self.dev_learner is not None:          # [world, T + 1, n, d]: the same rows, rank-major (the moments are sums over rows;
+                                                                  # the PyTorch twin keeps the time-major order = the single-process bits)
+                self.stats[pk].update(batch.blocks("obs_p")[:, :-1], reduce=False); self.stats[vk].update(batch.blocks("obs_v")[:, :-1], reduce=False)
+            else:
+                self.stats[pk].update(batch["obs_p"][:-1], reduce=sharded); self.stats[vk].update(batch["obs_v"][:-1], reduce=sharded)
         for k in (pk, vk):
             self._mean32[k].copy_(self.stats[k].mean32)
-        T, N = batch["reward"].shape
+        T, N = (batch.local["reward"].shape[0], batch.world * batch.local["reward"].shape[1]) if blocked else batch["reward"].shape
         gen = torch.Generator(device="cpu").manual_seed(cfg.seed + self.env_steps + (self.rank if sharded else 0))
         if self.dev_learner is not None:
             return self._update_device(batch, sharded, gen)
@@ -730,7 +796,8 @@ class PPOTrainer:
         """The update through include/oduck_ppo.h: one library call per minibatch, no host sync until the metrics are read."""
         cfg, L = self.cfg, self.dev_learner
         pk, vk = cfg.policy_obs_key, cfg.value_obs_key
-        T, N = batch["reward"].shape
+        blocked = isinstance(batch, GatheredRollout)
+        T, N = (batch.local["reward"].shape[0], batch.world * batch.local["reward"].shape[1]) if blocked else batch["reward"].shape
         B = N // cfg.num_minibatches
         if B != L.batch_envs:
             raise ValueError(f"device learner was built for {L.batch_envs} envs per minibatch, got {B}")
@@ -751,29 +818,26 @@ class PPOTrainer:
         # The minibatch step reads a static index / key buffer and is captured once into CUDA graphs (the library forks and
         # joins its side streams inside the capture); a minibatch is then two small copies + one replay (two around the
         # gradient all-reduce when sharded).  Only with the persistent rollout buffers of the graphed unroll (static pointers).
-        graphed = cfg.cuda_graph and self._roll is not None and batch is self._roll["buf"]
+        graphed = cfg.cuda_graph and self._roll is not None and (batch is self._roll["buf"] or (blocked and batch.local is self._roll["buf"] and batch.flat is self._roll.get("gathered")))
         if graphed and getattr(self, "_upd", None) is None:
             U = {"idx": torch.zeros(B, dtype=torch.int32, device=dev), "key": torch.zeros(2, dtype=torch.int32, device=dev), "ro": ro, "nm": nm}
-            # single GPU: the fused cooperative reduce + clip + Adam launch as a graph node (a kernel node with the cooperative
-            # attribute); if this driver / runtime cannot capture it, the two-kernel tail (plain kernel nodes)
-            variants = [[FLB, capi.PPO_STAGE_ADAM]] if sharded else [[capi.PPO_ALL], [capi.PPO_ALL | capi.PPO_NO_COOP]]
-            U["graphs"], U["coop_in_graph"] = None, False
-            for stages in variants:
-                try:
-                    L.minibatch(ro, nm, U["idx"].data_ptr(), 0, U["key"].data_ptr(), capi.PPO_STAGE_FORWARD)    # warm-up outside the capture
-                    torch.cuda.synchronize(dev)
-                    graphs = []
-                    for stg in stages:
-                        g = torch.cuda.CUDAGraph()
-                        with torch.cuda.graph(g):
-                            L.minibatch(ro, nm, U["idx"].data_ptr(), 0, U["key"].data_ptr(), stg)
-                        graphs.append(g)
-                    U["graphs"], U["coop_in_graph"] = graphs, stages == [capi.PPO_ALL]
-                    break
-                except Exception as e:                                                   # capture of this form unsupported: next form, else eager
-                    import sys
-                    print(f"[ppo] minibatch graph capture (stages {stages}) unavailable ({type(e).__name__}: {str(e)[:120]})", file=sys.stderr)
-                    torch.cuda.synchronize(dev)
+            # plain kernel nodes only: the two-kernel reduce / Adam tail.  (The fused cooperative launch can be captured on this
+            # driver as a kernel node with the cooperative attribute, but inside the graph it ran 49 us against 29 + 18 us for the two
+            # plain kernels and serialised the side streams: measured on B200, profiles/r02d_launches_ppo_tf32.csv.)
+            stages = [FLB, capi.PPO_STAGE_ADAM] if sharded else [capi.PPO_ALL | capi.PPO_NO_COOP]
+            try:
+                L.minibatch(ro, nm, U["idx"].data_ptr(), 0, U["key"].data_ptr(), capi.PPO_STAGE_FORWARD)    # warm-up outside the capture
+                torch.cuda.synchronize(dev)
+                U["graphs"] = []
+                for stg in stages:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        L.minibatch(ro, nm, U["idx"].data_ptr(), 0, U["key"].data_ptr(), stg)
+                    U["graphs"].append(g)
+            except Exception as e:                                                       # capture unsupported: stay eager
+                import sys
+                print(f"[ppo] minibatch graph capture unavailable ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
+                U["graphs"] = None
             self._upd = U
         U = getattr(self, "_upd", None) if graphed else None
         for e in range(cfg.num_updates_per_batch):
@@ -815,7 +879,15 @@ class PPOTrainer:
             mode = "sharded" if (self.world > 1 and self.env.device.type == "cuda") else "replicated"
         sharded = mode == "sharded" and self.world > 1
         self.last_update_mode = "sharded" if sharded else ("replicated" if self.world > 1 else "single")
-        batch = local if sharded else all_gather_rollout(local, self.world)
+        if sharded or self.world == 1:
+            batch = local
+        else:
+            out = None
+            if self._roll is not None and local is self._roll["buf"]:            # persistent (graph-static) gather buffer
+                if self._roll.get("gathered") is None:
+                    self._roll["gathered"] = torch.empty(self.world * local.flat.numel(), device=local.flat.device)
+                out = self._roll["gathered"]
+            batch = all_gather_rollout(local, self.world, out)
         if ev: ev[2].record()
         m = self.update(batch, sharded=sharded)
         if ev:

@@ -831,7 +831,11 @@ static void hfield_convex(const OduckHandle& h, const Scratch& s, int k, int slo
   // (max-norm; hull vertices are millimetres apart) of an EARLIER in-threshold candidate is therefore masked out before the
   // manifold selection -- the first copy in list order (triangle, face, polygon vertex) stands for all of them.
   {
+#ifdef ODUCK_HF_NO_TWIN
+    const real HF_TWIN = (real)-1;
+#else
     const real HF_TWIN = (real)1e-5;
+#endif
     static thread_local bool twin[MAXC];
     for (int j = 0; j < nc; j++) {
       twin[j] = false;
