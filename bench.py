@@ -256,7 +256,11 @@ def leg_physics(args, rank, world, dev, steps=None):
     def step(k):
         envs[k % n_sets].physics_substeps(ctrls[k % 8], 10)
 
-    warm = max(3, n_sets)
+    # reset drops the robot at the keyframe height whatever the terrain under it (reference joystick.py:206-321), so for the first
+    # ~3 control steps the feet sit up to 1 cm inside the field (3 x the pairs, 7 x the candidates of a walking foot: tools/hf_stats.py);
+    # every env set is stepped `settle` times untimed, so that the timed steps see rollout states rather than that transient
+    settle = 12
+    warm = settle * n_sets
     for k in range(warm):
         step(k)
     _dist_barrier(world)
@@ -301,7 +305,11 @@ def leg_rough(args, rank, world, dev, total_envs=16384, steps=20):
     def step(k):
         ppo.rollout_step(envs[k % n_sets], weights, keys[k % 4], k % UNROLL)
 
-    warm = max(3, n_sets)
+    # reset drops the robot at the keyframe height whatever the terrain under it (reference joystick.py:206-321), so for the first
+    # ~3 control steps the feet sit up to 1 cm inside the field (3 x the pairs, 7 x the candidates of a walking foot: tools/hf_stats.py);
+    # every env set is stepped `settle` times untimed, so that the timed steps see rollout states rather than that transient
+    settle = 12
+    warm = settle * n_sets
     for k in range(warm):
         step(k)
     _dist_barrier(world)
@@ -314,7 +322,7 @@ def leg_rough(args, rank, world, dev, total_envs=16384, steps=20):
     ms = _max_over_ranks(t0.elapsed_time(t1), world, dev)
     return {"value": world * n * steps / (ms * 1e-3), "unit": "env-steps/s", "steps": steps, "warmup": warm, "ms_per_step": ms / steps, "envs_per_gpu": n, "global_envs": world * n,
             "workload": f"{task} (height-field floor) joystick rollout step + imitation reward, {world * n} envs over {world} GPU(s) (BASELINE configs[3])",
-            "l2": f"{n_sets} env sets rotated", "gpu_launches": 6 * steps}
+            "l2": f"{n_sets} env sets rotated", "settle_steps_per_env_set": settle, "gpu_launches": 6 * steps}
 
 
 def leg_ppo(args, rank, world, dev, num_envs=8192, steps=3, warmup=2, pipeline=None, update_mode="auto", matmul=None):

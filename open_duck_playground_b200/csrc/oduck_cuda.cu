@@ -602,6 +602,8 @@ int oduck_create(const OduckModel* model, const OduckEnvConfig* cfg, int num_env
   if (cfg->task != ODUCK_TASK_JOYSTICK && cfg->task != ODUCK_TASK_STANDING) return fail(ODUCK_ERR_ARG, "oduck_create: unknown task");
   if (model->floor_is_hfield && (!model->hfield_data || model->hfield_nrow < 2 || model->hfield_ncol < 2))
     return fail(ODUCK_ERR_MODEL, "oduck_create: height-field floor without elevation data");
+  if (model->floor_is_hfield && (model->hfield_ncol > 4096 || model->hfield_nrow > 8192))
+    return fail(ODUCK_ERR_UNSUPPORTED, "oduck_create: height field larger than 8192 x 4096 samples (the collider packs row / column into one word)");
   if (cfg->action_max_delay > MAX_DELAY || cfg->imu_max_delay * 3 > 16 || cfg->action_max_delay < 1) return fail(ODUCK_ERR_ARG, "oduck_create: delay history out of range");
   bool use_lib = false;
   for (int k = 0; k < ODUCK_NLIBTERM; k++) use_lib |= cfg->lib.scale[k] != 0.0;

@@ -18,6 +18,35 @@
 #define GBLK_A (2 * TC_M * TC_KC)                                   // floats per A block (hi + lo) = 8192
 __host__ __device__ constexpr int gblk_b(int nt) { return 2 * nt * TC_KC; }
 __device__ __forceinline__ int gblk_off(int r, int kk) { return (r >> 3) * 256 + (kk >> 2) * 32 + (r & 7) * 4 + (kk & 3); }
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute may begin while
+// its predecessor in the stream still runs.  Every kernel of the learner chain therefore (1) lets its successor go as early as
+// possible -- pdl_launch_dependents() first thing, so that the successor's CTAs take free SMs, allocate TMEM, initialise their
+// barriers and then block in pdl_wait() -- and (2) calls pdl_wait() BEFORE ITS FIRST GLOBAL-MEMORY ACCESS, read or write:
+// that returns when the predecessor grid has completed and its writes are visible.  Launch-to-launch latency (2 - 4 us per
+// dependent pair, ~14 pairs on a minibatch's critical path) overlaps the predecessor's tail.  Both are no-ops without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() {
+#ifndef ODUCK_WARP_EMU
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_wait() {
+#ifndef ODUCK_WARP_EMU
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+// <<<grid, block, smem, st>>> with (pdl = true) the programmatic-stream-serialization attribute
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 __device__ __forceinline__ void gsplit_tf32(float v, float& hi, float& lo) {
   hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
   lo = v - hi;
@@ -202,6 +231,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_gemm_tc(GemmParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = blockIdx.x, nt = blockIdx.y, z = blockIdx.z;
   constexpr uint32_t kCols = NT < 32 ? 32 : NT;
+  pdl_launch_dependents();
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "r"(kCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
@@ -212,6 +242,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_gemm_tc(GemmParams p) {
     mbar_init(&done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
+  pdl_wait();                                                      // the producer grid is done: operands, bias, Z may be read, outputs written
   if (EPI == EPI_FWD || EPI == EPI_OUT || EPI == EPI_ACT) {
     for (int i = threadIdx.x; i < NT; i += GEMM_THREADS) { const int n = nt * NT + i; s_bias[i] = n < p.nvalid ? __ldg(p.bias + n) : 0.f; }
   }
@@ -327,7 +358,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_gemm_simt(GemmParams p) {
 }
 
 template <int NT, int NSTAGE, int EPI>
-static cudaError_t launch_gemm(const GemmParams& p, int mtiles, int ntiles, bool simt, cudaStream_t st) {
+static cudaError_t launch_gemm(const GemmParams& p, int mtiles, int ntiles, bool simt, cudaStream_t st, bool pdl = false) {
   const int splits = (p.nchunks + p.cps - 1) / p.cps;
   dim3 grid(mtiles, ntiles, splits);
   if (simt) {
@@ -343,6 +374,5 @@ static cudaError_t launch_gemm(const GemmParams& p, int mtiles, int ntiles, bool
     if (e != cudaSuccess) return e;
     attr_done |= 1ull << (dev & 63);
   }
-  k_gemm_tc<NT, NSTAGE, EPI><<<grid, GEMM_THREADS, smem, st>>>(p);
-  return cudaGetLastError();
+  return launch_kernel(k_gemm_tc<NT, NSTAGE, EPI>, grid, dim3(GEMM_THREADS), (size_t)smem, st, pdl, p);
 }

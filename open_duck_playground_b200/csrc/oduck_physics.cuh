@@ -30,11 +30,14 @@ struct LSPoint { float alpha, d0, d1; };
 #ifndef ODUCK_PHASE_MARK
 #define ODUCK_PHASE_MARK(bit)      // tests/emu counts warp exchanges per phase through this hook
 #endif
-// Height-field instantiations: the collider's work varies from warp to warp (a swing foot costs nothing, a foot lying on a cell
-// border clips dozens of pairs), so a CTA barrier makes seven warps wait for the slowest one every substep (ncu r02d: 20 % of
-// k_step<HF>'s stall samples); ODUCK_HF_BARRIERS selects the barrier points of those instantiations separately (A/B on B200).
+// Height-field instantiations: the collider's work varies from warp to warp (a swing foot costs nothing, a foot lying across cell
+// borders clips dozens of (triangle, face) pairs), so the CTA's warps leave it at different times and then run the rest of the
+// substep -- ~25 k straight-line instructions -- out of phase, each streaming them through the instruction cache on its own (ncu
+// r02f: sm__icc hit rate 62 %, 5.8 no-instruction stall cycles per issue).  A second barrier before the Newton phase (bit 3) puts
+// them back in step: 3.89 -> 2.38 ms per rollout step at 4096 envs on B200 (profiles/r02g_bench_rough_*.json; masks 0x0b and
+// 0x19 measure the same, no barrier at all is slower than one).  ODUCK_HF_BARRIERS selects the barrier points of those instantiations.
 #ifndef ODUCK_HF_BARRIERS
-#define ODUCK_HF_BARRIERS ODUCK_BARRIERS
+#define ODUCK_HF_BARRIERS 0x09
 #endif
 #define PHASE_MASK (HF ? (ODUCK_HF_BARRIERS) : (ODUCK_BARRIERS))
 #define PHASE_SYNC(bit, pre_exit) { ODUCK_PHASE_MARK(bit) if (BAR && ((PHASE_MASK >> (bit)) & 1) && (!(pre_exit) || !FF)) __syncthreads(); }

@@ -13,6 +13,7 @@
 //   k_ppo_adam           global-norm clip, Adam, master weights + both packed operand forms of every kernel matrix
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -79,6 +80,10 @@ struct OduckPpo {
   int* step;                // [3]: adam step count, finished-block tickets of k_ppo_adam and k_ppo_gae
   int reduce_blocks;
   int64_t launches;
+  bool pdl;                 // programmatic dependent launch along the kernel chain (oduck_gemm_tc.cuh): OFF by default, ODUCK_PPO_PDL=1 turns it on.
+                            // Measured on B200 (profiles/r02g_bench_ppo_*_pdl{0,1}.json): the update takes 38.3 ms with it against 37.0 ms without
+                            // (3xTF32) and 30.8 against 30.2 ms (one-pass TF32) -- inside a captured graph the kernel-to-kernel hand-over is
+                            // already short, and early-launched CTAs hold SMs / TMEM that the other streams' kernels could use.
   cudaStream_t side;        // the value net's chain runs here, concurrently with the policy net's chain on the caller's stream
   cudaStream_t side_w[2];   // weight-gradient GEMMs of the policy / value net (off the dZ critical path)
   cudaEvent_t ev_fork, ev_join, ev_join_w[2], ev_dz[2][PPO_NL];
@@ -98,6 +103,8 @@ __device__ __forceinline__ size_t ro_off(const int be, const long long bstride, 
 // (R(X^T)) contiguous, so every store is a float4.
 __global__ void k_ppo_pack(const float* __restrict__ obs, int be, long long bstride, int K, const int* __restrict__ idx, int B, int M, int Mpad, int kch,
                            const float* __restrict__ mean, const float* __restrict__ stdv, float* __restrict__ Xr, float* __restrict__ Xt) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int K4 = kch * (TC_KC / 4), ytn = Mpad / TC_KC;
   const int total = (Mpad / 4) * K4;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -159,6 +166,8 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
 __global__ void __launch_bounds__(GAE_THREADS) k_ppo_gae(const float* __restrict__ values /*[Mv_pad][32]*/, OduckRollout ro, const int* __restrict__ idx, int B, int T,
                                                          float discount, float lambda, float reward_scaling, float* __restrict__ adv, float* __restrict__ vs,
                                                          double* __restrict__ stats /*[4 + 2 * gridDim.x]*/, int* __restrict__ ticket, double* __restrict__ losses) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (blockIdx.x == 0 && threadIdx.x < 8) losses[threadIdx.x] = 0.0;
   const int be = ro.block_envs > 0 ? ro.block_envs : ro.num_envs;
   const int b = blockIdx.x * GAE_THREADS + threadIdx.x;
@@ -243,6 +252,8 @@ struct LossParams {
 __global__ void __launch_bounds__(LOSS_ROWS * 16) k_ppo_loss(LossParams p) {
   __shared__ double sh[32];
   __shared__ float gp[LOSS_ROWS][PPO_HEADW], gv[LOSS_ROWS];
+  pdl_launch_dependents();
+  pdl_wait();
   const int sub = threadIdx.x >> 4, a = threadIdx.x & 15;        // row slot in the CTA, action lane
   const int r = blockIdx.x * LOSS_ROWS + sub;
   double l_pol = 0.0, l_val = 0.0, l_ent = 0.0, l_clip = 0.0, l_adv = 0.0;
@@ -571,6 +582,8 @@ __global__ void __launch_bounds__(256) k_ppo_reduce_adam(const SegTable* __restr
 __global__ void __launch_bounds__(256) k_ppo_grad_reduce(const SegTable* __restrict__ tbp, const float* __restrict__ partial, float* __restrict__ grads, float* __restrict__ sumsq_part) {
   __shared__ double sh[32];
   __shared__ SegTable tb;
+  pdl_launch_dependents();
+  pdl_wait();
   for (int i = threadIdx.x; i < (int)(sizeof(SegTable) / 4); i += blockDim.x) reinterpret_cast<int*>(&tb)[i] = reinterpret_cast<const int*>(tbp)[i];
   __syncthreads();
   double ss = 0.0;
@@ -588,6 +601,8 @@ __global__ void __launch_bounds__(256) k_ppo_grad_reduce(const SegTable* __restr
 
 __global__ void __launch_bounds__(256) k_ppo_gradnorm(const float* __restrict__ grads, long long total, float* __restrict__ sumsq_part) {
   __shared__ double sh[32];
+  pdl_launch_dependents();
+  pdl_wait();
   double ss = 0.0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) ss += (double)grads[i] * grads[i];
   const double t = block_sum(ss, sh);
@@ -600,6 +615,8 @@ __global__ void __launch_bounds__(256) k_ppo_adam(const SegTable* __restrict__ t
                                                   float lr, float b1, float b2, float eps, float max_norm, int update) {
   __shared__ SegTable tb;
   __shared__ float s_scale, s_c1, s_c2;
+  pdl_launch_dependents();
+  pdl_wait();
   for (int i = threadIdx.x; i < (int)(sizeof(SegTable) / 4); i += blockDim.x) reinterpret_cast<int*>(&tb)[i] = reinterpret_cast<const int*>(tbp)[i];
   if (threadIdx.x < 32 && update) {
     const double ss = warp_total(sumsq_part, nparts, threadIdx.x);
@@ -668,6 +685,7 @@ int oduck_ppo_create(const OduckPpoConfig* cfg, int device, OduckPpo** out) {
   PPO_TRY(cudaSetDevice(device));
   OduckPpo* h = new OduckPpo();
   h->cfg = *cfg; h->device = device; h->B = B; h->T = T; h->na = na; h->launches = 0;
+  { const char* e = getenv("ODUCK_PPO_PDL"); h->pdl = e && e[0] == '1'; }
   h->side = nullptr; h->ev_fork = h->ev_join = nullptr; h->coop_blocks = 0;
   memset(h->side_w, 0, sizeof(h->side_w)); memset(h->ev_join_w, 0, sizeof(h->ev_join_w)); memset(h->ev_dz, 0, sizeof(h->ev_dz));
   {
@@ -775,9 +793,8 @@ int oduck_ppo_packed_weights(OduckPpo* h, int net, int layer, const float** ptr)
 
 static int launch_adam(OduckPpo* h, int update, cudaStream_t st) {
   const OduckPpoConfig& c = h->cfg;
-  k_ppo_adam<<<h->reduce_blocks, 256, 0, st>>>(h->dseg, h->params, h->grads, h->adam_m, h->adam_v, h->packed, h->sumsq_part, h->reduce_blocks, h->step,
-                                               c.learning_rate, c.adam_b1, c.adam_b2, c.adam_eps, c.max_grad_norm, update);
-  PPO_TRY(cudaGetLastError());
+  PPO_TRY(launch_kernel(k_ppo_adam, dim3(h->reduce_blocks), dim3(256), 0, st, h->pdl, h->dseg, h->params, h->grads, h->adam_m, h->adam_v, h->packed, h->sumsq_part,
+                        h->reduce_blocks, h->step, c.learning_rate, c.adam_b1, c.adam_b2, c.adam_eps, c.max_grad_norm, update));
   h->launches++;
   return ODUCK_OK;
 }
@@ -836,10 +853,10 @@ static int net_forward(OduckPpo* h, int net, bool simt, cudaStream_t st) {
       g.Z = nb.Z[l]; g.z_nch = w.N / TC_KC;
       g.Yr = nb.Xr[l + 1]; g.yr_nch = w.N / TC_KC;
       g.Yt = nb.Xt[l + 1]; g.yt_nch = nb.Mpad / TC_KC;
-      GEMM_TRY((launch_gemm<128, 3, EPI_FWD>(g, nb.mtiles, w.N / 128, simt, st)));
+      GEMM_TRY((launch_gemm<128, 3, EPI_FWD>(g, nb.mtiles, w.N / 128, simt, st, h->pdl)));
     } else {
       g.out = nb.out; g.ldo = PPO_HEADW;
-      GEMM_TRY((launch_gemm<PPO_HEADW, 4, EPI_OUT>(g, nb.mtiles, 1, simt, st)));
+      GEMM_TRY((launch_gemm<PPO_HEADW, 4, EPI_OUT>(g, nb.mtiles, 1, simt, st, h->pdl)));
     }
   }
   return ODUCK_OK;
@@ -860,8 +877,8 @@ static int net_backward(OduckPpo* h, int net, bool simt, cudaStream_t sx, cudaSt
       g.nchunks = nb.Mpad / TC_KC; g.cps = ceil_div(g.nchunks, w.nsplit);
       g.out = h->partial + w.dwpart; g.ldo = w.ldo; g.out_split = w.split_stride;
       const int mt = ceil_div(w.K, 128);
-      if (l == PPO_NL - 1) GEMM_TRY((launch_gemm<PPO_HEADW, 4, EPI_DW>(g, mt, 1, simt, sw)));
-      else GEMM_TRY((launch_gemm<128, 3, EPI_DW>(g, mt, w.N / 128, simt, sw)));
+      if (l == PPO_NL - 1) GEMM_TRY((launch_gemm<PPO_HEADW, 4, EPI_DW>(g, mt, 1, simt, sw, h->pdl)));
+      else GEMM_TRY((launch_gemm<128, 3, EPI_DW>(g, mt, w.N / 128, simt, sw, h->pdl)));
     }
     if (l > 0) {
       // dZ_{l-1} = (dZ_l W_l^T) * swish'(Z_{l-1}): columns = in features of layer l, contraction over its out features
@@ -876,7 +893,7 @@ static int net_backward(OduckPpo* h, int net, bool simt, cudaStream_t sx, cudaSt
       g.Yt = nb.dZt[l - 1]; g.yt_nch = nb.Mpad / TC_KC;
       g.dbpart = h->partial + bprev.dbpart; g.ldb = bprev.ldb;
       g.nvalid = w.K;
-      GEMM_TRY((launch_gemm<128, 3, EPI_DX>(g, nb.mtiles, w.K / 128, simt, sx)));
+      GEMM_TRY((launch_gemm<128, 3, EPI_DX>(g, nb.mtiles, w.K / 128, simt, sx, h->pdl)));
       if (sw != sx) {
         PPO_TRY(cudaEventRecord(h->ev_dz[net][l - 1], sx));
         PPO_TRY(cudaStreamWaitEvent(sw, h->ev_dz[net][l - 1], 0));
@@ -905,19 +922,16 @@ int oduck_ppo_minibatch(OduckPpo* h, const OduckRollout* ro, const OduckNormaliz
 #define JOIN() { PPO_TRY(cudaEventRecord(h->ev_join, h->side)); PPO_TRY(cudaStreamWaitEvent(st, h->ev_join, 0)); }
   if (stages & ODUCK_PPO_STAGE_FORWARD) {
     FORK()
-    k_ppo_pack<<<296, 256, 0, h->side>>>(ro->obs_value, be, ro->block_stride, nv.dims[0], env_idx, h->B, nv.M, nv.Mpad, ceil_div(nv.dims[0], TC_KC), nm->value_mean, nm->value_std, nv.Xr[0], nv.Xt[0]);
-    GEMM_TRY(cudaGetLastError());
+    GEMM_TRY(launch_kernel(k_ppo_pack, dim3(296), dim3(256), 0, h->side, h->pdl, ro->obs_value, be, (long long)ro->block_stride, nv.dims[0], env_idx, h->B, nv.M, nv.Mpad, ceil_div(nv.dims[0], TC_KC), nm->value_mean, nm->value_std, nv.Xr[0], nv.Xt[0]));
     int rc = net_forward(h, 1, simt, h->side);
     if (rc) return rc;
-    k_ppo_pack<<<296, 256, 0, st>>>(ro->obs_policy, be, ro->block_stride, np.dims[0], env_idx, h->B, np.M, np.Mpad, ceil_div(np.dims[0], TC_KC), nm->policy_mean, nm->policy_std, np.Xr[0], np.Xt[0]);
-    GEMM_TRY(cudaGetLastError());
+    GEMM_TRY(launch_kernel(k_ppo_pack, dim3(296), dim3(256), 0, st, h->pdl, ro->obs_policy, be, (long long)ro->block_stride, np.dims[0], env_idx, h->B, np.M, np.Mpad, ceil_div(np.dims[0], TC_KC), nm->policy_mean, nm->policy_std, np.Xr[0], np.Xt[0]));
     rc = net_forward(h, 0, simt, st);
     if (rc) return rc;
     JOIN()
   }
   if (stages & ODUCK_PPO_STAGE_LOSS) {
-    k_ppo_gae<<<ceil_div(h->B, GAE_THREADS), GAE_THREADS, 0, st>>>(nv.out, *ro, env_idx, h->B, h->T, c.discounting, c.gae_lambda, c.reward_scaling, h->adv, h->vs, h->stats, h->step + 2, h->losses);
-    GEMM_TRY(cudaGetLastError());
+    GEMM_TRY(launch_kernel(k_ppo_gae, dim3(ceil_div(h->B, GAE_THREADS)), dim3(GAE_THREADS), 0, st, h->pdl, nv.out, *ro, env_idx, h->B, h->T, c.discounting, c.gae_lambda, c.reward_scaling, h->adv, h->vs, h->stats, h->step + 2, h->losses));
     LossParams lp;
     memset(&lp, 0, sizeof(lp));
     lp.logits = np.out; lp.values = nv.out; lp.adv = h->adv; lp.vs = h->vs; lp.stats = h->stats; lp.adv_norm = h->adv_norm; lp.normalize = c.normalize_advantage; lp.ro = *ro; lp.idx = env_idx; lp.noise = noise; lp.key = key;
@@ -928,8 +942,7 @@ int oduck_ppo_minibatch(OduckPpo* h, const OduckRollout* ro, const OduckNormaliz
     lp.dZr_p = np.dZr[PPO_NL - 1]; lp.dZt_p = np.dZt[PPO_NL - 1]; lp.db_p = h->partial + bp.dbpart;
     lp.dZr_v = nv.dZr[PPO_NL - 1]; lp.dZt_v = nv.dZt[PPO_NL - 1]; lp.db_v = h->partial + bv.dbpart;
     lp.losses = h->losses;
-    k_ppo_loss<<<nv.Mpad / LOSS_ROWS, LOSS_ROWS * 16, 0, st>>>(lp);
-    GEMM_TRY(cudaGetLastError());
+    GEMM_TRY(launch_kernel(k_ppo_loss, dim3(nv.Mpad / LOSS_ROWS), dim3(LOSS_ROWS * 16), 0, st, h->pdl, lp));
   }
   if (stages & ODUCK_PPO_STAGE_BACKWARD) {
     FORK()
@@ -951,13 +964,11 @@ int oduck_ppo_minibatch(OduckPpo* h, const OduckRollout* ro, const OduckNormaliz
       h->launches++;
       return ODUCK_OK;
     }
-    k_ppo_grad_reduce<<<h->reduce_blocks, 256, 0, st>>>(h->dseg, h->partial, h->grads, h->sumsq_part);
-    GEMM_TRY(cudaGetLastError());
+    GEMM_TRY(launch_kernel(k_ppo_grad_reduce, dim3(h->reduce_blocks), dim3(256), 0, st, h->pdl, h->dseg, h->partial, h->grads, h->sumsq_part));
   }
   if (stages & ODUCK_PPO_STAGE_ADAM) {
     if (!(stages & ODUCK_PPO_STAGE_BACKWARD)) {           // gradients were all-reduced by the caller: recompute their norm
-      k_ppo_gradnorm<<<h->reduce_blocks, 256, 0, st>>>(h->grads, h->P, h->sumsq_part);
-      GEMM_TRY(cudaGetLastError());
+      GEMM_TRY(launch_kernel(k_ppo_gradnorm, dim3(h->reduce_blocks), dim3(256), 0, st, h->pdl, h->grads, (long long)h->P, h->sumsq_part));
     }
     return launch_adam(h, 1, st);
   }

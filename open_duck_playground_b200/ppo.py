@@ -820,29 +820,44 @@ class PPOTrainer:
         # gradient all-reduce when sharded).  Only with the persistent rollout buffers of the graphed unroll (static pointers).
         graphed = cfg.cuda_graph and self._roll is not None and (batch is self._roll["buf"] or (blocked and batch.local is self._roll["buf"] and batch.flat is self._roll.get("gathered")))
         if graphed and getattr(self, "_upd", None) is None:
-            U = {"idx": torch.zeros(B, dtype=torch.int32, device=dev), "key": torch.zeros(2, dtype=torch.int32, device=dev), "ro": ro, "nm": nm}
+            nmb = cfg.num_minibatches
+            U = {"idx": torch.zeros(B, dtype=torch.int32, device=dev), "key": torch.zeros(2, dtype=torch.int32, device=dev), "ro": ro, "nm": nm,
+                 "perm": torch.zeros(N, dtype=torch.int32, device=dev), "keys": torch.zeros(nmb, 2, dtype=torch.int32, device=dev)}
             # plain kernel nodes only: the two-kernel reduce / Adam tail.  (The fused cooperative launch can be captured on this
             # driver as a kernel node with the cooperative attribute, but inside the graph it ran 49 us against 29 + 18 us for the two
             # plain kernels and serialised the side streams: measured on B200, profiles/r02d_launches_ppo_tf32.csv.)
-            stages = [FLB, capi.PPO_STAGE_ADAM] if sharded else [capi.PPO_ALL | capi.PPO_NO_COOP]
             try:
                 L.minibatch(ro, nm, U["idx"].data_ptr(), 0, U["key"].data_ptr(), capi.PPO_STAGE_FORWARD)    # warm-up outside the capture
                 torch.cuda.synchronize(dev)
-                U["graphs"] = []
-                for stg in stages:
+                U["graphs"], U["epoch"] = [], None
+                if sharded:
+                    for stg in (FLB, capi.PPO_STAGE_ADAM):
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g):
+                            L.minibatch(ro, nm, U["idx"].data_ptr(), 0, U["key"].data_ptr(), stg)
+                        U["graphs"].append(g)
+                else:
+                    # one graph per EPOCH: the num_minibatches SGD steps back to back, minibatch i reading slice i of the static
+                    # permutation / key buffers -- per epoch two small copies and one replay instead of three host calls per minibatch
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g):
-                        L.minibatch(ro, nm, U["idx"].data_ptr(), 0, U["key"].data_ptr(), stg)
-                    U["graphs"].append(g)
+                        for i in range(nmb):
+                            L.minibatch(ro, nm, U["perm"].data_ptr() + 4 * i * B, 0, U["keys"].data_ptr() + 8 * i, capi.PPO_ALL | capi.PPO_NO_COOP)
+                    U["epoch"] = g
             except Exception as e:                                                       # capture unsupported: stay eager
                 import sys
                 print(f"[ppo] minibatch graph capture unavailable ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
-                U["graphs"] = None
+                U["graphs"], U["epoch"] = None, None
             self._upd = U
         U = getattr(self, "_upd", None) if graphed else None
         for e in range(cfg.num_updates_per_batch):
             perm = torch.randperm(N, generator=gen).to(torch.int32).to(dev)
             keep.append(perm)
+            if U is not None and U.get("epoch") is not None:
+                U["perm"].copy_(perm, non_blocking=True)
+                U["keys"].copy_(keys[e * cfg.num_minibatches:(e + 1) * cfg.num_minibatches], non_blocking=True)
+                U["epoch"].replay()
+                continue
             for i in range(cfg.num_minibatches):
                 j = e * cfg.num_minibatches + i
                 if U is not None and U["graphs"]:

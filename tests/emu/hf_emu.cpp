@@ -6,6 +6,13 @@
 #include <thread>
 #include <vector>
 
+#ifdef ODUCK_HF_STATS   // tools/hf_stats.py: triangles after the height cull / after the plane-side cull, pairs, candidates per call
+static long long g_hf_stat[8];
+#define ODUCK_HF_STAT(what, n) { if (lane == 0) g_hf_stat[what] += (n); }
+extern "C" long long* emu_hf_stats(void) { return g_hf_stat; }
+static float g_hf_last_cand[1 << 14];
+extern "C" float* emu_hf_last_candidates(void) { return g_hf_last_cand; }   // the candidate list of the last call
+#endif
 #include "../../open_duck_playground_b200/csrc/oduck_hfcollide.cuh"
 
 extern "C" int emu_hf_scratch_floats(void) { return HF_SCRATCH; }
@@ -45,6 +52,9 @@ extern "C" int emu_hf_collide(const float* xpos, const float* xmat, const float*
       hf_collide(m, &ff, &hf, s, l, f, cand.data());
     });
   for (auto& t : th) t.join();
+#ifdef ODUCK_HF_STATS
+  std::memcpy(g_hf_last_cand, cand.data(), sizeof(float) * HF_SCRATCH);
+#endif
   for (int c = 0; c < 4; c++) {
     const float* cc = s.con[c];
     float* o = out + 8 * c;

@@ -416,5 +416,6 @@ def test_learner_reads_the_gathered_rank_major_blocks_in_place():
         L.minibatch(ro, nm, idx.data_ptr(), noise.data_ptr(), 0, capi.PPO_STAGE_FORWARD | capi.PPO_STAGE_LOSS | capi.PPO_STAGE_BACKWARD)
         torch.cuda.synchronize()
         grads.append((L.grads.clone(), L.view("ADV").clone(), list(L.losses.tolist())))
-    assert torch.equal(grads[0][0], grads[1][0]) and torch.equal(grads[0][1], grads[1][1]) and grads[0][2] == grads[1][2]
+    assert torch.equal(grads[0][0], grads[1][0]) and torch.equal(grads[0][1], grads[1][1])
+    assert np.allclose(grads[0][2], grads[1][2], rtol=1e-12, atol=0)      # the reported losses are fp64 atomic sums: order-dependent in the last bits
     assert grads[0][0].abs().max().item() > 0
