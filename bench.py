@@ -51,7 +51,7 @@ FLOP_PER_ENV_STEP = 9.39e5         # counted: op-counter build of the oracle (to
 L2_BYTES = 126e6
 STATE_BYTES_PER_ENV = 4 * (128 + 144 + 224 + 256 + 101 + 212 + 16)   # records one step touches (csrc/oduck_device.cuh)
 UNROLL = 20                        # PPO unroll length (Brax table, common/runner.py:87-89)
-DEFAULT_PIPELINE = 4
+DEFAULT_PIPELINE = 2
 ROLLOUT_FLOATS_PER_ENV = (UNROLL + 1) * (101 + 212) + UNROLL * (14 + 1 + 3)   # one unroll's Transition record per env
 
 

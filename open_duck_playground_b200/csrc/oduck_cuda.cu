@@ -17,7 +17,11 @@
 #endif
 
 #ifndef WPB
-#define WPB 8   // warps (= envs in flight) per CTA
+// warps (= envs in flight) per CTA.  16 = ONE CTA per SM: the substep is ~9 k straight-line instructions (140 KB) that stream through
+// the instruction cache once per substep and convoy, and a CTA's warps are kept in one convoy by the substep barrier; two 8-warp
+// CTAs per SM (rounds 1 and 2a) are two convoys.  Measured on B200 (profiles/r02i_bench_*.json): flat 7.24 -> 7.53 M env-steps/s,
+// rough terrain 8.28 -> 6.58 ms per 16384-env step.
+#define WPB 16
 #endif
 #ifndef CTAS_PER_SM
 #define CTAS_PER_SM (WPB <= 8 ? 2 : 1)

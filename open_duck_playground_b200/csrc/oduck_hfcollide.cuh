@@ -42,6 +42,9 @@ struct DevHF {   // global memory
 __device__ __forceinline__ void hf_clip_pass(V3& P, int& cnt, const int j, const int gb, const unsigned gmask, const unsigned glt, const int G,
                                              float* __restrict__ sc, const float r0x, const float r0y, const float sdx, const float sdy) {
   const float d0 = sdx * (P.x - r0x) + sdy * (P.y - r0y);
+  // no vertex of any of the warp's polygons outside this plane: the pass returns every polygon as it is (cells are 8 cm wide, most
+  // faces 1 - 3 cm: a face usually lies inside two of its triangle's three half-planes)
+  if (__ballot_sync(FULLMASK, j < cnt && !(d0 <= 0.f)) == 0u) return;   // warp-uniform
   const int src = gb + ((j + 1 >= cnt) ? 0 : j + 1);                    // the next vertex, the first one after the last
   const V3 N = v3(__shfl_sync(FULLMASK, P.x, src), __shfl_sync(FULLMASK, P.y, src), __shfl_sync(FULLMASK, P.z, src));
   const float d1 = __shfl_sync(FULLMASK, d0, src);
@@ -358,6 +361,7 @@ static __device__ __noinline__ void hf_collide(const DevModel& m, const DevFF* _
   // Twins (oracle hfield_convex): an in-threshold candidate whose clipped point lies within HF_TWIN of an EARLIER in-threshold
   // candidate is a copy of the same point seen through a neighbouring triangle or face; it is masked out, so the arg-max passes
   // below never choose between copies that differ only by rounding and by the triangle normal they carry.
+  const int nch = (nin + 31) >> 5;                                       // chunks in use (warp-uniform)
   float dm[HF_NIN / 32];
   {
     bool tw[HF_NIN / 32];
@@ -368,12 +372,11 @@ static __device__ __noinline__ void hf_collide(const DevModel& m, const DevFF* _
       const float ox = scr[3 * i], oy = scr[3 * i + 1], oz = scr[3 * i + 2];
 #pragma unroll
       for (int c = 0; c < HF_NIN / 32; ++c)
-        if (i < lane + 32 * c && fmaxf(fabsf(Pc[c].x - ox), fmaxf(fabsf(Pc[c].y - oy), fabsf(Pc[c].z - oz))) < HF_TWIN) tw[c] = true;
+        if (c < nch && i < lane + 32 * c && fmaxf(fabsf(Pc[c].x - ox), fmaxf(fabsf(Pc[c].y - oy), fabsf(Pc[c].z - oz))) < HF_TWIN) tw[c] = true;
     }
 #pragma unroll
     for (int c = 0; c < HF_NIN / 32; ++c) dm[c] = (ok[c] && !tw[c]) ? 0.f : ninf;
   }
-  const int nch = (nin + 31) >> 5;                                       // chunks in use (warp-uniform)
   auto point = [&](int sl) {                                             // midway point of slot sl, from the lane that holds it
     const int c = sl >> 5;
     const V3 v = c == 0 ? Pm[0] : (c == 1 ? Pm[1] : Pm[2]);

@@ -16,6 +16,8 @@ import math
 from dataclasses import dataclass, field
 from typing import Callable, Dict, Optional, Tuple
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -830,7 +832,20 @@ class PPOTrainer:
                 L.minibatch(ro, nm, U["idx"].data_ptr(), 0, U["key"].data_ptr(), capi.PPO_STAGE_FORWARD)    # warm-up outside the capture
                 torch.cuda.synchronize(dev)
                 U["graphs"], U["epoch"] = [], None
-                if sharded:
+                if sharded and os.environ.get("ODUCK_PPO_GRAPH_NCCL", "1") != "0":
+                    # sharded update, one graph per EPOCH with the gradient all-reduces inside: forward / loss / backward, NCCL
+                    # all-reduce (average) of the flat gradient, clip + Adam, num_minibatches times -- NCCL collectives are
+                    # capturable, so the host issues two copies and one replay per epoch instead of six calls per minibatch
+                    dist.all_reduce(torch.zeros(8, device=dev), op=dist.ReduceOp.AVG)       # communicator set up outside the capture
+                    torch.cuda.synchronize(dev)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        for i in range(nmb):
+                            L.minibatch(ro, nm, U["perm"].data_ptr() + 4 * i * B, 0, U["keys"].data_ptr() + 8 * i, FLB)
+                            dist.all_reduce(L.grads, op=dist.ReduceOp.AVG)
+                            L.minibatch(ro, nm, U["perm"].data_ptr() + 4 * i * B, 0, U["keys"].data_ptr() + 8 * i, capi.PPO_STAGE_ADAM)
+                    U["epoch"] = g
+                elif sharded:
                     for stg in (FLB, capi.PPO_STAGE_ADAM):
                         g = torch.cuda.CUDAGraph()
                         with torch.cuda.graph(g):

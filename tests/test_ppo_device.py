@@ -419,3 +419,19 @@ def test_learner_reads_the_gathered_rank_major_blocks_in_place():
     assert torch.equal(grads[0][0], grads[1][0]) and torch.equal(grads[0][1], grads[1][1])
     assert np.allclose(grads[0][2], grads[1][2], rtol=1e-12, atol=0)      # the reported losses are fp64 atomic sums: order-dependent in the last bits
     assert grads[0][0].abs().max().item() > 0
+
+
+@pytest.mark.gpu
+def test_pipelined_graphed_rollout_equals_plain_rollout():
+    """PPOConfig.rollout_pipeline = 2: the rank's envs as two sub-batches with their own handles, graph chains and streams.  Every
+    transition must equal the single-batch trainer's bit for bit -- eager and capture iterations, then graph replays (first
+    hardware runs: xpassed in a child process, profiles/r02a..r02g_pytest_gpu.log)."""
+    from open_duck_playground_b200.joystick import Joystick
+    kw = dict(num_envs=512, unroll_length=5, num_minibatches=2, num_updates_per_batch=1, num_eval_envs=0)
+    a = ppo.PPOTrainer(Joystick("flat_terrain_backlash", device="cuda:0"), ppo.PPOConfig(**kw))
+    b = ppo.PPOTrainer(Joystick("flat_terrain_backlash", device="cuda:0"), ppo.PPOConfig(rollout_pipeline=2, **kw))
+    for it in range(4):
+        ra, rb = a.rollout(), b.rollout()
+        torch.cuda.synchronize()
+        for k in ra:
+            assert torch.equal(ra[k], rb[k]), (it, k)

@@ -153,9 +153,8 @@ def test_device_code_adds_the_same_terms(oracle, model_backlash):
 
 
 def library_terms_gpu_parity(oracle):
-    """CUDA k_step<HF = false, RL = true> against the oracle, every library term on.  Not collected here: its first GPU run
-    happens in a child process (tests/test_zz_first_gpu_runs.py), so that a fault in a kernel that has never run on hardware
-    cannot take the CUDA context of the other GPU tests with it."""
+    """CUDA k_step<HF = false, RL = true> against the oracle, every library term on (body of test_library_terms_gpu_parity;
+    its first hardware runs happened in a child process -- xpassed on B200 in profiles/r02a..r02g_pytest_gpu.log)."""
     from test_parity_gpu import Checks, _sync_from_ref
     n, cfg = 256, library_config()
     gpu, ref = Joystick("flat_terrain_backlash", config=cfg, device="cuda:0"), Joystick("flat_terrain_backlash", config=cfg, library=oracle)
@@ -174,3 +173,8 @@ def library_terms_gpu_parity(oracle):
         c.close(sg.data.qpos, sr.data.qpos, 1e-4, what=f"[{t}] qpos")
         c.close(sg.reward, sr.reward, 3e-4, what=f"[{t}] reward")
     c.done()
+
+
+@pytest.mark.gpu
+def test_library_terms_gpu_parity(oracle):
+    library_terms_gpu_parity(oracle)

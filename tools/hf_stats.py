@@ -21,7 +21,7 @@ from oracle import oracle_lib  # noqa: E402
 def main(n=32, steps=40, sample=(0, 1, 2, 4, 9, 19, 39)):
     out = "/tmp/hf/libhf_stats.so"
     os.makedirs("/tmp/hf", exist_ok=True)
-    subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-fPIC", "-shared", f"-I{ROOT}/tests/emu", "-DODUCK_HF_STATS", *sys.argv[1:],
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-fPIC", "-shared", f"-I{ROOT}/tests/emu", "-DODUCK_HF_STATS", *[a for a in sys.argv[1:] if a.startswith("-D")],
                            f"{ROOT}/tests/emu/hf_emu.cpp", "-o", out])
     lib = C.CDLL(out)
     lib.emu_hf_collide.argtypes = [C.c_void_p] * 3 + [C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -38,9 +38,20 @@ def main(n=32, steps=40, sample=(0, 1, 2, 4, 9, 19, 39)):
     data = np.ascontiguousarray(A["hfield_data"], np.float32)
     size = np.asarray(A["hfield_size"][:3], np.float32)
     g = torch.Generator().manual_seed(0)
+    from open_duck_playground_b200 import ppo
+    torch.manual_seed(0)
+    weights = ppo.PolicyWeights(ppo.MLP([101, 512, 256, 128, 28]), 101, torch.device("cpu"))     # the bench's actor: random weights, sampled actions
+    policy = "--mlp" in sys.argv
     rows = []
     for t in range(steps):
-        s = env.step(s, torch.rand(n, 14, generator=g) * 2 - 1)
+        if policy:
+            keys = torch.from_numpy(jr.split(jr.PRNGKey(2000 + t), n).view(np.int32).copy())
+            act, _, _ = ppo.policy_forward(env, weights, keys, False)
+            s = env.step(s, act)
+        else:
+            s = env.step(s, torch.rand(n, 14, generator=g) * 2 - 1)
+        if t in sample:
+            print(f"step {t + 1}: done {float(s.done.mean()):.2f}  base z mean {float(s.data.qpos[:, 2].mean()):.3f}  min {float(s.data.qpos[:, 2].min()):.3f}")
         if t not in sample:
             continue
         q = s.data.qpos.numpy()
