@@ -10,8 +10,8 @@ One "step" = one rollout step over the whole batch = ``oduck_rollout_step``: act
 rollout buffers (OduckRolloutSink; PPO unroll of 20 steps, common/runner.py:104-118).
 Workload at N = 1: BASELINE.json configs[1] -- ``flat_terrain_backlash`` (the task the metric names), 4096 envs per GPU,
 domain randomisation on, no PPO update.  Envs are independent, so ranks take disjoint env shards (weak scaling: per-GPU work
-fixed).  At N > 1 every 20th step ends with north_star's one exchange, INSIDE the timed region: a single NCCL all-gather of
-the rollout buffers.
+fixed).  At N > 1 north_star's one exchange -- the NCCL all-gather of the rollout buffers at the PPO boundary -- is INSIDE
+the timed region: issued slice by slice on a communication stream behind the step that makes the slice final, joined every 20th step.
 
 The rank's envs run as P sub-batches (``--pipeline``, default 4), each with its own library handle, CUDA-graph chain and stream:
 4096 envs are 1.73 waves of ``k_step`` and a latency-bound wave costs the same full or not, so sub-batch q + 1's step k fills the
@@ -77,7 +77,7 @@ def workload_config(task, n, world, pipeline):
             "parallelism": f"env-shard x{world}", "pipeline": pipeline,
             "l2": f"{sets} env sets rotated, {sets * n * STATE_BYTES_PER_ENV / 1e6:.0f} MB working set > L2",
             "launch": f"{pipeline} sub-batches per GPU, one CUDA graph per (env set, sub-batch, unroll step) replayed on the sub-batch's stream; "
-                      "streams join every 20 steps; at N > 1 one NCCL all-gather of the rollout buffers there (inside the timed region)"}
+                      "streams join every 20 steps; at N > 1 the NCCL all-gather of the rollout buffers runs slice by slice behind the steps on a communication stream and is joined there (inside the timed region)"}
 
 
 class ClockSampler(threading.Thread):
@@ -385,7 +385,12 @@ def run_rollout(args, rank, world, dev, local):
     host_keys = [k.cpu().pin_memory() for k in keys]
     key_static = torch.empty_like(keys[0])
     roll = ppo.RolloutBuffers(UNROLL, n, 101, 212, 14, dev)              # the rank's rollout buffers: the kernels write them
-    gathered = torch.empty(world * roll.flat.numel(), device=dev) if world > 1 else None
+    # N > 1: the gathered rollout, time-major [T(+1), world * n, ...] per field (what the replicated learner consumes with
+    # block_envs = 0).  Slice t of a field is the contiguous concatenation of every rank's slice t, so the exchange of SURVEY 8e
+    # is issued SLICE BY SLICE on a communication stream as soon as step t has made its slice final, under the steps that follow;
+    # only the last step's slices are still in flight at the unroll boundary.
+    gathered = {k: torch.empty((v.shape[0], world * n) + tuple(v.shape[2:]), device=dev) for k, v in roll.items()} if world > 1 else None
+    comm = torch.cuda.Stream(device=dev) if world > 1 else None
     for row in envs:
         for q, e in enumerate(row):
             ppo.attach_rollout_sink(e, roll, q * m)
@@ -419,9 +424,28 @@ def run_rollout(args, rank, world, dev, local):
     torch.cuda.synchronize()
 
     gather_events = []
+    gather_graphs = {}
+
+    def gather_slice(t):
+        """What step t made final: its Transition (slot t) and the observations after it (slot t + 1; slot 0 with step 0)."""
+        for k in ("obs_p", "obs_v"):
+            if t == 0:
+                dist.all_gather_into_tensor(gathered[k][0], roll[k][0])
+            dist.all_gather_into_tensor(gathered[k][t + 1], roll[k][t + 1])
+        for k in ("raw", "logp", "reward", "done", "trunc"):
+            dist.all_gather_into_tensor(gathered[k][t], roll[k][t])
+
+    if world > 1:
+        with torch.cuda.stream(comm):
+            gather_slice(0)                                              # communicator set-up outside the captures
+        torch.cuda.synchronize()
+        for t in range(T):
+            gather_graphs[t] = capture_graph(comm, pool, lambda: gather_slice(t))     # NCCL collectives are capturable: one replay per step
+        torch.cuda.synchronize()
 
     def boundary(timed):
-        """Unroll boundary: the sub-batch streams join the main stream; at N > 1 the one exchange of SURVEY 8e runs there."""
+        """Unroll boundary (where the PPO update would sit): the sub-batch streams join the main stream; at N > 1 so does the
+        communication stream -- the wait for the slices still in flight is the exposed part of the exchange."""
         for st in streams:
             ev = torch.cuda.Event()
             ev.record(st)
@@ -429,7 +453,7 @@ def run_rollout(args, rank, world, dev, local):
         if world > 1:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(main)
-            dist.all_gather_into_tensor(gathered, roll.flat)
+            main.wait_stream(comm)
             b.record(main)
             if timed:
                 gather_events.append((a, b))
@@ -448,6 +472,13 @@ def run_rollout(args, rank, world, dev, local):
                     key_static[q * m:(q + 1) * m].copy_(key_src[k % n_keys][q * m:(q + 1) * m], non_blocking=True)
                     graphs[(s_, q, t)].replay()
                 n_launched[0] += launches_of[(s_, q, t)]
+            if world > 1:                                                # slice t of the exchange, behind step t of every sub-batch
+                for st in streams:
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                    comm.wait_event(ev)
+                with torch.cuda.stream(comm):
+                    gather_graphs[t].replay()
             if t == T - 1 or k == steps - 1:
                 boundary(timed)
 
@@ -605,10 +636,13 @@ def run_rollout(args, rank, world, dev, local):
             "physics_substeps_per_s": value * 10,
         }
         if world > 1:
-            line["gather"] = {"collective": "ncclAllGather of the rank's rollout buffers (obs 21x(101+212), raw action, log-prob, reward, done, truncation) every 20 steps, inside the timed region",
-                              "count": len(gather_ms), "ms_each": float(np.mean(gather_ms)) if gather_ms else None,
-                              "bytes_sent_per_rank": roll.bytes, "bytes_received_per_rank": (world - 1) * roll.bytes,
-                              "bus_gbs": ((world - 1) * roll.bytes / (np.mean(gather_ms) * 1e-3) / 1e9) if gather_ms else None}
+            line["gather"] = {"collective": "ncclAllGather of the rank's rollout buffers (obs 21x(101+212), raw action, log-prob, reward, done, truncation) into the time-major "
+                                            "[T, world * n, ...] rollout every rank's learner reads, inside the timed region: issued slice by slice on a communication stream "
+                                            "behind the step that makes the slice final (7 collectives per step, captured in one CUDA graph per step), joined at every unroll boundary",
+                              "unrolls": len(gather_ms), "exposed_ms_per_unroll": float(np.mean(gather_ms)) if gather_ms else None,
+                              "bytes_sent_per_rank_per_unroll": roll.bytes, "bytes_received_per_rank_per_unroll": (world - 1) * roll.bytes,
+                              "note": "exposed = the main stream's wait for the communication stream at the boundary (the last step's slices); round 2a issued ONE all-gather of "
+                                      "the whole buffer at the boundary: 0.31 ms at 2 GPUs, 1.33 ms at 8 GPUs per unroll, all of it exposed (profiles/r02k_bench_n2.json, r02m_bench_n8.json)"}
     # release the headline's graphs / envs before the extra legs
     del graphs, graphs_e2e, envs, full
     return line
