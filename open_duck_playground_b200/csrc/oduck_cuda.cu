@@ -94,8 +94,9 @@ __global__ void __launch_bounds__(WPB * 32, CTAS_PER_SM) k_physics(Params p) {
   WarpSmem& s = ws[warp];
   for (int env0 = blockIdx.x * WPB; env0 < p.N; env0 += gridDim.x * WPB) {
     const int env = env0 + warp;
-    if (env >= p.N) { if (!DBG) substep_idle_barriers<HF>(p.nsub); continue; }     // the CTA's other warps synchronise inside the substeps
+    if (env >= p.N) continue;                                  // grid tail: the CTA's other warps synchronise among themselves (L.bar_n)
     Lane L;
+    L.bar_n = 32 * min(WPB, p.N - env0);
     float* ph = p.phys + (size_t)env * PHYS_STRIDE;
     load_env(m, s, L, lane, ph, p.dr + (size_t)env * DR_STRIDE);
     if (p.action) { const int a = m.d_act[lane]; if (a >= 0) L.ctrl = p.action[(size_t)env * m.nu + a]; }
@@ -267,8 +268,9 @@ __global__ void __launch_bounds__(WPB * 32, CTAS_PER_SM) k_step(Params p) {
   const float PI = 3.14159265358979323846f;
   for (int env0 = blockIdx.x * WPB; env0 < p.N; env0 += gridDim.x * WPB) {
     const int env = env0 + warp;
-    if (env >= p.N) { substep_idle_barriers<HF>(c.n_substeps); continue; }   // the CTA's other warps synchronise inside the substeps
+    if (env >= p.N) continue;                                  // grid tail: the CTA's other warps synchronise among themselves (L.bar_n)
     Lane L;
+    L.bar_n = 32 * min(WPB, p.N - env0);
     float* ph = p.phys + (size_t)env * PHYS_STRIDE;
     load_env(m, s, L, lane, ph, p.dr + (size_t)env * DR_STRIDE);
     float* inf = p.info + (size_t)env * INFO_STRIDE;

@@ -13,6 +13,7 @@ struct Lane {
   float mass;                                     // body role
   float imt;                                      // 1 / total mass (constant over the substeps of a launch)
   V3 ipos;
+  int bar_n;                                      // threads that take part in the CTA's phase barriers: 32 x the warps that own an env in this pass
 };
 
 struct LSPoint { float alpha, d0, d1; };
@@ -23,7 +24,9 @@ struct LSPoint { float alpha, d0, d1; };
 // stretch of this ~200 KB instruction stream, so that they share instruction-cache lines instead of each streaming the code
 // from L2 (measured: -15 % kernel time with one barrier per substep).  Every warp of the CTA must execute the same number of
 // barriers: points before the foot-foot early exit exist only in the FF = false instantiation (the FF = true re-run skips
-// them), points after it exist in both; warps without an env call substep_idle_barriers().
+// them), points after it exist in both.  The barrier is a NAMED barrier with an explicit thread count (bar.sync 1, n; n = 32 x
+// the warps that own an env in this pass of the grid-stride loop): warps of the grid tail without an env take no part in it, and
+// warps may arrive from different instantiations (compute-sanitizer synccheck rejects a plain __syncthreads() used that way).
 #ifndef ODUCK_BARRIERS
 #define ODUCK_BARRIERS 0x01
 #endif
@@ -40,11 +43,14 @@ struct LSPoint { float alpha, d0, d1; };
 #define ODUCK_HF_BARRIERS 0x09
 #endif
 #define PHASE_MASK (HF ? (ODUCK_HF_BARRIERS) : (ODUCK_BARRIERS))
-#define PHASE_SYNC(bit, pre_exit) { ODUCK_PHASE_MARK(bit) if (BAR && ((PHASE_MASK >> (bit)) & 1) && (!(pre_exit) || !FF)) __syncthreads(); }
-template <bool HF>
-__device__ __forceinline__ void substep_idle_barriers(int substeps) {
-  for (int k = 0; k < substeps * __popc(PHASE_MASK & 0x3f); ++k) __syncthreads();
+__device__ __forceinline__ void phase_barrier(const int nthreads) {
+#ifdef ODUCK_WARP_EMU
+  __syncthreads();
+#else
+  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+#endif
 }
+#define PHASE_SYNC(bit, pre_exit) { ODUCK_PHASE_MARK(bit) if (BAR && ((PHASE_MASK >> (bit)) & 1) && (!(pre_exit) || !FF)) phase_barrier(L.bar_n); }
 
 // root-to-leaf sweep after chol_rev_tree: table-free on the chain plans, level-parallel with the ancestor table otherwise
 __device__ __forceinline__ float back_tree(const DevModel& m, const float* L, int n, int lane, float y) {

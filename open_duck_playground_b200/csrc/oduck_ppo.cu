@@ -578,7 +578,9 @@ __global__ void __launch_bounds__(256) k_ppo_reduce_adam(const SegTable* __restr
   if (blockIdx.x == 0 && threadIdx.x == 0) step[0] += 1;
 }
 
-// flat gradient <- split-K partials (kernels) / per-warp column sums (biases); per-block sum of squares for the global norm
+// flat gradient <- split-K partials (kernels) / per-warp column sums (biases); per-block sum of squares for the global norm.
+// Quads of 4 consecutive elements like the fused kernel above (float4 partial loads, 8 in flight; same summation order as the
+// scalar reduce_partials): the scalar version of this kernel took 29 us per minibatch (profiles/r02d_launches_ppo_tf32.csv).
 __global__ void __launch_bounds__(256) k_ppo_grad_reduce(const SegTable* __restrict__ tbp, const float* __restrict__ partial, float* __restrict__ grads, float* __restrict__ sumsq_part) {
   __shared__ double sh[32];
   __shared__ SegTable tb;
@@ -587,12 +589,14 @@ __global__ void __launch_bounds__(256) k_ppo_grad_reduce(const SegTable* __restr
   for (int i = threadIdx.x; i < (int)(sizeof(SegTable) / 4); i += blockDim.x) reinterpret_cast<int*>(&tb)[i] = reinterpret_cast<const int*>(tbp)[i];
   __syncthreads();
   double ss = 0.0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tb.total; i += (long long)gridDim.x * blockDim.x) {
-    const Seg& s = find_seg(tb, i);
-    if (s.bias) continue;                                  // reduce_biases owns the bias elements
-    const float g = reduce_partials(s, partial, i - s.off);
-    grads[i] = g;
-    ss += (double)g * g;
+  const long long nquad = (tb.total + 3) >> 2;
+  for (long long qd = (long long)blockIdx.x * blockDim.x + threadIdx.x; qd < nquad; qd += (long long)gridDim.x * blockDim.x) {
+    unsigned skip;
+    const float4 x = reduce_quad(tb, partial, qd * 4, skip);               // bias elements are skipped: reduce_biases owns them
+    const float* px = reinterpret_cast<const float*>(&x);
+    if (skip == 0u) *reinterpret_cast<float4*>(grads + qd * 4) = x;
+    else for (int e = 0; e < 4; ++e) if (!((skip >> e) & 1u)) grads[qd * 4 + e] = px[e];
+    for (int e = 0; e < 4; ++e) if (!((skip >> e) & 1u)) ss += (double)px[e] * px[e];
   }
   reduce_biases(tb, partial, grads, ss);
   const double t = block_sum(ss, sh);
@@ -629,8 +633,62 @@ __global__ void __launch_bounds__(256) k_ppo_adam(const SegTable* __restrict__ t
     }
   }
   __syncthreads();
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tb.total; i += (long long)gridDim.x * blockDim.x)
-    adam_element(find_seg(tb, i), i, update ? grads[i] : 0.f, s_scale, s_c1, s_c2, lr, b1, b2, eps, params, m1, m2, packed, update != 0);
+  // quads of 4 consecutive elements: one segment lookup, float4 loads / stores of the gradient, the master weights and both
+  // moments, and the dX operand form R(W) of a quad is one float4 per half (4 consecutive out features of one in feature)
+  const long long nquad = (tb.total + 3) >> 2;
+  for (long long qd = (long long)blockIdx.x * blockDim.x + threadIdx.x; qd < nquad; qd += (long long)gridDim.x * blockDim.x) {
+    const long long i0 = qd * 4;
+    const Seg& sg = find_seg(tb, i0);
+    const unsigned j = (unsigned)(i0 - sg.off);
+    const unsigned len = sg.bias ? (unsigned)sg.N : (unsigned)sg.K * (unsigned)sg.N;
+    if (!((sg.N & 3) == 0 && j + 4 <= len && !sg.bias)) {             // ragged quad (a bias tensor, a 1-wide head, a segment border): element by element
+      for (int e = 0; e < 4; ++e) {
+        const long long i = i0 + e;
+        if (i < tb.total) adam_element(find_seg(tb, i), i, update ? grads[i] : 0.f, s_scale, s_c1, s_c2, lr, b1, b2, eps, params, m1, m2, packed, update != 0);
+      }
+      continue;
+    }
+    float4 w4 = *reinterpret_cast<const float4*>(params + i0);
+    float* w = reinterpret_cast<float*>(&w4);
+    if (update) {
+      const float4 g4 = *reinterpret_cast<const float4*>(grads + i0);
+      float4 a4 = *reinterpret_cast<const float4*>(m1 + i0), v4 = *reinterpret_cast<const float4*>(m2 + i0);
+      const float* g = reinterpret_cast<const float*>(&g4);
+      float* mm = reinterpret_cast<float*>(&a4);
+      float* vv = reinterpret_cast<float*>(&v4);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float ge = g[e] * s_scale;
+        mm[e] = b1 * mm[e] + (1.f - b1) * ge; vv[e] = b2 * vv[e] + (1.f - b2) * ge * ge;
+        w[e] -= lr * (mm[e] * s_c1) / (sqrtf(vv[e] * s_c2) + eps);
+      }
+      *reinterpret_cast<float4*>(m1 + i0) = a4; *reinterpret_cast<float4*>(m2 + i0) = v4; *reinterpret_cast<float4*>(params + i0) = w4;
+    }
+    const int k = (int)(j / (unsigned)sg.N), n = (int)(j - (unsigned)k * (unsigned)sg.N);
+    float hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) gsplit_tf32(w[e], hi[e], lo[e]);
+    {
+      // forward B operand R_nt(W^T): rows = out feature n (4 different rows), contraction over the in feature k
+      const int kch = (sg.K + TC_KC - 1) / TC_KC;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int ne = n + e;
+        const int ntile = sg.nt == 128 ? ne >> 7 : ne >> 5, nrow = ne & (sg.nt - 1);
+        float* blk = packed + sg.wf + ((size_t)ntile * kch + (k >> 5)) * gblk_b(sg.nt);
+        const int off = gblk_off(nrow, k & 31);
+        blk[off] = hi[e]; blk[sg.nt * TC_KC + off] = lo[e];
+      }
+    }
+    if (sg.wb >= 0) {
+      // dX B operand R(W): row = in feature k, the 4 out features n .. n + 3 are one 16-byte core-matrix row segment
+      const int nch = (sg.N + TC_KC - 1) / TC_KC;
+      float* blk = packed + sg.wb + ((size_t)(k >> 7) * nch + (n >> 5)) * GBLK_A;
+      const int off = gblk_off(k & 127, n & 31);
+      *reinterpret_cast<float4*>(blk + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<float4*>(blk + TC_M * TC_KC + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
   if (update) {
     __threadfence();
     __syncthreads();
