@@ -10,8 +10,8 @@ One "step" = one rollout step over the whole batch = ``oduck_rollout_step``: act
 rollout buffers (OduckRolloutSink; PPO unroll of 20 steps, common/runner.py:104-118).
 Workload at N = 1: BASELINE.json configs[1] -- ``flat_terrain_backlash`` (the task the metric names), 4096 envs per GPU,
 domain randomisation on, no PPO update.  Envs are independent, so ranks take disjoint env shards (weak scaling: per-GPU work
-fixed).  At N > 1 north_star's one exchange -- the NCCL all-gather of the rollout buffers at the PPO boundary -- is INSIDE
-the timed region: issued slice by slice on a communication stream behind the step that makes the slice final, joined every 20th step.
+fixed).  At N > 1 every 20th step ends with north_star's one exchange, INSIDE the timed region: a single NCCL all-gather of the
+rollout buffers (``--gather sliced`` issues it slice by slice behind the steps instead -- measured slower).
 
 The rank's envs run as P sub-batches (``--pipeline``, default 4), each with its own library handle, CUDA-graph chain and stream:
 4096 envs are 1.73 waves of ``k_step`` and a latency-bound wave costs the same full or not, so sub-batch q + 1's step k fills the
@@ -77,7 +77,7 @@ def workload_config(task, n, world, pipeline):
             "parallelism": f"env-shard x{world}", "pipeline": pipeline,
             "l2": f"{sets} env sets rotated, {sets * n * STATE_BYTES_PER_ENV / 1e6:.0f} MB working set > L2",
             "launch": f"{pipeline} sub-batches per GPU, one CUDA graph per (env set, sub-batch, unroll step) replayed on the sub-batch's stream; "
-                      "streams join every 20 steps; at N > 1 the NCCL all-gather of the rollout buffers runs slice by slice behind the steps on a communication stream and is joined there (inside the timed region)"}
+                      "streams join every 20 steps; at N > 1 one NCCL all-gather of the rollout buffers there (inside the timed region)"}
 
 
 class ClockSampler(threading.Thread):
@@ -389,8 +389,20 @@ def run_rollout(args, rank, world, dev, local):
     # block_envs = 0).  Slice t of a field is the contiguous concatenation of every rank's slice t, so the exchange of SURVEY 8e
     # is issued SLICE BY SLICE on a communication stream as soon as step t has made its slice final, under the steps that follow;
     # only the last step's slices are still in flight at the unroll boundary.
-    gathered = {k: torch.empty((v.shape[0], world * n) + tuple(v.shape[2:]), device=dev) for k, v in roll.items()} if world > 1 else None
-    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    # (--gather boundary: ONE all-gather of the whole buffer at the unroll boundary, all of it exposed.)  The slice collectives run on a
+    # process group of their own that is limited to a few CTAs (ncclConfig maxCTAs): they are small and have a whole step to finish,
+    # and every SM they take is taken from a step kernel that owns its SM's entire register file.
+    sliced = world > 1 and args.gather == "sliced"
+    gathered = {k: torch.empty((v.shape[0], world * n) + tuple(v.shape[2:]), device=dev) for k, v in roll.items()} if sliced else None
+    roll.policy_prefix = world > 1 and not sliced                        # obs["state"] = the first 101 columns of obs["privileged_state"]: it stays at home
+    gathered_flat = torch.empty(world * (roll.flat.numel() - roll.skip), device=dev) if (world > 1 and not sliced) else None
+    comm = torch.cuda.Stream(device=dev) if sliced else None
+    gpg = None
+    if sliced and args.gather_max_ctas > 0:
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.config.max_ctas = int(args.gather_max_ctas)
+        opts.config.min_ctas = 1
+        gpg = dist.new_group(list(range(world)), pg_options=opts)
     for row in envs:
         for q, e in enumerate(row):
             ppo.attach_rollout_sink(e, roll, q * m)
@@ -430,12 +442,12 @@ def run_rollout(args, rank, world, dev, local):
         """What step t made final: its Transition (slot t) and the observations after it (slot t + 1; slot 0 with step 0)."""
         for k in ("obs_p", "obs_v"):
             if t == 0:
-                dist.all_gather_into_tensor(gathered[k][0], roll[k][0])
-            dist.all_gather_into_tensor(gathered[k][t + 1], roll[k][t + 1])
+                dist.all_gather_into_tensor(gathered[k][0], roll[k][0], group=gpg)
+            dist.all_gather_into_tensor(gathered[k][t + 1], roll[k][t + 1], group=gpg)
         for k in ("raw", "logp", "reward", "done", "trunc"):
-            dist.all_gather_into_tensor(gathered[k][t], roll[k][t])
+            dist.all_gather_into_tensor(gathered[k][t], roll[k][t], group=gpg)
 
-    if world > 1:
+    if sliced:
         with torch.cuda.stream(comm):
             gather_slice(0)                                              # communicator set-up outside the captures
         torch.cuda.synchronize()
@@ -453,7 +465,10 @@ def run_rollout(args, rank, world, dev, local):
         if world > 1:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(main)
-            main.wait_stream(comm)
+            if sliced:
+                main.wait_stream(comm)
+            else:
+                dist.all_gather_into_tensor(gathered_flat, roll.flat[roll.skip:])
             b.record(main)
             if timed:
                 gather_events.append((a, b))
@@ -472,7 +487,7 @@ def run_rollout(args, rank, world, dev, local):
                     key_static[q * m:(q + 1) * m].copy_(key_src[k % n_keys][q * m:(q + 1) * m], non_blocking=True)
                     graphs[(s_, q, t)].replay()
                 n_launched[0] += launches_of[(s_, q, t)]
-            if world > 1:                                                # slice t of the exchange, behind step t of every sub-batch
+            if sliced:                                                   # slice t of the exchange, behind step t of every sub-batch
                 for st in streams:
                     ev = torch.cuda.Event()
                     ev.record(st)
@@ -636,13 +651,21 @@ def run_rollout(args, rank, world, dev, local):
             "physics_substeps_per_s": value * 10,
         }
         if world > 1:
-            line["gather"] = {"collective": "ncclAllGather of the rank's rollout buffers (obs 21x(101+212), raw action, log-prob, reward, done, truncation) into the time-major "
-                                            "[T, world * n, ...] rollout every rank's learner reads, inside the timed region: issued slice by slice on a communication stream "
-                                            "behind the step that makes the slice final (7 collectives per step, captured in one CUDA graph per step), joined at every unroll boundary",
-                              "unrolls": len(gather_ms), "exposed_ms_per_unroll": float(np.mean(gather_ms)) if gather_ms else None,
-                              "bytes_sent_per_rank_per_unroll": roll.bytes, "bytes_received_per_rank_per_unroll": (world - 1) * roll.bytes,
-                              "note": "exposed = the main stream's wait for the communication stream at the boundary (the last step's slices); round 2a issued ONE all-gather of "
-                                      "the whole buffer at the boundary: 0.31 ms at 2 GPUs, 1.33 ms at 8 GPUs per unroll, all of it exposed (profiles/r02k_bench_n2.json, r02m_bench_n8.json)"}
+            gbytes = roll.bytes - 4 * roll.skip
+            gms = float(np.mean(gather_ms)) if gather_ms else None
+            if sliced:
+                line["gather"] = {"mode": "sliced", "max_ctas": args.gather_max_ctas,
+                                  "collective": "ncclAllGather of the rollout into the time-major [T, world * n, ...] layout, issued slice by slice on a communication stream behind the "
+                                                "step that makes the slice final (7 collectives per step, one captured graph per step), joined at every unroll boundary",
+                                  "unrolls": len(gather_ms), "exposed_ms_per_unroll": gms, "bytes_sent_per_rank_per_unroll": gbytes,
+                                  "note": "measured slower than one gather at the boundary at 2 and 8 GPUs (profiles/r02q_bench_n*_sliced_*.json): 140 small collectives per unroll"}
+            else:
+                line["gather"] = {"mode": "boundary",
+                                  "collective": "ONE ncclAllGather of the rank's rollout buffers at every unroll boundary (where the PPO update would sit), inside the timed region: "
+                                                "obs privileged 21 x 212 (obs state is its first 101 columns and stays at home: the learner reads it in place, OduckRollout.obs_policy_ld), "
+                                                "raw action, log-prob, reward, done, truncation; the gathered rank-major blocks are what the learner consumes (block_envs / block_stride)",
+                                  "unrolls": len(gather_ms), "ms_each": gms, "bytes_sent_per_rank": gbytes, "bytes_received_per_rank": (world - 1) * gbytes,
+                                  "bus_gbs": ((world - 1) * gbytes / (gms * 1e-3) / 1e9) if gms else None}
     # release the headline's graphs / envs before the extra legs
     del graphs, graphs_e2e, envs, full
     return line
@@ -663,6 +686,9 @@ def main():
     ap.add_argument("--ppo-pipeline", type=int, default=2, help="PPOConfig.rollout_pipeline of the ppo leg / mode")
     ap.add_argument("--rough-envs", type=int, default=16384, help="total envs of the rough leg / mode (BASELINE configs[3]: 16384, split over the ranks)")
     ap.add_argument("--learner-matmul", default="fp32", choices=["fp32", "tf32"], help="PPOConfig.learner_matmul of the ppo leg / mode")
+    ap.add_argument("--gather", default=os.environ.get("ODUCK_BENCH_GATHER", "boundary"), choices=["sliced", "boundary"],
+                    help="N > 1: the all-gather of the rollout slice by slice behind the steps (communication stream), or once at the unroll boundary")
+    ap.add_argument("--gather-max-ctas", type=int, default=int(os.environ.get("ODUCK_BENCH_GATHER_MAX_CTAS", "4")), help="CTA limit of the slice collectives' NCCL group (0: the default group)")
     ap.add_argument("--update-mode", default="auto", choices=["auto", "sharded", "replicated"], help="ppo mode at N > 1")
     ap.add_argument("--mode", default="rollout", choices=["rollout", "ppo", "physics", "rough"],
                     help="ppo = BASELINE configs[2] alone; physics = oduck_physics_substeps(10) alone; rough = configs[3] alone")
@@ -719,7 +745,7 @@ def main():
         # BASELINE configs[1] literal, [2], [3] as extra keys of the one line (short legs, all ranks take part)
         for key, fn in (("physics_only", lambda: leg_physics(args, rank, world, dev, steps=30)),
                         ("ppo", lambda: leg_ppo(args, rank, world, dev)),
-                        ("ppo_tf32", lambda: leg_ppo(args, rank, world, dev, steps=2, warmup=1, matmul="tf32")),
+                        ("ppo_tf32", lambda: leg_ppo(args, rank, world, dev, steps=3, warmup=2, matmul="tf32")),
                         ("rough", lambda: leg_rough(args, rank, world, dev, total_envs=args.rough_envs))):
             try:
                 torch.cuda.empty_cache()

@@ -67,6 +67,11 @@ typedef struct OduckRollout {
    * f + (e / block_envs) * block_stride + (t * block_envs + e % block_envs) * width.  block_envs = 0: one block of N envs. */
   int32_t block_envs;
   int64_t block_stride;
+  /* Floats between consecutive env rows of obs_policy; 0 = the policy observation size (a dense [T + 1][N][policy_dim] tensor).
+   * Both reference envs build the value observation as hstack([state, privileged tail]) (joystick.py:596-615, standing.py), so the
+   * policy observation is its first policy_dim columns: a caller may pass obs_policy = obs_value with obs_policy_ld = value_dim and
+   * keep / all-gather ONE observation tensor instead of two (30 % fewer bytes in the exchange of SURVEY 8e). */
+  int32_t obs_policy_ld;
 } OduckRollout;
 
 /* Observation normaliser (brax running_statistics): obs_n = (obs - mean) / std per feature. */

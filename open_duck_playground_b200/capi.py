@@ -118,7 +118,7 @@ class OduckRollout(C.Structure):
         ("num_envs", i32), ("unroll", i32),
         ("obs_policy", C.c_void_p), ("obs_value", C.c_void_p), ("raw_action", C.c_void_p), ("log_prob", C.c_void_p),
         ("reward", C.c_void_p), ("done", C.c_void_p), ("truncation", C.c_void_p),
-        ("block_envs", i32), ("block_stride", C.c_int64),
+        ("block_envs", i32), ("block_stride", C.c_int64), ("obs_policy_ld", i32),
     ]
 
 

@@ -685,9 +685,27 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
     const float Dfe = hasf ? Df : 0.f;
     const float fq1 = Dfe * jvf * Jf, fq2 = Dfe * jvf * jvf, flin = hasf ? floss * jvf : 0.f;
     const float lq1 = Dl * jvl * Jl, lq2 = Dl * jvl * jvl;
-    float cq1[4], cq2[4];
+    // Contact rows of the search.  The four pyramid rows of contact c live in lane c < 8 (12 with the foot-foot contacts), but a
+    // trial point costs the WARP the same whether 8 lanes or 32 evaluate a row, so without foot-foot contacts (FF = false: 8
+    // contacts = 32 rows) the rows are dealt out one per lane for the search: row r of contact c goes to lane 4 c + r (four
+    // shuffles per quantity, once per substep), and every slope / cost evaluation handles one contact row instead of four
+    // (17 slope evaluations per substep).  The foot-foot instantiation (rare path) keeps four rows in its contact lanes.
+    constexpr int NCR = FF ? 4 : 1;
+    float tJ[NCR], tjv[NCR], cq1[NCR], cq2[NCR], tD;
+    if constexpr (FF) {
+      tD = Dc;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) { cq1[r] = Dc * jvc[r] * Jc[r]; cq2[r] = Dc * jvc[r] * jvc[r]; }
+      for (int r = 0; r < 4; ++r) { tJ[r] = Jc[r]; tjv[r] = jvc[r]; }
+    } else {
+      const int sc = lane >> 2, sr = lane & 3;
+      const float j0 = __shfl_sync(FULLMASK, Jc[0], sc), j1 = __shfl_sync(FULLMASK, Jc[1], sc), j2 = __shfl_sync(FULLMASK, Jc[2], sc), j3 = __shfl_sync(FULLMASK, Jc[3], sc);
+      const float v0 = __shfl_sync(FULLMASK, jvc[0], sc), v1 = __shfl_sync(FULLMASK, jvc[1], sc), v2 = __shfl_sync(FULLMASK, jvc[2], sc), v3_ = __shfl_sync(FULLMASK, jvc[3], sc);
+      tJ[0] = sr == 0 ? j0 : (sr == 1 ? j1 : (sr == 2 ? j2 : j3));
+      tjv[0] = sr == 0 ? v0 : (sr == 1 ? v1 : (sr == 2 ? v2 : v3_));
+      tD = __shfl_sync(FULLMASK, Dc, sc);
+    }
+#pragma unroll
+    for (int r = 0; r < NCR; ++r) { cq1[r] = tD * tjv[r] * tJ[r]; cq2[r] = tD * tjv[r] * tjv[r]; }
     // lane-local slope and curvature at alpha
     auto slope = [&](const float alpha, float& d0, float& d1) {
       const float x = Jf + alpha * jvf;
@@ -696,8 +714,8 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
       d1 = quad ? fq2 : 0.f;
       if (Jl + alpha * jvl < 0.f) { d0 += fmaf(alpha, lq2, lq1); d1 += lq2; }
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
-        if (Jc[r] + alpha * jvc[r] < 0.f) { d0 += fmaf(alpha, cq2[r], cq1[r]); d1 += cq2[r]; }
+      for (int r = 0; r < NCR; ++r)
+        if (tJ[r] + alpha * tjv[r] < 0.f) { d0 += fmaf(alpha, cq2[r], cq1[r]); d1 += cq2[r]; }
     };
     // lane-local cost at alpha
     auto cost = [&](const float alpha) {
@@ -710,8 +728,8 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
       }
       if (Jl + alpha * jvl < 0.f) { q0 += 0.5f * Dl * Jl * Jl; q1 += lq1; q2 += 0.5f * lq2; }
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
-        if (Jc[r] + alpha * jvc[r] < 0.f) { q0 += 0.5f * Dc * Jc[r] * Jc[r]; q1 += cq1[r]; q2 += 0.5f * cq2[r]; }
+      for (int r = 0; r < NCR; ++r)
+        if (tJ[r] + alpha * tjv[r] < 0.f) { q0 += 0.5f * tD * tJ[r] * tJ[r]; q1 += cq1[r]; q2 += 0.5f * cq2[r]; }
       return fmaf(alpha, fmaf(alpha, q2, q1), q0);
     };
 #define LS_FINISH(pt, sd0, sd1)                                                                                        \

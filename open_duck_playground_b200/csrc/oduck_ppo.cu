@@ -101,7 +101,7 @@ __device__ __forceinline__ size_t ro_off(const int be, const long long bstride, 
 // Gather the minibatch rows (row = t * B + b <- env idx[b] at time t), normalise, emit R(X) and R(X^T).
 // One thread per 4 x 4 micro-tile (4 rows x 4 features): both layouts keep 4 consecutive k (R(X)) / 4 consecutive rows
 // (R(X^T)) contiguous, so every store is a float4.
-__global__ void k_ppo_pack(const float* __restrict__ obs, int be, long long bstride, int K, const int* __restrict__ idx, int B, int M, int Mpad, int kch,
+__global__ void k_ppo_pack(const float* __restrict__ obs, int be, long long bstride, int ld, int K, const int* __restrict__ idx, int B, int M, int Mpad, int kch,
                            const float* __restrict__ mean, const float* __restrict__ stdv, float* __restrict__ Xr, float* __restrict__ Xt) {
   pdl_launch_dependents();
   pdl_wait();
@@ -115,7 +115,7 @@ __global__ void k_ppo_pack(const float* __restrict__ obs, int be, long long bstr
     for (int a = 0; a < 4; ++a) {
       const int row = row0 + a;
       const float* src = nullptr;
-      if (row < M) { const int t = row / B, b = row - t * B; src = obs + ro_off(be, bstride, t, idx[b], K); }
+      if (row < M) { const int t = row / B, b = row - t * B; src = obs + ro_off(be, bstride, t, idx[b], ld); }
 #pragma unroll
       for (int e = 0; e < 4; ++e) { const int k = k0 + e; v[a][e] = (src && k < K) ? (src[k] - mean[k]) / stdv[k] : 0.f; }
     }
@@ -965,6 +965,7 @@ int oduck_ppo_minibatch(OduckPpo* h, const OduckRollout* ro, const OduckNormaliz
                         const uint32_t* key, int stages, void* stream) {
   if (!h || !ro || !nm || !env_idx) return oduck_fail(ODUCK_ERR_ARG, "oduck_ppo_minibatch: bad argument");
   if (ro->unroll != h->T || ro->num_envs < 1) return oduck_fail(ODUCK_ERR_ARG, "oduck_ppo_minibatch: rollout shape does not match the learner");
+  if (ro->obs_policy_ld != 0 && ro->obs_policy_ld < h->net[0].dims[0]) return oduck_fail(ODUCK_ERR_ARG, "oduck_ppo_minibatch: obs_policy_ld smaller than the policy observation");
   if (ro->block_envs < 0 || (ro->block_envs > 0 && ro->num_envs % ro->block_envs)) return oduck_fail(ODUCK_ERR_ARG, "oduck_ppo_minibatch: num_envs must be a multiple of block_envs");
   const int be = ro->block_envs > 0 ? ro->block_envs : ro->num_envs;
   if ((stages & ODUCK_PPO_STAGE_LOSS) && !noise && !key) return oduck_fail(ODUCK_ERR_ARG, "oduck_ppo_minibatch: entropy term needs noise or a key");
@@ -980,10 +981,10 @@ int oduck_ppo_minibatch(OduckPpo* h, const OduckRollout* ro, const OduckNormaliz
 #define JOIN() { PPO_TRY(cudaEventRecord(h->ev_join, h->side)); PPO_TRY(cudaStreamWaitEvent(st, h->ev_join, 0)); }
   if (stages & ODUCK_PPO_STAGE_FORWARD) {
     FORK()
-    GEMM_TRY(launch_kernel(k_ppo_pack, dim3(296), dim3(256), 0, h->side, h->pdl, ro->obs_value, be, (long long)ro->block_stride, nv.dims[0], env_idx, h->B, nv.M, nv.Mpad, ceil_div(nv.dims[0], TC_KC), nm->value_mean, nm->value_std, nv.Xr[0], nv.Xt[0]));
+    GEMM_TRY(launch_kernel(k_ppo_pack, dim3(296), dim3(256), 0, h->side, h->pdl, ro->obs_value, be, (long long)ro->block_stride, nv.dims[0], nv.dims[0], env_idx, h->B, nv.M, nv.Mpad, ceil_div(nv.dims[0], TC_KC), nm->value_mean, nm->value_std, nv.Xr[0], nv.Xt[0]));
     int rc = net_forward(h, 1, simt, h->side);
     if (rc) return rc;
-    GEMM_TRY(launch_kernel(k_ppo_pack, dim3(296), dim3(256), 0, st, h->pdl, ro->obs_policy, be, (long long)ro->block_stride, np.dims[0], env_idx, h->B, np.M, np.Mpad, ceil_div(np.dims[0], TC_KC), nm->policy_mean, nm->policy_std, np.Xr[0], np.Xt[0]));
+    GEMM_TRY(launch_kernel(k_ppo_pack, dim3(296), dim3(256), 0, st, h->pdl, ro->obs_policy, be, (long long)ro->block_stride, ro->obs_policy_ld > 0 ? ro->obs_policy_ld : np.dims[0], np.dims[0], env_idx, h->B, np.M, np.Mpad, ceil_div(np.dims[0], TC_KC), nm->policy_mean, nm->policy_std, np.Xr[0], np.Xt[0]));
     rc = net_forward(h, 0, simt, st);
     if (rc) return rc;
     JOIN()

@@ -159,6 +159,10 @@ class Joystick:
     def n_substeps(self) -> int:
         return int(round(self.dt / self.sim_dt))
 
+    # obs["privileged_state"][:, :101] IS obs["state"] (joystick.py:596-615: privileged_state = hstack([state, ...]); the kernels write
+    # the same values into both records, csrc/oduck_env.cuh write_obs): a learner may read its policy rows out of the value rows
+    privileged_obs_has_state_prefix = True
+
     @property
     def observation_size(self) -> Dict[str, tuple]:
         ds, dp = capi.OBS_DIMS[self.TASK]

@@ -268,6 +268,15 @@ class RolloutBuffers(dict):
             off += cnt
         self.bytes = total * 4
         self.T, self.n = T, n
+        # The policy observation is the first dp columns of the value observation (both reference envs: privileged_state =
+        # hstack([state, ...]), joystick.py:596-615): when the owner says so, the exchange leaves obs_p at home -- the gathered part
+        # of ``flat`` starts behind it -- and the learner reads the policy rows out of obs_v (OduckRollout.obs_policy_ld).
+        self.policy_prefix = False
+
+    @property
+    def skip(self) -> int:
+        """Leading floats of ``flat`` that do not travel in the all-gather."""
+        return self.offsets["obs_v"][0] if self.policy_prefix else 0
 
 
 class GatheredRollout:
@@ -277,14 +286,17 @@ class GatheredRollout:
 
     def __init__(self, gathered: torch.Tensor, local: RolloutBuffers, world: int):
         self.flat, self.local, self.world = gathered, local, world
-        self.block_stride = local.flat.numel()
+        self.skip = local.skip
+        self.block_stride = local.flat.numel() - self.skip
         self._cache: Dict[str, torch.Tensor] = {}
 
     def blocks(self, key: str) -> torch.Tensor:
         """[world, T(+1), n, ...] view of a field."""
+        if key == "obs_p" and self.skip:                                # stayed at home: the leading columns of obs_v
+            return self.blocks("obs_v")[..., :self.local["obs_p"].shape[-1]]
         off, shape = self.local.offsets[key]
         cnt = int(np.prod(shape))
-        return self.flat.view(self.world, self.block_stride)[:, off:off + cnt].view(self.world, *shape)
+        return self.flat.view(self.world, self.block_stride)[:, off - self.skip:off - self.skip + cnt].view(self.world, *shape)
 
     def __getitem__(self, key: str) -> torch.Tensor:
         if key not in self._cache:
@@ -306,8 +318,9 @@ def all_gather_rollout(batch, world: int, out: Optional[torch.Tensor] = None):
     if world == 1:
         return batch
     if isinstance(batch, RolloutBuffers):
-        g = out if out is not None else torch.empty(world * batch.flat.numel(), device=batch.flat.device)
-        dist.all_gather_into_tensor(g, batch.flat)
+        part = batch.flat[batch.skip:]
+        g = out if out is not None else torch.empty(world * part.numel(), device=batch.flat.device)
+        dist.all_gather_into_tensor(g, part)
         return GatheredRollout(g, batch, world)
     res = {}
     for k, v in batch.items():
@@ -392,7 +405,9 @@ def rollout_struct(batch) -> "capi.OduckRollout":
         src = batch.local
         T, n = src["reward"].shape
         ro.num_envs, ro.unroll, ro.block_envs, ro.block_stride = int(batch.world * n), int(T), int(n), int(batch.block_stride)
-        ptr = lambda k: batch.flat.data_ptr() + 4 * src.offsets[k][0]                    # noqa: E731  (block 0's field)
+        ptr = lambda k: batch.flat.data_ptr() + 4 * (src.offsets[k][0] - batch.skip)     # noqa: E731  (block 0's field)
+        if batch.skip:                                                                    # policy rows = leading columns of the value rows
+            ro.obs_policy_ld = int(src["obs_v"].shape[-1])
     else:
         T, N = batch["reward"].shape
         for k, v in batch.items():
@@ -400,7 +415,7 @@ def rollout_struct(batch) -> "capi.OduckRollout":
                 raise ValueError(f"rollout tensor {k} must be contiguous float32")
         ro.num_envs, ro.unroll, ro.block_envs, ro.block_stride = int(N), int(T), 0, 0
         ptr = lambda k: batch[k].data_ptr()                                               # noqa: E731
-    ro.obs_policy, ro.obs_value, ro.raw_action = ptr("obs_p"), ptr("obs_v"), ptr("raw")
+    ro.obs_policy, ro.obs_value, ro.raw_action = ptr("obs_v" if ro.obs_policy_ld else "obs_p"), ptr("obs_v"), ptr("raw")
     ro.log_prob, ro.reward, ro.done, ro.truncation = ptr("logp"), ptr("reward"), ptr("done"), ptr("trunc")
     return ro
 
@@ -512,8 +527,13 @@ class PPOTrainer:
 
     def _new_buffers(self) -> RolloutBuffers:
         cfg, env = self.cfg, self.env
-        return RolloutBuffers(cfg.unroll_length, self.n_local, env.observation_size[cfg.policy_obs_key][0], env.observation_size[cfg.value_obs_key][0],
-                              env.action_size, env.device)
+        buf = RolloutBuffers(cfg.unroll_length, self.n_local, env.observation_size[cfg.policy_obs_key][0], env.observation_size[cfg.value_obs_key][0],
+                             env.action_size, env.device)
+        # obs["privileged_state"] starts with obs["state"] in both reference envs (joystick.py:596-615, standing.py): the exchange
+        # then carries one observation tensor (device learner only: the PyTorch twin reads obs_p as a tensor of its own)
+        buf.policy_prefix = bool(getattr(env, "privileged_obs_has_state_prefix", False) and cfg.policy_obs_key == "state"
+                                 and cfg.value_obs_key == "privileged_state" and self.dev_learner is not None)
+        return buf
 
     def _attach(self, buf) -> None:
         if self._sink_buf is not buf:
@@ -915,7 +935,7 @@ class PPOTrainer:
             out = None
             if self._roll is not None and local is self._roll["buf"]:            # persistent (graph-static) gather buffer
                 if self._roll.get("gathered") is None:
-                    self._roll["gathered"] = torch.empty(self.world * local.flat.numel(), device=local.flat.device)
+                    self._roll["gathered"] = torch.empty(self.world * (local.flat.numel() - local.skip), device=local.flat.device)
                 out = self._roll["gathered"]
             batch = all_gather_rollout(local, self.world, out)
         if ev: ev[2].record()

@@ -418,6 +418,24 @@ def test_learner_reads_the_gathered_rank_major_blocks_in_place():
         grads.append((L.grads.clone(), L.view("ADV").clone(), list(L.losses.tolist())))
     assert torch.equal(grads[0][0], grads[1][0]) and torch.equal(grads[0][1], grads[1][1])
     assert np.allclose(grads[0][2], grads[1][2], rtol=1e-12, atol=0)      # the reported losses are fp64 atomic sums: order-dependent in the last bits
+    # The same with the policy observation left at home: obs["privileged_state"] starts with obs["state"] (joystick.py:596-615), so the
+    # exchange may carry obs_v only and the learner reads its policy rows out of it (OduckRollout.obs_policy_ld = 212).
+    for b in bufs:
+        b["obs_v"][..., :101].copy_(b["obs_p"])
+        b.policy_prefix = True
+    assert bufs[0].skip == bufs[0]["obs_p"].numel()
+    g2 = ppo.GatheredRollout(torch.cat([b.flat[b.skip:] for b in bufs]), bufs[0], world)
+    assert g2.block_stride == bufs[0].flat.numel() - bufs[0].skip and torch.equal(g2["obs_p"], torch.cat([b["obs_p"] for b in bufs], dim=1))
+    tm2 = {k: g2[k] for k in g2.keys()}
+    grads2 = []
+    for batch in (tm2, g2):
+        L = ppo.DeviceLearner(cfg, policy, value, B, 14, dev)
+        ro = ppo.rollout_struct(batch)
+        assert ro.obs_policy_ld == (212 if batch is g2 else 0) and (batch is not g2 or ro.obs_policy == ro.obs_value)
+        L.minibatch(ro, nm, idx.data_ptr(), noise.data_ptr(), 0, capi.PPO_STAGE_FORWARD | capi.PPO_STAGE_LOSS | capi.PPO_STAGE_BACKWARD)
+        torch.cuda.synchronize()
+        grads2.append(L.grads.clone())
+    assert torch.equal(grads2[0], grads2[1]) and grads2[0].abs().max().item() > 0
     assert grads[0][0].abs().max().item() > 0
 
 
