@@ -270,8 +270,12 @@ def test_graphed_rollout_equals_eager_rollout():
         torch.cuda.synchronize()
         out[graph] = (tr.dev_learner.params.clone(), tr._roll["buf"]["reward"].clone() if graph else None, m)
         assert math.isfinite(m["loss"])
-    # (the graphed update uses the two-kernel reduce + Adam tail: same gradients, the global norm is summed in another grouping)
-    assert (out[False][0] - out[True][0]).abs().max().item() < 1e-6
+    # (the graphed update uses the two-kernel reduce + Adam tail: same gradients, the global norm is summed in another grouping, so the
+    # clip factor differs in its last bit.  Adam's first steps move a weight by ~lr * sign(m): an element whose gradient sits at zero
+    # within that bit may step the other way -- at most a 1e-4 fraction of the elements, by at most lr per step; all others agree to 1e-6.
+    # Measured on B200: 0 or 1 such element of 490 k, profiles/r02r_pytest_gpu.log.)
+    d = (out[False][0] - out[True][0]).abs()
+    assert (d > 1e-6).float().mean().item() < 1e-4 and d.max().item() < 3 * 2 * 3e-4, (float((d > 1e-6).float().mean()), float(d.max()))
 
 
 @pytest.mark.gpu
