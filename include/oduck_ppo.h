@@ -124,6 +124,13 @@ int oduck_ppo_get_buffer(OduckPpo* p, int id, void** ptr, int64_t* count, int* d
  * With world_size > 1 the caller runs stages FORWARD|LOSS|BACKWARD, all-reduces buffer GRADS (mean), then ADAM. */
 int oduck_ppo_minibatch(OduckPpo* p, const OduckRollout* rollout, const OduckNormalizer* norm, const int32_t* env_idx,
                         const float* entropy_noise, const uint32_t* entropy_key, int stages, void* stream);
+/* Optional, call it right AFTER the oduck_ppo_minibatch of the current minibatch (same stream, stages including FORWARD): packs the
+ * observation operands of the NEXT minibatch (env trajectories next_env_idx[0..B)) into the learner's alternate input buffers on
+ * a side stream forked from the START of the current minibatch, i.e. beside its kernels.  The next oduck_ppo_minibatch call
+ * whose env_idx pointer equals next_env_idx waits for that side stream and skips its own gather / normalise / pack pass (13 us
+ * on the critical path of a 0.2 ms step).  The rollout, the normaliser and next_env_idx must not change until then.  Capturable
+ * like oduck_ppo_minibatch (inside one capture: never before the first oduck_ppo_minibatch, never after the last). */
+int oduck_ppo_prefetch(OduckPpo* p, const OduckRollout* rollout, const OduckNormalizer* norm, const int32_t* next_env_idx, void* stream);
 /* Kernels launched since create (bench `gpu_launches`). */
 int64_t oduck_ppo_launch_count(const OduckPpo* p);
 

@@ -215,6 +215,7 @@ class Library:
             L.oduck_ppo_set_params.argtypes = [vp, vp, C.c_int, vp]
             L.oduck_ppo_get_buffer.argtypes = [vp, C.c_int, p(vp), p(C.c_int64), p(C.c_int)]
             L.oduck_ppo_minibatch.argtypes = [vp, p(OduckRollout), p(OduckNormalizer), vp, vp, vp, C.c_int, vp]
+            L.oduck_ppo_prefetch.argtypes = [vp, p(OduckRollout), p(OduckNormalizer), vp, vp]
             L.oduck_ppo_packed_weights.argtypes = [vp, C.c_int, C.c_int, p(vp)]
         if L.oduck_abi_version() != ABI_VERSION:
             raise OduckError(f"{path}: ABI version {L.oduck_abi_version()} != {ABI_VERSION}")
@@ -344,6 +345,9 @@ class PpoHandle:
 
     def minibatch(self, rollout: OduckRollout, norm: OduckNormalizer, env_idx: int, noise: int, key: int, stages: int, stream: int = 0):
         self.L.check(self.L.lib.oduck_ppo_minibatch(self.h, C.byref(rollout), C.byref(norm), env_idx, noise or None, key or None, stages, stream))
+
+    def prefetch(self, rollout: OduckRollout, norm: OduckNormalizer, next_env_idx: int, stream: int = 0):
+        self.L.check(self.L.lib.oduck_ppo_prefetch(self.h, C.byref(rollout), C.byref(norm), next_env_idx, stream))
 
     def launch_count(self) -> int:
         return int(self.L.lib.oduck_ppo_launch_count(self.h))

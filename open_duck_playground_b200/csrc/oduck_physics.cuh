@@ -17,8 +17,6 @@ struct Lane {
 };
 
 struct LSPoint { float alpha, d0, d1; };
-#define ODUCK_PRAGMA_(x) _Pragma(#x)
-#define ODUCK_PRAGMA(x) ODUCK_PRAGMA_(x)
 
 // FF = false: no foot-foot code is compiled in; if the feet's bounding spheres overlap the function returns true BEFORE
 // touching any persistent state and the caller re-runs the substep with FF = true (rare).
@@ -243,9 +241,7 @@ __device__ __forceinline__ bool forward_euler_impl(const DevModel& m, WarpSmem& 
     *reinterpret_cast<float4*>(&bf[lane][0]) = make_float4(buf.a0, buf.a1, buf.a2, buf.l0);
     *reinterpret_cast<float4*>(&bf[lane][4]) = make_float4(buf.l1, buf.l2, L.arm, 0.f);
     __syncwarp();
-#ifdef ODUCK_MPAIR_UNROLL
-    ODUCK_PRAGMA(unroll ODUCK_MPAIR_UNROLL)
-#endif
+    // (unrolling this loop 2x / 4x changes nothing: 7.82 / 7.84 vs 7.85 M env-steps/s, profiles/r02t_bench_n1_mp*.json)
     for (int pp = lane; pp < m.n_mpairs; pp += 32) {
       const unsigned ij = m.mpair[pp];
       const int i = ij >> 8, j = ij & 255;

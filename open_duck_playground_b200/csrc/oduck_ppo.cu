@@ -86,6 +86,13 @@ struct OduckPpo {
                             // already short, and early-launched CTAs hold SMs / TMEM that the other streams' kernels could use.
   cudaStream_t side;        // the value net's chain runs here, concurrently with the policy net's chain on the caller's stream
   cudaStream_t side_w[2];   // weight-gradient GEMMs of the policy / value net (off the dZ critical path)
+  // input prefetch (oduck_ppo_prefetch): two sets of layer-0 operand buffers per net; x0_sel = the set the current minibatch reads
+  float* X0r[2][2];         // [net][set]
+  float* X0t[2][2];
+  int x0_sel;
+  const int32_t* pf_idx;    // env_idx pointer the other set was packed for (nullptr: nothing prefetched)
+  cudaStream_t pf_stream;
+  cudaEvent_t ev_mb_start, ev_pf_done;
   cudaEvent_t ev_fork, ev_join, ev_join_w[2], ev_dz[2][PPO_NL];
   int coop_blocks;          // co-resident CTAs of the fused reduce + Adam kernel (0: cooperative launch unavailable)
   int num_sms;
@@ -715,6 +722,9 @@ int oduck_ppo_destroy(OduckPpo* h) {
   cudaSetDevice(h->device);
   for (void* q : h->allocs) cudaFree(q);
   if (h->side) cudaStreamDestroy(h->side);
+  if (h->pf_stream) cudaStreamDestroy(h->pf_stream);
+  if (h->ev_mb_start) cudaEventDestroy(h->ev_mb_start);
+  if (h->ev_pf_done) cudaEventDestroy(h->ev_pf_done);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   for (int k = 0; k < 2; ++k) {
@@ -745,6 +755,7 @@ int oduck_ppo_create(const OduckPpoConfig* cfg, int device, OduckPpo** out) {
   h->cfg = *cfg; h->device = device; h->B = B; h->T = T; h->na = na; h->launches = 0;
   { const char* e = getenv("ODUCK_PPO_PDL"); h->pdl = e && e[0] == '1'; }
   h->side = nullptr; h->ev_fork = h->ev_join = nullptr; h->coop_blocks = 0;
+  h->pf_stream = nullptr; h->ev_mb_start = h->ev_pf_done = nullptr; h->x0_sel = 0; h->pf_idx = nullptr; memset(h->X0r, 0, sizeof(h->X0r)); memset(h->X0t, 0, sizeof(h->X0t));
   memset(h->side_w, 0, sizeof(h->side_w)); memset(h->ev_join_w, 0, sizeof(h->ev_join_w)); memset(h->ev_dz, 0, sizeof(h->ev_dz));
   {
     bool sok = cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
@@ -753,6 +764,8 @@ int oduck_ppo_create(const OduckPpoConfig* cfg, int device, OduckPpo** out) {
       sok = cudaStreamCreateWithFlags(&h->side_w[k], cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&h->ev_join_w[k], cudaEventDisableTiming) == cudaSuccess;
       for (int l = 0; l < PPO_NL && sok; ++l) sok = cudaEventCreateWithFlags(&h->ev_dz[k][l], cudaEventDisableTiming) == cudaSuccess;
     }
+    sok = sok && cudaStreamCreateWithFlags(&h->pf_stream, cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&h->ev_mb_start, cudaEventDisableTiming) == cudaSuccess &&
+          cudaEventCreateWithFlags(&h->ev_pf_done, cudaEventDisableTiming) == cudaSuccess;
     if (!sok) { oduck_ppo_destroy(h); return oduck_fail(ODUCK_ERR_CUDA, "oduck_ppo_create: stream / event creation failed"); }
   }
   // ---- parameter segments, packed-operand and partial-gradient layouts
@@ -806,6 +819,11 @@ int oduck_ppo_create(const OduckPpoConfig* cfg, int device, OduckPpo** out) {
       const int K = nb.dims[l];
       ok = ok && dev_alloc(h, nb.Xr[l], (size_t)nb.mtiles * ceil_div(K, TC_KC) * GBLK_A) == 0;
       ok = ok && dev_alloc(h, nb.Xt[l], (size_t)ceil_div(K, 128) * bch * GBLK_A) == 0;
+      if (l == 0) {                                                    // second input set for oduck_ppo_prefetch
+        h->X0r[net][0] = nb.Xr[0]; h->X0t[net][0] = nb.Xt[0];
+        ok = ok && dev_alloc(h, h->X0r[net][1], (size_t)nb.mtiles * ceil_div(K, TC_KC) * GBLK_A) == 0;
+        ok = ok && dev_alloc(h, h->X0t[net][1], (size_t)ceil_div(K, 128) * bch * GBLK_A) == 0;
+      }
       const int N = nb.dims[l + 1];
       if (l < PPO_NL - 1) {
         ok = ok && dev_alloc(h, nb.Z[l], (size_t)nb.Mpad * N) == 0;
@@ -961,6 +979,32 @@ static int net_backward(OduckPpo* h, int net, bool simt, cudaStream_t sx, cudaSt
   return ODUCK_OK;
 }
 
+int oduck_ppo_prefetch(OduckPpo* h, const OduckRollout* ro, const OduckNormalizer* nm, const int32_t* next_env_idx, void* stream) {
+  if (!h || !ro || !nm || !next_env_idx) return oduck_fail(ODUCK_ERR_ARG, "oduck_ppo_prefetch: bad argument");
+  if (ro->unroll != h->T || ro->num_envs < 1) return oduck_fail(ODUCK_ERR_ARG, "oduck_ppo_prefetch: rollout shape does not match the learner");
+  if (ro->block_envs < 0 || (ro->block_envs > 0 && ro->num_envs % ro->block_envs)) return oduck_fail(ODUCK_ERR_ARG, "oduck_ppo_prefetch: num_envs must be a multiple of block_envs");
+  if (ro->obs_policy_ld != 0 && ro->obs_policy_ld < h->net[0].dims[0]) return oduck_fail(ODUCK_ERR_ARG, "oduck_ppo_prefetch: obs_policy_ld smaller than the policy observation");
+  PPO_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int be = ro->block_envs > 0 ? ro->block_envs : ro->num_envs;
+  NetBuf& np = h->net[0];
+  NetBuf& nv = h->net[1];
+  const int alt = h->x0_sel ^ 1;                 // the set the current minibatch does not read (its last reader, the previous
+                                                 // minibatch's layer-0 dW GEMM, is ordered before the current minibatch's start)
+  // fork from the START of the current minibatch (recorded by oduck_ppo_minibatch at its FORWARD stage), not from the tail of
+  // `stream`: the pack then runs beside the current minibatch's kernels
+  (void)st;
+  PPO_TRY(cudaStreamWaitEvent(h->pf_stream, h->ev_mb_start, 0));
+  PPO_TRY(launch_kernel(k_ppo_pack, dim3(296), dim3(256), 0, h->pf_stream, false, ro->obs_value, be, (long long)ro->block_stride, nv.dims[0], nv.dims[0], next_env_idx, h->B, nv.M, nv.Mpad,
+                        ceil_div(nv.dims[0], TC_KC), nm->value_mean, nm->value_std, h->X0r[1][alt], h->X0t[1][alt]));
+  PPO_TRY(launch_kernel(k_ppo_pack, dim3(296), dim3(256), 0, h->pf_stream, false, ro->obs_policy, be, (long long)ro->block_stride, ro->obs_policy_ld > 0 ? ro->obs_policy_ld : np.dims[0], np.dims[0],
+                        next_env_idx, h->B, np.M, np.Mpad, ceil_div(np.dims[0], TC_KC), nm->policy_mean, nm->policy_std, h->X0r[0][alt], h->X0t[0][alt]));
+  PPO_TRY(cudaEventRecord(h->ev_pf_done, h->pf_stream));
+  h->launches += 2;
+  h->pf_idx = next_env_idx;
+  return ODUCK_OK;
+}
+
 int oduck_ppo_minibatch(OduckPpo* h, const OduckRollout* ro, const OduckNormalizer* nm, const int32_t* env_idx, const float* noise,
                         const uint32_t* key, int stages, void* stream) {
   if (!h || !ro || !nm || !env_idx) return oduck_fail(ODUCK_ERR_ARG, "oduck_ppo_minibatch: bad argument");
@@ -980,11 +1024,22 @@ int oduck_ppo_minibatch(OduckPpo* h, const OduckRollout* ro, const OduckNormaliz
 #define FORK() { PPO_TRY(cudaEventRecord(h->ev_fork, st)); PPO_TRY(cudaStreamWaitEvent(h->side, h->ev_fork, 0)); }
 #define JOIN() { PPO_TRY(cudaEventRecord(h->ev_join, h->side)); PPO_TRY(cudaStreamWaitEvent(st, h->ev_join, 0)); }
   if (stages & ODUCK_PPO_STAGE_FORWARD) {
+    // input operands: the set oduck_ppo_prefetch packed for this very minibatch (wait for its stream), or pack them now
+    const bool prefetched = h->pf_idx != nullptr && h->pf_idx == env_idx;
+    if (prefetched) {
+      h->x0_sel ^= 1;
+      PPO_TRY(cudaStreamWaitEvent(st, h->ev_pf_done, 0));
+    }
+    h->pf_idx = nullptr;
+    for (int net = 0; net < 2; ++net) { h->net[net].Xr[0] = h->X0r[net][h->x0_sel]; h->net[net].Xt[0] = h->X0t[net][h->x0_sel]; }
+    PPO_TRY(cudaEventRecord(h->ev_mb_start, st));                     // fork point of a following oduck_ppo_prefetch
     FORK()
-    GEMM_TRY(launch_kernel(k_ppo_pack, dim3(296), dim3(256), 0, h->side, h->pdl, ro->obs_value, be, (long long)ro->block_stride, nv.dims[0], nv.dims[0], env_idx, h->B, nv.M, nv.Mpad, ceil_div(nv.dims[0], TC_KC), nm->value_mean, nm->value_std, nv.Xr[0], nv.Xt[0]));
+    if (!prefetched)
+      GEMM_TRY(launch_kernel(k_ppo_pack, dim3(296), dim3(256), 0, h->side, h->pdl, ro->obs_value, be, (long long)ro->block_stride, nv.dims[0], nv.dims[0], env_idx, h->B, nv.M, nv.Mpad, ceil_div(nv.dims[0], TC_KC), nm->value_mean, nm->value_std, nv.Xr[0], nv.Xt[0]));
     int rc = net_forward(h, 1, simt, h->side);
     if (rc) return rc;
-    GEMM_TRY(launch_kernel(k_ppo_pack, dim3(296), dim3(256), 0, st, h->pdl, ro->obs_policy, be, (long long)ro->block_stride, ro->obs_policy_ld > 0 ? ro->obs_policy_ld : np.dims[0], np.dims[0], env_idx, h->B, np.M, np.Mpad, ceil_div(np.dims[0], TC_KC), nm->policy_mean, nm->policy_std, np.Xr[0], np.Xt[0]));
+    if (!prefetched)
+      GEMM_TRY(launch_kernel(k_ppo_pack, dim3(296), dim3(256), 0, st, h->pdl, ro->obs_policy, be, (long long)ro->block_stride, ro->obs_policy_ld > 0 ? ro->obs_policy_ld : np.dims[0], np.dims[0], env_idx, h->B, np.M, np.Mpad, ceil_div(np.dims[0], TC_KC), nm->policy_mean, nm->policy_std, np.Xr[0], np.Xt[0]));
     rc = net_forward(h, 0, simt, st);
     if (rc) return rc;
     JOIN()

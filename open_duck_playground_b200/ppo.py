@@ -60,6 +60,9 @@ class PPOConfig:
                                     # 0 = auto: 2 on CUDA from 2048 envs per rank (measured on B200: rollout 26.9 -> 25.8 ms at 8192), else 1
     kernel_rollout_writes: bool = True   # the step / actor kernels store each Transition in the rollout buffers themselves
                                     # (oduck_rollout_step); False = the 7 torch copies per step of round 1 (kept as the checker)
+    learner_fused_tail: bool = True  # eager device-learner steps end with the fused cooperative reduce + clip + Adam launch; False: the two plain
+                                     # kernels a captured graph uses (same gradients; the global norm is summed in another grouping, so the
+                                     # clip factor -- and with it every weight -- may differ in its last bit)
     learner_matmul: str = "fp32"    # device learner GEMMs: "fp32" = fp32-faithful (3 tf32 tensor-core passes; the parity-tested default),
                                     # "tf32" = one tf32 pass, XLA's default arithmetic for f32 dots on NVIDIA GPUs (the reference's own)
     learner: str = "auto"           # "device": the fused learner step of include/oduck_ppo.h (tcgen05 GEMMs, fused GAE/loss/Adam kernels);
@@ -395,6 +398,10 @@ class DeviceLearner:
 
     def minibatch(self, rollout: "capi.OduckRollout", norm: "capi.OduckNormalizer", env_idx: int, noise: int = 0, key: int = 0, stages: int = capi.PPO_ALL) -> None:
         self.h.minibatch(rollout, norm, env_idx, noise, key, stages, self._stream())
+
+    def prefetch(self, rollout: "capi.OduckRollout", norm: "capi.OduckNormalizer", next_env_idx: int) -> None:
+        """Pack the NEXT minibatch's observation operands beside the current minibatch's kernels (call right after ``minibatch``)."""
+        self.h.prefetch(rollout, norm, next_env_idx, self._stream())
 
 
 def rollout_struct(batch) -> "capi.OduckRollout":
@@ -862,6 +869,8 @@ class PPOTrainer:
                     with torch.cuda.graph(g):
                         for i in range(nmb):
                             L.minibatch(ro, nm, U["perm"].data_ptr() + 4 * i * B, 0, U["keys"].data_ptr() + 8 * i, FLB)
+                            if i + 1 < nmb:
+                                L.prefetch(ro, nm, U["perm"].data_ptr() + 4 * (i + 1) * B)
                             dist.all_reduce(L.grads, op=dist.ReduceOp.AVG)
                             L.minibatch(ro, nm, U["perm"].data_ptr() + 4 * i * B, 0, U["keys"].data_ptr() + 8 * i, capi.PPO_STAGE_ADAM)
                     U["epoch"] = g
@@ -878,6 +887,8 @@ class PPOTrainer:
                     with torch.cuda.graph(g):
                         for i in range(nmb):
                             L.minibatch(ro, nm, U["perm"].data_ptr() + 4 * i * B, 0, U["keys"].data_ptr() + 8 * i, capi.PPO_ALL | capi.PPO_NO_COOP)
+                            if i + 1 < nmb:                              # the next minibatch's inputs are packed beside this one's kernels
+                                L.prefetch(ro, nm, U["perm"].data_ptr() + 4 * (i + 1) * B)
                     U["epoch"] = g
             except Exception as e:                                                       # capture unsupported: stay eager
                 import sys
@@ -906,13 +917,18 @@ class PPOTrainer:
                     continue
                 idx = perm.data_ptr() + 4 * i * B
                 key = keys.data_ptr() + 8 * j
+                nxt = perm.data_ptr() + 4 * (i + 1) * B if i + 1 < cfg.num_minibatches else 0
                 if sharded:
                     L.minibatch(ro, nm, idx, 0, key, FLB)
+                    if nxt:
+                        L.prefetch(ro, nm, nxt)
                     dist.all_reduce(L.grads)
                     L.grads.div_(self.world)
                     L.minibatch(ro, nm, idx, 0, key, capi.PPO_STAGE_ADAM)
                 else:
-                    L.minibatch(ro, nm, idx, 0, key, capi.PPO_ALL)
+                    L.minibatch(ro, nm, idx, 0, key, capi.PPO_ALL if cfg.learner_fused_tail else (capi.PPO_ALL | capi.PPO_NO_COOP))
+                    if nxt:
+                        L.prefetch(ro, nm, nxt)
         [e.handle.policy_invalidate() for e in self._envs]                                                # the actor repacks the new weights on its next forward
         self._prefetched_keys = self._rollout_keys()                                       # host work of the next unroll, under the GPU's update
         o = L.losses.tolist()                                                              # host sync: the update is done, `keep` may go
