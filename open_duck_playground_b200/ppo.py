@@ -849,9 +849,11 @@ class PPOTrainer:
         # gradient all-reduce when sharded).  Only with the persistent rollout buffers of the graphed unroll (static pointers).
         graphed = cfg.cuda_graph and self._roll is not None and (batch is self._roll["buf"] or (blocked and batch.local is self._roll["buf"] and batch.flat is self._roll.get("gathered")))
         if graphed and getattr(self, "_upd", None) is None:
-            nmb = cfg.num_minibatches
+            nmb, E = cfg.num_minibatches, cfg.num_updates_per_batch
             U = {"idx": torch.zeros(B, dtype=torch.int32, device=dev), "key": torch.zeros(2, dtype=torch.int32, device=dev), "ro": ro, "nm": nm,
-                 "perm": torch.zeros(N, dtype=torch.int32, device=dev), "keys": torch.zeros(nmb, 2, dtype=torch.int32, device=dev)}
+                 "perm": torch.zeros(E * N, dtype=torch.int32, device=dev), "keys": torch.zeros(E * nmb, 2, dtype=torch.int32, device=dev)}
+            mb_idx = lambda j: U["perm"].data_ptr() + 4 * ((j // nmb) * N + (j % nmb) * B)        # noqa: E731  minibatch j = (epoch, i): slice i of epoch's permutation
+            mb_key = lambda j: U["keys"].data_ptr() + 8 * j                                        # noqa: E731
             # plain kernel nodes only: the two-kernel reduce / Adam tail.  (The fused cooperative launch can be captured on this
             # driver as a kernel node with the cooperative attribute, but inside the graph it ran 49 us against 29 + 18 us for the two
             # plain kernels and serialised the side streams: measured on B200, profiles/r02d_launches_ppo_tf32.csv.)
@@ -860,19 +862,19 @@ class PPOTrainer:
                 torch.cuda.synchronize(dev)
                 U["graphs"], U["epoch"] = [], None
                 if sharded and os.environ.get("ODUCK_PPO_GRAPH_NCCL", "1") != "0":
-                    # sharded update, one graph per EPOCH with the gradient all-reduces inside: forward / loss / backward, NCCL
-                    # all-reduce (average) of the flat gradient, clip + Adam, num_minibatches times -- NCCL collectives are
-                    # capturable, so the host issues two copies and one replay per epoch instead of six calls per minibatch
+                    # sharded update, ONE graph for the whole update with the gradient all-reduces inside: forward / loss / backward,
+                    # NCCL all-reduce (average) of the flat gradient, clip + Adam, epochs x num_minibatches times -- NCCL collectives
+                    # are capturable, so the host issues two copies and one replay per update instead of six calls per minibatch
                     dist.all_reduce(torch.zeros(8, device=dev), op=dist.ReduceOp.AVG)       # communicator set up outside the capture
                     torch.cuda.synchronize(dev)
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g):
-                        for i in range(nmb):
-                            L.minibatch(ro, nm, U["perm"].data_ptr() + 4 * i * B, 0, U["keys"].data_ptr() + 8 * i, FLB)
-                            if i + 1 < nmb:
-                                L.prefetch(ro, nm, U["perm"].data_ptr() + 4 * (i + 1) * B)
+                        for j in range(E * nmb):
+                            L.minibatch(ro, nm, mb_idx(j), 0, mb_key(j), FLB)
+                            if j + 1 < E * nmb:
+                                L.prefetch(ro, nm, mb_idx(j + 1))
                             dist.all_reduce(L.grads, op=dist.ReduceOp.AVG)
-                            L.minibatch(ro, nm, U["perm"].data_ptr() + 4 * i * B, 0, U["keys"].data_ptr() + 8 * i, capi.PPO_STAGE_ADAM)
+                            L.minibatch(ro, nm, mb_idx(j), 0, mb_key(j), capi.PPO_STAGE_ADAM)
                     U["epoch"] = g
                 elif sharded:
                     for stg in (FLB, capi.PPO_STAGE_ADAM):
@@ -881,14 +883,15 @@ class PPOTrainer:
                             L.minibatch(ro, nm, U["idx"].data_ptr(), 0, U["key"].data_ptr(), stg)
                         U["graphs"].append(g)
                 else:
-                    # one graph per EPOCH: the num_minibatches SGD steps back to back, minibatch i reading slice i of the static
-                    # permutation / key buffers -- per epoch two small copies and one replay instead of three host calls per minibatch
+                    # ONE graph for the whole update: the epochs x num_minibatches SGD steps back to back, minibatch (epoch, i) reading
+                    # slice i of that epoch's permutation in the static index buffer -- per update two small copies and one replay
+                    # instead of three host calls per minibatch (and no idle GPU while the host shuffles between epochs)
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g):
-                        for i in range(nmb):
-                            L.minibatch(ro, nm, U["perm"].data_ptr() + 4 * i * B, 0, U["keys"].data_ptr() + 8 * i, capi.PPO_ALL | capi.PPO_NO_COOP)
-                            if i + 1 < nmb:                              # the next minibatch's inputs are packed beside this one's kernels
-                                L.prefetch(ro, nm, U["perm"].data_ptr() + 4 * (i + 1) * B)
+                        for j in range(E * nmb):
+                            L.minibatch(ro, nm, mb_idx(j), 0, mb_key(j), capi.PPO_ALL | capi.PPO_NO_COOP)
+                            if j + 1 < E * nmb:                          # the next minibatch's inputs are packed beside this one's kernels
+                                L.prefetch(ro, nm, mb_idx(j + 1))
                     U["epoch"] = g
             except Exception as e:                                                       # capture unsupported: stay eager
                 import sys
@@ -896,14 +899,15 @@ class PPOTrainer:
                 U["graphs"], U["epoch"] = None, None
             self._upd = U
         U = getattr(self, "_upd", None) if graphed else None
-        for e in range(cfg.num_updates_per_batch):
-            perm = torch.randperm(N, generator=gen).to(torch.int32).to(dev)
+        perms = [torch.randperm(N, generator=gen).to(torch.int32) for _ in range(cfg.num_updates_per_batch)]   # (the same draws, in the same order, as epoch by epoch)
+        if U is not None and U.get("epoch") is not None:
+            U["perm"].copy_(torch.cat(perms), non_blocking=True)
+            U["keys"].copy_(keys, non_blocking=True)
+            U["epoch"].replay()
+            perms = []
+        for e, perm in enumerate(perms):
+            perm = perm.to(dev)
             keep.append(perm)
-            if U is not None and U.get("epoch") is not None:
-                U["perm"].copy_(perm, non_blocking=True)
-                U["keys"].copy_(keys[e * cfg.num_minibatches:(e + 1) * cfg.num_minibatches], non_blocking=True)
-                U["epoch"].replay()
-                continue
             for i in range(cfg.num_minibatches):
                 j = e * cfg.num_minibatches + i
                 if U is not None and U["graphs"]:

@@ -1,6 +1,6 @@
 #!/bin/bash
-# Round-2 GPU pass U: learner input prefetch (oduck_ppo_prefetch): gpu suite, PPO bench fp32 / tf32.
-tag=${1:-r02u}
+# Round-2 GPU pass V: whole-update graph + input prefetch: gpu suite, PPO bench fp32 / tf32.
+tag=${1:-r02v}
 o=gpurun_out
 mkdir -p $o
 timeout 900 python -m pytest tests -m gpu -q -s -rxX > $o/${tag}_pytest_gpu.log 2>&1; echo "pytest exit $?" >> $o/${tag}_pytest_gpu.log; grep -E "passed|failed|pytest exit|FAILED" $o/${tag}_pytest_gpu.log | tail -8
