@@ -616,6 +616,8 @@ def run_rollout(args, rank, world, dev, local):
                     graphs_e2e[(s_, q)].replay()
                     host_out[slot][q * m:(q + 1) * m].copy_(stage[s_][q], non_blocking=True)                              # D2H (pinned)
                     ev_done[slot][q].record()
+            if world > 1 and k % T == T - 1:                             # the same exchange as in the device-timed region, every unroll
+                boundary(False)
             if k > 0:
                 consume(slot ^ 1)
         consume((steps - 1) & 1)
@@ -660,7 +662,8 @@ def run_rollout(args, rank, world, dev, local):
                                            f"{P} streams right after the timed region (the timed steps replay CUDA graphs of the same launches; {P} launches overlap, so each "
                                            "one shares the SMs); kernel_share_of_step = k_step time / (k_step + the five actor kernels) of ONE sub-batch stepping alone on its stream (eager, launch gaps included; compare the serialised ncu launch list in profiles/); actor_ms = the actor kernels in the concurrent pass, queueing behind the other sub-batch's k_step included; kernel_ms_full_batch = one k_step launch over all envs of the rank, alone"},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": n * 2 * 4, "d2h_bytes_per_step": n * (101 + 17) * 4, "steps": e2e_steps,
-                    "note": "host keys H2D + policy + env.step + D2H of obs/raw/logp/reward/done every step, per sub-batch on its stream; the host reads step k-1's result before it issues step k+1"},
+                    "note": "host keys H2D + policy + env.step + D2H of obs/raw/logp/reward/done every step, per sub-batch on its stream; the host reads step k-1's result before it issues step k+1"
+                            + ("; at N > 1 the all-gather of the rollout buffers every 20 steps, as in the device-timed region" if world > 1 else "")},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "physics_substeps_per_s": value * 10,

@@ -306,7 +306,7 @@ __device__ __forceinline__ void branch_elim(float* H, float* rhs, const int lane
     a[i] = (i >= CH_NB && j <= i && col) ? H[TRI(gi) + gj] : 0.f;
   }
   r = (j >= CH_NB && col) ? rhs[gj] : 0.f;
-  // Square-root-free form (measured on B200: +0.5 % env-steps/s over the Cholesky form, profiles/r02c).  The pivot row stays unnormalised (u_kj, u_kk = d_k), so
+  // Square-root-free form (measured on B200: +0.4 % env-steps/s over the Cholesky form, profiles/r02b_bench_n1_ldl.json).  The pivot row stays unnormalised (u_kj, u_kk = d_k), so
   // its hand-over through shared memory no longer waits for the pivot's broadcast and reciprocal root: per pivot the chain
   // SHFL -> RSQ -> MUL -> STS -> LDS -> FMA becomes max(SHFL -> RCP -> MUL, STS -> LDS) -> FMA.  H then holds U with
   // M = U^T D^-1 U and rhs the unscaled sweep r = sqrt(D) y; chol_rev_back reads both forms with the same code

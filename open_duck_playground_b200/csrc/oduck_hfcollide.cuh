@@ -4,7 +4,7 @@
 // looks down onto it is clipped to the triangle's vertical column; clipped points below the triangle plane are candidates
 // (dist along the triangle normal, pos midway, normal = triangle normal); 4 of the candidates within 1 mm of the deepest one
 // are kept by _manifold_points with the mean normal (copies of one point on a shared triangle edge masked first).  Warp mapping:
-// see hf_collide.
+// see hf_collide; the three versions of this collider and their measurements: DESIGN.md 3e.
 #pragma once
 #include "oduck_ffcollide.cuh"
 
@@ -24,18 +24,18 @@ struct DevHF {   // global memory
 #ifndef ODUCK_HF_STAT
 #define ODUCK_HF_STAT(what, n)  // tests/emu counts triangles / pairs / candidates through this hook
 #endif
-#ifdef ODUCK_HF_NO_TWIN
+// clipped points closer than this (max-norm) are copies of one point seen through a neighbouring triangle or face ("twins")
+#ifdef ODUCK_HF_NO_TWIN        // (A/B switch of the oracle and the kernel: no twin masking)
 #define HF_TWIN -1.f
 #else
 #define HF_TWIN 1e-5f
 #endif
-//         // clipped points closer than this (max-norm) are copies of one point on a shared triangle edge
 
 // One Sutherland-Hodgman pass, one polygon per group of G consecutive lanes (G = 8 or 16, lane j of the group holds vertex j in
 // registers): keep the part of the polygon on the inner side (d <= 0) of the vertical plane through r0 with outward normal
-// (sdx, sdy).  Every lane classifies its own vertex and the edge to the next one (shuffle), an exclusive prefix sum over the group
-// (two ballots) gives the output slot of what it emits (the vertex if inside, then the crossing if the edge changes side), the emitted points
-// go through 3 G floats of shared memory and come back as vertex j of the clipped polygon.  The same arithmetic on the same
+// (sdx, sdy).  Every lane classifies its own vertex and the edge to the next one (shuffle), two ballots give it the output slot
+// of what it emits (the vertex if inside, then the crossing if the edge changes side), the emitted points go through 3 G floats
+// of shared memory and come back as vertex j of the clipped polygon.  The same arithmetic on the same
 // points, in the same output order, as the serial loop of oracle/oduck_oracle.cpp hfield_convex; no lane-divergent loop.
 // (The first two versions clipped one polygon per lane serially -- local memory, then shared memory: 13 busy lanes, divergent
 // trip counts, 11 k warp-instructions per foot and substep in the clipping alone, ncu r02e in profiles/.)

@@ -345,3 +345,34 @@ def test_hfield_gpu_env_step_parity(oracle):
         for k in ("command", "motor_targets", "feet_air_time", "last_contact", "push"):
             c.close(sg.info[k], sr.info[k], 1e-5, what=f"[{t}] {k}")
     c.done()
+
+
+@pytest.mark.gpu
+def test_hfield_gpu_env_step_parity_at_scale(oracle):
+    """The same comparison at 2048 envs -- BASELINE configs[3]'s share of one GPU out of eight (16384 envs), 128 CTAs of 16 warps --
+    over reset + 2 control steps, with the flat floor's tight allowance from the 4096-env test (0.4 % of the envs per quantity)
+    doubled for the 2 x 10 manifold selections a height-field step adds; the measured counts are printed."""
+    import torch
+    from test_parity_gpu import Checks, _np, _sync_from_ref
+    n = 2048
+    gpu, ref, sg, sr = _gpu_pair(oracle, n)
+    c = Checks()
+    c.OUTLIER_FRAC = 0.008
+    c.equal(gpu.buffer("INFO_RNG").cpu().numpy(), ref.buffer("INFO_RNG").numpy(), "rng key stream")
+    c.close(sg.data.qpos, sr.data.qpos, 1e-6, what="reset qpos")
+    c.rows(sg.obs["state"], sr.obs["state"], 2e-3, 2e-3, what="reset obs state")
+    rs = np.random.default_rng(3)
+    for t in range(2):
+        act = rs.uniform(-1, 1, (n, gpu.action_size)).astype(np.float32)
+        _sync_from_ref(gpu, ref)
+        sg, sr = gpu.step(sg, torch.from_numpy(act).cuda()), ref.step(sr, torch.from_numpy(act))
+        torch.cuda.synchronize()
+        for name in ("INFO_RNG", "INFO_STEP", "INFO_STEPS"):
+            c.equal(gpu.buffer(name).cpu().numpy(), ref.buffer(name).numpy(), f"[{t}] {name}")
+        c.close(sg.data.qpos, sr.data.qpos, 1e-4, what=f"[{t}] qpos")
+        c.rows(sg.data.qvel, sr.data.qvel, 2e-3, 1e-3, what=f"[{t}] qvel")
+        c.close(sg.reward, sr.reward, 2e-4, what=f"[{t}] reward")
+        c.mostly_equal(_np(sg.done), _np(sr.done), f"[{t}] done")
+        c.rows(sg.obs["privileged_state"], sr.obs["privileged_state"], 2e-3, 2e-3, what=f"[{t}] obs privileged")
+        c.mostly_equal(_np(sg.data.contact_dist) < 0, _np(sr.data.contact_dist) < 0, f"[{t}] active contact set")
+    c.done()
