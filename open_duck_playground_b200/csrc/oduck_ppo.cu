@@ -789,8 +789,13 @@ int oduck_ppo_create(const OduckPpoConfig* cfg, int device, OduckPpo** out) {
       w.wf = poff; poff += (long long)(Npad / nt) * kch * gblk_b(nt);
       w.wb = -1;
       if (l > 0) { w.wb = poff; poff += (long long)ceil_div(K, 128) * ceil_div(N, TC_KC) * GBLK_A; }
-      // dW partials: [nsplit][round_up(K, 128)][Npad]; about 16 splits over the batch chunks
-      const int bch = nb.Mpad / TC_KC, cps = ceil_div(bch, 16);
+      // dW partials: [nsplit][round_up(K, 128)][Npad]; about 8 splits over the batch chunks: fewer splits mean less partial-sum traffic
+      // for the reduce kernel on the critical path, more mean fuller grids for the dW GEMMs beside it.  Measured on B200 (update of
+      // configs[2], two runs each, profiles/r02aa_bench_ppo_*.json): 8 vs 16 splits 26.41 / 26.42 vs 27.25 / 27.29 ms (TF32),
+      // 33.37 / 33.29 vs 33.73 / 33.71 ms (3xTF32); 6 / 10 / 12 splits 27.9 / 28.0 / 27.1 ms (TF32, r02y / r02z).  ODUCK_PPO_SPLITS overrides.
+      int want_splits = 8;
+      { const char* e = getenv("ODUCK_PPO_SPLITS"); if (e && atoi(e) > 0) want_splits = atoi(e); }
+      const int bch = nb.Mpad / TC_KC, cps = ceil_div(bch, want_splits);
       w.nsplit = ceil_div(bch, cps); w.ldo = Npad; w.split_stride = (long long)round_up(K, 128) * Npad;
       w.dwpart = goff; goff += w.split_stride * w.nsplit;
       off += (long long)K * N;
