@@ -990,7 +990,7 @@ int oduck_ppo_prefetch(OduckPpo* h, const OduckRollout* ro, const OduckNormalize
   if (ro->block_envs < 0 || (ro->block_envs > 0 && ro->num_envs % ro->block_envs)) return oduck_fail(ODUCK_ERR_ARG, "oduck_ppo_prefetch: num_envs must be a multiple of block_envs");
   if (ro->obs_policy_ld != 0 && ro->obs_policy_ld < h->net[0].dims[0]) return oduck_fail(ODUCK_ERR_ARG, "oduck_ppo_prefetch: obs_policy_ld smaller than the policy observation");
   PPO_TRY(cudaSetDevice(h->device));
-  cudaStream_t st = (cudaStream_t)stream;
+  (void)stream;                                  // (kept in the signature: the fork point is an event of that stream, see below)
   const int be = ro->block_envs > 0 ? ro->block_envs : ro->num_envs;
   NetBuf& np = h->net[0];
   NetBuf& nv = h->net[1];
@@ -998,7 +998,6 @@ int oduck_ppo_prefetch(OduckPpo* h, const OduckRollout* ro, const OduckNormalize
                                                  // minibatch's layer-0 dW GEMM, is ordered before the current minibatch's start)
   // fork from the START of the current minibatch (recorded by oduck_ppo_minibatch at its FORWARD stage), not from the tail of
   // `stream`: the pack then runs beside the current minibatch's kernels
-  (void)st;
   PPO_TRY(cudaStreamWaitEvent(h->pf_stream, h->ev_mb_start, 0));
   PPO_TRY(launch_kernel(k_ppo_pack, dim3(296), dim3(256), 0, h->pf_stream, false, ro->obs_value, be, (long long)ro->block_stride, nv.dims[0], nv.dims[0], next_env_idx, h->B, nv.M, nv.Mpad,
                         ceil_div(nv.dims[0], TC_KC), nm->value_mean, nm->value_std, h->X0r[1][alt], h->X0t[1][alt]));
