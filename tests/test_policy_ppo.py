@@ -228,3 +228,27 @@ def test_rollout_sink_argument_checks(oracle):
     ppo.attach_rollout_sink(env, None)
     with pytest.raises(Exception, match="no sink attached"):
         ppo.rollout_step(env, w, keys, 0)
+
+
+def test_running_statistics_one_pass_update_equals_the_literal_brax_form():
+    """RunningStats.update takes its two sums out of one fused pass (torch.var_mean); the result must be brax
+    running_statistics.update's -- count += n, mean += sum(x - mean_old) / count, summed_variance += sum((x - mean_old)(x - mean_new)),
+    std = sqrt(summed_variance / count) -- here evaluated literally in float64, over several batches with offsets up to 100 sigma."""
+    from open_duck_playground_b200.ppo import RunningStats
+    torch.manual_seed(0)
+    scale = torch.tensor([1, 2, 0.1, 5, 1, 1, 30.0])
+    shift = torch.tensor([0, 3, -2, 100, 0, 1e-3, -50.0])
+    rs = RunningStats(7, "cpu")
+    cnt, mean, m2 = 0.0, torch.zeros(7, dtype=torch.float64), torch.zeros(7, dtype=torch.float64)
+    for it in range(5):
+        x = torch.randn(5, 600, 7) * scale + shift + 0.1 * it
+        rs.update(x)
+        xd = x.double().reshape(-1, 7)
+        d_old = xd - mean
+        cnt += xd.shape[0]
+        mean = mean + d_old.sum(0) / cnt
+        m2 = m2 + (d_old * (xd - mean)).sum(0)
+    std = torch.sqrt(m2 / cnt)
+    assert float(rs.count) == cnt
+    assert ((rs.mean.double() - mean).abs() / (std + mean.abs())).max().item() < 1e-6
+    assert ((rs.std.double() - std) / std).abs().max().item() < 2e-5
