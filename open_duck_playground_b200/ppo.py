@@ -964,13 +964,13 @@ class PPOTrainer:
                 out = self._roll["gathered"]
             batch = all_gather_rollout(local, self.world, out)
         if ev: ev[2].record()
+        summary = torch.stack([batch["reward"].mean(), batch["done"].mean()])      # enqueued ahead of the update: read after it without another round trip
         m = self.update(batch, sharded=sharded)
         if ev:
             ev[3].record(); torch.cuda.synchronize()
             self.timing = {"rollout_ms": ev[0].elapsed_time(ev[1]), "gather_ms": ev[1].elapsed_time(ev[2]), "update_ms": ev[2].elapsed_time(ev[3])}
         self.env_steps += self.cfg.num_envs * self.cfg.unroll_length
-        m["reward_per_step"] = float(batch["reward"].mean())        # (this rank's shard in sharded mode)
-        m["episode_done_rate"] = float(batch["done"].mean())
+        m["reward_per_step"], m["episode_done_rate"] = summary.tolist()             # (this rank's shard in sharded mode)
         return m
 
     def evaluate(self) -> Dict[str, float]:
