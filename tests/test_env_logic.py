@@ -154,3 +154,22 @@ def test_single_env_headless_loop_config1(oracle):
         st = env.step(st, 0.2 * act)
     assert torch.isfinite(st.obs["privileged_state"]).all() and torch.isfinite(st.data.qpos).all()
     assert abs(float(st.data.qpos[0, 3:7].norm()) - 1) < 1e-9
+
+
+@pytest.mark.parametrize("cls_name", ["Joystick", "Standing"])
+def test_privileged_observation_starts_with_the_policy_observation(oracle, cls_name):
+    """joystick.py:596-615 / standing.py: privileged_state = hstack([state, ...]).  The learner and the multi-GPU exchange rely on it
+    (OduckRollout.obs_policy_ld: the policy rows are read out of the value rows), so it is asserted on reset and on noisy steps."""
+    from open_duck_playground_b200.standing import Standing
+    cls = {"Joystick": Joystick, "Standing": Standing}[cls_name]
+    env = cls("flat_terrain_backlash", library=oracle)
+    assert env.privileged_obs_has_state_prefix
+    n = 6
+    st = env.reset(jr.split(jr.PRNGKey(4), n))
+    ds = env.observation_size["state"][0]
+    assert torch.equal(st.obs["privileged_state"][:, :ds], st.obs["state"])
+    g = torch.Generator().manual_seed(1)
+    for _ in range(3):
+        st = env.step(st, torch.rand(n, env.action_size, generator=g) * 2 - 1)
+        assert torch.equal(st.obs["privileged_state"][:, :ds], st.obs["state"])
+        assert st.obs["state"].abs().max().item() > 0

@@ -252,3 +252,33 @@ def test_running_statistics_one_pass_update_equals_the_literal_brax_form():
     assert float(rs.count) == cnt
     assert ((rs.mean.double() - mean).abs() / (std + mean.abs())).max().item() < 1e-6
     assert ((rs.std.double() - std) / std).abs().max().item() < 2e-5
+
+
+def test_gathered_rollout_without_the_policy_observation():
+    """Host logic of the reduced exchange: when obs["privileged_state"] starts with obs["state"] the rank's flat buffer
+    travels from obs_v on (RolloutBuffers.skip), and the gathered blocks still answer for every field -- obs_p as the leading columns
+    of obs_v -- with the pointers / strides the device learner needs (OduckRollout.block_envs, block_stride, obs_policy_ld)."""
+    from open_duck_playground_b200 import capi
+    from open_duck_playground_b200.ppo import GatheredRollout, RolloutBuffers, rollout_struct
+    T, n, world = 3, 5, 2
+    bufs = [RolloutBuffers(T, n, 101, 212, 14, "cpu") for _ in range(world)]
+    g0 = torch.Generator().manual_seed(3)
+    for b in bufs:
+        b.flat.copy_(torch.randn(b.flat.shape, generator=g0))
+        b["obs_v"][..., :101].copy_(b["obs_p"])
+        b.policy_prefix = True
+    assert bufs[0].skip == (T + 1) * n * 101 and bufs[0].offsets["obs_v"][0] == bufs[0].skip
+    g = GatheredRollout(torch.cat([b.flat[b.skip:] for b in bufs]), bufs[0], world)        # what all_gather_into_tensor leaves behind
+    assert g.block_stride == bufs[0].flat.numel() - bufs[0].skip
+    for k in bufs[0].keys():
+        assert torch.equal(g[k], torch.cat([b[k] for b in bufs], dim=1)), k
+    ro = rollout_struct(g)
+    assert (ro.num_envs, ro.unroll, ro.block_envs, ro.block_stride, ro.obs_policy_ld) == (world * n, T, n, g.block_stride, 212)
+    assert ro.obs_policy == ro.obs_value == g.flat.data_ptr() and ro.raw_action == g.flat.data_ptr() + 4 * (bufs[0].offsets["raw"][0] - bufs[0].skip)
+    # without the prefix property everything travels and the learner gets two dense observation tensors
+    for b in bufs:
+        b.policy_prefix = False
+    g = GatheredRollout(torch.cat([b.flat for b in bufs]), bufs[0], world)
+    ro = rollout_struct(g)
+    assert ro.obs_policy_ld == 0 and ro.obs_policy == g.flat.data_ptr() and ro.obs_value == g.flat.data_ptr() + 4 * bufs[0].offsets["obs_v"][0]
+    assert torch.equal(g["obs_p"], torch.cat([b["obs_p"] for b in bufs], dim=1))
