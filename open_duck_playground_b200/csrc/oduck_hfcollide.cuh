@@ -21,6 +21,7 @@ struct DevHF {   // global memory
                                // fp64 oracle clips to a sliver at |x| ~ 9 m
 #define HF_MAXPAIR 64          // pair list of a batch (the rhs + rowbuf rows of WarpSmem)
 #define HF_NIN 96              // in-threshold candidates the shared-memory selection handles (3 per lane); more: hf_select_generic
+#define HF_MAXTRI 28           // triangle table of a foot in shared memory (12 floats each): 96 + 96 + 28 * 12 = 528 floats = WarpSmem::H
 #ifndef ODUCK_HF_STAT
 #define ODUCK_HF_STAT(what, n)  // tests/emu counts triangles / pairs / candidates through this hook
 #endif
@@ -197,8 +198,11 @@ static __device__ __noinline__ void hf_collide(const DevModel& m, const DevFF* _
   cmin = max(cmin, 0); rmin = max(rmin, 0); cmax = min(cmax, ncol - 2); rmax = min(rmax, nrow - 2);
   float* wv = s.H;                                                       // world hull vertices [32][3]
   float* scr = s.H + 96;                                                 // stage 2: clip scratch, 3 floats per lane; stage 3: compacted points [HF_NIN][3]
+  float4* tri = reinterpret_cast<float4*>(s.H + 192);                    // stages 1 - 2: triangles that own pairs, 3 float4 each: T0 | n.x, T1 | n.y, T2 | n.z
+                                                                         // (at most HF_MAXTRI: the bounding sphere spans 3 x 3 cells; stage 3 reuses the space)
+  int ntri = 0;                                                          // warp-uniform
   int* cidx = reinterpret_cast<int*>(s.H + 96 + 3 * HF_NIN);             // stage 3: list index of compacted candidate i
-  int* wp = reinterpret_cast<int*>(s.rhs);                               // pair list: row << 18 | column << 6 | half << 5 | face (the field has at most 4096 columns)
+  int* wp = reinterpret_cast<int*>(s.rhs);                               // pair list: triangle slot << 5 | face
   float hx0, hx1, hy0, hy1, hz0;                                          // box of the hull
   const bool vv = lane < m.nvert;                                         // lane = hull vertex (world position wl kept for the plane-side cull)
   V3 wl;
@@ -247,16 +251,10 @@ static __device__ __noinline__ void hf_collide(const DevModel& m, const DevFF* _
       const int i = base + gi;
       const bool valid = i < np;
       const int pr = wp[valid ? i : 0];
-      const int qq = pr & 31, half = (pr >> 5) & 1, c = (pr >> 6) & 0xfff, r = pr >> 18;
-      // the triangle, by the expressions of the enumeration below (the same floats)
-      const float x0 = c * dx - sx, x1 = (c + 1) * dx - sx, y0 = r * dy - sy, y1 = (r + 1) * dy - sy;
-      const float h00 = data[(size_t)r * ncol + c] * sz, h01 = data[(size_t)r * ncol + c + 1] * sz;
-      const float h10 = data[(size_t)(r + 1) * ncol + c] * sz, h11 = data[(size_t)(r + 1) * ncol + c + 1] * sz;
-      const V3 T0 = half == 0 ? v3(x0, y1, h10) : v3(x0, y0, h00);
-      const V3 T1 = half == 0 ? v3(x0, y0, h00) : v3(x1, y0, h01);
-      const V3 T2 = v3(x1, y1, h11);
-      V3 n = cross(T1 - T0, T2 - T0);
-      n = (1.f / sqrtf(dot(n, n))) * n;
+      const int qq = pr & 31;
+      // the triangle as the enumeration below computed it (the same floats): three float4 broadcasts
+      const float4 t0 = tri[3 * (pr >> 5)], t1 = tri[3 * (pr >> 5) + 1], t2 = tri[3 * (pr >> 5) + 2];
+      const V3 T0 = v3(t0.x, t0.y, t0.z), T1 = v3(t1.x, t1.y, t1.z), T2 = v3(t2.x, t2.y, t2.z), n = v3(t0.w, t1.w, t2.w);
       int cnt = valid ? ff->plane_nvert[qq] : 0;
       V3 P = v3(0.f, 0.f, 0.f);
       if (j < cnt) { const int vid = ff->plane_vert[qq][j]; P = v3(wv[3 * vid], wv[3 * vid + 1], wv[3 * vid + 2]); }
@@ -308,8 +306,13 @@ static __device__ __noinline__ void hf_collide(const DevModel& m, const DevFF* _
         const bool act = has && (fmask & below) != 0u && dot(Nw, n) < 0.f && !(x1 < gx0 || x0 > gx1 || y1 < gy0 || y0 > gy1);   // the face looks down onto the triangle
         const unsigned bm = __ballot_sync(FULLMASK, act);
         if (!bm) continue;                                              // warp-uniform
-        if (np + __popc(bm) > HF_MAXPAIR) flush();
-        if (act) wp[np + __popc(bm & lt)] = (r << 18) | (c << 6) | (i << 5) | lane;
+        if (np + __popc(bm) > HF_MAXPAIR || ntri == HF_MAXTRI) { flush(); ntri = 0; }
+        if (lane < 3) {
+          const V3 Tl = lane == 0 ? T0 : (lane == 1 ? T1 : T2);
+          tri[3 * ntri + lane] = make_float4(Tl.x, Tl.y, Tl.z, lane == 0 ? n.x : (lane == 1 ? n.y : n.z));
+        }
+        if (act) wp[np + __popc(bm & lt)] = (ntri << 5) | lane;       // pair = (triangle slot, face)
+        ++ntri;
         np += __popc(bm);
         ODUCK_HF_STAT(2, __popc(bm))
       }
