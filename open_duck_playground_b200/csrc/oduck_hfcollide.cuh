@@ -255,6 +255,8 @@ static __device__ __noinline__ void hf_collide(const DevModel& m, const DevFF* _
       // the triangle as the enumeration below computed it (the same floats): three float4 broadcasts
       const float4 t0 = tri[3 * (pr >> 5)], t1 = tri[3 * (pr >> 5) + 1], t2 = tri[3 * (pr >> 5) + 2];
       const V3 T0 = v3(t0.x, t0.y, t0.z), T1 = v3(t1.x, t1.y, t1.z), T2 = v3(t2.x, t2.y, t2.z), n = v3(t0.w, t1.w, t2.w);
+      // (the face's vertex list through two shuffles from lane = face instead of these cached global loads: 2.67 vs 2.71 M
+      // env-steps/s at 16384 envs, profiles/r02ae_bench_rough_*.json -- not taken)
       int cnt = valid ? ff->plane_nvert[qq] : 0;
       V3 P = v3(0.f, 0.f, 0.f);
       if (j < cnt) { const int vid = ff->plane_vert[qq][j]; P = v3(wv[3 * vid], wv[3 * vid + 1], wv[3 * vid + 2]); }
