@@ -282,6 +282,9 @@ static __device__ __noinline__ void hf_collide(const DevModel& m, const DevFF* _
     __syncwarp();
     np = 0;
   };
+  // (lane = triangle for the hull-independent part -- vertices, normal, box / height culls -- and a visit of the survivors through the
+  // table was measured slower than these warp-uniform loops with their early exits: 2.61 vs 2.71 M env-steps/s at 16384 envs,
+  // profiles/r02af_bench_rough_*.json)
   for (int r = rmin; r <= rmax; ++r)
     for (int c = cmin; c <= cmax; ++c) {
       const float x0 = c * dx - sx, x1 = (c + 1) * dx - sx, y0 = r * dy - sy, y1 = (r + 1) * dy - sy;

@@ -1,6 +1,6 @@
 #!/bin/bash
-# Round-2 GPU pass AE: face vertex lists of the HF collider through shuffles: height-field parity tests + rough bench.
-tag=${1:-r02ae}
+# Round-2 GPU pass AF: lane-parallel triangle enumeration in the HF collider: height-field parity tests + rough bench.
+tag=${1:-r02af}
 o=gpurun_out
 mkdir -p $o
 timeout 600 python -m pytest tests/test_hfield.py tests/test_ppo_device.py -m gpu -q 2>&1 | tail -2
