@@ -77,3 +77,64 @@ def test_headless_inference_loop(oracle, tmp_path):
         act, _, _ = ppo.policy_forward(env2, w, None, deterministic=True)
         st = env2.step(st, act)
     assert torch.allclose(env.buffer("QPOS").double(), env2.buffer("QPOS").double(), atol=1e-4)
+
+
+def test_onnx_file_parses_with_the_protobuf_runtime_against_the_onnx_schema(tmp_path):
+    """An INDEPENDENT decoder: Google's protobuf runtime parses the exported bytes against the ONNX schema (tests/onnx_schema.py:
+    the published message names and field numbers), nothing of export_onnx.py's own reader is used.  The parsed model must be a
+    well-formed opset-13 graph (no unknown fields anywhere, every node input defined before use, one input / one output with
+    static shapes), carry the checkpoint's tensors bit for bit, and -- evaluated from the PARSED messages -- reproduce the torch
+    policy."""
+    import onnx_schema
+    M = onnx_schema.onnx_messages()
+    pol, mean, std, params = _checkpoint(3)
+    norm, tree = ex.brax_param_tree(params)
+    path = ex.export_onnx((norm, tree), 14, (512, 256, 128), 101, str(tmp_path / "policy.onnx"))
+    model = M["ModelProto"]()
+    model.ParseFromString(open(path, "rb").read())
+
+    from google.protobuf import unknown_fields
+
+    def no_unknown(msg):                                                  # recursively: every byte was claimed by a declared field
+        assert len(unknown_fields.UnknownFieldSet(msg)) == 0, type(msg).__name__
+        for fd, v in msg.ListFields():
+            if fd.message_type is not None:
+                for sub in (v if (fd.is_repeated if hasattr(fd, "is_repeated") else fd.label == fd.LABEL_REPEATED) else [v]):
+                    no_unknown(sub)
+    no_unknown(model)
+    assert model.SerializeToString() != b"" and model.ir_version == 8 and model.producer_name == "open_duck_playground_b200"
+    assert len(model.opset_import) == 1 and model.opset_import[0].domain == "" and model.opset_import[0].version == 13
+    g = model.graph
+    assert g.name == "open_duck_policy" and len(g.input) == 1 and len(g.output) == 1
+    dims = lambda vi: [d.dim_value for d in vi.type.tensor_type.shape.dim]  # noqa: E731
+    assert g.input[0].name == "obs" and g.input[0].type.tensor_type.elem_type == 1 and dims(g.input[0]) == [1, 101]
+    assert g.output[0].name == "continuous_actions" and g.output[0].type.tensor_type.elem_type == 1 and dims(g.output[0]) == [1, 14]
+    # initializers: float tensors with raw little-endian data of exactly prod(dims) elements, equal to the checkpoint's
+    init = {}
+    for t in g.initializer:
+        assert t.data_type == 1 and len(t.raw_data) == 4 * int(np.prod(list(t.dims))) and not t.float_data
+        init[t.name] = np.frombuffer(t.raw_data, "<f4").reshape(list(t.dims))
+    assert np.array_equal(init["mean"], norm.mean["state"]) and np.array_equal(init["std"], norm.std["state"])
+    for i in range(4):
+        k, b = tree["params"][f"hidden_{i}"]["kernel"], tree["params"][f"hidden_{i}"]["bias"]
+        if i == 3:
+            k, b = k[:, :14], b[:14]                                     # the loc half of the head
+        assert np.array_equal(init[f"hidden_{i}/kernel"], k) and np.array_equal(init[f"hidden_{i}/bias"], b)
+    # nodes: standard-domain ops of opset 13, topologically ordered, unique output names
+    assert [n.op_type for n in g.node] == ["Sub", "Div"] + ["MatMul", "Add", "Sigmoid", "Mul"] * 3 + ["MatMul", "Add", "Tanh"]
+    known, outs = set(init) | {"obs"}, set()
+    for n in g.node:
+        assert n.domain == "" and len(n.attribute) == 0 and all(i in known for i in n.input) and len(n.output) == 1 and n.output[0] not in outs
+        known.add(n.output[0]); outs.add(n.output[0])
+    assert g.output[0].name in outs
+    # evaluate the PARSED graph
+    ops = {"Sub": np.subtract, "Div": np.divide, "MatMul": np.matmul, "Add": np.add, "Mul": np.multiply,
+           "Sigmoid": lambda a: 1.0 / (1.0 + np.exp(-a)), "Tanh": np.tanh}
+    obs = np.random.default_rng(1).normal(0, 1, (1, 101)).astype(np.float32)
+    env = dict(init, obs=obs)
+    for n in g.node:
+        env[n.output[0]] = ops[n.op_type](*[env[i] for i in n.input]).astype(np.float32)
+    with torch.no_grad():
+        ref = torch.tanh(pol((torch.from_numpy(obs) - mean) / std)[:, :14]).numpy()
+    assert np.abs(env["continuous_actions"] - ref).max() < 2e-6
+    assert np.array_equal(env["continuous_actions"], ex.run_onnx(path, obs))      # and the module's own reader agrees with it
