@@ -63,6 +63,25 @@ def _peaks():
     return 6650.0, "fallback", 1965.0
 
 
+def issue_slot_ceiling(task, envs_per_launch, kernel_ms, sm_mhz, n_sm=148, schedulers_per_sm=4):
+    """The bound that binds k_step: warp-instructions one launch executes -- one warp per env, so the
+    committed ncu count per env (profiles/traffic.json: smsp__inst_executed.sum of the --set full capture / its envs) x the envs
+    of the launch -- over the issue slots the GPU offers in the launch's measured duration (n_sm x 4 schedulers x 1 warp-instruction
+    per cycle).  Returns None when no capture of this scene is committed."""
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(tpath) or not kernel_ms or not sm_mhz:
+        return None
+    per_env = json.load(open(tpath)).get("k_step_inst_per_env" if task.startswith("flat") else "k_step_hf_inst_per_env")
+    if not per_env:
+        return None
+    inst = float(per_env) * envs_per_launch
+    slots = n_sm * schedulers_per_sm * sm_mhz * 1e6 * kernel_ms * 1e-3
+    return {"bound": "issue", "achieved": inst / (kernel_ms * 1e-3) / 1e12, "peak": n_sm * schedulers_per_sm * sm_mhz * 1e6 / 1e12, "unit": "T warp-inst/s",
+            "frac": inst / slots, "warp_instructions_per_env_step": float(per_env), "envs_per_launch": envs_per_launch, "kernel_ms": kernel_ms,
+            "note": "instruction count from the committed ncu --set full capture (static), duration and SM clock measured in this run; "
+                    "the launch timed alone over all envs of the rank (kernel_ms_full_batch)"}
+
+
 def n_env_sets(n, bytes_per_env=STATE_BYTES_PER_ENV):
     """Env sets rotated step by step so that the working set exceeds L2 (timing rule: inputs larger than L2)."""
     return max(3, int(np.ceil(1.3 * L2_BYTES / (n * bytes_per_env))))
@@ -658,6 +677,7 @@ def run_rollout(args, rank, world, dev, local):
                          "kernel_share_of_step": ms_kstep_alone / (ms_kstep_alone + ms_actor_alone), "kernel_ms_alone": ms_kstep_alone, "actor_ms_alone": ms_actor_alone, "actor_ms": ms_actor,
                          "kernel_ms_full_batch": ms_kstep_full, "achieved_full_batch": BYTES_PER_ENV_STEP * n / (ms_kstep_full * 1e-3) / 1e9,
                          "step_achieved": BYTES_PER_ENV_STEP * n / (ms_step * 1e-3) / 1e9,
+                         "issue": issue_slot_ceiling(TASK, n, ms_kstep_full, clocks.get("sm_mhz") or sm_max),
                          "kernel_ms_note": f"kernel_ms = average k_step launch duration ({m} envs per launch) from CUDA events around every launch of an eager pass with the same "
                                            f"{P} streams right after the timed region (the timed steps replay CUDA graphs of the same launches; {P} launches overlap, so each "
                                            "one shares the SMs); kernel_share_of_step = k_step time / (k_step + the five actor kernels) of ONE sub-batch stepping alone on its stream (eager, launch gaps included; compare the serialised ncu launch list in profiles/); actor_ms = the actor kernels in the concurrent pass, queueing behind the other sub-batch's k_step included; kernel_ms_full_batch = one k_step launch over all envs of the rank, alone"},

@@ -1,12 +1,13 @@
 """PPO rollout + update around the fused env step (reference: Brax ``ppo.train`` as driven by common/runner.py:86-118).
 
-The hot path -- policy forward (``oduck_policy_forward``) and ``env.step`` -- runs in the CUDA library; the update (GAE,
-clipped surrogate, Adam, observation normaliser) is host-orchestrated PyTorch like the reference's is host-orchestrated
-JAX.  Hyper-parameters default to ``locomotion_params.brax_ppo_config("BerkeleyHumanoidJoystickFlatTerrain")`` -- the table
+The hot path -- policy forward (``oduck_policy_forward``) and ``env.step``, fused as ``oduck_rollout_step`` -- runs in the CUDA
+library, and so does the update (``DeviceLearner`` over include/oduck_ppo.h: GAE, clipped surrogate, backward, clip + Adam);
+the PyTorch fp32 twin of the update in this file is its checker and the CPU path of the tests.  Hyper-parameters default to ``locomotion_params.brax_ppo_config("BerkeleyHumanoidJoystickFlatTerrain")`` -- the table
 the reference looks up at common/runner.py:87-89 (values: SURVEY.md 3.1).
 
-Multi-GPU: ranks own disjoint env shards; one ``all_gather`` of the rollout per training step over NCCL,
-then a replicated (bit-identical) update.
+Multi-GPU: ranks own disjoint env shards; ``update_mode = "replicated"``: one ``all_gather`` of the rollout per
+training step over NCCL, then the same update on every rank; ``"sharded"`` (the CUDA default): every rank updates on its own
+shard and the flat gradient is all-reduced per minibatch inside the captured update graph (Brax's pmean).
 """
 from __future__ import annotations
 
@@ -1022,6 +1023,7 @@ class PPOTrainer:
             [e.handle.policy_invalidate() for e in self._envs]
         else:
             self.opt.load_state_dict(params["optimizer"])
+            self._g_fb = self._g_step = None                  # load_state_dict REPLACES the Adam state tensors a captured step updates by address: capture again on the next update
         for k, s in self.stats.items():
             d = params["normalizer"][k]
             s.mean = d["mean"].float().to(self.env.device); s.std.copy_(d["std"].to(self.env.device)); s.count = torch.tensor(float(d["count"]), device=self.env.device)
