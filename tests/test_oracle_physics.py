@@ -165,6 +165,101 @@ def test_standing_equilibrium_and_sensors(oracle, model_backlash, poly_table):
     assert 0.12 < q[2] < 0.2 and abs(np.linalg.norm(q[3:7]) - 1) < 1e-12
 
 
+def _make_frame(n):
+    """MJX math.make_frame: tangent from the y axis unless the normal is close to it, then from z."""
+    a = n / np.linalg.norm(n)
+    b0 = np.array([0.0, 1.0, 0.0]) if -0.5 < a[1] < 0.5 else np.array([0.0, 0.0, 1.0])
+    b = b0 - a * (a @ b0)
+    b /= np.linalg.norm(b)
+    return np.stack([a, b, np.cross(a, b)])
+
+
+def test_newton_gradient_and_hessian_from_independent_contact_jacobians(oracle, model_backlash, poly_table):
+    """The Newton solver's gradient, search direction and Hessian (constraint.py / solver.py: grad = M qacc - qfrc_smooth - J^T f,
+    H = M + J_active^T D J_active, search = -H^-1 grad) rebuilt outside the oracle: constraint rows J from mjcf.body_jacobians (point Jacobian of the foot
+    body at the contact position = COM Jacobian + rotational Jacobian x lever arm; the oracle builds them from cdof about the
+    subtree COM), pyramid edges n +- mu t from the contact normal, unit rows for dry friction and joint limits; only the
+    per-row regularisation D and reference acceleration aref are taken from the oracle's dump.  A settled stance with both feet
+    down, one knee pushed to its limit so that a limit row is live."""
+    m = model_backlash
+    A = m.arrays
+    h = make_handle(oracle, m, poly_table, 1)
+    h.physics_substeps(0, 400)
+    q = h.buffer_numpy("QPOS").copy(); v = h.buffer_numpy("QVEL").copy()
+    lim_j = next(j for j in range(m.njnt) if A["jnt_limited"][j] and A["jnt_type"][j] != mjcf.JNT_FREE)
+    q[0, A["jnt_qposadr"][lim_j]] = A["jnt_range"][lim_j][1] + 0.02            # 0.02 rad beyond the upper limit
+    qf, vf = q.astype(np.float32), (v + 0.05).astype(np.float32)             # some velocity everywhere: the friction rows leave zero
+    h.set_state(qf.ctypes.data, vf.ctypes.data, 0)
+    warm = h.buffer_numpy("QACC_WARM")[0].copy()
+    d = _dump(oracle, h)[0]
+    nv = m.nv
+    M = d[:1024].reshape(32, 32)[:nv, :nv]
+    qfrc_smooth, qacc_smooth = d[1056:1056 + nv], d[1088:1088 + nv]
+    start = warm[:nv] if d[2536] < d[2537] else qacc_smooth                  # solver.py: the cheaper of warm start and qacc_smooth
+    _, xmat, xipos, jacp, jacr = mjcf.body_jacobians(m, qf[0, : m.nq].astype(np.float64))
+    rows = []                                                                # (J, D, aref, kind, floss)
+    for dof in range(nv):
+        if A["dof_frictionloss"][dof] > 0:
+            e = np.zeros(nv); e[dof] = 1
+            rows.append((e, d[1184 + dof], d[1264 + dof], "friction", float(A["dof_frictionloss"][dof])))
+    n_lim = 0
+    for j in range(m.njnt):
+        if not A["jnt_limited"][j] or A["jnt_type"][j] == mjcf.JNT_FREE:
+            continue
+        dof, x = A["jnt_dofadr"][j], float(qf[0, A["jnt_qposadr"][j]])
+        lo, hi = x - A["jnt_range"][j][0], A["jnt_range"][j][1] - x
+        if min(lo, hi) < 0:
+            e = np.zeros(nv); e[dof] = 1.0 if lo < hi else -1.0
+            rows.append((e, d[1216 + dof], d[1296 + dof], "limit", 0.0)); n_lim += 1
+    assert n_lim >= 1
+    n_con = 0
+    for c in range(8):
+        if not d[1120 + c] < 0:
+            continue
+        n_con += 1
+        b = int(A["foot_body"][c // 4])
+        pos, frame = d[1136 + 3 * c: 1139 + 3 * c], _make_frame(d[2560 + 3 * c: 2563 + 3 * c])
+        lever = pos - xipos[b]
+        jp = jacp[b] + np.stack([np.cross(jacr[b][:, k], lever) for k in range(nv)], axis=1)      # floor = world: body1 adds nothing
+        jf = frame @ jp
+        mu = float(A["floor_friction"])
+        for e4 in range(4):
+            rows.append((jf[0] + (1 if e4 % 2 == 0 else -1) * mu * jf[1 + e4 // 2], d[1248 + c], d[1328 + 4 * c + e4], "contact", 0.0))
+    assert n_con >= 6
+    def assemble(qacc):
+        H, f_total, n_active = M.copy(), np.zeros(nv), 0
+        for J, D, aref, kind, floss in rows:
+            x = J @ qacc - aref
+            if kind == "friction":
+                rf = floss / D
+                if x <= -rf:
+                    f = floss
+                elif x >= rf:
+                    f = -floss
+                else:
+                    f = -D * x
+                    H += D * np.outer(J, J)
+            else:
+                f = -D * x if x < 0 else 0.0
+                if x < 0:
+                    H += D * np.outer(J, J)
+                    n_active += 1
+            f_total += J * f
+        return H, M @ qacc - qfrc_smooth - f_total, n_active
+
+    H0, grad0, n_active = assemble(start)
+    assert n_active >= 4
+    g_or, search_or = d[1408:1408 + nv], d[1376:1376 + nv]
+    assert np.abs(grad0 - g_or).max() < 1e-9 * max(1.0, np.abs(g_or).max()), (np.abs(grad0 - g_or).max(), np.abs(g_or).max())
+    # the search direction the solver takes from there is the Newton step of the independently assembled system
+    assert np.abs(np.linalg.solve(H0, -grad0) - search_or).max() < 1e-7 * max(1.0, np.abs(search_or).max())
+    # the dumped Hessian is the one at the END of the iteration (active set of the new qacc)
+    H1, _, _ = assemble(d[1736:1736 + nv])
+    H_or = d[4096:4096 + 1024].reshape(32, 32)[:nv, :nv]
+    assert np.abs(H_or - M).max() > 1.0                                        # the constraint part dominates: not a test of M again
+    assert np.abs(H1 - H_or).max() < 1e-9 * np.abs(H_or).max(), np.abs(H1 - H_or).max() / np.abs(H_or).max()
+
+
 def test_joint_limit_pushes_back(oracle, model_backlash, poly_table):
     m = copy.deepcopy(model_backlash)
     m.arrays["act_kp"][:] = 0
