@@ -27,6 +27,9 @@ def main():
     ap.add_argument("--num_eval_envs", type=int, default=64)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r02_cpu_learning_curve.json"))
+    ap.add_argument("--save_prefix", default=None, help="write <prefix>.pt (trainer.params()) and <prefix>.onnx (deterministic policy, "
+                                                        "common/runner.py:68-84) at the end, then run the ONNX file headless (infer.run_policy) and record it")
+    ap.add_argument("--infer_steps", type=int, default=1000)
     args = ap.parse_args()
 
     import torch
@@ -51,7 +54,24 @@ def main():
                        "command": " ".join(sys.argv), "config": {k: (list(v) if isinstance(v, tuple) else v) for k, v in cfg.__dict__.items()}, "curve": curve}, f, indent=1)
 
     tr = ppo.PPOTrainer(env, cfg, progress_fn=progress)
-    tr.train()
+    params = tr.train()
+    if args.save_prefix:
+        # checkpoint -> deployment format -> sim-to-sim, the reference's own validation chain (common/runner.py:68-84, mujoco_infer.py)
+        from open_duck_playground_b200 import infer
+        from open_duck_playground_b200.export_onnx import brax_param_tree, export_onnx
+        torch.save(params, args.save_prefix + ".pt")
+        hidden = list(cfg.policy_hidden_layer_sizes)
+        export_onnx(brax_param_tree(params, "state"), env.action_size, hidden, int(env.observation_size["state"][0]), output_path=args.save_prefix + ".onnx")
+        sim = {}
+        for name, command in (("forward_0.1", [0.1, 0, 0, 0, 0, 0, 0]), ("stand", [0, 0, 0, 0, 0, 0, 0])):
+            e2 = Joystick(args.task, library=oracle_lib.load(f32=True, native=True))
+            sim[name] = infer.run_policy(e2, args.save_prefix + ".onnx", steps=args.infer_steps, seed=3, command=command, num_envs=8)
+            print("sim2sim", name, json.dumps(sim[name]), flush=True)
+        d = json.load(open(args.out))
+        d["onnx_sim2sim"] = {"what": f"{args.save_prefix}.onnx (deterministic policy of the last checkpoint) evaluated with NumPy, 8 envs x {args.infer_steps} control steps "
+                                     "under a fixed command (infer.run_policy; episode_ends counts falls + the 1000-step truncations)", **sim}
+        with open(args.out, "w") as f:
+            json.dump(d, f, indent=1)
 
 
 if __name__ == "__main__":
