@@ -17,7 +17,7 @@ from __future__ import annotations
 
 import struct
 from types import SimpleNamespace
-from typing import Dict, List, Sequence, Tuple
+from typing import Dict, Sequence, Tuple
 
 import numpy as np
 

@@ -17,7 +17,6 @@ All tensors in a ``State`` are zero-copy views of library-owned device buffers: 
 from __future__ import annotations
 
 import copy
-import os
 from dataclasses import dataclass, field
 from typing import Any, Dict, Optional, Union
 

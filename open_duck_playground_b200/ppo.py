@@ -12,12 +12,10 @@ shard and the flat gradient is all-reduced per minibatch inside the captured upd
 from __future__ import annotations
 
 import copy
-import ctypes as C
 import math
-from dataclasses import dataclass, field
-from typing import Callable, Dict, Optional, Tuple
-
 import os
+from dataclasses import dataclass
+from typing import Callable, Dict, Optional, Tuple
 
 import numpy as np
 import torch
@@ -196,12 +194,12 @@ def attach_rollout_sink(env, buf: Optional[Dict[str, torch.Tensor]], env_offset:
     sk = capi.OduckRolloutSink()
     sk.unroll, sk.num_envs, sk.env_offset = int(T), int(n), int(env_offset)
     sk.policy_dim, sk.value_dim = int(buf["obs_p"].shape[-1]), int(buf["obs_v"].shape[-1])
-    for field, key in (("obs_policy", "obs_p"), ("obs_value", "obs_v"), ("raw_action", "raw"), ("log_prob", "logp"), ("reward", "reward"),
-                       ("done", "done"), ("truncation", "trunc")):
+    for attr, key in (("obs_policy", "obs_p"), ("obs_value", "obs_v"), ("raw_action", "raw"), ("log_prob", "logp"), ("reward", "reward"),
+                      ("done", "done"), ("truncation", "trunc")):
         t = buf[key]
         if not t.is_contiguous() or t.dtype != torch.float32 or t.device != env.device:
             raise ValueError(f"rollout buffer {key} must be a contiguous float32 tensor on {env.device}")
-        setattr(sk, field, t.data_ptr())
+        setattr(sk, attr, t.data_ptr())
     env.handle.set_rollout_sink(sk)
     env._sink_keep = (sk, buf)               # the library holds raw pointers: keep the tensors alive with the env
 
