@@ -794,7 +794,7 @@ def main():
                 line[f"{key}_env_steps_per_s"] = leg.get("value")
                 line[f"{key}_leg"] = leg
     if rank == 0 and not args.no_cpu_baseline and world == 1:
-        r = cpu_reference(args.envs_per_gpu, 10, 1)
+        r = cpu_reference(args.envs_per_gpu, 150, 2)                      # ~11 s of CPU work on 16 host cores (the tier's 10 - 30 s sample)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
     finish(line)
 
