@@ -42,6 +42,9 @@ class PPOConfig:
     normalize_observations: bool = True
     episode_length: int = 1000
     num_evals: int = 15
+    num_resets_per_eval: int = 1    # Brax ppo.train: training epochs per evaluation, each followed by a hard reset of every training env with
+                                    # fresh keys (the AutoReset wrapper only ever returns an env to the first state of its LAST hard reset);
+                                    # 0 = one epoch per evaluation and no hard resets (Brax's default; the reference's table says 1)
     num_eval_envs: int = 128        # Brax ppo.train default: evaluation episodes run on their own envs (rank 0); 0 = estimate from the rollout
     deterministic_eval: bool = False   # Brax default: the evaluator samples actions like the behaviour policy
     policy_hidden_layer_sizes: Tuple[int, ...] = (512, 256, 128)
@@ -982,22 +985,54 @@ class PPOTrainer:
         self.weights.refresh(mean, std)
         return self.evaluator.run(self.weights)
 
+    def reset_training_envs(self) -> None:
+        """Hard reset of every training env with fresh keys (Brax ppo.train: ``env_state = reset_fn(key_envs)`` after each training
+        epoch when num_resets_per_eval > 0).  Keys are split(seed', world * n) sliced per rank: independent of the GPU count."""
+        self._hard_resets = getattr(self, "_hard_resets", 0) + 1
+        rk = shard_keys(self.cfg.seed + 7919 * self._hard_resets, self.world, self.rank, self.n_local)
+        if self.P == 1:
+            self.state = self.env.reset(rk)
+        else:
+            m = self.n_local // self.P
+            for q, e in enumerate(self._envs):
+                self.state[q] = e.reset(rk[q * m:(q + 1) * m])
+
     def train(self):
+        """Brax ``ppo.train``'s outer loop: an evaluation of the initial policy (num_evals > 1), then ``num_evals - 1`` iterations of
+        [max(num_resets_per_eval, 1) training epochs, each ending in a hard env reset if num_resets_per_eval > 0] + evaluation +
+        ``progress_fn`` / ``policy_params_fn`` (rank 0).  An epoch is ceil(num_timesteps / (iterations x epochs x env-steps per
+        training step)) training steps, so at least ``num_timesteps`` env-steps are run, like Brax."""
         cfg = self.cfg
-        n_steps = max(1, cfg.num_timesteps // (cfg.num_envs * cfg.unroll_length))
-        eval_every = max(1, n_steps // max(1, cfg.num_evals))
-        for it in range(n_steps):
-            m = self.training_step()
-            if self.rank == 0 and (it % eval_every == 0 or it == n_steps - 1):
-                if self.evaluator is not None:
-                    ev = self.evaluate()
-                else:                                        # no eval envs: extrapolate the behaviour policy's mean step reward
-                    ev = {"eval/episode_reward": m["reward_per_step"] * cfg.episode_length, "eval/episode_reward_std": 0.0}
-                metrics = {**ev, **{f"training/{k}": v for k, v in m.items()}, **{f"time/{k}": v for k, v in self.timing.items()}}
-                if self.progress_fn:
-                    self.progress_fn(self.env_steps, metrics)
-                if self.policy_params_fn:
-                    self.policy_params_fn(self.env_steps, None, self.params())
+        per_step = cfg.num_envs * cfg.unroll_length
+        iters, epochs = max(cfg.num_evals - 1, 1), max(cfg.num_resets_per_eval, 1)
+        steps_per_epoch = max(1, -(-cfg.num_timesteps // (iters * epochs * per_step)))
+
+        def report(m):
+            if self.rank != 0:
+                return
+            if self.evaluator is not None:
+                ev = self.evaluate()
+            elif m is not None:                              # no eval envs: extrapolate the behaviour policy's mean step reward
+                ev = {"eval/episode_reward": m["reward_per_step"] * cfg.episode_length, "eval/episode_reward_std": 0.0}
+            else:
+                return
+            metrics = dict(ev)
+            if m is not None:
+                metrics.update({f"training/{k}": v for k, v in m.items()}, **{f"time/{k}": v for k, v in self.timing.items()})
+            if self.progress_fn:
+                self.progress_fn(self.env_steps, metrics)
+            if m is not None and self.policy_params_fn:
+                self.policy_params_fn(self.env_steps, None, self.params())
+
+        if cfg.num_evals > 1:
+            report(None)                                     # the initial policy (Brax: progress_fn(0, metrics))
+        for _ in range(iters):
+            for _ in range(epochs):
+                for _ in range(steps_per_epoch):
+                    m = self.training_step()
+                if cfg.num_resets_per_eval > 0:
+                    self.reset_training_envs()
+            report(m)
         return self.params()
 
     def params(self):

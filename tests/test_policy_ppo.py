@@ -112,6 +112,39 @@ def test_evaluator_reports_first_episode_sums(oracle):
     assert m and "eval/episode_reward" in m[-1] and "training/loss" in m[-1] and "eval/avg_episode_length" in m[-1]
 
 
+def test_train_loop_follows_brax_outer_loop(oracle):
+    """Brax ppo.train: evaluation of the initial policy at step 0, then num_evals - 1 iterations of num_resets_per_eval epochs (each
+    ended by a hard reset of every training env with fresh keys) + evaluation + progress_fn + policy_params_fn; an epoch is
+    ceil(num_timesteps / (iterations x epochs x env-steps per training step)) training steps."""
+    def run(resets, pipeline=1):
+        cfg = ppo.PPOConfig(num_envs=8, unroll_length=8, num_minibatches=2, num_updates_per_batch=1, num_eval_envs=2, episode_length=5, num_evals=3,
+                            num_resets_per_eval=resets, num_timesteps=8 * 8 * 7, rollout_pipeline=pipeline)
+        prog, saved, hard = [], [], []
+        tr = ppo.PPOTrainer(Joystick("flat_terrain_backlash", library=oracle), cfg, progress_fn=lambda s, m: prog.append((s, set(m))),
+                            policy_params_fn=lambda s, mk, p: saved.append((s, p["env_steps"])))
+        orig = tr.reset_training_envs
+        tr.reset_training_envs = lambda: (hard.append(tr.env_steps), orig())[1]
+        tr.train()
+        return tr, prog, saved, hard
+    # 2 iterations x 2 epochs x ceil(448 / (2 x 2 x 64)) = 2 training steps each: 8 training steps = 512 >= 448 env-steps
+    tr, prog, saved, hard = run(2)
+    assert [s for s, _ in prog] == [0, 256, 512] and tr.env_steps == 512
+    assert not any(k.startswith("training/") for k in prog[0][1]) and "eval/episode_reward" in prog[0][1]      # initial policy: evaluation only
+    assert {"training/loss", "time/rollout_ms", "eval/avg_episode_length"} <= prog[1][1]
+    assert saved == [(256, 256), (512, 512)]
+    assert hard == [128, 256, 384, 512]                                    # after every epoch
+    st = tr.state
+    assert int(st.info["step"].max()) == 0 and float(st.done.max()) == 0.0    # the training envs are freshly reset at the end
+    # num_resets_per_eval = 0: one epoch per evaluation, no hard resets (Brax's default)
+    tr0, prog0, _, hard0 = run(0)
+    assert [s for s, _ in prog0] == [0, 256, 512] and hard0 == [] and int(tr0.state.info["step"].max()) > 0
+    # the sub-batch pipeline resets every sub-env, with the same keys as the single batch
+    trp, _, _, hardp = run(2, pipeline=2)
+    assert hardp == hard
+    q = torch.cat([s_.data.qpos for s_ in trp.state])
+    assert torch.equal(q, tr.state.data.qpos)
+
+
 def test_pipelined_rollout_equals_plain_rollout(oracle):
     """PPOConfig.rollout_pipeline = P: the rank's envs as P sub-batches with their own handles.  Envs are independent
     and the keys are sliced, so transitions and the parameters after a training step equal the single-batch trainer's bit for bit."""

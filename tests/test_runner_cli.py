@@ -32,7 +32,7 @@ def test_cli_trains_checkpoints_and_resumes(cpu_runner, tmp_path, monkeypatch, c
     monkeypatch.setattr(sys, "argv", argv)
     cpu_runner.main()
     text = capsys.readouterr().out
-    assert "Observation size: " + ("101" if env_name == "joystick" else "85") in text and "STEP: 64 reward:" in text and "Saving checkpoint (step: 192)" in text
+    assert "Observation size: " + ("101" if env_name == "joystick" else "85") in text and "STEP: 0 reward:" in text and "STEP: 192 reward:" in text and "Saving checkpoint (step: 192)" in text
     pts, onnxs = sorted(glob.glob(str(out / "*.pt"))), sorted(glob.glob(str(out / "*.onnx")))
     assert len(pts) >= 1 and len(onnxs) == len(pts)                          # one ONNX next to every checkpoint (common/runner.py:76-84)
     ck = torch.load(pts[-1], weights_only=False)
@@ -53,7 +53,8 @@ def test_cli_trains_checkpoints_and_resumes(cpu_runner, tmp_path, monkeypatch, c
     monkeypatch.setattr(ppo.PPOTrainer, "load", spy)
     cpu_runner.main()
     assert seen == {"env_steps": 192, "same": True}
-    assert "STEP: 256 reward:" in capsys.readouterr().out                      # 192 restored + one more training step of 8 x 8
+    text = capsys.readouterr().out
+    assert "STEP: 192 reward:" in text and "STEP: 384 reward:" in text           # evaluation of the restored policy, then 3 more training steps of 8 x 8
 
 
 def test_cli_rejects_an_unknown_env(cpu_runner, tmp_path, monkeypatch):
