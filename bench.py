@@ -13,7 +13,7 @@ domain randomisation on, no PPO update.  Envs are independent, so ranks take dis
 fixed).  At N > 1 every 20th step ends with north_star's one exchange, INSIDE the timed region: a single NCCL all-gather of the
 rollout buffers (``--gather sliced`` issues it slice by slice behind the steps instead -- measured slower).
 
-The rank's envs run as P sub-batches (``--pipeline``, default 4), each with its own library handle, CUDA-graph chain and stream:
+The rank's envs run as P sub-batches (``--pipeline``, default 2), each with its own library handle, CUDA-graph chain and stream:
 4096 envs are 1.73 waves of ``k_step`` and a latency-bound wave costs the same full or not, so sub-batch q + 1's step k fills the
 SM slots under the tail of sub-batch q's (same per-env results: envs are independent, keys are sliced).  The streams join at
 every unroll boundary (where a PPO update would sit) and at the end of the timed region.
@@ -21,8 +21,8 @@ every unroll boundary (where a PPO update would sit) and at the end of the timed
 ``value``  : keys already resident in HBM, K steps timed with CUDA events, max over ranks.
 ``e2e``    : the same step through the C-ABI with HOST buffers: pinned keys H2D, actor + env.step, D2H of obs["state"], raw
              action, log-prob, reward and done every step -- copies inside the timed region, the host reads every step's result.
-``roofline``: HBM roofline the metric asks for (algorithmic 3400 B / env-step) plus the fp32 fraction that
-             actually binds.
+``roofline``: HBM roofline the metric asks for (algorithmic 3400 B / env-step) plus the fp32 fraction and the
+             issue-slot fraction (``issue``: the ceiling that actually binds).
 ``cpu_baseline`` / ``--impl reference``: the reference's CPU path.  ``mujoco.mj_step`` when a MuJoCo install is reachable
              (oracle/mujoco_ref.py: kind "reference"); otherwise -- this image has none -- the C++ oracle port (fp32,
              -O3 -march=native, std::thread over envs: kind "port") on this box's host cores, at the FULL config (4096 envs
